@@ -1,0 +1,160 @@
+/*
+ * orb_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE ONLY).
+ *
+ * A plain scalar C++ restatement of the reference front-end hot path
+ *   R21 = /root/reference/ORB_SLAM2.1
+ *   R21/src/ORBextractor.cc  (pyramid, cell FAST, quadtree, IC_Angle, blur, rBRIEF)
+ *   R21/src/ORBmatcher.cc    (DescriptorDistance, SearchByBoW x2, SearchForTriangulation)
+ *   R21/src/Frame.cc:471-645 (ComputeStereoMatches)
+ * plus integer models of the OpenCV primitives those files call (resize,
+ * copyMakeBorder, GaussianBlur, FAST, fastAtan2), pinned against cv2 4.13.0.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may link or call this.  The product (liborbcuda.so) never does.
+ *
+ * PARITY PINNING: the reference ships no tests / golden vectors.
+ * This oracle is pinned two ways: (1) every primitive is checked bit-for-bit against
+ * cv2 4.13.0 (tests/test_oracle_primitives.py + tests/golden/), (2) the whole
+ * extractor is checked bit-for-bit against the reference's own ORBextractor.cc
+ * compiled verbatim over oracle/cvshim (oracle/_ref/liborbref.so, built by
+ * oracle/Makefile; tests/test_oracle_vs_ref.py).  The matcher loops cannot be
+ * compiled from the reference (they need Frame/KeyFrame/MapPoint/DBoW2), so the
+ * matcher restatement is "parity unpinned" beyond DescriptorDistance KATs.
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same 28-byte layout as cv::KeyPoint. */
+typedef struct {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} orc_keypoint;
+
+/* ---- OpenCV primitive models ---- */
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, size_t sstride,
+                          uint8_t* dst, int dw, int dh, size_t dstride);
+void orc_copy_make_border_reflect101(const uint8_t* src, int w, int h, size_t sstride,
+                                     uint8_t* dst, size_t dstride, int top, int bottom,
+                                     int left, int right);
+void orc_gaussian_blur7_sigma2(const uint8_t* src, int w, int h, size_t sstride,
+                               uint8_t* dst, size_t dstride);
+/* cv::FAST(img, kps, th, nms) TYPE_9_16. Returns the number found (writes at most cap). */
+int orc_fast9_16(const uint8_t* img, int w, int h, size_t stride, int threshold, int nms,
+                 orc_keypoint* out, int cap);
+/* FAST corner score of one pixel (0 if not a corner at `threshold`). */
+int orc_fast_score(const uint8_t* center, size_t stride, int threshold);
+float orc_fast_atan2(float y, float x);
+int orc_cv_round_f(float v);
+
+/* ---- extractor (R21/src/ORBextractor.cc) ---- */
+typedef struct orc_extractor orc_extractor;
+
+/* trig_mode 0: a=cosf(angle), b=sinf(angle) exactly as the reference (libm, :113-114).
+ * trig_mode 1: correctly rounded a=(float)cos((double)angle) (what the CUDA path uses).
+ * fma_mode  0: separate fp32 mul,mul,add in the rotation (canonical, -ffp-contract=off).
+ * fma_mode  1: fma(x,b, y*a) / fma(x,a, -(y*b)) -- what g++ -O3 -march=native makes of
+ *              :119-120 on an FMA host. */
+orc_extractor* orc_extractor_create(int nfeatures, float scale_factor, int nlevels,
+                                    int ini_th_fast, int min_th_fast, int trig_mode,
+                                    int fma_mode);
+void orc_extractor_destroy(orc_extractor* e);
+/* mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2, mnFeaturesPerLevel (:415-446) */
+void orc_extractor_tables(const orc_extractor* e, float* sf, float* isf, float* s2, float* is2,
+                          int* nfeat_per_level, int* umax16);
+/* operator() (:1043-1105). Returns 0 on success; *n = number of keypoints (<= cap written). */
+int orc_extract(orc_extractor* e, const uint8_t* img, int w, int h, size_t stride,
+                orc_keypoint* kps, uint8_t* desc, int cap, int* n);
+/* stage dumps of the last orc_extract call */
+int orc_level_size(const orc_extractor* e, int level, int* w, int* h);
+/* with_border: copies (w+38)x(h+38) padded plane, else the w x h ROI */
+int orc_get_pyramid(const orc_extractor* e, int level, int with_border, uint8_t* dst, size_t dstride);
+int orc_get_blurred(const orc_extractor* e, int level, uint8_t* dst, size_t dstride);
+/* FAST candidates handed to DistributeOctTree (cell-major order, coords relative to (16,16)) */
+int orc_get_candidates(const orc_extractor* e, int level, int16_t* x, int16_t* y, uint8_t* score, int cap);
+/* keypoints per level after octree + orientation (level coords, before the final scale) */
+int orc_get_level_keypoints(const orc_extractor* e, int level, orc_keypoint* out, int cap);
+/* Stand-alone DistributeOctTree (:539-763) on caller-provided candidates. */
+int orc_distribute_octtree(const int16_t* x, const int16_t* y, const uint8_t* score, int n,
+                           int min_x, int max_x, int min_y, int max_y, int n_features,
+                           int32_t* out_index, int cap);
+/* IC_Angle (:77-104) on a padded plane: center points at pixel (x,y). */
+float orc_ic_angle(const uint8_t* center, size_t stride);
+/* computeOrbDescriptor (:108-147) */
+void orc_orb_descriptor(const uint8_t* center, size_t stride, float angle_deg, int trig_mode,
+                        int fma_mode, uint8_t* desc32);
+
+/* ---- matcher (R21/src/ORBmatcher.cc) ---- */
+int orc_descriptor_distance(const uint8_t* a, const uint8_t* b); /* :1647-1663 */
+
+/* Brute-force 2-NN with the reference update rule (:216-225): for each query the best
+ * (first index on ties), its distance and the second-best distance; both start at 256. */
+void orc_knn2(const uint8_t* q, int nq, const uint8_t* m, int64_t nm, int64_t index_base,
+              int32_t* best_idx, int32_t* best_d1, int32_t* best_d2, int nthreads);
+/* Like orc_knn2 but also reports the index of the second best (lexicographic (d,idx) order);
+ * used to check the sharded merge. */
+void orc_knn2_full(const uint8_t* q, int nq, const uint8_t* m, int64_t nm, int64_t index_base,
+                   int32_t* i1, int32_t* d1, int32_t* i2, int32_t* d2, int nthreads);
+
+/* FeatureVector as CSR: node_ids ascending; node i owns idx[ptr[i]..ptr[i+1]) */
+typedef struct {
+    int32_t n_nodes;
+    const int32_t* node_ids;
+    const int32_t* ptr;
+    const int32_t* idx;
+} orc_featvec;
+
+/* SearchByBoW(KeyFrame*,Frame&,...) :159-288.  kf_valid[i]!=0 <=> KF feature i has a good
+ * MapPoint.  out_match_f[j] = KF feature index matched to frame feature j, or -1.
+ * Returns nmatches. */
+int orc_search_by_bow_kf_f(const uint8_t* desc_kf, const float* angle_kf, const uint8_t* kf_valid,
+                           int n_kf, const orc_featvec* fv_kf, const uint8_t* desc_f,
+                           const float* angle_f, int n_f, const orc_featvec* fv_f, float nnratio,
+                           int check_ori, int32_t* out_match_f);
+/* SearchByBoW(KeyFrame*,KeyFrame*,...) :522-655. out_match12[i1] = idx2 or -1. */
+int orc_search_by_bow_kf_kf(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                            const orc_featvec* fv1, const uint8_t* desc2, const float* angle2,
+                            const uint8_t* valid2, int n2, const orc_featvec* fv2, float nnratio,
+                            int check_ori, int32_t* out_match12);
+
+typedef struct {
+    float x, y;       /* mvKeysUn[i].pt */
+    float angle;      /* mvKeysUn[i].angle */
+    int32_t octave;   /* mvKeysUn[i].octave */
+    float u_right;    /* mvuRight[i] (<0: monocular) */
+    int32_t has_mp;   /* GetMapPoint(i) != NULL */
+} orc_tri_feature;
+
+/* SearchForTriangulation :657-823.  F12 row-major 3x3; (ex,ey) epipole in image 2 (:664-670);
+ * scale_factors2 / level_sigma2_2 are pKF2->mvScaleFactors / mvLevelSigma2.
+ * out_pairs = (idx1, idx2) sorted by idx1.  Returns nmatches. */
+int orc_search_for_triangulation(const uint8_t* desc1, const orc_tri_feature* f1, int n1,
+                                 const orc_featvec* fv1, const uint8_t* desc2,
+                                 const orc_tri_feature* f2, int n2, const orc_featvec* fv2,
+                                 const float* F12, float ex, float ey, const float* scale_factors2,
+                                 const float* level_sigma2_2, int only_stereo, int check_ori,
+                                 int32_t* out_pairs, int cap_pairs);
+
+/* Frame::ComputeStereoMatches (R21/src/Frame.cc:471-645).  Pyramids are the padded planes of
+ * the two extractors (ROI origin at +19,+19; plane l is (w_l+38) wide with `strides[l]`).
+ * mb = mbf/fx is passed explicitly (the reference reads an uninitialised mb). */
+int orc_stereo_matches(const orc_keypoint* kl, const uint8_t* dl, int nl, const orc_keypoint* kr,
+                       const uint8_t* dr, int nr, int nlevels, const float* scale_factors,
+                       const float* inv_scale_factors, const uint8_t* const* pyr_l,
+                       const uint8_t* const* pyr_r, const int* lvl_w, const int* lvl_h,
+                       const size_t* strides, float mbf, float mb, float* u_right, float* depth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,262 @@
+"""ctypes bindings to the CPU oracle (oracle/liborb_oracle.so) and to the reference's own
+ORBextractor compiled over cvshim (oracle/_ref/liborbref*.so).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+class KeyPoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28 == C.sizeof(KeyPoint)
+
+
+class FeatVec(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("ptr", C.c_void_p), ("idx", C.c_void_p)]
+
+
+TRI_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("u_right", "<f4"),
+                      ("has_mp", "<i4")])
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ORACLE_DIR, "liborb_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_ic_angle.restype = C.c_float
+        L.orc_ic_angle.argtypes = [C.c_void_p, C.c_size_t]
+        L.orc_extractor_create.restype = C.c_void_p
+        L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_extractor_destroy.argtypes = [C.c_void_p]
+        L.orc_extractor_tables.argtypes = [C.c_void_p] * 7
+        L.orc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_void_p]
+        L.orc_level_size.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_get_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        L.orc_get_blurred.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.orc_get_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_get_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_size_t]
+        L.orc_copy_make_border_reflect101.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p,
+                                                      C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_gaussian_blur7_sigma2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_fast9_16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_fast_score.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+        L.orc_orb_descriptor.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_int, C.c_int, C.c_void_p]
+        L.orc_distribute_octtree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_int]
+        L.orc_knn2_full.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_search_by_bow_kf_f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+        L.orc_search_by_bow_kf_kf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int,
+                                              C.c_void_p]
+        L.orc_search_for_triangulation.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+# ----------------------------------------------------------------------------- primitives
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dst.strides[0])
+    return dst
+
+
+def copy_make_border(src, b):
+    src = np.ascontiguousarray(src)
+    h, w = src.shape
+    dst = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+    lib().orc_copy_make_border_reflect101(_p(src), w, h, src.strides[0], _p(dst), dst.strides[0], b, b, b, b)
+    return dst
+
+
+def gaussian_blur(src):
+    src = np.ascontiguousarray(src)
+    dst = np.empty_like(src)
+    lib().orc_gaussian_blur7_sigma2(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast(img, th, nms=True):
+    """img may be a non-contiguous 2-D view (row stride honoured)."""
+    assert img.strides[1] == 1
+    h, w = img.shape
+    cap = w * h
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_fast9_16(C.c_void_p(img.ctypes.data), w, h, img.strides[0], th, int(nms), _p(out), cap)
+    return out[:n]
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+# ----------------------------------------------------------------------------- extractor
+class OracleExtractor:
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, trig_mode=0, fma_mode=0):
+        self.L = lib()
+        self.nlevels = nlevels
+        self.h = self.L.orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th, trig_mode, fma_mode)
+        assert self.h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_extractor_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sf, isf, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        nf = np.zeros(n, np.int32); um = np.zeros(16, np.int32)
+        self.L.orc_extractor_tables(self.h, _p(sf), _p(isf), _p(s2), _p(is2), _p(nf), _p(um))
+        return dict(sf=sf, isf=isf, s2=s2, is2=is2, nfeat=nf, umax=um)
+
+    def extract(self, img, cap=20000):
+        img = np.ascontiguousarray(img)
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        rc = self.L.orc_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap,
+                                C.byref(n))
+        if rc != 0:
+            raise RuntimeError("orc_extract rc=%d" % rc)
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level_size(self, l):
+        w = C.c_int(); h = C.c_int()
+        self.L.orc_level_size(self.h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def pyramid(self, l, with_border=False):
+        w, h = self.level_size(l)
+        b = 19 if with_border else 0
+        out = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+        self.L.orc_get_pyramid(self.h, l, int(with_border), _p(out), out.strides[0])
+        return out
+
+    def blurred(self, l):
+        w, h = self.level_size(l)
+        out = np.empty((h, w), np.uint8)
+        rc = self.L.orc_get_blurred(self.h, l, _p(out), out.strides[0])
+        return out if rc == 0 else None
+
+    def candidates(self, l, cap=200000):
+        x = np.zeros(cap, np.int16); y = np.zeros(cap, np.int16); s = np.zeros(cap, np.uint8)
+        n = self.L.orc_get_candidates(self.h, l, _p(x), _p(y), _p(s), cap)
+        return x[:n].copy(), y[:n].copy(), s[:n].copy()
+
+    def level_keypoints(self, l, cap=20000):
+        out = np.zeros(cap, KP_DTYPE)
+        n = self.L.orc_get_level_keypoints(self.h, l, _p(out), cap)
+        return out[:n].copy()
+
+
+def distribute_octtree(x, y, score, min_x, max_x, min_y, max_y, nfeat):
+    x = np.ascontiguousarray(x, np.int16); y = np.ascontiguousarray(y, np.int16)
+    score = np.ascontiguousarray(score, np.uint8)
+    cap = len(x) + 8
+    out = np.zeros(cap, np.int32)
+    n = lib().orc_distribute_octtree(_p(x), _p(y), _p(score), len(x), min_x, max_x, min_y, max_y, nfeat, _p(out), cap)
+    if n < 0:
+        raise RuntimeError("orc_distribute_octtree rc=%d" % n)
+    return out[:n].copy()
+
+
+# ----------------------------------------------------------------------------- compiled reference
+_ref = {}
+
+
+def ref_available(fma=False):
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "liborbref_fma.so" if fma else "liborbref.so"))
+
+
+def ref_lib(fma=False):
+    if fma not in _ref:
+        path = os.path.join(ORACLE_DIR, "_ref", "liborbref_fma.so" if fma else "liborbref.so")
+        L = C.CDLL(path)
+        L.orbref_create.restype = C.c_void_p
+        L.orbref_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orbref_destroy.argtypes = [C.c_void_p]
+        L.orbref_tables.argtypes = [C.c_void_p] * 5
+        L.orbref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p]
+        L.orbref_level_size.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orbref_get_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        _ref[fma] = L
+    return _ref[fma]
+
+
+class RefExtractor:
+    """The reference's ORB_SLAM2::ORBextractor (compiled from /root/reference) behind ctypes."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, fma=False):
+        self.L = ref_lib(fma)
+        self.nlevels = nlevels
+        self.h = self.L.orbref_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orbref_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sf, isf, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        self.L.orbref_tables(self.h, _p(sf), _p(isf), _p(s2), _p(is2))
+        return dict(sf=sf, isf=isf, s2=s2, is2=is2)
+
+    def extract(self, img, cap=20000):
+        img = np.ascontiguousarray(img)
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        self.L.orbref_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap,
+                              C.byref(n))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def pyramid(self, l, with_border=False):
+        w = C.c_int(); h = C.c_int()
+        self.L.orbref_level_size(self.h, l, C.byref(w), C.byref(h))
+        b = 19 if with_border else 0
+        out = np.empty((h.value + 2 * b, w.value + 2 * b), np.uint8)
+        self.L.orbref_get_pyramid(self.h, l, int(with_border), _p(out), out.strides[0])
+        return out
