@@ -1,0 +1,385 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the ORB front-end hot path (BASELINE.json metric:
+"ORB extract frames/s @640x480/1000kp; Hamming 2-NN Gcmp/s; at 1-8 B200").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A step = one batch of B synthetic 640x480 frames (TUM1.yaml extractor: 1000 features, 8 levels, 1.2,
+FAST 20/7) through the whole extraction path (pyramid, FAST, quadtree, orientation, blur, rBRIEF).
+  value : frames/s with the frames already resident in HBM (orbx_extract_batch_device), CUDA events on the
+          extractor streams, max over ranks.
+  e2e   : frames/s through orbx_extract_batch_async/orbx_wait with HOST (pinned) buffers: H2D of every frame
+          and D2H of every key point / descriptor inside the timed region.
+  roofline     : the dominant kernel's algorithmic bytes / CUDA-event duration vs the measured HBM peak.
+  cpu_baseline : the reference's own ORBextractor.cc (oracle/_ref, compiled over oracle/cvshim) on the host cores.
+  matching     : brute-force 2-NN Hamming, 2000 queries x 1M map descriptors (map sharded over the ranks,
+                 per-rank records all-gathered over NCCL and merged), Gcmp/s.
+N > 1: one process per GPU (torchrun), replicas for extraction (weak scaling), sharded map for matching.
+--impl reference: times the reference CPU path (rank 0 only) and prints the same JSON shape.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT = 640, 480, 1000
+METRIC = "ORB extract frames/s @640x480/1000kp"
+# algorithmic bytes per 640x480 frame
+BYTES = {"pyramid": 2391758, "blur": 1901064, "fast_score": 950532, "cell_nms": 950532}
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref) on all host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_fps(frames, seconds_budget, threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    kind = "reference" if oracle_lib.ref_available() else "port"
+    threads = threads or (os.cpu_count() or 1)
+    mk = (lambda: oracle_lib.RefExtractor(NFEAT)) if kind == "reference" else (lambda: oracle_lib.OracleExtractor(NFEAT))
+    exts = [mk() for _ in range(threads)]
+    done = [0] * threads
+    stop_at = [0.0]
+
+    def work(t):
+        i = t
+        while time.perf_counter() < stop_at[0]:
+            exts[t].extract(frames[i % len(frames)], cap=1100)   # ctypes releases the GIL inside the call
+            done[t] += 1
+            i += threads
+
+    exts[0].extract(frames[0], cap=1100)   # warm
+    t0 = time.perf_counter()
+    stop_at[0] = t0 + seconds_budget
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    dt = time.perf_counter() - t0
+    n = sum(done)
+    return n / dt, kind, threads, n, dt
+
+
+def run_reference(args):
+    rank, world, local = _dist_env()
+    if rank != 0:
+        return
+    synth = importlib.import_module("cooperative-orb-slam_b200.synth")
+    frames = [synth.frame(s, W, H) for s in range(16)]
+    # each "step" is a bounded sample: ~2 s of all-core extraction
+    per_step = 2.0
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_fps(frames, 0.5)
+    tot_n = 0; tot_t = 0.0; kind = "port"; threads = 1
+    for _ in range(args.steps):
+        fps, kind, threads, n, dt = cpu_reference_fps(frames, per_step)
+        tot_n += n; tot_t += dt
+    fps = tot_n / tot_t
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "640x480 gray frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7 (TUM1.yaml)",
+                       "sample": "%d frames in %.1f s on %d host threads" % (tot_n, tot_t, threads)},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                             "sample": "%d frames (16 distinct seeds) over %d steps of %.1f s" % (tot_n, args.steps, per_step)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    orb = importlib.import_module("cooperative-orb-slam_b200")
+    synth = importlib.import_module("cooperative-orb-slam_b200.synth")
+    dev = torch.device("cuda", local)
+    B = args.batch
+    n_streams = args.streams
+    pool = 4   # distinct batches cycled through (working set per step >> L2)
+    seeds = np.arange(pool * B) + 1000 * rank
+    host_frames = np.stack([synth.frame(int(s), W, H) for s in seeds[:min(len(seeds), 64)]])
+    # tile the distinct frames over the pool (content repeats every 64 frames; still distinct memory)
+    reps = (pool * B + len(host_frames) - 1) // len(host_frames)
+    host_frames = np.concatenate([host_frames] * reps)[:pool * B].reshape(pool, B, H, W)
+
+    exts = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local, max_width=W, max_height=H, max_batch=B)
+            for _ in range(n_streams)]
+    cap = exts[0].max_keypoints(W, H)
+    streams = [torch.cuda.ExternalStream(e.stream(), device=dev) for e in exts]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: inputs resident in HBM -------------------------------------------------------
+    d_frames = torch.from_numpy(host_frames).to(dev)                      # [pool,B,H,W] uint8
+    d_kps = [torch.empty((B, cap, 7), dtype=torch.int32, device=dev) for _ in range(n_streams)]
+    d_desc = [torch.empty((B, cap, 32), dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+    d_cnt = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(n_streams)]
+
+    def dev_step(i):
+        s = i % n_streams
+        fr = d_frames[i % pool]
+        exts[s].extract_batch_device(fr.data_ptr(), B, W, H, W, W * H, d_kps[s].data_ptr(), d_desc[s].data_ptr(), cap,
+                                     d_cnt[s].data_ptr())
+
+    for i in range(args.warmup):
+        dev_step(i)
+    barrier()
+    l0 = sum(e.launch_count() for e in exts)
+    sampler = ClockSampler(local) if rank == 0 else None
+    start = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_streams)]
+    start.record(streams[0])
+    for s in range(1, n_streams):
+        streams[s].wait_event(start)
+    for i in range(args.steps):
+        dev_step(i)
+    for s in range(n_streams):
+        ends[s].record(streams[s])
+    barrier()
+    dev_ms = max(start.elapsed_time(e) for e in ends)
+    launches = sum(e.launch_count() for e in exts) - l0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = max_over_ranks(dev_ms)
+    value = world * B * args.steps / (dev_ms * 1e-3)
+    kp_mean = float(d_cnt[0].float().mean().item())
+
+    # ---------------- e2e: host buffers, H2D + D2H inside the timed region ---------------------------------
+    pin_in = [orb.PinnedArray((B, H, W), np.uint8) for _ in range(pool)]
+    for p in range(pool):
+        pin_in[p].array[...] = host_frames[p]
+    pin_k = [orb.PinnedArray((B, cap), orb.KP_DTYPE) for _ in range(n_streams)]
+    pin_d = [orb.PinnedArray((B, cap, 32), np.uint8) for _ in range(n_streams)]
+    pin_c = [orb.PinnedArray((B,), np.int32) for _ in range(n_streams)]
+
+    def e2e_run(steps):
+        inflight = [False] * n_streams
+        tot = 0
+        for i in range(steps):
+            s = i % n_streams
+            if inflight[s]:
+                exts[s].wait(); tot += int(pin_c[s].array.sum())
+            exts[s].extract_batch_async(pin_in[i % pool].array, pin_k[s].array, pin_d[s].array, pin_c[s].array)
+            inflight[s] = True
+        for s in range(n_streams):
+            if inflight[s]:
+                exts[s].wait(); tot += int(pin_c[s].array.sum())
+        return tot
+
+    e2e_run(max(args.warmup, n_streams))
+    barrier()
+    t0 = time.perf_counter()
+    tot_kp = e2e_run(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = world * B * args.steps / e2e_s
+    h2d = B * W * H
+    d2h = B * cap * (28 + 32) + B * 4
+
+    # ---------------- per-kernel durations (CUDA events on the extractor stream; outside the timed regions) --
+    exts[0].set_profiling(True)
+    acc = {}
+    reps_prof = 5
+    for i in range(reps_prof):
+        dev_step(i * n_streams)   # always stream 0
+        exts[0].wait()
+        for k, v in exts[0].stage_times().items():
+            acc[k] = acc.get(k, 0.0) + v / reps_prof
+    exts[0].set_profiling(False)
+    kern = {k: acc[k] for k in ("pyramid", "fast_score", "blur", "cell_nms", "quadtree", "describe")}
+    dominant = max(kern, key=kern.get)
+    peak, peak_src = _peaks()
+    if dominant in BYTES:
+        ach = BYTES[dominant] * B / (kern[dominant] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src}
+    else:
+        # latency-bound stage (quadtree / describe): report the best pixel kernel against HBM and name the dominant one
+        ach = BYTES["fast_score"] * B / (kern["fast_score"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "fast_score", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "note": "dominant stage is %s (latency-bound, no byte roofline)" % dominant}
+    roof["stage_ms_per_batch"] = {k: round(v, 4) for k, v in acc.items()}
+    roof["stage_gbs"] = {k: round(BYTES[k] * B / (kern[k] * 1e-3) / 1e9, 1) for k in BYTES if kern.get(k, 0) > 0}
+
+    # ---------------- matching: 2000 x 1M brute-force 2-NN, map sharded over ranks -------------------------
+    matching = None
+    if not args.no_matching:
+        NQ, NM = 2000, 1000000
+        m_all = synth.descriptors(NM, seed=1234)
+        q, m_all, _ = synth.query_set(m_all, nq=NQ, seed=4321)
+        lo = NM * rank // world; hi = NM * (rank + 1) // world
+        d_m = torch.from_numpy(m_all[lo:hi].copy()).to(dev)
+        d_q = torch.from_numpy(q).to(dev)
+        rec = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
+        L = orb.lib()
+        import ctypes as C
+        cur = torch.cuda.current_stream(dev)
+
+        def match_step():
+            rc = L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), NQ, C.c_void_p(d_m.data_ptr()), hi - lo, lo,
+                                    C.c_void_p(rec.data_ptr()), 0, C.c_void_p(cur.cuda_stream))
+            assert rc == 0, L.orb_last_error()
+            if world > 1:
+                parts = torch.empty((world, NQ, 4), dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(parts, rec)
+                out = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
+                rc = L.orbm_merge_top2_device(C.c_void_p(parts.data_ptr()), world, NQ, C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(cur.cuda_stream))
+                assert rc == 0
+                return out
+            return rec
+
+        for _ in range(3):
+            match_step()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        msteps = 10
+        e0.record(cur)
+        for _ in range(msteps):
+            out = match_step()
+        e1.record(cur)
+        barrier()
+        mms = max_over_ranks(e0.elapsed_time(e1)) / msteps
+        gcmp = NQ * NM / (mms * 1e-3) / 1e9
+        chk = int(out[:, 0].sum().item())
+        matching = {"metric": "Hamming 2-NN Gcmp/s (2000 queries x 1M map, 256-bit)", "value": gcmp, "unit": "Gcmp/s",
+                    "ms_per_batch": mms, "map_shards": world, "d1_checksum": chk,
+                    "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8, "frac_of_popc_peak": gcmp / (148 * 16 * 1.965 / 8)}
+
+    # ---------------- CPU baseline (rank 0, N=1 only; bounded sample) --------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        fps, kind, threads, n, dt = cpu_reference_fps([host_frames[0, i] for i in range(min(B, 16))], args.cpu_seconds)
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+               "sample": "%d frames of the same workload in %.1f s on %d host threads (one extractor per thread)" % (n, dt, threads)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "640x480 gray frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7 (TUM1.yaml)",
+                           "frames_per_step": B, "streams_per_gpu": n_streams, "parallelism": "replicas x%d" % world,
+                           "l2_policy": "inputs+intermediates per step (%.0f MB) exceed the 126 MB L2; %d distinct batches cycled"
+                                        % (B * 5.6, pool),
+                           "keypoints_per_frame": kp_mean},
+                "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "keypoints_downloaded": tot_kp},
+                "gpu_launches": int(launches), "clocks": clocks, "matching": matching}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-matching", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

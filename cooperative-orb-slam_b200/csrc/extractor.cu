@@ -1,0 +1,680 @@
+// extractor.cu -- host side of the extractor: handle, level geometry, staging and the orbx_* C ABI.
+// Mirrors ORB_SLAM2::ORBextractor (R21/include/ORBextractor.h:45-111, R21/src/ORBextractor.cc:410-470,
+// :1043-1132): same constructor arithmetic for the scale tables / features per level / cell grid,
+// kernels K1..K5 replace the per-frame work.
+#include "internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace orbcuda {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    set_error("CUDA error %s (%d) in %s", cudaGetErrorString(e), (int)e, what);
+    return false;
+}
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }   // cvRound: round-half-even
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace orbcuda
+
+using namespace orbcuda;
+
+struct orbx_handle_s {
+    orbx_params_t prm;
+    int device = 0;
+    double scale_factor_d = 1.2;   // R21/include/ORBextractor.h:98: a double member holding the float argument
+    std::vector<float> sf, isf, s2, is2;
+    std::vector<int> nfeat;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[10] = {};
+    bool profiling = false;
+    float stage_ms[9] = {};
+    bool timing_pending = false;
+    int64_t launches = 0;
+
+    // geometry of the current image size
+    int cur_w = 0, cur_h = 0;
+    FrameLayout fl = {};
+    std::vector<LevelGeom> geom;
+    std::vector<CellInfo> cells;
+    std::vector<ResizeTap> xtab, ytab;
+    LevelGeom* d_geom = nullptr;
+    CellInfo* d_cells = nullptr;
+    ResizeTap* d_xtab = nullptr;
+    ResizeTap* d_ytab = nullptr;
+    size_t cap_geom = 0, cap_cells = 0, cap_xtab = 0, cap_ytab = 0;
+
+    // per-batch device buffers (grown on demand)
+    int batch_cap = 0;
+    uint8_t* d_in = nullptr; size_t cap_in = 0;
+    uint8_t* d_pyr = nullptr; size_t cap_pyr = 0;
+    uint8_t* d_blur = nullptr; size_t cap_blur = 0;
+    uint8_t* d_score = nullptr; size_t cap_score = 0;
+    uint32_t* d_cand = nullptr; size_t cap_cand = 0;
+    uint32_t* d_scratch = nullptr; size_t cap_scratch = 0;
+    uint16_t* d_node = nullptr; size_t cap_node = 0;
+    int32_t* d_cell_count = nullptr; size_t cap_cell_count = 0;
+    uint32_t* d_sel = nullptr; size_t cap_sel = 0;
+    int32_t* d_level_count = nullptr; size_t cap_level_count = 0;
+    orb_keypoint_t* d_kps = nullptr; size_t cap_kps = 0;
+    uint8_t* d_desc = nullptr; size_t cap_desc = 0;
+    int32_t* d_counts = nullptr; size_t cap_counts = 0;
+    // pinned staging
+    uint8_t* h_in = nullptr; size_t cap_h_in = 0;
+    orb_keypoint_t* h_kps = nullptr; size_t cap_h_kps = 0;
+    uint8_t* h_desc = nullptr; size_t cap_h_desc = 0;
+    int32_t* h_counts = nullptr; size_t cap_h_counts = 0;
+
+    // pending async call
+    bool pending = false;
+    int p_frames = 0, p_cap = 0;
+    orb_keypoint_t* p_kps = nullptr; uint8_t* p_desc = nullptr; int32_t* p_counts = nullptr;
+    bool p_direct = false;
+    int last_frames = 0;
+};
+
+namespace {
+
+template <class T> int grow_dev(T*& p, size_t& cap, size_t need_bytes) {
+    if (need_bytes <= cap) return ORB_OK;
+    if (p) ORB_CUDA_TRY(cudaFree(p));
+    p = nullptr; cap = 0;
+    ORB_CUDA_TRY(cudaMalloc((void**)&p, need_bytes));
+    cap = need_bytes;
+    return ORB_OK;
+}
+template <class T> int grow_host(T*& p, size_t& cap, size_t need_bytes) {
+    if (need_bytes <= cap) return ORB_OK;
+    if (p) ORB_CUDA_TRY(cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    ORB_CUDA_TRY(cudaHostAlloc((void**)&p, need_bytes, cudaHostAllocDefault));
+    cap = need_bytes;
+    return ORB_OK;
+}
+
+// cv::resize INTER_LINEAR tap table (OpenCV imgproc resize.cpp)
+void make_taps(int ssize, int dsize, bool clamp_x, std::vector<ResizeTap>& out) {
+    const double inv_scale = (double)dsize / ssize;
+    const double scale = 1. / inv_scale;
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        ResizeTap t;
+        if (clamp_x) {   // horizontal taps clamp the position and zero the fraction
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+            t.ofs = (int16_t)s;
+            t.pad = (int16_t)std::min(s + 1, ssize - 1);
+        } else {         // vertical taps keep the fraction and clip the row indices
+            t.ofs = (int16_t)std::min(std::max(s, 0), ssize - 1);
+            t.pad = (int16_t)std::min(std::max(s + 1, 0), ssize - 1);
+        }
+        t.c0 = (int16_t)cv_round_f((1.f - f) * 2048.f);
+        t.c1 = (int16_t)cv_round_f(f * 2048.f);
+        out.push_back(t);
+    }
+}
+
+// Level geometry for an image size.  Returns ORB_ERR_ARG for shapes the reference itself cannot
+// process (a level narrower than one FAST cell divides by zero at R21 :781-784).
+int build_geometry(orbx_handle_s* h, int width, int height) {
+    const int L = h->prm.nlevels;
+    if (width > 4096 || height > 4096) { set_error("image larger than 4096 px is not supported"); return ORB_ERR_ARG; }
+    std::vector<LevelGeom> geom(L);
+    std::vector<CellInfo> cells;
+    std::vector<ResizeTap> xtab, ytab;
+    int64_t pyr_off = 0, sp_off = 0, cand_off = 0;
+    int kp_slot = 0, node_cap = 0;
+    for (int l = 0; l < L; l++) {
+        LevelGeom& g = geom[l];
+        memset(&g, 0, sizeof(g));
+        const float scale = h->isf[l];
+        g.w = cv_round_f((float)width * scale);    // R21 :1112
+        g.h = cv_round_f((float)height * scale);
+        const int minB = kMinBorder, maxBX = g.w - kEdge + 3, maxBY = g.h - kEdge + 3;
+        const float fw = (float)(maxBX - minB), fh = (float)(maxBY - minB);
+        const float W = 30;
+        g.n_cols = (int)(fw / W);
+        g.n_rows = (int)(fh / W);
+        if (g.n_cols < 1 || g.n_rows < 1) {
+            set_error("level %d (%dx%d) is smaller than one 30-px FAST cell; the reference divides by zero here", l, g.w, g.h);
+            return ORB_ERR_ARG;
+        }
+        g.w_cell = (int)ceilf(fw / g.n_cols);
+        g.h_cell = (int)ceilf(fh / g.n_rows);
+        g.pitch = (int)align_up(kXPad + g.w + kEdge, 64);
+        g.plane_rows = g.h + 2 * kEdge;
+        g.plane_off = pyr_off;
+        pyr_off += align_up((int64_t)g.pitch * g.plane_rows, 256);
+        g.spitch = (int)align_up(g.w, 16);
+        g.splane_off = sp_off;
+        sp_off += align_up((int64_t)g.spitch * g.h, 256);
+        g.cell_base = (int)cells.size();
+        g.cand_off = cand_off;
+        int slot = 0;
+        for (int i = 0; i < g.n_rows; i++) {
+            const int iniY = minB + i * g.h_cell;
+            int maxY = iniY + g.h_cell + 6;
+            const bool skip_row = iniY >= maxBY - 3;
+            if (maxY > maxBY) maxY = maxBY;
+            for (int j = 0; j < g.n_cols; j++) {
+                const int iniX = minB + j * g.w_cell;
+                int maxX = iniX + g.w_cell + 6;
+                const bool skip = skip_row || iniX >= maxBX - 6;
+                if (maxX > maxBX) maxX = maxBX;
+                CellInfo c;
+                c.x0 = (int16_t)(iniX + 3); c.x1 = (int16_t)(maxX - 3);
+                c.y0 = (int16_t)(iniY + 3); c.y1 = (int16_t)(maxY - 3);
+                if (skip || c.x1 <= c.x0 || c.y1 <= c.y0) { c.x1 = c.x0; c.y1 = c.y0; }
+                const int iw = c.x1 - c.x0, ih = c.y1 - c.y0;
+                if (iw * ih >= 4096) { set_error("FAST cell larger than 4095 px"); return ORB_ERR_ARG; }
+                c.slot_off = slot;
+                slot += ((iw + 1) / 2) * ((ih + 1) / 2);   // strict 3x3 NMS keeps at most one pixel per 2x2 block
+                cells.push_back(c);
+            }
+        }
+        cand_off += align_up(std::max(slot, 1), 4);
+        g.n_feat = h->nfeat[l];
+        g.n_ini = (int)roundf((float)(maxBX - minB) / (maxBY - minB));   // R21 :543
+        if (g.n_ini < 1) {
+            set_error("level %d: height > 2x width gives zero quadtree roots (the reference divides by zero)", l);
+            return ORB_ERR_ARG;
+        }
+        g.h_x = (float)(maxBX - minB) / g.n_ini;                            // R21 :545
+        g.kp_cap = std::max(g.n_feat + 3, 4 * g.n_ini);
+        g.kp_slot = kp_slot;
+        kp_slot += g.kp_cap;
+        node_cap = std::max(node_cap, g.kp_cap);
+        g.scale = h->sf[l];
+        g.patch_size = (float)(int)(31 * h->sf[l]);                         // R21 :836
+        if (l > 0) {
+            g.xtab_off = (int)xtab.size();
+            g.ytab_off = (int)ytab.size();
+            make_taps(geom[l - 1].w, g.w, true, xtab);
+            make_taps(geom[l - 1].h, g.h, false, ytab);
+        }
+    }
+    if (node_cap > 60000) { set_error("nfeatures per level too large"); return ORB_ERR_ARG; }
+    FrameLayout fl;
+    fl.nlevels = L; fl.width = width; fl.height = height;
+    fl.in_pitch = (int)align_up(width, 16);
+    fl.pyr_bytes = pyr_off; fl.splane_bytes = sp_off;
+    fl.n_cells = (int)cells.size();
+    fl.cand_entries = cand_off;
+    fl.kp_cap = kp_slot;
+    fl.node_cap = (int)align_up(node_cap + 4, 32);
+    h->geom.swap(geom); h->cells.swap(cells); h->xtab.swap(xtab); h->ytab.swap(ytab);
+    if (h->xtab.empty()) { h->xtab.push_back(ResizeTap()); h->ytab.push_back(ResizeTap()); }
+    h->fl = fl;
+    return ORB_OK;
+}
+
+int upload_geometry(orbx_handle_s* h) {
+    int rc;
+    if ((rc = grow_dev(h->d_geom, h->cap_geom, h->geom.size() * sizeof(LevelGeom)))) return rc;
+    if ((rc = grow_dev(h->d_cells, h->cap_cells, h->cells.size() * sizeof(CellInfo)))) return rc;
+    if ((rc = grow_dev(h->d_xtab, h->cap_xtab, h->xtab.size() * sizeof(ResizeTap)))) return rc;
+    if ((rc = grow_dev(h->d_ytab, h->cap_ytab, h->ytab.size() * sizeof(ResizeTap)))) return rc;
+    // synchronous copies from pageable vectors: only when the image size changes
+    ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_geom, h->geom.data(), h->geom.size() * sizeof(LevelGeom), cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellInfo), cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_xtab, h->xtab.data(), h->xtab.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(h->d_ytab, h->ytab.data(), h->ytab.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+    return ORB_OK;
+}
+
+int ensure_size(orbx_handle_s* h, int width, int height, int n_frames) {
+    int rc;
+    if (width != h->cur_w || height != h->cur_h) {
+        if ((rc = build_geometry(h, width, height))) return rc;
+        if ((rc = upload_geometry(h))) return rc;
+        h->cur_w = width; h->cur_h = height;
+    }
+    const FrameLayout& fl = h->fl;
+    const size_t B = (size_t)n_frames;
+    if ((rc = grow_dev(h->d_pyr, h->cap_pyr, B * fl.pyr_bytes))) return rc;
+    if ((rc = grow_dev(h->d_blur, h->cap_blur, B * fl.splane_bytes))) return rc;
+    if ((rc = grow_dev(h->d_score, h->cap_score, B * fl.splane_bytes))) return rc;
+    if ((rc = grow_dev(h->d_cand, h->cap_cand, B * fl.cand_entries * 4))) return rc;
+    if ((rc = grow_dev(h->d_scratch, h->cap_scratch, B * fl.cand_entries * 4))) return rc;
+    if ((rc = grow_dev(h->d_node, h->cap_node, B * fl.cand_entries * 2))) return rc;
+    if ((rc = grow_dev(h->d_cell_count, h->cap_cell_count, B * fl.n_cells * 4))) return rc;
+    if ((rc = grow_dev(h->d_sel, h->cap_sel, B * fl.kp_cap * 4))) return rc;
+    if ((rc = grow_dev(h->d_level_count, h->cap_level_count, B * kMaxLevels * 4))) return rc;
+    return ORB_OK;
+}
+
+void fill_ptrs(orbx_handle_s* h, DevPtrs& d, const uint8_t* d_in) {
+    d.in = d_in; d.pyr = h->d_pyr; d.blur = h->d_blur; d.score = h->d_score; d.cand = h->d_cand;
+    d.cell_count = h->d_cell_count; d.oct_scratch = h->d_scratch; d.oct_node = h->d_node; d.sel = h->d_sel;
+    d.level_count = h->d_level_count; d.geom = h->d_geom; d.cells = h->d_cells; d.xtab = h->d_xtab; d.ytab = h->d_ytab;
+}
+
+// Enqueue K1..K5 for n_frames images resident at d_in (row pitch fl.in_pitch).
+int enqueue_kernels(orbx_handle_s* h, const uint8_t* d_in, size_t in_frame_stride, int n_frames, orb_keypoint_t* d_kps,
+                    uint8_t* d_desc, int32_t* d_counts, int cap) {
+    DevPtrs d;
+    fill_ptrs(h, d, d_in);
+    cudaStream_t s = h->stream;
+    const bool prof = h->profiling;
+    int n;
+    if (prof) cudaEventRecord(h->ev[1], s);
+    if ((n = launch_pyramid(d, h->fl, h->geom.data(), n_frames, in_frame_stride, s)) < 0) return ORB_ERR_CUDA;
+    h->launches += n;
+    if (prof) cudaEventRecord(h->ev[2], s);
+    if ((n = launch_fast_score(d, h->fl, h->geom.data(), n_frames, h->prm.min_th_fast, s)) < 0) return ORB_ERR_CUDA;
+    h->launches += n;
+    if (prof) cudaEventRecord(h->ev[3], s);
+    if ((n = launch_blur(d, h->fl, h->geom.data(), n_frames, s)) < 0) return ORB_ERR_CUDA;
+    h->launches += n;
+    if (prof) cudaEventRecord(h->ev[4], s);
+    if ((n = launch_fast_cells(d, h->fl, n_frames, h->prm.ini_th_fast, s)) < 0) return ORB_ERR_CUDA;
+    h->launches += n;
+    if (prof) cudaEventRecord(h->ev[5], s);
+    if ((n = launch_octree(d, h->fl, n_frames, s)) < 0) { set_error("quadtree kernel configuration failed"); return ORB_ERR_CUDA; }
+    h->launches += n;
+    if (prof) cudaEventRecord(h->ev[6], s);
+    if ((n = launch_describe(d, h->fl, n_frames, d_kps, d_desc, d_counts, cap, s)) < 0) return ORB_ERR_CUDA;
+    h->launches += n;
+    if (prof) cudaEventRecord(h->ev[7], s);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orb_last_error(void) { return g_err; }
+
+int orb_device_count(int* count) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (count) *count = n;
+    return ORB_OK;
+}
+
+int orb_host_alloc(void** ptr, size_t bytes) {
+    ORB_CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return ORB_OK;
+}
+int orb_host_free(void* ptr) {
+    ORB_CUDA_TRY(cudaFreeHost(ptr));
+    return ORB_OK;
+}
+
+int orbx_create(const orbx_params_t* p, int max_width, int max_height, int max_batch, int device, orbx_handle_t* out) {
+    if (!p || !out || p->nlevels < 1 || p->nlevels > kMaxLevels || p->nfeatures < 1 || !(p->scale_factor > 1.0f)) {
+        set_error("orbx_create: bad parameters");
+        return ORB_ERR_ARG;
+    }
+    orbx_handle_s* h = new orbx_handle_s;
+    h->prm = *p;
+    h->device = device;
+    // R21 ORBextractor.cc:415-446 -- same float/double mix
+    const int L = p->nlevels;
+    h->scale_factor_d = p->scale_factor;
+    h->sf.resize(L); h->s2.resize(L); h->isf.resize(L); h->is2.resize(L); h->nfeat.resize(L);
+    h->sf[0] = 1.0f; h->s2[0] = 1.0f;
+    for (int i = 1; i < L; i++) {
+        h->sf[i] = (float)(h->sf[i - 1] * h->scale_factor_d);
+        h->s2[i] = h->sf[i] * h->sf[i];
+    }
+    for (int i = 0; i < L; i++) { h->isf[i] = 1.0f / h->sf[i]; h->is2[i] = 1.0f / h->s2[i]; }
+    float factor = (float)(1.0f / h->scale_factor_d);
+    float ndesired = p->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)L));
+    int sum = 0;
+    for (int l = 0; l < L - 1; l++) {
+        h->nfeat[l] = cv_round_f(ndesired);
+        sum += h->nfeat[l];
+        ndesired *= factor;
+    }
+    h->nfeat[L - 1] = std::max(p->nfeatures - sum, 0);
+    *out = h;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        set_error("orbx_create: no usable CUDA device %d (this library has no CPU fallback)", device);
+        cudaGetLastError();
+        delete h; *out = nullptr;
+        return ORB_ERR_CUDA;
+    }
+    if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete h; *out = nullptr; return ORB_ERR_CUDA; }
+    for (auto& e : h->ev) if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) { *out = nullptr; return ORB_ERR_CUDA; }
+    if (max_width > 0 && max_height > 0 && max_batch > 0) {
+        int rc = ensure_size(h, max_width, max_height, max_batch);
+        if (rc) { orbx_destroy(h); *out = nullptr; return rc; }
+        h->batch_cap = max_batch;
+    }
+    return ORB_OK;
+}
+
+int orbx_destroy(orbx_handle_t h) {
+    if (!h) return ORB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* dev[] = {h->d_geom, h->d_cells, h->d_xtab, h->d_ytab, h->d_in, h->d_pyr, h->d_blur, h->d_score, h->d_cand,
+                   h->d_scratch, h->d_node, h->d_cell_count, h->d_sel, h->d_level_count, h->d_kps, h->d_desc, h->d_counts};
+    for (void* p : dev) if (p) cudaFree(p);
+    void* host[] = {h->h_in, h->h_kps, h->h_desc, h->h_counts};
+    for (void* p : host) if (p) cudaFreeHost(p);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ORB_OK;
+}
+
+int orbx_tables(orbx_handle_t h, float* sf, float* isf, float* s2, float* is2, int32_t* nfeat) {
+    if (!h) return ORB_ERR_ARG;
+    for (int i = 0; i < h->prm.nlevels; i++) {
+        if (sf) sf[i] = h->sf[i];
+        if (isf) isf[i] = h->isf[i];
+        if (s2) s2[i] = h->s2[i];
+        if (is2) is2[i] = h->is2[i];
+        if (nfeat) nfeat[i] = h->nfeat[i];
+    }
+    return ORB_OK;
+}
+
+int orbx_max_keypoints(orbx_handle_t h, int width, int height, int* cap) {
+    if (!h || !cap) return ORB_ERR_ARG;
+    orbx_handle_s tmp;
+    tmp.prm = h->prm; tmp.sf = h->sf; tmp.isf = h->isf; tmp.nfeat = h->nfeat;
+    const int rc = build_geometry(&tmp, width, height);
+    if (rc) return rc;
+    *cap = tmp.fl.kp_cap;
+    return ORB_OK;
+}
+
+int orbx_set_profiling(orbx_handle_t h, int enable) {
+    if (!h) return ORB_ERR_ARG;
+    h->profiling = enable != 0;
+    return ORB_OK;
+}
+
+int orbx_stage_times(orbx_handle_t h, float* ms) {
+    if (!h || !ms) return ORB_ERR_ARG;
+    if (h->timing_pending) {
+        cudaSetDevice(h->device);
+        ORB_CUDA_TRY(cudaEventSynchronize(h->ev[9]));
+        for (int i = 0; i < 8; i++) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); t = 0; }
+            h->stage_ms[i] = t;
+        }
+        float t = 0;
+        if (cudaEventElapsedTime(&t, h->ev[0], h->ev[8]) != cudaSuccess) { cudaGetLastError(); t = 0; }
+        h->stage_ms[8] = t;
+        h->timing_pending = false;
+    }
+    memcpy(ms, h->stage_ms, sizeof(h->stage_ms));
+    return ORB_OK;
+}
+
+int orbx_launch_count(orbx_handle_t h, int64_t* n) {
+    if (!h || !n) return ORB_ERR_ARG;
+    *n = h->launches;
+    return ORB_OK;
+}
+
+int orbx_stream(orbx_handle_t h, void** stream) {
+    if (!h || !stream) return ORB_ERR_ARG;
+    *stream = (void*)h->stream;
+    return ORB_OK;
+}
+
+int orbx_extract_batch_device(orbx_handle_t h, const uint8_t* d_images, int n_frames, int width, int height,
+                              size_t row_stride, size_t frame_stride, orb_keypoint_t* d_kps, uint8_t* d_desc, int cap,
+                              int32_t* d_counts) {
+    if (!h || !d_images || n_frames < 1 || width < 1 || height < 1 || !d_kps || !d_desc || !d_counts || cap < 1) {
+        set_error("orbx_extract_batch_device: bad arguments");
+        return ORB_ERR_ARG;
+    }
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure_size(h, width, height, n_frames))) return rc;
+    const uint8_t* src = d_images;
+    size_t fstride = frame_stride;
+    int pitch = (int)row_stride;
+    if ((row_stride & 3) || (frame_stride & 3) || (reinterpret_cast<uintptr_t>(d_images) & 3)) {
+        // unaligned user layout: repack into the handle's own input buffer
+        if ((rc = grow_dev(h->d_in, h->cap_in, (size_t)n_frames * h->fl.in_pitch * height))) return rc;
+        for (int f = 0; f < n_frames; f++)
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * h->fl.in_pitch * height, h->fl.in_pitch,
+                                           d_images + f * frame_stride, row_stride, width, height,
+                                           cudaMemcpyDeviceToDevice, h->stream));
+        src = h->d_in; fstride = (size_t)h->fl.in_pitch * height; pitch = h->fl.in_pitch;
+    }
+    const int saved = h->fl.in_pitch;
+    h->fl.in_pitch = pitch;
+    if (h->profiling) { cudaEventRecord(h->ev[0], h->stream); }
+    rc = enqueue_kernels(h, src, fstride, n_frames, d_kps, d_desc, d_counts, cap);
+    if (h->profiling) { cudaEventRecord(h->ev[8], h->stream); cudaEventRecord(h->ev[9], h->stream); h->timing_pending = true; }
+    h->fl.in_pitch = saved;
+    h->last_frames = n_frames;
+    return rc;
+}
+
+int orbx_extract_batch_async(orbx_handle_t h, const uint8_t* images, int n_frames, int width, int height,
+                             size_t row_stride, size_t frame_stride, orb_keypoint_t* kps, uint8_t* desc, int cap,
+                             int32_t* counts) {
+    if (!h || n_frames < 1 || !counts || cap < 1 || !kps || !desc) { set_error("orbx_extract_batch: bad arguments"); return ORB_ERR_ARG; }
+    if (h->pending) { set_error("orbx_extract_batch_async: previous call not waited for"); return ORB_ERR_ARG; }
+    if (!images || width <= 0 || height <= 0) {   // R21 :1046-1047: silent return on an empty image
+        for (int f = 0; f < n_frames; f++) counts[f] = 0;
+        return ORB_OK;
+    }
+    if (row_stride < (size_t)width) { set_error("row stride smaller than width"); return ORB_ERR_ARG; }
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure_size(h, width, height, n_frames))) return rc;
+    const FrameLayout& fl = h->fl;
+    const size_t dev_frame = (size_t)fl.in_pitch * height;
+    if ((rc = grow_dev(h->d_in, h->cap_in, (size_t)n_frames * dev_frame))) return rc;
+    if ((rc = grow_dev(h->d_kps, h->cap_kps, (size_t)n_frames * cap * sizeof(orb_keypoint_t)))) return rc;
+    if ((rc = grow_dev(h->d_desc, h->cap_desc, (size_t)n_frames * cap * 32))) return rc;
+    if ((rc = grow_dev(h->d_counts, h->cap_counts, (size_t)n_frames * 4))) return rc;
+    cudaStream_t s = h->stream;
+    if (h->profiling) cudaEventRecord(h->ev[0], s);
+    // ---- upload: straight from the caller's buffer when it is pinned, else through pinned staging
+    const bool in_pinned = is_pinned(images);
+    if (in_pinned && row_stride == (size_t)fl.in_pitch && frame_stride == dev_frame) {
+        ORB_CUDA_TRY(cudaMemcpyAsync(h->d_in, images, (size_t)n_frames * dev_frame, cudaMemcpyHostToDevice, s));
+    } else if (in_pinned) {
+        for (int f = 0; f < n_frames; f++)
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + f * dev_frame, fl.in_pitch, images + f * frame_stride, row_stride, width,
+                                           height, cudaMemcpyHostToDevice, s));
+    } else {
+        if ((rc = grow_host(h->h_in, h->cap_h_in, (size_t)n_frames * dev_frame))) return rc;
+        for (int f = 0; f < n_frames; f++)
+            for (int y = 0; y < height; y++)
+                memcpy(h->h_in + f * dev_frame + (size_t)y * fl.in_pitch, images + f * frame_stride + (size_t)y * row_stride, width);
+        ORB_CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, (size_t)n_frames * dev_frame, cudaMemcpyHostToDevice, s));
+    }
+    if ((rc = enqueue_kernels(h, h->d_in, dev_frame, n_frames, h->d_kps, h->d_desc, h->d_counts, cap))) return rc;
+    // ---- download
+    const size_t kb = (size_t)n_frames * cap * sizeof(orb_keypoint_t), db = (size_t)n_frames * cap * 32;
+    const bool direct = is_pinned(kps) && is_pinned(desc) && is_pinned(counts);
+    if (direct) {
+        ORB_CUDA_TRY(cudaMemcpyAsync(counts, h->d_counts, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA_TRY(cudaMemcpyAsync(kps, h->d_kps, kb, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA_TRY(cudaMemcpyAsync(desc, h->d_desc, db, cudaMemcpyDeviceToHost, s));
+    } else {
+        if ((rc = grow_host(h->h_kps, h->cap_h_kps, kb))) return rc;
+        if ((rc = grow_host(h->h_desc, h->cap_h_desc, db))) return rc;
+        if ((rc = grow_host(h->h_counts, h->cap_h_counts, (size_t)n_frames * 4))) return rc;
+        ORB_CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA_TRY(cudaMemcpyAsync(h->h_kps, h->d_kps, kb, cudaMemcpyDeviceToHost, s));
+        ORB_CUDA_TRY(cudaMemcpyAsync(h->h_desc, h->d_desc, db, cudaMemcpyDeviceToHost, s));
+    }
+    if (h->profiling) { cudaEventRecord(h->ev[8], s); cudaEventRecord(h->ev[9], s); h->timing_pending = true; }
+    h->pending = true; h->p_direct = direct; h->p_frames = n_frames; h->p_cap = cap;
+    h->p_kps = kps; h->p_desc = desc; h->p_counts = counts;
+    h->last_frames = n_frames;
+    return ORB_OK;
+}
+
+int orbx_wait(orbx_handle_t h) {
+    if (!h) return ORB_ERR_ARG;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!h->pending) return ORB_OK;
+    h->pending = false;
+    int rc = ORB_OK;
+    const int cap = h->p_cap;
+    const int32_t* cnt = h->p_direct ? h->p_counts : h->h_counts;
+    for (int f = 0; f < h->p_frames; f++) {
+        int n = cnt[f];
+        if (n > cap) { set_error("frame %d produced %d key points but cap is %d", f, n, cap); rc = ORB_ERR_CAPACITY; n = cap; }
+        if (!h->p_direct) {
+            memcpy(h->p_kps + (size_t)f * cap, h->h_kps + (size_t)f * cap, (size_t)n * sizeof(orb_keypoint_t));
+            memcpy(h->p_desc + (size_t)f * cap * 32, h->h_desc + (size_t)f * cap * 32, (size_t)n * 32);
+            h->p_counts[f] = cnt[f];
+        }
+    }
+    return rc;
+}
+
+int orbx_extract_batch(orbx_handle_t h, const uint8_t* images, int n_frames, int width, int height, size_t row_stride,
+                       size_t frame_stride, orb_keypoint_t* kps, uint8_t* desc, int cap, int32_t* counts) {
+    const int rc = orbx_extract_batch_async(h, images, n_frames, width, height, row_stride, frame_stride, kps, desc, cap, counts);
+    if (rc) return rc;
+    return orbx_wait(h);
+}
+
+int orbx_extract(orbx_handle_t h, const uint8_t* image, int width, int height, size_t stride, orb_keypoint_t* kps,
+                 uint8_t* desc, int cap, int* n) {
+    int32_t cnt = 0;
+    const int rc = orbx_extract_batch(h, image, 1, width, height, stride, stride * (size_t)std::max(height, 0), kps, desc, cap, &cnt);
+    if (n) *n = cnt;
+    return rc;
+}
+
+// ---- views of intermediate results --------------------------------------------------------------
+int orbx_level_size(orbx_handle_t h, int level, int* w, int* hh) {
+    if (!h || level < 0 || level >= (int)h->geom.size()) return ORB_ERR_ARG;
+    *w = h->geom[level].w; *hh = h->geom[level].h;
+    return ORB_OK;
+}
+
+int orbx_download_level(orbx_handle_t h, int frame, int level, int with_border, uint8_t* dst, size_t dst_stride) {
+    if (!h || level < 0 || level >= (int)h->geom.size() || frame < 0 || frame >= h->last_frames || !dst) return ORB_ERR_ARG;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const LevelGeom& g = h->geom[level];
+    const int b = with_border ? kEdge : 0;
+    const uint8_t* src = h->d_pyr + (size_t)frame * h->fl.pyr_bytes + g.plane_off + (size_t)(kEdge - b) * g.pitch + kXPad - b;
+    ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, src, g.pitch, g.w + 2 * b, g.h + 2 * b, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+static int download_splane(orbx_handle_t h, const uint8_t* base, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    if (!h || level < 0 || level >= (int)h->geom.size() || frame < 0 || frame >= h->last_frames || !dst) return ORB_ERR_ARG;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const LevelGeom& g = h->geom[level];
+    ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, base + (size_t)frame * h->fl.splane_bytes + g.splane_off, g.spitch, g.w, g.h,
+                              cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+int orbx_download_blurred(orbx_handle_t h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    return download_splane(h, h ? h->d_blur : nullptr, frame, level, dst, dst_stride);
+}
+int orbx_download_scores(orbx_handle_t h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+    return download_splane(h, h ? h->d_score : nullptr, frame, level, dst, dst_stride);
+}
+
+int orbx_download_candidates(orbx_handle_t h, int frame, int level, int16_t* x, int16_t* y, uint8_t* score, int cap, int* n) {
+    if (!h || level < 0 || level >= (int)h->geom.size() || frame < 0 || frame >= h->last_frames || !n) return ORB_ERR_ARG;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const LevelGeom& g = h->geom[level];
+    const int ncell = g.n_cols * g.n_rows;
+    std::vector<int32_t> cc(ncell);
+    ORB_CUDA_TRY(cudaMemcpy(cc.data(), h->d_cell_count + (size_t)frame * h->fl.n_cells + g.cell_base, ncell * 4, cudaMemcpyDeviceToHost));
+    const int64_t lvl_entries = (level + 1 < (int)h->geom.size() ? h->geom[level + 1].cand_off : h->fl.cand_entries) - g.cand_off;
+    std::vector<uint32_t> buf(lvl_entries);
+    ORB_CUDA_TRY(cudaMemcpy(buf.data(), h->d_cand + (size_t)frame * h->fl.cand_entries + g.cand_off, lvl_entries * 4, cudaMemcpyDeviceToHost));
+    int k = 0;
+    for (int c = 0; c < ncell; c++) {
+        const uint32_t* s = buf.data() + h->cells[g.cell_base + c].slot_off;
+        for (int i = 0; i < cc[c]; i++, k++) {
+            if (k < cap) { x[k] = (int16_t)(s[i] & 0xfff); y[k] = (int16_t)((s[i] >> 12) & 0xfff); score[k] = (uint8_t)(s[i] >> 24); }
+        }
+    }
+    *n = k;
+    return ORB_OK;
+}
+
+int orbx_distribute_octtree(const int16_t* x, const int16_t* y, const uint8_t* score, int n, int min_x, int max_x, int min_y,
+                            int max_y, int n_features, int32_t* out_index, int cap, int* n_out, int device) {
+    if (!n_out || n < 0 || (n > 0 && (!x || !y || !score))) return ORB_ERR_ARG;
+    *n_out = 0;
+    if (n == 0) return ORB_OK;
+    const int width = max_x - min_x, height = max_y - min_y;
+    if (width <= 0 || height <= 0 || width > 4095 || height > 4095 || n >= (1 << 24)) return ORB_ERR_ARG;
+    const int n_ini = (int)roundf((float)width / height);
+    if (n_ini < 1) { set_error("zero quadtree roots"); return ORB_ERR_ARG; }
+    const float h_x = (float)width / n_ini;
+    const int kp_cap = std::max(n_features + 3, 4 * n_ini);
+    const int node_cap = (int)align_up(kp_cap + 4, 32);
+    if (node_cap > 60000) return ORB_ERR_ARG;
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    std::vector<uint32_t> packed(n);
+    for (int i = 0; i < n; i++) packed[i] = (uint32_t)(x[i] & 0xfff) | ((uint32_t)(y[i] & 0xfff) << 12) | ((uint32_t)score[i] << 24);
+    uint32_t *d_kp = nullptr, *d_sel = nullptr; uint16_t* d_node = nullptr; int32_t *d_cnt = nullptr, *d_idx = nullptr;
+    int rc = ORB_OK;
+    std::vector<int32_t> sel(kp_cap);
+    int32_t cnt = 0;
+    do {
+        if (!cuda_ok(cudaMalloc((void**)&d_kp, (size_t)n * 4), "cudaMalloc") || !cuda_ok(cudaMalloc((void**)&d_sel, (size_t)kp_cap * 4), "cudaMalloc") ||
+            !cuda_ok(cudaMalloc((void**)&d_node, (size_t)n * 2), "cudaMalloc") || !cuda_ok(cudaMalloc((void**)&d_cnt, 4), "cudaMalloc") ||
+            !cuda_ok(cudaMalloc((void**)&d_idx, (size_t)kp_cap * 4), "cudaMalloc")) { rc = ORB_ERR_CUDA; break; }
+        if (!cuda_ok(cudaMemcpy(d_kp, packed.data(), (size_t)n * 4, cudaMemcpyHostToDevice), "cudaMemcpy")) { rc = ORB_ERR_CUDA; break; }
+        if (launch_octree_single(d_kp, n, width, height, n_features, n_ini, h_x, d_idx, d_node, d_sel, d_cnt, kp_cap, node_cap, 0) < 0) { rc = ORB_ERR_CUDA; break; }
+        if (!cuda_ok(cudaDeviceSynchronize(), "octree kernel")) { rc = ORB_ERR_CUDA; break; }
+        if (!cuda_ok(cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost), "cudaMemcpy") ||
+            !cuda_ok(cudaMemcpy(sel.data(), d_idx, (size_t)kp_cap * 4, cudaMemcpyDeviceToHost), "cudaMemcpy")) { rc = ORB_ERR_CUDA; break; }
+    } while (0);
+    cudaFree(d_kp); cudaFree(d_sel); cudaFree(d_node); cudaFree(d_cnt); cudaFree(d_idx);
+    if (rc) return rc;
+    *n_out = cnt;
+    for (int i = 0; i < cnt && i < cap; i++) out_index[i] = sel[i];
+    return cnt > cap ? ORB_ERR_CAPACITY : ORB_OK;
+}
+
+}  // extern "C"
+
+// Internal (not in orbcuda.h): device views of a handle's last extraction for orbm_stereo_matches.
+extern "C" int orbx_internal_view(orbx_handle_t h, const uint8_t** d_pyr, const orbcuda::LevelGeom** d_geom,
+                                  const orbcuda::LevelGeom** h_geom, orbcuda::FrameLayout* fl, int* device,
+                                  const float** sf, const float** isf) {
+    if (!h || h->last_frames < 1) return ORB_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) return ORB_ERR_CUDA;
+    *d_pyr = h->d_pyr; *d_geom = h->d_geom; *h_geom = h->geom.data(); *fl = h->fl; *device = h->device;
+    *sf = h->sf.data(); *isf = h->isf.data();
+    return ORB_OK;
+}

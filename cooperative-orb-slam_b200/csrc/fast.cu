@@ -1,0 +1,241 @@
+// fast.cu -- K3: FAST-9/16 detection with the reference's per-cell semantics
+// (replaces the cell loop of ORBextractor::ComputeKeyPointsOctTree, R21/src/ORBextractor.cc:765-829,
+// i.e. cv::FAST(cell, iniThFAST, nms) with the minThFAST retry on empty cells).
+//
+// Two kernels:
+//   fast_score_kernel  dense per-pixel corner score at minThFAST over [19,W-19)x[19,H-19) of every
+//                      level (the union of all cell interiors).  score = cornerScore<16>() =
+//                      (max over the 16 arcs of 9 of max(min(I_p - I_k), min(I_k - I_p))) - 1 where that
+//                      maximum exceeds the threshold, else 0.  FAST(th=20) == {FAST(th=7): score >= 20}
+//                       so one map serves both thresholds.
+//   fast_cell_kernel   one warp per cell: strict 3x3 non-max suppression that ignores neighbours
+//                      outside the cell interior (cv::FAST is called on the cell sub-image), per-cell
+//                      iniTh -> minTh fallback, ordered compaction (raster inside the cell).
+#include "internal.h"
+
+namespace orbcuda {
+
+constexpr int kFastRows = 14;   // rows per strip (two 7-row register rotations)
+
+__device__ __forceinline__ uint32_t fun16(uint32_t lo, uint32_t hi) { return __funnelshift_r(lo, hi, 16); }
+__device__ __forceinline__ uint32_t mn3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t mx3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+
+// One image row around a 4-pixel group at x0 as 16-bit pairs:
+//   a0=(p[x0-4],p[x0-2]) a1=(p[x0-3],p[x0-1]) b0=(p[x0],p[x0+2]) b1=(p[x0+1],p[x0+3])
+//   c0=(p[x0+4],p[x0+6]) c1=(p[x0+5],p[x0+7])
+struct Row6 { uint32_t a0, a1, b0, b1, c0, c1; };
+
+__device__ __forceinline__ Row6 load_row6(const uint8_t* p) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    Row6 r;
+    r.a0 = w0 & 0x00ff00ffu; r.a1 = (w0 >> 8) & 0x00ff00ffu;
+    r.b0 = w1 & 0x00ff00ffu; r.b1 = (w1 >> 8) & 0x00ff00ffu;
+    r.c0 = w2 & 0x00ff00ffu; r.c1 = (w2 >> 8) & 0x00ff00ffu;
+    return r;
+}
+// E<t>(row) = (p[x0+t], p[x0+t+2])
+__device__ __forceinline__ uint32_t Em3(const Row6& r) { return r.a1; }
+__device__ __forceinline__ uint32_t Em2(const Row6& r) { return fun16(r.a0, r.b0); }
+__device__ __forceinline__ uint32_t Em1(const Row6& r) { return fun16(r.a1, r.b1); }
+__device__ __forceinline__ uint32_t E0(const Row6& r) { return r.b0; }
+__device__ __forceinline__ uint32_t E1(const Row6& r) { return r.b1; }
+__device__ __forceinline__ uint32_t E2(const Row6& r) { return fun16(r.b0, r.c0); }
+__device__ __forceinline__ uint32_t E3(const Row6& r) { return fun16(r.b1, r.c1); }
+__device__ __forceinline__ uint32_t E4(const Row6& r) { return r.c0; }
+
+// max over the 16 circular 9-arcs of min(arc), and min over them of max(arc), on two pixels at once
+__device__ __forceinline__ void arc_extrema(const uint32_t (&p)[16], uint32_t& max_of_min, uint32_t& min_of_max) {
+    uint32_t lo3[16], hi3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        lo3[k] = mn3(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+        hi3[k] = mx3(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+    }
+    uint32_t lo9[16], hi9[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        lo9[k] = mn3(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        hi9[k] = mx3(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    }
+    uint32_t a = mx3(mx3(lo9[0], lo9[1], lo9[2]), mx3(lo9[3], lo9[4], lo9[5]), mx3(lo9[6], lo9[7], lo9[8]));
+    uint32_t b = mx3(mx3(lo9[9], lo9[10], lo9[11]), mx3(lo9[12], lo9[13], lo9[14]), lo9[15]);
+    max_of_min = __vmaxs2(a, b);
+    a = mn3(mn3(hi9[0], hi9[1], hi9[2]), mn3(hi9[3], hi9[4], hi9[5]), mn3(hi9[6], hi9[7], hi9[8]));
+    b = mn3(mn3(hi9[9], hi9[10], hi9[11]), mn3(hi9[12], hi9[13], hi9[14]), hi9[15]);
+    min_of_max = __vmins2(a, b);
+}
+
+// scores of the 4 pixels x0..x0+3 of the centre row r[3] (window rows r[0..6] = y-3..y+3), packed u8x4
+__device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
+    // circle (dx,dy), OpenCV order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+    const uint32_t e2_5 = E2(r[5]), em1_5 = Em1(r[5]), e2_1 = E2(r[1]), em1_1 = Em1(r[1]);
+    const uint32_t em1_6 = Em1(r[6]), e2_6 = E2(r[6]), em1_0 = Em1(r[0]), e2_0 = E2(r[0]);
+    const uint32_t e3_4 = E3(r[4]), e3_3 = E3(r[3]), e3_2 = E3(r[2]);
+    const uint32_t em2_4 = Em2(r[4]), em2_3 = Em2(r[3]), em2_2 = Em2(r[2]);
+    uint32_t P[16], Q[16];
+    // pixels (x0, x0+2)
+    P[0] = E0(r[6]);  P[1] = E1(r[6]);  P[2] = e2_5;       P[3] = e3_4;
+    P[4] = e3_3;      P[5] = e3_2;      P[6] = e2_1;       P[7] = E1(r[0]);
+    P[8] = E0(r[0]);  P[9] = em1_0;     P[10] = Em2(r[1]); P[11] = Em3(r[2]);
+    P[12] = Em3(r[3]); P[13] = Em3(r[4]); P[14] = Em2(r[5]); P[15] = em1_6;
+    // pixels (x0+1, x0+3): same offsets shifted by one column
+    Q[0] = E1(r[6]);  Q[1] = e2_6;      Q[2] = E3(r[5]);   Q[3] = E4(r[4]);
+    Q[4] = E4(r[3]);  Q[5] = E4(r[2]);  Q[6] = E3(r[1]);   Q[7] = e2_0;
+    Q[8] = E1(r[0]);  Q[9] = E0(r[0]);  Q[10] = em1_1;     Q[11] = em2_2;
+    Q[12] = em2_3;    Q[13] = em2_4;    Q[14] = em1_5;     Q[15] = E0(r[6]);
+    uint32_t amaxP, bminP, amaxQ, bminQ;
+    arc_extrema(P, amaxP, bminP);
+    arc_extrema(Q, amaxQ, bminQ);
+    const uint32_t cP = E0(r[3]), cQ = E1(r[3]);
+    // best = max( c - min_arcs(max_arc), max_arcs(min_arc) - c )   (per 16-bit lane, signed)
+    const uint32_t bestP = __vmaxs2(__vsub2(cP, bminP), __vsub2(amaxP, cP));
+    const uint32_t bestQ = __vmaxs2(__vsub2(cQ, bminQ), __vsub2(amaxQ, cQ));
+    const int b0 = (int)(short)(bestP & 0xffffu), b2 = (int)bestP >> 16;
+    const int b1 = (int)(short)(bestQ & 0xffffu), b3 = (int)bestQ >> 16;
+    const uint32_t s0 = b0 > th ? b0 - 1 : 0, s1 = b1 > th ? b1 - 1 : 0;
+    const uint32_t s2 = b2 > th ? b2 - 1 : 0, s3 = b3 > th ? b3 - 1 : 0;
+    return s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+}
+
+__global__ void __launch_bounds__(128) fast_score_kernel(const uint8_t* __restrict__ pyr, int64_t pyr_frame_bytes,
+                                                         uint8_t* __restrict__ score, int64_t score_frame_bytes,
+                                                         const LevelGeom* __restrict__ geom, int nlevels,
+                                                         LevelBlocks lb, int th) {
+    int level = 0;
+    while (level + 1 < nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
+    const LevelGeom g = geom[level];
+    // strips: x0 = 16 + 4*sx covers [16, W-19); y0 = 19 + kFastRows*sy covers [19, H-19)
+    const int nsx = (g.w - kEdge - kMinBorder + 3) >> 2;
+    const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
+    const int sy = id / nsx;
+    const int x0 = kMinBorder + 4 * (id - sy * nsx);
+    const int y0 = kEdge + sy * kFastRows;
+    if (y0 >= g.h - kEdge) return;
+    const uint8_t* src = pyr + (size_t)blockIdx.y * pyr_frame_bytes + g.plane_off + (size_t)kEdge * g.pitch + kXPad + (x0 - 4);
+    uint8_t* dst = score + (size_t)blockIdx.y * score_frame_bytes + g.splane_off + x0;
+    // byte mask of the columns inside [19, W-19)
+    uint32_t colmask = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (x0 + b >= kEdge && x0 + b < g.w - kEdge) colmask |= 0xffu << (8 * b);
+
+    Row6 r[7];
+#pragma unroll
+    for (int k = 0; k < 6; k++) r[k] = load_row6(src + (ptrdiff_t)(y0 - 3 + k) * g.pitch);
+#pragma unroll
+    for (int j = 0; j < kFastRows; j++) {
+        const int y = y0 + j;
+        r[6] = load_row6(src + (ptrdiff_t)(y + 3) * g.pitch);
+        const uint32_t s4 = fast_score4(r, th) & colmask;
+        if (y < g.h - kEdge) *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.spitch) = s4;
+#pragma unroll
+        for (int k = 0; k < 6; k++) r[k] = r[k + 1];
+    }
+}
+
+int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, int min_th,
+                      cudaStream_t s) {
+    LevelBlocks lb;
+    int total = 0;
+    const int threads = 128;
+    for (int l = 0; l < fl.nlevels; l++) {
+        lb.start[l] = total;
+        const int nsx = (hg[l].w - kEdge - kMinBorder + 3) / 4;
+        const int nsy = (hg[l].h - 2 * kEdge + kFastRows - 1) / kFastRows;
+        total += (nsx * nsy + threads - 1) / threads;
+    }
+    for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
+    fast_score_kernel<<<dim3(total, n_frames), threads, 0, s>>>(d.pyr, fl.pyr_bytes, d.score, fl.splane_bytes, d.geom,
+                                                                fl.nlevels, lb, min_th);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-cell NMS + threshold fallback + ordered compaction.  One warp per cell.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool nms_keep(const uint8_t* __restrict__ sc, int pitch, int x, int y, int s, int x0, int y0,
+                                         int x1, int y1) {
+    bool keep = true;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+        const int ny = y + dy;
+        if (ny < y0 || ny >= y1) continue;   // outside the cell interior counts as 0 (< s)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+            if (dx == 0 && dy == 0) continue;
+            const int nx = x + dx;
+            if (nx < x0 || nx >= x1) continue;
+            keep = keep && (s > (int)sc[(size_t)ny * pitch + nx]);
+        }
+    }
+    return keep;
+}
+
+__global__ void __launch_bounds__(256) fast_cell_kernel(const uint8_t* __restrict__ score, int64_t score_frame_bytes,
+                                                        uint32_t* __restrict__ cand, int64_t cand_frame_entries,
+                                                        int32_t* __restrict__ cell_count, int n_cells,
+                                                        const LevelGeom* __restrict__ geom, int nlevels,
+                                                        const CellInfo* __restrict__ cells, int ini_th) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_cells) return;
+    const int frame = blockIdx.y;
+    const CellInfo c = cells[warp];
+    int level = 0;
+    while (level + 1 < nlevels && warp >= geom[level + 1].cell_base) level++;
+    const int pitch = geom[level].spitch;
+    const uint8_t* sc = score + (size_t)frame * score_frame_bytes + geom[level].splane_off;
+    uint32_t* out = cand + (size_t)frame * cand_frame_entries + geom[level].cand_off + c.slot_off;
+    const int iw = c.x1 - c.x0, ih = c.y1 - c.y0;
+    const int npx = iw > 0 && ih > 0 ? iw * ih : 0;
+    const uint32_t magic = iw > 0 ? ((1u << 20) + iw - 1) / iw : 0;   // idx / iw == (idx*magic)>>20 for idx < 4096
+
+    // pass 1: does any NMS survivor reach iniThFAST?
+    bool any_hi = false;
+    for (int base = 0; base < npx; base += 32) {
+        const int idx = base + lane;
+        bool hi = false;
+        if (idx < npx) {
+            const int ry = (int)(((uint32_t)idx * magic) >> 20);
+            const int x = c.x0 + idx - ry * iw, y = c.y0 + ry;
+            const int s = sc[(size_t)y * pitch + x];
+            if (s >= ini_th) hi = nms_keep(sc, pitch, x, y, s, c.x0, c.y0, c.x1, c.y1);
+        }
+        any_hi = any_hi || __any_sync(0xffffffffu, hi);
+        if (any_hi) break;
+    }
+    const int th = any_hi ? ini_th : 1;   // the score map is already 0 below minThFAST
+    // pass 2: ordered emission
+    int count = 0;
+    for (int base = 0; base < npx; base += 32) {
+        const int idx = base + lane;
+        bool keep = false;
+        uint32_t packed = 0;
+        if (idx < npx) {
+            const int ry = (int)(((uint32_t)idx * magic) >> 20);
+            const int x = c.x0 + idx - ry * iw, y = c.y0 + ry;
+            const int s = sc[(size_t)y * pitch + x];
+            if (s >= th) {
+                keep = nms_keep(sc, pitch, x, y, s, c.x0, c.y0, c.x1, c.y1);
+                packed = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | ((uint32_t)s << 24);
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[count + __popc(m & ((1u << lane) - 1))] = packed;
+        count += __popc(m);
+    }
+    if (lane == 0) cell_count[(size_t)frame * n_cells + warp] = count;
+}
+
+int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, int n_frames, int ini_th, cudaStream_t s) {
+    const int threads = 256;
+    const int blocks = (fl.n_cells * 32 + threads - 1) / threads;
+    fast_cell_kernel<<<dim3(blocks, n_frames), threads, 0, s>>>(d.score, fl.splane_bytes, d.cand, fl.cand_entries,
+                                                                d.cell_count, fl.n_cells, d.geom, fl.nlevels, d.cells,
+                                                                ini_th);
+    return 1;
+}
+
+}  // namespace orbcuda

@@ -1,0 +1,118 @@
+// internal.h -- shared host/device definitions of liborbcuda (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "orbcuda.h"
+
+namespace orbcuda {
+
+constexpr int kEdge = 19;          // EDGE_THRESHOLD (R21 ORBextractor.cc:74)
+constexpr int kXPad = 32;          // interior column origin inside a padded plane (16-B aligned)
+constexpr int kMinBorder = 16;     // EDGE_THRESHOLD-3 (R21 :773)
+constexpr int kMaxLevels = ORB_MAX_LEVELS;
+
+// Geometry of one pyramid level for the current image size.  Lives in device constant-like global
+// memory (one array per handle) and on the host.
+struct LevelGeom {
+    int w, h;               // level size (R21 :1112)
+    int pitch;              // padded plane pitch in bytes; interior pixel (x,y) at (y+19)*pitch + 32 + x
+    int plane_rows;         // h + 38
+    int64_t plane_off;      // byte offset of the padded plane inside one frame's pyramid block
+    int spitch;             // pitch of the un-padded planes (blurred level, score map); origin (0,0)
+    int64_t splane_off;     // byte offset inside one frame's blurred / score block
+    // FAST cell grid (R21 :773-807)
+    int n_cols, n_rows, w_cell, h_cell;
+    int cell_base;          // index of this level's first cell in the per-frame cell table
+    int64_t cand_off;       // offset (in uint32 entries) of this level's candidate slots in a frame
+    // quadtree (R21 :539-545)
+    int n_feat;             // mnFeaturesPerLevel[level]
+    int n_ini;              // number of root nodes
+    float h_x;              // root width
+    int kp_slot;            // first keypoint slot of this level inside a frame (slot = max(N+3, 4*nIni))
+    int kp_cap;             // slot size
+    // resize tables for producing this level from level-1 (offsets into the table buffers)
+    int xtab_off, ytab_off;
+    float scale;            // mvScaleFactor[level]
+    float patch_size;       // (float)(int)(31*scale)
+};
+
+struct CellInfo {           // one FAST cell; interior = [x0,x1) x [y0,y1) in level coordinates
+    int16_t x0, y0, x1, y1;
+    int32_t slot_off;       // offset (uint32 entries) of the cell's candidate slot inside the level
+};
+
+struct ResizeTap {          // one destination column/row of cv::resize INTER_LINEAR
+    int16_t ofs;            // source index
+    int16_t c0, c1;         // 11-bit fixed-point weights
+    int16_t pad;
+};
+
+struct FrameLayout {        // sizes of the per-frame device blocks
+    int nlevels;
+    int width, height;
+    int in_pitch;           // device input image pitch
+    int64_t pyr_bytes;      // padded pyramid block
+    int64_t splane_bytes;   // blurred block == score block
+    int n_cells;            // cells per frame
+    int64_t cand_entries;   // candidate slot entries (uint32) per frame
+    int kp_cap;             // keypoint slots per frame
+    int node_cap;           // quadtree node capacity
+};
+
+// flattened (level, block) grids: blocks [start[l], start[l+1]) belong to level l
+struct LevelBlocks {
+    int start[kMaxLevels + 1];
+};
+
+// ---- kernel launchers (each returns the number of kernels it launched) ----
+struct DevPtrs {
+    const uint8_t* in;          // [B][height][in_pitch]
+    uint8_t* pyr;               // [B][pyr_bytes]
+    uint8_t* blur;              // [B][splane_bytes]
+    uint8_t* score;             // [B][splane_bytes]
+    uint32_t* cand;             // [B][cand_entries]  packed x | y<<12 | score<<24 (relative to 16,16)
+    int32_t* cell_count;        // [B][n_cells]
+    uint32_t* oct_scratch;      // [B][cand_entries] packed candidates in list order (quadtree input)
+    uint16_t* oct_node;         // [B][cand_entries] node id per candidate
+    uint32_t* sel;              // [B][kp_cap] selected candidate (packed) per slot
+    int32_t* level_count;       // [B][kMaxLevels] keypoints per level
+    const LevelGeom* geom;      // [nlevels]
+    const CellInfo* cells;      // [n_cells]
+    const ResizeTap* xtab;
+    const ResizeTap* ytab;
+};
+
+int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, size_t in_frame_stride,
+                   cudaStream_t s);
+int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, int min_th,
+                      cudaStream_t s);
+int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, cudaStream_t s);
+int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, int n_frames, int ini_th, cudaStream_t s);
+int launch_octree(const DevPtrs& d, const FrameLayout& fl, int n_frames, cudaStream_t s);
+int launch_describe(const DevPtrs& d, const FrameLayout& fl, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
+                    int32_t* d_counts, int cap, cudaStream_t s);
+
+// stand-alone quadtree on packed candidates already in device memory
+int launch_octree_single(const uint32_t* d_cand, int n, int width, int height, int n_feat, int n_ini, float h_x,
+                         int32_t* d_sel_idx, uint16_t* d_node, uint32_t* d_sel, int32_t* d_count, int kp_cap,
+                         int node_cap, cudaStream_t s);
+size_t octree_smem_bytes(int node_cap);
+
+// matcher
+int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out,
+                int variant, cudaStream_t s);
+int launch_merge_top2(const int32_t* d_parts, int parts, int nq, int32_t* d_out, cudaStream_t s);
+void host_merge_top2(const int32_t* parts, int nparts, int nq, int32_t* out);
+
+void set_error(const char* fmt, ...);
+bool cuda_ok(cudaError_t e, const char* what);
+
+}  // namespace orbcuda
+
+#define ORB_CUDA_TRY(expr)                                            \
+    do {                                                              \
+        if (!::orbcuda::cuda_ok((expr), #expr)) return ORB_ERR_CUDA;  \
+    } while (0)

@@ -1,0 +1,97 @@
+// matcher.cu -- orbm_* C ABI: host wrappers around the matching kernels.
+// Mirrors ORB_SLAM2::ORBmatcher (R21/include/ORBmatcher.h:37-102, R21/src/ORBmatcher.cc).
+#include "internal.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+using namespace orbcuda;
+
+extern "C" {
+
+// ORBmatcher::DescriptorDistance R21/src/ORBmatcher.cc:1647-1663 -- any exact 256-bit popcount is bit-identical
+int orb_hamming256(const void* a, const void* b) {
+    uint64_t x[4], y[4];
+    memcpy(x, a, 32);
+    memcpy(y, b, 32);
+    return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) + __builtin_popcountll(x[2] ^ y[2]) +
+           __builtin_popcountll(x[3] ^ y[3]);
+}
+
+int orbm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out,
+                     int variant, void* stream) {
+    if (!d_q || nq < 1 || !d_out || nm < 0 || (nm > 0 && !d_m)) { set_error("orbm_knn2_device: bad arguments"); return ORB_ERR_ARG; }
+    if (variant != 0) { set_error("orbm_knn2: variant %d is not available in this build", variant); return ORB_ERR_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_q) & 15) || (reinterpret_cast<uintptr_t>(d_m) & 15)) {
+        set_error("orbm_knn2_device: descriptor arrays must be 16-byte aligned");
+        return ORB_ERR_ARG;
+    }
+    if (launch_knn2(d_q, nq, d_m, nm, index_base, d_out, variant, (cudaStream_t)stream) < 0) {
+        cuda_ok(cudaGetLastError(), "knn2 launch");
+        return ORB_ERR_CUDA;
+    }
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbm_merge_top2_device(const int32_t* d_parts, int parts, int nq, int32_t* d_out, void* stream) {
+    if (!d_parts || parts < 1 || nq < 1 || !d_out) return ORB_ERR_ARG;
+    launch_merge_top2(d_parts, parts, nq, d_out, (cudaStream_t)stream);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbm_merge_top2_host(const int32_t* parts_rec, int parts, int nq, int32_t* out) {
+    if (!parts_rec || parts < 1 || nq < 0 || !out) return ORB_ERR_ARG;
+    host_merge_top2(parts_rec, parts, nq, out);
+    return ORB_OK;
+}
+
+int orbm_ratio_test_host(const int32_t* rec, int nq, float ratio, int th, int strict, int32_t* out_match) {
+    if (!rec || !out_match) return ORB_ERR_ARG;
+    for (int i = 0; i < nq; i++) {
+        const int d1 = rec[4 * i], i1 = rec[4 * i + 1], d2 = rec[4 * i + 2];
+        const bool ok = (strict ? d1 < th : d1 <= th) && (float)d1 < ratio * (float)d2;   // R21 ORBmatcher.cc:228-230 / :598-600
+        out_match[i] = ok ? i1 : -1;
+    }
+    return ORB_OK;
+}
+
+int orbm_knn2(const uint8_t* queries, int nq, const uint8_t* map, int64_t nm, int64_t index_base, int32_t* best_idx,
+              int32_t* best_dist, int32_t* second_dist, int32_t* second_idx, int variant, int device) {
+    if (!queries || nq < 1 || nm < 0 || (nm > 0 && !map) || !best_idx || !best_dist || !second_dist) {
+        set_error("orbm_knn2: bad arguments");
+        return ORB_ERR_ARG;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("orbm_knn2: no usable CUDA device %d (this library has no CPU fallback)", device);
+        return ORB_ERR_CUDA;
+    }
+    uint8_t *d_q = nullptr, *d_m = nullptr; int32_t* d_out = nullptr;
+    std::vector<int32_t> rec((size_t)nq * 4);
+    int rc = ORB_OK;
+    cudaStream_t s = nullptr;
+    do {
+        if (!cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) { rc = ORB_ERR_CUDA; break; }
+        if (!cuda_ok(cudaMalloc((void**)&d_q, (size_t)nq * 32), "cudaMalloc") ||
+            !cuda_ok(cudaMalloc((void**)&d_m, (size_t)std::max<int64_t>(nm, 1) * 32), "cudaMalloc") ||
+            !cuda_ok(cudaMalloc((void**)&d_out, (size_t)nq * 16), "cudaMalloc")) { rc = ORB_ERR_CUDA; break; }
+        if (!cuda_ok(cudaMemcpyAsync(d_q, queries, (size_t)nq * 32, cudaMemcpyHostToDevice, s), "cudaMemcpy")) { rc = ORB_ERR_CUDA; break; }
+        if (nm > 0 && !cuda_ok(cudaMemcpyAsync(d_m, map, (size_t)nm * 32, cudaMemcpyHostToDevice, s), "cudaMemcpy")) { rc = ORB_ERR_CUDA; break; }
+        if ((rc = orbm_knn2_device(d_q, nq, d_m, nm, index_base, d_out, variant, s))) break;
+        if (!cuda_ok(cudaMemcpyAsync(rec.data(), d_out, (size_t)nq * 16, cudaMemcpyDeviceToHost, s), "cudaMemcpy")) { rc = ORB_ERR_CUDA; break; }
+        if (!cuda_ok(cudaStreamSynchronize(s), "knn2 kernel")) { rc = ORB_ERR_CUDA; break; }
+    } while (0);
+    cudaFree(d_q); cudaFree(d_m); cudaFree(d_out);
+    if (s) cudaStreamDestroy(s);
+    if (rc) return rc;
+    for (int i = 0; i < nq; i++) {
+        best_dist[i] = rec[4 * i]; best_idx[i] = rec[4 * i + 1]; second_dist[i] = rec[4 * i + 2];
+        if (second_idx) second_idx[i] = rec[4 * i + 3];
+    }
+    return ORB_OK;
+}
+
+}  // extern "C"

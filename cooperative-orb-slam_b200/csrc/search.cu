@@ -1,0 +1,482 @@
+// search.cu -- K8/K9: the reference's candidate loops on the GPU.
+//   orbm_search_by_bow_kf_f        ORBmatcher::SearchByBoW(KeyFrame*,Frame&,...)      R21/src/ORBmatcher.cc:159-288
+//   orbm_search_by_bow_kf_kf       ORBmatcher::SearchByBoW(KeyFrame*,KeyFrame*,...)   R21/src/ORBmatcher.cc:522-655
+//   orbm_search_for_triangulation  ORBmatcher::SearchForTriangulation               R21/src/ORBmatcher.cc:657-823
+//   orbm_stereo_matches            Frame::ComputeStereoMatches                      R21/src/Frame.cc:471-645
+// The vocabulary-node walk, rotation histogram (ComputeThreeMaxima :1601-1642) and the stereo median cut
+// are tiny and stay on the host; all Hamming / SAD work runs in the kernels below.  SearchByBoW's greedy
+// "skip features already matched" is node-local (a feature index lives in exactly one FeatureVector
+// node), so nodes run in parallel -- one warp each -- and only the walk inside a node is sequential.
+#include "internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+namespace orbcuda {
+
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // R21/src/ORBmatcher.cc:37-39
+
+struct NodePair { int a0, a1, b0, b1; };
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4* __restrict__ b) {
+    const uint4 b0 = b[0], b1 = b[1];
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+__device__ __forceinline__ unsigned warp_min(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// One warp per shared vocabulary node.  mode 0: KF -> Frame (accept d1 <= TH_LOW, exclusion = matchB >= 0);
+// mode 1: KF -> KF (accept d1 < TH_LOW, both sides need valid map points, exclusion = matched flag).
+__global__ void __launch_bounds__(128) bow_kernel(const uint4* __restrict__ descA, const uint8_t* __restrict__ validA,
+                                                  const int* __restrict__ idxA, const uint4* __restrict__ descB,
+                                                  const uint8_t* __restrict__ validB, const int* __restrict__ idxB,
+                                                  const NodePair* __restrict__ pairs, int n_pairs, float ratio, int mode,
+                                                  volatile int* matchB, int* __restrict__ matchA) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_pairs) return;
+    const NodePair np = pairs[w];
+    for (int p = np.a0; p < np.a1; p++) {
+        const int ia = idxA[p];
+        if (!validA[ia]) continue;
+        const uint4 a0 = descA[2 * (size_t)ia], a1 = descA[2 * (size_t)ia + 1];
+        int d1 = 256, d2 = 256, pos1 = 0xfffff;
+        for (int r = np.b0 + lane; r < np.b1; r += 32) {
+            const int ib = idxB[r];
+            if (matchB[ib] >= 0) continue;
+            if (mode == 1 && !validB[ib]) continue;
+            const int d = hamming256(a0, a1, descB + 2 * (size_t)ib);
+            if (d < d1) { d2 = d1; d1 = d; pos1 = r - np.b0; }
+            else if (d < d2) { d2 = d; }
+        }
+        // warp merge: best = lexicographic min (distance, list position); second counts duplicates
+        const unsigned key = ((unsigned)d1 << 20) | (unsigned)pos1;
+        const unsigned best = warp_min(key);
+        const int second = (int)warp_min((unsigned)(key == best ? d2 : d1));
+        const int bd = (int)(best >> 20);
+        const bool accept = (mode == 0 ? bd <= TH_LOW : bd < TH_LOW) && ((float)bd < __fmul_rn(ratio, (float)second));
+        if (accept && lane == 0) {
+            const int ib = idxB[np.b0 + (int)(best & 0xfffff)];
+            matchB[ib] = ia;
+            if (matchA) matchA[ia] = ib;
+        }
+        __syncwarp();
+    }
+}
+
+struct TriFeat { float x, y, angle; int octave; float u_right; int has_mp; };
+struct TriItem { int ia, b0, b1; };
+
+// One warp per unmatched key point of KF1: scan its vocabulary node in KF2 (rows are independent because the
+// reference never sets vbMatched2, :677,:725).  Winner = qualifying candidate of minimal distance, last on ties.
+__global__ void __launch_bounds__(128) triangulation_kernel(const uint4* __restrict__ desc1, const TriFeat* __restrict__ f1,
+                                                            const uint4* __restrict__ desc2, const TriFeat* __restrict__ f2,
+                                                            const int* __restrict__ idx2, const TriItem* __restrict__ items,
+                                                            int n_items, const float* __restrict__ F, float ex, float ey,
+                                                            const float* __restrict__ sf2, const float* __restrict__ sig2,
+                                                            int only_stereo, int* __restrict__ match12) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_items) return;
+    const TriItem it = items[w];
+    const TriFeat k1 = f1[it.ia];
+    const bool stereo1 = k1.u_right >= 0;
+    const uint4 a0 = desc1[2 * (size_t)it.ia], a1 = desc1[2 * (size_t)it.ia + 1];
+    // epipolar line l = x1' F12 (CheckDistEpipolarLine :140-157)
+    const float la = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, F[0]), __fmul_rn(k1.y, F[3])), F[6]);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, F[1]), __fmul_rn(k1.y, F[4])), F[7]);
+    const float lc = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, F[2]), __fmul_rn(k1.y, F[5])), F[8]);
+    const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    unsigned key = 0xffffffffu;
+    for (int r = it.b0 + lane; r < it.b1; r += 32) {
+        const int ib = idx2[r];
+        const TriFeat k2 = f2[ib];
+        if (k2.has_mp) continue;
+        const bool stereo2 = k2.u_right >= 0;
+        if (only_stereo && !stereo2) continue;
+        const int d = hamming256(a0, a1, desc2 + 2 * (size_t)ib);
+        if (d > TH_LOW) continue;
+        if (!stereo1 && !stereo2) {
+            const float dx = __fsub_rn(ex, k2.x), dy = __fsub_rn(ey, k2.y);
+            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, sf2[k2.octave])) continue;
+        }
+        const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, k2.x), __fmul_rn(lb, k2.y)), lc);
+        if (den == 0) continue;
+        const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+        if (!((double)dsqr < 3.84 * (double)sig2[k2.octave])) continue;
+        key = min(key, ((unsigned)d << 20) | (0xfffffu - (unsigned)(r - it.b0)));
+    }
+    key = warp_min(key);
+    if (lane == 0) match12[it.ia] = key == 0xffffffffu ? -1 : idx2[it.b0 + (int)(0xfffffu - (key & 0xfffffu))];
+}
+
+struct StereoOut { float u_right, depth; int sad; int ok; };
+
+// One warp per left key point (Frame::ComputeStereoMatches :504-628).
+__global__ void __launch_bounds__(128) stereo_kernel(const orb_keypoint_t* __restrict__ kl, const uint4* __restrict__ dl, int nl,
+                                                     const orb_keypoint_t* __restrict__ kr, const uint4* __restrict__ dr, int nr,
+                                                     const float* __restrict__ sfs, const float* __restrict__ isfs,
+                                                     const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
+                                                     const LevelGeom* __restrict__ geom, int n_rows, float mbf, float max_d,
+                                                     StereoOut* __restrict__ out) {
+    const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (iL >= nl) return;
+    StereoOut o = {-1.f, -1.f, 0, 0};
+    const orb_keypoint_t kpL = kl[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    const float minU = __fsub_rn(uL, max_d), maxU = uL;
+    bool alive = row >= 0 && row < n_rows && !(maxU < 0);
+    unsigned best = 0xffffffffu;
+    if (alive) {
+        const uint4 a0 = dl[2 * (size_t)iL], a1 = dl[2 * (size_t)iL + 1];
+        for (int iR = lane; iR < nr; iR += 32) {
+            const orb_keypoint_t kpR = kr[iR];
+            // membership of iR in vRowIndices[row] (:481-498)
+            const float r = __fmul_rn(2.0f, sfs[kpR.octave]);
+            const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
+            if (row < minr || row > maxr) continue;
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            if (!(kpR.x >= minU && kpR.x <= maxU)) continue;
+            const int d = hamming256(a0, a1, dr + 2 * (size_t)iR);
+            if (d < TH_HIGH) best = min(best, ((unsigned)d << 20) | (unsigned)iR);   // first strict minimum
+        }
+        best = warp_min(best);
+        alive = best != 0xffffffffu && (int)(best >> 20) < (TH_HIGH + TH_LOW) / 2;
+    }
+    if (alive) {
+        const int bestIdxR = (int)(best & 0xfffff);
+        const float uR0 = kr[bestIdxR].x;
+        const float scaleFactor = isfs[levelL];
+        const int cu = (int)roundf(__fmul_rn(kpL.x, scaleFactor));
+        const int cv = (int)roundf(__fmul_rn(kpL.y, scaleFactor));
+        const int cr0 = (int)roundf(__fmul_rn(uR0, scaleFactor));
+        const LevelGeom g = geom[levelL];
+        const int w = 5, L = 5;
+        if (!(cr0 < 0 || cr0 + L + w + 1 >= g.w)) {   // iniu < 0 || endu >= cols  (:579-582)
+            const uint8_t* PL = pyrL + g.plane_off + (size_t)kEdge * g.pitch + kXPad;
+            const uint8_t* PR = pyrR + g.plane_off + (size_t)kEdge * g.pitch + kXPad;
+            const int cL = PL[(ptrdiff_t)cv * g.pitch + cu];
+            int sads[11];
+#pragma unroll
+            for (int s = 0; s < 11; s++) {
+                const int incR = s - L;
+                const int cR = PR[(ptrdiff_t)cv * g.pitch + cr0 + incR];
+                int acc = 0;
+                for (int t = lane; t < 121; t += 32) {
+                    const int dy = t / 11 - w, dx = t % 11 - w;
+                    const int a = (int)PL[(ptrdiff_t)(cv + dy) * g.pitch + cu + dx] - cL;
+                    const int b = (int)PR[(ptrdiff_t)(cv + dy) * g.pitch + cr0 + incR + dx] - cR;
+                    acc += abs(a - b);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                sads[s] = acc;
+            }
+            int bestSad = 0x7fffffff, bestinc = 0;
+#pragma unroll
+            for (int s = 0; s < 11; s++)
+                if (sads[s] < bestSad) { bestSad = sads[s]; bestinc = s - L; }
+            if (bestinc != -L && bestinc != L) {
+                float d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+                for (int s = 1; s < 10; s++)
+                    if (s - L == bestinc) { d1 = (float)sads[s - 1]; d2 = (float)sads[s]; d3 = (float)sads[s + 1]; }
+                const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+                if (!(deltaR < -1 || deltaR > 1)) {
+                    float bestuR = __fmul_rn(sfs[levelL], __fadd_rn(__fadd_rn((float)cr0, (float)bestinc), deltaR));
+                    float disparity = __fsub_rn(uL, bestuR);
+                    if (disparity >= 0 && disparity < max_d) {
+                        if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                        o.depth = __fdiv_rn(mbf, disparity);
+                        o.u_right = bestuR;
+                        o.sad = bestSad;
+                        o.ok = 1;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) out[iL] = o;
+}
+
+// ---- host helpers -----------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return (T*)p; }
+    bool upload(const void* src, size_t bytes, cudaStream_t s) {
+        if (!cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc")) return false;
+        if (bytes && !cuda_ok(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync")) return false;
+        return true;
+    }
+    bool alloc(size_t bytes) { return cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc"); }
+};
+
+static void shared_nodes(const orbm_featvec_t* a, const orbm_featvec_t* b, std::vector<NodePair>& out) {
+    int i = 0, j = 0;   // merge walk of two sorted maps (R21 ORBmatcher.cc:175-263)
+    while (i < a->n_nodes && j < b->n_nodes) {
+        if (a->node_ids[i] == b->node_ids[j]) {
+            out.push_back(NodePair{a->ptr[i], a->ptr[i + 1], b->ptr[j], b->ptr[j + 1]});
+            i++; j++;
+        } else if (a->node_ids[i] < b->node_ids[j]) i++;
+        else j++;
+    }
+}
+
+// ComputeThreeMaxima R21 :1601-1642 on bin counts
+static void three_maxima(const int* cnt, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = cnt[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+static inline int rot_bin(float a1, float a2) {   // R21 :236-243 (factor = 1.0f/HISTO_LENGTH as written there)
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+static int run_bow(int mode, const uint8_t* dA, const uint8_t* vA, int nA, const orbm_featvec_t* fvA, const uint8_t* dB,
+                   const uint8_t* vB, int nB, const orbm_featvec_t* fvB, float ratio, std::vector<int>& matchB,
+                   std::vector<int>& matchA, int device) {
+    if (!dA || !vA || !fvA || !dB || !fvB || nA < 0 || nB < 0 || (mode == 1 && !vB)) { set_error("SearchByBoW: bad arguments"); return ORB_ERR_ARG; }
+    if (nB >= (1 << 20)) { set_error("SearchByBoW: too many features"); return ORB_ERR_ARG; }
+    matchB.assign(nB, -1);
+    matchA.assign(nA, -1);
+    std::vector<NodePair> pairs;
+    shared_nodes(fvA, fvB, pairs);
+    if (pairs.empty() || nA == 0 || nB == 0) return ORB_OK;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no usable CUDA device %d (no CPU fallback)", device); return ORB_ERR_CUDA; }
+    cudaStream_t s = nullptr;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return ORB_ERR_CUDA;
+    int rc = ORB_OK;
+    {
+        DevBuf bdA, bvA, biA, bdB, bvB, biB, bpairs, bmB, bmA;
+        const int nia = fvA->ptr[fvA->n_nodes], nib = fvB->ptr[fvB->n_nodes];
+        const bool ok = bdA.upload(dA, (size_t)nA * 32, s) && bvA.upload(vA, nA, s) && biA.upload(fvA->idx, (size_t)nia * 4, s) &&
+                        bdB.upload(dB, (size_t)nB * 32, s) && bvB.upload(vB ? vB : vA, vB ? nB : 0, s) && biB.upload(fvB->idx, (size_t)nib * 4, s) &&
+                        bpairs.upload(pairs.data(), pairs.size() * sizeof(NodePair), s) && bmB.upload(matchB.data(), (size_t)nB * 4, s) &&
+                        bmA.upload(matchA.data(), (size_t)nA * 4, s);
+        if (!ok) rc = ORB_ERR_CUDA;
+        if (!rc) {
+            const int np = (int)pairs.size();
+            bow_kernel<<<(np * 32 + 127) / 128, 128, 0, s>>>(bdA.as<uint4>(), bvA.as<uint8_t>(), biA.as<int>(), bdB.as<uint4>(),
+                                                           bvB.as<uint8_t>(), biB.as<int>(), bpairs.as<NodePair>(), np, ratio, mode,
+                                                           bmB.as<int>(), bmA.as<int>());
+            if (!cuda_ok(cudaGetLastError(), "bow_kernel") ||
+                !cuda_ok(cudaMemcpyAsync(matchB.data(), bmB.p, (size_t)nB * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
+                !cuda_ok(cudaMemcpyAsync(matchA.data(), bmA.p, (size_t)nA * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
+                !cuda_ok(cudaStreamSynchronize(s), "bow_kernel"))
+                rc = ORB_ERR_CUDA;
+        }
+    }
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+}  // namespace orbcuda
+
+using namespace orbcuda;
+
+// accessor implemented in extractor.cu
+extern "C" int orbx_internal_view(orbx_handle_t h, const uint8_t** d_pyr, const orbcuda::LevelGeom** d_geom,
+                                  const orbcuda::LevelGeom** h_geom, orbcuda::FrameLayout* fl, int* device,
+                                  const float** sf, const float** isf);
+
+extern "C" {
+
+int orbm_search_by_bow_kf_f(const uint8_t* desc_kf, const float* angle_kf, const uint8_t* kf_valid, int n_kf,
+                            const orbm_featvec_t* fv_kf, const uint8_t* desc_f, const float* angle_f, int n_f,
+                            const orbm_featvec_t* fv_f, float nnratio, int check_ori, int32_t* out_match_f, int* n_matches,
+                            int device) {
+    if (!out_match_f || !n_matches || (check_ori && (!angle_kf || !angle_f))) { set_error("SearchByBoW: bad arguments"); return ORB_ERR_ARG; }
+    std::vector<int> mB, mA;
+    const int rc = run_bow(0, desc_kf, kf_valid, n_kf, fv_kf, desc_f, nullptr, n_f, fv_f, nnratio, mB, mA, device);
+    if (rc) return rc;
+    int nmatches = 0;
+    for (int j = 0; j < n_f; j++) nmatches += mB[j] >= 0;
+    if (check_ori) {   // R21 :236-285
+        int cnt[HISTO_LENGTH] = {0};
+        std::vector<int> bin(n_f, -1);
+        for (int j = 0; j < n_f; j++)
+            if (mB[j] >= 0) { bin[j] = rot_bin(angle_kf[mB[j]], angle_f[j]); cnt[bin[j]]++; }
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(cnt, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int j = 0; j < n_f; j++)
+            if (bin[j] >= 0 && bin[j] != ind1 && bin[j] != ind2 && bin[j] != ind3) { mB[j] = -1; nmatches--; }
+    }
+    for (int j = 0; j < n_f; j++) out_match_f[j] = mB[j];
+    *n_matches = nmatches;
+    return ORB_OK;
+}
+
+int orbm_search_by_bow_kf_kf(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                             const orbm_featvec_t* fv1, const uint8_t* desc2, const float* angle2, const uint8_t* valid2,
+                             int n2, const orbm_featvec_t* fv2, float nnratio, int check_ori, int32_t* out_match12,
+                             int* n_matches, int device) {
+    if (!out_match12 || !n_matches || (check_ori && (!angle1 || !angle2))) { set_error("SearchByBoW: bad arguments"); return ORB_ERR_ARG; }
+    std::vector<int> mB, mA;
+    const int rc = run_bow(1, desc1, valid1, n1, fv1, desc2, valid2, n2, fv2, nnratio, mB, mA, device);
+    if (rc) return rc;
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) nmatches += mA[i] >= 0;
+    if (check_ori) {   // R21 :607-653
+        int cnt[HISTO_LENGTH] = {0};
+        std::vector<int> bin(n1, -1);
+        for (int i = 0; i < n1; i++)
+            if (mA[i] >= 0) { bin[i] = rot_bin(angle1[i], angle2[mA[i]]); cnt[bin[i]]++; }
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(cnt, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < n1; i++)
+            if (bin[i] >= 0 && bin[i] != ind1 && bin[i] != ind2 && bin[i] != ind3) { mA[i] = -1; nmatches--; }
+    }
+    for (int i = 0; i < n1; i++) out_match12[i] = mA[i];
+    *n_matches = nmatches;
+    return ORB_OK;
+}
+
+int orbm_search_for_triangulation(const uint8_t* desc1, const orbm_tri_feature_t* f1, int n1, const orbm_featvec_t* fv1,
+                                  const uint8_t* desc2, const orbm_tri_feature_t* f2, int n2, const orbm_featvec_t* fv2,
+                                  const float* F12, float ex, float ey, const float* scale_factors2,
+                                  const float* level_sigma2_2, int only_stereo, int check_ori, int32_t* out_pairs,
+                                  int cap_pairs, int* n_matches, int device) {
+    if (!desc1 || !f1 || !fv1 || !desc2 || !f2 || !fv2 || !F12 || !scale_factors2 || !level_sigma2_2 || !n_matches || n1 < 0 || n2 < 0 ||
+        (cap_pairs > 0 && !out_pairs)) { set_error("SearchForTriangulation: bad arguments"); return ORB_ERR_ARG; }
+    *n_matches = 0;
+    std::vector<NodePair> pairs;
+    shared_nodes(fv1, fv2, pairs);
+    std::vector<TriItem> items;
+    for (const NodePair& p : pairs)
+        for (int q = p.a0; q < p.a1; q++) {
+            const int ia = fv1->idx[q];
+            if (f1[ia].has_mp) continue;                         // :700-702
+            if (only_stereo && !(f1[ia].u_right >= 0)) continue;  // :704-708
+            if (p.b1 - p.b0 >= (1 << 20)) { set_error("node too large"); return ORB_ERR_ARG; }
+            items.push_back(TriItem{ia, p.b0, p.b1});
+        }
+    std::vector<int> m12(n1, -1);
+    if (!items.empty() && n2 > 0) {
+        if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no usable CUDA device %d (no CPU fallback)", device); return ORB_ERR_CUDA; }
+        cudaStream_t s = nullptr;
+        if (!cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return ORB_ERR_CUDA;
+        int rc = ORB_OK;
+        {
+            int max_oct = 0;
+            for (int i = 0; i < n2; i++) max_oct = std::max(max_oct, f2[i].octave);
+            DevBuf bd1, bf1, bd2, bf2, bi2, bit, bF, bsf, bs2, bm;
+            const bool ok = bd1.upload(desc1, (size_t)n1 * 32, s) && bf1.upload(f1, (size_t)n1 * sizeof(TriFeat), s) &&
+                            bd2.upload(desc2, (size_t)n2 * 32, s) && bf2.upload(f2, (size_t)n2 * sizeof(TriFeat), s) &&
+                            bi2.upload(fv2->idx, (size_t)fv2->ptr[fv2->n_nodes] * 4, s) && bit.upload(items.data(), items.size() * sizeof(TriItem), s) &&
+                            bF.upload(F12, 36, s) && bsf.upload(scale_factors2, (size_t)(max_oct + 1) * 4, s) &&
+                            bs2.upload(level_sigma2_2, (size_t)(max_oct + 1) * 4, s) && bm.upload(m12.data(), (size_t)n1 * 4, s);
+            if (!ok) rc = ORB_ERR_CUDA;
+            if (!rc) {
+                const int ni = (int)items.size();
+                triangulation_kernel<<<(ni * 32 + 127) / 128, 128, 0, s>>>(bd1.as<uint4>(), bf1.as<TriFeat>(), bd2.as<uint4>(), bf2.as<TriFeat>(),
+                                                                         bi2.as<int>(), bit.as<TriItem>(), ni, bF.as<float>(), ex, ey,
+                                                                         bsf.as<float>(), bs2.as<float>(), only_stereo, bm.as<int>());
+                if (!cuda_ok(cudaGetLastError(), "triangulation_kernel") ||
+                    !cuda_ok(cudaMemcpyAsync(m12.data(), bm.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
+                    !cuda_ok(cudaStreamSynchronize(s), "triangulation_kernel"))
+                    rc = ORB_ERR_CUDA;
+            }
+        }
+        cudaStreamDestroy(s);
+        if (rc) return rc;
+    }
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) nmatches += m12[i] >= 0;
+    if (check_ori) {   // :775-808
+        int cnt[HISTO_LENGTH] = {0};
+        std::vector<int> bin(n1, -1);
+        for (int i = 0; i < n1; i++)
+            if (m12[i] >= 0) { bin[i] = rot_bin(f1[i].angle, f2[m12[i]].angle); cnt[bin[i]]++; }
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(cnt, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < n1; i++)
+            if (bin[i] >= 0 && bin[i] != ind1 && bin[i] != ind2 && bin[i] != ind3) { m12[i] = -1; nmatches--; }
+    }
+    int np = 0;
+    for (int i = 0; i < n1; i++) {   // :812-820
+        if (m12[i] < 0) continue;
+        if (np < cap_pairs) { out_pairs[2 * np] = i; out_pairs[2 * np + 1] = m12[i]; }
+        np++;
+    }
+    *n_matches = nmatches;
+    return np > cap_pairs ? ORB_ERR_CAPACITY : ORB_OK;
+}
+
+int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t* keys_left, const uint8_t* desc_left,
+                        int n_left, const orb_keypoint_t* keys_right, const uint8_t* desc_right, int n_right, float mbf,
+                        float mb, float* u_right, float* depth, int* n_matches) {
+    if (!hl || !hr || n_left < 0 || n_right < 0 || !u_right || !depth || (n_left && (!keys_left || !desc_left)) ||
+        (n_right && (!keys_right || !desc_right))) { set_error("orbm_stereo_matches: bad arguments"); return ORB_ERR_ARG; }
+    for (int i = 0; i < n_left; i++) { u_right[i] = -1.0f; depth[i] = -1.0f; }   // :473-474
+    if (n_matches) *n_matches = 0;
+    if (n_left == 0 || n_right == 0) return ORB_OK;
+    const uint8_t *pl, *pr; const LevelGeom *dgl, *dgr, *hgl, *hgr; FrameLayout fll, flr; int devl, devr;
+    const float *sf, *isf, *sfr, *isfr;
+    if (orbx_internal_view(hl, &pl, &dgl, &hgl, &fll, &devl, &sf, &isf) || orbx_internal_view(hr, &pr, &dgr, &hgr, &flr, &devr, &sfr, &isfr) ||
+        !pl || !pr || devl != devr || fll.width != flr.width || fll.height != flr.height || fll.nlevels != flr.nlevels) {
+        set_error("orbm_stereo_matches: the two extractors must have processed same-size images on one device");
+        return ORB_ERR_ARG;
+    }
+    if (n_right >= (1 << 20)) return ORB_ERR_ARG;
+    ORB_CUDA_TRY(cudaSetDevice(devl));
+    cudaStream_t s = nullptr;
+    ORB_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    std::vector<StereoOut> res(n_left);
+    int rc = ORB_OK;
+    {
+        const float max_d = mbf / mb;   // maxD = mbf/minZ, minZ = mb  (:501-503)
+        DevBuf bkl, bdl, bkr, bdr, bsf, bisf, bout;
+        const bool ok = bkl.upload(keys_left, (size_t)n_left * sizeof(orb_keypoint_t), s) && bdl.upload(desc_left, (size_t)n_left * 32, s) &&
+                        bkr.upload(keys_right, (size_t)n_right * sizeof(orb_keypoint_t), s) && bdr.upload(desc_right, (size_t)n_right * 32, s) &&
+                        bsf.upload(sf, (size_t)fll.nlevels * 4, s) && bisf.upload(isf, (size_t)fll.nlevels * 4, s) &&
+                        bout.alloc((size_t)n_left * sizeof(StereoOut));
+        if (!ok) rc = ORB_ERR_CUDA;
+        if (!rc) {
+            stereo_kernel<<<(n_left * 32 + 127) / 128, 128, 0, s>>>(bkl.as<orb_keypoint_t>(), bdl.as<uint4>(), n_left, bkr.as<orb_keypoint_t>(),
+                                                                  bdr.as<uint4>(), n_right, bsf.as<float>(), bisf.as<float>(), pl, pr, dgl,
+                                                                  hgl[0].h, mbf, max_d, bout.as<StereoOut>());
+            if (!cuda_ok(cudaGetLastError(), "stereo_kernel") ||
+                !cuda_ok(cudaMemcpyAsync(res.data(), bout.p, (size_t)n_left * sizeof(StereoOut), cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
+                !cuda_ok(cudaStreamSynchronize(s), "stereo_kernel"))
+                rc = ORB_ERR_CUDA;
+        }
+    }
+    cudaStreamDestroy(s);
+    if (rc) return rc;
+    std::vector<std::pair<int, int>> distIdx;
+    for (int i = 0; i < n_left; i++)
+        if (res[i].ok) { u_right[i] = res[i].u_right; depth[i] = res[i].depth; distIdx.push_back(std::make_pair(res[i].sad, i)); }
+    int kept = (int)distIdx.size();
+    if (!distIdx.empty()) {   // :630-644 (the reference indexes an empty vector here; guarded)
+        std::sort(distIdx.begin(), distIdx.end());
+        const float median = (float)distIdx[distIdx.size() / 2].first;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = (int)distIdx.size() - 1; i >= 0; i--) {
+            if (distIdx[i].first < thDist) break;
+            u_right[distIdx[i].second] = -1; depth[distIdx[i].second] = -1; kept--;
+        }
+    }
+    if (n_matches) *n_matches = kept;
+    return ORB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+/*
+ * orbcuda.h -- C ABI of liborbcuda.so: the B200 (sm_100a) ORB front-end.
+ *
+ * Drop-in boundary for the reference's ORBextractor / ORBmatcher hot path.  The reference
+ * (R21 = ORB_SLAM2.1 in 530300865/Cooperative-ORB-SLAM) has no FFI layer: the boundary is its C++
+ * class API, so each entry point below names the reference interface it replaces (file:line) and
+ * the C++ shim classes in cooperative-orb-slam_b200/shim/ forward to it 1:1.  POD only: plain
+ * pointers and sizes, no cv:: or torch types, no exceptions.  Every function returns an int status
+ * (ORB_OK == 0); there is NO CPU fallback -- without a CUDA device every compute call returns
+ * ORB_ERR_CUDA.
+ *
+ * Threading: one orbx handle per ORBextractor instance; calls on one handle must be serialised by
+ * the caller, different handles may be used concurrently (the reference runs left/right extractors
+ * on two threads, R21/src/Frame.cc:80-83).  Matcher entry points are re-entrant.
+ */
+#ifndef ORBCUDA_H
+#define ORBCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORB_OK 0
+#define ORB_ERR_ARG 1        /* bad argument / unsupported shape */
+#define ORB_ERR_CUDA 2       /* CUDA runtime error or no device  */
+#define ORB_ERR_CAPACITY 3   /* caller buffer too small          */
+#define ORB_MAX_LEVELS 16
+
+/* Same 28-byte layout as cv::KeyPoint {Point2f pt; float size, angle, response; int octave, class_id}
+ * so a shim can memcpy into std::vector<cv::KeyPoint>. */
+typedef struct {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} orb_keypoint_t;
+
+/* ORBextractor::ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
+ * R21/src/ORBextractor.cc:410-470 */
+typedef struct {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} orbx_params_t;
+
+typedef struct orbx_handle_s* orbx_handle_t;
+
+const char* orb_last_error(void);          /* thread-local text of the last failure */
+int orb_device_count(int* count);
+
+/* ---------------------------------------------------------------- extractor ------------------ */
+/* Creates an extractor bound to CUDA device `device` for images up to max_width x max_height and up
+ * to max_batch frames per call.  Owns device buffers, pinned staging and one stream. */
+int orbx_create(const orbx_params_t* params, int max_width, int max_height, int max_batch, int device,
+                orbx_handle_t* out);
+int orbx_destroy(orbx_handle_t h);
+
+/* GetLevels/GetScaleFactor(s)/GetInverseScaleFactors/GetScaleSigmaSquares/GetInverseScaleSigmaSquares
+ * (R21/include/ORBextractor.h:63-83) plus mnFeaturesPerLevel (:435-446).  Any pointer may be NULL.
+ * Pure host code (no CUDA call). */
+int orbx_tables(orbx_handle_t h, float* scale_factors, float* inv_scale_factors, float* level_sigma2,
+                float* inv_level_sigma2, int32_t* features_per_level);
+/* Upper bound of keypoints one frame can produce (sum over levels of max(N_l + 3, 4*nIni)). */
+int orbx_max_keypoints(orbx_handle_t h, int width, int height, int* cap);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors)  R21/src/ORBextractor.cc:1043-1105.
+ * image: CV_8UC1, `stride` bytes per row, host memory.  The mask is ignored by the reference and has
+ * no parameter here.  keypoints[cap] / descriptors[cap*32] are caller-owned host buffers;
+ * *n_keypoints receives the count (level-major, quadtree list order inside a level).  An empty image
+ * (NULL / 0 size) returns ORB_OK with 0 keypoints like :1046-1047.  Synchronous. */
+int orbx_extract(orbx_handle_t h, const uint8_t* image, int width, int height, size_t stride,
+                 orb_keypoint_t* keypoints, uint8_t* descriptors, int cap, int* n_keypoints);
+
+/* Batched form for agent streams: n_frames images of identical size; frame i is at
+ * images + i*frame_stride.  Outputs are [n_frames][cap] / [n_frames][cap][32] / [n_frames].
+ * orbx_extract_batch_async enqueues upload + kernels + download on the handle's stream and returns;
+ * orbx_wait blocks until the results are in the caller's buffers (which must be pinned or stay
+ * alive until then).  orbx_extract_batch == async + wait. */
+int orbx_extract_batch(orbx_handle_t h, const uint8_t* images, int n_frames, int width, int height,
+                       size_t row_stride, size_t frame_stride, orb_keypoint_t* keypoints,
+                       uint8_t* descriptors, int cap, int32_t* n_keypoints);
+int orbx_extract_batch_async(orbx_handle_t h, const uint8_t* images, int n_frames, int width, int height,
+                             size_t row_stride, size_t frame_stride, orb_keypoint_t* keypoints,
+                             uint8_t* descriptors, int cap, int32_t* n_keypoints);
+int orbx_wait(orbx_handle_t h);
+
+/* Device-resident form: images already in HBM (device pointer, same strides), results stay in HBM.
+ * d_keypoints [n_frames][cap], d_descriptors [n_frames][cap][32], d_counts [n_frames] are device
+ * pointers; enqueued on the handle's stream (orbx_wait to finish). */
+int orbx_extract_batch_device(orbx_handle_t h, const uint8_t* d_images, int n_frames, int width, int height,
+                              size_t row_stride, size_t frame_stride, orb_keypoint_t* d_keypoints,
+                              uint8_t* d_descriptors, int cap, int32_t* d_counts);
+
+/* Host pinned memory helpers so callers can make uploads truly asynchronous. */
+int orb_host_alloc(void** ptr, size_t bytes);
+int orb_host_free(void* ptr);
+
+/* ---- views of the last call's intermediate results (public mvImagePyramid + parity tests) ---- */
+/* Level geometry of the last extraction. */
+int orbx_level_size(orbx_handle_t h, int level, int* width, int* height);
+/* mvImagePyramid[level] (R21/include/ORBextractor.h:85; ROI of the padded plane :1113-1116).
+ * with_border != 0 copies the (w+38) x (h+38) padded plane, else the w x h ROI. */
+int orbx_download_level(orbx_handle_t h, int frame, int level, int with_border, uint8_t* dst, size_t dst_stride);
+/* The 7x7 sigma=2 blurred level used for descriptors (R21 :1085-1086). */
+int orbx_download_blurred(orbx_handle_t h, int frame, int level, uint8_t* dst, size_t dst_stride);
+/* vToDistributeKeys of a level (R21 :789-826): candidates in cell-major, raster-in-cell order;
+ * coordinates relative to (minBorderX, minBorderY) = (16,16), response = FAST score. */
+int orbx_download_candidates(orbx_handle_t h, int frame, int level, int16_t* x, int16_t* y, uint8_t* score,
+                             int cap, int* n);
+/* The per-pixel FAST score map at minThFAST (0 where not a corner), w x h of the level. */
+int orbx_download_scores(orbx_handle_t h, int frame, int level, uint8_t* dst, size_t dst_stride);
+
+/* CUDA-event stage timers of the last batch, milliseconds:
+ * [0]=upload [1]=pyramid [2]=fast score [3]=blur [4]=cell nms [5]=quadtree [6]=orient+describe
+ * [7]=download [8]=total.  Enabled with orbx_set_profiling(h,1) (adds event records). */
+int orbx_set_profiling(orbx_handle_t h, int enable);
+int orbx_stage_times(orbx_handle_t h, float* ms9);
+/* Number of kernel launches issued by this handle since creation. */
+int orbx_launch_count(orbx_handle_t h, int64_t* launches);
+/* The CUDA stream of the handle as an opaque pointer (cudaStream_t). */
+int orbx_stream(orbx_handle_t h, void** stream);
+
+/* ---- stand-alone stage entry points (tests, stage benchmarks); host in/out, synchronous ---- */
+/* DistributeOctTree (R21 :539-763) on caller-provided candidates (coords relative to min_x/min_y). */
+int orbx_distribute_octtree(const int16_t* x, const int16_t* y, const uint8_t* score, int n, int min_x,
+                            int max_x, int min_y, int max_y, int n_features, int32_t* out_index, int cap,
+                            int* n_out, int device);
+
+/* ---------------------------------------------------------------- matcher -------------------- */
+/* ORBmatcher::DescriptorDistance(a, b)  R21/src/ORBmatcher.cc:1647-1663 (host, bit-exact). */
+int orb_hamming256(const void* a, const void* b);
+
+/* Brute-force 2-NN over 256-bit descriptors with the reference's best/second-best rule
+ * (R21/src/ORBmatcher.cc:216-225: strict '<', both start at 256, first index wins ties).
+ * queries [nq][32], map [nm][32] host memory.  Outputs per query: best index (+index_base, -1 if
+ * nm==0), best distance, second-best distance, and (optional, may be NULL) the index of the second
+ * best in (distance, index) lexicographic order.  variant: 0 = LOP3+POPC kernel, 1 = tensor-core
+ * AND-popc contraction (same results). */
+int orbm_knn2(const uint8_t* queries, int nq, const uint8_t* map, int64_t nm, int64_t index_base,
+              int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int32_t* second_idx,
+              int variant, int device);
+/* Same with device pointers, asynchronous on `stream` (cudaStream_t; NULL = default stream).
+ * d_out is [nq] x int32[4] = {d1, i1, d2, i2}: the per-rank record exchanged by the sharded map
+ * match (allgather) and merged with orbm_merge_top2_device. */
+int orbm_knn2_device(const uint8_t* d_queries, int nq, const uint8_t* d_map, int64_t nm, int64_t index_base,
+                     int32_t* d_out, int variant, void* stream);
+/* Merge `parts` records per query ([parts][nq][4] int32, device) in lexicographic (dist, index)
+ * order into [nq][4]; bit-identical to a single-rank search over the concatenated map. */
+int orbm_merge_top2_device(const int32_t* d_parts, int parts, int nq, int32_t* d_out, void* stream);
+int orbm_merge_top2_host(const int32_t* parts_rec, int parts, int nq, int32_t* out);
+/* Acceptance test of R21 ORBmatcher.cc:228-230 on merged records: match iff d1 <= th (or < th when
+ * strict) and (float)d1 < ratio*(float)d2.  out_match[i] = i1 or -1. */
+int orbm_ratio_test_host(const int32_t* rec, int nq, float ratio, int th, int strict, int32_t* out_match);
+
+/* DBoW2::FeatureVector as CSR: node ids ascending; node i owns idx[ptr[i] .. ptr[i+1]). */
+typedef struct {
+    int32_t n_nodes;
+    const int32_t* node_ids;
+    const int32_t* ptr;
+    const int32_t* idx;
+} orbm_featvec_t;
+
+/* int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
+ * R21/src/ORBmatcher.cc:159-288.  kf_valid[i] != 0 <=> KF feature i has a non-bad MapPoint.
+ * out_match_f[j] = KF feature index whose MapPoint is assigned to frame feature j, or -1.
+ * *n_matches = return value. */
+int orbm_search_by_bow_kf_f(const uint8_t* desc_kf, const float* angle_kf, const uint8_t* kf_valid, int n_kf,
+                            const orbm_featvec_t* fv_kf, const uint8_t* desc_f, const float* angle_f, int n_f,
+                            const orbm_featvec_t* fv_f, float nnratio, int check_orientation,
+                            int32_t* out_match_f, int* n_matches, int device);
+/* int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)
+ * R21/src/ORBmatcher.cc:522-655.  out_match12[i1] = feature index in KF2 or -1. */
+int orbm_search_by_bow_kf_kf(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                             const orbm_featvec_t* fv1, const uint8_t* desc2, const float* angle2,
+                             const uint8_t* valid2, int n2, const orbm_featvec_t* fv2, float nnratio,
+                             int check_orientation, int32_t* out_match12, int* n_matches, int device);
+
+typedef struct {
+    float x, y;       /* mvKeysUn[i].pt      */
+    float angle;      /* mvKeysUn[i].angle   */
+    int32_t octave;   /* mvKeysUn[i].octave  */
+    float u_right;    /* mvuRight[i] (<0: monocular) */
+    int32_t has_mp;   /* GetMapPoint(i) != NULL */
+} orbm_tri_feature_t;
+
+/* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
+ *       vector<pair<size_t,size_t>>& vMatchedPairs, const bool bOnlyStereo)
+ * R21/src/ORBmatcher.cc:657-823.  F12 row-major 3x3 float; (ex,ey) = epipole in image 2 (:664-670);
+ * scale_factors2 / level_sigma2_2 = pKF2->mvScaleFactors / mvLevelSigma2.  out_pairs = (idx1, idx2)
+ * ascending idx1 (:812-820). */
+int orbm_search_for_triangulation(const uint8_t* desc1, const orbm_tri_feature_t* f1, int n1,
+                                  const orbm_featvec_t* fv1, const uint8_t* desc2,
+                                  const orbm_tri_feature_t* f2, int n2, const orbm_featvec_t* fv2,
+                                  const float* F12, float ex, float ey, const float* scale_factors2,
+                                  const float* level_sigma2_2, int only_stereo, int check_orientation,
+                                  int32_t* out_pairs, int cap_pairs, int* n_matches, int device);
+
+/* void Frame::ComputeStereoMatches()  R21/src/Frame.cc:471-645.  hl/hr: the two extractor handles
+ * whose last orbx_extract produced the left/right keypoints (their pyramids are read on the device,
+ * replacing the reads of mpORBextractorLeft/Right->mvImagePyramid, :568,:585).  mb = mbf/fx is
+ * passed explicitly.  u_right[n_left], depth[n_left] = mvuRight / mvDepth. */
+int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t* keys_left,
+                        const uint8_t* desc_left, int n_left, const orb_keypoint_t* keys_right,
+                        const uint8_t* desc_right, int n_right, float mbf, float mb, float* u_right,
+                        float* depth, int* n_matches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBCUDA_H */
