@@ -80,7 +80,7 @@ ABI = {
     "orbm_search_by_bow_kf_kf": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _F, _I, _VP, _VP, _I]),
     "orbm_search_for_triangulation": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _F, _F, _VP, _VP, _I, _I, _VP,
                                           _I, _VP, _I]),
-    "orbm_stereo_matches": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _VP, _VP, _VP]),
+    "orbm_stereo_matches": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _VP, _VP, _VP]),
 }
 
 

@@ -1,0 +1,159 @@
+// ORBmatcher_accel.h -- adapters that route the reference's ORBmatcher hot loops to liborbcuda.
+//
+// The reference's ORBmatcher methods take Frame / KeyFrame / MapPoint objects (R21/include/ORBmatcher.h).
+// Those classes stay untouched; the function templates below are duck-typed on exactly the members the
+// reference's loops read, flatten them into the POD arrays of include/orbcuda.h, call the C ABI and
+// scatter the result back in the reference's own output type.  Inside ORBmatcher.cc a method body becomes
+// one call, e.g.
+//     int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
+//     { return orbaccel::SearchByBoW_KF_F(pKF, F, vpMapPointMatches, mfNNratio, mbCheckOrientation); }
+// ORBmatcher::DescriptorDistance (R21/src/ORBmatcher.cc:1647) -> orb_hamming256(a.ptr(), b.ptr()).
+#ifndef ORBMATCHER_ACCEL_H
+#define ORBMATCHER_ACCEL_H
+
+#include <cstddef>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "orbcuda.h"
+
+namespace orbaccel
+{
+
+// DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>) -> CSR
+template <class FeatureVector>
+struct FlatFeatVec
+{
+    std::vector<int32_t> ids, ptr, idx;
+    orbm_featvec_t view;
+    explicit FlatFeatVec(const FeatureVector& fv)
+    {
+        ptr.push_back(0);
+        for(typename FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it)
+        {
+            ids.push_back((int32_t)it->first);
+            for(size_t k = 0; k < it->second.size(); k++)
+                idx.push_back((int32_t)it->second[k]);
+            ptr.push_back((int32_t)idx.size());
+        }
+        view.n_nodes = (int32_t)ids.size();
+        view.node_ids = ids.empty() ? 0 : &ids[0];
+        view.ptr = &ptr[0];
+        view.idx = idx.empty() ? 0 : &idx[0];
+    }
+};
+
+inline void check(int rc, const char* what)
+{
+    if(rc != ORB_OK)
+        throw std::runtime_error(std::string(what) + " failed: " + orb_last_error());
+}
+
+template <class KeyPointVec>
+inline std::vector<float> angles(const KeyPointVec& v)
+{
+    std::vector<float> a(v.size());
+    for(size_t i = 0; i < v.size(); i++) a[i] = v[i].angle;
+    return a;
+}
+
+// R21/src/ORBmatcher.cc:159-288.  mDescriptors must be continuous N x 32 CV_8U (it is: ORBextractor output).
+template <class KeyFrame, class Frame, class MapPoint>
+int SearchByBoW_KF_F(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches, float nnratio, bool checkOri,
+                     int device = 0)
+{
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    const int nKF = (int)vpMapPointsKF.size();
+    std::vector<unsigned char> valid(nKF);
+    for(int i = 0; i < nKF; i++) valid[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
+    FlatFeatVec<typename std::remove_reference<decltype(pKF->mFeatVec)>::type> fk(pKF->mFeatVec);
+    FlatFeatVec<typename std::remove_reference<decltype(F.mFeatVec)>::type> ff(F.mFeatVec);
+    std::vector<float> aKF = angles(pKF->mvKeysUn), aF = angles(F.mvKeys);
+    std::vector<int32_t> match(F.N);
+    int nmatches = 0;
+    check(orbm_search_by_bow_kf_f(pKF->mDescriptors.ptr(0), &aKF[0], &valid[0], nKF, &fk.view, F.mDescriptors.ptr(0), &aF[0], F.N,
+                                  &ff.view, nnratio, checkOri, &match[0], &nmatches, device), "orbm_search_by_bow_kf_f");
+    vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+    for(int j = 0; j < F.N; j++)
+        if(match[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[match[j]];
+    return nmatches;
+}
+
+// R21/src/ORBmatcher.cc:522-655
+template <class KeyFrame, class MapPoint>
+int SearchByBoW_KF_KF(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, float nnratio, bool checkOri,
+                      int device = 0)
+{
+    const std::vector<MapPoint*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+    const int n1 = (int)mp1.size(), n2 = (int)mp2.size();
+    std::vector<unsigned char> v1(n1), v2(n2);
+    for(int i = 0; i < n1; i++) v1[i] = mp1[i] && !mp1[i]->isBad();
+    for(int i = 0; i < n2; i++) v2[i] = mp2[i] && !mp2[i]->isBad();
+    FlatFeatVec<typename std::remove_reference<decltype(pKF1->mFeatVec)>::type> f1(pKF1->mFeatVec), f2(pKF2->mFeatVec);
+    std::vector<float> a1 = angles(pKF1->mvKeysUn), a2 = angles(pKF2->mvKeysUn);
+    std::vector<int32_t> match(n1);
+    int nmatches = 0;
+    check(orbm_search_by_bow_kf_kf(pKF1->mDescriptors.ptr(0), &a1[0], &v1[0], n1, &f1.view, pKF2->mDescriptors.ptr(0), &a2[0], &v2[0],
+                                   n2, &f2.view, nnratio, checkOri, &match[0], &nmatches, device), "orbm_search_by_bow_kf_kf");
+    vpMatches12 = std::vector<MapPoint*>(n1, static_cast<MapPoint*>(NULL));
+    for(int i = 0; i < n1; i++)
+        if(match[i] >= 0) vpMatches12[i] = mp2[match[i]];
+    return nmatches;
+}
+
+// R21/src/ORBmatcher.cc:657-823.  F12 is a 3x3 CV_32F cv::Mat; the epipole (:664-670) is computed by the caller's
+// own geometry code and passed in.
+template <class KeyFrame>
+int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, const float* F12_rowmajor, float ex, float ey,
+                           std::vector<std::pair<size_t, size_t> >& vMatchedPairs, bool bOnlyStereo, bool checkOri,
+                           int device = 0)
+{
+    const int n1 = pKF1->N, n2 = pKF2->N;
+    std::vector<orbm_tri_feature_t> t1(n1), t2(n2);
+    for(int i = 0; i < n1; i++)
+    {
+        t1[i].x = pKF1->mvKeysUn[i].pt.x; t1[i].y = pKF1->mvKeysUn[i].pt.y; t1[i].angle = pKF1->mvKeysUn[i].angle;
+        t1[i].octave = pKF1->mvKeysUn[i].octave; t1[i].u_right = pKF1->mvuRight[i]; t1[i].has_mp = pKF1->GetMapPoint(i) ? 1 : 0;
+    }
+    for(int i = 0; i < n2; i++)
+    {
+        t2[i].x = pKF2->mvKeysUn[i].pt.x; t2[i].y = pKF2->mvKeysUn[i].pt.y; t2[i].angle = pKF2->mvKeysUn[i].angle;
+        t2[i].octave = pKF2->mvKeysUn[i].octave; t2[i].u_right = pKF2->mvuRight[i]; t2[i].has_mp = pKF2->GetMapPoint(i) ? 1 : 0;
+    }
+    FlatFeatVec<typename std::remove_reference<decltype(pKF1->mFeatVec)>::type> f1(pKF1->mFeatVec), f2(pKF2->mFeatVec);
+    std::vector<int32_t> pairs((size_t)2 * (n1 > 0 ? n1 : 1));
+    int nmatches = 0;
+    check(orbm_search_for_triangulation(pKF1->mDescriptors.ptr(0), &t1[0], n1, &f1.view, pKF2->mDescriptors.ptr(0), &t2[0], n2,
+                                        &f2.view, F12_rowmajor, ex, ey, &pKF2->mvScaleFactors[0], &pKF2->mvLevelSigma2[0],
+                                        bOnlyStereo, checkOri, &pairs[0], n1, &nmatches, device), "orbm_search_for_triangulation");
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(nmatches);
+    for(int k = 0; k < nmatches; k++)
+        vMatchedPairs.push_back(std::make_pair((size_t)pairs[2 * k], (size_t)pairs[2 * k + 1]));
+    return nmatches;
+}
+
+// Frame::ComputeStereoMatches (R21/src/Frame.cc:471-645): body becomes
+//     orbaccel::ComputeStereoMatches(*this);
+template <class Frame>
+void ComputeStereoMatches(Frame& F)
+{
+    F.mvuRight = std::vector<float>(F.N, -1.0f);
+    F.mvDepth = std::vector<float>(F.N, -1.0f);
+    const int Nr = (int)F.mvKeysRight.size();
+    if(F.N == 0 || Nr == 0) return;
+    static_assert(sizeof(F.mvKeys[0]) == sizeof(orb_keypoint_t), "cv::KeyPoint layout");
+    int n = 0;
+    // mb is mbf/fx; the reference reads it before assigning it (R21/src/Frame.cc:116 vs :501)
+    check(orbm_stereo_matches(F.mpORBextractorLeft->Handle(), F.mpORBextractorRight->Handle(),
+                              reinterpret_cast<const orb_keypoint_t*>(&F.mvKeys[0]), F.mDescriptors.ptr(0), F.N,
+                              reinterpret_cast<const orb_keypoint_t*>(&F.mvKeysRight[0]), F.mDescriptorsRight.ptr(0), Nr,
+                              F.mbf, F.mbf / F.fx, &F.mvuRight[0], &F.mvDepth[0], &n), "orbm_stereo_matches");
+}
+
+} // namespace orbaccel
+
+#endif

@@ -260,3 +260,65 @@ class RefExtractor:
         out = np.empty((h.value + 2 * b, w.value + 2 * b), np.uint8)
         self.L.orbref_get_pyramid(self.h, l, int(with_border), _p(out), out.strides[0])
         return out
+
+
+# ----------------------------------------------------------------------------- matcher loops
+def _fv_struct(fv):
+    node_ids, ptr, idx = (np.ascontiguousarray(a, np.int32) for a in fv)
+    s = FeatVec(len(node_ids), node_ids.ctypes.data, ptr.ctypes.data, idx.ctypes.data)
+    s._keep = (node_ids, ptr, idx)
+    return s
+
+
+def search_by_bow_kf_f(dk, ak, vk, fvk, df, af, fvf, ratio, check_ori):
+    dk = np.ascontiguousarray(dk, np.uint8); df = np.ascontiguousarray(df, np.uint8)
+    ak = np.ascontiguousarray(ak, np.float32); af = np.ascontiguousarray(af, np.float32)
+    vk = np.ascontiguousarray(vk, np.uint8)
+    a, b = _fv_struct(fvk), _fv_struct(fvf)
+    out = np.zeros(len(df), np.int32)
+    n = lib().orc_search_by_bow_kf_f(_p(dk), _p(ak), _p(vk), len(dk), C.addressof(a), _p(df), _p(af), len(df), C.addressof(b),
+                                     ratio, int(check_ori), _p(out))
+    return n, out
+
+
+def search_by_bow_kf_kf(d1, a1, v1, fv1, d2, a2, v2, fv2, ratio, check_ori):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    a1 = np.ascontiguousarray(a1, np.float32); a2 = np.ascontiguousarray(a2, np.float32)
+    v1 = np.ascontiguousarray(v1, np.uint8); v2 = np.ascontiguousarray(v2, np.uint8)
+    a, b = _fv_struct(fv1), _fv_struct(fv2)
+    out = np.zeros(len(d1), np.int32)
+    n = lib().orc_search_by_bow_kf_kf(_p(d1), _p(a1), _p(v1), len(d1), C.addressof(a), _p(d2), _p(a2), _p(v2), len(d2),
+                                      C.addressof(b), ratio, int(check_ori), _p(out))
+    return n, out
+
+
+def search_for_triangulation(d1, f1, fv1, d2, f2, fv2, F12, ex, ey, sf2, sig2, only_stereo, check_ori):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    f1 = np.ascontiguousarray(f1, TRI_DTYPE); f2 = np.ascontiguousarray(f2, TRI_DTYPE)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sf2 = np.ascontiguousarray(sf2, np.float32); sig2 = np.ascontiguousarray(sig2, np.float32)
+    a, b = _fv_struct(fv1), _fv_struct(fv2)
+    cap = max(len(d1), 1)
+    out = np.zeros((cap, 2), np.int32)
+    n = lib().orc_search_for_triangulation(_p(d1), _p(f1), len(d1), C.addressof(a), _p(d2), _p(f2), len(d2), C.addressof(b),
+                                           _p(F), float(ex), float(ey), _p(sf2), _p(sig2), int(only_stereo), int(check_ori),
+                                           _p(out), cap)
+    return n, out[:n].copy()
+
+
+def stereo_matches(kl, dl, kr, dr, ext_l, ext_r, mbf, mb):
+    """ext_l / ext_r: OracleExtractor objects that produced the key points (their pyramids are read)."""
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    L = ext_l.nlevels
+    t = ext_l.tables()
+    pl = [ext_l.pyramid(l, True) for l in range(L)]
+    pr = [ext_r.pyramid(l, True) for l in range(L)]
+    PL = (C.c_void_p * L)(*[p.ctypes.data for p in pl]); PR = (C.c_void_p * L)(*[p.ctypes.data for p in pr])
+    lw = np.array([p.shape[1] - 38 for p in pl], np.int32); lh = np.array([p.shape[0] - 38 for p in pl], np.int32)
+    st = np.array([p.strides[0] for p in pl], np.uint64)
+    ur = np.zeros(len(kl), np.float32); dep = np.zeros(len(kl), np.float32)
+    n = lib().orc_stereo_matches(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), L, _p(t["sf"]), _p(t["isf"]),
+                                 C.cast(PL, C.c_void_p), C.cast(PR, C.c_void_p), _p(lw), _p(lh), _p(st), float(mbf), float(mb),
+                                 _p(ur), _p(dep))
+    return ur, dep, n

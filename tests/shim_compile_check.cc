@@ -1,0 +1,43 @@
+// Compile-time check (CPU, tests/test_boundary.py): the drop-in shim classes build against an
+// OpenCV-compatible header set and the adapter templates instantiate on types shaped like the
+// reference's Frame / KeyFrame / MapPoint.  Uses oracle/cvshim only as a stand-in for OpenCV headers.
+#include <map>
+#include <type_traits>
+#include "ORBextractor.h"
+#include "ORBmatcher_accel.h"
+
+struct MapPoint { bool isBad() { return false; } };
+typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
+struct KeyFrame {
+    int N;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
+    cv::Mat mDescriptors;
+    FeatureVector mFeatVec;
+    std::vector<MapPoint*> mps;
+    std::vector<MapPoint*> GetMapPointMatches() { return mps; }
+    MapPoint* GetMapPoint(size_t i) { return mps[i]; }
+};
+struct Frame {
+    int N;
+    float mbf, fx;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors, mDescriptorsRight;
+    FeatureVector mFeatVec;
+    ORB_SLAM2::ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
+};
+
+int shim_instantiate(KeyFrame* a, KeyFrame* b, Frame& f) {
+    std::vector<MapPoint*> out;
+    std::vector<std::pair<size_t, size_t> > pairs;
+    float F12[9] = {0};
+    int n = orbaccel::SearchByBoW_KF_F(a, f, out, 0.7f, true);
+    n += orbaccel::SearchByBoW_KF_KF(a, b, out, 0.75f, true);
+    n += orbaccel::SearchForTriangulation(a, b, F12, 0.f, 0.f, pairs, false, false);
+    orbaccel::ComputeStereoMatches(f);
+    ORB_SLAM2::ORBextractor e(1000, 1.2f, 8, 20, 7);
+    std::vector<cv::KeyPoint> k; cv::Mat d, img;
+    e(img, cv::Mat(), k, d);
+    return n + e.GetLevels() + (int)e.GetScaleFactors().size() + (int)e.mvImagePyramid.size();
+}

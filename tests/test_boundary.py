@@ -1,0 +1,103 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/orbcuda.h declares, the C++ shim classes compile against an OpenCV-compatible header set, the
+host-side merge logic is exact, and the product never routes through the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "orbcuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(orb[xm]?_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import orbcuda
+    L = orbcuda.lib()
+    decl = _declared_symbols()
+    assert len(decl) >= 30
+    for s in decl:
+        assert hasattr(L, s), "liborbcuda.so does not export " + s
+    assert sorted(orbcuda.ABI) == decl, set(orbcuda.ABI) ^ set(decl)
+
+
+def test_no_cpu_fallback_without_device():
+    import orbcuda
+    if orbcuda.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(orbcuda.OrbCudaError):
+        orbcuda.ORBextractor(1000, 1.2, 8, 20, 7)
+    with pytest.raises(orbcuda.OrbCudaError):
+        orbcuda.ORBmatcher().knn2(np.zeros((4, 32), np.uint8), np.zeros((8, 32), np.uint8))
+
+
+def test_host_only_entry_points(oracle):
+    import orbcuda
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (64, 32), dtype=np.uint8); b = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+    for i in range(64):
+        assert orbcuda.ORBmatcher.DescriptorDistance(a[i], b[i]) == oracle.descriptor_distance(a[i], b[i])
+    # ratio test R21 ORBmatcher.cc:228-230 / :598-600
+    rec = np.array([[50, 7, 100, 9], [50, 7, 60, 9], [49, 3, 100, 1], [51, 2, 256, -1], [256, -1, 256, -1]], np.int32)
+    out = np.zeros(5, np.int32)
+    assert orbcuda.lib().orbm_ratio_test_host(rec.ctypes.data, 5, 0.6, 50, 0, out.ctypes.data) == 0
+    assert list(out) == [7, -1, 3, -1, -1]
+    assert orbcuda.lib().orbm_ratio_test_host(rec.ctypes.data, 5, 0.6, 50, 1, out.ctypes.data) == 0
+    assert list(out) == [-1, -1, 3, -1, -1]
+
+
+def test_merge_top2_host_equals_single_search(oracle, synth):
+    import orbcuda
+    m = synth.descriptors(6000, seed=3)
+    q, m, _ = synth.query_set(m, nq=200, seed=4)
+    m[100] = m[5]; m[5999] = m[5]; q[0] = m[5]          # ties across shards
+    L = oracle.lib()
+
+    def full(mm, base):
+        i1, d1, i2, d2 = (np.zeros(len(q), np.int32) for _ in range(4))
+        L.orc_knn2_full(q.ctypes.data, len(q), mm.ctypes.data, len(mm), base, i1.ctypes.data, d1.ctypes.data,
+                        i2.ctypes.data, d2.ctypes.data, 2)
+        return np.stack([d1, i1, d2, i2], 1).astype(np.int32)
+
+    ref = full(m, 0)
+    for G in (1, 2, 3, 8):
+        bounds = np.linspace(0, len(m), G + 1).astype(int)
+        parts = np.ascontiguousarray(np.stack([full(np.ascontiguousarray(m[bounds[g]:bounds[g + 1]]), int(bounds[g]))
+                                               for g in range(G)]))
+        out = np.zeros((len(q), 4), np.int32)
+        assert orbcuda.lib().orbm_merge_top2_host(parts.ctypes.data, G, len(q), out.ctypes.data) == 0
+        assert np.array_equal(out, ref), G
+        # any grouping / order of the shards gives the same answer (associative + commutative)
+        perm = parts[::-1].copy()
+        assert orbcuda.lib().orbm_merge_top2_host(perm.ctypes.data, G, len(q), out.ctypes.data) == 0
+        assert np.array_equal(out, ref)
+
+
+def test_shim_classes_compile():
+    """cooperative-orb-slam_b200/shim/{ORBextractor.h,.cc,ORBmatcher_accel.h} against OpenCV-compatible headers."""
+    inc = ["-I" + os.path.join(ROOT, p) for p in ("oracle/cvshim", "oracle", "include", "cooperative-orb-slam_b200/shim")]
+    src = [os.path.join(ROOT, "tests", "shim_compile_check.cc"),
+           os.path.join(ROOT, "cooperative-orb-slam_b200", "shim", "ORBextractor.cc")]
+    subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-Wall"] + inc + src)
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under the package or include/ may import, include or link oracle/ (the checker is not the product)."""
+    bad = []
+    for base in ("cooperative-orb-slam_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".so", ".o", ".pyc", ".inc")):
+                    continue
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"oracle_lib|orb_oracle|liborb_oracle|liborbref|orc_[a-z]", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+    out = subprocess.check_output(["ldd", os.path.join(ROOT, "cooperative-orb-slam_b200", "liborbcuda.so")], text=True)
+    assert "oracle" not in out and "orbref" not in out

@@ -66,3 +66,71 @@ def test_sharded_merge_is_exact(orb, oracle, synth):
         out = np.zeros((len(q), 4), np.int32)
         assert orb.lib().orbm_merge_top2_host(parts.ctypes.data, G, len(q), out.ctypes.data) == 0
         assert np.array_equal(out, full.astype(np.int32)), G
+
+
+# ---------------------------------------------------------------------------------- candidate loops
+import matchdata
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_search_by_bow_kf_f(orb, oracle, seed, check_ori):
+    d1, d2, a1, a2, src, dst, rng = matchdata.two_views(1000, 1100, seed)
+    valid = (rng.random(len(d1)) < 0.8).astype(np.uint8)
+    fv1, fv2 = matchdata.featvec(d1), matchdata.featvec(d2)
+    for ratio in (0.7, 0.75, 0.9):
+        n_ref, m_ref = oracle.search_by_bow_kf_f(d1, a1, valid, fv1, d2, a2, fv2, ratio, check_ori)
+        n_gpu, m_gpu = orb.ORBmatcher(ratio, check_ori).SearchByBoW(d1, a1, valid, fv1, d2, a2, fv2)
+        assert n_ref == n_gpu and np.array_equal(m_ref, m_gpu), (ratio, n_ref, n_gpu)
+        assert n_ref > 100
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_search_by_bow_kf_kf(orb, oracle, seed):
+    d1, d2, a1, a2, src, dst, rng = matchdata.two_views(900, 1000, seed)
+    v1 = (rng.random(len(d1)) < 0.7).astype(np.uint8); v2 = (rng.random(len(d2)) < 0.7).astype(np.uint8)
+    fv1, fv2 = matchdata.featvec(d1, 5), matchdata.featvec(d2, 5)
+    for check_ori in (True, False):
+        n_ref, m_ref = oracle.search_by_bow_kf_kf(d1, a1, v1, fv1, d2, a2, v2, fv2, 0.75, check_ori)
+        n_gpu, m_gpu = orb.ORBmatcher(0.75, check_ori).SearchByBoW_KF(d1, a1, v1, fv1, d2, a2, v2, fv2)
+        assert n_ref == n_gpu and np.array_equal(m_ref, m_gpu)
+        assert n_ref > 50
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+@pytest.mark.parametrize("only_stereo", [False, True])
+def test_search_for_triangulation(orb, oracle, seed, only_stereo):
+    d1, d2, a1, a2, src, dst, rng = matchdata.two_views(1000, 1000, seed)
+    f1, f2 = matchdata.tri_features(len(d1), len(d2), src, dst, rng)
+    f1["angle"] = a1; f2["angle"] = a2
+    fv1, fv2 = matchdata.featvec(d1), matchdata.featvec(d2)
+    t = oracle.OracleExtractor(1000).tables()
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)      # sideways translation: epipolar lines y2 = y1
+    for (ex, ey) in ((1e6, 240.0), (300.0, 240.0)):                       # far epipole / epipole inside the image
+        n_ref, p_ref = oracle.search_for_triangulation(d1, f1, fv1, d2, f2, fv2, F12, ex, ey, t["sf"], t["s2"], only_stereo, False)
+        n_gpu, p_gpu = orb.ORBmatcher(0.6, False).SearchForTriangulation(d1, f1, fv1, d2, f2, fv2, F12, (ex, ey), t["sf"],
+                                                                         t["s2"], only_stereo)
+        assert n_ref == n_gpu and np.array_equal(p_ref, p_gpu), (n_ref, n_gpu)
+    assert only_stereo or n_ref > 30
+    n_ref, p_ref = oracle.search_for_triangulation(d1, f1, fv1, d2, f2, fv2, F12, 1e6, 0, t["sf"], t["s2"], only_stereo, True)
+    n_gpu, p_gpu = orb.ORBmatcher(0.6, True).SearchForTriangulation(d1, f1, fv1, d2, f2, fv2, F12, (1e6, 0), t["sf"], t["s2"],
+                                                                    only_stereo)
+    assert n_ref == n_gpu and np.array_equal(p_ref, p_gpu)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_stereo_matches(orb, oracle, synth, seed):
+    left, right = synth.stereo_pair(seed, 752, 480)
+    el = orb.ORBextractor(1200, 1.2, 8, 20, 7); er = orb.ORBextractor(1200, 1.2, 8, 20, 7)
+    kl, dl = el(left); kr, dr = er(right)
+    ol = oracle.OracleExtractor(1200, trig_mode=1); orr = oracle.OracleExtractor(1200, trig_mode=1)
+    okl, odl = ol.extract(left); okr, odr = orr.extract(right)
+    assert kl.tobytes() == okl.tobytes() and kr.tobytes() == okr.tobytes()
+    mbf, fx = 40.0, 458.0
+    ur, dep, n = orb.compute_stereo_matches(el, er, kl, dl, kr, dr, mbf, mbf / fx)
+    our, odep, on = oracle.stereo_matches(okl, odl, okr, odr, ol, orr, mbf, mbf / fx)
+    assert n == on and n > 100, (n, on)
+    assert np.array_equal(ur, our) and np.array_equal(dep, odep)
+    # empty sides are legal
+    ur0, dep0, n0 = orb.compute_stereo_matches(el, er, kl, dl, kr[:0], dr[:0], mbf, mbf / fx)
+    assert n0 == 0 and (ur0 == -1).all()
