@@ -70,6 +70,7 @@ struct orbx_handle_s {
     uint32_t* d_scratch = nullptr; size_t cap_scratch = 0;
     uint16_t* d_node = nullptr; size_t cap_node = 0;
     int32_t* d_cell_count = nullptr; size_t cap_cell_count = 0;
+    int32_t* d_level_raw = nullptr; size_t cap_level_raw = 0;
     uint32_t* d_sel = nullptr; size_t cap_sel = 0;
     int32_t* d_level_count = nullptr; size_t cap_level_count = 0;
     orb_keypoint_t* d_kps = nullptr; size_t cap_kps = 0;
@@ -184,7 +185,7 @@ int build_geometry(orbx_handle_s* h, int width, int height) {
                 c.y0 = (int16_t)(iniY + 3); c.y1 = (int16_t)(maxY - 3);
                 if (skip || c.x1 <= c.x0 || c.y1 <= c.y0) { c.x1 = c.x0; c.y1 = c.y0; }
                 const int iw = c.x1 - c.x0, ih = c.y1 - c.y0;
-                if (iw * ih >= 4096) { set_error("FAST cell larger than 4095 px"); return ORB_ERR_ARG; }
+                if (iw > 64) { set_error("FAST cell wider than 64 px"); return ORB_ERR_ARG; }
                 c.slot_off = slot;
                 slot += ((iw + 1) / 2) * ((ih + 1) / 2);   // strict 3x3 NMS keeps at most one pixel per 2x2 block
                 cells.push_back(c);
@@ -209,6 +210,21 @@ int build_geometry(orbx_handle_s* h, int width, int height) {
             g.ytab_off = (int)ytab.size();
             make_taps(geom[l - 1].w, g.w, true, xtab);
             make_taps(geom[l - 1].h, g.h, false, ytab);
+            // source footprint of one output tile (for the resize kernel's shared-memory staging)
+            for (int x0 = 0; x0 < g.w; x0 += kPyrTileW) {
+                const int x1 = std::min(x0 + kPyrTileW, g.w) - 1;
+                const int lo = xtab[g.xtab_off + x0].ofs & ~3, hi = xtab[g.xtab_off + x1].pad;
+                g.rs_cols = std::max(g.rs_cols, (int)align_up(hi - lo + 1, 4));
+            }
+            for (int y0 = 0; y0 < g.h; y0 += kPyrTileH) {
+                const int y1 = std::min(y0 + kPyrTileH, g.h) - 1;
+                int lo = 1 << 30, hi = 0;   // vertical taps are monotone but take min/max anyway
+                for (int y = y0; y <= y1; y++) {
+                    lo = std::min(lo, (int)ytab[g.ytab_off + y].ofs);
+                    hi = std::max(hi, (int)ytab[g.ytab_off + y].pad);
+                }
+                g.rs_rows = std::max(g.rs_rows, hi - lo + 1);
+            }
         }
     }
     if (node_cap > 60000) { set_error("nfeatures per level too large"); return ORB_ERR_ARG; }
@@ -220,6 +236,7 @@ int build_geometry(orbx_handle_s* h, int width, int height) {
     fl.cand_entries = cand_off;
     fl.kp_cap = kp_slot;
     fl.node_cap = (int)align_up(node_cap + 4, 32);
+    fl.ini_th = h->prm.ini_th_fast;
     h->geom.swap(geom); h->cells.swap(cells); h->xtab.swap(xtab); h->ytab.swap(ytab);
     if (h->xtab.empty()) { h->xtab.push_back(ResizeTap()); h->ytab.push_back(ResizeTap()); }
     h->fl = fl;
@@ -252,11 +269,12 @@ int ensure_size(orbx_handle_s* h, int width, int height, int n_frames) {
     const size_t B = (size_t)n_frames;
     if ((rc = grow_dev(h->d_pyr, h->cap_pyr, B * fl.pyr_bytes))) return rc;
     if ((rc = grow_dev(h->d_blur, h->cap_blur, B * fl.splane_bytes))) return rc;
-    if ((rc = grow_dev(h->d_score, h->cap_score, B * fl.splane_bytes))) return rc;
+    if ((rc = grow_dev(h->d_score, h->cap_score, B * fl.splane_bytes + 256))) return rc;
     if ((rc = grow_dev(h->d_cand, h->cap_cand, B * fl.cand_entries * 4))) return rc;
     if ((rc = grow_dev(h->d_scratch, h->cap_scratch, B * fl.cand_entries * 4))) return rc;
     if ((rc = grow_dev(h->d_node, h->cap_node, B * fl.cand_entries * 2))) return rc;
     if ((rc = grow_dev(h->d_cell_count, h->cap_cell_count, B * fl.n_cells * 4))) return rc;
+    if ((rc = grow_dev(h->d_level_raw, h->cap_level_raw, B * kMaxLevels * 4))) return rc;
     if ((rc = grow_dev(h->d_sel, h->cap_sel, B * fl.kp_cap * 4))) return rc;
     if ((rc = grow_dev(h->d_level_count, h->cap_level_count, B * kMaxLevels * 4))) return rc;
     return ORB_OK;
@@ -264,7 +282,7 @@ int ensure_size(orbx_handle_s* h, int width, int height, int n_frames) {
 
 void fill_ptrs(orbx_handle_s* h, DevPtrs& d, const uint8_t* d_in) {
     d.in = d_in; d.pyr = h->d_pyr; d.blur = h->d_blur; d.score = h->d_score; d.cand = h->d_cand;
-    d.cell_count = h->d_cell_count; d.oct_scratch = h->d_scratch; d.oct_node = h->d_node; d.sel = h->d_sel;
+    d.cell_count = h->d_cell_count; d.level_raw = h->d_level_raw; d.oct_scratch = h->d_scratch; d.oct_node = h->d_node; d.sel = h->d_sel;
     d.level_count = h->d_level_count; d.geom = h->d_geom; d.cells = h->d_cells; d.xtab = h->d_xtab; d.ytab = h->d_ytab;
 }
 
@@ -277,7 +295,10 @@ int enqueue_kernels(orbx_handle_s* h, const uint8_t* d_in, size_t in_frame_strid
     const bool prof = h->profiling;
     int n;
     if (prof) cudaEventRecord(h->ev[1], s);
-    if ((n = launch_pyramid(d, h->fl, h->geom.data(), n_frames, in_frame_stride, s)) < 0) return ORB_ERR_CUDA;
+    if ((n = launch_pyramid(d, h->fl, h->geom.data(), n_frames, in_frame_stride, s)) < 0) {
+        set_error("scale factor too large for the resize kernel's shared-memory tile");
+        return ORB_ERR_ARG;
+    }
     h->launches += n;
     if (prof) cudaEventRecord(h->ev[2], s);
     if ((n = launch_fast_score(d, h->fl, h->geom.data(), n_frames, h->prm.min_th_fast, s)) < 0) return ORB_ERR_CUDA;
@@ -286,7 +307,7 @@ int enqueue_kernels(orbx_handle_s* h, const uint8_t* d_in, size_t in_frame_strid
     if ((n = launch_blur(d, h->fl, h->geom.data(), n_frames, s)) < 0) return ORB_ERR_CUDA;
     h->launches += n;
     if (prof) cudaEventRecord(h->ev[4], s);
-    if ((n = launch_fast_cells(d, h->fl, n_frames, h->prm.ini_th_fast, s)) < 0) return ORB_ERR_CUDA;
+    if ((n = launch_fast_cells(d, h->fl, h->geom.data(), n_frames, h->prm.ini_th_fast, s)) < 0) return ORB_ERR_CUDA;
     h->launches += n;
     if (prof) cudaEventRecord(h->ev[5], s);
     if ((n = launch_octree(d, h->fl, n_frames, s)) < 0) { set_error("quadtree kernel configuration failed"); return ORB_ERR_CUDA; }
@@ -376,7 +397,7 @@ int orbx_destroy(orbx_handle_t h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* dev[] = {h->d_geom, h->d_cells, h->d_xtab, h->d_ytab, h->d_in, h->d_pyr, h->d_blur, h->d_score, h->d_cand,
-                   h->d_scratch, h->d_node, h->d_cell_count, h->d_sel, h->d_level_count, h->d_kps, h->d_desc, h->d_counts};
+                   h->d_scratch, h->d_node, h->d_cell_count, h->d_level_raw, h->d_sel, h->d_level_count, h->d_kps, h->d_desc, h->d_counts};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {h->h_in, h->h_kps, h->h_desc, h->h_counts};
     for (void* p : host) if (p) cudaFreeHost(p);
@@ -613,17 +634,28 @@ int orbx_download_candidates(orbx_handle_t h, int frame, int level, int16_t* x, 
     ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
     const LevelGeom& g = h->geom[level];
     const int ncell = g.n_cols * g.n_rows;
-    std::vector<int32_t> cc(ncell);
-    ORB_CUDA_TRY(cudaMemcpy(cc.data(), h->d_cell_count + (size_t)frame * h->fl.n_cells + g.cell_base, ncell * 4, cudaMemcpyDeviceToHost));
-    const int64_t lvl_entries = (level + 1 < (int)h->geom.size() ? h->geom[level + 1].cand_off : h->fl.cand_entries) - g.cand_off;
-    std::vector<uint32_t> buf(lvl_entries);
-    ORB_CUDA_TRY(cudaMemcpy(buf.data(), h->d_cand + (size_t)frame * h->fl.cand_entries + g.cand_off, lvl_entries * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> flag(ncell);
+    ORB_CUDA_TRY(cudaMemcpy(flag.data(), h->d_cell_count + (size_t)frame * h->fl.n_cells + g.cell_base, ncell * 4, cudaMemcpyDeviceToHost));
+    int32_t nraw = 0;
+    ORB_CUDA_TRY(cudaMemcpy(&nraw, h->d_level_raw + (size_t)frame * kMaxLevels + level, 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> buf(std::max(nraw, 1));
+    ORB_CUDA_TRY(cudaMemcpy(buf.data(), h->d_cand + (size_t)frame * h->fl.cand_entries + g.cand_off, (size_t)nraw * 4, cudaMemcpyDeviceToHost));
+    // same rule as the quadtree gather (iniTh survivors where the cell has any, else all), then the
+    // reference's order: cells row-major, raster inside a cell
+    std::vector<std::pair<uint32_t, uint32_t>> keyed;
+    for (int i = 0; i < nraw; i++) {
+        const uint32_t v = buf[i];
+        const int xr = (int)(v & 0xfff) - 3, yr = (int)((v >> 12) & 0xfff) - 3;
+        const int cx = xr / g.w_cell, cy = yr / g.h_cell;
+        const int cell = cy * g.n_cols + cx;
+        if (flag[cell] && (int)(v >> 24) < h->prm.ini_th_fast) continue;
+        keyed.push_back(std::make_pair(((uint32_t)cell << 12) | (uint32_t)((yr - cy * g.h_cell) * g.w_cell + (xr - cx * g.w_cell)), v));
+    }
+    std::sort(keyed.begin(), keyed.end());
     int k = 0;
-    for (int c = 0; c < ncell; c++) {
-        const uint32_t* s = buf.data() + h->cells[g.cell_base + c].slot_off;
-        for (int i = 0; i < cc[c]; i++, k++) {
-            if (k < cap) { x[k] = (int16_t)(s[i] & 0xfff); y[k] = (int16_t)((s[i] >> 12) & 0xfff); score[k] = (uint8_t)(s[i] >> 24); }
-        }
+    for (size_t i = 0; i < keyed.size(); i++, k++) {
+        const uint32_t v = keyed[i].second;
+        if (k < cap) { x[k] = (int16_t)(v & 0xfff); y[k] = (int16_t)((v >> 12) & 0xfff); score[k] = (uint8_t)(v >> 24); }
     }
     *n = k;
     return ORB_OK;

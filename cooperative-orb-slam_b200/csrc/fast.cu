@@ -8,9 +8,10 @@
 //                      (max over the 16 arcs of 9 of max(min(I_p - I_k), min(I_k - I_p))) - 1 where that
 //                      maximum exceeds the threshold, else 0.  FAST(th=20) == {FAST(th=7): score >= 20}
 //                       so one map serves both thresholds.
-//   fast_cell_kernel   one warp per cell: strict 3x3 non-max suppression that ignores neighbours
-//                      outside the cell interior (cv::FAST is called on the cell sub-image), per-cell
-//                      iniTh -> minTh fallback, ordered compaction (raster inside the cell).
+//   fast_nms_kernel    dense strict 3x3 non-max suppression that ignores neighbours outside the pixel's
+//                      cell interior (cv::FAST is called on the cell sub-image); survivors are appended
+//                      to the level's candidate list.  The per-cell iniTh -> minTh fallback happens in
+//                      the quadtree kernel's gather (octree.cu).
 #include "internal.h"
 
 namespace orbcuda {
@@ -153,88 +154,135 @@ int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-cell NMS + threshold fallback + ordered compaction.  One warp per cell.
+// K3b: dense cell-aware non-max suppression + candidate emission.  A pixel survives if its score is
+// strictly greater than its 8 neighbours, counting neighbours outside the pixel's own FAST cell interior
+// as 0 (cv::FAST runs on the cell sub-image, so its NMS never sees them).  Cell interiors tile
+// [19,W-19)x[19,H-19) with period (wCell,hCell) (R21 :773-807), so "is this pixel on its cell's
+// left/right/top/bottom edge" is a function of (x-19) mod wCell and (y-19) mod hCell.  4 pixels (packed
+// bytes) per thread, rows roll through registers.  Survivors (1-2 % of the pixels) are buffered in
+// registers and appended to the level's list with ONE atomic per warp (shuffle prefix); a survivor
+// reaching iniThFAST also raises its cell's flag (plain store).  The list order is arbitrary: the
+// quadtree kernel applies the per-cell iniTh -> minTh fallback from the flags and resolves ties with an
+// explicit (cell, raster) order key, so nothing downstream depends on it.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool nms_keep(const uint8_t* __restrict__ sc, int pitch, int x, int y, int s, int x0, int y0,
-                                         int x1, int y1) {
-    bool keep = true;
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++) {
-        const int ny = y + dy;
-        if (ny < y0 || ny >= y1) continue;   // outside the cell interior counts as 0 (< s)
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-            if (dx == 0 && dy == 0) continue;
-            const int nx = x + dx;
-            if (nx < x0 || nx >= x1) continue;
-            keep = keep && (s > (int)sc[(size_t)ny * pitch + nx]);
-        }
-    }
-    return keep;
-}
+constexpr int kNmsRows = 16;
 
-__global__ void __launch_bounds__(256) fast_cell_kernel(const uint8_t* __restrict__ score, int64_t score_frame_bytes,
-                                                        uint32_t* __restrict__ cand, int64_t cand_frame_entries,
-                                                        int32_t* __restrict__ cell_count, int n_cells,
-                                                        const LevelGeom* __restrict__ geom, int nlevels,
-                                                        const CellInfo* __restrict__ cells, int ini_th) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_cells) return;
-    const int frame = blockIdx.y;
-    const CellInfo c = cells[warp];
+__global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict__ score, int64_t plane_frame_bytes,
+                                                       uint32_t* __restrict__ cand, int64_t cand_frame_entries,
+                                                       int32_t* __restrict__ cell_flag, int n_cells,
+                                                       int32_t* __restrict__ level_raw, const LevelGeom* __restrict__ geom,
+                                                       int nlevels, LevelBlocks lb, int ini_th) {
     int level = 0;
-    while (level + 1 < nlevels && warp >= geom[level + 1].cell_base) level++;
-    const int pitch = geom[level].spitch;
-    const uint8_t* sc = score + (size_t)frame * score_frame_bytes + geom[level].splane_off;
-    uint32_t* out = cand + (size_t)frame * cand_frame_entries + geom[level].cand_off + c.slot_off;
-    const int iw = c.x1 - c.x0, ih = c.y1 - c.y0;
-    const int npx = iw > 0 && ih > 0 ? iw * ih : 0;
-    const uint32_t magic = iw > 0 ? ((1u << 20) + iw - 1) / iw : 0;   // idx / iw == (idx*magic)>>20 for idx < 4096
-
-    // pass 1: does any NMS survivor reach iniThFAST?
-    bool any_hi = false;
-    for (int base = 0; base < npx; base += 32) {
-        const int idx = base + lane;
-        bool hi = false;
-        if (idx < npx) {
-            const int ry = (int)(((uint32_t)idx * magic) >> 20);
-            const int x = c.x0 + idx - ry * iw, y = c.y0 + ry;
-            const int s = sc[(size_t)y * pitch + x];
-            if (s >= ini_th) hi = nms_keep(sc, pitch, x, y, s, c.x0, c.y0, c.x1, c.y1);
-        }
-        any_hi = any_hi || __any_sync(0xffffffffu, hi);
-        if (any_hi) break;
-    }
-    const int th = any_hi ? ini_th : 1;   // the score map is already 0 below minThFAST
-    // pass 2: ordered emission
-    int count = 0;
-    for (int base = 0; base < npx; base += 32) {
-        const int idx = base + lane;
-        bool keep = false;
-        uint32_t packed = 0;
-        if (idx < npx) {
-            const int ry = (int)(((uint32_t)idx * magic) >> 20);
-            const int x = c.x0 + idx - ry * iw, y = c.y0 + ry;
-            const int s = sc[(size_t)y * pitch + x];
-            if (s >= th) {
-                keep = nms_keep(sc, pitch, x, y, s, c.x0, c.y0, c.x1, c.y1);
-                packed = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | ((uint32_t)s << 24);
+    while (level + 1 < nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
+    const LevelGeom g = geom[level];
+    const int lane = threadIdx.x & 31;
+    const int nsx = (g.w - kEdge - kMinBorder + 3) >> 2;     // same strips as the score kernel: x0 = 16 + 4*sx
+    const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
+    const int sy = id / nsx;
+    const int x0 = kMinBorder + 4 * (id - sy * nsx);
+    const int y0 = kEdge + sy * kNmsRows;
+    const bool active = y0 < g.h - kEdge;
+    uint32_t* list = cand + (size_t)blockIdx.y * cand_frame_entries + g.cand_off;
+    int32_t* counter = level_raw + (size_t)blockIdx.y * kMaxLevels + level;
+    uint32_t pend[4];
+    int npend = 0;
+    if (active) {
+        const uint8_t* src = score + (size_t)blockIdx.y * plane_frame_bytes + g.splane_off + x0;
+        // per-column validity masks (bytes): pixel in range / its left neighbour in the same cell / its right one
+        uint32_t MC = 0, ML = 0, MR = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int x = x0 + b;
+            if (x >= kEdge && x < g.w - kEdge) {
+                const int m = (x - kEdge) % g.w_cell;
+                MC |= 0xffu << (8 * b);
+                if (m != 0) ML |= 0xffu << (8 * b);
+                if (m != g.w_cell - 1 && x != g.w - kEdge - 1) MR |= 0xffu << (8 * b);
             }
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        if (keep) out[count + __popc(m & ((1u << lane) - 1))] = packed;
-        count += __popc(m);
+        // h3(row) = bytewise max of (left, centre, right) with out-of-cell horizontal neighbours zeroed
+        auto load = [&](int y, uint32_t& c, uint32_t& lr) -> uint32_t {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)y * g.spitch);
+            const uint32_t w0 = p[-1], w1 = p[0], w2 = p[1];
+            const uint32_t L = __funnelshift_l(w0, w1, 8) & ML;      // byte b = pixel x0+b-1
+            const uint32_t R = __funnelshift_r(w1, w2, 8) & MR;      // byte b = pixel x0+b+1
+            c = w1;
+            lr = __vmaxu4(L, R);
+            return __vmaxu4(lr, w1);
+        };
+        int ymod = (y0 - kEdge) % g.h_cell;
+        int cy = (y0 - kEdge) / g.h_cell;
+        const int cx0 = (max(x0, kEdge) - kEdge) / g.w_cell;     // cell column of the 4 pixels: cx0 or cx0+1
+        const int xnext = kEdge + (cx0 + 1) * g.w_cell;
+        int32_t* flags = cell_flag + (size_t)blockIdx.y * n_cells + g.cell_base;
+        uint32_t c_cur, lr_cur, c_nxt, lr_nxt, c_tmp, lr_tmp;
+        uint32_t h_prev = load(y0 - 1, c_tmp, lr_tmp);   // masked out at a cell's top row, so row 18 is never used
+        uint32_t h_cur = load(y0, c_cur, lr_cur);
+#pragma unroll 4
+        for (int r = 0; r < kNmsRows; r++) {
+            const int y = y0 + r;
+            if (y >= g.h - kEdge) break;
+            const uint32_t h_nxt = load(y + 1, c_nxt, lr_nxt);
+            const bool top = ymod == 0, bot = ymod == g.h_cell - 1 || y == g.h - kEdge - 1;
+            const uint32_t up = top ? 0u : h_prev, dn = bot ? 0u : h_nxt;
+            const uint32_t m = __vmaxu4(__vmaxu4(up, dn), lr_cur);
+            const uint32_t kept = c_cur & __vcmpgtu4(c_cur, m) & MC;   // strict: equal neighbours suppress each other
+            if (kept) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t sc = (kept >> (8 * b)) & 0xffu;
+                    if (sc) {
+                        const int x = x0 + b;
+                        const uint32_t v = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | (sc << 24);
+                        if ((int)sc >= ini_th) flags[cy * g.n_cols + cx0 + (x >= xnext ? 1 : 0)] = 1;
+                        if (npend == 4) {   // rare overflow: append one entry directly
+                            list[atomicAdd(counter, 1)] = v;
+                        } else {
+                            // static indexing keeps the buffer in registers
+                            if (npend == 0) pend[0] = v; else if (npend == 1) pend[1] = v; else if (npend == 2) pend[2] = v; else pend[3] = v;
+                            npend++;
+                        }
+                    }
+                }
+            }
+            h_prev = h_cur; h_cur = h_nxt; c_cur = c_nxt; lr_cur = lr_nxt;
+            if (++ymod == g.h_cell) { ymod = 0; cy++; }
+        }
     }
-    if (lane == 0) cell_count[(size_t)frame * n_cells + warp] = count;
+    // warp-aggregated append: one atomic per warp
+    int incl = npend;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - npend;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (i < npend) list[base + i] = pend[i];
 }
 
-int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, int n_frames, int ini_th, cudaStream_t s) {
-    const int threads = 256;
-    const int blocks = (fl.n_cells * 32 + threads - 1) / threads;
-    fast_cell_kernel<<<dim3(blocks, n_frames), threads, 0, s>>>(d.score, fl.splane_bytes, d.cand, fl.cand_entries,
-                                                                d.cell_count, fl.n_cells, d.geom, fl.nlevels, d.cells,
-                                                                ini_th);
+int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, int ini_th,
+                      cudaStream_t s) {
+    LevelBlocks lb;
+    int total = 0;
+    const int nthreads = 128;
+    for (int l = 0; l < fl.nlevels; l++) {
+        lb.start[l] = total;
+        const int nsx = (hg[l].w - kEdge - kMinBorder + 3) / 4;
+        const int nsy = (hg[l].h - 2 * kEdge + kNmsRows - 1) / kNmsRows;
+        total += (nsx * nsy + nthreads - 1) / nthreads;
+    }
+    for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
+    if (cudaMemsetAsync(d.cell_count, 0, (size_t)n_frames * fl.n_cells * sizeof(int32_t), s) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(d.level_raw, 0, (size_t)n_frames * kMaxLevels * sizeof(int32_t), s) != cudaSuccess) return -1;
+    fast_nms_kernel<<<dim3(total, n_frames), nthreads, 0, s>>>(d.score, fl.splane_bytes, d.cand, fl.cand_entries,
+                                                               d.cell_count, fl.n_cells, d.level_raw, d.geom, fl.nlevels, lb,
+                                                               ini_th);
     return 1;
 }
 

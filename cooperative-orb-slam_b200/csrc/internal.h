@@ -13,6 +13,8 @@ constexpr int kEdge = 19;          // EDGE_THRESHOLD (R21 ORBextractor.cc:74)
 constexpr int kXPad = 32;          // interior column origin inside a padded plane (16-B aligned)
 constexpr int kMinBorder = 16;     // EDGE_THRESHOLD-3 (R21 :773)
 constexpr int kMaxLevels = ORB_MAX_LEVELS;
+constexpr int kPyrTileW = 128;     // output tile of the resize kernel
+constexpr int kPyrTileH = 64;       // 8 warps x 8 rows
 
 // Geometry of one pyramid level for the current image size.  Lives in device constant-like global
 // memory (one array per handle) and on the host.
@@ -35,6 +37,7 @@ struct LevelGeom {
     int kp_cap;             // slot size
     // resize tables for producing this level from level-1 (offsets into the table buffers)
     int xtab_off, ytab_off;
+    int rs_rows, rs_cols;   // source rows / columns (word aligned) one kPyrTileH x kPyrTileW output tile of this level needs
     float scale;            // mvScaleFactor[level]
     float patch_size;       // (float)(int)(31*scale)
 };
@@ -60,6 +63,7 @@ struct FrameLayout {        // sizes of the per-frame device blocks
     int64_t cand_entries;   // candidate slot entries (uint32) per frame
     int kp_cap;             // keypoint slots per frame
     int node_cap;           // quadtree node capacity
+    int ini_th;             // iniThFAST (per-cell threshold fallback, applied in the quadtree gather)
 };
 
 // flattened (level, block) grids: blocks [start[l], start[l+1]) belong to level l
@@ -72,9 +76,10 @@ struct DevPtrs {
     const uint8_t* in;          // [B][height][in_pitch]
     uint8_t* pyr;               // [B][pyr_bytes]
     uint8_t* blur;              // [B][splane_bytes]
-    uint8_t* score;             // [B][splane_bytes]
-    uint32_t* cand;             // [B][cand_entries]  packed x | y<<12 | score<<24 (relative to 16,16)
-    int32_t* cell_count;        // [B][n_cells]
+    uint8_t* score;             // [B][splane_bytes]  FAST score at minThFAST
+    uint32_t* cand;             // [B][cand_entries]  per level: NMS survivors, packed x | y<<12 | score<<24 (relative to 16,16)
+    int32_t* cell_count;        // [B][n_cells]  flag: the cell holds a survivor with score >= iniThFAST
+    int32_t* level_raw;         // [B][kMaxLevels] NMS survivors appended to each level's list
     uint32_t* oct_scratch;      // [B][cand_entries] packed candidates in list order (quadtree input)
     uint16_t* oct_node;         // [B][cand_entries] node id per candidate
     uint32_t* sel;              // [B][kp_cap] selected candidate (packed) per slot
@@ -90,7 +95,8 @@ int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hge
 int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, int min_th,
                       cudaStream_t s);
 int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, cudaStream_t s);
-int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, int n_frames, int ini_th, cudaStream_t s);
+int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, int ini_th,
+                      cudaStream_t s);
 int launch_octree(const DevPtrs& d, const FrameLayout& fl, int n_frames, cudaStream_t s);
 int launch_describe(const DevPtrs& d, const FrameLayout& fl, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
                     int32_t* d_counts, int cap, cudaStream_t s);

@@ -74,7 +74,8 @@ __device__ __forceinline__ int quadrant_of(uint32_t kp, short4 b) {
 // kp[0..n): packed candidates in input order; node[0..n): scratch; out_sel[0..kp_cap): selected
 // candidates in list order; returns the number of nodes (all threads).
 __device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, int height, int N, int n_ini, float h_x,
-                          uint32_t* out_sel, int32_t* out_idx, int cap, unsigned char* smem_raw) {
+                          uint32_t* out_sel, int32_t* out_idx, int cap, unsigned char* smem_raw, int order_cols, int w_cell,
+                          int h_cell) {
     __shared__ int wsum[17];
     __shared__ int s_flag[4];
     const int tid = threadIdx.x;
@@ -285,17 +286,30 @@ __device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, 
         }
         __syncthreads();
     }
-    // ---- keep the best key point of each node (R21 :741-760): max response, first in input order on ties
-    unsigned* best = reinterpret_cast<unsigned*>(S.a0);
-    for (int i = tid; i < alive; i += kOctThreads) best[i] = 0u;
+    // ---- keep the best key point of each node (R21 :741-760): max response, first in input order on ties.
+    // "Input order" is cell-major, raster inside a cell (:789-826).  With order_cols > 0 that rank is computed
+    // from the coordinates (the list itself may be in any order); with order_cols == 0 it is the list index.
+    unsigned long long* best = S.key;
+    for (int i = tid; i < alive; i += kOctThreads) best[i] = 0ull;
     __syncthreads();
-    for (int k = tid; k < n; k += kOctThreads)
-        atomicMax(&best[node[k]], ((kp[k] >> 24) << 24) | (0xffffffu - (unsigned)k));
+    auto order_of = [&](int k, uint32_t v) -> unsigned {
+        if (order_cols <= 0) return (unsigned)k;
+        const int xr = (int)(v & 0xfff) - 3, yr = (int)((v >> 12) & 0xfff) - 3;   // relative to the first cell interior (19,19)
+        const int cx = xr / w_cell, cyy = yr / h_cell;
+        return ((unsigned)(cyy * order_cols + cx) << 12) | (unsigned)((yr - cyy * h_cell) * w_cell + (xr - cx * w_cell));
+    };
+    for (int k = tid; k < n; k += kOctThreads) {
+        const uint32_t v = kp[k];
+        atomicMax(&best[node[k]], ((unsigned long long)(v >> 24) << 32) | (0xffffffffu - order_of(k, v)));
+    }
     __syncthreads();
-    for (int i = tid; i < alive; i += kOctThreads) {
-        const unsigned k = 0xffffffu - (best[i] & 0xffffffu);
-        out_sel[alive - 1 - i] = kp[k];   // list order == descending creation index
-        if (out_idx) out_idx[alive - 1 - i] = (int32_t)k;
+    for (int k = tid; k < n; k += kOctThreads) {
+        const uint32_t v = kp[k];
+        const int nd = node[k];
+        if (best[nd] == (((unsigned long long)(v >> 24) << 32) | (0xffffffffu - order_of(k, v)))) {
+            out_sel[alive - 1 - nd] = v;   // list order == descending creation index
+            if (out_idx) out_idx[alive - 1 - nd] = (int32_t)k;
+        }
     }
     return alive;
 }
@@ -308,30 +322,46 @@ size_t octree_smem_bytes(int cap) {
 __global__ void __launch_bounds__(kOctThreads) octree_kernel(DevPtrs d, FrameLayout fl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_total;
-    __shared__ int s_wsum[17];
     const int level = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
     const LevelGeom g = d.geom[level];
-    const int ncell = g.n_cols * g.n_rows;
     const int32_t* cc = d.cell_count + (size_t)frame * fl.n_cells + g.cell_base;
     const uint32_t* cand = d.cand + (size_t)frame * fl.cand_entries + g.cand_off;
     uint32_t* kp = d.oct_scratch + (size_t)frame * fl.cand_entries + g.cand_off;
     uint16_t* node = d.oct_node + (size_t)frame * fl.cand_entries + g.cand_off;
-    // gather the per-cell lists into one cell-major list (the order of vToDistributeKeys, R21 :789-826)
+    // Filter the level's NMS survivors into the quadtree's input list (vToDistributeKeys, R21 :789-826): a
+    // cell whose flag is up holds a survivor reaching iniThFAST and keeps only those (== cv::FAST(cell,
+    // iniThFAST)); otherwise it keeps all (== the minThFAST retry, :809-816).  The list order is arbitrary:
+    // nothing in the quadtree depends on it except the "first maximum wins" rule, which octree_run resolves
+    // with an explicit (cell, raster) order key instead of the list position.
     int running = 0;
-    int* offs = reinterpret_cast<int*>(smem_raw);
-    for (int base = 0; base < ncell; base += kOctThreads) {
-        const int c = base + tid;
-        const int cnt = c < ncell ? cc[c] : 0;
-        offs[tid] = cnt;
-        __syncthreads();
-        const int tot = block_excl_scan(offs, kOctThreads, s_wsum);
-        if (c < ncell && cnt > 0) {
-            const uint32_t* src = cand + d.cells[g.cell_base + c].slot_off;
-            uint32_t* dst = kp + running + offs[tid];
-            for (int k = 0; k < cnt; k++) dst[k] = src[k];
+    {
+        const int nraw = d.level_raw[(size_t)frame * kMaxLevels + level];
+        const int lane = tid & 31, wid = tid >> 5;
+        int* wcnt = reinterpret_cast<int*>(smem_raw);   // [16] warp counts, [16..31] exclusive bases
+        for (int base = 0; base < nraw; base += kOctThreads) {
+            const int i = base + tid;
+            uint32_t v = 0;
+            bool pass = false;
+            if (i < nraw) {
+                v = cand[i];
+                const int xr = (int)(v & 0xfff) - 3, yr = (int)((v >> 12) & 0xfff) - 3;
+                const int cell = (yr / g.h_cell) * g.n_cols + xr / g.w_cell;
+                pass = cc[cell] == 0 || (int)(v >> 24) >= fl.ini_th;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) wcnt[wid] = __popc(m);
+            __syncthreads();
+            if (wid == 0) {
+                const int c = lane < kOctThreads / 32 ? wcnt[lane] : 0;
+                const int inc = warp_incl_scan(c, lane);
+                if (lane < kOctThreads / 32) wcnt[16 + lane] = inc - c;
+                if (lane == kOctThreads / 32 - 1) wcnt[32] = inc;
+            }
+            __syncthreads();
+            if (pass) kp[running + wcnt[16 + wid] + __popc(m & ((1u << lane) - 1))] = v;
+            running += wcnt[32];
+            __syncthreads();
         }
-        running += tot;
-        __syncthreads();
     }
     if (tid == 0) s_total = running;
     __syncthreads();
@@ -340,7 +370,8 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(DevPtrs d, FrameLay
     if (n > 0) {
         __threadfence_block();
         count = octree_run(kp, node, n, g.w - 2 * kMinBorder, g.h - 2 * kMinBorder, g.n_feat, g.n_ini, g.h_x,
-                           d.sel + (size_t)frame * fl.kp_cap + g.kp_slot, nullptr, fl.node_cap, smem_raw);
+                           d.sel + (size_t)frame * fl.kp_cap + g.kp_slot, nullptr, fl.node_cap, smem_raw, g.n_cols, g.w_cell,
+                           g.h_cell);
     }
     if (tid == 0) d.level_count[(size_t)frame * kMaxLevels + level] = count;
 }
@@ -363,7 +394,7 @@ __global__ void __launch_bounds__(kOctThreads) octree_single_kernel(const uint32
                                                                     uint32_t* sel, int32_t* sel_idx, int32_t* count,
                                                                     int node_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = n > 0 ? octree_run(kp, node, n, width, height, n_feat, n_ini, h_x, sel, sel_idx, node_cap, smem_raw) : 0;
+    const int c = n > 0 ? octree_run(kp, node, n, width, height, n_feat, n_ini, h_x, sel, sel_idx, node_cap, smem_raw, 0, 1, 1) : 0;
     if (threadIdx.x == 0) *count = c;
 }
 

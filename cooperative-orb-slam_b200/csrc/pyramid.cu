@@ -47,47 +47,134 @@ __global__ void __launch_bounds__(256) pyr_level0_kernel(const uint8_t* __restri
 // (R21 :1118-1123).  cv::resize 8-bit linear: 11-bit fixed-point taps, int32 horizontal pass,
 // vertical pass (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.  Taps are computed on the host
 // exactly as OpenCV does (float -> saturate_cast<short>) and read from a table.
+//
+// One CTA produces a kPyrTileW x kPyrTileH tile of the level interior.  The source footprint is staged in
+// shared memory with coalesced 32-bit loads.  Each thread owns 4 adjacent output columns (its 8 horizontal
+// taps stay in registers) and each warp streams down 8 output rows: the horizontal pass of a source row
+// ((r>>4), 16 bits) is computed once and reused by the next output row, the vertical pass combines the two
+// live rows and the 4 results leave as one 32-bit store.  Pixels within 19 px of an edge are also stored to
+// their REFLECT_101 mirror positions, so the border needs no second pass.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* pyr, int64_t pyr_frame_bytes,
-                                                         LevelGeom gs, LevelGeom gd,
-                                                         const ResizeTap* __restrict__ xtab,
+__global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* pyr, int64_t pyr_frame_bytes, LevelGeom gs,
+                                                         LevelGeom gd, const ResizeTap* __restrict__ xtab,
                                                          const ResizeTap* __restrict__ ytab) {
-    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int py = blockIdx.y * blockDim.y + threadIdx.y;
-    const int px0 = 12 + 4 * wx;
-    if (px0 >= kXPad + gd.w + kEdge || py >= gd.plane_rows) return;
+    extern __shared__ __align__(16) unsigned char s_src[];   // [rs_rows][rs_cols]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * kPyrTileW, y0 = blockIdx.y * kPyrTileH;
+    const int tw = min(kPyrTileW, gd.w - x0), th = min(kPyrTileH, gd.h - y0);
     uint8_t* frame = pyr + (size_t)blockIdx.z * pyr_frame_bytes;
     const uint8_t* src = frame + gs.plane_off + (size_t)kEdge * gs.pitch + kXPad;   // ROI origin of level l-1
-    uint8_t* dst = frame + gd.plane_off;
-    const int dy = reflect101(py - kEdge, gd.h);
-    const ResizeTap ty = ytab[gd.ytab_off + dy];
-    const uint8_t* S0 = src + (size_t)ty.ofs * gs.pitch;
-    const uint8_t* S1 = src + (size_t)ty.pad * gs.pitch;
-    uint32_t v = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        const int dx = reflect101(px0 + b - kXPad, gd.w);
-        const ResizeTap tx = xtab[gd.xtab_off + dx];
-        const int r0 = S0[tx.ofs] * tx.c0 + S0[tx.pad] * tx.c1;
-        const int r1 = S1[tx.ofs] * tx.c0 + S1[tx.pad] * tx.c1;
-        const int o = (((ty.c0 * (r0 >> 4)) >> 16) + ((ty.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        v |= (uint32_t)(o & 0xff) << (8 * b);
+    uint8_t* dst = frame + gd.plane_off + (size_t)kEdge * gd.pitch + kXPad;          // ROI origin of level l
+    const ResizeTap* xt = xtab + gd.xtab_off;
+    const ResizeTap* yt = ytab + gd.ytab_off;
+    // source footprint of the tile
+    const int sxa = xt[x0].ofs & ~3;
+    const int sxe = xt[x0 + tw - 1].pad;
+    const int sy0 = yt[y0].ofs;
+    const int nrows = yt[y0 + th - 1].pad - sy0 + 1;
+    const int nwords = (sxe - sxa + 4) >> 2;       // <= 64 (checked on the host)
+    const int spitch = gd.rs_cols;                 // bytes per staged row (multiple of 4)
+    {
+        const int wcol = tid & 63;
+        if (wcol < nwords) {
+            const uint8_t* gp = src + (size_t)sy0 * gs.pitch + sxa + 4 * wcol;
+            for (int r = tid >> 6; r < nrows; r += 4)
+                reinterpret_cast<uint32_t*>(s_src + r * spitch)[wcol] =
+                    *reinterpret_cast<const uint32_t*>(gp + (size_t)r * gs.pitch);
+        }
     }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)py * gd.pitch + px0) = v;
+    const int X0 = x0 + 4 * lane;
+    const int npx = max(0, min(4, tw - 4 * lane));
+    int o0[4], o1[4], c0[4], c1[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const ResizeTap t = xt[min(X0 + i, gd.w - 1)];
+        o0[i] = t.ofs - sxa; o1[i] = t.pad - sxa; c0[i] = t.c0; c1[i] = t.c1;
+    }
+    __syncthreads();
+    if (npx == 0) return;
+    auto hrow = [&](int r, int (&hh)[4]) {
+        const uint8_t* S = s_src + r * spitch;
+#pragma unroll
+        for (int i = 0; i < 4; i++) hh[i] = (S[o0[i]] * c0[i] + S[o1[i]] * c1[i]) >> 4;
+    };
+    constexpr int kNone = -(1 << 20);
+    const bool xedge = X0 <= kEdge || X0 + 3 >= gd.w - 1 - kEdge;
+    int lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    int r_lo = kNone, r_hi = kNone;
+    const int dy_end = min(th, warp * 8 + 8);
+    for (int dy = warp * 8; dy < dy_end; dy++) {
+        const int Y = y0 + dy;
+        const ResizeTap ty = yt[Y];
+        const int r0 = ty.ofs - sy0, r1 = ty.pad - sy0;
+        if (r0 != r_lo) {
+            if (r0 == r_hi) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) lo[i] = hi[i];
+            } else {
+                hrow(r0, lo);
+            }
+            r_lo = r0;
+        }
+        if (r1 != r_hi) {
+            if (r1 == r_lo) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) hi[i] = lo[i];
+            } else {
+                hrow(r1, hi);
+            }
+            r_hi = r1;
+        }
+        const int b0 = ty.c0, b1 = ty.c1;
+        uint32_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = (uint32_t)((((b0 * lo[i]) >> 16) + ((b1 * hi[i]) >> 16) + 2) >> 2) & 0xffu;
+        int ym = kNone;
+        if (Y >= 1 && Y <= kEdge) ym = -Y;
+        else if (Y >= gd.h - 1 - kEdge && Y <= gd.h - 2) ym = 2 * (gd.h - 1) - Y;
+        uint8_t* row = dst + (ptrdiff_t)Y * gd.pitch;
+        uint8_t* mrow = dst + (ptrdiff_t)(ym == kNone ? Y : ym) * gd.pitch;
+        if (npx == 4) {
+            const uint32_t pk = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+            *reinterpret_cast<uint32_t*>(row + X0) = pk;
+            if (ym != kNone) *reinterpret_cast<uint32_t*>(mrow + X0) = pk;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                if (i < npx) { row[X0 + i] = (uint8_t)v[i]; if (ym != kNone) mrow[X0 + i] = (uint8_t)v[i]; }
+        }
+        if (xedge) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int X = X0 + i;
+                int xm = kNone;
+                if (X >= 1 && X <= kEdge) xm = -X;
+                else if (X >= gd.w - 1 - kEdge && X <= gd.w - 2) xm = 2 * (gd.w - 1) - X;
+                if (i < npx && xm != kNone) {
+                    row[xm] = (uint8_t)v[i];
+                    if (ym != kNone) mrow[xm] = (uint8_t)v[i];
+                }
+            }
+        }
+    }
 }
 
 int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, size_t in_frame_stride,
                    cudaStream_t s) {
-    const dim3 block(64, 4);
     int launches = 0;
     for (int l = 0; l < fl.nlevels; l++) {
         const LevelGeom& g = hg[l];
-        const int nwords = (kXPad + g.w + kEdge - 12 + 3) / 4;
-        const dim3 grid((nwords + block.x - 1) / block.x, (g.plane_rows + block.y - 1) / block.y, n_frames);
-        if (l == 0)
+        if (l == 0) {
+            const dim3 block(64, 4);
+            const int nwords = (kXPad + g.w + kEdge - 12 + 3) / 4;
+            const dim3 grid((nwords + block.x - 1) / block.x, (g.plane_rows + block.y - 1) / block.y, n_frames);
             pyr_level0_kernel<<<grid, block, 0, s>>>(d.in, in_frame_stride, fl.in_pitch, d.pyr, fl.pyr_bytes, g);
-        else
-            pyr_resize_kernel<<<grid, block, 0, s>>>(d.pyr, fl.pyr_bytes, hg[l - 1], g, d.xtab, d.ytab);
+        } else {
+            const size_t smem = (size_t)g.rs_rows * g.rs_cols;
+            if (smem > 48 * 1024 || g.rs_cols > 256) return -1;   // scale factors this large are not supported
+            const dim3 grid((g.w + kPyrTileW - 1) / kPyrTileW, (g.h + kPyrTileH - 1) / kPyrTileH, n_frames);
+            pyr_resize_kernel<<<grid, 256, smem, s>>>(d.pyr, fl.pyr_bytes, hg[l - 1], g, d.xtab, d.ytab);
+        }
         launches++;
     }
     return launches;
