@@ -184,10 +184,11 @@ __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict
     const bool active = y0 < g.h - kEdge;
     uint32_t* list = cand + (size_t)blockIdx.y * cand_frame_entries + g.cand_off;
     int32_t* counter = level_raw + (size_t)blockIdx.y * kMaxLevels + level;
-    uint32_t pend[4];
-    int npend = 0;
+    // survivor bitmask of the strip: bit (4*r + b) of km[r / 8] <=> pixel (x0+b, y0+r) survives
+    uint32_t km0 = 0, km1 = 0;
+    const uint8_t* src = score + (size_t)blockIdx.y * plane_frame_bytes + g.splane_off + x0;
+    int cy0 = 0, ymod0 = 0;
     if (active) {
-        const uint8_t* src = score + (size_t)blockIdx.y * plane_frame_bytes + g.splane_off + x0;
         // per-column validity masks (bytes): pixel in range / its left neighbour in the same cell / its right one
         uint32_t MC = 0, ML = 0, MR = 0;
 #pragma unroll
@@ -200,57 +201,42 @@ __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict
                 if (m != g.w_cell - 1 && x != g.w - kEdge - 1) MR |= 0xffu << (8 * b);
             }
         }
+        ymod0 = (y0 - kEdge) % g.h_cell;
+        cy0 = (y0 - kEdge) / g.h_cell;
+        int ymod = ymod0;
+        // all rows of the strip are fetched up front (54 independent 32-bit loads in flight per thread)
+        const int ylast = g.h - kEdge;   // row H-19 exists in the plane; it is masked out below
+        uint32_t W0[kNmsRows + 2], W1[kNmsRows + 2], W2[kNmsRows + 2];
+#pragma unroll
+        for (int r = 0; r < kNmsRows + 2; r++) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)min(y0 - 1 + r, ylast) * g.spitch);
+            W0[r] = p[-1]; W1[r] = p[0]; W2[r] = p[1];
+        }
         // h3(row) = bytewise max of (left, centre, right) with out-of-cell horizontal neighbours zeroed
-        auto load = [&](int y, uint32_t& c, uint32_t& lr) -> uint32_t {
-            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)y * g.spitch);
-            const uint32_t w0 = p[-1], w1 = p[0], w2 = p[1];
-            const uint32_t L = __funnelshift_l(w0, w1, 8) & ML;      // byte b = pixel x0+b-1
-            const uint32_t R = __funnelshift_r(w1, w2, 8) & MR;      // byte b = pixel x0+b+1
-            c = w1;
-            lr = __vmaxu4(L, R);
-            return __vmaxu4(lr, w1);
-        };
-        int ymod = (y0 - kEdge) % g.h_cell;
-        int cy = (y0 - kEdge) / g.h_cell;
-        const int cx0 = (max(x0, kEdge) - kEdge) / g.w_cell;     // cell column of the 4 pixels: cx0 or cx0+1
-        const int xnext = kEdge + (cx0 + 1) * g.w_cell;
-        int32_t* flags = cell_flag + (size_t)blockIdx.y * n_cells + g.cell_base;
-        uint32_t c_cur, lr_cur, c_nxt, lr_nxt, c_tmp, lr_tmp;
-        uint32_t h_prev = load(y0 - 1, c_tmp, lr_tmp);   // masked out at a cell's top row, so row 18 is never used
-        uint32_t h_cur = load(y0, c_cur, lr_cur);
-#pragma unroll 4
+        uint32_t LR[kNmsRows + 2], H3[kNmsRows + 2];
+#pragma unroll
+        for (int r = 0; r < kNmsRows + 2; r++) {
+            const uint32_t L = __funnelshift_l(W0[r], W1[r], 8) & ML;      // byte b = pixel x0+b-1
+            const uint32_t R = __funnelshift_r(W1[r], W2[r], 8) & MR;      // byte b = pixel x0+b+1
+            LR[r] = __vmaxu4(L, R);
+            H3[r] = __vmaxu4(LR[r], W1[r]);
+        }
+#pragma unroll
         for (int r = 0; r < kNmsRows; r++) {
             const int y = y0 + r;
-            if (y >= g.h - kEdge) break;
-            const uint32_t h_nxt = load(y + 1, c_nxt, lr_nxt);
             const bool top = ymod == 0, bot = ymod == g.h_cell - 1 || y == g.h - kEdge - 1;
-            const uint32_t up = top ? 0u : h_prev, dn = bot ? 0u : h_nxt;
-            const uint32_t m = __vmaxu4(__vmaxu4(up, dn), lr_cur);
-            const uint32_t kept = c_cur & __vcmpgtu4(c_cur, m) & MC;   // strict: equal neighbours suppress each other
-            if (kept) {
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const uint32_t sc = (kept >> (8 * b)) & 0xffu;
-                    if (sc) {
-                        const int x = x0 + b;
-                        const uint32_t v = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | (sc << 24);
-                        if ((int)sc >= ini_th) flags[cy * g.n_cols + cx0 + (x >= xnext ? 1 : 0)] = 1;
-                        if (npend == 4) {   // rare overflow: append one entry directly
-                            list[atomicAdd(counter, 1)] = v;
-                        } else {
-                            // static indexing keeps the buffer in registers
-                            if (npend == 0) pend[0] = v; else if (npend == 1) pend[1] = v; else if (npend == 2) pend[2] = v; else pend[3] = v;
-                            npend++;
-                        }
-                    }
-                }
-            }
-            h_prev = h_cur; h_cur = h_nxt; c_cur = c_nxt; lr_cur = lr_nxt;
-            if (++ymod == g.h_cell) { ymod = 0; cy++; }
+            const uint32_t up = top ? 0u : H3[r], dn = bot ? 0u : H3[r + 2];   // row 18 / H-19 never used: masked here
+            const uint32_t m = __vmaxu4(__vmaxu4(up, dn), LR[r + 1]);
+            uint32_t keep = __vcmpgtu4(W1[r + 1], m) & MC;      // strict: equal neighbours suppress each other
+            if (y >= g.h - kEdge) keep = 0;
+            const uint32_t bits = ((keep & 0x08040201u) * 0x01010101u) >> 24;   // 0xff bytes -> 4 bits
+            if (r < 8) km0 |= bits << (4 * r); else km1 |= bits << (4 * (r - 8));
+            if (++ymod == g.h_cell) ymod = 0;
         }
     }
-    // warp-aggregated append: one atomic per warp
-    int incl = npend;
+    // warp-aggregated append: one atomic per warp reserves room for all its survivors
+    const int mine = __popc(km0) + __popc(km1);
+    int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -260,10 +246,28 @@ __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict
     if (total == 0) return;
     int base = 0;
     if (lane == 31) base = atomicAdd(counter, total);
-    base = __shfl_sync(0xffffffffu, base, 31) + incl - npend;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        if (i < npend) list[base + i] = pend[i];
+    int pos = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+    if (mine == 0) return;
+    const int cx0 = (max(x0, kEdge) - kEdge) / g.w_cell;     // cell column of the 4 pixels: cx0 or cx0+1
+    const int xnext = kEdge + (cx0 + 1) * g.w_cell;
+    int32_t* flags = cell_flag + (size_t)blockIdx.y * n_cells + g.cell_base;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        uint32_t km = half ? km1 : km0;
+        while (km) {
+            const int bit = __ffs(km) - 1;
+            km &= km - 1;
+            const int r = half * 8 + (bit >> 2), b = bit & 3;
+            const int x = x0 + b, y = y0 + r;
+            const uint32_t sc = src[(size_t)y * g.spitch + b];
+            list[pos++] = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | (sc << 24);
+            if ((int)sc >= ini_th) {
+                // cell row of y: rows advance from (cy0, ymod0)
+                const int cy = cy0 + (ymod0 + r) / g.h_cell;
+                flags[cy * g.n_cols + cx0 + (x >= xnext ? 1 : 0)] = 1;
+            }
+        }
+    }
 }
 
 int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, int ini_th,

@@ -226,22 +226,25 @@ __global__ void __launch_bounds__(128) blur7_kernel(const uint8_t* __restrict__ 
     const uint8_t* src = pyr + (size_t)blockIdx.y * pyr_frame_bytes + g.plane_off + (size_t)kEdge * g.pitch + kXPad;
     uint8_t* dst = blur + (size_t)blockIdx.y * blur_frame_bytes + g.splane_off;
 
-    uint2 hs[7];   // sliding window of horizontal sums, hs[k] = row (y-3+k)
-    auto load_row = [&](int y) -> uint2 {
-        y = min(y, g.h + 2);   // rows up to h+2 exist in the padded plane (border 19)
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)y * g.pitch + x0 - 4);
-        return blur_hsum4(p[0], p[1], p[2]);
-    };
+    // all 22 source rows of the strip are fetched up front (66 independent 32-bit loads in flight per thread),
+    // then reduced to horizontal sums; the vertical pass slides over them
+    uint32_t w0[kBlurRows + 6], w1[kBlurRows + 6], w2[kBlurRows + 6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) hs[k] = load_row(y0 - 3 + k);
+    for (int k = 0; k < kBlurRows + 6; k++) {
+        const int y = min(y0 - 3 + k, g.h + 2);   // rows up to h+2 exist in the padded plane (border 19)
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)y * g.pitch + x0 - 4);
+        w0[k] = p[0]; w1[k] = p[1]; w2[k] = p[2];
+    }
+    uint2 hs[kBlurRows + 6];   // hs[k] = horizontal sums of row (y0-3+k)
+#pragma unroll
+    for (int k = 0; k < kBlurRows + 6; k++) hs[k] = blur_hsum4(w0[k], w1[k], w2[k]);
 #pragma unroll
     for (int r = 0; r < kBlurRows; r++) {
-        hs[6] = load_row(y0 + r + 3);
         uint32_t o[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             auto H = [&](int k) -> uint32_t {
-                const uint32_t pr = (c & 1) ? hs[k].y : hs[k].x;
+                const uint32_t pr = (c & 1) ? hs[r + k].y : hs[r + k].x;
                 return (c & 2) ? (pr >> 16) : (pr & 0xffffu);
             };
             const uint32_t s = 18u * (H(0) + H(6)) + 34u * (H(1) + H(5)) + 48u * (H(2) + H(4)) + 56u * H(3);
@@ -250,8 +253,6 @@ __global__ void __launch_bounds__(128) blur7_kernel(const uint8_t* __restrict__ 
         if (y0 + r < g.h)
             *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * g.spitch + x0) =
                 o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-#pragma unroll
-        for (int k = 0; k < 6; k++) hs[k] = hs[k + 1];
     }
 }
 
