@@ -307,9 +307,9 @@ def run_ours(args):
         import ctypes as C
         cur = torch.cuda.current_stream(dev)
 
-        def match_step():
+        def match_step(variant):
             rc = L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), NQ, C.c_void_p(d_m.data_ptr()), hi - lo, lo,
-                                    C.c_void_p(rec.data_ptr()), 0, C.c_void_p(cur.cuda_stream))
+                                    C.c_void_p(rec.data_ptr()), variant, C.c_void_p(cur.cuda_stream))
             assert rc == 0, L.orb_last_error()
             if world > 1:
                 parts = torch.empty((world, NQ, 4), dtype=torch.int32, device=dev)
@@ -321,22 +321,33 @@ def run_ours(args):
                 return out
             return rec
 
-        for _ in range(3):
-            match_step()
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        msteps = 10
-        e0.record(cur)
-        for _ in range(msteps):
-            out = match_step()
-        e1.record(cur)
-        barrier()
-        mms = max_over_ranks(e0.elapsed_time(e1)) / msteps
-        gcmp = NQ * NM / (mms * 1e-3) / 1e9
-        chk = int(out[:, 0].sum().item())
+        per_variant = {}
+        ref_out = None
+        for variant, name in ((0, "popc"), (1, "imma")):
+            for _ in range(3):
+                match_step(variant)
+            barrier()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            msteps = 10
+            e0.record(cur)
+            for _ in range(msteps):
+                out = match_step(variant)
+            e1.record(cur)
+            barrier()
+            mms = max_over_ranks(e0.elapsed_time(e1)) / msteps
+            per_variant[name] = {"ms_per_batch": mms, "gcmp_s": NQ * NM / (mms * 1e-3) / 1e9}
+            if ref_out is None:
+                ref_out = out.clone()
+            else:
+                assert bool((ref_out == out).all().item()), "2-NN variants disagree"
+        bestv = max(per_variant, key=lambda k: per_variant[k]["gcmp_s"])
+        gcmp = per_variant[bestv]["gcmp_s"]
+        chk = int(ref_out[:, 0].sum().item())
         matching = {"metric": "Hamming 2-NN Gcmp/s (2000 queries x 1M map, 256-bit)", "value": gcmp, "unit": "Gcmp/s",
-                    "ms_per_batch": mms, "map_shards": world, "d1_checksum": chk,
-                    "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8, "frac_of_popc_peak": gcmp / (148 * 16 * 1.965 / 8)}
+                    "ms_per_batch": per_variant[bestv]["ms_per_batch"], "kernel": bestv, "variants": per_variant,
+                    "map_shards": world, "d1_checksum": chk,
+                    "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8,
+                    "popc_kernel_frac_of_popc_peak": per_variant["popc"]["gcmp_s"] / (148 * 16 * 1.965 / 8)}
 
     # ---------------- CPU baseline (rank 0, N=1 only; bounded sample) --------------------------------------
     cpu = None

@@ -69,6 +69,133 @@ __global__ void __launch_bounds__(kKnnThreads) knn2_popc_kernel(const uint4* __r
     if (valid) partial[(size_t)blockIdx.y * nq + qi] = make_int4(t.d1, t.i1, t.d2, t.i2);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K7: tensor-core variant.  d(a,b) = popc(a) + popc(b) - 2*popc(a & b); popc(a & b) is the dot product of
+// the two descriptors seen as 256-element {0,1} vectors, i.e. a 16x8x256 AND-popc contraction per warp
+// tile.  PTX's own `mma.sync ... b1 ... and.popc` is software-emulated on sm_100a (each m16n8k256 expands
+// the bits and issues 8 IMMA.16832 plus ~100 ALU ops), so this kernel issues the integer MMAs
+// directly (mma.sync.m16n8k32.s32.u8.u8.s32) and hoists the bit -> byte expansion out of the inner loop:
+// query fragments are expanded once into registers (64 regs: 32 queries x 256 elements per warp), map
+// descriptors once per CTA into a shared-memory tile laid out in fragment order (conflict-free LDS.64).
+// The k dimension is permuted freely (element e of k-step s = bit e of descriptor word s) because the
+// same permutation is applied to both operands.  Top-2 bookkeeping as in the POPC kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMmaThreads = 256;            // 8 warps x 32 queries
+constexpr int kMmaQPerCta = 256;
+constexpr int kMmaTile = 128;               // map descriptors per shared-memory tile (32 KB expanded)
+
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t w, int shift) {
+    // 4 bits -> 4 bytes of 0/1
+    return (((w >> shift) & 0xfu) * 0x00204081u) & 0x01010101u;
+}
+
+__device__ __forceinline__ void mma_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 2) knn2_mma_kernel(const uint32_t* __restrict__ q, int nq,
+                                                                 const uint4* __restrict__ m, long long nm,
+                                                                 long long per_split, long long index_base,
+                                                                 int4* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* s_b = reinterpret_cast<uint2*>(smem_raw);                            // [tile/8][8 k-steps][32 lanes]
+    int* s_pb = reinterpret_cast<int*>(smem_raw + (size_t)kMmaTile * 256);        // popc of each staged descriptor
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int q0 = blockIdx.x * kMmaQPerCta + warp * 32;
+    // ---- A fragments: rows gid, gid+8 of two 16-query tiles; k-step s = descriptor word s
+    uint32_t A[2][8][4];
+    int pa[2][2];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int r0 = q0 + t * 16 + gid, r1 = r0 + 8;
+        int p0 = 0, p1 = 0;
+#pragma unroll
+        for (int sx = 0; sx < 8; sx++) {
+            const uint32_t w0 = r0 < nq ? q[(size_t)r0 * 8 + sx] : 0u;
+            const uint32_t w1 = r1 < nq ? q[(size_t)r1 * 8 + sx] : 0u;
+            p0 += __popc(w0); p1 += __popc(w1);
+            A[t][sx][0] = expand_nibble(w0, 4 * tig);          // row gid,   k = 4*tig .. +3
+            A[t][sx][1] = expand_nibble(w1, 4 * tig);          // row gid+8
+            A[t][sx][2] = expand_nibble(w0, 16 + 4 * tig);     // row gid,   k = 16 + 4*tig .. +3
+            A[t][sx][3] = expand_nibble(w1, 16 + 4 * tig);
+        }
+        pa[t][0] = p0; pa[t][1] = p1;
+    }
+    Top2 best[2][2];
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) best[t][h] = Top2{256, -1, 256, -1};
+
+    const long long lo = (long long)blockIdx.y * per_split;
+    const long long hi = min(nm, lo + per_split);
+    for (long long base = lo; base < hi; base += kMmaTile) {
+        const int cnt = (int)min((long long)kMmaTile, hi - base);
+        __syncthreads();
+        // ---- stage + expand the map tile: thread handles (descriptor j, k-step s) pairs
+        for (int it = tid; it < kMmaTile * 8; it += kMmaThreads) {
+            const int j = it >> 3, sx = it & 7;
+            const uint32_t w = j < cnt ? reinterpret_cast<const uint32_t*>(m + 2 * (base + j))[sx] : 0u;
+            // B fragment of column n = j%8 at k-step sx: lane (gid=n, tig) holds k = 4*tig..+3 and 16+4*tig..+3
+            uint2* dstp = s_b + ((size_t)(j >> 3) * 8 + sx) * 32 + (j & 7) * 4;
+#pragma unroll
+            for (int tg = 0; tg < 4; tg++) dstp[tg] = make_uint2(expand_nibble(w, 4 * tg), expand_nibble(w, 16 + 4 * tg));
+        }
+        for (int j = tid; j < kMmaTile; j += kMmaThreads) {
+            int p = 0;
+            if (j < cnt) {
+                const uint4 x = m[2 * (base + j)], y = m[2 * (base + j) + 1];
+                p = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w) + __popc(y.x) + __popc(y.y) + __popc(y.z) + __popc(y.w);
+            }
+            s_pb[j] = p;
+        }
+        __syncthreads();
+        const int ngroups = (cnt + 7) >> 3;
+        for (int g8 = 0; g8 < ngroups; g8++) {
+            int c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+            const uint2* bp = s_b + (size_t)g8 * 8 * 32 + lane;
+#pragma unroll
+            for (int sx = 0; sx < 8; sx++) {
+                const uint2 b = bp[sx * 32];
+                mma_u8(c0, A[0][sx], b.x, b.y);
+                mma_u8(c1, A[1][sx], b.x, b.y);
+            }
+            const int col = g8 * 8 + 2 * tig;
+            const int pb0 = s_pb[col], pb1 = s_pb[col + 1];
+            const int idx0 = (int)(index_base + base) + col;
+            const bool v0 = col < cnt, v1 = col + 1 < cnt;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int* c = t ? c1 : c0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int d0 = pa[t][h] + pb0 - 2 * c[2 * h], d1 = pa[t][h] + pb1 - 2 * c[2 * h + 1];
+                    if (v0 && d0 < best[t][h].d2) top2_push(best[t][h], d0, idx0);
+                    if (v1 && d1 < best[t][h].d2) top2_push(best[t][h], d1, idx0 + 1);
+                }
+            }
+        }
+    }
+    // ---- merge the four lanes of a row group (they saw disjoint column subsets), lane tig==0 writes
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            Top2 b = best[t][h];
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const int e1 = __shfl_xor_sync(0xffffffffu, b.d1, o), j1 = __shfl_xor_sync(0xffffffffu, b.i1, o);
+                const int e2 = __shfl_xor_sync(0xffffffffu, b.d2, o), j2 = __shfl_xor_sync(0xffffffffu, b.i2, o);
+                top2_merge(b.d1, b.i1, b.d2, b.i2, e1, j1, e2, j2);
+            }
+            const int row = q0 + t * 16 + gid + 8 * h;
+            if (tig == 0 && row < nq) partial[(size_t)blockIdx.y * nq + row] = make_int4(b.d1, b.i1, b.d2, b.i2);
+        }
+}
+
 __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -82,25 +209,38 @@ __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, in
 
 int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out, int variant,
                 cudaStream_t s) {
-    (void)variant;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int qblocks = (nq + kKnnThreads - 1) / kKnnThreads;
-    // enough map splits for >= 2 CTAs per SM, each at least one tile
-    int splits = (2 * sms + qblocks - 1) / qblocks;
-    const int64_t max_splits = (nm + kKnnTile - 1) / kKnnTile;
+    const int qper = variant == 1 ? kMmaQPerCta : kKnnThreads;
+    const int tile = variant == 1 ? kMmaTile : kKnnTile;
+    const int per_sm = 2;
+    const int qblocks = (nq + qper - 1) / qper;
+    // enough map splits to fill the SMs, each at least one tile
+    int splits = (per_sm * sms + qblocks - 1) / qblocks;
+    const int64_t max_splits = (nm + tile - 1) / tile;
     if (splits > max_splits) splits = (int)std::max<int64_t>(max_splits, 1);
     int64_t per_split = (nm + splits - 1) / splits;
-    per_split = (per_split + kKnnTile - 1) / kKnnTile * kKnnTile;
+    per_split = (per_split + tile - 1) / tile * tile;
     splits = nm > 0 ? (int)((nm + per_split - 1) / per_split) : 1;
     // per-call scratch from the stream-ordered allocator: matcher entry points are re-entrant
     const size_t need = (size_t)splits * nq * sizeof(int4);
     int4* partial = nullptr;
     if (cudaMallocAsync((void**)&partial, need, s) != cudaSuccess) return -1;
-    knn2_popc_kernel<<<dim3(qblocks, splits), kKnnThreads, 0, s>>>((const uint4*)d_q, nq, (const uint4*)d_m, nm, per_split,
-                                                                   index_base, partial);
+    if (variant == 1) {
+        const size_t smem = (size_t)kMmaTile * 256 + kMmaTile * sizeof(int);
+        static bool configured = false;
+        if (!configured) {
+            if (cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            configured = true;
+        }
+        knn2_mma_kernel<<<dim3(qblocks, splits), kMmaThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
+                                                                       index_base, partial);
+    } else {
+        knn2_popc_kernel<<<dim3(qblocks, splits), kKnnThreads, 0, s>>>((const uint4*)d_q, nq, (const uint4*)d_m, nm, per_split,
+                                                                       index_base, partial);
+    }
     merge_top2_kernel<<<(nq + 255) / 256, 256, 0, s>>>(partial, splits, nq, (int4*)d_out);
     cudaFreeAsync(partial, s);
     return 2;

@@ -32,8 +32,9 @@ def test_hamming_kat(orb, oracle):
     assert orb.ORBmatcher.DescriptorDistance(z, f) == 256 and orb.ORBmatcher.DescriptorDistance(f, f) == 0
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("nq,nm", [(1, 1), (7, 300), (257, 5000), (2000, 60000), (100, 0)])
-def test_knn2_matches_oracle(orb, oracle, synth, nq, nm):
+def test_knn2_matches_oracle(orb, oracle, synth, nq, nm, variant):
     m = synth.descriptors(max(nm, 1), seed=5)[:nm]
     if nm > nq:
         q, m, _ = synth.query_set(m, nq=nq, seed=6)
@@ -43,7 +44,7 @@ def test_knn2_matches_oracle(orb, oracle, synth, nq, nm):
     if nm > 10:
         m[nm // 2] = m[3]; m[nm - 1] = m[3]
         q[0] = m[3]
-    bi, bd, sd, si = orb.ORBmatcher().knn2(q, m, index_base=1000)
+    bi, bd, sd, si = orb.ORBmatcher().knn2(q, m, index_base=1000, variant=variant)
     i1, d1, i2, d2 = _oracle_knn2_full(oracle, q, np.ascontiguousarray(m).reshape(-1, 32), base=1000)
     assert np.array_equal(bd, d1) and np.array_equal(sd, d2)
     assert np.array_equal(bi, i1) and np.array_equal(si, i2)
