@@ -159,3 +159,67 @@ def test_octree_standalone(orb, oracle):
         ref = oracle.distribute_octtree(x, y, s, 16, 16 + w, 16, 16 + h, N)
         got = orb.distribute_octtree(x, y, s, 16, 16 + w, 16, 16 + h, N)
         assert np.array_equal(ref, got), (trial, w, h, n, N, len(ref), len(got))
+
+
+PARAM_CASES = [(640, 480, 2000, 1.2, 8, 20, 7),      # the 2x monocular-initialisation extractor (R21 Tracking.cc:125)
+               (640, 480, 500, 1.2, 8, 20, 7),
+               (640, 480, 1000, 1.1, 8, 20, 7),
+               (800, 600, 1500, 1.5, 5, 25, 10),
+               (640, 480, 1000, 1.2, 4, 12, 5),
+               (1920, 1080, 3000, 1.2, 8, 20, 7),
+               (376, 413, 800, 1.2, 6, 20, 7)]         # taller than wide: one quadtree root
+
+
+@pytest.mark.parametrize("case", PARAM_CASES)
+def test_other_parameters(orb, oracle, synth, case):
+    w, h, nf, sf, nl, ini, mn = case
+    img = synth.frame(5, w, h)
+    kps, desc = orb.ORBextractor(nf, sf, nl, ini, mn)(img)
+    okps, odesc = oracle.OracleExtractor(nf, sf, nl, ini, mn, trig_mode=1).extract(img, cap=40000)
+    assert len(kps) == len(okps)
+    assert kps.tobytes() == okps.tobytes()
+    assert np.array_equal(desc, odesc)
+
+
+def test_stream_of_frames_kitti_shape(orb, oracle, synth):
+    """BASELINE config 2 shape: 1241x376, nFeatures=2000 -- a short stream through one handle, batched."""
+    frames = np.stack([synth.frame(100 + s, 1241, 376) for s in range(8)])
+    ex = orb.ORBextractor(2000, 1.2, 8, 20, 7, max_width=1241, max_height=376, max_batch=4)
+    oe = oracle.OracleExtractor(2000, trig_mode=1)
+    for b0 in (0, 4):
+        kps, desc, cnt = ex.extract_batch(frames[b0:b0 + 4])
+        for i in range(4):
+            ok, od = oe.extract(frames[b0 + i])
+            assert cnt[i] == len(ok)
+            assert kps[i, :cnt[i]].tobytes() == ok.tobytes() and np.array_equal(desc[i, :cnt[i]], od)
+
+
+def test_size_change_and_reuse(orb, oracle, synth):
+    """One handle, alternating image sizes (geometry is rebuilt; results must not depend on history)."""
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7)
+    for (w, h, seed) in [(640, 480, 1), (752, 480, 2), (640, 480, 3), (320, 240, 4), (640, 480, 1)]:
+        img = synth.frame(seed, w, h)
+        k, d = ex(img)
+        ok, od = oracle.OracleExtractor(1000, trig_mode=1).extract(img)
+        assert k.tobytes() == ok.tobytes() and np.array_equal(d, od), (w, h, seed)
+
+
+def test_concurrent_handles(orb, oracle, synth):
+    """Two extractors used from two threads at once (the stereo Frame constructor, R21 Frame.cc:80-83)."""
+    import threading
+    left, right = synth.stereo_pair(3, 752, 480)
+    res = {}
+
+    def run(name, img):
+        ex = orb.ORBextractor(1200, 1.2, 8, 20, 7)
+        for _ in range(5):
+            res[name] = ex(img)
+
+    th = [threading.Thread(target=run, args=("l", left)), threading.Thread(target=run, args=("r", right))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for name, img in (("l", left), ("r", right)):
+        ok, od = oracle.OracleExtractor(1200, trig_mode=1).extract(img)
+        assert res[name][0].tobytes() == ok.tobytes() and np.array_equal(res[name][1], od)
