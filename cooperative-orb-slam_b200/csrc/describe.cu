@@ -85,14 +85,16 @@ __global__ void __launch_bounds__(32 * kDescWarps) describe_kernel(DevPtrs d, Fr
         const int oidx = __shfl_sync(0xffffffffu, incl - my_cnt, level) + rank;
         if (rank >= cnt || oidx >= cap) continue;
         const LevelGeom* gp = d.geom + level;
-        const int pitch = gp->pitch, spitch = gp->spitch;
+        const int spitch = gp->spitch;
+        int pitch;
+        const uint8_t* roi = level_roi(d, fl, *gp, level, frame, pitch);
         const uint32_t pk = d.sel[(size_t)frame * fl.kp_cap + slot];
         const int x = (int)(pk & 0xfff) + kMinBorder, y = (int)((pk >> 12) & 0xfff) + kMinBorder;
 
         // ---- IC_Angle on the un-blurred padded level.  Lane u sweeps its column of the disc:
         // |v| <= umax[|u|] (the patch is symmetric by construction, :462-469).  All 31 predicated loads are
         // issued back to back (fully unrolled) so their latencies overlap.
-        const uint8_t* img = d.pyr + (size_t)frame * fl.pyr_bytes + gp->plane_off + (size_t)(kEdge + y) * pitch + kXPad + x;
+        const uint8_t* img = roi + (size_t)y * pitch + x;   // key points sit >= 19 px inside the level, the patch radius is 15
         int m01 = 0, m10 = 0;
         {
             const int u = lane - 15;

@@ -88,6 +88,8 @@ struct orbx_handle_s {
     orb_keypoint_t* p_kps = nullptr; uint8_t* p_desc = nullptr; int32_t* p_counts = nullptr;
     bool p_direct = false;
     int last_frames = 0;
+    // level 0 of the last extraction is the input itself (the handle's own d_in, or the caller's device buffer)
+    const uint8_t* last_in = nullptr; size_t last_in_stride = 0; int last_in_pitch = 0;
 };
 
 namespace {
@@ -280,8 +282,8 @@ int ensure_size(orbx_handle_s* h, int width, int height, int n_frames) {
     return ORB_OK;
 }
 
-void fill_ptrs(orbx_handle_s* h, DevPtrs& d, const uint8_t* d_in) {
-    d.in = d_in; d.pyr = h->d_pyr; d.blur = h->d_blur; d.score = h->d_score; d.cand = h->d_cand;
+void fill_ptrs(orbx_handle_s* h, DevPtrs& d, const uint8_t* d_in, size_t in_frame_stride) {
+    d.in = d_in; d.in_frame_stride = in_frame_stride; d.pyr = h->d_pyr; d.blur = h->d_blur; d.score = h->d_score; d.cand = h->d_cand;
     d.cell_count = h->d_cell_count; d.level_raw = h->d_level_raw; d.oct_scratch = h->d_scratch; d.oct_node = h->d_node; d.sel = h->d_sel;
     d.level_count = h->d_level_count; d.geom = h->d_geom; d.cells = h->d_cells; d.xtab = h->d_xtab; d.ytab = h->d_ytab;
 }
@@ -290,12 +292,13 @@ void fill_ptrs(orbx_handle_s* h, DevPtrs& d, const uint8_t* d_in) {
 int enqueue_kernels(orbx_handle_s* h, const uint8_t* d_in, size_t in_frame_stride, int n_frames, orb_keypoint_t* d_kps,
                     uint8_t* d_desc, int32_t* d_counts, int cap) {
     DevPtrs d;
-    fill_ptrs(h, d, d_in);
+    fill_ptrs(h, d, d_in, in_frame_stride);
+    h->last_in = d_in; h->last_in_stride = in_frame_stride; h->last_in_pitch = h->fl.in_pitch;
     cudaStream_t s = h->stream;
     const bool prof = h->profiling;
     int n;
     if (prof) cudaEventRecord(h->ev[1], s);
-    if ((n = launch_pyramid(d, h->fl, h->geom.data(), n_frames, in_frame_stride, s)) < 0) {
+    if ((n = launch_pyramid(d, h->fl, h->geom.data(), n_frames, s)) < 0) {
         set_error("scale factor too large for the resize kernel's shared-memory tile");
         return ORB_ERR_ARG;
     }
@@ -606,8 +609,26 @@ int orbx_download_level(orbx_handle_t h, int frame, int level, int with_border, 
     ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
     const LevelGeom& g = h->geom[level];
     const int b = with_border ? kEdge : 0;
-    const uint8_t* src = h->d_pyr + (size_t)frame * h->fl.pyr_bytes + g.plane_off + (size_t)(kEdge - b) * g.pitch + kXPad - b;
-    ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, src, g.pitch, g.w + 2 * b, g.h + 2 * b, cudaMemcpyDeviceToHost));
+    uint8_t* roi = dst + (size_t)b * dst_stride + b;
+    if (level == 0) {
+        ORB_CUDA_TRY(cudaMemcpy2D(roi, dst_stride, h->last_in + (size_t)frame * h->last_in_stride, h->last_in_pitch, g.w, g.h,
+                                  cudaMemcpyDeviceToHost));
+    } else {
+        const uint8_t* src = h->d_pyr + (size_t)frame * h->fl.pyr_bytes + g.plane_off + (size_t)kEdge * g.pitch + kXPad;
+        ORB_CUDA_TRY(cudaMemcpy2D(roi, dst_stride, src, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    }
+    if (b) {
+        // the REFLECT_101 border of cv::copyMakeBorder (R21 :1122-1128) is rebuilt here: the device never needs it
+        auto refl = [](int p, int len) { if (p < 0) p = -p; if (p >= len) p = 2 * len - 2 - p; return p; };
+        for (int y = 0; y < g.h; y++) {
+            uint8_t* row = roi + (size_t)y * dst_stride;
+            for (int k = 1; k <= b; k++) { row[-k] = row[refl(-k, g.w)]; row[g.w - 1 + k] = row[refl(g.w - 1 + k, g.w)]; }
+        }
+        for (int k = 1; k <= b; k++) {
+            memcpy(roi + (ptrdiff_t)(-k) * (ptrdiff_t)dst_stride - b, roi + (size_t)refl(-k, g.h) * dst_stride - b, g.w + 2 * b);
+            memcpy(roi + (size_t)(g.h - 1 + k) * dst_stride - b, roi + (size_t)refl(g.h - 1 + k, g.h) * dst_stride - b, g.w + 2 * b);
+        }
+    }
     return ORB_OK;
 }
 
@@ -703,10 +724,11 @@ int orbx_distribute_octtree(const int16_t* x, const int16_t* y, const uint8_t* s
 // Internal (not in orbcuda.h): device views of a handle's last extraction for orbm_stereo_matches.
 extern "C" int orbx_internal_view(orbx_handle_t h, const uint8_t** d_pyr, const orbcuda::LevelGeom** d_geom,
                                   const orbcuda::LevelGeom** h_geom, orbcuda::FrameLayout* fl, int* device,
-                                  const float** sf, const float** isf) {
+                                  const float** sf, const float** isf, const uint8_t** d_level0, int* level0_pitch) {
     if (!h || h->last_frames < 1) return ORB_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) return ORB_ERR_CUDA;
     *d_pyr = h->d_pyr; *d_geom = h->d_geom; *h_geom = h->geom.data(); *fl = h->fl; *device = h->device;
     *sf = h->sf.data(); *isf = h->isf.data();
+    *d_level0 = h->last_in; *level0_pitch = h->last_in_pitch;
     return ORB_OK;
 }

@@ -100,13 +100,10 @@ __device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
     return s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
 }
 
-__global__ void __launch_bounds__(128) fast_score_kernel(const uint8_t* __restrict__ pyr, int64_t pyr_frame_bytes,
-                                                         uint8_t* __restrict__ score, int64_t score_frame_bytes,
-                                                         const LevelGeom* __restrict__ geom, int nlevels,
-                                                         LevelBlocks lb, int th) {
+__global__ void __launch_bounds__(128) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
     int level = 0;
-    while (level + 1 < nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
-    const LevelGeom g = geom[level];
+    while (level + 1 < fl.nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
+    const LevelGeom g = d.geom[level];
     // strips: x0 = 16 + 4*sx covers [16, W-19); y0 = 19 + kFastRows*sy covers [19, H-19)
     const int nsx = (g.w - kEdge - kMinBorder + 3) >> 2;
     const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
@@ -114,8 +111,9 @@ __global__ void __launch_bounds__(128) fast_score_kernel(const uint8_t* __restri
     const int x0 = kMinBorder + 4 * (id - sy * nsx);
     const int y0 = kEdge + sy * kFastRows;
     if (y0 >= g.h - kEdge) return;
-    const uint8_t* src = pyr + (size_t)blockIdx.y * pyr_frame_bytes + g.plane_off + (size_t)kEdge * g.pitch + kXPad + (x0 - 4);
-    uint8_t* dst = score + (size_t)blockIdx.y * score_frame_bytes + g.splane_off + x0;
+    int pitch;
+    const uint8_t* src = level_roi(d, fl, g, level, blockIdx.y, pitch) + (x0 - 4);   // x0 >= 16: never leaves the row
+    uint8_t* dst = d.score + (size_t)blockIdx.y * fl.splane_bytes + g.splane_off + x0;
     // byte mask of the columns inside [19, W-19)
     uint32_t colmask = 0;
 #pragma unroll
@@ -124,11 +122,11 @@ __global__ void __launch_bounds__(128) fast_score_kernel(const uint8_t* __restri
 
     Row6 r[7];
 #pragma unroll
-    for (int k = 0; k < 6; k++) r[k] = load_row6(src + (ptrdiff_t)(y0 - 3 + k) * g.pitch);
+    for (int k = 0; k < 6; k++) r[k] = load_row6(src + (ptrdiff_t)(y0 - 3 + k) * pitch);
 #pragma unroll
     for (int j = 0; j < kFastRows; j++) {
         const int y = y0 + j;
-        r[6] = load_row6(src + (ptrdiff_t)(y + 3) * g.pitch);
+        r[6] = load_row6(src + (ptrdiff_t)min(y + 3, g.h - 1) * pitch);
         const uint32_t s4 = fast_score4(r, th) & colmask;
         if (y < g.h - kEdge) *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.spitch) = s4;
 #pragma unroll
@@ -148,8 +146,7 @@ int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* 
         total += (nsx * nsy + threads - 1) / threads;
     }
     for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
-    fast_score_kernel<<<dim3(total, n_frames), threads, 0, s>>>(d.pyr, fl.pyr_bytes, d.score, fl.splane_bytes, d.geom,
-                                                                fl.nlevels, lb, min_th);
+    fast_score_kernel<<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb, min_th);
     return 1;
 }
 

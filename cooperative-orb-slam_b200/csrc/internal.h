@@ -73,7 +73,8 @@ struct LevelBlocks {
 
 // ---- kernel launchers (each returns the number of kernels it launched) ----
 struct DevPtrs {
-    const uint8_t* in;          // [B][height][in_pitch]
+    const uint8_t* in;          // [B][height][in_pitch]: pyramid level 0 is read from here directly (no copy)
+    size_t in_frame_stride;     // bytes between frames of `in`
     uint8_t* pyr;               // [B][pyr_bytes]
     uint8_t* blur;              // [B][splane_bytes]
     uint8_t* score;             // [B][splane_bytes]  FAST score at minThFAST
@@ -90,8 +91,7 @@ struct DevPtrs {
     const ResizeTap* ytab;
 };
 
-int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, size_t in_frame_stride,
-                   cudaStream_t s);
+int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, cudaStream_t s);
 int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, int min_th,
                       cudaStream_t s);
 int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, cudaStream_t s);
@@ -112,6 +112,18 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
                 int variant, cudaStream_t s);
 int launch_merge_top2(const int32_t* d_parts, int parts, int nq, int32_t* d_out, cudaStream_t s);
 void host_merge_top2(const int32_t* parts, int nparts, int nq, int32_t* out);
+
+#ifdef __CUDACC__
+// Pointer to pixel (0,0) of a pyramid level and its row pitch.  Level 0 is the input image itself; levels >= 1
+// live in the padded planes of the pyramid block (only the interior is ever written or read on the device:
+// every consumer either stays inside the level or applies REFLECT_101 itself).
+__device__ __forceinline__ const uint8_t* level_roi(const DevPtrs& d, const FrameLayout& fl, const LevelGeom& g, int level,
+                                                    int frame, int& pitch) {
+    if (level == 0) { pitch = fl.in_pitch; return d.in + (size_t)frame * d.in_frame_stride; }
+    pitch = g.pitch;
+    return d.pyr + (size_t)frame * fl.pyr_bytes + g.plane_off + (size_t)kEdge * g.pitch + kXPad;
+}
+#endif
 
 void set_error(const char* fmt, ...);
 bool cuda_ok(cudaError_t e, const char* what);

@@ -2,10 +2,14 @@
 // R21/src/ORBextractor.cc:1107-1132) and K2: 7x7 sigma=2 Gaussian blur (replaces the GaussianBlur call
 // at R21 :1085-1086).  uint8 planes, 4 pixels (one 32-bit word) per thread, HBM/L2 bound.
 //
-// Layout: a padded plane stores level pixel (x,y) at byte (y+19)*pitch + 32 + x; the 19-pixel
-// REFLECT_101 border of cv::copyMakeBorder occupies columns [13,32) and [32+w, 51+w).  The interior
-// origin is therefore 32-byte aligned and every row is `pitch` (multiple of 64) bytes.
+// Layout: level 0 is the input image itself; a level l >= 1 is stored in a padded plane with pixel (x,y) at
+// byte (y+19)*pitch + 32 + x (interior origin 32-byte aligned, pitch a multiple of 64).  The 19-pixel
+// REFLECT_101 border that cv::copyMakeBorder adds (R21 :1122-1128) is NOT materialised on the device: FAST,
+// IC_Angle, the descriptor sampler and the stereo SAD never leave the level interior, the blur applies
+// REFLECT_101 itself, and orbx_download_level rebuilds the border on the host for mvImagePyramid consumers.
 #include "internal.h"
+
+#include <algorithm>
 
 namespace orbcuda {
 
@@ -14,32 +18,6 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     if (p < 0) p = -p;
     if (p >= len) p = 2 * len - 2 - p;
     return min(max(p, 0), len - 1);
-}
-
-// ---------------------------------------------------------------------------------------------
-// level 0: copyMakeBorder(image, temp, 19,19,19,19, BORDER_REFLECT_101)   (R21 :1126-1128)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pyr_level0_kernel(const uint8_t* __restrict__ in, size_t in_frame_stride,
-                                                         int in_pitch, uint8_t* __restrict__ pyr,
-                                                         int64_t pyr_frame_bytes, LevelGeom g) {
-    const int wx = blockIdx.x * blockDim.x + threadIdx.x;   // word index; word 0 starts at plane column 12
-    const int py = blockIdx.y * blockDim.y + threadIdx.y;   // padded row
-    const int px0 = 12 + 4 * wx;
-    if (px0 >= kXPad + g.w + kEdge || py >= g.plane_rows) return;
-    const uint8_t* src = in + (size_t)blockIdx.z * in_frame_stride;
-    uint8_t* dst = pyr + (size_t)blockIdx.z * pyr_frame_bytes + g.plane_off;
-    const int iy = reflect101(py - kEdge, g.h);
-    const uint8_t* srow = src + (size_t)iy * in_pitch;
-    uint32_t v;
-    const int ix0 = px0 - kXPad;
-    if (ix0 >= 0 && ix0 + 3 < g.w && ((reinterpret_cast<uintptr_t>(srow + ix0) & 3) == 0)) {
-        v = *reinterpret_cast<const uint32_t*>(srow + ix0);
-    } else {
-        v = 0;
-#pragma unroll
-        for (int b = 0; b < 4; b++) v |= (uint32_t)srow[reflect101(ix0 + b, g.w)] << (8 * b);
-    }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)py * g.pitch + px0) = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -52,21 +30,19 @@ __global__ void __launch_bounds__(256) pyr_level0_kernel(const uint8_t* __restri
 // shared memory with coalesced 32-bit loads.  Each thread owns 4 adjacent output columns (its 8 horizontal
 // taps stay in registers) and each warp streams down 8 output rows: the horizontal pass of a source row
 // ((r>>4), 16 bits) is computed once and reused by the next output row, the vertical pass combines the two
-// live rows and the 4 results leave as one 32-bit store.  Pixels within 19 px of an edge are also stored to
-// their REFLECT_101 mirror positions, so the border needs no second pass.
+// live rows and the 4 results leave as one 32-bit store.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* pyr, int64_t pyr_frame_bytes, LevelGeom gs,
-                                                         LevelGeom gd, const ResizeTap* __restrict__ xtab,
-                                                         const ResizeTap* __restrict__ ytab) {
+__global__ void __launch_bounds__(256) pyr_resize_kernel(DevPtrs d, FrameLayout fl, int level) {
     extern __shared__ __align__(16) unsigned char s_src[];   // [rs_rows][rs_cols]
+    const LevelGeom gs = d.geom[level - 1], gd = d.geom[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * kPyrTileW, y0 = blockIdx.y * kPyrTileH;
     const int tw = min(kPyrTileW, gd.w - x0), th = min(kPyrTileH, gd.h - y0);
-    uint8_t* frame = pyr + (size_t)blockIdx.z * pyr_frame_bytes;
-    const uint8_t* src = frame + gs.plane_off + (size_t)kEdge * gs.pitch + kXPad;   // ROI origin of level l-1
-    uint8_t* dst = frame + gd.plane_off + (size_t)kEdge * gd.pitch + kXPad;          // ROI origin of level l
-    const ResizeTap* xt = xtab + gd.xtab_off;
-    const ResizeTap* yt = ytab + gd.ytab_off;
+    int src_pitch;
+    const uint8_t* src = level_roi(d, fl, gs, level - 1, blockIdx.z, src_pitch);    // pixel (0,0) of level l-1
+    uint8_t* dst = d.pyr + (size_t)blockIdx.z * fl.pyr_bytes + gd.plane_off + (size_t)kEdge * gd.pitch + kXPad;
+    const ResizeTap* xt = d.xtab + gd.xtab_off;
+    const ResizeTap* yt = d.ytab + gd.ytab_off;
     // source footprint of the tile
     const int sxa = xt[x0].ofs & ~3;
     const int sxe = xt[x0 + tw - 1].pad;
@@ -77,10 +53,10 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* pyr, int64_t p
     {
         const int wcol = tid & 63;
         if (wcol < nwords) {
-            const uint8_t* gp = src + (size_t)sy0 * gs.pitch + sxa + 4 * wcol;
+            const uint8_t* gp = src + (size_t)sy0 * src_pitch + sxa + 4 * wcol;
             for (int r = tid >> 6; r < nrows; r += 4)
                 reinterpret_cast<uint32_t*>(s_src + r * spitch)[wcol] =
-                    *reinterpret_cast<const uint32_t*>(gp + (size_t)r * gs.pitch);
+                    *reinterpret_cast<const uint32_t*>(gp + (size_t)r * src_pitch);
         }
     }
     const int X0 = x0 + 4 * lane;
@@ -99,7 +75,6 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* pyr, int64_t p
         for (int i = 0; i < 4; i++) hh[i] = (S[o0[i]] * c0[i] + S[o1[i]] * c1[i]) >> 4;
     };
     constexpr int kNone = -(1 << 20);
-    const bool xedge = X0 <= kEdge || X0 + 3 >= gd.w - 1 - kEdge;
     int lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
     int r_lo = kNone, r_hi = kNone;
     const int dy_end = min(th, warp * 8 + 8);
@@ -129,52 +104,25 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(uint8_t* pyr, int64_t p
         uint32_t v[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) v[i] = (uint32_t)((((b0 * lo[i]) >> 16) + ((b1 * hi[i]) >> 16) + 2) >> 2) & 0xffu;
-        int ym = kNone;
-        if (Y >= 1 && Y <= kEdge) ym = -Y;
-        else if (Y >= gd.h - 1 - kEdge && Y <= gd.h - 2) ym = 2 * (gd.h - 1) - Y;
         uint8_t* row = dst + (ptrdiff_t)Y * gd.pitch;
-        uint8_t* mrow = dst + (ptrdiff_t)(ym == kNone ? Y : ym) * gd.pitch;
         if (npx == 4) {
-            const uint32_t pk = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-            *reinterpret_cast<uint32_t*>(row + X0) = pk;
-            if (ym != kNone) *reinterpret_cast<uint32_t*>(mrow + X0) = pk;
+            *reinterpret_cast<uint32_t*>(row + X0) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
         } else {
 #pragma unroll
             for (int i = 0; i < 3; i++)
-                if (i < npx) { row[X0 + i] = (uint8_t)v[i]; if (ym != kNone) mrow[X0 + i] = (uint8_t)v[i]; }
-        }
-        if (xedge) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int X = X0 + i;
-                int xm = kNone;
-                if (X >= 1 && X <= kEdge) xm = -X;
-                else if (X >= gd.w - 1 - kEdge && X <= gd.w - 2) xm = 2 * (gd.w - 1) - X;
-                if (i < npx && xm != kNone) {
-                    row[xm] = (uint8_t)v[i];
-                    if (ym != kNone) mrow[xm] = (uint8_t)v[i];
-                }
-            }
+                if (i < npx) row[X0 + i] = (uint8_t)v[i];
         }
     }
 }
 
-int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, size_t in_frame_stride,
-                   cudaStream_t s) {
+int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
     int launches = 0;
-    for (int l = 0; l < fl.nlevels; l++) {
+    for (int l = 1; l < fl.nlevels; l++) {   // level 0 is the input image itself
         const LevelGeom& g = hg[l];
-        if (l == 0) {
-            const dim3 block(64, 4);
-            const int nwords = (kXPad + g.w + kEdge - 12 + 3) / 4;
-            const dim3 grid((nwords + block.x - 1) / block.x, (g.plane_rows + block.y - 1) / block.y, n_frames);
-            pyr_level0_kernel<<<grid, block, 0, s>>>(d.in, in_frame_stride, fl.in_pitch, d.pyr, fl.pyr_bytes, g);
-        } else {
-            const size_t smem = (size_t)g.rs_rows * g.rs_cols;
-            if (smem > 48 * 1024 || g.rs_cols > 256) return -1;   // scale factors this large are not supported
-            const dim3 grid((g.w + kPyrTileW - 1) / kPyrTileW, (g.h + kPyrTileH - 1) / kPyrTileH, n_frames);
-            pyr_resize_kernel<<<grid, 256, smem, s>>>(d.pyr, fl.pyr_bytes, hg[l - 1], g, d.xtab, d.ytab);
-        }
+        const size_t smem = (size_t)g.rs_rows * g.rs_cols;
+        if (smem > 48 * 1024 || g.rs_cols > 256) return -1;   // scale factors this large are not supported
+        const dim3 grid((g.w + kPyrTileW - 1) / kPyrTileW, (g.h + kPyrTileH - 1) / kPyrTileH, n_frames);
+        pyr_resize_kernel<<<grid, 256, smem, s>>>(d, fl, l);
         launches++;
     }
     return launches;
@@ -183,8 +131,8 @@ int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg,
 // ---------------------------------------------------------------------------------------------
 // K2 blur.  cv::GaussianBlur(7x7, sigma 2) on CV_8U uses an 8.8 fixed-point separable kernel
 // [18,34,48,56,48,34,18] with one rounding: (sum + 32768) >> 16.  The source is clone() of the level
-// ROI with BORDER_REFLECT_101, which is exactly what the padded plane already holds around the ROI,
-// so the kernel is a plain 7x7 convolution over the padded plane.
+// ROI with BORDER_REFLECT_101: rows are reflected by index, and the two edge strips of a row gather
+// their 12-byte window with reflected column indices.
 //
 // Each thread owns a 4-pixel-wide column strip and slides down kBlurRows rows keeping the last seven
 // horizontal sums in registers.  Horizontal pass on 16-bit pairs: a 32-bit IMAD does two columns
@@ -210,30 +158,38 @@ __device__ __forceinline__ uint2 blur_hsum4(uint32_t w0, uint32_t w1, uint32_t w
     return r;
 }
 
-__global__ void __launch_bounds__(128) blur7_kernel(const uint8_t* __restrict__ pyr, int64_t pyr_frame_bytes,
-                                                    uint8_t* __restrict__ blur, int64_t blur_frame_bytes,
-                                                    const LevelGeom* __restrict__ geom, int nlevels, LevelBlocks lb) {
-    int level = 0;
-    while (level + 1 < nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
-    const LevelGeom g = geom[level];
-    // strips of a level are flattened so every block is full whatever the level width
-    const int nsx = (g.w + 3) >> 2;
-    const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
-    const int sy = id / nsx;
-    const int x0 = 4 * (id - sy * nsx);
-    const int y0 = sy * kBlurRows;
-    if (y0 >= g.h) return;
-    const uint8_t* src = pyr + (size_t)blockIdx.y * pyr_frame_bytes + g.plane_off + (size_t)kEdge * g.pitch + kXPad;
-    uint8_t* dst = blur + (size_t)blockIdx.y * blur_frame_bytes + g.splane_off;
-
+// One strip: 4 columns x kBlurRows rows.  EDGE strips (window x0-4 .. x0+7 leaves the row) gather their
+// bytes with reflected column indices; they are numbered after all interior strips of the level so that
+// whole warps take one path or the other.
+template <bool EDGE>
+__device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int pitch, uint8_t* __restrict__ dst, int spitch,
+                                           int w, int h, int x0, int y0) {
     // all 22 source rows of the strip are fetched up front (66 independent 32-bit loads in flight per thread),
     // then reduced to horizontal sums; the vertical pass slides over them
     uint32_t w0[kBlurRows + 6], w1[kBlurRows + 6], w2[kBlurRows + 6];
 #pragma unroll
     for (int k = 0; k < kBlurRows + 6; k++) {
-        const int y = min(y0 - 3 + k, g.h + 2);   // rows up to h+2 exist in the padded plane (border 19)
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)y * g.pitch + x0 - 4);
-        w0[k] = p[0]; w1[k] = p[1]; w2[k] = p[2];
+        int y = y0 - 3 + k;
+        y = y < 0 ? -y : y;                               // BORDER_REFLECT_101
+        y = y >= h ? max(2 * h - 2 - y, 0) : y;           // (rows past h+2 feed outputs that are never stored)
+        const uint8_t* row = src + (size_t)y * pitch;
+        if (!EDGE) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(row + x0 - 4);
+            w0[k] = p[0]; w1[k] = p[1]; w2[k] = p[2];
+        } else {
+            uint32_t a = 0, b = 0, c = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int xa = x0 - 4 + i, xb = x0 + i, xc = x0 + 4 + i;
+                xa = xa < 0 ? -xa : xa;
+                xb = xb >= w ? max(2 * w - 2 - xb, 0) : xb;
+                xc = xc >= w ? max(2 * w - 2 - xc, 0) : xc;
+                a |= (uint32_t)row[xa] << (8 * i);
+                b |= (uint32_t)row[xb] << (8 * i);
+                c |= (uint32_t)row[xc] << (8 * i);
+            }
+            w0[k] = a; w1[k] = b; w2[k] = c;
+        }
     }
     uint2 hs[kBlurRows + 6];   // hs[k] = horizontal sums of row (y0-3+k)
 #pragma unroll
@@ -247,28 +203,53 @@ __global__ void __launch_bounds__(128) blur7_kernel(const uint8_t* __restrict__ 
                 const uint32_t pr = (c & 1) ? hs[r + k].y : hs[r + k].x;
                 return (c & 2) ? (pr >> 16) : (pr & 0xffffu);
             };
-            const uint32_t s = 18u * (H(0) + H(6)) + 34u * (H(1) + H(5)) + 48u * (H(2) + H(4)) + 56u * H(3);
-            o[c] = (s + 32768u) >> 16;
+            const uint32_t sum = 18u * (H(0) + H(6)) + 34u * (H(1) + H(5)) + 48u * (H(2) + H(4)) + 56u * H(3);
+            o[c] = (sum + 32768u) >> 16;
         }
-        if (y0 + r < g.h)
-            *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * g.spitch + x0) =
+        if (y0 + r < h)
+            *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * spitch + x0) =
                 o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
     }
 }
 
+// EDGE = false: the interior strips (4 <= x0 <= w-8) of every level; EDGE = true: the 2-3 edge strips per strip row.
+template <bool EDGE>
+__global__ void __launch_bounds__(128) blur7_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb) {
+    int level = 0;
+    while (level + 1 < fl.nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
+    const LevelGeom g = d.geom[level];
+    // strips of a level are flattened so every block is full whatever the level width
+    const int nsx = (g.w + 3) >> 2;
+    const int ni = max((g.w - 8) >> 2, 0);            // interior strips per row: x0 = 4, 8, ..., 4*ni
+    const int per_row = EDGE ? nsx - ni : ni;
+    const int nsy = (g.h + kBlurRows - 1) / kBlurRows;
+    const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
+    if (id >= per_row * nsy) return;
+    int pitch;
+    const uint8_t* src = level_roi(d, fl, g, level, blockIdx.y, pitch);
+    uint8_t* dst = d.blur + (size_t)blockIdx.y * fl.splane_bytes + g.splane_off;
+    const int sy = id / per_row, k = id - sy * per_row;
+    const int x0 = EDGE ? (k == 0 ? 0 : 4 * (ni + k)) : 4 + 4 * k;
+    blur_strip<EDGE>(src, pitch, dst, g.spitch, g.w, g.h, x0, sy * kBlurRows);
+}
+
 int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
-    LevelBlocks lb;
-    int total = 0;
     const int threads = 128;
-    for (int l = 0; l < fl.nlevels; l++) {
-        lb.start[l] = total;
-        const int strips = ((hg[l].w + 3) / 4) * ((hg[l].h + kBlurRows - 1) / kBlurRows);
-        total += (strips + threads - 1) / threads;
+    for (int edge = 0; edge < 2; edge++) {
+        LevelBlocks lb;
+        int total = 0;
+        for (int l = 0; l < fl.nlevels; l++) {
+            lb.start[l] = total;
+            const int nsx = (hg[l].w + 3) / 4, ni = std::max((hg[l].w - 8) / 4, 0);
+            const int strips = (edge ? nsx - ni : ni) * ((hg[l].h + kBlurRows - 1) / kBlurRows);
+            total += (strips + threads - 1) / threads;
+        }
+        for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
+        if (total == 0) continue;
+        if (edge) blur7_kernel<true><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb);
+        else blur7_kernel<false><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb);
     }
-    for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
-    blur7_kernel<<<dim3(total, n_frames), threads, 0, s>>>(d.pyr, fl.pyr_bytes, d.blur, fl.splane_bytes, d.geom,
-                                                           fl.nlevels, lb);
-    return 1;
+    return 2;
 }
 
 }  // namespace orbcuda

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(128) stereo_kernel(const orb_keypoint_t* __res
                                                      const orb_keypoint_t* __restrict__ kr, const uint4* __restrict__ dr, int nr,
                                                      const float* __restrict__ sfs, const float* __restrict__ isfs,
                                                      const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
+                                                     const uint8_t* __restrict__ l0L, const uint8_t* __restrict__ l0R, int l0_pitch,
                                                      const LevelGeom* __restrict__ geom, int n_rows, float mbf, float max_d,
                                                      StereoOut* __restrict__ out) {
     const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -160,19 +161,21 @@ __global__ void __launch_bounds__(128) stereo_kernel(const orb_keypoint_t* __res
         const LevelGeom g = geom[levelL];
         const int w = 5, L = 5;
         if (!(cr0 < 0 || cr0 + L + w + 1 >= g.w)) {   // iniu < 0 || endu >= cols  (:579-582)
-            const uint8_t* PL = pyrL + g.plane_off + (size_t)kEdge * g.pitch + kXPad;
-            const uint8_t* PR = pyrR + g.plane_off + (size_t)kEdge * g.pitch + kXPad;
-            const int cL = PL[(ptrdiff_t)cv * g.pitch + cu];
+            // level 0 is the input image itself, levels >= 1 live in the padded pyramid planes
+            const int pitch = levelL ? g.pitch : l0_pitch;
+            const uint8_t* PL = levelL ? pyrL + g.plane_off + (size_t)kEdge * g.pitch + kXPad : l0L;
+            const uint8_t* PR = levelL ? pyrR + g.plane_off + (size_t)kEdge * g.pitch + kXPad : l0R;
+            const int cL = PL[(ptrdiff_t)cv * pitch + cu];
             int sads[11];
 #pragma unroll
             for (int s = 0; s < 11; s++) {
                 const int incR = s - L;
-                const int cR = PR[(ptrdiff_t)cv * g.pitch + cr0 + incR];
+                const int cR = PR[(ptrdiff_t)cv * pitch + cr0 + incR];
                 int acc = 0;
                 for (int t = lane; t < 121; t += 32) {
                     const int dy = t / 11 - w, dx = t % 11 - w;
-                    const int a = (int)PL[(ptrdiff_t)(cv + dy) * g.pitch + cu + dx] - cL;
-                    const int b = (int)PR[(ptrdiff_t)(cv + dy) * g.pitch + cr0 + incR + dx] - cR;
+                    const int a = (int)PL[(ptrdiff_t)(cv + dy) * pitch + cu + dx] - cL;
+                    const int b = (int)PR[(ptrdiff_t)(cv + dy) * pitch + cr0 + incR + dx] - cR;
                     acc += abs(a - b);
                 }
 #pragma unroll
@@ -296,7 +299,7 @@ using namespace orbcuda;
 // accessor implemented in extractor.cu
 extern "C" int orbx_internal_view(orbx_handle_t h, const uint8_t** d_pyr, const orbcuda::LevelGeom** d_geom,
                                   const orbcuda::LevelGeom** h_geom, orbcuda::FrameLayout* fl, int* device,
-                                  const float** sf, const float** isf);
+                                  const float** sf, const float** isf, const uint8_t** d_level0, int* level0_pitch);
 
 extern "C" {
 
@@ -431,8 +434,10 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
     if (n_left == 0 || n_right == 0) return ORB_OK;
     const uint8_t *pl, *pr; const LevelGeom *dgl, *dgr, *hgl, *hgr; FrameLayout fll, flr; int devl, devr;
     const float *sf, *isf, *sfr, *isfr;
-    if (orbx_internal_view(hl, &pl, &dgl, &hgl, &fll, &devl, &sf, &isf) || orbx_internal_view(hr, &pr, &dgr, &hgr, &flr, &devr, &sfr, &isfr) ||
-        !pl || !pr || devl != devr || fll.width != flr.width || fll.height != flr.height || fll.nlevels != flr.nlevels) {
+    const uint8_t *l0l, *l0r; int l0pl, l0pr;
+    if (orbx_internal_view(hl, &pl, &dgl, &hgl, &fll, &devl, &sf, &isf, &l0l, &l0pl) ||
+        orbx_internal_view(hr, &pr, &dgr, &hgr, &flr, &devr, &sfr, &isfr, &l0r, &l0pr) ||
+        !pl || !pr || !l0l || !l0r || l0pl != l0pr || devl != devr || fll.width != flr.width || fll.height != flr.height || fll.nlevels != flr.nlevels) {
         set_error("orbm_stereo_matches: the two extractors must have processed same-size images on one device");
         return ORB_ERR_ARG;
     }
@@ -452,7 +457,7 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
         if (!ok) rc = ORB_ERR_CUDA;
         if (!rc) {
             stereo_kernel<<<(n_left * 32 + 127) / 128, 128, 0, s>>>(bkl.as<orb_keypoint_t>(), bdl.as<uint4>(), n_left, bkr.as<orb_keypoint_t>(),
-                                                                  bdr.as<uint4>(), n_right, bsf.as<float>(), bisf.as<float>(), pl, pr, dgl,
+                                                                  bdr.as<uint4>(), n_right, bsf.as<float>(), bisf.as<float>(), pl, pr, l0l, l0r, l0pl, dgl,
                                                                   hgl[0].h, mbf, max_d, bout.as<StereoOut>());
             if (!cuda_ok(cudaGetLastError(), "stereo_kernel") ||
                 !cuda_ok(cudaMemcpyAsync(res.data(), bout.p, (size_t)n_left * sizeof(StereoOut), cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
