@@ -335,7 +335,7 @@ def run_ours(args):
 
         per_variant = {}
         ref_out = None
-        for variant, name in ((0, "popc"), (1, "imma")):
+        for variant, name in ((0, "popc"), (1, "imma_smem"), (2, "imma_stream")):
             for _ in range(3):
                 match_step(variant)
             barrier()

@@ -196,6 +196,97 @@ __global__ void __launch_bounds__(kMmaThreads, 2) knn2_mma_kernel(const uint32_t
         }
 }
 
+// K7b: same contraction without shared memory.  Every warp streams the map itself: the four lanes of a
+// fragment column load that column's packed descriptor (one 32-byte read, coalesced across the group) and
+// expand their own nibbles in registers, so there is no staging pass and no block barrier; the next group's
+// descriptor is prefetched while the current one is multiplied.
+__global__ void __launch_bounds__(kMmaThreads, 2) knn2_mma_stream_kernel(const uint32_t* __restrict__ q, int nq,
+                                                                        const uint4* __restrict__ m, long long nm,
+                                                                        long long per_split, long long index_base,
+                                                                        int4* __restrict__ partial) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int q0 = blockIdx.x * kMmaQPerCta + warp * 32;
+    uint32_t A[2][8][4];
+    int pa[2][2];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int r0 = q0 + t * 16 + gid, r1 = r0 + 8;
+        int p0 = 0, p1 = 0;
+#pragma unroll
+        for (int sx = 0; sx < 8; sx++) {
+            const uint32_t w0 = r0 < nq ? q[(size_t)r0 * 8 + sx] : 0u;
+            const uint32_t w1 = r1 < nq ? q[(size_t)r1 * 8 + sx] : 0u;
+            p0 += __popc(w0); p1 += __popc(w1);
+            A[t][sx][0] = expand_nibble(w0, 4 * tig);
+            A[t][sx][1] = expand_nibble(w1, 4 * tig);
+            A[t][sx][2] = expand_nibble(w0, 16 + 4 * tig);
+            A[t][sx][3] = expand_nibble(w1, 16 + 4 * tig);
+        }
+        pa[t][0] = p0; pa[t][1] = p1;
+    }
+    Top2 best[2][2];
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) best[t][h] = Top2{256, -1, 256, -1};
+
+    const long long lo = (long long)blockIdx.y * per_split;
+    const long long hi = min(nm, lo + per_split);
+    const long long last = hi - 1;
+    auto fetch = [&](long long j, uint4& x, uint4& y) {
+        const long long jj = min(j, last);     // clamp: columns past the end are masked in the epilogue
+        x = m[2 * jj]; y = m[2 * jj + 1];
+    };
+    if (lo < hi) {
+        uint4 cx, cy, nx, ny;
+        fetch(lo + gid, cx, cy);
+        for (long long base = lo; base < hi; base += 8) {
+            fetch(base + 8 + gid, nx, ny);                  // prefetch the next group's column
+            const uint32_t w[8] = {cx.x, cx.y, cx.z, cx.w, cy.x, cy.y, cy.z, cy.w};
+            int c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+            int pb = 0;
+#pragma unroll
+            for (int sx = 0; sx < 8; sx++) {
+                const uint32_t b0 = expand_nibble(w[sx], 4 * tig), b1 = expand_nibble(w[sx], 16 + 4 * tig);
+                pb += __popc(w[sx]);
+                mma_u8(c0, A[0][sx], b0, b1);
+                mma_u8(c1, A[1][sx], b0, b1);
+            }
+            // popcounts of columns 2*tig and 2*tig+1 live in the lanes of groups gid' = 2*tig, 2*tig+1
+            const int pb0 = __shfl_sync(0xffffffffu, pb, (2 * tig) * 4), pb1 = __shfl_sync(0xffffffffu, pb, (2 * tig + 1) * 4);
+            const long long col = base + 2 * tig;
+            const int idx0 = (int)(index_base + col);
+            const bool v0 = col < hi, v1 = col + 1 < hi;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int* c = t ? c1 : c0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int d0 = pa[t][h] + pb0 - 2 * c[2 * h], d1 = pa[t][h] + pb1 - 2 * c[2 * h + 1];
+                    if (v0 && d0 < best[t][h].d2) top2_push(best[t][h], d0, idx0);
+                    if (v1 && d1 < best[t][h].d2) top2_push(best[t][h], d1, idx0 + 1);
+                }
+            }
+            cx = nx; cy = ny;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            Top2 b = best[t][h];
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const int e1 = __shfl_xor_sync(0xffffffffu, b.d1, o), j1 = __shfl_xor_sync(0xffffffffu, b.i1, o);
+                const int e2 = __shfl_xor_sync(0xffffffffu, b.d2, o), j2 = __shfl_xor_sync(0xffffffffu, b.i2, o);
+                top2_merge(b.d1, b.i1, b.d2, b.i2, e1, j1, e2, j2);
+            }
+            const int row = q0 + t * 16 + gid + 8 * h;
+            if (tig == 0 && row < nq) partial[(size_t)blockIdx.y * nq + row] = make_int4(b.d1, b.i1, b.d2, b.i2);
+        }
+}
+
 __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -213,8 +304,8 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int qper = variant == 1 ? kMmaQPerCta : kKnnThreads;
-    const int tile = variant == 1 ? kMmaTile : kKnnTile;
+    const int qper = variant >= 1 ? kMmaQPerCta : kKnnThreads;
+    const int tile = variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile);
     const int per_sm = 2;
     const int qblocks = (nq + qper - 1) / qper;
     // enough map splits to fill the SMs, each at least one tile
@@ -237,6 +328,9 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         }
         knn2_mma_kernel<<<dim3(qblocks, splits), kMmaThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);
+    } else if (variant == 2) {
+        knn2_mma_stream_kernel<<<dim3(qblocks, splits), kMmaThreads, 0, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
+                                                                              index_base, partial);
     } else {
         knn2_popc_kernel<<<dim3(qblocks, splits), kKnnThreads, 0, s>>>((const uint4*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);

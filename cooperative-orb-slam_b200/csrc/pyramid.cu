@@ -139,6 +139,7 @@ int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg,
 // (row sums <= 255*256 fit 16 bits).  Vertical pass in 32 bit with the symmetric-tap factoring.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlurRows = 16;
+constexpr int kBlurEdgeRows = 4;   // edge strips gather bytes: keep those threads short
 
 
 __device__ __forceinline__ uint32_t funnel16(uint32_t lo, uint32_t hi) { return __funnelshift_r(lo, hi, 16); }
@@ -161,14 +162,14 @@ __device__ __forceinline__ uint2 blur_hsum4(uint32_t w0, uint32_t w1, uint32_t w
 // One strip: 4 columns x kBlurRows rows.  EDGE strips (window x0-4 .. x0+7 leaves the row) gather their
 // bytes with reflected column indices; they are numbered after all interior strips of the level so that
 // whole warps take one path or the other.
-template <bool EDGE>
+template <bool EDGE, int ROWS>
 __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int pitch, uint8_t* __restrict__ dst, int spitch,
                                            int w, int h, int x0, int y0) {
     // all 22 source rows of the strip are fetched up front (66 independent 32-bit loads in flight per thread),
     // then reduced to horizontal sums; the vertical pass slides over them
-    uint32_t w0[kBlurRows + 6], w1[kBlurRows + 6], w2[kBlurRows + 6];
+    uint32_t w0[ROWS + 6], w1[ROWS + 6], w2[ROWS + 6];
 #pragma unroll
-    for (int k = 0; k < kBlurRows + 6; k++) {
+    for (int k = 0; k < ROWS + 6; k++) {
         int y = y0 - 3 + k;
         y = y < 0 ? -y : y;                               // BORDER_REFLECT_101
         y = y >= h ? max(2 * h - 2 - y, 0) : y;           // (rows past h+2 feed outputs that are never stored)
@@ -191,11 +192,11 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
             w0[k] = a; w1[k] = b; w2[k] = c;
         }
     }
-    uint2 hs[kBlurRows + 6];   // hs[k] = horizontal sums of row (y0-3+k)
+    uint2 hs[ROWS + 6];   // hs[k] = horizontal sums of row (y0-3+k)
 #pragma unroll
-    for (int k = 0; k < kBlurRows + 6; k++) hs[k] = blur_hsum4(w0[k], w1[k], w2[k]);
+    for (int k = 0; k < ROWS + 6; k++) hs[k] = blur_hsum4(w0[k], w1[k], w2[k]);
 #pragma unroll
-    for (int r = 0; r < kBlurRows; r++) {
+    for (int r = 0; r < ROWS; r++) {
         uint32_t o[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(128) blur7_kernel(DevPtrs d, FrameLayout fl, L
     const int nsx = (g.w + 3) >> 2;
     const int ni = max((g.w - 8) >> 2, 0);            // interior strips per row: x0 = 4, 8, ..., 4*ni
     const int per_row = EDGE ? nsx - ni : ni;
-    const int nsy = (g.h + kBlurRows - 1) / kBlurRows;
+    constexpr int ROWS = EDGE ? kBlurEdgeRows : kBlurRows;
+    const int nsy = (g.h + ROWS - 1) / ROWS;
     const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
     if (id >= per_row * nsy) return;
     int pitch;
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(128) blur7_kernel(DevPtrs d, FrameLayout fl, L
     uint8_t* dst = d.blur + (size_t)blockIdx.y * fl.splane_bytes + g.splane_off;
     const int sy = id / per_row, k = id - sy * per_row;
     const int x0 = EDGE ? (k == 0 ? 0 : 4 * (ni + k)) : 4 + 4 * k;
-    blur_strip<EDGE>(src, pitch, dst, g.spitch, g.w, g.h, x0, sy * kBlurRows);
+    blur_strip<EDGE, ROWS>(src, pitch, dst, g.spitch, g.w, g.h, x0, sy * ROWS);
 }
 
 int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
@@ -241,7 +243,8 @@ int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, in
         for (int l = 0; l < fl.nlevels; l++) {
             lb.start[l] = total;
             const int nsx = (hg[l].w + 3) / 4, ni = std::max((hg[l].w - 8) / 4, 0);
-            const int strips = (edge ? nsx - ni : ni) * ((hg[l].h + kBlurRows - 1) / kBlurRows);
+            const int rows = edge ? kBlurEdgeRows : kBlurRows;
+            const int strips = (edge ? nsx - ni : ni) * ((hg[l].h + rows - 1) / rows);
             total += (strips + threads - 1) / threads;
         }
         for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
