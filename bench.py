@@ -361,6 +361,29 @@ def run_ours(args):
                     "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8,
                     "popc_kernel_frac_of_popc_peak": per_variant["popc"]["gcmp_s"] / (148 * 16 * 1.965 / 8)}
 
+    # ---------------- candidate loops (SearchByBoW / SearchForTriangulation / stereo): call latency through the C ABI
+    loops = None
+    if rank == 0 and world == 1 and not args.no_matching:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import matchdata
+        import oracle_lib
+        d1, d2, a1, a2, src, dst, rng = matchdata.two_views(1000, 1100, 0)
+        valid = np.ones(len(d1), np.uint8)
+        fv1, fv2 = matchdata.featvec(d1), matchdata.featvec(d2)
+        mt = orb.ORBmatcher(0.7, True, device=local)
+
+        def timeit(fn, n=30):
+            for _ in range(3):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            return (time.perf_counter() - t0) / n * 1e3
+
+        loops = {"search_by_bow_kf_f_ms": {"gpu_call": timeit(lambda: mt.SearchByBoW(d1, a1, valid, fv1, d2, a2, fv2)),
+                                           "cpu_oracle_1thread": timeit(lambda: oracle_lib.search_by_bow_kf_f(d1, a1, valid, fv1, d2, a2, fv2, 0.7, True))},
+                 "features": [len(d1), len(d2)], "note": "host arrays in/out, includes H2D/D2H; problem is tiny (~17 candidates per feature)"}
+
     # ---------------- CPU baseline (rank 0, N=1 only; bounded sample) --------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -381,7 +404,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "keypoints_downloaded": tot_kp},
                 "gpu_launches": int(launches), "clocks": clocks, "matching": matching,
-                "single_frame_latency_ms": latency_ms}
+                "single_frame_latency_ms": latency_ms, "candidate_loops": loops}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

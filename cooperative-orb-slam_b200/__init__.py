@@ -81,6 +81,7 @@ ABI = {
     "orbm_search_for_triangulation": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _F, _F, _VP, _VP, _I, _I, _VP,
                                           _I, _VP, _I]),
     "orbm_stereo_matches": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _VP, _VP, _VP]),
+    "orbm_distinctive_descriptors": (_I, [_VP, _VP, _I, _VP, _I]),
 }
 
 
@@ -407,6 +408,14 @@ class ORBmatcher:
                                                      _p(s2), int(bOnlyStereo), int(self.mbCheckOrientation), _p(out),
                                                      cap, C.byref(n), self.device), "orbm_search_for_triangulation")
         return n.value, out[:n.value].copy()
+
+
+def compute_distinctive_descriptors(desc, ptr, device=0):
+    """MapPoint::ComputeDistinctiveDescriptors (R21/src/MapPoint.cc:242-307) for a batch of map points (CSR)."""
+    d = np.ascontiguousarray(desc, np.uint8); p = np.ascontiguousarray(ptr, np.int32)
+    best = np.zeros(len(p) - 1, np.int32)
+    _check(lib().orbm_distinctive_descriptors(_p(d), _p(p), len(p) - 1, _p(best), device), "orbm_distinctive_descriptors")
+    return best
 
 
 def compute_stereo_matches(ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mbf, mb):

@@ -125,6 +125,26 @@ __device__ __forceinline__ const uint8_t* level_roi(const DevPtrs& d, const Fram
 }
 #endif
 
+// Per-thread workspace of the matcher entry points: one stream, one grow-only device arena and one pinned
+// host arena per calling thread, so a call costs no cudaMalloc / stream creation and all its copies are
+// truly asynchronous.  The reference constructs ORBmatcher objects on the stack from three threads at once
+// (SURVEY 3.3); a thread-local context keeps the entry points re-entrant without locks.
+struct MatchCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    char* dbase = nullptr; size_t dcap = 0, doff = 0;
+    char* hbase = nullptr; size_t hcap = 0, hoff = 0;
+    struct Pending { void* dst; const void* staged; size_t bytes; };
+    Pending pend[8]; int npend = 0;
+    bool begin(int dev, size_t dev_bytes, size_t host_bytes);   // select device, size the arenas, reset them
+    void* dalloc(size_t bytes);                                   // device bump allocation (256-B aligned)
+    void* upload(const void* src, size_t bytes);                  // staged async H2D, returns the device copy
+    bool download(void* dst, const void* dsrc, size_t bytes);     // async D2H into staging; copied out by finish()
+    bool finish();                                                // stream sync + deliver the downloads
+    ~MatchCtx();
+};
+MatchCtx& match_ctx();
+
 void set_error(const char* fmt, ...);
 bool cuda_ok(cudaError_t e, const char* what);
 

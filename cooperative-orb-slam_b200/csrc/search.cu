@@ -115,6 +115,40 @@ __global__ void __launch_bounds__(128) triangulation_kernel(const uint4* __restr
     if (lane == 0) match12[it.ia] = key == 0xffffffffu ? -1 : idx2[it.b0 + (int)(0xfffffu - (key & 0xfffffu))];
 }
 
+// One warp per map point (MapPoint::ComputeDistinctiveDescriptors R21/src/MapPoint.cc:242-307): all-pairs
+// Hamming distances into scratch, then each row's median by counting (the k-th smallest is the value v with
+// #{< v} <= k < #{<= v}), then the first row of least median.
+__global__ void __launch_bounds__(128) distinctive_kernel(const uint4* __restrict__ desc, const int* __restrict__ ptr,
+                                                          const long long* __restrict__ soff, int n_points,
+                                                          unsigned short* __restrict__ scratch, int* __restrict__ best) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n_points) return;
+    const int first = ptr[p], N = ptr[p + 1] - first;
+    if (N <= 0) { if (lane == 0) best[p] = -1; return; }
+    unsigned short* D = scratch + soff[p];
+    for (int idx = lane; idx < N * N; idx += 32) {
+        const int i = idx / N, j = idx - i * N;
+        const uint4 a0 = desc[2 * (size_t)(first + i)], a1 = desc[2 * (size_t)(first + i) + 1];
+        D[idx] = (unsigned short)hamming256(a0, a1, desc + 2 * (size_t)(first + j));
+    }
+    __syncwarp();
+    const int k = (int)(0.5 * (N - 1));
+    unsigned key = 0xffffffffu;
+    for (int i = lane; i < N; i += 32) {
+        const unsigned short* row = D + (size_t)i * N;
+        int median = 256;
+        for (int j = 0; j < N; j++) {
+            const int v = row[j];
+            int lt = 0, le = 0;
+            for (int l = 0; l < N; l++) { const int u = row[l]; lt += u < v; le += u <= v; }
+            if (lt <= k && k < le) { median = v; break; }
+        }
+        key = min(key, ((unsigned)median << 20) | (unsigned)i);   // least median, first index on ties
+    }
+    key = warp_min(key);
+    if (lane == 0) best[p] = (int)(key & 0xfffff);
+}
+
 struct StereoOut { float u_right, depth; int sad; int ok; };
 
 // One warp per left key point (Frame::ComputeStereoMatches :504-628).
@@ -210,18 +244,6 @@ __global__ void __launch_bounds__(128) stereo_kernel(const orb_keypoint_t* __res
 }
 
 // ---- host helpers -----------------------------------------------------------------------------------
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    template <class T> T* as() { return (T*)p; }
-    bool upload(const void* src, size_t bytes, cudaStream_t s) {
-        if (!cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc")) return false;
-        if (bytes && !cuda_ok(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync")) return false;
-        return true;
-    }
-    bool alloc(size_t bytes) { return cuda_ok(cudaMalloc(&p, std::max<size_t>(bytes, 16)), "cudaMalloc"); }
-};
-
 static void shared_nodes(const orbm_featvec_t* a, const orbm_featvec_t* b, std::vector<NodePair>& out) {
     int i = 0, j = 0;   // merge walk of two sorted maps (R21 ORBmatcher.cc:175-263)
     while (i < a->n_nodes && j < b->n_nodes) {
@@ -264,32 +286,29 @@ static int run_bow(int mode, const uint8_t* dA, const uint8_t* vA, int nA, const
     std::vector<NodePair> pairs;
     shared_nodes(fvA, fvB, pairs);
     if (pairs.empty() || nA == 0 || nB == 0) return ORB_OK;
-    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no usable CUDA device %d (no CPU fallback)", device); return ORB_ERR_CUDA; }
-    cudaStream_t s = nullptr;
-    if (!cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return ORB_ERR_CUDA;
-    int rc = ORB_OK;
-    {
-        DevBuf bdA, bvA, biA, bdB, bvB, biB, bpairs, bmB, bmA;
-        const int nia = fvA->ptr[fvA->n_nodes], nib = fvB->ptr[fvB->n_nodes];
-        const bool ok = bdA.upload(dA, (size_t)nA * 32, s) && bvA.upload(vA, nA, s) && biA.upload(fvA->idx, (size_t)nia * 4, s) &&
-                        bdB.upload(dB, (size_t)nB * 32, s) && bvB.upload(vB ? vB : vA, vB ? nB : 0, s) && biB.upload(fvB->idx, (size_t)nib * 4, s) &&
-                        bpairs.upload(pairs.data(), pairs.size() * sizeof(NodePair), s) && bmB.upload(matchB.data(), (size_t)nB * 4, s) &&
-                        bmA.upload(matchA.data(), (size_t)nA * 4, s);
-        if (!ok) rc = ORB_ERR_CUDA;
-        if (!rc) {
-            const int np = (int)pairs.size();
-            bow_kernel<<<(np * 32 + 127) / 128, 128, 0, s>>>(bdA.as<uint4>(), bvA.as<uint8_t>(), biA.as<int>(), bdB.as<uint4>(),
-                                                           bvB.as<uint8_t>(), biB.as<int>(), bpairs.as<NodePair>(), np, ratio, mode,
-                                                           bmB.as<int>(), bmA.as<int>());
-            if (!cuda_ok(cudaGetLastError(), "bow_kernel") ||
-                !cuda_ok(cudaMemcpyAsync(matchB.data(), bmB.p, (size_t)nB * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
-                !cuda_ok(cudaMemcpyAsync(matchA.data(), bmA.p, (size_t)nA * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
-                !cuda_ok(cudaStreamSynchronize(s), "bow_kernel"))
-                rc = ORB_ERR_CUDA;
-        }
-    }
-    cudaStreamDestroy(s);
-    return rc;
+    const int nia = fvA->ptr[fvA->n_nodes], nib = fvB->ptr[fvB->n_nodes];
+    const size_t bytes = (size_t)nA * 32 + nA + (size_t)nia * 4 + (size_t)nB * 32 + nB + (size_t)nib * 4 +
+                         pairs.size() * sizeof(NodePair) + (size_t)(nA + nB) * 4;
+    MatchCtx& cx = match_ctx();
+    if (!cx.begin(device, bytes + 16 * 256, bytes + (size_t)(nA + nB) * 4 + 24 * 256)) return ORB_ERR_CUDA;
+    const uint4* d_dA = (const uint4*)cx.upload(dA, (size_t)nA * 32);
+    const uint8_t* d_vA = (const uint8_t*)cx.upload(vA, nA);
+    const int* d_iA = (const int*)cx.upload(fvA->idx, (size_t)nia * 4);
+    const uint4* d_dB = (const uint4*)cx.upload(dB, (size_t)nB * 32);
+    const uint8_t* d_vB = (const uint8_t*)cx.upload(vB ? vB : vA, vB ? nB : 0);
+    const int* d_iB = (const int*)cx.upload(fvB->idx, (size_t)nib * 4);
+    const NodePair* d_pairs = (const NodePair*)cx.upload(pairs.data(), pairs.size() * sizeof(NodePair));
+    int* d_mB = (int*)cx.dalloc((size_t)nB * 4);
+    int* d_mA = (int*)cx.dalloc((size_t)nA * 4);
+    if (!d_dA || !d_vA || !d_iA || !d_dB || !d_vB || !d_iB || !d_pairs || !d_mB || !d_mA) return ORB_ERR_CUDA;
+    ORB_CUDA_TRY(cudaMemsetAsync(d_mB, 0xff, (size_t)nB * 4, cx.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_mA, 0xff, (size_t)nA * 4, cx.stream));
+    const int np = (int)pairs.size();
+    bow_kernel<<<(np * 32 + 127) / 128, 128, 0, cx.stream>>>(d_dA, d_vA, d_iA, d_dB, d_vB, d_iB, d_pairs, np, ratio, mode, d_mB, d_mA);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (!cx.download(matchB.data(), d_mB, (size_t)nB * 4) || !cx.download(matchA.data(), d_mA, (size_t)nA * 4) || !cx.finish())
+        return ORB_ERR_CUDA;
+    return ORB_OK;
 }
 
 }  // namespace orbcuda
@@ -374,33 +393,30 @@ int orbm_search_for_triangulation(const uint8_t* desc1, const orbm_tri_feature_t
         }
     std::vector<int> m12(n1, -1);
     if (!items.empty() && n2 > 0) {
-        if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no usable CUDA device %d (no CPU fallback)", device); return ORB_ERR_CUDA; }
-        cudaStream_t s = nullptr;
-        if (!cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return ORB_ERR_CUDA;
-        int rc = ORB_OK;
-        {
-            int max_oct = 0;
-            for (int i = 0; i < n2; i++) max_oct = std::max(max_oct, f2[i].octave);
-            DevBuf bd1, bf1, bd2, bf2, bi2, bit, bF, bsf, bs2, bm;
-            const bool ok = bd1.upload(desc1, (size_t)n1 * 32, s) && bf1.upload(f1, (size_t)n1 * sizeof(TriFeat), s) &&
-                            bd2.upload(desc2, (size_t)n2 * 32, s) && bf2.upload(f2, (size_t)n2 * sizeof(TriFeat), s) &&
-                            bi2.upload(fv2->idx, (size_t)fv2->ptr[fv2->n_nodes] * 4, s) && bit.upload(items.data(), items.size() * sizeof(TriItem), s) &&
-                            bF.upload(F12, 36, s) && bsf.upload(scale_factors2, (size_t)(max_oct + 1) * 4, s) &&
-                            bs2.upload(level_sigma2_2, (size_t)(max_oct + 1) * 4, s) && bm.upload(m12.data(), (size_t)n1 * 4, s);
-            if (!ok) rc = ORB_ERR_CUDA;
-            if (!rc) {
-                const int ni = (int)items.size();
-                triangulation_kernel<<<(ni * 32 + 127) / 128, 128, 0, s>>>(bd1.as<uint4>(), bf1.as<TriFeat>(), bd2.as<uint4>(), bf2.as<TriFeat>(),
-                                                                         bi2.as<int>(), bit.as<TriItem>(), ni, bF.as<float>(), ex, ey,
-                                                                         bsf.as<float>(), bs2.as<float>(), only_stereo, bm.as<int>());
-                if (!cuda_ok(cudaGetLastError(), "triangulation_kernel") ||
-                    !cuda_ok(cudaMemcpyAsync(m12.data(), bm.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
-                    !cuda_ok(cudaStreamSynchronize(s), "triangulation_kernel"))
-                    rc = ORB_ERR_CUDA;
-            }
-        }
-        cudaStreamDestroy(s);
-        if (rc) return rc;
+        int max_oct = 0;
+        for (int i = 0; i < n2; i++) max_oct = std::max(max_oct, f2[i].octave);
+        const int ni2 = fv2->ptr[fv2->n_nodes];
+        const size_t bytes = (size_t)n1 * (32 + sizeof(TriFeat) + 4) + (size_t)n2 * (32 + sizeof(TriFeat)) + (size_t)ni2 * 4 +
+                             items.size() * sizeof(TriItem) + 36 + (size_t)(max_oct + 1) * 8;
+        MatchCtx& cx = match_ctx();
+        if (!cx.begin(device, bytes + 16 * 256, bytes + (size_t)n1 * 4 + 24 * 256)) return ORB_ERR_CUDA;
+        const uint4* d_d1 = (const uint4*)cx.upload(desc1, (size_t)n1 * 32);
+        const TriFeat* d_f1 = (const TriFeat*)cx.upload(f1, (size_t)n1 * sizeof(TriFeat));
+        const uint4* d_d2 = (const uint4*)cx.upload(desc2, (size_t)n2 * 32);
+        const TriFeat* d_f2 = (const TriFeat*)cx.upload(f2, (size_t)n2 * sizeof(TriFeat));
+        const int* d_i2 = (const int*)cx.upload(fv2->idx, (size_t)ni2 * 4);
+        const TriItem* d_it = (const TriItem*)cx.upload(items.data(), items.size() * sizeof(TriItem));
+        const float* d_F = (const float*)cx.upload(F12, 36);
+        const float* d_sf = (const float*)cx.upload(scale_factors2, (size_t)(max_oct + 1) * 4);
+        const float* d_s2 = (const float*)cx.upload(level_sigma2_2, (size_t)(max_oct + 1) * 4);
+        int* d_m = (int*)cx.dalloc((size_t)n1 * 4);
+        if (!d_d1 || !d_f1 || !d_d2 || !d_f2 || !d_i2 || !d_it || !d_F || !d_sf || !d_s2 || !d_m) return ORB_ERR_CUDA;
+        ORB_CUDA_TRY(cudaMemsetAsync(d_m, 0xff, (size_t)n1 * 4, cx.stream));
+        const int ni = (int)items.size();
+        triangulation_kernel<<<(ni * 32 + 127) / 128, 128, 0, cx.stream>>>(d_d1, d_f1, d_d2, d_f2, d_i2, d_it, ni, d_F, ex, ey, d_sf, d_s2,
+                                                                         only_stereo, d_m);
+        ORB_CUDA_TRY(cudaGetLastError());
+        if (!cx.download(m12.data(), d_m, (size_t)n1 * 4) || !cx.finish()) return ORB_ERR_CUDA;
     }
     int nmatches = 0;
     for (int i = 0; i < n1; i++) nmatches += m12[i] >= 0;
@@ -424,6 +440,30 @@ int orbm_search_for_triangulation(const uint8_t* desc1, const orbm_tri_feature_t
     return np > cap_pairs ? ORB_ERR_CAPACITY : ORB_OK;
 }
 
+int orbm_distinctive_descriptors(const uint8_t* desc, const int32_t* ptr, int n_points, int32_t* best, int device) {
+    if (n_points < 0 || !ptr || !best || (n_points > 0 && ptr[n_points] > 0 && !desc)) { set_error("orbm_distinctive_descriptors: bad arguments"); return ORB_ERR_ARG; }
+    if (n_points == 0) return ORB_OK;
+    std::vector<long long> soff(n_points + 1, 0);
+    for (int p = 0; p < n_points; p++) {
+        const long long N = ptr[p + 1] - ptr[p];
+        if (N < 0 || N >= (1 << 20)) { set_error("orbm_distinctive_descriptors: bad CSR"); return ORB_ERR_ARG; }
+        soff[p + 1] = soff[p] + N * N;
+    }
+    const size_t up = (size_t)ptr[n_points] * 32 + (size_t)(n_points + 1) * 12;
+    MatchCtx& cx = match_ctx();
+    if (!cx.begin(device, up + (size_t)soff[n_points] * 2 + (size_t)n_points * 4 + 16 * 256, up + (size_t)n_points * 4 + 16 * 256)) return ORB_ERR_CUDA;
+    const uint4* d_desc = (const uint4*)cx.upload(desc, (size_t)ptr[n_points] * 32);
+    const int* d_ptr = (const int*)cx.upload(ptr, (size_t)(n_points + 1) * 4);
+    const long long* d_soff = (const long long*)cx.upload(soff.data(), (size_t)(n_points + 1) * 8);
+    unsigned short* d_scr = (unsigned short*)cx.dalloc((size_t)soff[n_points] * 2);
+    int* d_best = (int*)cx.dalloc((size_t)n_points * 4);
+    if (!d_desc || !d_ptr || !d_soff || !d_scr || !d_best) return ORB_ERR_CUDA;
+    distinctive_kernel<<<(n_points * 32 + 127) / 128, 128, 0, cx.stream>>>(d_desc, d_ptr, d_soff, n_points, d_scr, d_best);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (!cx.download(best, d_best, (size_t)n_points * 4) || !cx.finish()) return ORB_ERR_CUDA;
+    return ORB_OK;
+}
+
 int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t* keys_left, const uint8_t* desc_left,
                         int n_left, const orb_keypoint_t* keys_right, const uint8_t* desc_right, int n_right, float mbf,
                         float mb, float* u_right, float* depth, int* n_matches) {
@@ -442,31 +482,25 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
         return ORB_ERR_ARG;
     }
     if (n_right >= (1 << 20)) return ORB_ERR_ARG;
-    ORB_CUDA_TRY(cudaSetDevice(devl));
-    cudaStream_t s = nullptr;
-    ORB_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     std::vector<StereoOut> res(n_left);
-    int rc = ORB_OK;
     {
         const float max_d = mbf / mb;   // maxD = mbf/minZ, minZ = mb  (:501-503)
-        DevBuf bkl, bdl, bkr, bdr, bsf, bisf, bout;
-        const bool ok = bkl.upload(keys_left, (size_t)n_left * sizeof(orb_keypoint_t), s) && bdl.upload(desc_left, (size_t)n_left * 32, s) &&
-                        bkr.upload(keys_right, (size_t)n_right * sizeof(orb_keypoint_t), s) && bdr.upload(desc_right, (size_t)n_right * 32, s) &&
-                        bsf.upload(sf, (size_t)fll.nlevels * 4, s) && bisf.upload(isf, (size_t)fll.nlevels * 4, s) &&
-                        bout.alloc((size_t)n_left * sizeof(StereoOut));
-        if (!ok) rc = ORB_ERR_CUDA;
-        if (!rc) {
-            stereo_kernel<<<(n_left * 32 + 127) / 128, 128, 0, s>>>(bkl.as<orb_keypoint_t>(), bdl.as<uint4>(), n_left, bkr.as<orb_keypoint_t>(),
-                                                                  bdr.as<uint4>(), n_right, bsf.as<float>(), bisf.as<float>(), pl, pr, l0l, l0r, l0pl, dgl,
-                                                                  hgl[0].h, mbf, max_d, bout.as<StereoOut>());
-            if (!cuda_ok(cudaGetLastError(), "stereo_kernel") ||
-                !cuda_ok(cudaMemcpyAsync(res.data(), bout.p, (size_t)n_left * sizeof(StereoOut), cudaMemcpyDeviceToHost, s), "cudaMemcpy") ||
-                !cuda_ok(cudaStreamSynchronize(s), "stereo_kernel"))
-                rc = ORB_ERR_CUDA;
-        }
+        const size_t bytes = (size_t)(n_left + n_right) * (sizeof(orb_keypoint_t) + 32) + (size_t)fll.nlevels * 8;
+        MatchCtx& cx = match_ctx();
+        if (!cx.begin(devl, bytes + (size_t)n_left * sizeof(StereoOut) + 16 * 256, bytes + (size_t)n_left * sizeof(StereoOut) + 16 * 256)) return ORB_ERR_CUDA;
+        const orb_keypoint_t* d_kl = (const orb_keypoint_t*)cx.upload(keys_left, (size_t)n_left * sizeof(orb_keypoint_t));
+        const uint4* d_dl = (const uint4*)cx.upload(desc_left, (size_t)n_left * 32);
+        const orb_keypoint_t* d_kr = (const orb_keypoint_t*)cx.upload(keys_right, (size_t)n_right * sizeof(orb_keypoint_t));
+        const uint4* d_dr = (const uint4*)cx.upload(desc_right, (size_t)n_right * 32);
+        const float* d_sf = (const float*)cx.upload(sf, (size_t)fll.nlevels * 4);
+        const float* d_isf = (const float*)cx.upload(isf, (size_t)fll.nlevels * 4);
+        StereoOut* d_out = (StereoOut*)cx.dalloc((size_t)n_left * sizeof(StereoOut));
+        if (!d_kl || !d_dl || !d_kr || !d_dr || !d_sf || !d_isf || !d_out) return ORB_ERR_CUDA;
+        stereo_kernel<<<(n_left * 32 + 127) / 128, 128, 0, cx.stream>>>(d_kl, d_dl, n_left, d_kr, d_dr, n_right, d_sf, d_isf, pl, pr, l0l, l0r,
+                                                                      l0pl, dgl, hgl[0].h, mbf, max_d, d_out);
+        ORB_CUDA_TRY(cudaGetLastError());
+        if (!cx.download(res.data(), d_out, (size_t)n_left * sizeof(StereoOut)) || !cx.finish()) return ORB_ERR_CUDA;
     }
-    cudaStreamDestroy(s);
-    if (rc) return rc;
     std::vector<std::pair<int, int>> distIdx;
     for (int i = 0; i < n_left; i++)
         if (res[i].ok) { u_right[i] = res[i].u_right; depth[i] = res[i].depth; distIdx.push_back(std::make_pair(res[i].sad, i)); }

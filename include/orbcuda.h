@@ -160,6 +160,12 @@ int orbm_merge_top2_host(const int32_t* parts_rec, int parts, int nq, int32_t* o
  * strict) and (float)d1 < ratio*(float)d2.  out_match[i] = i1 or -1. */
 int orbm_ratio_test_host(const int32_t* rec, int nq, float ratio, int th, int strict, int32_t* out_match);
 
+/* void MapPoint::ComputeDistinctiveDescriptors()  R21/src/MapPoint.cc:242-307, batched over map points.
+ * Point p owns the descriptors of its (non-bad) observations desc[ptr[p] .. ptr[p+1]) (N x 32 bytes, host);
+ * best[p] = index inside that list of the descriptor with the least median Hamming distance to the others
+ * (median = sorted[(int)(0.5*(N-1))], first minimum wins), -1 for a point without observations. */
+int orbm_distinctive_descriptors(const uint8_t* desc, const int32_t* ptr, int n_points, int32_t* best, int device);
+
 /* DBoW2::FeatureVector as CSR: node ids ascending; node i owns idx[ptr[i] .. ptr[i+1]). */
 typedef struct {
     int32_t n_nodes;

@@ -768,6 +768,33 @@ extern "C" void orc_knn2_full(const uint8_t* q, int nq, const uint8_t* m, int64_
     });
 }
 
+// MapPoint::ComputeDistinctiveDescriptors R21/src/MapPoint.cc:242-307
+extern "C" void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* ptr, int n_points, int32_t* best) {
+    for (int p = 0; p < n_points; p++) {
+        const int N = ptr[p + 1] - ptr[p];
+        best[p] = -1;
+        if (N <= 0) continue;
+        const uint8_t* D = desc + (size_t)ptr[p] * 32;
+        std::vector<float> dist((size_t)N * N);
+        for (int i = 0; i < N; i++) {
+            dist[(size_t)i * N + i] = 0;
+            for (int j = i + 1; j < N; j++) {
+                const int dij = orc_descriptor_distance(D + (size_t)i * 32, D + (size_t)j * 32);
+                dist[(size_t)i * N + j] = (float)dij;
+                dist[(size_t)j * N + i] = (float)dij;
+            }
+        }
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            std::vector<int> v(dist.begin() + (size_t)i * N, dist.begin() + (size_t)(i + 1) * N);
+            std::sort(v.begin(), v.end());
+            const int median = v[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best[p] = BestIdx;
+    }
+}
+
 namespace {
 const int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;  // R21 ORBmatcher.cc:37-39
 

@@ -106,6 +106,11 @@ void orc_knn2(const uint8_t* q, int nq, const uint8_t* m, int64_t nm, int64_t in
 void orc_knn2_full(const uint8_t* q, int nq, const uint8_t* m, int64_t nm, int64_t index_base,
                    int32_t* i1, int32_t* d1, int32_t* i2, int32_t* d2, int nthreads);
 
+/* MapPoint::ComputeDistinctiveDescriptors (R21/src/MapPoint.cc:242-307) for a batch of map points: point p owns
+ * the observation descriptors desc[ptr[p] .. ptr[p+1]); best[p] = index (within the point's list) of the descriptor
+ * with the least median Hamming distance to the others (-1 for a point without observations). */
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* ptr, int n_points, int32_t* best);
+
 /* FeatureVector as CSR: node_ids ascending; node i owns idx[ptr[i]..ptr[i+1]) */
 typedef struct {
     int32_t n_nodes;

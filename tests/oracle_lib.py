@@ -322,3 +322,12 @@ def stereo_matches(kl, dl, kr, dr, ext_l, ext_r, mbf, mb):
                                  C.cast(PL, C.c_void_p), C.cast(PR, C.c_void_p), _p(lw), _p(lh), _p(st), float(mbf), float(mb),
                                  _p(ur), _p(dep))
     return ur, dep, n
+
+
+def distinctive_descriptors(desc, ptr):
+    d = np.ascontiguousarray(desc, np.uint8); p = np.ascontiguousarray(ptr, np.int32)
+    best = np.zeros(len(p) - 1, np.int32)
+    L = lib()
+    L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_distinctive_descriptors(_p(d), _p(p), len(p) - 1, _p(best))
+    return best

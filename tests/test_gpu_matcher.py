@@ -135,3 +135,21 @@ def test_stereo_matches(orb, oracle, synth, seed):
     # empty sides are legal
     ur0, dep0, n0 = orb.compute_stereo_matches(el, er, kl, dl, kr[:0], dr[:0], mbf, mbf / fx)
     assert n0 == 0 and (ur0 == -1).all()
+
+
+def test_distinctive_descriptors(orb, oracle):
+    """MapPoint::ComputeDistinctiveDescriptors batched: least-median descriptor per map point."""
+    rng = np.random.default_rng(42)
+    sizes = [0, 1, 2, 3, 5, 8, 31, 32, 33, 70] + list(rng.integers(1, 40, 500))
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    base = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    desc = np.zeros((ptr[-1], 32), np.uint8)
+    for p, n in enumerate(sizes):
+        bits = np.unpackbits(np.repeat(base[p][None], n, 0), axis=1) if n else np.zeros((0, 256), np.uint8)
+        flip = rng.random(bits.shape) < 0.1
+        desc[ptr[p]:ptr[p + 1]] = np.packbits(bits ^ flip, axis=1) if n else desc[ptr[p]:ptr[p + 1]]
+    if sizes[4] >= 3:
+        desc[ptr[4] + 1] = desc[ptr[4]]          # duplicates -> tied medians, the first index must win
+    ref = oracle.distinctive_descriptors(desc, ptr)
+    got = orb.compute_distinctive_descriptors(desc, ptr)
+    assert np.array_equal(ref, got)
