@@ -335,7 +335,7 @@ def run_ours(args):
 
         per_variant = {}
         ref_out = None
-        for variant, name in ((0, "popc"), (1, "imma_smem"), (2, "imma_stream")):
+        for variant, name in ((0, "popc"), (1, "imma_smem"), (2, "imma_stream"), (3, "tcgen05")):
             for _ in range(3):
                 match_step(variant)
             barrier()

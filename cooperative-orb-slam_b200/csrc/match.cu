@@ -287,6 +287,185 @@ __global__ void __launch_bounds__(kMmaThreads, 2) knn2_mma_stream_kernel(const u
         }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K7c: the same contraction on the 5th-generation tensor cores: tcgen05.mma kind::i8 (M=128 queries x
+// N=256 map descriptors x K=32 per instruction, 8 instructions per tile) with the int32 accumulators in
+// tensor memory (256 columns).  Operands are the {0,1}-expanded descriptors, written by the CTA itself into
+// shared memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices; leading
+// byte offset 128 between the K chunks, stride byte offset 2048 between 8-row groups), so no TMA is needed.
+// One elected thread issues the MMAs and commits them to an mbarrier; all four warps then drain TMEM with
+// tcgen05.ld (warp w owns lanes 32w..32w+31 = query rows, 32 columns per load).  The query operand is signed
+// (+1 for a set bit, -1 for a clear one), the map operand unsigned {0,1}, so the accumulator already is
+// g = 2*popc(a&b) - popc(b) and d = popc(a) - g: a column can only enter a query's top-2 if g > popc(a) - d2,
+// a per-thread scalar, so the drain is one 3-input max tree per 32 columns and a rare detailed scan.  Two
+// CTAs per SM (2 x 256 TMEM columns, 2 x 97 KB smem) overlap one CTA's staging / drain with the other's MMAs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 128;
+constexpr int kTcM = 128;     // queries per CTA
+constexpr int kTcN = 256;     // map descriptors per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_NONE: start address, LBO = 128 B, SBO = 2048 B (all >> 4), version 1 (Blackwell)
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46);
+}
+
+// 16 bits -> 16 bytes of 0/1 stored as one 16-byte chunk
+__device__ __forceinline__ uint4 expand16(uint32_t bits16) {
+    return make_uint4(expand_nibble(bits16, 0), expand_nibble(bits16, 4), expand_nibble(bits16, 8), expand_nibble(bits16, 12));
+}
+
+// bytes of 0/1 -> bytes of -1/+1 (signed 8 bit)
+__device__ __forceinline__ uint32_t pm1(uint32_t e) { return e | ((e ^ 0x01010101u) * 0xffu); }
+__device__ __forceinline__ uint4 to_pm1(uint4 v) { return make_uint4(pm1(v.x), pm1(v.y), pm1(v.z), pm1(v.w)); }
+
+__global__ void __launch_bounds__(kTcThreads, 2) knn2_tc_kernel(const uint32_t* __restrict__ q, int nq,
+                                                               const uint32_t* __restrict__ m, long long nm,
+                                                               long long per_split, long long index_base,
+                                                               int4* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [128 rows][256 B] UMMA layout (32 KB)
+    unsigned char* s_b = s_a + kTcM * 256;                       // [256 rows][256 B] UMMA layout (64 KB)
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int q0 = blockIdx.x * kTcM;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kTcN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    // ---- A tile: query row = thread; element (r, c) at (r/8)*2048 + (c/16)*128 + (r%8)*16 + c%16
+    int pa = 0;
+    {
+        const int r = tid, row = q0 + r;
+        unsigned char* dst = s_a + (r >> 3) * 2048 + (r & 7) * 16;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint32_t bits = row < nq ? q[(size_t)row * 8 + w] : 0u;
+            pa += __popc(bits);
+            *reinterpret_cast<uint4*>(dst + (2 * w) * 128) = to_pm1(expand16(bits & 0xffffu));
+            *reinterpret_cast<uint4*>(dst + (2 * w + 1) * 128) = to_pm1(expand16(bits >> 16));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::);
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::);
+    const uint32_t tmem = s_tmem;
+    // instruction descriptor: D = s32, A = signed 8 bit, B = unsigned 8 bit, both K-major, N = 256, M = 128
+    const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+    const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b), bar = smem_u32(&s_bar);
+
+    Top2 best = {256, -1, 256, -1};
+    const long long lo = (long long)blockIdx.y * per_split;
+    const long long hi = min(nm, lo + per_split);
+    uint32_t phase = 0;
+    // raw words of the next tile are fetched into registers one tile ahead (16 per thread), so the global-memory
+    // latency hides behind the MMAs and the drain of the current tile
+    constexpr int kWordsPerThread = kTcN * 8 / kTcThreads;   // 16
+    uint32_t raw[kWordsPerThread];
+    auto fetch = [&](long long base) {
+        const int cnt = (int)min((long long)kTcN, hi - base);
+#pragma unroll
+        for (int i = 0; i < kWordsPerThread; i++) {
+            // consecutive threads -> consecutive rows of one 8-row group (conflict-free 16-byte stores later)
+            const int it = tid + i * kTcThreads;
+            const int r = (it & 7) | ((it >> 6) << 3), w = (it >> 3) & 7;
+            raw[i] = (base < hi && r < cnt) ? m[(size_t)(base + r) * 8 + w] : 0u;
+        }
+    };
+    fetch(lo);
+    for (long long base = lo; base < hi; base += kTcN) {
+        const int cnt = (int)min((long long)kTcN, hi - base);
+        // ---- expand the prefetched B tile into the UMMA layout
+#pragma unroll
+        for (int i = 0; i < kWordsPerThread; i++) {
+            const int it = tid + i * kTcThreads;
+            const int r = (it & 7) | ((it >> 6) << 3), w = (it >> 3) & 7;
+            unsigned char* dst = s_b + (r >> 3) * 2048 + (r & 7) * 16 + (2 * w) * 128;
+            *reinterpret_cast<uint4*>(dst) = expand16(raw[i] & 0xffffu);
+            *reinterpret_cast<uint4*>(dst + 128) = expand16(raw[i] >> 16);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::);   // generic-proxy smem writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::);
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+                const uint64_t da = umma_desc(a_base + ks * 256), db = umma_desc(b_base + ks * 256);
+                const uint32_t accumulate = ks ? 1u : 0u;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+                    "}\n"
+                    :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u));
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar));
+        }
+        fetch(base + kTcN);   // next tile's words: in flight while the tensor core works
+        // ---- wait for the MMAs
+        {
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t"
+                    "}\n"
+                    : "=r"(done) : "r"(bar), "r"(phase));
+            }
+            phase ^= 1;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::);
+        // ---- drain: thread = query row (TMEM lane 32*warp + lane), 32 columns per load
+        const int ib = (int)(index_base + base);
+        const int pa_ = pa;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTcN; c0 += 32) {
+            if (c0 >= cnt) break;
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // g = 2*dot - popc(b) per column; d = pa - g.  Columns past `cnt` hold g = 0 - 0 = 0 from zero rows
+            // and are excluded explicitly in the rare path.
+            int mx = max(max((int)v[0], (int)v[1]), (int)v[2]);
+#pragma unroll
+            for (int j = 3; j + 1 < 32; j += 2) mx = max(max(mx, (int)v[j]), (int)v[j + 1]);
+            mx = max(mx, (int)v[31]);
+            if (mx > pa_ - best.d2) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int col = c0 + j;
+                    const int d = pa_ - (int)v[j];
+                    if (col < cnt && d < best.d2) top2_push(best, d, ib + col);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::);
+        __syncthreads();   // TMEM drained and s_b / s_pb free before the next tile overwrites them
+    }
+    if (q0 + tid < nq) partial[(size_t)blockIdx.y * nq + q0 + tid] = make_int4(best.d1, best.i1, best.d2, best.i2);
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTcN));
+}
+
 __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -304,8 +483,8 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int qper = variant >= 1 ? kMmaQPerCta : kKnnThreads;
-    const int tile = variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile);
+    const int qper = variant == 3 ? kTcM : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
+    const int tile = variant == 3 ? kTcN : (variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile));
     const int per_sm = 2;
     const int qblocks = (nq + qper - 1) / qper;
     // enough map splits to fill the SMs, each at least one tile
@@ -328,6 +507,15 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         }
         knn2_mma_kernel<<<dim3(qblocks, splits), kMmaThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);
+    } else if (variant == 3) {
+        const size_t smem = (size_t)kTcM * 256 + (size_t)kTcN * 256 + 1024;
+        static bool configured3 = false;
+        if (!configured3) {
+            if (cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            configured3 = true;
+        }
+        knn2_tc_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
+                                                                      index_base, partial);
     } else if (variant == 2) {
         knn2_mma_stream_kernel<<<dim3(qblocks, splits), kMmaThreads, 0, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                               index_base, partial);
