@@ -289,19 +289,25 @@ __global__ void __launch_bounds__(kMmaThreads, 2) knn2_mma_stream_kernel(const u
 
 // ---------------------------------------------------------------------------------------------
 // K7c: the same contraction on the 5th-generation tensor cores: tcgen05.mma kind::i8 (M=128 queries x
-// N=256 map descriptors x K=32 per instruction, 8 instructions per tile) with the int32 accumulators in
-// tensor memory (256 columns).  Operands are the {0,1}-expanded descriptors, written by the CTA itself into
-// shared memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices; leading
-// byte offset 128 between the K chunks, stride byte offset 2048 between 8-row groups), so no TMA is needed.
-// One elected thread issues the MMAs and commits them to an mbarrier; all four warps then drain TMEM with
-// tcgen05.ld (warp w owns lanes 32w..32w+31 = query rows, 32 columns per load).  The query operand is signed
-// (+1 for a set bit, -1 for a clear one), the map operand unsigned {0,1}, so the accumulator already is
-// g = 2*popc(a&b) - popc(b) and d = popc(a) - g: a column can only enter a query's top-2 if g > popc(a) - d2,
-// a per-thread scalar, so the drain is one 3-input max tree per 32 columns and a rare detailed scan.  Two
-// CTAs per SM (2 x 256 TMEM columns, 2 x 97 KB smem) overlap one CTA's staging / drain with the other's MMAs.
+// N=256 map descriptors x K=32 per instruction) with the int32 accumulators in tensor memory.  Operands are
+// the expanded descriptors, written by the CTA itself into shared memory in the canonical K-major
+// no-swizzle UMMA layout (8-row x 16-byte core matrices; leading byte offset 128 between the K chunks,
+// stride byte offset 2048 between 8-row groups), so no TMA is needed.
+//   * The query operand is signed (+1 for a set bit, -1 for a clear one), the map operand unsigned {0,1}: the
+//     accumulator already is g = 2*popc(a&b) - popc(b) and d = popc(a) - g.  A column can only enter a
+//     query's top-2 if g > popc(a) - d2, a per-thread scalar, so draining 32 columns costs one tcgen05.ld,
+//     one 3-input max tree and -- rarely -- a detailed scan.
+//   * One CTA = 256 queries (two 128-row A tiles) x one map split.  Each expanded 256-descriptor B tile is
+//     multiplied against both A tiles (two 256-column accumulators = all 512 TMEM columns), halving the
+//     expansion work per comparison.  B is double buffered: while the tensor core works on tile t (one
+//     elected thread issues 16 MMAs and commits them to an mbarrier), all 8 warps expand tile t+1 into the
+//     other buffer from registers that were filled one tile earlier (global latency hidden), then wait on
+//     the mbarrier and drain: warps 0-3 own the rows of accumulator 0, warps 4-7 those of accumulator 1
+//     (a warp may only touch TMEM lanes 32*(warp%4)..+31).
 // ---------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 128;
-constexpr int kTcM = 128;     // queries per CTA
+constexpr int kTcThreads = 256;
+constexpr int kTcM = 128;     // rows of one A tile / one accumulator
+constexpr int kTcQ = 256;     // queries per CTA (two A tiles)
 constexpr int kTcN = 256;     // map descriptors per tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -315,36 +321,35 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 __device__ __forceinline__ uint4 expand16(uint32_t bits16) {
     return make_uint4(expand_nibble(bits16, 0), expand_nibble(bits16, 4), expand_nibble(bits16, 8), expand_nibble(bits16, 12));
 }
-
 // bytes of 0/1 -> bytes of -1/+1 (signed 8 bit)
 __device__ __forceinline__ uint32_t pm1(uint32_t e) { return e | ((e ^ 0x01010101u) * 0xffu); }
 __device__ __forceinline__ uint4 to_pm1(uint4 v) { return make_uint4(pm1(v.x), pm1(v.y), pm1(v.z), pm1(v.w)); }
 
-__global__ void __launch_bounds__(kTcThreads, 2) knn2_tc_kernel(const uint32_t* __restrict__ q, int nq,
+__global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* __restrict__ q, int nq,
                                                                const uint32_t* __restrict__ m, long long nm,
                                                                long long per_split, long long index_base,
                                                                int4* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [128 rows][256 B] UMMA layout (32 KB)
-    unsigned char* s_b = s_a + kTcM * 256;                       // [256 rows][256 B] UMMA layout (64 KB)
+    unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 2 x [128 rows][256 B] (64 KB)
+    unsigned char* s_b = s_a + kTcQ * 256;                                               // 2 x [256 rows][256 B] (128 KB)
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int q0 = blockIdx.x * kTcM;
+    const int q0 = blockIdx.x * kTcQ;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kTcN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
-    // ---- A tile: query row = thread; element (r, c) at (r/8)*2048 + (c/16)*128 + (r%8)*16 + c%16
+    // ---- A tiles: query row = thread (tile tid/128); element (r, c) at (r/8)*2048 + (c/16)*128 + (r%8)*16 + c%16
     int pa = 0;
     {
-        const int r = tid, row = q0 + r;
-        unsigned char* dst = s_a + (r >> 3) * 2048 + (r & 7) * 16;
+        const int r = tid & 127, row = q0 + tid;
+        unsigned char* dst = s_a + (tid >> 7) * (kTcM * 256) + (r >> 3) * 2048 + (r & 7) * 16;
 #pragma unroll
         for (int w = 0; w < 8; w++) {
             const uint32_t bits = row < nq ? q[(size_t)row * 8 + w] : 0u;
@@ -353,6 +358,33 @@ __global__ void __launch_bounds__(kTcThreads, 2) knn2_tc_kernel(const uint32_t* 
             *reinterpret_cast<uint4*>(dst + (2 * w + 1) * 128) = to_pm1(expand16(bits >> 16));
         }
     }
+    const long long lo = (long long)blockIdx.y * per_split;
+    const long long hi = min(nm, lo + per_split);
+    // raw words of a tile: 8 per thread; consecutive threads -> consecutive rows of one 8-row group
+    constexpr int kWordsPerThread = kTcN * 8 / kTcThreads;   // 8
+    uint32_t raw[kWordsPerThread];
+    auto fetch = [&](long long base) {
+        const int cnt = (int)min((long long)kTcN, hi - base);
+#pragma unroll
+        for (int i = 0; i < kWordsPerThread; i++) {
+            const int it = tid + i * kTcThreads;
+            const int r = (it & 7) | ((it >> 6) << 3), w = (it >> 3) & 7;
+            raw[i] = (base < hi && r < cnt) ? m[(size_t)(base + r) * 8 + w] : 0u;
+        }
+    };
+    auto expand_tile = [&](unsigned char* buf) {
+#pragma unroll
+        for (int i = 0; i < kWordsPerThread; i++) {
+            const int it = tid + i * kTcThreads;
+            const int r = (it & 7) | ((it >> 6) << 3), w = (it >> 3) & 7;
+            unsigned char* dst = buf + (r >> 3) * 2048 + (r & 7) * 16 + (2 * w) * 128;
+            *reinterpret_cast<uint4*>(dst) = expand16(raw[i] & 0xffffu);
+            *reinterpret_cast<uint4*>(dst + 128) = expand16(raw[i] >> 16);
+        }
+    };
+    fetch(lo);
+    expand_tile(s_b);                 // tile 0 -> buffer 0
+    fetch(lo + kTcN);                 // tile 1 in registers
     asm volatile("tcgen05.fence::before_thread_sync;" ::);
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::);
@@ -362,54 +394,34 @@ __global__ void __launch_bounds__(kTcThreads, 2) knn2_tc_kernel(const uint32_t* 
     const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b), bar = smem_u32(&s_bar);
 
     Top2 best = {256, -1, 256, -1};
-    const long long lo = (long long)blockIdx.y * per_split;
-    const long long hi = min(nm, lo + per_split);
     uint32_t phase = 0;
-    // raw words of the next tile are fetched into registers one tile ahead (16 per thread), so the global-memory
-    // latency hides behind the MMAs and the drain of the current tile
-    constexpr int kWordsPerThread = kTcN * 8 / kTcThreads;   // 16
-    uint32_t raw[kWordsPerThread];
-    auto fetch = [&](long long base) {
+    int buf = 0;
+    for (long long base = lo; base < hi; base += kTcN, buf ^= 1) {
         const int cnt = (int)min((long long)kTcN, hi - base);
-#pragma unroll
-        for (int i = 0; i < kWordsPerThread; i++) {
-            // consecutive threads -> consecutive rows of one 8-row group (conflict-free 16-byte stores later)
-            const int it = tid + i * kTcThreads;
-            const int r = (it & 7) | ((it >> 6) << 3), w = (it >> 3) & 7;
-            raw[i] = (base < hi && r < cnt) ? m[(size_t)(base + r) * 8 + w] : 0u;
-        }
-    };
-    fetch(lo);
-    for (long long base = lo; base < hi; base += kTcN) {
-        const int cnt = (int)min((long long)kTcN, hi - base);
-        // ---- expand the prefetched B tile into the UMMA layout
-#pragma unroll
-        for (int i = 0; i < kWordsPerThread; i++) {
-            const int it = tid + i * kTcThreads;
-            const int r = (it & 7) | ((it >> 6) << 3), w = (it >> 3) & 7;
-            unsigned char* dst = s_b + (r >> 3) * 2048 + (r & 7) * 16 + (2 * w) * 128;
-            *reinterpret_cast<uint4*>(dst) = expand16(raw[i] & 0xffffu);
-            *reinterpret_cast<uint4*>(dst + 128) = expand16(raw[i] >> 16);
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::);   // generic-proxy smem writes -> visible to the tensor core
-        __syncthreads();
+        __syncthreads();                                      // B[buf] complete, TMEM drained by everybody
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
 #pragma unroll
-            for (int ks = 0; ks < 8; ks++) {
-                const uint64_t da = umma_desc(a_base + ks * 256), db = umma_desc(b_base + ks * 256);
-                const uint32_t accumulate = ks ? 1u : 0u;
-                asm volatile(
-                    "{\n\t"
-                    ".reg .pred p;\n\t"
-                    "setp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-                    "}\n"
-                    :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u));
-            }
+            for (int t = 0; t < 2; t++)
+#pragma unroll
+                for (int ks = 0; ks < 8; ks++) {
+                    const uint64_t da = umma_desc(a_base + t * (kTcM * 256) + ks * 256);
+                    const uint64_t db = umma_desc(b_base + buf * (kTcN * 256) + ks * 256);
+                    const uint32_t accumulate = ks ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+                        "}\n"
+                        :: "r"(tmem + (uint32_t)(t * kTcN)), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u));
+                }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar));
         }
-        fetch(base + kTcN);   // next tile's words: in flight while the tensor core works
+        // ---- while the tensor core works: expand the next tile into the other buffer, fetch the one after
+        if (base + kTcN < hi) expand_tile(s_b + (buf ^ 1) * (kTcN * 256));
+        fetch(base + 2 * kTcN);
         // ---- wait for the MMAs
         {
             uint32_t done = 0;
@@ -425,14 +437,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) knn2_tc_kernel(const uint32_t* 
             phase ^= 1;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::);
-        // ---- drain: thread = query row (TMEM lane 32*warp + lane), 32 columns per load
+        // ---- drain: thread = query row (accumulator tid/128, TMEM lane 32*(warp%4) + lane), 32 columns per load
         const int ib = (int)(index_base + base);
-        const int pa_ = pa;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTcN);
 #pragma unroll 1
         for (int c0 = 0; c0 < kTcN; c0 += 32) {
             if (c0 >= cnt) break;
             uint32_t v[32];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -441,29 +452,28 @@ __global__ void __launch_bounds__(kTcThreads, 2) knn2_tc_kernel(const uint32_t* 
                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
+                : "r"(trow + (uint32_t)c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // g = 2*dot - popc(b) per column; d = pa - g.  Columns past `cnt` hold g = 0 - 0 = 0 from zero rows
-            // and are excluded explicitly in the rare path.
+            // g = 2*dot - popc(b) per column; d = pa - g.  Columns past `cnt` come from zero rows (g = 0) and are
+            // excluded explicitly in the rare path.
             int mx = max(max((int)v[0], (int)v[1]), (int)v[2]);
 #pragma unroll
             for (int j = 3; j + 1 < 32; j += 2) mx = max(max(mx, (int)v[j]), (int)v[j + 1]);
             mx = max(mx, (int)v[31]);
-            if (mx > pa_ - best.d2) {
+            if (mx > pa - best.d2) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const int col = c0 + j;
-                    const int d = pa_ - (int)v[j];
+                    const int d = pa - (int)v[j];
                     if (col < cnt && d < best.d2) top2_push(best, d, ib + col);
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::);
-        __syncthreads();   // TMEM drained and s_b / s_pb free before the next tile overwrites them
     }
     if (q0 + tid < nq) partial[(size_t)blockIdx.y * nq + q0 + tid] = make_int4(best.d1, best.i1, best.d2, best.i2);
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTcN));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
 __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out) {
@@ -483,12 +493,13 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int qper = variant == 3 ? kTcM : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
+    const int qper = variant == 3 ? kTcQ : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
     const int tile = variant == 3 ? kTcN : (variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile));
-    const int per_sm = 2;
+    const int per_sm = variant == 3 ? 1 : 2;
     const int qblocks = (nq + qper - 1) / qper;
     // enough map splits to fill the SMs, each at least one tile
-    int splits = (per_sm * sms + qblocks - 1) / qblocks;
+    // never more CTAs than fit at once (a partial second wave would double the run time)
+    int splits = std::max(1, (per_sm * sms) / qblocks);
     const int64_t max_splits = (nm + tile - 1) / tile;
     if (splits > max_splits) splits = (int)std::max<int64_t>(max_splits, 1);
     int64_t per_split = (nm + splits - 1) / splits;
@@ -508,7 +519,7 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         knn2_mma_kernel<<<dim3(qblocks, splits), kMmaThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);
     } else if (variant == 3) {
-        const size_t smem = (size_t)kTcM * 256 + (size_t)kTcN * 256 + 1024;
+        const size_t smem = (size_t)kTcQ * 256 + 2 * (size_t)kTcN * 256 + 1024;
         static bool configured3 = false;
         if (!configured3) {
             if (cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;

@@ -141,9 +141,12 @@ int orb_hamming256(const void* a, const void* b);
  * (R21/src/ORBmatcher.cc:216-225: strict '<', both start at 256, first index wins ties).
  * queries [nq][32], map [nm][32] host memory.  Outputs per query: best index (+index_base, -1 if
  * nm==0), best distance, second-best distance, and (optional, may be NULL) the index of the second
- * best in (distance, index) lexicographic order.  variant: 0 = LOP3+POPC kernel, 1 = tensor-core
- * AND-popc contraction d = popc(a)+popc(b)-2*popc(a&b) on integer MMAs (same results, ~1.9x faster
- * on B200; profiles/). */
+ * best in (distance, index) lexicographic order.  variant selects the kernel (identical results):
+ *   0  LOP3+POPC, one query per thread (XU/POPC-pipe bound, ~0.5 Tcmp/s on B200)
+ *   1  tensor-core AND-popc contraction d = popc(a)+popc(b)-2*popc(a&b) on mma.sync integer MMAs (~1.0 Tcmp/s)
+ *   2  same, streaming the map without shared memory (~0.8 Tcmp/s; kept as evidence)
+ *   3  the contraction on tcgen05.mma kind::i8 with TMEM accumulators (~2.4 Tcmp/s; the default of the
+ *      Python/C++ host layers).  See DESIGN.md section 4 and profiles/. */
 int orbm_knn2(const uint8_t* queries, int nq, const uint8_t* map, int64_t nm, int64_t index_base,
               int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int32_t* second_idx,
               int variant, int device);
