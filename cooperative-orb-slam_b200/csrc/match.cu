@@ -289,26 +289,31 @@ __global__ void __launch_bounds__(kMmaThreads, 2) knn2_mma_stream_kernel(const u
 
 // ---------------------------------------------------------------------------------------------
 // K7c: the same contraction on the 5th-generation tensor cores: tcgen05.mma kind::i8 (M=128 queries x
-// N=256 map descriptors x K=32 per instruction) with the int32 accumulators in tensor memory.  Operands are
+// N=128 map descriptors x K=32 per instruction) with the int32 accumulators in tensor memory.  Operands are
 // the expanded descriptors, written by the CTA itself into shared memory in the canonical K-major
 // no-swizzle UMMA layout (8-row x 16-byte core matrices; leading byte offset 128 between the K chunks,
 // stride byte offset 2048 between 8-row groups), so no TMA is needed.
 //   * The query operand is signed (+1 for a set bit, -1 for a clear one), the map operand unsigned {0,1}: the
 //     accumulator already is g = 2*popc(a&b) - popc(b) and d = popc(a) - g.  A column can only enter a
 //     query's top-2 if g > popc(a) - d2, a per-thread scalar, so draining 32 columns costs one tcgen05.ld,
-//     one 3-input max tree and -- rarely -- a detailed scan.
-//   * One CTA = 256 queries (two 128-row A tiles) x one map split.  Each expanded 256-descriptor B tile is
-//     multiplied against both A tiles (two 256-column accumulators = all 512 TMEM columns), halving the
-//     expansion work per comparison.  B is double buffered: while the tensor core works on tile t (one
-//     elected thread issues 16 MMAs and commits them to an mbarrier), all 8 warps expand tile t+1 into the
-//     other buffer from registers that were filled one tile earlier (global latency hidden), then wait on
-//     the mbarrier and drain: warps 0-3 own the rows of accumulator 0, warps 4-7 those of accumulator 1
-//     (a warp may only touch TMEM lanes 32*(warp%4)..+31).
+//     one 3-input max tree and -- rarely -- a detailed scan of the 8-column groups that beat the bound.
+//   * The contraction index may be permuted freely as long as both operands agree, so bit b of a 32-bit
+//     word goes to byte (b%8)*4 + b/8 of its 32-byte run: four bytes per shift+mask.
+//   * One CTA = 256 queries (two 128-row A tiles) x one map split, warp specialised: 16 worker warps and
+//     one MMA warp coupled only through mbarriers (no CTA-wide barrier in the loop).  A stage = one
+//     expanded 128-descriptor B tile in shared memory + two 128-column accumulators in TMEM; two stages.
+//     Workers: expand tile i into stage i%2 (raw words were loaded one tile earlier) -> arrive full[i%2];
+//     prefetch the raw words of tile i+1; wait done[(i-1)%2]; drain tile i-1 -> arrive empty[(i-1)%2].
+//     MMA warp: wait full[st] and empty[st]; one elected lane issues the 16 MMAs and commits to done[st].
+//     The tensor pipe runs tile i while the workers drain tile i-1 and expand tile i+1.
+//   * A warp may only touch TMEM lanes 32*(warp%4)..+31: worker w owns query rows 128*((w/4)%2) +
+//     32*(w%4) + lane and the column half w/8 of every tile; the two halves are merged at the end.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 256;
+constexpr int kTcWorkers = 16;                       // worker warps
+constexpr int kTcThreads = (kTcWorkers + 1) * 32;    // + the MMA warp
 constexpr int kTcM = 128;     // rows of one A tile / one accumulator
 constexpr int kTcQ = 256;     // queries per CTA (two A tiles)
-constexpr int kTcN = 256;     // map descriptors per tile
+constexpr int kTcN = 128;     // map descriptors per tile (2 stages x 2 A tiles x 128 = 512 TMEM columns)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -317,13 +322,55 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46);
 }
 
-// 16 bits -> 16 bytes of 0/1 stored as one 16-byte chunk
-__device__ __forceinline__ uint4 expand16(uint32_t bits16) {
-    return make_uint4(expand_nibble(bits16, 0), expand_nibble(bits16, 4), expand_nibble(bits16, 8), expand_nibble(bits16, 12));
-}
 // bytes of 0/1 -> bytes of -1/+1 (signed 8 bit)
 __device__ __forceinline__ uint32_t pm1(uint32_t e) { return e | ((e ^ 0x01010101u) * 0xffu); }
-__device__ __forceinline__ uint4 to_pm1(uint4 v) { return make_uint4(pm1(v.x), pm1(v.y), pm1(v.z), pm1(v.w)); }
+
+// 32 bits -> 32 bytes of 0/1 (two 16-byte K chunks); byte 4*j + k holds bit 8*k + j
+__device__ __forceinline__ void expand32(uint32_t x, uint4& c0, uint4& c1) {
+    c0 = make_uint4(x & 0x01010101u, (x >> 1) & 0x01010101u, (x >> 2) & 0x01010101u, (x >> 3) & 0x01010101u);
+    c1 = make_uint4((x >> 4) & 0x01010101u, (x >> 5) & 0x01010101u, (x >> 6) & 0x01010101u, (x >> 7) & 0x01010101u);
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+// drain 32 accumulator columns of one query row: v[j] = g of column col0 + j
+__device__ __forceinline__ void tc_drain32(const uint32_t (&v)[32], int pa, int idx0, int valid, Top2& best) {
+    int s[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        int m = __vimax3_s32((int)v[8 * g], (int)v[8 * g + 1], (int)v[8 * g + 2]);
+        m = __vimax3_s32(m, (int)v[8 * g + 3], (int)v[8 * g + 4]);
+        m = __vimax3_s32(m, (int)v[8 * g + 5], (int)v[8 * g + 6]);
+        s[g] = max(m, (int)v[8 * g + 7]);
+    }
+    const int mx = max(__vimax3_s32(s[0], s[1], s[2]), s[3]);
+    if (mx > pa - best.d2) {
+        // columns past `valid` come from zero rows (g = 0) and are excluded here
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            if (s[g] > pa - best.d2) {
+#pragma unroll
+                for (int j = 8 * g; j < 8 * g + 8; j++) {
+                    const int d = pa - (int)v[j];
+                    if (j < valid && d < best.d2) top2_push(best, d, idx0 + j);
+                }
+            }
+    }
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* __restrict__ q, int nq,
                                                                const uint32_t* __restrict__ m, long long nm,
@@ -331,149 +378,181 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
                                                                int4* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 2 x [128 rows][256 B] (64 KB)
-    unsigned char* s_b = s_a + kTcQ * 256;                                               // 2 x [256 rows][256 B] (128 KB)
-    __shared__ __align__(8) unsigned long long s_bar;
+    unsigned char* s_b = s_a + kTcQ * 256;                                               // 2 stages x [kTcN rows][256 B]
+    __shared__ __align__(8) unsigned long long s_full[2], s_done[2], s_empty[2];
     __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * kTcQ;
+    constexpr int kWorkThreads = kTcWorkers * 32;
 
-    if (warp == 0) {
+    if (warp == kTcWorkers) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)));
+#pragma unroll
+        for (int st = 0; st < 2; st++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[st])), "r"(kTcWorkers));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_done[st])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_empty[st])), "r"(kTcWorkers));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
-    // ---- A tiles: query row = thread (tile tid/128); element (r, c) at (r/8)*2048 + (c/16)*128 + (r%8)*16 + c%16
-    int pa = 0;
-    {
-        const int r = tid & 127, row = q0 + tid;
-        unsigned char* dst = s_a + (tid >> 7) * (kTcM * 256) + (r >> 3) * 2048 + (r & 7) * 16;
-#pragma unroll
-        for (int w = 0; w < 8; w++) {
-            const uint32_t bits = row < nq ? q[(size_t)row * 8 + w] : 0u;
-            pa += __popc(bits);
-            *reinterpret_cast<uint4*>(dst + (2 * w) * 128) = to_pm1(expand16(bits & 0xffffu));
-            *reinterpret_cast<uint4*>(dst + (2 * w + 1) * 128) = to_pm1(expand16(bits >> 16));
-        }
+    // ---- A tiles (+1 / -1): element (r, c) of a tile at (r/8)*2048 + (c/16)*128 + (r%8)*16 + c%16
+    for (int it = tid; it < kTcQ * 8; it += kTcThreads) {
+        const int row = it >> 3, w = it & 7, r = row & 127;
+        const uint32_t bits = q0 + row < nq ? q[(size_t)(q0 + row) * 8 + w] : 0u;
+        uint4 c0, c1;
+        expand32(bits, c0, c1);
+        unsigned char* dst = s_a + (row >> 7) * (kTcM * 256) + (r >> 3) * 2048 + (r & 7) * 16 + (2 * w) * 128;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pm1(c0.x), pm1(c0.y), pm1(c0.z), pm1(c0.w));
+        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(pm1(c1.x), pm1(c1.y), pm1(c1.z), pm1(c1.w));
     }
     const long long lo = (long long)blockIdx.y * per_split;
     const long long hi = min(nm, lo + per_split);
-    // raw words of a tile: 8 per thread; consecutive threads -> consecutive rows of one 8-row group
-    constexpr int kWordsPerThread = kTcN * 8 / kTcThreads;   // 8
-    uint32_t raw[kWordsPerThread];
-    auto fetch = [&](long long base) {
-        const int cnt = (int)min((long long)kTcN, hi - base);
-#pragma unroll
-        for (int i = 0; i < kWordsPerThread; i++) {
-            const int it = tid + i * kTcThreads;
-            const int r = (it & 7) | ((it >> 6) << 3), w = (it >> 3) & 7;
-            raw[i] = (base < hi && r < cnt) ? m[(size_t)(base + r) * 8 + w] : 0u;
-        }
-    };
-    auto expand_tile = [&](unsigned char* buf) {
-#pragma unroll
-        for (int i = 0; i < kWordsPerThread; i++) {
-            const int it = tid + i * kTcThreads;
-            const int r = (it & 7) | ((it >> 6) << 3), w = (it >> 3) & 7;
-            unsigned char* dst = buf + (r >> 3) * 2048 + (r & 7) * 16 + (2 * w) * 128;
-            *reinterpret_cast<uint4*>(dst) = expand16(raw[i] & 0xffffu);
-            *reinterpret_cast<uint4*>(dst + 128) = expand16(raw[i] >> 16);
-        }
-    };
-    fetch(lo);
-    expand_tile(s_b);                 // tile 0 -> buffer 0
-    fetch(lo + kTcN);                 // tile 1 in registers
+    const int ntiles = hi > lo ? (int)((hi - lo + kTcN - 1) / kTcN) : 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::);
     asm volatile("tcgen05.fence::before_thread_sync;" ::);
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::);
     const uint32_t tmem = s_tmem;
-    // instruction descriptor: D = s32, A = signed 8 bit, B = unsigned 8 bit, both K-major, N = 256, M = 128
-    const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-    const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b), bar = smem_u32(&s_bar);
+    const uint32_t full0 = smem_u32(&s_full[0]), done0 = smem_u32(&s_done[0]), empty0 = smem_u32(&s_empty[0]);
 
     Top2 best = {256, -1, 256, -1};
-    uint32_t phase = 0;
-    int buf = 0;
-    for (long long base = lo; base < hi; base += kTcN, buf ^= 1) {
-        const int cnt = (int)min((long long)kTcN, hi - base);
-        asm volatile("fence.proxy.async.shared::cta;" ::);   // generic-proxy smem writes -> visible to the tensor core
-        __syncthreads();                                      // B[buf] complete, TMEM drained by everybody
-        if (tid == 0) {
+    if (warp == kTcWorkers) {
+        // =========================== MMA warp ===========================
+        // instruction descriptor: D = s32, A = signed 8 bit, B = unsigned 8 bit, both K-major, N = kTcN, M = 128
+        const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+        const uint64_t a_desc = umma_desc(smem_u32(s_a)), b_desc = umma_desc(smem_u32(s_b));
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
+        for (int i = 0; i < ntiles; i++) {
+            const int st = i & 1;
+            const uint32_t ph = (uint32_t)((i >> 1) & 1);
+            mbar_wait(full0 + 8 * st, ph);          // B tile i expanded by all workers
+            mbar_wait(empty0 + 8 * st, ph ^ 1u);    // accumulators of tile i-2 drained (passes at once for i < 2)
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
+            if (leader) {
 #pragma unroll
-            for (int t = 0; t < 2; t++)
+                for (int t = 0; t < 2; t++)
 #pragma unroll
-                for (int ks = 0; ks < 8; ks++) {
-                    const uint64_t da = umma_desc(a_base + t * (kTcM * 256) + ks * 256);
-                    const uint64_t db = umma_desc(b_base + buf * (kTcN * 256) + ks * 256);
-                    const uint32_t accumulate = ks ? 1u : 0u;
+                    for (int ks = 0; ks < 8; ks++) {
+                        // descriptors address in 16-byte units: A tile t at +t*32 KB, K step at +256 B, stage at +kTcN*256 B
+                        const uint64_t da = a_desc + (uint64_t)((t * (kTcM * 256) + ks * 256) >> 4);
+                        const uint64_t db = b_desc + (uint64_t)((st * (kTcN * 256) + ks * 256) >> 4);
+                        const uint32_t accumulate = ks ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+                            "}\n"
+                            :: "r"(tmem + (uint32_t)((2 * st + t) * kTcN)), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u));
+                    }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(done0 + 8 * st));
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================== worker warps ===========================
+        // my query row (TMEM lane) and column half
+        const int row = ((warp >> 2) & 1) * kTcM + (warp & 3) * 32 + lane;
+        const int chalf = warp >> 3;
+        constexpr int kColsPerWarp = kTcN / (kTcWorkers / 8);
+        int pa = 0;
+        if (q0 + row < nq) {
+            const uint4 x = *reinterpret_cast<const uint4*>(q + (size_t)(q0 + row) * 8);
+            const uint4 y = *reinterpret_cast<const uint4*>(q + (size_t)(q0 + row) * 8 + 4);
+            pa = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w) + __popc(y.x) + __popc(y.y) + __popc(y.z) + __popc(y.w);
+        }
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) & 1) * kTcN + chalf * kColsPerWarp);
+        // raw words of a tile: thread t takes word w of rows r0 + 64*i (consecutive threads: the 8 rows of a group, then w)
+        constexpr int kWordsPerThread = kTcN * 8 / kWorkThreads;   // 2
+        constexpr int kRowStep = kWorkThreads / 8;                  // 64
+        const int r0 = (tid & 7) | ((tid >> 6) << 3), w0 = (tid >> 3) & 7;
+        const uint32_t* src = m + ((size_t)lo + r0) * 8 + w0;
+        const uint32_t b_off = (uint32_t)((r0 >> 3) * 2048 + (r0 & 7) * 16 + (2 * w0) * 128);
+        uint32_t raw[kWordsPerThread];
+        auto fetch = [&](int tile) {
+            const long long base = lo + (long long)tile * kTcN;
+            if (base + kTcN <= hi) {
+#pragma unroll
+                for (int i = 0; i < kWordsPerThread; i++) raw[i] = __ldg(src + (size_t)tile * (kTcN * 8) + i * (kRowStep * 8));
+            } else {
+#pragma unroll
+                for (int i = 0; i < kWordsPerThread; i++)
+                    raw[i] = base + r0 + i * kRowStep < hi ? __ldg(src + (size_t)tile * (kTcN * 8) + i * (kRowStep * 8)) : 0u;
+            }
+        };
+        auto drain = [&](int tile) {
+            const int st = tile & 1;
+            mbar_wait(done0 + 8 * st, (uint32_t)((tile >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::);
+            const long long base = lo + (long long)tile * kTcN;
+            const int cnt = (int)min((long long)kTcN, hi - base) - chalf * kColsPerWarp;   // valid columns of my half
+            const int ib = (int)(index_base + base) + chalf * kColsPerWarp;
+#pragma unroll
+            for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
+                if (c0 < cnt) {      // warp-uniform
+                    uint32_t v[32];
                     asm volatile(
-                        "{\n\t"
-                        ".reg .pred p;\n\t"
-                        "setp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-                        "}\n"
-                        :: "r"(tmem + (uint32_t)(t * kTcN)), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u));
-                }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar));
-        }
-        // ---- while the tensor core works: expand the next tile into the other buffer, fetch the one after
-        if (base + kTcN < hi) expand_tile(s_b + (buf ^ 1) * (kTcN * 256));
-        fetch(base + 2 * kTcN);
-        // ---- wait for the MMAs
-        {
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t"
-                    ".reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t"
-                    "}\n"
-                    : "=r"(done) : "r"(bar), "r"(phase));
-            }
-            phase ^= 1;
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::);
-        // ---- drain: thread = query row (accumulator tid/128, TMEM lane 32*(warp%4) + lane), 32 columns per load
-        const int ib = (int)(index_base + base);
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTcN);
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTcN; c0 += 32) {
-            if (c0 >= cnt) break;
-            uint32_t v[32];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(trow + (uint32_t)c0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // g = 2*dot - popc(b) per column; d = pa - g.  Columns past `cnt` come from zero rows (g = 0) and are
-            // excluded explicitly in the rare path.
-            int mx = max(max((int)v[0], (int)v[1]), (int)v[2]);
-#pragma unroll
-            for (int j = 3; j + 1 < 32; j += 2) mx = max(max(mx, (int)v[j]), (int)v[j + 1]);
-            mx = max(mx, (int)v[31]);
-            if (mx > pa - best.d2) {
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int col = c0 + j;
-                    const int d = pa - (int)v[j];
-                    if (col < cnt && d < best.d2) top2_push(best, d, ib + col);
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(trow + (uint32_t)(2 * st * kTcN + c0)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    tc_drain32(v, pa, ib + c0, cnt - c0, best);
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * st);
+        };
+        if (ntiles > 0) fetch(0);
+        for (int i = 0; i < ntiles; i++) {
+            const int st = i & 1;
+            // stage st was last read by the MMAs of tile i-2, whose completion this warp saw before draining it
+            unsigned char* dst = s_b + st * (kTcN * 256) + b_off;
+#pragma unroll
+            for (int k = 0; k < kWordsPerThread; k++) {
+                uint4 c0, c1;
+                expand32(raw[k], c0, c1);
+                *reinterpret_cast<uint4*>(dst + k * (kRowStep / 8) * 2048) = c0;
+                *reinterpret_cast<uint4*>(dst + k * (kRowStep / 8) * 2048 + 128) = c1;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * st);
+            if (i + 1 < ntiles) fetch(i + 1);
+            if (i > 0) drain(i - 1);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::);
+        if (ntiles > 0) drain(ntiles - 1);
     }
-    if (q0 + tid < nq) partial[(size_t)blockIdx.y * nq + q0 + tid] = make_int4(best.d1, best.i1, best.d2, best.i2);
+    // ---- merge the column halves (index ranges interleave: lexicographic merge) and store
+    asm volatile("tcgen05.fence::before_thread_sync;" ::);
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+    int4* s_rec = reinterpret_cast<int4*>(s_b);     // all MMAs retired: the B stages are free
+    if (warp >= 8 && warp < kTcWorkers) {
+        const int row = ((warp >> 2) & 1) * kTcM + (warp & 3) * 32 + lane;
+        s_rec[row] = make_int4(best.d1, best.i1, best.d2, best.i2);
+    }
+    __syncthreads();
+    if (warp < 8) {
+        const int row = ((warp >> 2) & 1) * kTcM + (warp & 3) * 32 + lane;
+        if (kTcWorkers > 8) {
+            const int4 o = s_rec[row];
+            top2_merge(best.d1, best.i1, best.d2, best.i2, o.x, o.y, o.z, o.w);
+        }
+        if (q0 + row < nq) partial[(size_t)blockIdx.y * nq + q0 + row] = make_int4(best.d1, best.i1, best.d2, best.i2);
+    }
+    if (warp == kTcWorkers) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::);
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+    }
 }
 
 __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out) {
