@@ -314,6 +314,8 @@ constexpr int kTcThreads = (kTcWorkers + 1) * 32;    // + the MMA warp
 constexpr int kTcM = 128;     // rows of one A tile / one accumulator
 constexpr int kTcQ = 256;     // queries per CTA (two A tiles)
 constexpr int kTcN = 128;     // map descriptors per tile (2 stages x 2 A tiles x 128 = 512 TMEM columns)
+constexpr int kTcBStages = 4; // expanded B tiles in shared memory (the workers run ahead of the tensor pipe)
+constexpr int kTcLag = 2;     // a worker drains tile i - kTcLag after expanding tile i
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -322,13 +324,24 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46);
 }
 
-// bytes of 0/1 -> bytes of -1/+1 (signed 8 bit)
-__device__ __forceinline__ uint32_t pm1(uint32_t e) { return e | ((e ^ 0x01010101u) * 0xffu); }
-
-// 32 bits -> 32 bytes of 0/1 (two 16-byte K chunks); byte 4*j + k holds bit 8*k + j
-__device__ __forceinline__ void expand32(uint32_t x, uint4& c0, uint4& c1) {
-    c0 = make_uint4(x & 0x01010101u, (x >> 1) & 0x01010101u, (x >> 2) & 0x01010101u, (x >> 3) & 0x01010101u);
-    c1 = make_uint4((x >> 4) & 0x01010101u, (x >> 5) & 0x01010101u, (x >> 6) & 0x01010101u, (x >> 7) & 0x01010101u);
+// Operand encoding.  Bit b = 8*k + j of a 32-bit descriptor word goes to byte 4*j + k of the word's 32-byte run
+// (plane j, byte k).  The map operand keeps the bit where it is: plane j < 7 holds x & (0x01010101 << j), i.e.
+// bytes of 0 or 2^j (one LOP3 each); plane 7 holds (x >> 1) & 0x40404040 (0 or 64).  The query operand carries
+// the compensating weight with the sign of its bit: +-2^(6-j) for j < 7, +-1 for plane 7.  Every product is
+// +-64 or 0, so the accumulator is 64 * (2*popc(a&b) - popc(b)) = 64 * g, |.| <= 16384: it fits 16 bits.
+constexpr int kTcScaleLog2 = 6;
+__device__ __forceinline__ void expand32_map(uint32_t x, uint4& c0, uint4& c1) {
+    c0 = make_uint4(x & 0x01010101u, x & 0x02020202u, x & 0x04040404u, x & 0x08080808u);
+    c1 = make_uint4(x & 0x10101010u, x & 0x20202020u, x & 0x40404040u, (x >> 1) & 0x40404040u);
+}
+__device__ __forceinline__ uint32_t query_plane(uint32_t x, int j) {
+    const uint32_t e = (x >> j) & 0x01010101u;           // bytes of 0/1
+    const uint32_t w = j < 7 ? (1u << (6 - j)) : 1u;     // weight; -w as a byte = 256 - w
+    return e * w | (e ^ 0x01010101u) * (256u - w);
+}
+__device__ __forceinline__ void expand32_query(uint32_t x, uint4& c0, uint4& c1) {
+    c0 = make_uint4(query_plane(x, 0), query_plane(x, 1), query_plane(x, 2), query_plane(x, 3));
+    c1 = make_uint4(query_plane(x, 4), query_plane(x, 5), query_plane(x, 6), query_plane(x, 7));
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -343,32 +356,67 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
+// same, letting the hardware park the thread for up to `ns` before it re-polls (the MMA warp must not eat issue slots)
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-// drain 32 accumulator columns of one query row: v[j] = g of column col0 + j
-__device__ __forceinline__ void tc_drain32(const uint32_t (&v)[32], int pa, int idx0, int valid, Top2& best) {
-    int s[4];
+// drain 64 accumulator columns of one query row, loaded as packed int16 pairs: v[r] = columns 2r (low half) and
+// 2r + 1 (high half), each 64 * g.  Columns >= valid come from zero rows and are skipped.
+template <bool FULL>
+__device__ __forceinline__ void tc_drain64(const uint32_t (&v)[32], int pa, int idx0, int valid, Top2& best) {
+    uint32_t s[8];
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
-        int m = __vimax3_s32((int)v[8 * g], (int)v[8 * g + 1], (int)v[8 * g + 2]);
-        m = __vimax3_s32(m, (int)v[8 * g + 3], (int)v[8 * g + 4]);
-        m = __vimax3_s32(m, (int)v[8 * g + 5], (int)v[8 * g + 6]);
-        s[g] = max(m, (int)v[8 * g + 7]);
-    }
-    const int mx = max(__vimax3_s32(s[0], s[1], s[2]), s[3]);
-    if (mx > pa - best.d2) {
-        // columns past `valid` come from zero rows (g = 0) and are excluded here
+    for (int g = 0; g < 8; g++) s[g] = __vmaxs2(__vimax3_s16x2(v[4 * g], v[4 * g + 1], v[4 * g + 2]), v[4 * g + 3]);
+    uint32_t mx = __vimax3_s16x2(s[0], s[1], s[2]);
+    mx = __vimax3_s16x2(mx, s[3], s[4]);
+    mx = __vimax3_s16x2(mx, s[5], s[6]);
+    mx = __vmaxs2(mx, s[7]);
+    // a column enters the top-2 iff g > pa - d2; in the packed domain: max(x, bound) != bound for some half
+    int bound = (pa - best.d2) << kTcScaleLog2;
+    uint32_t bound2 = __byte_perm((uint32_t)bound, 0u, 0x1010);
+    if (__vmaxs2(mx, bound2) != bound2) {
 #pragma unroll
-        for (int g = 0; g < 4; g++)
-            if (s[g] > pa - best.d2) {
+        for (int g = 0; g < 8; g++) {
+            if (__vmaxs2(s[g], bound2) != bound2) {
+                // visit the 8 columns of this group by (g descending, column ascending) through packed keys
+                // key = 8 * g_value + (7 - column): a later column never displaces an equal earlier one, so
+                // the visit order keeps the first-index rule
+                int key[8];
 #pragma unroll
-                for (int j = 8 * g; j < 8 * g + 8; j++) {
-                    const int d = pa - (int)v[j];
-                    if (j < valid && d < best.d2) top2_push(best, d, idx0 + j);
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t x = v[4 * g + r];
+                    const int lo = ((int)(x << 16) >> (16 + kTcScaleLog2 - 3)) | (7 - 2 * r);
+                    const int hi = ((int)x >> (16 + kTcScaleLog2 - 3)) | (6 - 2 * r);
+                    key[2 * r] = FULL || 8 * g + 2 * r < valid ? lo : (int)0x80000000;
+                    key[2 * r + 1] = FULL || 8 * g + 2 * r + 1 < valid ? hi : (int)0x80000000;
                 }
+                // the largest key certainly beats the bound when FULL (that is why we are here)
+                int k = max(__vimax3_s32(key[0], key[1], key[2]), __vimax3_s32(key[3], key[4], key[5]));
+                k = __vimax3_s32(k, key[6], key[7]);
+                while ((k >> 3) > pa - best.d2) {
+                    top2_push(best, pa - (k >> 3), idx0 + 8 * g + 7 - (k & 7));
+                    const int last = k;
+                    k = (int)0x80000000;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) k = max(k, key[j] < last ? key[j] : (int)0x80000000);
+                }
+                bound = (pa - best.d2) << kTcScaleLog2;
+                bound2 = __byte_perm((uint32_t)bound, 0u, 0x1010);
             }
+        }
     }
 }
 
@@ -379,7 +427,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 2 x [128 rows][256 B] (64 KB)
     unsigned char* s_b = s_a + kTcQ * 256;                                               // 2 stages x [kTcN rows][256 B]
-    __shared__ __align__(8) unsigned long long s_full[2], s_done[2], s_empty[2];
+    __shared__ __align__(8) unsigned long long s_full[kTcBStages], s_done[2], s_empty[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * kTcQ;
@@ -391,8 +439,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
     }
     if (tid == 0) {
 #pragma unroll
+        for (int sb = 0; sb < kTcBStages; sb++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[sb])), "r"(kTcWorkers));
+#pragma unroll
         for (int st = 0; st < 2; st++) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[st])), "r"(kTcWorkers));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_done[st])), "r"(1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_empty[st])), "r"(kTcWorkers));
         }
@@ -403,10 +453,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
         const int row = it >> 3, w = it & 7, r = row & 127;
         const uint32_t bits = q0 + row < nq ? q[(size_t)(q0 + row) * 8 + w] : 0u;
         uint4 c0, c1;
-        expand32(bits, c0, c1);
+        expand32_query(bits, c0, c1);
         unsigned char* dst = s_a + (row >> 7) * (kTcM * 256) + (r >> 3) * 2048 + (r & 7) * 16 + (2 * w) * 128;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pm1(c0.x), pm1(c0.y), pm1(c0.z), pm1(c0.w));
-        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(pm1(c1.x), pm1(c1.y), pm1(c1.z), pm1(c1.w));
+        *reinterpret_cast<uint4*>(dst) = c0;
+        *reinterpret_cast<uint4*>(dst + 128) = c1;
     }
     const long long lo = (long long)blockIdx.y * per_split;
     const long long hi = min(nm, lo + per_split);
@@ -427,10 +477,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
         for (int i = 0; i < ntiles; i++) {
-            const int st = i & 1;
-            const uint32_t ph = (uint32_t)((i >> 1) & 1);
-            mbar_wait(full0 + 8 * st, ph);          // B tile i expanded by all workers
-            mbar_wait(empty0 + 8 * st, ph ^ 1u);    // accumulators of tile i-2 drained (passes at once for i < 2)
+            const int st = i & 1, sb = i & (kTcBStages - 1);
+            mbar_wait_parked(full0 + 8 * sb, (uint32_t)((i / kTcBStages) & 1), 4000);   // B tile i expanded by all workers
+            mbar_wait_parked(empty0 + 8 * st, (uint32_t)(((i >> 1) & 1) ^ 1), 4000);    // accumulators of tile i-2 drained (passes at once for i < 2)
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
             if (leader) {
 #pragma unroll
@@ -439,7 +488,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
                     for (int ks = 0; ks < 8; ks++) {
                         // descriptors address in 16-byte units: A tile t at +t*32 KB, K step at +256 B, stage at +kTcN*256 B
                         const uint64_t da = a_desc + (uint64_t)((t * (kTcM * 256) + ks * 256) >> 4);
-                        const uint64_t db = b_desc + (uint64_t)((st * (kTcN * 256) + ks * 256) >> 4);
+                        const uint64_t db = b_desc + (uint64_t)((sb * (kTcN * 256) + ks * 256) >> 4);
                         const uint32_t accumulate = ks ? 1u : 0u;
                         asm volatile(
                             "{\n\t"
@@ -473,64 +522,84 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
         const uint32_t* src = m + ((size_t)lo + r0) * 8 + w0;
         const uint32_t b_off = (uint32_t)((r0 >> 3) * 2048 + (r0 & 7) * 16 + (2 * w0) * 128);
         uint32_t raw[kWordsPerThread];
-        auto fetch = [&](int tile) {
-            const long long base = lo + (long long)tile * kTcN;
-            if (base + kTcN <= hi) {
+        const int ib0 = (int)(index_base + lo) + chalf * kColsPerWarp;
+        const int n_full = (int)((hi - lo) / kTcN);                 // tiles whose kTcN rows all exist
+        const int last_cnt = (int)(hi - lo) - n_full * kTcN;        // rows of the ragged last tile
+        auto fetch = [&](int tile) {      // called with tile = 0, 1, 2, ...
+            if (tile < n_full) {
 #pragma unroll
-                for (int i = 0; i < kWordsPerThread; i++) raw[i] = __ldg(src + (size_t)tile * (kTcN * 8) + i * (kRowStep * 8));
+                for (int i = 0; i < kWordsPerThread; i++) raw[i] = __ldg(src + i * (kRowStep * 8));
             } else {
 #pragma unroll
-                for (int i = 0; i < kWordsPerThread; i++)
-                    raw[i] = base + r0 + i * kRowStep < hi ? __ldg(src + (size_t)tile * (kTcN * 8) + i * (kRowStep * 8)) : 0u;
+                for (int i = 0; i < kWordsPerThread; i++) raw[i] = r0 + i * kRowStep < last_cnt ? __ldg(src + i * (kRowStep * 8)) : 0u;
             }
+            src += kTcN * 8;
         };
-        auto drain = [&](int tile) {
+        static_assert(kColsPerWarp == 64, "one packed 32-register load covers the warp's 64 columns");
+        // drain, part 1: wait for the tile's MMAs and start the TMEM load (64 columns as int16 pairs)
+        auto drain_load = [&](int tile, uint32_t (&v)[32]) {
             const int st = tile & 1;
             mbar_wait(done0 + 8 * st, (uint32_t)((tile >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
-            const long long base = lo + (long long)tile * kTcN;
-            const int cnt = (int)min((long long)kTcN, hi - base) - chalf * kColsPerWarp;   // valid columns of my half
-            const int ib = (int)(index_base + base) + chalf * kColsPerWarp;
-#pragma unroll
-            for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
-                if (c0 < cnt) {      // warp-uniform
-                    uint32_t v[32];
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(trow + (uint32_t)(2 * st * kTcN + c0)));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    tc_drain32(v, pa, ib + c0, cnt - c0, best);
-                }
+            const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;   // valid columns of my half
+            if (cnt > 0) {      // warp-uniform
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(trow + (uint32_t)(2 * st * kTcN)));
             }
+        };
+        // drain, part 2: the load has landed; update the top-2 and hand the accumulators back
+        auto drain_finish = [&](int tile, uint32_t (&v)[32]) {
+            const int st = tile & 1;
+            const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;
+            const int ib = ib0 + tile * kTcN;
+            if (cnt > 0) {
+                // the wait makes the registers of the load above valid: tie them to it for the compiler
+                asm volatile("tcgen05.wait::ld.sync.aligned;"
+                    : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                      "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                      "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                    :: "memory");
+            }
+            // the accumulators are in registers: hand the TMEM stage back before looking at them
             asm volatile("tcgen05.fence::before_thread_sync;" ::);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * st);
+            if (cnt >= kColsPerWarp) tc_drain64<true>(v, pa, ib, kColsPerWarp, best);
+            else if (cnt > 0) tc_drain64<false>(v, pa, ib, cnt, best);
         };
         if (ntiles > 0) fetch(0);
         for (int i = 0; i < ntiles; i++) {
-            const int st = i & 1;
-            // stage st was last read by the MMAs of tile i-2, whose completion this warp saw before draining it
-            unsigned char* dst = s_b + st * (kTcN * 256) + b_off;
+            const int sb = i & (kTcBStages - 1);
+            uint32_t v[32];
+            if (i >= kTcLag) drain_load(i - kTcLag, v);      // TMEM latency hides behind the expansion below
+            // buffer sb was last read by the MMAs of tile i - kTcBStages, whose completion this warp saw before draining it
+            unsigned char* dst = s_b + sb * (kTcN * 256) + b_off;
 #pragma unroll
             for (int k = 0; k < kWordsPerThread; k++) {
                 uint4 c0, c1;
-                expand32(raw[k], c0, c1);
+                expand32_map(raw[k], c0, c1);
                 *reinterpret_cast<uint4*>(dst + k * (kRowStep / 8) * 2048) = c0;
                 *reinterpret_cast<uint4*>(dst + k * (kRowStep / 8) * 2048 + 128) = c1;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * st);
+            if (lane == 0) mbar_arrive(full0 + 8 * sb);
             if (i + 1 < ntiles) fetch(i + 1);
-            if (i > 0) drain(i - 1);
+            if (i >= kTcLag) drain_finish(i - kTcLag, v);
         }
-        if (ntiles > 0) drain(ntiles - 1);
+        for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
+            uint32_t v[32];
+            drain_load(t, v);
+            drain_finish(t, v);
+        }
     }
     // ---- merge the column halves (index ranges interleave: lexicographic merge) and store
     asm volatile("tcgen05.fence::before_thread_sync;" ::);
@@ -598,7 +667,7 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         knn2_mma_kernel<<<dim3(qblocks, splits), kMmaThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);
     } else if (variant == 3) {
-        const size_t smem = (size_t)kTcQ * 256 + 2 * (size_t)kTcN * 256 + 1024;
+        const size_t smem = (size_t)kTcQ * 256 + kTcBStages * (size_t)kTcN * 256 + 1024;
         static bool configured3 = false;
         if (!configured3) {
             if (cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
