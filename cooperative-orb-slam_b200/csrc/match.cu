@@ -315,7 +315,7 @@ constexpr int kTcM = 128;     // rows of one A tile / one accumulator
 constexpr int kTcQ = 256;     // queries per CTA (two A tiles)
 constexpr int kTcN = 128;     // map descriptors per tile (2 stages x 2 A tiles x 128 = 512 TMEM columns)
 constexpr int kTcBStages = 4; // expanded B tiles in shared memory (the workers run ahead of the tensor pipe)
-constexpr int kTcLag = 2;     // a worker drains tile i - kTcLag after expanding tile i
+constexpr int kTcLag = 3;     // a worker drains tile i - kTcLag after expanding tile i (< kTcBStages: see the worker loop)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -356,17 +356,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
-// same, letting the hardware park the thread for up to `ns` before it re-polls (the MMA warp must not eat issue slots)
+// same with a back-off between polls: the MMA warp shares its scheduler with four worker warps and must not eat
+// their issue slots while it waits
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
-    uint32_t done = 0;
-    while (!done) {
+    while (true) {
+        uint32_t done;
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}\n"
-            : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -376,7 +379,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // drain 64 accumulator columns of one query row, loaded as packed int16 pairs: v[r] = columns 2r (low half) and
 // 2r + 1 (high half), each 64 * g.  Columns >= valid come from zero rows and are skipped.
 template <bool FULL>
-__device__ __forceinline__ void tc_drain64(const uint32_t (&v)[32], int pa, int idx0, int valid, Top2& best) {
+__device__ __forceinline__ void tc_drain64(const uint32_t (&v)[32], int pa, int idx0, int valid, int glim, int* gptr, Top2& best) {
     uint32_t s[8];
 #pragma unroll
     for (int g = 0; g < 8; g++) s[g] = __vmaxs2(__vimax3_s16x2(v[4 * g], v[4 * g + 1], v[4 * g + 2]), v[4 * g + 3]);
@@ -384,8 +387,13 @@ __device__ __forceinline__ void tc_drain64(const uint32_t (&v)[32], int pa, int 
     mx = __vimax3_s16x2(mx, s[3], s[4]);
     mx = __vimax3_s16x2(mx, s[5], s[6]);
     mx = __vmaxs2(mx, s[7]);
-    // a column enters the top-2 iff g > pa - d2; in the packed domain: max(x, bound) != bound for some half
-    int bound = (pa - best.d2) << kTcScaleLog2;
+    // a column enters this CTA's top-2 iff g > pa - d2, and it can only matter for the merged result if its distance
+    // does not exceed the smallest second-best any CTA has published for this query (g > glim = pa - G - 1: two real
+    // columns are at distance <= G, so nothing farther than G survives the merge; ties are kept).  In the packed
+    // domain the test is max(x, bound) != bound for some half.
+    const int d2_in = best.d2;
+    int lim = max(pa - best.d2, glim);
+    int bound = lim << kTcScaleLog2;
     uint32_t bound2 = __byte_perm((uint32_t)bound, 0u, 0x1010);
     if (__vmaxs2(mx, bound2) != bound2) {
 #pragma unroll
@@ -406,24 +414,26 @@ __device__ __forceinline__ void tc_drain64(const uint32_t (&v)[32], int pa, int 
                 // the largest key certainly beats the bound when FULL (that is why we are here)
                 int k = max(__vimax3_s32(key[0], key[1], key[2]), __vimax3_s32(key[3], key[4], key[5]));
                 k = __vimax3_s32(k, key[6], key[7]);
-                while ((k >> 3) > pa - best.d2) {
+                while ((k >> 3) > lim) {
                     top2_push(best, pa - (k >> 3), idx0 + 8 * g + 7 - (k & 7));
+                    lim = max(pa - best.d2, glim);
                     const int last = k;
                     k = (int)0x80000000;
 #pragma unroll
                     for (int j = 0; j < 8; j++) k = max(k, key[j] < last ? key[j] : (int)0x80000000);
                 }
-                bound = (pa - best.d2) << kTcScaleLog2;
+                bound = lim << kTcScaleLog2;
                 bound2 = __byte_perm((uint32_t)bound, 0u, 0x1010);
             }
         }
+        if (best.d2 < d2_in) atomicMin(gptr, best.d2);
     }
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* __restrict__ q, int nq,
                                                                const uint32_t* __restrict__ m, long long nm,
                                                                long long per_split, long long index_base,
-                                                               int4* __restrict__ partial) {
+                                                               int4* __restrict__ partial, int* __restrict__ shared_d2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 2 x [128 rows][256 B] (64 KB)
     unsigned char* s_b = s_a + kTcQ * 256;                                               // 2 stages x [kTcN rows][256 B]
@@ -466,20 +476,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::);
     const uint32_t tmem = s_tmem;
-    const uint32_t full0 = smem_u32(&s_full[0]), done0 = smem_u32(&s_done[0]), empty0 = smem_u32(&s_empty[0]);
+    // shared-window addresses pinned in registers (otherwise they are re-derived from the CTA id at every use)
+    uint32_t full0 = smem_u32(&s_full[0]), done0 = smem_u32(&s_done[0]), empty0 = smem_u32(&s_empty[0]), b0 = smem_u32(s_b);
+    asm volatile("" : "+r"(full0), "+r"(done0), "+r"(empty0), "+r"(b0));
 
     Top2 best = {256, -1, 256, -1};
     if (warp == kTcWorkers) {
         // =========================== MMA warp ===========================
         // instruction descriptor: D = s32, A = signed 8 bit, B = unsigned 8 bit, both K-major, N = kTcN, M = 128
         const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-        const uint64_t a_desc = umma_desc(smem_u32(s_a)), b_desc = umma_desc(smem_u32(s_b));
+        const uint64_t a_desc = umma_desc(smem_u32(s_a)), b_desc = umma_desc(b0);
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
         for (int i = 0; i < ntiles; i++) {
             const int st = i & 1, sb = i & (kTcBStages - 1);
-            mbar_wait_parked(full0 + 8 * sb, (uint32_t)((i / kTcBStages) & 1), 4000);   // B tile i expanded by all workers
-            mbar_wait_parked(empty0 + 8 * st, (uint32_t)(((i >> 1) & 1) ^ 1), 4000);    // accumulators of tile i-2 drained (passes at once for i < 2)
+            mbar_wait_parked(full0 + 8 * sb, (uint32_t)((i / kTcBStages) & 1), 32);   // B tile i expanded by all workers
+            mbar_wait_parked(empty0 + 8 * st, (uint32_t)(((i >> 1) & 1) ^ 1), 32);    // accumulators of tile i-2 drained (passes at once for i < 2)
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
             if (leader) {
 #pragma unroll
@@ -537,8 +549,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
         };
         static_assert(kColsPerWarp == 64, "one packed 32-register load covers the warp's 64 columns");
         // drain, part 1: wait for the tile's MMAs and start the TMEM load (64 columns as int16 pairs)
+        int* const gptr = shared_d2 + q0 + row;     // padded to whole query blocks
+        int gval = 0x7f7f7f7f;
         auto drain_load = [&](int tile, uint32_t (&v)[32]) {
             const int st = tile & 1;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval) : "l"(gptr) : "memory");   // consumed after the expansion
             mbar_wait(done0 + 8 * st, (uint32_t)((tile >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
             const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;   // valid columns of my half
@@ -572,8 +587,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
             asm volatile("tcgen05.fence::before_thread_sync;" ::);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * st);
-            if (cnt >= kColsPerWarp) tc_drain64<true>(v, pa, ib, kColsPerWarp, best);
-            else if (cnt > 0) tc_drain64<false>(v, pa, ib, cnt, best);
+            const int glim = pa - gval - 1;
+            if (cnt >= kColsPerWarp) tc_drain64<true>(v, pa, ib, kColsPerWarp, glim, gptr, best);
+            else if (cnt > 0) tc_drain64<false>(v, pa, ib, cnt, glim, gptr, best);
         };
         if (ntiles > 0) fetch(0);
         for (int i = 0; i < ntiles; i++) {
@@ -581,13 +597,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
             uint32_t v[32];
             if (i >= kTcLag) drain_load(i - kTcLag, v);      // TMEM latency hides behind the expansion below
             // buffer sb was last read by the MMAs of tile i - kTcBStages, whose completion this warp saw before draining it
-            unsigned char* dst = s_b + sb * (kTcN * 256) + b_off;
+            const uint32_t dst = b0 + sb * (kTcN * 256) + b_off;
 #pragma unroll
             for (int k = 0; k < kWordsPerThread; k++) {
                 uint4 c0, c1;
                 expand32_map(raw[k], c0, c1);
-                *reinterpret_cast<uint4*>(dst + k * (kRowStep / 8) * 2048) = c0;
-                *reinterpret_cast<uint4*>(dst + k * (kRowStep / 8) * 2048 + 128) = c1;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(dst + k * (kRowStep / 8) * 2048), "r"(c0.x), "r"(c0.y), "r"(c0.z), "r"(c0.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(dst + k * (kRowStep / 8) * 2048 + 128), "r"(c1.x), "r"(c1.y), "r"(c1.z), "r"(c1.w) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -654,7 +670,9 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     per_split = (per_split + tile - 1) / tile * tile;
     splits = nm > 0 ? (int)((nm + per_split - 1) / per_split) : 1;
     // per-call scratch from the stream-ordered allocator: matcher entry points are re-entrant
-    const size_t need = (size_t)splits * nq * sizeof(int4);
+    // variant 3 also keeps one int per (padded) query: the smallest second-best distance published by any CTA
+    const size_t bound_bytes = variant == 3 ? (size_t)qblocks * kTcQ * sizeof(int) : 0;
+    const size_t need = (size_t)splits * nq * sizeof(int4) + bound_bytes;
     int4* partial = nullptr;
     if (cudaMallocAsync((void**)&partial, need, s) != cudaSuccess) return -1;
     if (variant == 1) {
@@ -673,8 +691,10 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
             if (cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
             configured3 = true;
         }
+        int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
+        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
         knn2_tc_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
-                                                                      index_base, partial);
+                                                                      index_base, partial, shared_d2);
     } else if (variant == 2) {
         knn2_mma_stream_kernel<<<dim3(qblocks, splits), kMmaThreads, 0, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                               index_base, partial);
