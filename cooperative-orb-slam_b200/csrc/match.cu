@@ -533,11 +533,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
         const int r0 = (tid & 7) | ((tid >> 6) << 3), w0 = (tid >> 3) & 7;
         const uint32_t* src = m + ((size_t)lo + r0) * 8 + w0;
         const uint32_t b_off = (uint32_t)((r0 >> 3) * 2048 + (r0 & 7) * 16 + (2 * w0) * 128);
-        uint32_t raw[kWordsPerThread];
+        uint32_t raw_a[kWordsPerThread], raw_b[kWordsPerThread];     // tiles i and i + 1: global latency > one iteration
         const int ib0 = (int)(index_base + lo) + chalf * kColsPerWarp;
         const int n_full = (int)((hi - lo) / kTcN);                 // tiles whose kTcN rows all exist
         const int last_cnt = (int)(hi - lo) - n_full * kTcN;        // rows of the ragged last tile
-        auto fetch = [&](int tile) {      // called with tile = 0, 1, 2, ...
+        auto fetch = [&](int tile, uint32_t (&raw)[kWordsPerThread]) {      // called with tile = 0, 1, 2, ...
             if (tile < n_full) {
 #pragma unroll
                 for (int i = 0; i < kWordsPerThread; i++) raw[i] = __ldg(src + i * (kRowStep * 8));
@@ -553,7 +553,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
         int gval = 0x7f7f7f7f;
         auto drain_load = [&](int tile, uint32_t (&v)[32]) {
             const int st = tile & 1;
-            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval) : "l"(gptr) : "memory");   // consumed after the expansion
             mbar_wait(done0 + 8 * st, (uint32_t)((tile >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::);
             const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;   // valid columns of my half
@@ -570,7 +569,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
             }
         };
         // drain, part 2: the load has landed; update the top-2 and hand the accumulators back
-        auto drain_finish = [&](int tile, uint32_t (&v)[32]) {
+        auto drain_finish = [&](int tile, uint32_t (&v)[32], int glim) {
             const int st = tile & 1;
             const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;
             const int ib = ib0 + tile * kTcN;
@@ -587,11 +586,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
             asm volatile("tcgen05.fence::before_thread_sync;" ::);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * st);
-            const int glim = pa - gval - 1;
             if (cnt >= kColsPerWarp) tc_drain64<true>(v, pa, ib, kColsPerWarp, glim, gptr, best);
             else if (cnt > 0) tc_drain64<false>(v, pa, ib, cnt, glim, gptr, best);
         };
-        if (ntiles > 0) fetch(0);
+        if (ntiles > 0) fetch(0, raw_a);
+        if (ntiles > 1) fetch(1, raw_b);
         for (int i = 0; i < ntiles; i++) {
             const int sb = i & (kTcBStages - 1);
             uint32_t v[32];
@@ -601,20 +600,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
 #pragma unroll
             for (int k = 0; k < kWordsPerThread; k++) {
                 uint4 c0, c1;
-                expand32_map(raw[k], c0, c1);
+                expand32_map(raw_a[k], c0, c1);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(dst + k * (kRowStep / 8) * 2048), "r"(c0.x), "r"(c0.y), "r"(c0.z), "r"(c0.w) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(dst + k * (kRowStep / 8) * 2048 + 128), "r"(c1.x), "r"(c1.y), "r"(c1.z), "r"(c1.w) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * sb);
-            if (i + 1 < ntiles) fetch(i + 1);
-            if (i >= kTcLag) drain_finish(i - kTcLag, v);
+            // tile i + 1 was requested a whole iteration ago; tile i + 2 goes out now
+#pragma unroll
+            for (int k = 0; k < kWordsPerThread; k++) raw_a[k] = raw_b[k];
+            if (i + 2 < ntiles) fetch(i + 2, raw_b);
+            const int glim = pa - gval - 1;        // the bound read one iteration ago
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval) : "l"(gptr) : "memory");
+            if (i >= kTcLag) drain_finish(i - kTcLag, v, glim);
         }
         for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
             uint32_t v[32];
             drain_load(t, v);
-            drain_finish(t, v);
+            int gnow;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gnow) : "l"(gptr) : "memory");
+            drain_finish(t, v, pa - gnow - 1);
         }
     }
     // ---- merge the column halves (index ranges interleave: lexicographic merge) and store
@@ -640,6 +646,290 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K7d: K7c with the query operand held in tensor memory.  With both operands in shared memory an M128 x N128 x K32
+// MMA reads 8 KB per 64 cycles -- the whole shared-memory bandwidth -- and every expansion store of the workers
+// steals from it.  The queries never change, so they are written ONCE into TMEM (row = lane, 4 K-bytes per 32-bit
+// column: 64 columns per 128-query tile, 128 columns for both) and each MMA only streams its 4 KB B slab.
+//   TMEM: columns [0,128) = A0 | A1; three accumulator slots of 128 columns behind them.
+//   Unit u = (tile u/2, A tile u%2) -> slot u%3: 8 MMAs, one commit.  Workers: 4 lane quarters x 4 column quarters;
+//   a thread follows the two query rows (one per A tile) of its lane and 32 columns of every unit.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTsSlots = 3;
+constexpr int kTsAccCol0 = 128;      // first accumulator column
+
+// drain 32 accumulator columns (16 packed int16 pairs) of one query row; see tc_drain64
+template <bool FULL>
+__device__ __forceinline__ void tc_drain32p(const uint32_t (&v)[16], int pa, int idx0, int valid, int glim, int* gptr, Top2& best) {
+    uint32_t s[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) s[g] = __vmaxs2(__vimax3_s16x2(v[4 * g], v[4 * g + 1], v[4 * g + 2]), v[4 * g + 3]);
+    const uint32_t mx = __vmaxs2(__vimax3_s16x2(s[0], s[1], s[2]), s[3]);
+    const int d2_in = best.d2;
+    int lim = max(pa - best.d2, glim);
+    uint32_t bound2 = __byte_perm((uint32_t)(lim << kTcScaleLog2), 0u, 0x1010);
+    if (__vmaxs2(mx, bound2) != bound2) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if (__vmaxs2(s[g], bound2) != bound2) {
+                int key[8];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t x = v[4 * g + r];
+                    const int lo = ((int)(x << 16) >> (16 + kTcScaleLog2 - 3)) | (7 - 2 * r);
+                    const int hi = ((int)x >> (16 + kTcScaleLog2 - 3)) | (6 - 2 * r);
+                    key[2 * r] = FULL || 8 * g + 2 * r < valid ? lo : (int)0x80000000;
+                    key[2 * r + 1] = FULL || 8 * g + 2 * r + 1 < valid ? hi : (int)0x80000000;
+                }
+                int k = max(__vimax3_s32(key[0], key[1], key[2]), __vimax3_s32(key[3], key[4], key[5]));
+                k = __vimax3_s32(k, key[6], key[7]);
+                while ((k >> 3) > lim) {
+                    top2_push(best, pa - (k >> 3), idx0 + 8 * g + 7 - (k & 7));
+                    lim = max(pa - best.d2, glim);
+                    const int last = k;
+                    k = (int)0x80000000;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) k = max(k, key[j] < last ? key[j] : (int)0x80000000);
+                }
+                bound2 = __byte_perm((uint32_t)(lim << kTcScaleLog2), 0u, 0x1010);
+            }
+        }
+        if (best.d2 < d2_in) atomicMin(gptr, best.d2);
+    }
+}
+
+#define TMEM_LD16P(v, addr)                                                                                          \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "                                                 \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"                  \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+                 : "r"(addr))
+#define TMEM_WAIT_LD16(v)                                                                                            \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                    \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),   \
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) \
+                 :: "memory")
+
+__global__ void __launch_bounds__(kTcThreads, 1) knn2_ts_kernel(const uint32_t* __restrict__ q, int nq,
+                                                               const uint32_t* __restrict__ m, long long nm,
+                                                               long long per_split, long long index_base,
+                                                               int4* __restrict__ partial, int* __restrict__ shared_d2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* s_b = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // kTcBStages x [kTcN rows][256 B]
+    __shared__ __align__(8) unsigned long long s_full[kTcBStages], s_done[kTsSlots], s_empty[kTsSlots];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * kTcQ;
+    constexpr int kWorkThreads = kTcWorkers * 32;
+
+    if (warp == kTcWorkers) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int sb = 0; sb < kTcBStages; sb++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[sb])), "r"(kTcWorkers));
+#pragma unroll
+        for (int st = 0; st < kTsSlots; st++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_done[st])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_empty[st])), "r"(kTcWorkers));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::);
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::);
+    const uint32_t tmem = s_tmem;
+    const int quarter = warp & 3;                               // TMEM lanes 32*quarter .. +31
+    const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+    // ---- query operand -> TMEM: warps 0-3 write A0, warps 4-7 A1; a thread writes the 64 columns of its row
+    if (warp < 8) {
+        const int t = warp >> 2;
+        const int row = q0 + t * kTcM + quarter * 32 + lane;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint32_t bits = row < nq ? q[(size_t)row * 8 + w] : 0u;
+            uint4 c0, c1;
+            expand32_query(bits, c0, c1);       // plane j -> column 8*w + j, byte k -> K index 4*j + k of the word's slab
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         :: "r"(tlane + (uint32_t)(t * 64 + w * 8)), "r"(c0.x), "r"(c0.y), "r"(c0.z), "r"(c0.w), "r"(c1.x), "r"(c1.y),
+                            "r"(c1.z), "r"(c1.w));
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    const long long lo = (long long)blockIdx.y * per_split;
+    const long long hi = min(nm, lo + per_split);
+    const int ntiles = hi > lo ? (int)((hi - lo + kTcN - 1) / kTcN) : 0;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::);
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::);
+    uint32_t full0 = smem_u32(&s_full[0]), done0 = smem_u32(&s_done[0]), empty0 = smem_u32(&s_empty[0]), b0 = smem_u32(s_b);
+    asm volatile("" : "+r"(full0), "+r"(done0), "+r"(empty0), "+r"(b0));
+
+    Top2 best[2] = {{256, -1, 256, -1}, {256, -1, 256, -1}};
+    const int cq = warp >> 2;                                   // column quarter (workers)
+    if (warp == kTcWorkers) {
+        // =========================== MMA warp ===========================
+        const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+        const uint64_t b_desc = umma_desc(b0);
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
+        int slot = 0;
+        uint32_t use_par = 0;       // parity of the slot's use count
+        for (int i = 0; i < ntiles; i++) {
+            const int sb = i & (kTcBStages - 1);
+            mbar_wait_parked(full0 + 8 * sb, (uint32_t)((i / kTcBStages) & 1), 32);   // B tile i expanded by all workers
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                mbar_wait_parked(empty0 + 8 * slot, use_par ^ 1u, 32);   // previous use of the slot loaded out (passes at once the first time)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::);
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ks++) {
+                        const uint64_t db = b_desc + (uint64_t)((sb * (kTcN * 256) + ks * 256) >> 4);
+                        const uint32_t accumulate = ks ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+                            "}\n"
+                            :: "r"(tmem + (uint32_t)(kTsAccCol0 + slot * kTcN)), "r"(tmem + (uint32_t)(t * 64 + ks * 8)), "l"(db), "r"(idesc),
+                               "r"(accumulate), "r"(0u));
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(done0 + 8 * slot));
+                }
+                __syncwarp();
+                if (++slot == kTsSlots) { slot = 0; use_par ^= 1u; }
+            }
+        }
+    } else {
+        // =========================== worker warps ===========================
+        int pa[2];
+        int* gptr[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int row = q0 + t * kTcM + quarter * 32 + lane;
+            gptr[t] = shared_d2 + row;      // padded to whole query blocks
+            pa[t] = 0;
+            if (row < nq) {
+                const uint4 x = *reinterpret_cast<const uint4*>(q + (size_t)row * 8);
+                const uint4 y = *reinterpret_cast<const uint4*>(q + (size_t)row * 8 + 4);
+                pa[t] = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w) + __popc(y.x) + __popc(y.y) + __popc(y.z) + __popc(y.w);
+            }
+        }
+        constexpr int kColsPerWarp = 32;
+        const uint32_t tacc = tlane + (uint32_t)(kTsAccCol0 + cq * kColsPerWarp);
+        constexpr int kWordsPerThread = kTcN * 8 / kWorkThreads;   // 2
+        constexpr int kRowStep = kWorkThreads / 8;                  // 64
+        const int r0 = (tid & 7) | ((tid >> 6) << 3), w0 = (tid >> 3) & 7;
+        const uint32_t* src = m + ((size_t)lo + r0) * 8 + w0;
+        const uint32_t b_off = (uint32_t)((r0 >> 3) * 2048 + (r0 & 7) * 16 + (2 * w0) * 128);
+        uint32_t raw[kWordsPerThread];
+        const int ib0 = (int)(index_base + lo) + cq * kColsPerWarp;
+        const int n_full = (int)((hi - lo) / kTcN);
+        const int last_cnt = (int)(hi - lo) - n_full * kTcN;
+        auto fetch = [&](int tile) {
+            if (tile < n_full) {
+#pragma unroll
+                for (int i = 0; i < kWordsPerThread; i++) raw[i] = __ldg(src + i * (kRowStep * 8));
+            } else {
+#pragma unroll
+                for (int i = 0; i < kWordsPerThread; i++) raw[i] = r0 + i * kRowStep < last_cnt ? __ldg(src + i * (kRowStep * 8)) : 0u;
+            }
+            src += kTcN * 8;
+        };
+        int dslot = 0;              // slot / use parity of the next unit this warp drains
+        uint32_t dpar = 0;
+        int gval[2] = {0x7f7f7f7f, 0x7f7f7f7f};
+        // wait for a unit's MMAs and start loading my 32 columns of it
+        auto unit_load = [&](uint32_t (&v)[16]) {
+            mbar_wait(done0 + 8 * dslot, dpar);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::);
+            TMEM_LD16P(v, tacc + (uint32_t)(dslot * kTcN));
+        };
+        // the load has landed: give the slot back
+        auto unit_release = [&](uint32_t (&v)[16]) {
+            TMEM_WAIT_LD16(v);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * dslot);
+            if (++dslot == kTsSlots) { dslot = 0; dpar ^= 1u; }
+        };
+        auto unit_update = [&](const uint32_t (&v)[16], int tile, int t) {
+            const int cnt = (tile < n_full ? kTcN : last_cnt) - cq * kColsPerWarp;     // valid columns of my quarter
+            const int ib = ib0 + tile * kTcN;
+            const int glim = pa[t] - gval[t] - 1;
+            if (cnt >= kColsPerWarp) tc_drain32p<true>(v, pa[t], ib, kColsPerWarp, glim, gptr[t], best[t]);
+            else if (cnt > 0) tc_drain32p<false>(v, pa[t], ib, cnt, glim, gptr[t], best[t]);
+        };
+        auto drain_tile = [&](int tile, uint32_t (&v0)[16], uint32_t (&v1)[16]) {    // after unit_load(v0)
+            unit_release(v0);
+            unit_load(v1);
+            unit_update(v0, tile, 0);
+            unit_release(v1);
+            unit_update(v1, tile, 1);
+        };
+        if (ntiles > 0) fetch(0);
+        for (int i = 0; i < ntiles; i++) {
+            const int sb = i & (kTcBStages - 1);
+            uint32_t v0[16], v1[16];
+            if (i >= kTcLag) {
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval[0]) : "l"(gptr[0]) : "memory");
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval[1]) : "l"(gptr[1]) : "memory");
+                unit_load(v0);      // TMEM latency hides behind the expansion below
+            }
+            // buffer sb was last read by the MMAs of tile i - kTcBStages, whose completion this warp saw before draining it
+            const uint32_t dst = b0 + sb * (kTcN * 256) + b_off;
+#pragma unroll
+            for (int k = 0; k < kWordsPerThread; k++) {
+                uint4 c0, c1;
+                expand32_map(raw[k], c0, c1);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(dst + k * (kRowStep / 8) * 2048), "r"(c0.x), "r"(c0.y), "r"(c0.z), "r"(c0.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(dst + k * (kRowStep / 8) * 2048 + 128), "r"(c1.x), "r"(c1.y), "r"(c1.z), "r"(c1.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * sb);
+            if (i + 1 < ntiles) fetch(i + 1);
+            if (i >= kTcLag) drain_tile(i - kTcLag, v0, v1);
+        }
+        for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
+            uint32_t v0[16], v1[16];
+            unit_load(v0);
+            drain_tile(t, v0, v1);
+        }
+    }
+    // ---- merge the column quarters (index ranges interleave: lexicographic merge) and store
+    asm volatile("tcgen05.fence::before_thread_sync;" ::);
+    __syncthreads();
+    int4* s_rec = reinterpret_cast<int4*>(s_b);     // all MMAs retired: the B stages are free
+    if (warp >= 4 && warp < kTcWorkers) {
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+            s_rec[(cq - 1) * kTcQ + t * kTcM + quarter * 32 + lane] = make_int4(best[t].d1, best[t].i1, best[t].d2, best[t].i2);
+    }
+    __syncthreads();
+    if (warp < 4) {
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int row = t * kTcM + quarter * 32 + lane;
+            Top2 b = best[t];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int4 o = s_rec[c * kTcQ + row];
+                top2_merge(b.d1, b.i1, b.d2, b.i2, o.x, o.y, o.z, o.w);
+            }
+            if (q0 + row < nq) partial[(size_t)blockIdx.y * nq + q0 + row] = make_int4(b.d1, b.i1, b.d2, b.i2);
+        }
+    }
+    if (warp == kTcWorkers) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::);
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+    }
+}
+
 __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -657,9 +947,9 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int qper = variant == 3 ? kTcQ : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
-    const int tile = variant == 3 ? kTcN : (variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile));
-    const int per_sm = variant == 3 ? 1 : 2;
+    const int qper = variant >= 3 ? kTcQ : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
+    const int tile = variant >= 3 ? kTcN : (variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile));
+    const int per_sm = variant >= 3 ? 1 : 2;
     const int qblocks = (nq + qper - 1) / qper;
     // enough map splits to fill the SMs, each at least one tile
     // never more CTAs than fit at once (a partial second wave would double the run time)
@@ -671,7 +961,7 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     splits = nm > 0 ? (int)((nm + per_split - 1) / per_split) : 1;
     // per-call scratch from the stream-ordered allocator: matcher entry points are re-entrant
     // variant 3 also keeps one int per (padded) query: the smallest second-best distance published by any CTA
-    const size_t bound_bytes = variant == 3 ? (size_t)qblocks * kTcQ * sizeof(int) : 0;
+    const size_t bound_bytes = variant >= 3 ? (size_t)qblocks * kTcQ * sizeof(int) : 0;
     const size_t need = (size_t)splits * nq * sizeof(int4) + bound_bytes;
     int4* partial = nullptr;
     if (cudaMallocAsync((void**)&partial, need, s) != cudaSuccess) return -1;
@@ -694,6 +984,17 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
         if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
         knn2_tc_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
+                                                                      index_base, partial, shared_d2);
+    } else if (variant == 4) {
+        const size_t smem = kTcBStages * (size_t)kTcN * 256 + 1024;
+        static bool configured4 = false;
+        if (!configured4) {
+            if (cudaFuncSetAttribute(knn2_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            configured4 = true;
+        }
+        int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
+        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
+        knn2_ts_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                       index_base, partial, shared_d2);
     } else if (variant == 2) {
         knn2_mma_stream_kernel<<<dim3(qblocks, splits), kMmaThreads, 0, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
