@@ -656,6 +656,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_tc_kernel(const uint32_t* 
 //   a thread follows the two query rows (one per A tile) of its lane and 32 columns of every unit.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTsSlots = 3;
+constexpr int kTsLag = 2;         // tiles between expansion and drain: the three slots hold 1.5 tiles of accumulators
 constexpr int kTsAccCol0 = 128;      // first accumulator column
 
 // drain 32 accumulator columns (16 packed int16 pairs) of one query row; see tc_drain64
@@ -826,17 +827,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_ts_kernel(const uint32_t* 
         const int r0 = (tid & 7) | ((tid >> 6) << 3), w0 = (tid >> 3) & 7;
         const uint32_t* src = m + ((size_t)lo + r0) * 8 + w0;
         const uint32_t b_off = (uint32_t)((r0 >> 3) * 2048 + (r0 & 7) * 16 + (2 * w0) * 128);
-        uint32_t raw[kWordsPerThread];
+        uint32_t raw[kWordsPerThread], raw_next[kWordsPerThread];     // tiles i and i + 1
         const int ib0 = (int)(index_base + lo) + cq * kColsPerWarp;
         const int n_full = (int)((hi - lo) / kTcN);
         const int last_cnt = (int)(hi - lo) - n_full * kTcN;
-        auto fetch = [&](int tile) {
+        auto fetch = [&](int tile, uint32_t (&dstw)[kWordsPerThread]) {      // called with tile = 0, 1, 2, ...
             if (tile < n_full) {
 #pragma unroll
-                for (int i = 0; i < kWordsPerThread; i++) raw[i] = __ldg(src + i * (kRowStep * 8));
+                for (int i = 0; i < kWordsPerThread; i++) dstw[i] = __ldg(src + i * (kRowStep * 8));
             } else {
 #pragma unroll
-                for (int i = 0; i < kWordsPerThread; i++) raw[i] = r0 + i * kRowStep < last_cnt ? __ldg(src + i * (kRowStep * 8)) : 0u;
+                for (int i = 0; i < kWordsPerThread; i++) dstw[i] = r0 + i * kRowStep < last_cnt ? __ldg(src + i * (kRowStep * 8)) : 0u;
             }
             src += kTcN * 8;
         };
@@ -857,29 +858,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_ts_kernel(const uint32_t* 
             if (lane == 0) mbar_arrive(empty0 + 8 * dslot);
             if (++dslot == kTsSlots) { dslot = 0; dpar ^= 1u; }
         };
-        auto unit_update = [&](const uint32_t (&v)[16], int tile, int t) {
+        auto unit_update = [&](const uint32_t (&v)[16], int tile, int t, int glim) {
             const int cnt = (tile < n_full ? kTcN : last_cnt) - cq * kColsPerWarp;     // valid columns of my quarter
             const int ib = ib0 + tile * kTcN;
-            const int glim = pa[t] - gval[t] - 1;
             if (cnt >= kColsPerWarp) tc_drain32p<true>(v, pa[t], ib, kColsPerWarp, glim, gptr[t], best[t]);
             else if (cnt > 0) tc_drain32p<false>(v, pa[t], ib, cnt, glim, gptr[t], best[t]);
         };
-        auto drain_tile = [&](int tile, uint32_t (&v0)[16], uint32_t (&v1)[16]) {    // after unit_load(v0)
+        auto drain_tile = [&](int tile, uint32_t (&v0)[16], uint32_t (&v1)[16], int glim0, int glim1) {    // after unit_load(v0)
             unit_release(v0);
             unit_load(v1);
-            unit_update(v0, tile, 0);
+            unit_update(v0, tile, 0, glim0);
             unit_release(v1);
-            unit_update(v1, tile, 1);
+            unit_update(v1, tile, 1, glim1);
         };
-        if (ntiles > 0) fetch(0);
+        if (ntiles > 0) fetch(0, raw);
+        if (ntiles > 1) fetch(1, raw_next);
         for (int i = 0; i < ntiles; i++) {
             const int sb = i & (kTcBStages - 1);
             uint32_t v0[16], v1[16];
-            if (i >= kTcLag) {
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval[0]) : "l"(gptr[0]) : "memory");
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval[1]) : "l"(gptr[1]) : "memory");
-                unit_load(v0);      // TMEM latency hides behind the expansion below
-            }
+            if (i >= kTsLag) unit_load(v0);      // TMEM latency hides behind the expansion below
             // buffer sb was last read by the MMAs of tile i - kTcBStages, whose completion this warp saw before draining it
             const uint32_t dst = b0 + sb * (kTcN * 256) + b_off;
 #pragma unroll
@@ -892,13 +889,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_ts_kernel(const uint32_t* 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * sb);
-            if (i + 1 < ntiles) fetch(i + 1);
-            if (i >= kTcLag) drain_tile(i - kTcLag, v0, v1);
+            // tile i + 1 was requested a whole iteration ago; tile i + 2 goes out now
+#pragma unroll
+            for (int k = 0; k < kWordsPerThread; k++) raw[k] = raw_next[k];
+            if (i + 2 < ntiles) fetch(i + 2, raw_next);
+            const int glim0 = pa[0] - gval[0] - 1, glim1 = pa[1] - gval[1] - 1;
+            if ((i & 3) == 0) {     // a stale bound is still a bound: one L2 round trip every fourth tile
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "+r"(gval[0]) : "l"(gptr[0]) : "memory");
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "+r"(gval[1]) : "l"(gptr[1]) : "memory");
+            }
+            if (i >= kTsLag) drain_tile(i - kTsLag, v0, v1, glim0, glim1);
         }
-        for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
+        for (int t = max(0, ntiles - kTsLag); t < ntiles; t++) {
             uint32_t v0[16], v1[16];
             unit_load(v0);
-            drain_tile(t, v0, v1);
+            drain_tile(t, v0, v1, pa[0] - gval[0] - 1, pa[1] - gval[1] - 1);
         }
     }
     // ---- merge the column quarters (index ranges interleave: lexicographic merge) and store
