@@ -45,6 +45,15 @@ def _peaks():
         return 6650.0, "fallback"
 
 
+def _bf16_peak():
+    """Dense bf16 TFLOP/s: MEASURED_PEAKS.json (burst), else the profiling guide's nominal figure."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured"
+    except Exception:
+        return 2250.0, "fallback"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -335,7 +344,7 @@ def run_ours(args):
 
         per_variant = {}
         ref_out = None
-        for variant, name in ((0, "popc"), (1, "imma_smem"), (2, "imma_stream"), (3, "tcgen05")):
+        for variant, name in ((0, "popc"), (1, "imma_smem"), (2, "imma_stream"), (3, "tcgen05"), (4, "tcgen05_a_in_tmem")):
             for _ in range(3):
                 match_step(variant)
             barrier()
@@ -358,6 +367,11 @@ def run_ours(args):
         matching = {"metric": "Hamming 2-NN Gcmp/s (2000 queries x 1M map, 256-bit)", "value": gcmp, "unit": "Gcmp/s",
                     "ms_per_batch": per_variant[bestv]["ms_per_batch"], "kernel": bestv, "variants": per_variant,
                     "map_shards": world, "d1_checksum": chk,
+                    # one comparison = 256 int8 MACs on the tensor pipe; int8 dense peak = 2 x the measured bf16 peak
+                    "roofline": {"bound": "tensor", "achieved": 2 * 256 * gcmp / 1e3, "peak": 2 * _bf16_peak()[0],
+                                 "unit": "TOP/s", "frac": 2 * 256 * gcmp / 1e3 / (2 * _bf16_peak()[0]), "traffic": None,
+                                 "peak_source": "2 x bf16 burst peak (" + _bf16_peak()[1] + "; int8 runs at twice the bf16 rate); ncu: tensor pipe 71 % active, "
+                                                "shared-memory data pipe 93 % (operand reads + expansion stores) -- profiles/r1_ncu_knn2_tcgen05.csv"},
                     "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8,
                     "popc_kernel_frac_of_popc_peak": per_variant["popc"]["gcmp_s"] / (148 * 16 * 1.965 / 8)}
 

@@ -354,7 +354,7 @@ class ORBmatcher:
     def knn2(self, queries, map_desc, index_base=0, variant=3):
         """Brute-force 2-NN: returns (best_idx, best_dist, second_dist, second_idx).
         variant 0 = LOP3+POPC kernel, 1/2 = mma.sync integer tensor-core AND-popc contraction, 3 = tcgen05 (UMMA + TMEM)
-        contraction (fastest); all variants return identical results."""
+        contraction (default), 4 = the same with the query operand in TMEM; all variants return identical results."""
         q = np.ascontiguousarray(queries, np.uint8); m = np.ascontiguousarray(map_desc, np.uint8)
         nq = q.shape[0]
         bi, bd, sd, si = (np.zeros(nq, np.int32) for _ in range(4))

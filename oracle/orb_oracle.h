@@ -17,7 +17,7 @@
  * cv2 4.13.0 (tests/test_oracle_primitives.py + tests/golden/), (2) the whole
  * extractor is checked bit-for-bit against the reference's own ORBextractor.cc
  * compiled verbatim over oracle/cvshim (oracle/_ref/liborbref.so, built by
- * oracle/Makefile; tests/test_oracle_vs_ref.py).  The matcher loops cannot be
+ * oracle/Makefile; tests/test_oracle_extractor.py).  The matcher loops cannot be
  * compiled from the reference (they need Frame/KeyFrame/MapPoint/DBoW2), so the
  * matcher restatement is "parity unpinned" beyond DescriptorDistance KATs.
  */
