@@ -82,6 +82,12 @@ ABI = {
                                           _I, _VP, _I]),
     "orbm_stereo_matches": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _VP, _VP, _VP]),
     "orbm_distinctive_descriptors": (_I, [_VP, _VP, _I, _VP, _I]),
+    "orbf_undistort_keypoints": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I]),
+    "orbf_image_bounds": (_I, [_I, _I, _VP, _VP, _I, _VP, _I]),
+    "orbf_assign_grid": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I]),
+    "orbf_features_in_area": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I]),
+    "orbm_search_by_projection_frame": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _I,
+                                            _VP, _VP, _VP, _I]),
 }
 
 
@@ -417,6 +423,67 @@ def compute_distinctive_descriptors(desc, ptr, device=0):
     best = np.zeros(len(p) - 1, np.int32)
     _check(lib().orbm_distinctive_descriptors(_p(d), _p(p), len(p) - 1, _p(best), device), "orbm_distinctive_descriptors")
     return best
+
+
+GRID_COLS, GRID_ROWS = 64, 48
+MPV_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
+                      ("in_view", "<i4"), ("obs_positive", "<i4")])
+
+
+class FrameFeatures:
+    """The Frame-side steps right after extraction (R21/src/Frame.cc): UndistortKeyPoints (:409-439),
+    ComputeImageBounds (:441-470), AssignFeaturesToGrid (:235-250), GetFeaturesInArea (:332-385)."""
+
+    def __init__(self, keys, K, dist, cols, rows, device=0):
+        self.device = device
+        self.K = np.ascontiguousarray(K, np.float32); self.dist = np.ascontiguousarray(dist, np.float32).ravel()
+        assert self.K.shape == (4,), "K = (fx, fy, cx, cy)"
+        L = lib()
+        k = np.ascontiguousarray(keys, KP_DTYPE)
+        self.bounds = np.zeros(4, np.float32)
+        _check(L.orbf_image_bounds(cols, rows, _p(self.K), _p(self.dist), len(self.dist), _p(self.bounds), device), "orbf_image_bounds")
+        self.keys_un = np.zeros(len(k), KP_DTYPE)
+        _check(L.orbf_undistort_keypoints(_p(k), len(k), _p(self.K), _p(self.dist), len(self.dist), _p(self.keys_un), device),
+               "orbf_undistort_keypoints")
+        self.cell_ptr = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32); self.cell_idx = np.zeros(max(len(k), 1), np.int32)
+        n = C.c_int(0)
+        _check(L.orbf_assign_grid(_p(self.keys_un), len(k), _p(self.bounds), _p(self.cell_ptr), _p(self.cell_idx), C.byref(n), device),
+               "orbf_assign_grid")
+        self.n_assigned = n.value
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        """One window or arrays of windows -> list of index arrays (reference order)."""
+        qx = np.atleast_1d(np.asarray(x, np.float32)); nq = len(qx)
+        qy = np.broadcast_to(np.asarray(y, np.float32), (nq,)).copy(); qr = np.broadcast_to(np.asarray(r, np.float32), (nq,)).copy()
+        mn = np.broadcast_to(np.asarray(minLevel, np.int32), (nq,)).copy(); mx = np.broadcast_to(np.asarray(maxLevel, np.int32), (nq,)).copy()
+        ptr = np.zeros(nq + 1, np.int32)
+        cap = max(64 * nq, 1024)
+        while True:
+            out = np.zeros(cap, np.int32)
+            rc = lib().orbf_features_in_area(_p(self.keys_un), len(self.keys_un), _p(self.cell_ptr), _p(self.cell_idx), _p(self.bounds),
+                                             _p(qx), _p(qy), _p(qr), _p(mn), _p(mx), nq, _p(ptr), _p(out), cap, self.device)
+            if rc == 3 and ptr[nq] > cap:      # ORB_ERR_CAPACITY: out_ptr is complete, retry with the exact size
+                cap = int(ptr[nq]); continue
+            _check(rc, "orbf_features_in_area")
+            break
+        res = [out[ptr[q]:ptr[q + 1]].copy() for q in range(nq)]
+        return res if np.ndim(x) else res[0]
+
+
+def search_by_projection_frame(frame, desc_f, u_right, occupied, scale_factors, map_points, desc_mp, th=1.0, nnratio=0.6,
+                               th_high=100):
+    """ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th) (R21/src/ORBmatcher.cc:45-130).
+    frame: FrameFeatures; map_points: MPV_DTYPE array.  -> (feature -> point, point -> feature, nmatches)."""
+    df = np.ascontiguousarray(desc_f, np.uint8); ur = np.ascontiguousarray(u_right, np.float32)
+    occ = np.ascontiguousarray(occupied, np.uint8); sf = np.ascontiguousarray(scale_factors, np.float32)
+    mp = np.ascontiguousarray(map_points, MPV_DTYPE); dm = np.ascontiguousarray(desc_mp, np.uint8)
+    nf = len(frame.keys_un)
+    fp = np.zeros(max(nf, 1), np.int32); pf = np.zeros(max(len(mp), 1), np.int32); n = C.c_int(0)
+    _check(lib().orbm_search_by_projection_frame(_p(frame.keys_un), _p(df), _p(ur), _p(occ), nf, _p(frame.cell_ptr), _p(frame.cell_idx),
+                                                 _p(frame.bounds), _p(sf), len(sf), _p(mp), _p(dm), len(mp), float(th), float(nnratio),
+                                                 int(th_high), _p(fp), _p(pf), C.byref(n), frame.device),
+           "orbm_search_by_projection_frame")
+    return fp[:nf], pf[:len(mp)], n.value
 
 
 def compute_stereo_matches(ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mbf, mb):

@@ -1,0 +1,468 @@
+// frame.cu -- the steps right after extraction and the projection search that consumes them:
+//   Frame::UndistortKeyPoints      R21/src/Frame.cc:409-439   (cv::undistortPoints, R = I, P = K)
+//   Frame::ComputeImageBounds      R21/src/Frame.cc:441-470
+//   Frame::AssignFeaturesToGrid    R21/src/Frame.cc:235-250 + PosInGrid :387-397
+//   Frame::GetFeaturesInArea       R21/src/Frame.cc:332-385
+//   ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th)   R21/src/ORBmatcher.cc:45-130
+// All float/double arithmetic is spelled with explicit round-to-nearest intrinsics in the reference's (OpenCV's)
+// evaluation order: no FMA contraction, so the results are bit-identical to the CPU code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "internal.h"
+#include "orbcuda.h"
+
+namespace orbcuda {
+
+constexpr int kGridCols = 64, kGridRows = 48, kGridCells = kGridCols * kGridRows;   // Frame.h:36-37
+constexpr int kFrameMaxFeatures = 32768;      // per-CTA shared-memory tables are sized by the feature count
+
+struct UndistortParams {
+    double fx, fy, cx, cy, ifx, ify;
+    double k[12];
+    int identity;      // mDistCoef[0] == 0: key points are copied (Frame.cc:411-415)
+};
+
+// ---------------------------------------------------------------- undistort: one thread per point
+__device__ __forceinline__ void undistort_point(const UndistortParams& p, float fx_in, float fy_in, float& ox, float& oy) {
+    const double u = (double)fx_in, v = (double)fy_in;
+    double x = __dmul_rn(__dsub_rn(u, p.cx), p.ifx);
+    double y = __dmul_rn(__dsub_rn(v, p.cy), p.ify);
+    const double x0 = x, y0 = y;
+    const double* k = p.k;
+#pragma unroll 1
+    for (int j = 0; j < 5; j++) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[7], r2), k[6]), r2), k[5]), r2));
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[4], r2), k[1]), r2), k[0]), r2));
+        const double icdist = __ddiv_rn(num, den);
+        if (icdist < 0) {
+            x = __dmul_rn(__dsub_rn(u, p.cx), p.ifx);
+            y = __dmul_rn(__dsub_rn(v, p.cy), p.ify);
+            break;
+        }
+        // deltaX = 2*k2*x*y + k3*(r2 + 2*x*x) + k8*r2 + k9*r2*r2, left to right
+        const double two_xx = __dmul_rn(__dmul_rn(2.0, x), x), two_yy = __dmul_rn(__dmul_rn(2.0, y), y);
+        double dx = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, k[2]), x), y), __dmul_rn(k[3], __dadd_rn(r2, two_xx)));
+        dx = __dadd_rn(__dadd_rn(dx, __dmul_rn(k[8], r2)), __dmul_rn(__dmul_rn(k[9], r2), r2));
+        double dy = __dadd_rn(__dmul_rn(k[2], __dadd_rn(r2, two_yy)), __dmul_rn(__dmul_rn(__dmul_rn(2.0, k[3]), x), y));
+        dy = __dadd_rn(__dadd_rn(dy, __dmul_rn(k[10], r2)), __dmul_rn(__dmul_rn(k[11], r2), r2));
+        x = __dmul_rn(__dsub_rn(x0, dx), icdist);
+        y = __dmul_rn(__dsub_rn(y0, dy), icdist);
+    }
+    // RR = P * I: xx = fx*x + 0*y + cx, ww = 1/(0*x + 0*y + 1)
+    const double xx = __dadd_rn(__dadd_rn(__dmul_rn(p.fx, x), __dmul_rn(0.0, y)), p.cx);
+    const double yy = __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(p.fy, y)), p.cy);
+    const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(0.0, y)), 1.0));
+    ox = __double2float_rn(__dmul_rn(xx, ww));
+    oy = __double2float_rn(__dmul_rn(yy, ww));
+}
+
+__global__ void undistort_kernel(const orb_keypoint_t* __restrict__ in, int n, UndistortParams p, orb_keypoint_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    orb_keypoint_t kp = in[i];
+    if (!p.identity) undistort_point(p, kp.x, kp.y, kp.x, kp.y);
+    out[i] = kp;
+}
+
+// ---------------------------------------------------------------- grid: one CTA, stable counting sort by cell
+struct GridParams { float minx, miny, winv, hinv; };
+
+__device__ __forceinline__ int pos_in_grid(const GridParams& g, float x, float y) {
+    // PosInGrid: round((x - mnMinX) * mfGridElementWidthInv) in float, half away from zero
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(x, g.minx), g.winv));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(y, g.miny), g.hinv));
+    if (px < 0 || px >= kGridCols || py < 0 || py >= kGridRows) return -1;
+    return px * kGridRows + py;      // mGrid[ix][iy]
+}
+
+__global__ void __launch_bounds__(1024) grid_kernel(const orb_keypoint_t* __restrict__ kps, int n, GridParams g,
+                                                    int* __restrict__ cell_ptr, int* __restrict__ cell_idx) {
+    extern __shared__ int s_dyn[];
+    int* s_count = s_dyn;                                   // [kGridCells + 1]: counts, then exclusive offsets
+    short* s_cell = reinterpret_cast<short*>(s_dyn + kGridCells + 1);   // [n]
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x;
+    for (int c = tid; c <= kGridCells; c += 1024) s_count[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int c = pos_in_grid(g, kps[i].x, kps[i].y);
+        s_cell[i] = (short)c;
+        if (c >= 0) atomicAdd(&s_count[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan of 3072 counts: 3 cells per thread
+    const int c0 = tid * 3;
+    const int a = s_count[c0], b = s_count[c0 + 1], c = s_count[c0 + 2];
+    s_part[tid] = a + b + c;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int v = tid >= off ? s_part[tid - off] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    const int base = s_part[tid] - (a + b + c);
+    s_count[c0] = base; s_count[c0 + 1] = base + a; s_count[c0 + 2] = base + a + b;
+    if (tid == 1023) s_count[kGridCells] = s_part[1023];
+    __syncthreads();
+    for (int k = tid; k <= kGridCells; k += 1024) cell_ptr[k] = s_count[k];
+    // stable placement: rank inside the cell = number of earlier key points of the same cell (push_back order)
+    for (int i = tid; i < n; i += 1024) {
+        const int ci = s_cell[i];
+        if (ci < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < i; j++) rank += (s_cell[j] == ci);
+        cell_idx[s_count[ci] + rank] = i;
+    }
+}
+
+// ---------------------------------------------------------------- GetFeaturesInArea
+struct AreaWindow { int x0, x1, y0, y1; bool empty; };
+
+__device__ __forceinline__ AreaWindow area_window(const GridParams& g, float x, float y, float r) {
+    AreaWindow w;
+    w.empty = true;
+    w.x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.minx), r), g.winv)));
+    if (w.x0 >= kGridCols) return w;
+    w.x1 = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, g.minx), r), g.winv)));
+    if (w.x1 < 0) return w;
+    w.y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, g.miny), r), g.hinv)));
+    if (w.y0 >= kGridRows) return w;
+    w.y1 = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, g.miny), r), g.hinv)));
+    if (w.y1 < 0) return w;
+    w.empty = false;
+    return w;
+}
+
+// visits the indices GetFeaturesInArea would return, in its order; f(idx) returns false to stop early
+template <class F>
+__device__ __forceinline__ void for_features_in_area(const orb_keypoint_t* __restrict__ kps, const int* __restrict__ cell_ptr,
+                                                     const int* __restrict__ cell_idx, const GridParams& g, float x, float y, float r,
+                                                     int min_level, int max_level, F f) {
+    const AreaWindow w = area_window(g, x, y, r);
+    if (w.empty) return;
+    const bool check_levels = (min_level > 0) || (max_level >= 0);
+    for (int ix = w.x0; ix <= w.x1; ix++)
+        for (int iy = w.y0; iy <= w.y1; iy++) {
+            const int c = ix * kGridRows + iy;
+            const int e = cell_ptr[c + 1];
+            for (int j = cell_ptr[c]; j < e; j++) {
+                const int idx = cell_idx[j];
+                const int octave = kps[idx].octave;
+                if (check_levels) {
+                    if (octave < min_level) continue;
+                    if (max_level >= 0 && octave > max_level) continue;
+                }
+                const float distx = __fsub_rn(kps[idx].x, x), disty = __fsub_rn(kps[idx].y, y);
+                if (fabsf(distx) < r && fabsf(disty) < r)
+                    if (!f(idx)) return;
+            }
+        }
+}
+
+__global__ void area_count_kernel(const orb_keypoint_t* __restrict__ kps, const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx,
+                                  GridParams g, const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qr,
+                                  const int* __restrict__ qmin, const int* __restrict__ qmax, int nq, int* __restrict__ counts) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int n = 0;
+    for_features_in_area(kps, cell_ptr, cell_idx, g, qx[q], qy[q], qr[q], qmin[q], qmax[q], [&](int) { n++; return true; });
+    counts[q] = n;
+}
+
+// exclusive scan of counts[nq] into ptr[nq + 1], one CTA
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ counts, int nq, int* __restrict__ ptr) {
+    __shared__ int s_part[1024];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nq; base += 1024) {
+        const int v = base + tid < nq ? counts[base + tid] : 0;
+        s_part[tid] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            const int t = tid >= off ? s_part[tid - off] : 0;
+            __syncthreads();
+            s_part[tid] += t;
+            __syncthreads();
+        }
+        if (base + tid < nq) ptr[base + tid] = s_carry + s_part[tid] - v;
+        __syncthreads();
+        if (tid == 1023) s_carry += s_part[1023];
+        __syncthreads();
+    }
+    if (tid == 0) ptr[nq] = s_carry;
+}
+
+__global__ void area_fill_kernel(const orb_keypoint_t* __restrict__ kps, const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx,
+                                 GridParams g, const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qr,
+                                 const int* __restrict__ qmin, const int* __restrict__ qmax, int nq, const int* __restrict__ ptr,
+                                 int* __restrict__ out, int cap) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int at = ptr[q];
+    for_features_in_area(kps, cell_ptr, cell_idx, g, qx[q], qy[q], qr[q], qmin[q], qmax[q], [&](int idx) {
+        if (at < cap) out[at] = idx;
+        at++;
+        return true;
+    });
+}
+
+// ---------------------------------------------------------------- SearchByProjection(Frame&, vpMapPoints, th)
+// The reference walks the map points in order; a feature taken by an earlier point (with observations) is skipped by
+// the later ones (:82-84), so the result depends on the order.  One CTA reproduces it in rounds: every unresolved
+// point claims its candidate features (GetFeaturesInArea) with atomicMin(point index); a point whose candidates are
+// all claimed by nobody earlier cannot be influenced by an unresolved point any more and is resolved exactly as the
+// sequential loop would resolve it.  Points resolved in one round have pairwise disjoint candidate sets, so their
+// writes do not race.  The lowest unresolved point is always resolvable: the loop ends after at most n_mp rounds
+// (a handful in practice).
+__device__ __forceinline__ int hamming32(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b) {
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) d += __popc(a[w] ^ b[w]);
+    return d;
+}
+
+__global__ void __launch_bounds__(1024) projection_kernel(const orb_keypoint_t* __restrict__ kps, const uint32_t* __restrict__ desc_f,
+                                                          const float* __restrict__ u_right, const uint8_t* __restrict__ occupied, int n_f,
+                                                          const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx, GridParams g,
+                                                          const float* __restrict__ scale_factors, const orbm_map_point_view_t* __restrict__ mps,
+                                                          const uint32_t* __restrict__ desc_mp, int n_mp, float th, float nnratio, int th_high,
+                                                          int* __restrict__ out_feature_point, int* __restrict__ out_point_feature,
+                                                          uint8_t* __restrict__ resolved, int* __restrict__ out_nmatches) {
+    extern __shared__ int s_dyn[];
+    int* s_claim = s_dyn;                                             // [n_f]
+    uint8_t* s_blocked = reinterpret_cast<uint8_t*>(s_dyn + n_f);    // [n_f]
+    __shared__ int s_left, s_matches;
+    const int tid = threadIdx.x;
+    for (int f = tid; f < n_f; f += 1024) { s_blocked[f] = occupied[f]; out_feature_point[f] = -1; }
+    for (int i = tid; i < n_mp; i += 1024) {
+        out_point_feature[i] = -1;
+        resolved[i] = mps[i].in_view ? 0 : 1;
+    }
+    if (tid == 0) s_matches = 0;
+    const bool factor = th != 1.0f;
+    auto radius = [&](const orbm_map_point_view_t& mp) {
+        // RadiusByViewingCos (:132-138) compares the float with the double literal 0.998
+        float r = (double)mp.view_cos > 0.998 ? 2.5f : 4.0f;
+        if (factor) r = __fmul_rn(r, th);
+        return r;
+    };
+    while (true) {
+        __syncthreads();
+        for (int f = tid; f < n_f; f += 1024) s_claim[f] = 0x7fffffff;
+        if (tid == 0) s_left = 0;
+        __syncthreads();
+        for (int i = tid; i < n_mp; i += 1024) {
+            if (resolved[i]) continue;
+            const orbm_map_point_view_t mp = mps[i];
+            const float r = radius(mp);
+            for_features_in_area(kps, cell_ptr, cell_idx, g, mp.proj_x, mp.proj_y, __fmul_rn(r, scale_factors[mp.level]), mp.level - 1, mp.level,
+                                 [&](int idx) { atomicMin(&s_claim[idx], i); return true; });
+        }
+        __syncthreads();
+        for (int i = tid; i < n_mp; i += 1024) {
+            if (resolved[i]) continue;
+            const orbm_map_point_view_t mp = mps[i];
+            const float r = radius(mp);
+            const float win = __fmul_rn(r, scale_factors[mp.level]);
+            bool safe = true;
+            for_features_in_area(kps, cell_ptr, cell_idx, g, mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level,
+                                 [&](int idx) { safe = s_claim[idx] >= i; return safe; });
+            if (!safe) { atomicAdd(&s_left, 1); continue; }
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            const uint32_t* dmp = desc_mp + (size_t)i * 8;
+            for_features_in_area(kps, cell_ptr, cell_idx, g, mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level, [&](int idx) {
+                if (s_blocked[idx]) return true;
+                if (u_right[idx] > 0) {
+                    const float er = fabsf(__fsub_rn(mp.proj_xr, u_right[idx]));
+                    if (er > win) return true;
+                }
+                const int dist = hamming32(dmp, desc_f + (size_t)idx * 8);
+                if (dist < bestDist) {
+                    bestDist2 = bestDist; bestDist = dist;
+                    bestLevel2 = bestLevel; bestLevel = kps[idx].octave;
+                    bestIdx = idx;
+                } else if (dist < bestDist2) {
+                    bestLevel2 = kps[idx].octave;
+                    bestDist2 = dist;
+                }
+                return true;
+            });
+            resolved[i] = 1;
+            if (bestDist <= th_high) {
+                if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
+                out_feature_point[bestIdx] = i;
+                s_blocked[bestIdx] = mp.obs_positive ? 1 : 0;
+                out_point_feature[i] = bestIdx;
+                atomicAdd(&s_matches, 1);
+            }
+        }
+        __syncthreads();
+        if (s_left == 0) break;
+    }
+    if (tid == 0) *out_nmatches = s_matches;
+}
+
+static bool make_undistort_params(const float* K, const float* dist, int ndist, UndistortParams* p) {
+    if (!K || !dist || ndist < 4 || ndist > 12) return false;
+    p->fx = K[0]; p->fy = K[1]; p->cx = K[2]; p->cy = K[3];
+    p->ifx = 1. / p->fx; p->ify = 1. / p->fy;
+    for (int i = 0; i < 12; i++) p->k[i] = i < ndist ? (double)dist[i] : 0.0;
+    p->identity = dist[0] == 0.0f;
+    return true;
+}
+
+static GridParams make_grid_params(const float* bounds) {
+    GridParams g;
+    g.minx = bounds[0]; g.miny = bounds[2];
+    g.winv = (float)kGridCols / (float)(bounds[1] - bounds[0]);      // Frame.cc:216
+    g.hinv = (float)kGridRows / (float)(bounds[3] - bounds[2]);      // :217
+    return g;
+}
+
+}  // namespace orbcuda
+
+using namespace orbcuda;
+
+extern "C" {
+
+int orbf_undistort_keypoints(const orb_keypoint_t* kps, int n, const float* K, const float* dist, int ndist, orb_keypoint_t* out, int device) {
+    UndistortParams p;
+    if (n < 0 || (n && (!kps || !out)) || !make_undistort_params(K, dist, ndist, &p)) { set_error("orbf_undistort_keypoints: bad arguments (K = fx,fy,cx,cy; 4..12 distortion coefficients)"); return ORB_ERR_ARG; }
+    if (n == 0) return ORB_OK;
+    MatchCtx& cx = match_ctx();
+    const size_t bytes = (size_t)n * sizeof(orb_keypoint_t);
+    if (!cx.begin(device, 2 * bytes + 1024, 2 * bytes + 1024)) return ORB_ERR_CUDA;
+    const orb_keypoint_t* d_in = (const orb_keypoint_t*)cx.upload(kps, bytes);
+    orb_keypoint_t* d_out = (orb_keypoint_t*)cx.dalloc(bytes);
+    if (!d_in || !d_out) return ORB_ERR_CUDA;
+    undistort_kernel<<<(n + 255) / 256, 256, 0, cx.stream>>>(d_in, n, p, d_out);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (!cx.download(out, d_out, bytes) || !cx.finish()) return ORB_ERR_CUDA;
+    return ORB_OK;
+}
+
+int orbf_image_bounds(int cols, int rows, const float* K, const float* dist, int ndist, float* bounds, int device) {
+    if (!bounds || cols <= 0 || rows <= 0 || !dist) { set_error("orbf_image_bounds: bad arguments"); return ORB_ERR_ARG; }
+    if (dist[0] == 0.0f) {      // Frame.cc:463-468
+        bounds[0] = 0.f; bounds[1] = (float)cols; bounds[2] = 0.f; bounds[3] = (float)rows;
+        return ORB_OK;
+    }
+    orb_keypoint_t c[4] = {}, u[4];
+    c[1].x = (float)cols; c[2].y = (float)rows; c[3].x = (float)cols; c[3].y = (float)rows;
+    const int rc = orbf_undistort_keypoints(c, 4, K, dist, ndist, u, device);
+    if (rc) return rc;
+    bounds[0] = std::min(u[0].x, u[2].x);      // :456-459
+    bounds[1] = std::max(u[1].x, u[3].x);
+    bounds[2] = std::min(u[0].y, u[1].y);
+    bounds[3] = std::max(u[2].y, u[3].y);
+    return ORB_OK;
+}
+
+int orbf_assign_grid(const orb_keypoint_t* kps_un, int n, const float* bounds, int32_t* cell_ptr, int32_t* cell_idx, int* n_assigned, int device) {
+    if (n < 0 || n > kFrameMaxFeatures || !bounds || !cell_ptr || (n && (!kps_un || !cell_idx))) { set_error("orbf_assign_grid: bad arguments (at most %d key points)", kFrameMaxFeatures); return ORB_ERR_ARG; }
+    MatchCtx& cx = match_ctx();
+    const size_t kb = (size_t)std::max(n, 1) * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4, ib = (size_t)std::max(n, 1) * 4;
+    if (!cx.begin(device, kb + pb + ib + 2048, kb + pb + ib + 2048)) return ORB_ERR_CUDA;
+    const orb_keypoint_t* d_k = (const orb_keypoint_t*)cx.upload(kps_un, (size_t)n * sizeof(orb_keypoint_t));
+    int* d_ptr = (int*)cx.dalloc(pb);
+    int* d_idx = (int*)cx.dalloc(ib);
+    if ((n && !d_k) || !d_ptr || !d_idx) return ORB_ERR_CUDA;
+    const size_t smem = (size_t)(kGridCells + 1) * 4 + (size_t)n * 2 + 16;
+    static bool configured = false;
+    if (!configured) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16));
+        configured = true;
+    }
+    grid_kernel<<<1, 1024, smem, cx.stream>>>(d_k, n, make_grid_params(bounds), d_ptr, d_idx);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (!cx.download(cell_ptr, d_ptr, pb)) return ORB_ERR_CUDA;
+    if (n && !cx.download(cell_idx, d_idx, (size_t)n * 4)) return ORB_ERR_CUDA;
+    if (!cx.finish()) return ORB_ERR_CUDA;
+    if (n_assigned) *n_assigned = cell_ptr[kGridCells];
+    return ORB_OK;
+}
+
+int orbf_features_in_area(const orb_keypoint_t* kps_un, int n, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                          const float* qx, const float* qy, const float* qr, const int32_t* min_level, const int32_t* max_level, int nq,
+                          int32_t* out_ptr, int32_t* out_idx, int cap, int device) {
+    if (n < 0 || nq < 0 || cap < 0 || !bounds || !cell_ptr || !out_ptr || (cap && !out_idx) || (nq && (!qx || !qy || !qr || !min_level || !max_level)) ||
+        (n && (!kps_un || !cell_idx))) { set_error("orbf_features_in_area: bad arguments"); return ORB_ERR_ARG; }
+    if (nq == 0) { out_ptr[0] = 0; return ORB_OK; }
+    MatchCtx& cx = match_ctx();
+    const size_t kb = (size_t)std::max(n, 1) * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4, ib = (size_t)std::max(n, 1) * 4;
+    const size_t qb = (size_t)nq * 4, ob = (size_t)std::max(cap, 1) * 4;
+    const size_t need = kb + pb + ib + 7 * qb + 4 + ob + 16 * 256;
+    if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
+    const orb_keypoint_t* d_k = (const orb_keypoint_t*)cx.upload(kps_un, (size_t)n * sizeof(orb_keypoint_t));
+    const int* d_cp = (const int*)cx.upload(cell_ptr, pb);
+    const int* d_ci = (const int*)cx.upload(cell_idx, (size_t)n * 4);
+    const float* d_qx = (const float*)cx.upload(qx, qb); const float* d_qy = (const float*)cx.upload(qy, qb);
+    const float* d_qr = (const float*)cx.upload(qr, qb);
+    const int* d_mn = (const int*)cx.upload(min_level, qb); const int* d_mx = (const int*)cx.upload(max_level, qb);
+    int* d_cnt = (int*)cx.dalloc(qb); int* d_ptr = (int*)cx.dalloc(qb + 4); int* d_out = (int*)cx.dalloc(ob);
+    if ((n && (!d_k || !d_ci)) || !d_cp || !d_qx || !d_qy || !d_qr || !d_mn || !d_mx || !d_cnt || !d_ptr || !d_out) return ORB_ERR_CUDA;
+    const GridParams g = make_grid_params(bounds);
+    area_count_kernel<<<(nq + 127) / 128, 128, 0, cx.stream>>>(d_k, d_cp, d_ci, g, d_qx, d_qy, d_qr, d_mn, d_mx, nq, d_cnt);
+    scan_kernel<<<1, 1024, 0, cx.stream>>>(d_cnt, nq, d_ptr);
+    area_fill_kernel<<<(nq + 127) / 128, 128, 0, cx.stream>>>(d_k, d_cp, d_ci, g, d_qx, d_qy, d_qr, d_mn, d_mx, nq, d_ptr, d_out, cap);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (!cx.download(out_ptr, d_ptr, qb + 4)) return ORB_ERR_CUDA;
+    if (cap && !cx.download(out_idx, d_out, ob)) return ORB_ERR_CUDA;
+    if (!cx.finish()) return ORB_ERR_CUDA;
+    if (out_ptr[nq] > cap) { set_error("orbf_features_in_area: %d indices, capacity %d (out_ptr is complete, out_idx truncated)", out_ptr[nq], cap); return ORB_ERR_CAPACITY; }
+    return ORB_OK;
+}
+
+int orbm_search_by_projection_frame(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right, const uint8_t* occupied, int n_f,
+                                    const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* scale_factors, int n_levels,
+                                    const orbm_map_point_view_t* mps, const uint8_t* desc_mp, int n_mp, float th, float nnratio, int th_high,
+                                    int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device) {
+    if (n_f < 0 || n_f > kFrameMaxFeatures || n_mp < 0 || n_levels <= 0 || !bounds || !cell_ptr || !scale_factors || !n_matches ||
+        (n_f && (!kps_un || !desc_f || !u_right || !occupied || !cell_idx || !out_feature_point)) || (n_mp && (!mps || !desc_mp || !out_point_feature))) {
+        set_error("orbm_search_by_projection_frame: bad arguments (at most %d frame features)", kFrameMaxFeatures);
+        return ORB_ERR_ARG;
+    }
+    for (int i = 0; i < n_mp; i++)
+        if (mps[i].in_view && (mps[i].level < 0 || mps[i].level >= n_levels)) { set_error("orbm_search_by_projection_frame: map point %d predicts level %d of %d", i, mps[i].level, n_levels); return ORB_ERR_ARG; }
+    *n_matches = 0;
+    for (int f = 0; f < n_f; f++) out_feature_point[f] = -1;
+    for (int i = 0; i < n_mp; i++) out_point_feature[i] = -1;
+    if (n_f == 0 || n_mp == 0) return ORB_OK;
+    MatchCtx& cx = match_ctx();
+    const size_t kb = (size_t)n_f * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4;
+    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4) + pb + (size_t)n_levels * 4 + (size_t)n_mp * (sizeof(orbm_map_point_view_t) + 32 + 4 + 1) + 4 + 20 * 256;
+    if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
+    const orb_keypoint_t* d_k = (const orb_keypoint_t*)cx.upload(kps_un, kb);
+    const uint32_t* d_df = (const uint32_t*)cx.upload(desc_f, (size_t)n_f * 32);
+    const float* d_ur = (const float*)cx.upload(u_right, (size_t)n_f * 4);
+    const uint8_t* d_occ = (const uint8_t*)cx.upload(occupied, (size_t)n_f);
+    const int* d_cp = (const int*)cx.upload(cell_ptr, pb);
+    const int* d_ci = (const int*)cx.upload(cell_idx, (size_t)n_f * 4);
+    const float* d_sf = (const float*)cx.upload(scale_factors, (size_t)n_levels * 4);
+    const orbm_map_point_view_t* d_mp = (const orbm_map_point_view_t*)cx.upload(mps, (size_t)n_mp * sizeof(orbm_map_point_view_t));
+    const uint32_t* d_dm = (const uint32_t*)cx.upload(desc_mp, (size_t)n_mp * 32);
+    int* d_fp = (int*)cx.dalloc((size_t)n_f * 4); int* d_pf = (int*)cx.dalloc((size_t)n_mp * 4);
+    uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_mp); int* d_nm = (int*)cx.dalloc(4);
+    if (!d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_sf || !d_mp || !d_dm || !d_fp || !d_pf || !d_res || !d_nm) return ORB_ERR_CUDA;
+    static bool configured = false;
+    if (!configured) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 5 + 16));
+        configured = true;
+    }
+    projection_kernel<<<1, 1024, (size_t)n_f * 5 + 16, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, make_grid_params(bounds), d_sf, d_mp, d_dm, n_mp,
+                                                                    th, nnratio, th_high, d_fp, d_pf, d_res, d_nm);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (!cx.download(out_feature_point, d_fp, (size_t)n_f * 4) || !cx.download(out_point_feature, d_pf, (size_t)n_mp * 4) ||
+        !cx.download(n_matches, d_nm, 4) || !cx.finish()) return ORB_ERR_CUDA;
+    return ORB_OK;
+}
+
+}  // extern "C"

@@ -222,6 +222,53 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
                         const uint8_t* desc_right, int n_right, float mbf, float mb, float* u_right,
                         float* depth, int* n_matches);
 
+/* ---------------------------------------------------------------- frame (the steps after extraction) ---- */
+#define ORBF_GRID_COLS 64   /* FRAME_GRID_COLS, R21/include/Frame.h:37 */
+#define ORBF_GRID_ROWS 48   /* FRAME_GRID_ROWS, R21/include/Frame.h:36 */
+
+/* void Frame::UndistortKeyPoints()  R21/src/Frame.cc:409-439: cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK)
+ * on the key point coordinates (5 fixed-point iterations in double), everything else of the key point copied; a
+ * plain copy when dist[0] == 0 (:411-415).  K = (fx, fy, cx, cy) as in mK (CV_32F), dist = mDistCoef (k1, k2, p1, p2[, k3]). */
+int orbf_undistort_keypoints(const orb_keypoint_t* kps, int n, const float* K, const float* dist, int ndist,
+                             orb_keypoint_t* out, int device);
+/* void Frame::ComputeImageBounds(const cv::Mat& imLeft)  R21/src/Frame.cc:441-470.
+ * bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY). */
+int orbf_image_bounds(int cols, int rows, const float* K, const float* dist, int ndist, float* bounds, int device);
+/* void Frame::AssignFeaturesToGrid()  R21/src/Frame.cc:235-250 with PosInGrid :387-397 (round, not floor).  The
+ * grid is returned as CSR over the cells in mGrid[ix][iy] order (cell = ix * 48 + iy): cell_ptr[64*48 + 1],
+ * cell_idx[n]; indices ascend inside a cell (push_back order).  *n_assigned = key points inside the grid. */
+int orbf_assign_grid(const orb_keypoint_t* kps_un, int n, const float* bounds, int32_t* cell_ptr, int32_t* cell_idx,
+                     int* n_assigned, int device);
+/* vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel)  R21/src/Frame.cc:332-385, for nq windows
+ * at once.  Query q owns out_idx[out_ptr[q] .. out_ptr[q+1]) in the reference's order (cells ix-major, then the
+ * cell's push_back order).  ORB_ERR_CAPACITY when the total exceeds cap (out_ptr is still complete). */
+int orbf_features_in_area(const orb_keypoint_t* kps_un, int n, const int32_t* cell_ptr, const int32_t* cell_idx,
+                          const float* bounds, const float* qx, const float* qy, const float* qr,
+                          const int32_t* min_level, const int32_t* max_level, int nq, int32_t* out_ptr,
+                          int32_t* out_idx, int cap, int device);
+
+/* What Frame::isInFrustum (R21/src/Frame.cc:262-330) leaves on a MapPoint for the projection search. */
+typedef struct {
+    float proj_x, proj_y, proj_xr;   /* mTrackProjX, mTrackProjY, mTrackProjXR */
+    float view_cos;                  /* mTrackViewCos */
+    int32_t level;                   /* mnTrackScaleLevel */
+    int32_t in_view;                 /* mbTrackInView && !isBad()  (:52-56) */
+    int32_t obs_positive;            /* Observations() > 0, read when a later point meets the feature this one took (:82-84) */
+} orbm_map_point_view_t;
+
+/* int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th)
+ * R21/src/ORBmatcher.cc:45-130 (Tracking::SearchLocalPoints).  Frame side: undistorted key points, descriptors,
+ * mvuRight, occupied[idx] = (F.mvpMapPoints[idx] && Observations() > 0) on entry, the grid of orbf_assign_grid,
+ * F.mvScaleFactors.  th_high = ORBmatcher::TH_HIGH (100).  out_feature_point[idx] = index of the map point this
+ * call left in F.mvpMapPoints[idx] (-1: untouched); out_point_feature[i] = feature taken by point i or -1;
+ * *n_matches = return value.  The order dependence of the reference loop is reproduced exactly. */
+int orbm_search_by_projection_frame(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right,
+                                    const uint8_t* occupied, int n_f, const int32_t* cell_ptr,
+                                    const int32_t* cell_idx, const float* bounds, const float* scale_factors,
+                                    int n_levels, const orbm_map_point_view_t* mps, const uint8_t* desc_mp, int n_mp,
+                                    float th, float nnratio, int th_high, int32_t* out_feature_point,
+                                    int32_t* out_point_feature, int* n_matches, int device);
+
 #ifdef __cplusplus
 }
 #endif

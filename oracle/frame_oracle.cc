@@ -1,0 +1,200 @@
+/*
+ * frame_oracle.cc -- CPU ORACLE (TEST INFRASTRUCTURE ONLY), part of liborb_oracle.so.
+ *
+ * Restatement of the steps right after extraction and of the projection search that consumes them
+ * (SURVEY.md 8f rows 3 and 1):
+ *   R21/src/Frame.cc:409-439  Frame::UndistortKeyPoints      (cv::undistortPoints, R = I, P = K)
+ *   R21/src/Frame.cc:441-470  Frame::ComputeImageBounds
+ *   R21/src/Frame.cc:235-250  Frame::AssignFeaturesToGrid  + :387-397 Frame::PosInGrid
+ *   R21/src/Frame.cc:332-385  Frame::GetFeaturesInArea
+ *   R21/src/ORBmatcher.cc:45-130  ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th)
+ * cv::undistortPoints lives in OpenCV (not vendored by the reference); its published algorithm
+ * (calib3d undistort: 5 fixed-point iterations in double, no tilt, P*R folded into one matrix) is restated here
+ * and PINNED against cv2 4.13.0 by tests/golden/undistort_*.npz (made by tools/gen_golden_frame.py).
+ * The grid / area / projection loops need Frame/MapPoint objects and cannot be compiled from the reference:
+ * "parity unpinned" beyond the cv2-pinned arithmetic; they follow the cited lines statement by statement.
+ */
+#include "orb_oracle.h"
+
+#include <math.h>
+#include <algorithm>
+#include <vector>
+
+extern "C" {
+
+/* cv::undistortPoints(src, dst, K, D, noArray(), K): K = (fx, fy, cx, cy) as float (mK is CV_32F), D = ndist floats
+ * (k1, k2, p1, p2[, k3]); all arithmetic in double exactly as OpenCV orders it. */
+void orc_undistort_points(const float* xy, int n, const float* K, const float* dist, int ndist, float* out) {
+    double k[14] = {0};
+    for (int i = 0; i < ndist && i < 14; i++) k[i] = (double)dist[i];
+    const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; i++) {
+        double x = xy[2 * i], y = xy[2 * i + 1];
+        const double u = x, v = y;
+        x = (x - cx) * ifx;
+        y = (y - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) {
+                x = (u - cx) * ifx;
+                y = (v - cy) * ify;
+                break;
+            }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        // RR = P * I (a double GEMM: products with 0/1 and sums with 0 are exact)
+        const double xx = fx * x + 0. * y + cx;
+        const double yy = 0. * x + fy * y + cy;
+        const double ww = 1. / (0. * x + 0. * y + 1.);
+        out[2 * i] = (float)(xx * ww);
+        out[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+/* Frame::UndistortKeyPoints: copies everything but pt (:412-416 when k1 == 0, else :419-438). */
+void orc_undistort_keypoints(const orc_keypoint* kps, int n, const float* K, const float* dist, int ndist, orc_keypoint* out) {
+    if (dist[0] == 0.0f) {
+        for (int i = 0; i < n; i++) out[i] = kps[i];
+        return;
+    }
+    std::vector<float> xy(2 * (size_t)n), un(2 * (size_t)n);
+    for (int i = 0; i < n; i++) { xy[2 * i] = kps[i].x; xy[2 * i + 1] = kps[i].y; }
+    orc_undistort_points(xy.data(), n, K, dist, ndist, un.data());
+    for (int i = 0; i < n; i++) { out[i] = kps[i]; out[i].x = un[2 * i]; out[i].y = un[2 * i + 1]; }
+}
+
+/* Frame::ComputeImageBounds :441-470 -> bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY) */
+void orc_image_bounds(int cols, int rows, const float* K, const float* dist, int ndist, float* bounds) {
+    if (dist[0] != 0.0f) {
+        const float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+        float u[8];
+        orc_undistort_points(c, 4, K, dist, ndist, u);
+        bounds[0] = std::min(u[0], u[4]);
+        bounds[1] = std::max(u[2], u[6]);
+        bounds[2] = std::min(u[1], u[3]);
+        bounds[3] = std::max(u[5], u[7]);
+    } else {
+        bounds[0] = 0.f; bounds[1] = (float)cols; bounds[2] = 0.f; bounds[3] = (float)rows;
+    }
+}
+
+enum { kGridCols = 64, kGridRows = 48 };   /* FRAME_GRID_COLS / FRAME_GRID_ROWS, R21/include/Frame.h:36-37 */
+
+/* Frame::AssignFeaturesToGrid :235-250 with PosInGrid :387-397.  The grid comes back as CSR over cells in the
+ * reference's mGrid[ix][iy] order (cell = ix * 48 + iy); within a cell indices ascend (push_back order). */
+void orc_assign_grid(const orc_keypoint* kps_un, int n, const float* bounds, int32_t* cell_ptr, int32_t* cell_idx) {
+    const float winv = (float)kGridCols / (float)(bounds[1] - bounds[0]);   /* Frame.cc:216 */
+    const float hinv = (float)kGridRows / (float)(bounds[3] - bounds[2]);   /* :217 */
+    std::vector<std::vector<int32_t> > grid(kGridCols * kGridRows);
+    for (int i = 0; i < n; i++) {
+        const int px = (int)round((kps_un[i].x - bounds[0]) * winv);
+        const int py = (int)round((kps_un[i].y - bounds[2]) * hinv);
+        if (px < 0 || px >= kGridCols || py < 0 || py >= kGridRows) continue;
+        grid[px * kGridRows + py].push_back(i);
+    }
+    int32_t at = 0;
+    for (int c = 0; c < kGridCols * kGridRows; c++) {
+        cell_ptr[c] = at;
+        for (int32_t i : grid[c]) cell_idx[at++] = i;
+    }
+    cell_ptr[kGridCols * kGridRows] = at;
+}
+
+/* Frame::GetFeaturesInArea :332-385.  Returns the number of indices (writes at most cap). */
+int orc_features_in_area(const orc_keypoint* kps_un, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                         float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
+    const float winv = (float)kGridCols / (float)(bounds[1] - bounds[0]);
+    const float hinv = (float)kGridRows / (float)(bounds[3] - bounds[2]);
+    const float minx = bounds[0], miny = bounds[2];
+    int n = 0;
+    const int nMinCellX = std::max(0, (int)floor((x - minx - r) * winv));
+    if (nMinCellX >= kGridCols) return 0;
+    const int nMaxCellX = std::min((int)kGridCols - 1, (int)ceil((x - minx + r) * winv));
+    if (nMaxCellX < 0) return 0;
+    const int nMinCellY = std::max(0, (int)floor((y - miny - r) * hinv));
+    if (nMinCellY >= kGridRows) return 0;
+    const int nMaxCellY = std::min((int)kGridRows - 1, (int)ceil((y - miny + r) * hinv));
+    if (nMaxCellY < 0) return 0;
+    const bool bCheckLevels = (min_level > 0) || (max_level >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const int c = ix * kGridRows + iy;
+            for (int32_t j = cell_ptr[c]; j < cell_ptr[c + 1]; j++) {
+                const orc_keypoint& kp = kps_un[cell_idx[j]];
+                if (bCheckLevels) {
+                    if (kp.octave < min_level) continue;
+                    if (max_level >= 0 && kp.octave > max_level) continue;
+                }
+                const float distx = kp.x - x, disty = kp.y - y;
+                if (fabsf(distx) < r && fabsf(disty) < r) {
+                    if (n < cap) out[n] = cell_idx[j];
+                    n++;
+                }
+            }
+        }
+    return n;
+}
+
+/* ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th) :45-130.
+ * Per map point (the fields Frame::isInFrustum leaves on it, Frame.cc:262-330): in_view (mbTrackInView && !isBad()),
+ * proj_x/proj_y/proj_xr (mTrackProjX/Y/XR), level (mnTrackScaleLevel), view_cos (mTrackViewCos), descriptor, and
+ * obs_positive (Observations() > 0, read when a LATER point meets the feature this one took, :82-84).
+ * Per frame feature: undistorted key point, descriptor, u_right (mvuRight), occupied (mvpMapPoints[idx] &&
+ * Observations() > 0 on entry).  out_feature_point[idx] = index of the map point left in F.mvpMapPoints[idx] by this
+ * call (-1: untouched); out_point_feature[i] = feature matched by point i or -1.  Returns nmatches. */
+int orc_search_by_projection_frame(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right,
+                                   const uint8_t* occupied, int n_f, const int32_t* cell_ptr, const int32_t* cell_idx,
+                                   const float* bounds, const float* scale_factors, const orc_map_point_view* mps,
+                                   const uint8_t* desc_mp, int n_mp, float th, float nnratio, int th_high,
+                                   int32_t* out_feature_point, int32_t* out_point_feature) {
+    std::vector<uint8_t> blocked(occupied, occupied + n_f);
+    for (int i = 0; i < n_f; i++) out_feature_point[i] = -1;
+    std::vector<int32_t> cand((size_t)std::max(n_f, 1));
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    for (int i = 0; i < n_mp; i++) {
+        out_point_feature[i] = -1;
+        const orc_map_point_view& mp = mps[i];
+        if (!mp.in_view) continue;
+        const int lvl = mp.level;
+        float r = mp.view_cos > 0.998 ? 2.5 : 4.0;      /* RadiusByViewingCos :132-138 */
+        if (bFactor) r *= th;
+        const int nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, mp.proj_x, mp.proj_y, r * scale_factors[lvl],
+                                            lvl - 1, lvl, cand.data(), n_f);
+        if (nc == 0) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = cand[c];
+            if (blocked[idx]) continue;
+            if (u_right[idx] > 0) {
+                const float er = fabsf(mp.proj_xr - u_right[idx]);
+                if (er > r * scale_factors[lvl]) continue;
+            }
+            const int dist = orc_descriptor_distance(desc_mp + (size_t)i * 32, desc_f + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = kps_un[idx].octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kps_un[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= th_high) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            out_feature_point[bestIdx] = i;              /* F.mvpMapPoints[bestIdx] = pMP */
+            blocked[bestIdx] = mp.obs_positive ? 1 : 0;   /* what :82-84 will see for later points */
+            out_point_feature[i] = bestIdx;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+}  // extern "C"

@@ -159,6 +159,34 @@ int orc_stereo_matches(const orc_keypoint* kl, const uint8_t* dl, int nl, const 
                        const uint8_t* const* pyr_r, const int* lvl_w, const int* lvl_h,
                        const size_t* strides, float mbf, float mb, float* u_right, float* depth);
 
+/* ---- frame side (oracle/frame_oracle.cc): the steps right after extraction + the projection search ---- */
+/* cv::undistortPoints(src, dst, K, D, noArray(), K) as Frame.cc:428 calls it; K = (fx, fy, cx, cy). */
+void orc_undistort_points(const float* xy, int n, const float* K, const float* dist, int ndist, float* out);
+/* Frame::UndistortKeyPoints (R21/src/Frame.cc:409-439) */
+void orc_undistort_keypoints(const orc_keypoint* kps, int n, const float* K, const float* dist, int ndist, orc_keypoint* out);
+/* Frame::ComputeImageBounds (:441-470): bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY) */
+void orc_image_bounds(int cols, int rows, const float* K, const float* dist, int ndist, float* bounds);
+/* Frame::AssignFeaturesToGrid (:235-250): CSR over the 64 x 48 cells, cell = ix * 48 + iy; cell_ptr[3073], cell_idx[n] */
+void orc_assign_grid(const orc_keypoint* kps_un, int n, const float* bounds, int32_t* cell_ptr, int32_t* cell_idx);
+/* Frame::GetFeaturesInArea (:332-385) */
+int orc_features_in_area(const orc_keypoint* kps_un, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                         float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
+
+typedef struct {
+    float proj_x, proj_y, proj_xr;   /* mTrackProjX, mTrackProjY, mTrackProjXR */
+    float view_cos;                  /* mTrackViewCos */
+    int32_t level;                   /* mnTrackScaleLevel */
+    int32_t in_view;                 /* mbTrackInView && !isBad() */
+    int32_t obs_positive;            /* Observations() > 0 */
+} orc_map_point_view;
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (R21/src/ORBmatcher.cc:45-130) */
+int orc_search_by_projection_frame(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right,
+                                   const uint8_t* occupied, int n_f, const int32_t* cell_ptr, const int32_t* cell_idx,
+                                   const float* bounds, const float* scale_factors, const orc_map_point_view* mps,
+                                   const uint8_t* desc_mp, int n_mp, float th, float nnratio, int th_high,
+                                   int32_t* out_feature_point, int32_t* out_point_feature);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,3 +331,63 @@ def distinctive_descriptors(desc, ptr):
     L.orc_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.orc_distinctive_descriptors(_p(d), _p(p), len(p) - 1, _p(best))
     return best
+
+
+# ----------------------------------------------------------------------------- frame side (oracle/frame_oracle.cc)
+MPV_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
+                      ("in_view", "<i4"), ("obs_positive", "<i4")])
+GRID_CELLS = 64 * 48
+
+
+def undistort_points(xy, K, dist):
+    xy = np.ascontiguousarray(xy, np.float32); K = np.ascontiguousarray(K, np.float32); d = np.ascontiguousarray(dist, np.float32)
+    out = np.zeros_like(xy)
+    lib().orc_undistort_points(_p(xy), C.c_int(len(xy)), _p(K), _p(d), C.c_int(len(d)), _p(out))
+    return out
+
+
+def undistort_keypoints(kps, K, dist):
+    kps = np.ascontiguousarray(kps, KP_DTYPE); K = np.ascontiguousarray(K, np.float32); d = np.ascontiguousarray(dist, np.float32)
+    out = np.zeros_like(kps)
+    lib().orc_undistort_keypoints(_p(kps), C.c_int(len(kps)), _p(K), _p(d), C.c_int(len(d)), _p(out))
+    return out
+
+
+def image_bounds(cols, rows, K, dist):
+    K = np.ascontiguousarray(K, np.float32); d = np.ascontiguousarray(dist, np.float32)
+    b = np.zeros(4, np.float32)
+    lib().orc_image_bounds(C.c_int(cols), C.c_int(rows), _p(K), _p(d), C.c_int(len(d)), _p(b))
+    return b
+
+
+def assign_grid(kps_un, bounds):
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE); b = np.ascontiguousarray(bounds, np.float32)
+    ptr = np.zeros(GRID_CELLS + 1, np.int32); idx = np.zeros(max(len(kps_un), 1), np.int32)
+    lib().orc_assign_grid(_p(kps_un), C.c_int(len(kps_un)), _p(b), _p(ptr), _p(idx))
+    return ptr, idx
+
+
+def features_in_area(kps_un, ptr, idx, bounds, x, y, r, min_level, max_level):
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE); b = np.ascontiguousarray(bounds, np.float32)
+    out = np.zeros(max(len(kps_un), 1), np.int32)
+    L = lib()
+    L.orc_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_int]
+    n = L.orc_features_in_area(_p(kps_un), _p(ptr), _p(idx), _p(b), x, y, r, min_level, max_level, _p(out), len(out))
+    return out[:n].copy()
+
+
+def search_by_projection_frame(kps_un, desc_f, u_right, occupied, ptr, idx, bounds, scale_factors, mps, desc_mp, th, nnratio,
+                               th_high=100):
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE); df = np.ascontiguousarray(desc_f, np.uint8)
+    ur = np.ascontiguousarray(u_right, np.float32); occ = np.ascontiguousarray(occupied, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    mps = np.ascontiguousarray(mps, MPV_DTYPE); dm = np.ascontiguousarray(desc_mp, np.uint8)
+    fp = np.zeros(max(len(kps_un), 1), np.int32); pf = np.zeros(max(len(mps), 1), np.int32)
+    L = lib()
+    L.orc_search_by_projection_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                                 C.c_int, C.c_void_p, C.c_void_p]
+    n = L.orc_search_by_projection_frame(_p(kps_un), _p(df), _p(ur), _p(occ), len(kps_un), _p(ptr), _p(idx), _p(b), _p(sf), _p(mps),
+                                         _p(dm), len(mps), th, nnratio, th_high, _p(fp), _p(pf))
+    return fp[:len(kps_un)], pf[:len(mps)], n

@@ -1,0 +1,209 @@
+"""Frame-side steps (undistortion, image bounds, 64x48 grid, GetFeaturesInArea) and the projection search that consumes
+them.  CPU part: the oracle against cv2 golden vectors and against brute-force properties.
+GPU part (-m gpu): the CUDA path against the oracle, bit for bit."""
+import os
+import numpy as np
+import pytest
+
+CALS = ("tum1", "tum2", "four", "barrel")
+
+
+def _golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "undistort_cv2.npz"))
+
+
+def _keys(oracle, n, seed, w=640, h=480, nlevels=8):
+    rng = np.random.default_rng(seed)
+    k = np.zeros(n, oracle.KP_DTYPE)
+    lvl = rng.integers(0, nlevels, n)
+    s = 1.2 ** lvl
+    # extractor-like coordinates: integers at the level, scaled up to level 0
+    k["x"] = (rng.integers(16, (w / s - 16).astype(int).clip(17)) * s).astype(np.float32)
+    k["y"] = (rng.integers(16, (h / s - 16).astype(int).clip(17)) * s).astype(np.float32)
+    k["size"] = (31 * s).astype(np.float32); k["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    k["response"] = rng.integers(7, 200, n).astype(np.float32); k["octave"] = lvl; k["class_id"] = -1
+    return k
+
+
+def _scene(oracle, synth, nf, nmp, seed, K, dist, crowded=False):
+    """A frame with nf features and nmp projected map points around (some of) them."""
+    rng = np.random.default_rng(seed)
+    keys = _keys(oracle, nf, seed)
+    if crowded:      # many points fight for the same few features: forces many dependent rounds
+        keys["x"] = (200 + rng.integers(0, 60, nf)).astype(np.float32); keys["y"] = (200 + rng.integers(0, 40, nf)).astype(np.float32)
+    desc_f = synth.descriptors(nf, seed=seed + 1)
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    return keys, desc_f, sf, rng
+
+
+def _map_points(oracle, keys_un, desc_f, nmp, rng, noise_bits=20):
+    nf = len(keys_un)
+    mp = np.zeros(nmp, oracle.MPV_DTYPE)
+    src = rng.integers(0, nf, nmp)
+    mp["proj_x"] = keys_un["x"][src] + rng.normal(0, 2.0, nmp).astype(np.float32)
+    mp["proj_y"] = keys_un["y"][src] + rng.normal(0, 2.0, nmp).astype(np.float32)
+    mp["proj_xr"] = mp["proj_x"] - rng.uniform(0, 30, nmp).astype(np.float32)
+    mp["view_cos"] = rng.choice(np.array([0.9, 0.9975, 0.998, 0.9985, 1.0], np.float32), nmp)
+    mp["level"] = np.clip(keys_un["octave"][src] + rng.integers(0, 2, nmp), 0, 7)
+    mp["in_view"] = rng.random(nmp) < 0.9
+    mp["obs_positive"] = rng.random(nmp) < 0.85
+    dm = desc_f[src].copy()
+    flips = rng.integers(0, 256, (nmp, noise_bits))
+    for i in range(nmp):
+        for b in flips[i][: rng.integers(0, noise_bits + 1)]:
+            dm[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    far = rng.random(nmp) < 0.1      # some points look like nothing in the frame
+    dm[far] = rng.integers(0, 256, (int(far.sum()), 32), dtype=np.uint8)
+    return mp, dm
+
+
+# ------------------------------------------------------------------------------------------------ CPU: oracle
+@pytest.mark.parametrize("cal", CALS)
+def test_oracle_undistort_matches_cv2_golden(oracle, golden_dir, cal):
+    g = _golden(golden_dir)
+    out = oracle.undistort_points(g[cal + "_pts"], g[cal + "_K"], g[cal + "_D"])
+    assert np.array_equal(out.view(np.uint32), g[cal + "_und"].view(np.uint32))      # bit-exact with cv2 4.13.0
+
+
+def test_oracle_undistort_identity_and_bounds(oracle, golden_dir):
+    g = _golden(golden_dir)
+    k = _keys(oracle, 500, 3)
+    K = g["tum1_K"]
+    same = oracle.undistort_keypoints(k, K, np.zeros(5, np.float32))
+    assert same.tobytes() == k.tobytes()
+    assert np.array_equal(oracle.image_bounds(640, 480, K, np.zeros(4, np.float32)), np.array([0, 640, 0, 480], np.float32))
+    b = oracle.image_bounds(640, 480, K, g["tum1_D"])
+    c = oracle.undistort_points(np.array([[0, 0], [640, 0], [0, 480], [640, 480]], np.float32), K, g["tum1_D"])
+    assert b[0] == min(c[0, 0], c[2, 0]) and b[1] == max(c[1, 0], c[3, 0]) and b[2] == min(c[0, 1], c[1, 1]) and b[3] == max(c[2, 1], c[3, 1])
+    un = oracle.undistort_keypoints(k, K, g["tum1_D"])
+    for f in ("size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(un[f], k[f])
+    assert np.array_equal(np.stack([un["x"], un["y"]], 1), oracle.undistort_points(np.stack([k["x"], k["y"]], 1), K, g["tum1_D"]))
+
+
+def test_oracle_grid_and_area_properties(oracle, golden_dir):
+    g = _golden(golden_dir)
+    K, D = g["tum1_K"], g["tum1_D"]
+    k = oracle.undistort_keypoints(_keys(oracle, 3000, 5), K, D)
+    b = oracle.image_bounds(640, 480, K, D)
+    ptr, idx = oracle.assign_grid(k, b)
+    winv = np.float32(64) / np.float32(b[1] - b[0]); hinv = np.float32(48) / np.float32(b[3] - b[2])
+    px = np.round((k["x"] - b[0]) * winv).astype(int); py = np.round((k["y"] - b[2]) * hinv).astype(int)      # PosInGrid: round
+    inside = (px >= 0) & (px < 64) & (py >= 0) & (py < 48)
+    assert ptr[-1] == inside.sum() and np.all(np.diff(ptr) >= 0)
+    for c in np.flatnonzero(np.diff(ptr))[:400]:
+        members = idx[ptr[c]:ptr[c + 1]]
+        assert np.all(np.diff(members) > 0)                              # push_back order
+        assert np.all(px[members] * 48 + py[members] == c)
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        x, y, r = np.float32(rng.uniform(-20, 660)), np.float32(rng.uniform(-20, 500)), np.float32(rng.uniform(1, 40))
+        lo, hi = int(rng.integers(-1, 7)), int(rng.integers(-1, 8))
+        got = oracle.features_in_area(k, ptr, idx, b, x, y, r, lo, hi)
+        ok = (np.abs(k["x"] - x) < r) & (np.abs(k["y"] - y) < r) & inside
+        if lo > 0 or hi >= 0:
+            ok &= k["octave"] >= lo
+            if hi >= 0:
+                ok &= k["octave"] <= hi
+        assert set(got) <= set(np.flatnonzero(ok)) and len(set(got)) == len(got)
+        cells = px[got] * 48 + py[got]
+        assert np.all(np.diff(cells) >= 0)                               # ix-major, then iy, then push_back order
+
+
+def test_oracle_projection_search_is_order_dependent_greedy(oracle, synth, golden_dir):
+    g = _golden(golden_dir)
+    K, D = g["tum1_K"], g["tum1_D"]
+    keys, desc_f, sf, rng = _scene(oracle, synth, 600, 0, 11, K, D)
+    k = oracle.undistort_keypoints(keys, K, D); b = oracle.image_bounds(640, 480, K, D)
+    ptr, idx = oracle.assign_grid(k, b)
+    mp, dm = _map_points(oracle, k, desc_f, 900, rng)
+    ur = np.full(len(k), -1, np.float32); occ = np.zeros(len(k), np.uint8)
+    fp, pf, n = oracle.search_by_projection_frame(k, desc_f, ur, occ, ptr, idx, b, sf, mp, dm, 1.0, 0.8)
+    assert n == (pf >= 0).sum() > 100
+    # a feature keeps the LAST point that took it; a point with observations blocks it for the later ones
+    for f in np.flatnonzero(fp >= 0):
+        takers = np.flatnonzero(pf == f)
+        assert fp[f] == takers.max()
+        assert np.all(mp["obs_positive"][takers[:-1]] == 0)
+    assert np.all(pf[mp["in_view"] == 0] == -1)
+
+
+# ------------------------------------------------------------------------------------------------ GPU: CUDA vs oracle
+@pytest.fixture(scope="module")
+def orb():
+    import orbcuda
+    if orbcuda.device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
+    return orbcuda
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cal", CALS)
+def test_gpu_undistort_bounds_grid(orb, oracle, golden_dir, cal):
+    g = _golden(golden_dir)
+    K, D = g[cal + "_K"], g[cal + "_D"]
+    pts = g[cal + "_pts"]
+    k = np.zeros(len(pts), oracle.KP_DTYPE); k["x"] = pts[:, 0]; k["y"] = pts[:, 1]; k["octave"] = np.arange(len(pts)) % 8
+    fr = orb.FrameFeatures(k, K, D, 640, 480)
+    und = np.stack([fr.keys_un["x"], fr.keys_un["y"]], 1)
+    assert np.array_equal(und.view(np.uint32), g[cal + "_und"].view(np.uint32))          # cv2 golden, bit-exact
+    assert fr.keys_un.tobytes() == oracle.undistort_keypoints(k, K, D).tobytes()
+    assert np.array_equal(fr.bounds, oracle.image_bounds(640, 480, K, D))
+    ptr, idx = oracle.assign_grid(fr.keys_un, fr.bounds)
+    assert np.array_equal(fr.cell_ptr, ptr) and np.array_equal(fr.cell_idx[:ptr[-1]], idx[:ptr[-1]]) and fr.n_assigned == ptr[-1]
+
+
+@pytest.mark.gpu
+def test_gpu_undistort_identity_and_empty(orb, oracle, golden_dir):
+    g = _golden(golden_dir)
+    k = _keys(oracle, 777, 9)
+    fr = orb.FrameFeatures(k, g["tum1_K"], np.zeros(5, np.float32), 752, 480)
+    assert fr.keys_un.tobytes() == k.tobytes() and np.array_equal(fr.bounds, np.array([0, 752, 0, 480], np.float32))
+    ptr, idx = oracle.assign_grid(k, fr.bounds)
+    assert np.array_equal(fr.cell_ptr, ptr) and np.array_equal(fr.cell_idx[:ptr[-1]], idx[:ptr[-1]])
+    empty = orb.FrameFeatures(np.zeros(0, oracle.KP_DTYPE), g["tum1_K"], g["tum1_D"], 640, 480)
+    assert empty.n_assigned == 0 and not empty.cell_ptr.any()
+    assert len(empty.GetFeaturesInArea(100.0, 100.0, 50.0)) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_features_in_area(orb, oracle, golden_dir):
+    g = _golden(golden_dir)
+    K, D = g["tum2_K"], g["tum2_D"]
+    k = _keys(oracle, 2500, 21)
+    fr = orb.FrameFeatures(k, K, D, 640, 480)
+    rng = np.random.default_rng(2)
+    nq = 700
+    x = rng.uniform(-30, 670, nq).astype(np.float32); y = rng.uniform(-30, 510, nq).astype(np.float32)
+    r = rng.uniform(0.5, 60, nq).astype(np.float32)
+    lo = rng.integers(-1, 7, nq).astype(np.int32); hi = rng.integers(-1, 8, nq).astype(np.int32)
+    x[:3] = [-500, 5000, 320]; y[:3] = [240, 240, -900]                 # windows off the grid (early returns :338-351)
+    got = fr.GetFeaturesInArea(x, y, r, lo, hi)
+    total = 0
+    for q in range(nq):
+        ref = oracle.features_in_area(fr.keys_un, fr.cell_ptr, fr.cell_idx, fr.bounds, x[q], y[q], r[q], int(lo[q]), int(hi[q]))
+        assert np.array_equal(got[q], ref), q
+        total += len(ref)
+    assert total > 1000
+    one = fr.GetFeaturesInArea(320.0, 240.0, 25.0)
+    assert np.array_equal(one, oracle.features_in_area(fr.keys_un, fr.cell_ptr, fr.cell_idx, fr.bounds, 320.0, 240.0, 25.0, -1, -1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nf,nmp,crowded,th", [(1200, 2500, False, 1.0), (1500, 4000, False, 3.0), (300, 3000, True, 1.0),
+                                              (64, 900, True, 5.0), (1, 5, False, 1.0)])
+def test_gpu_search_by_projection_frame(orb, oracle, synth, golden_dir, nf, nmp, crowded, th):
+    g = _golden(golden_dir)
+    K, D = g["tum1_K"], g["tum1_D"]
+    keys, desc_f, sf, rng = _scene(oracle, synth, nf, nmp, 100 + nf, K, D, crowded)
+    fr = orb.FrameFeatures(keys, K, D, 640, 480)
+    mp, dm = _map_points(oracle, fr.keys_un, desc_f, nmp, rng)
+    ur = np.where(rng.random(nf) < 0.5, fr.keys_un["x"] - rng.uniform(0, 30, nf), -1).astype(np.float32)      # stereo for half
+    occ = (rng.random(nf) < 0.15).astype(np.uint8)
+    for nnratio in (0.8, 0.6):
+        ref_fp, ref_pf, ref_n = oracle.search_by_projection_frame(fr.keys_un, desc_f, ur, occ, fr.cell_ptr, fr.cell_idx, fr.bounds, sf,
+                                                                  mp, dm, th, nnratio)
+        fp, pf, n = orb.search_by_projection_frame(fr, desc_f, ur, occ, sf, mp, dm, th=th, nnratio=nnratio)
+        assert n == ref_n and np.array_equal(pf, ref_pf) and np.array_equal(fp, ref_fp)
+    if nf >= 300:
+        assert ref_n > 50
