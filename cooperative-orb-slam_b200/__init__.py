@@ -88,6 +88,10 @@ ABI = {
     "orbf_features_in_area": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I]),
     "orbm_search_by_projection_frame": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _I,
                                             _VP, _VP, _VP, _I]),
+    "orbm_search_by_projection_last_frame": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _I, _I,
+                                                 _VP, _VP, _VP, _I]),
+    "orbm_search_by_projection_keyframe": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _I,
+                                               _VP, _VP, _VP, _I]),
 }
 
 
@@ -484,6 +488,40 @@ def search_by_projection_frame(frame, desc_f, u_right, occupied, scale_factors, 
                                                  int(th_high), _p(fp), _p(pf), C.byref(n), frame.device),
            "orbm_search_by_projection_frame")
     return fp[:nf], pf[:len(mp)], n.value
+
+
+PROJ_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("valid", "<i4"),
+                       ("obs_positive", "<i4")])
+
+
+def search_by_projection_last_frame(frame, desc_f, u_right, occupied, scale_factors, points, desc_pts, th, direction=0,
+                                    check_orientation=True, th_high=100):
+    """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (R21/src/ORBmatcher.cc:1328-1470).
+    points: PROJ_DTYPE array (one per last-frame feature).  -> (feature -> point | -1 | -2, point -> feature, nmatches)."""
+    df = np.ascontiguousarray(desc_f, np.uint8); ur = np.ascontiguousarray(u_right, np.float32)
+    occ = np.ascontiguousarray(occupied, np.uint8); sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
+    nf = len(frame.keys_un)
+    fp = np.zeros(max(nf, 1), np.int32); pf = np.zeros(max(len(pts), 1), np.int32); n = C.c_int(0)
+    _check(lib().orbm_search_by_projection_last_frame(_p(frame.keys_un), _p(df), _p(ur), _p(occ), nf, _p(frame.cell_ptr), _p(frame.cell_idx),
+                                                      _p(frame.bounds), _p(sf), len(sf), _p(pts), _p(dp), len(pts), float(th), int(direction),
+                                                      int(bool(check_orientation)), int(th_high), _p(fp), _p(pf), C.byref(n), frame.device),
+           "orbm_search_by_projection_last_frame")
+    return fp[:nf], pf[:len(pts)], n.value
+
+
+def search_by_projection_keyframe(frame, desc_f, occupied, scale_factors, points, desc_pts, th, orb_dist, check_orientation=True):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (R21/src/ORBmatcher.cc:1472-1599)."""
+    df = np.ascontiguousarray(desc_f, np.uint8); occ = np.ascontiguousarray(occupied, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
+    nf = len(frame.keys_un)
+    fp = np.zeros(max(nf, 1), np.int32); pf = np.zeros(max(len(pts), 1), np.int32); n = C.c_int(0)
+    _check(lib().orbm_search_by_projection_keyframe(_p(frame.keys_un), _p(df), _p(occ), nf, _p(frame.cell_ptr), _p(frame.cell_idx),
+                                                    _p(frame.bounds), _p(sf), len(sf), _p(pts), _p(dp), len(pts), float(th), int(orb_dist),
+                                                    int(bool(check_orientation)), _p(fp), _p(pf), C.byref(n), frame.device),
+           "orbm_search_by_projection_keyframe")
+    return fp[:nf], pf[:len(pts)], n.value
 
 
 def compute_stereo_matches(ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mbf, mb):

@@ -214,14 +214,22 @@ __global__ void area_fill_kernel(const orb_keypoint_t* __restrict__ kps, const i
     });
 }
 
-// ---------------------------------------------------------------- SearchByProjection(Frame&, vpMapPoints, th)
-// The reference walks the map points in order; a feature taken by an earlier point (with observations) is skipped by
-// the later ones (:82-84), so the result depends on the order.  One CTA reproduces it in rounds: every unresolved
-// point claims its candidate features (GetFeaturesInArea) with atomicMin(point index); a point whose candidates are
-// all claimed by nobody earlier cannot be influenced by an unresolved point any more and is resolved exactly as the
-// sequential loop would resolve it.  Points resolved in one round have pairwise disjoint candidate sets, so their
-// writes do not race.  The lowest unresolved point is always resolvable: the loop ends after at most n_mp rounds
+// ---------------------------------------------------------------- SearchByProjection: window searches
+// The reference walks the projected points in order; a feature taken by an earlier point is skipped by the later ones
+// (ORBmatcher.cc:82-84, :1404-1406, :1543-1544), so the result depends on the order.  One CTA reproduces it in rounds:
+// every unresolved point claims its candidate features (GetFeaturesInArea) with atomicMin(point index); a point whose
+// candidates are claimed by nobody earlier cannot be influenced by an unresolved point any more and is resolved exactly
+// as the sequential loop would resolve it.  Points resolved in one round have pairwise disjoint candidate sets, so
+// their writes do not race.  The lowest unresolved point is always resolvable: the loop ends after at most n rounds
 // (a handful in practice).
+struct ProjWindow {
+    float x, y, r;              // window centre and half size (already multiplied by the scale factor)
+    int min_level, max_level;   // GetFeaturesInArea level filter
+    float ur;                   // right coordinate for the stereo check
+    int flags;                  // kWinValid | kWinBlocks | kWinStereo
+};
+enum { kWinValid = 1, kWinBlocks = 2, kWinStereo = 4 };
+
 __device__ __forceinline__ int hamming32(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b) {
     int d = 0;
 #pragma unroll
@@ -229,77 +237,69 @@ __device__ __forceinline__ int hamming32(const uint32_t* __restrict__ a, const u
     return d;
 }
 
-__global__ void __launch_bounds__(1024) projection_kernel(const orb_keypoint_t* __restrict__ kps, const uint32_t* __restrict__ desc_f,
-                                                          const float* __restrict__ u_right, const uint8_t* __restrict__ occupied, int n_f,
-                                                          const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx, GridParams g,
-                                                          const float* __restrict__ scale_factors, const orbm_map_point_view_t* __restrict__ mps,
-                                                          const uint32_t* __restrict__ desc_mp, int n_mp, float th, float nnratio, int th_high,
-                                                          int* __restrict__ out_feature_point, int* __restrict__ out_point_feature,
-                                                          uint8_t* __restrict__ resolved, int* __restrict__ out_nmatches) {
+// RATIO: best and second best with the same-level ratio rule (:99-125); otherwise best only (:1419-1424, :1551-1555)
+template <bool RATIO>
+__global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_t* __restrict__ kps, const uint32_t* __restrict__ desc_f,
+                                                             const float* __restrict__ u_right, const uint8_t* __restrict__ occupied, int n_f,
+                                                             const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx, GridParams g,
+                                                             const ProjWindow* __restrict__ wins, const uint32_t* __restrict__ desc_p, int n_p,
+                                                             float nnratio, int threshold, int* __restrict__ out_feature_point,
+                                                             int* __restrict__ out_point_feature, uint8_t* __restrict__ resolved,
+                                                             int* __restrict__ out_nmatches) {
     extern __shared__ int s_dyn[];
     int* s_claim = s_dyn;                                             // [n_f]
     uint8_t* s_blocked = reinterpret_cast<uint8_t*>(s_dyn + n_f);    // [n_f]
     __shared__ int s_left, s_matches;
     const int tid = threadIdx.x;
     for (int f = tid; f < n_f; f += 1024) { s_blocked[f] = occupied[f]; out_feature_point[f] = -1; }
-    for (int i = tid; i < n_mp; i += 1024) {
+    for (int i = tid; i < n_p; i += 1024) {
         out_point_feature[i] = -1;
-        resolved[i] = mps[i].in_view ? 0 : 1;
+        resolved[i] = (wins[i].flags & kWinValid) ? 0 : 1;
     }
     if (tid == 0) s_matches = 0;
-    const bool factor = th != 1.0f;
-    auto radius = [&](const orbm_map_point_view_t& mp) {
-        // RadiusByViewingCos (:132-138) compares the float with the double literal 0.998
-        float r = (double)mp.view_cos > 0.998 ? 2.5f : 4.0f;
-        if (factor) r = __fmul_rn(r, th);
-        return r;
-    };
     while (true) {
         __syncthreads();
         for (int f = tid; f < n_f; f += 1024) s_claim[f] = 0x7fffffff;
         if (tid == 0) s_left = 0;
         __syncthreads();
-        for (int i = tid; i < n_mp; i += 1024) {
+        for (int i = tid; i < n_p; i += 1024) {
             if (resolved[i]) continue;
-            const orbm_map_point_view_t mp = mps[i];
-            const float r = radius(mp);
-            for_features_in_area(kps, cell_ptr, cell_idx, g, mp.proj_x, mp.proj_y, __fmul_rn(r, scale_factors[mp.level]), mp.level - 1, mp.level,
+            const ProjWindow w = wins[i];
+            for_features_in_area(kps, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level,
                                  [&](int idx) { atomicMin(&s_claim[idx], i); return true; });
         }
         __syncthreads();
-        for (int i = tid; i < n_mp; i += 1024) {
+        for (int i = tid; i < n_p; i += 1024) {
             if (resolved[i]) continue;
-            const orbm_map_point_view_t mp = mps[i];
-            const float r = radius(mp);
-            const float win = __fmul_rn(r, scale_factors[mp.level]);
+            const ProjWindow w = wins[i];
             bool safe = true;
-            for_features_in_area(kps, cell_ptr, cell_idx, g, mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level,
+            for_features_in_area(kps, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level,
                                  [&](int idx) { safe = s_claim[idx] >= i; return safe; });
             if (!safe) { atomicAdd(&s_left, 1); continue; }
             int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-            const uint32_t* dmp = desc_mp + (size_t)i * 8;
-            for_features_in_area(kps, cell_ptr, cell_idx, g, mp.proj_x, mp.proj_y, win, mp.level - 1, mp.level, [&](int idx) {
+            const uint32_t* dp = desc_p + (size_t)i * 8;
+            for_features_in_area(kps, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level, [&](int idx) {
                 if (s_blocked[idx]) return true;
-                if (u_right[idx] > 0) {
-                    const float er = fabsf(__fsub_rn(mp.proj_xr, u_right[idx]));
-                    if (er > win) return true;
+                if ((w.flags & kWinStereo) && u_right[idx] > 0) {
+                    const float er = fabsf(__fsub_rn(w.ur, u_right[idx]));
+                    if (er > w.r) return true;
                 }
-                const int dist = hamming32(dmp, desc_f + (size_t)idx * 8);
+                const int dist = hamming32(dp, desc_f + (size_t)idx * 8);
                 if (dist < bestDist) {
                     bestDist2 = bestDist; bestDist = dist;
                     bestLevel2 = bestLevel; bestLevel = kps[idx].octave;
                     bestIdx = idx;
-                } else if (dist < bestDist2) {
+                } else if (RATIO && dist < bestDist2) {
                     bestLevel2 = kps[idx].octave;
                     bestDist2 = dist;
                 }
                 return true;
             });
             resolved[i] = 1;
-            if (bestDist <= th_high) {
-                if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
+            if (bestDist <= threshold) {
+                if (RATIO && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
                 out_feature_point[bestIdx] = i;
-                s_blocked[bestIdx] = mp.obs_positive ? 1 : 0;
+                s_blocked[bestIdx] = (w.flags & kWinBlocks) ? 1 : 0;
                 out_point_feature[i] = bestIdx;
                 atomicAdd(&s_matches, 1);
             }
@@ -308,6 +308,81 @@ __global__ void __launch_bounds__(1024) projection_kernel(const orb_keypoint_t* 
         if (s_left == 0) break;
     }
     if (tid == 0) *out_nmatches = s_matches;
+}
+
+static GridParams make_grid_params(const float* bounds);
+
+// uploads the frame and the windows, runs the search, downloads feature -> point, point -> feature and the count
+static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right, const uint8_t* occupied,
+                             int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const std::vector<ProjWindow>& wins,
+                             const uint8_t* desc_p, float nnratio, int threshold, int32_t* out_feature_point, int32_t* out_point_feature,
+                             int* n_matches, int device) {
+    const int n_p = (int)wins.size();
+    MatchCtx& cx = match_ctx();
+    const size_t kb = (size_t)n_f * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4;
+    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4) + pb + (size_t)n_p * (sizeof(ProjWindow) + 32 + 4 + 1) + 4 + 20 * 256;
+    if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
+    std::vector<float> no_stereo;
+    if (!u_right) { no_stereo.assign(n_f, -1.0f); u_right = no_stereo.data(); }
+    const orb_keypoint_t* d_k = (const orb_keypoint_t*)cx.upload(kps_un, kb);
+    const uint32_t* d_df = (const uint32_t*)cx.upload(desc_f, (size_t)n_f * 32);
+    const float* d_ur = (const float*)cx.upload(u_right, (size_t)n_f * 4);
+    const uint8_t* d_occ = (const uint8_t*)cx.upload(occupied, (size_t)n_f);
+    const int* d_cp = (const int*)cx.upload(cell_ptr, pb);
+    const int* d_ci = (const int*)cx.upload(cell_idx, (size_t)n_f * 4);
+    const ProjWindow* d_w = (const ProjWindow*)cx.upload(wins.data(), (size_t)n_p * sizeof(ProjWindow));
+    const uint32_t* d_dp = (const uint32_t*)cx.upload(desc_p, (size_t)n_p * 32);
+    int* d_fp = (int*)cx.dalloc((size_t)n_f * 4); int* d_pf = (int*)cx.dalloc((size_t)n_p * 4);
+    uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_p); int* d_nm = (int*)cx.dalloc(4);
+    if (!d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm) return ORB_ERR_CUDA;
+    static bool configured = false;
+    if (!configured) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 5 + 16));
+        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 5 + 16));
+        configured = true;
+    }
+    const size_t smem = (size_t)n_f * 5 + 16;
+    const GridParams g = make_grid_params(bounds);
+    if (ratio)
+        window_search_kernel<true><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_nm);
+    else
+        window_search_kernel<false><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_nm);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (!cx.download(out_feature_point, d_fp, (size_t)n_f * 4) || !cx.download(out_point_feature, d_pf, (size_t)n_p * 4) ||
+        !cx.download(n_matches, d_nm, 4) || !cx.finish()) return ORB_ERR_CUDA;
+    return ORB_OK;
+}
+
+// rotation consistency of the best-only searches (:1431-1466, :1561-1596): matches outside the three dominant bins of
+// the angle-difference histogram are set to NULL; every histogram entry removed decrements the count
+static void rotation_check(const orb_keypoint_t* kps_un, const orbm_proj_point_t* pts, int n_p, const int32_t* point_feature,
+                           int32_t* feature_point, int* n_matches) {
+    constexpr int kHisto = 30;      // ORBmatcher::HISTO_LENGTH
+    const float factor = 1.0f / kHisto;
+    int cnt[kHisto] = {0};
+    std::vector<int> bin(n_p, -1);
+    for (int i = 0; i < n_p; i++) {
+        if (point_feature[i] < 0) continue;
+        float rot = pts[i].angle - kps_un[point_feature[i]].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int b = (int)roundf(rot * factor);
+        if (b == kHisto) b = 0;
+        bin[i] = b; cnt[b]++;
+    }
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;      // ComputeThreeMaxima :1601-1642
+    for (int i = 0; i < kHisto; i++) {
+        const int s = cnt[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+    for (int i = 0; i < n_p; i++) {
+        if (bin[i] < 0 || bin[i] == ind1 || bin[i] == ind2 || bin[i] == ind3) continue;
+        feature_point[point_feature[i]] = -2;
+        (*n_matches)--;
+    }
 }
 
 static bool make_undistort_params(const float* K, const float* dist, int ndist, UndistortParams* p) {
@@ -421,48 +496,101 @@ int orbf_features_in_area(const orb_keypoint_t* kps_un, int n, const int32_t* ce
     return ORB_OK;
 }
 
+static bool check_frame_args(const char* who, const orb_keypoint_t* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
+                             const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* scale_factors, int n_levels,
+                             const void* pts, const uint8_t* desc_p, int n_p, int32_t* out_feature_point, int32_t* out_point_feature,
+                             int* n_matches) {
+    if (n_f < 0 || n_f > kFrameMaxFeatures || n_p < 0 || n_levels <= 0 || !bounds || !cell_ptr || !scale_factors || !n_matches ||
+        (n_f && (!kps_un || !desc_f || !occupied || !cell_idx || !out_feature_point)) || (n_p && (!pts || !desc_p || !out_point_feature))) {
+        set_error("%s: bad arguments (at most %d frame features)", who, kFrameMaxFeatures);
+        return false;
+    }
+    return true;
+}
+
 int orbm_search_by_projection_frame(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right, const uint8_t* occupied, int n_f,
                                     const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* scale_factors, int n_levels,
                                     const orbm_map_point_view_t* mps, const uint8_t* desc_mp, int n_mp, float th, float nnratio, int th_high,
                                     int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device) {
-    if (n_f < 0 || n_f > kFrameMaxFeatures || n_mp < 0 || n_levels <= 0 || !bounds || !cell_ptr || !scale_factors || !n_matches ||
-        (n_f && (!kps_un || !desc_f || !u_right || !occupied || !cell_idx || !out_feature_point)) || (n_mp && (!mps || !desc_mp || !out_point_feature))) {
-        set_error("orbm_search_by_projection_frame: bad arguments (at most %d frame features)", kFrameMaxFeatures);
+    if (!check_frame_args("orbm_search_by_projection_frame", kps_un, desc_f, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, n_levels, mps,
+                          desc_mp, n_mp, out_feature_point, out_point_feature, n_matches) || (n_f && !u_right)) {
+        if (n_f && !u_right) set_error("orbm_search_by_projection_frame: u_right is required");
         return ORB_ERR_ARG;
     }
-    for (int i = 0; i < n_mp; i++)
-        if (mps[i].in_view && (mps[i].level < 0 || mps[i].level >= n_levels)) { set_error("orbm_search_by_projection_frame: map point %d predicts level %d of %d", i, mps[i].level, n_levels); return ORB_ERR_ARG; }
+    std::vector<ProjWindow> wins(n_mp);
+    const bool factor = th != 1.0f;
+    for (int i = 0; i < n_mp; i++) {
+        const orbm_map_point_view_t& mp = mps[i];
+        ProjWindow& w = wins[i];
+        w.flags = 0;
+        if (!mp.in_view) continue;
+        if (mp.level < 0 || mp.level >= n_levels) { set_error("orbm_search_by_projection_frame: map point %d predicts level %d of %d", i, mp.level, n_levels); return ORB_ERR_ARG; }
+        float r = (double)mp.view_cos > 0.998 ? 2.5f : 4.0f;      // RadiusByViewingCos :132-138
+        if (factor) r *= th;                                        // :64-65
+        w.x = mp.proj_x; w.y = mp.proj_y; w.r = r * scale_factors[mp.level];      // :68
+        w.min_level = mp.level - 1; w.max_level = mp.level; w.ur = mp.proj_xr;
+        w.flags = kWinValid | kWinStereo | (mp.obs_positive ? kWinBlocks : 0);
+    }
     *n_matches = 0;
     for (int f = 0; f < n_f; f++) out_feature_point[f] = -1;
     for (int i = 0; i < n_mp; i++) out_point_feature[i] = -1;
     if (n_f == 0 || n_mp == 0) return ORB_OK;
-    MatchCtx& cx = match_ctx();
-    const size_t kb = (size_t)n_f * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4;
-    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4) + pb + (size_t)n_levels * 4 + (size_t)n_mp * (sizeof(orbm_map_point_view_t) + 32 + 4 + 1) + 4 + 20 * 256;
-    if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
-    const orb_keypoint_t* d_k = (const orb_keypoint_t*)cx.upload(kps_un, kb);
-    const uint32_t* d_df = (const uint32_t*)cx.upload(desc_f, (size_t)n_f * 32);
-    const float* d_ur = (const float*)cx.upload(u_right, (size_t)n_f * 4);
-    const uint8_t* d_occ = (const uint8_t*)cx.upload(occupied, (size_t)n_f);
-    const int* d_cp = (const int*)cx.upload(cell_ptr, pb);
-    const int* d_ci = (const int*)cx.upload(cell_idx, (size_t)n_f * 4);
-    const float* d_sf = (const float*)cx.upload(scale_factors, (size_t)n_levels * 4);
-    const orbm_map_point_view_t* d_mp = (const orbm_map_point_view_t*)cx.upload(mps, (size_t)n_mp * sizeof(orbm_map_point_view_t));
-    const uint32_t* d_dm = (const uint32_t*)cx.upload(desc_mp, (size_t)n_mp * 32);
-    int* d_fp = (int*)cx.dalloc((size_t)n_f * 4); int* d_pf = (int*)cx.dalloc((size_t)n_mp * 4);
-    uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_mp); int* d_nm = (int*)cx.dalloc(4);
-    if (!d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_sf || !d_mp || !d_dm || !d_fp || !d_pf || !d_res || !d_nm) return ORB_ERR_CUDA;
-    static bool configured = false;
-    if (!configured) {
-        ORB_CUDA_TRY(cudaFuncSetAttribute(projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 5 + 16));
-        configured = true;
+    return run_window_search(true, kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds, wins, desc_mp, nnratio, th_high,
+                             out_feature_point, out_point_feature, n_matches, device);
+}
+
+static int best_only_search(const char* who, bool keyframe_mode, const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right,
+                            const uint8_t* occupied, int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                            const float* scale_factors, int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th,
+                            int direction, int check_orientation, int threshold, int32_t* out_feature_point, int32_t* out_point_feature,
+                            int* n_matches, int device) {
+    if (!check_frame_args(who, kps_un, desc_f, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, n_levels, pts, desc_pts, n_pts,
+                          out_feature_point, out_point_feature, n_matches)) return ORB_ERR_ARG;
+    if (direction < 0 || direction > 2 || (!keyframe_mode && n_f && !u_right)) { set_error("%s: bad direction / u_right", who); return ORB_ERR_ARG; }
+    std::vector<ProjWindow> wins(n_pts);
+    for (int i = 0; i < n_pts; i++) {
+        const orbm_proj_point_t& p = pts[i];
+        ProjWindow& w = wins[i];
+        w.flags = 0;
+        if (!p.valid) continue;
+        const int oct = p.octave;
+        if (oct < 0 || oct >= n_levels) { set_error("%s: point %d has octave %d of %d", who, i, oct, n_levels); return ORB_ERR_ARG; }
+        w.x = p.u; w.y = p.v; w.r = th * scale_factors[oct];      // :1381, :1529
+        if (keyframe_mode || direction == 0) { w.min_level = oct - 1; w.max_level = oct + 1; }      // :1390, :1531
+        else if (direction == 1) { w.min_level = oct; w.max_level = -1; }                            // :1386
+        else { w.min_level = 0; w.max_level = oct; }                                                 // :1388
+        w.ur = p.ur;
+        w.flags = kWinValid | (keyframe_mode ? kWinBlocks : (kWinStereo | (p.obs_positive ? kWinBlocks : 0)));
     }
-    projection_kernel<<<1, 1024, (size_t)n_f * 5 + 16, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, make_grid_params(bounds), d_sf, d_mp, d_dm, n_mp,
-                                                                    th, nnratio, th_high, d_fp, d_pf, d_res, d_nm);
-    ORB_CUDA_TRY(cudaGetLastError());
-    if (!cx.download(out_feature_point, d_fp, (size_t)n_f * 4) || !cx.download(out_point_feature, d_pf, (size_t)n_mp * 4) ||
-        !cx.download(n_matches, d_nm, 4) || !cx.finish()) return ORB_ERR_CUDA;
+    *n_matches = 0;
+    for (int f = 0; f < n_f; f++) out_feature_point[f] = -1;
+    for (int i = 0; i < n_pts; i++) out_point_feature[i] = -1;
+    if (n_f == 0 || n_pts == 0) return ORB_OK;
+    const int rc = run_window_search(false, kps_un, desc_f, keyframe_mode ? nullptr : u_right, occupied, n_f, cell_ptr, cell_idx, bounds, wins,
+                                     desc_pts, 0.f, threshold, out_feature_point, out_point_feature, n_matches, device);
+    if (rc) return rc;
+    if (check_orientation) rotation_check(kps_un, pts, n_pts, out_point_feature, out_feature_point, n_matches);
     return ORB_OK;
+}
+
+int orbm_search_by_projection_last_frame(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right, const uint8_t* occupied,
+                                         int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                                         const float* scale_factors, int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts,
+                                         int n_pts, float th, int direction, int check_orientation, int th_high,
+                                         int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device) {
+    return best_only_search("orbm_search_by_projection_last_frame", false, kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds,
+                            scale_factors, n_levels, pts, desc_pts, n_pts, th, direction, check_orientation, th_high, out_feature_point,
+                            out_point_feature, n_matches, device);
+}
+
+int orbm_search_by_projection_keyframe(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
+                                       const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* scale_factors,
+                                       int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int orb_dist,
+                                       int check_orientation, int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches,
+                                       int device) {
+    return best_only_search("orbm_search_by_projection_keyframe", true, kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds,
+                            scale_factors, n_levels, pts, desc_pts, n_pts, th, 0, check_orientation, orb_dist, out_feature_point,
+                            out_point_feature, n_matches, device);
 }
 
 }  // extern "C"

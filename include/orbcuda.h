@@ -269,6 +269,38 @@ int orbm_search_by_projection_frame(const orb_keypoint_t* kps_un, const uint8_t*
                                     float th, float nnratio, int th_high, int32_t* out_feature_point,
                                     int32_t* out_point_feature, int* n_matches, int device);
 
+/* A projected point for the two best-only window searches below: what the reference computes before it calls
+ * GetFeaturesInArea (unchanged reference statements on the caller's side). */
+typedef struct {
+    float u, v;            /* projection into the current frame (:1365-1366, :1505-1506) */
+    float ur;              /* u - mbf * invzc (:1410); ignored by the key-frame variant */
+    float angle;           /* LastFrame.mvKeysUn[i].angle / pKF->mvKeysUn[i].angle (rotation histogram) */
+    int32_t octave;        /* LastFrame.mvKeys[i].octave (:1378) / pMP->PredictScale(dist3D, &CurrentFrame) (:1522) */
+    int32_t valid;         /* every test before the window search passed (:1354-1373 / :1491-1520) */
+    int32_t obs_positive;  /* pMP->Observations() > 0, read by later iterations (:1404-1406); ignored by the key-frame variant */
+} orbm_proj_point_t;
+
+/* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
+ * R21/src/ORBmatcher.cc:1328-1470 (Tracking::TrackWithMotionModel).  direction: 0 neither, 1 bForward, 2 bBackward
+ * (:1348-1349).  occupied[f] = CurrentFrame.mvpMapPoints[f] && Observations() > 0 on entry.  out_feature_point[f]:
+ * -1 untouched, -2 set to NULL by the rotation check (:1457-1461), else the index of the point left there. */
+int orbm_search_by_projection_last_frame(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right,
+                                         const uint8_t* occupied, int n_f, const int32_t* cell_ptr,
+                                         const int32_t* cell_idx, const float* bounds, const float* scale_factors,
+                                         int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts,
+                                         float th, int direction, int check_orientation, int th_high,
+                                         int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches,
+                                         int device);
+/* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound,
+ *                                    const float th, const int ORBdist)
+ * R21/src/ORBmatcher.cc:1472-1599 (Tracking::Relocalization).  occupied[f] = CurrentFrame.mvpMapPoints[f] != NULL. */
+int orbm_search_by_projection_keyframe(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const uint8_t* occupied,
+                                       int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                                       const float* scale_factors, int n_levels, const orbm_proj_point_t* pts,
+                                       const uint8_t* desc_pts, int n_pts, float th, int orb_dist,
+                                       int check_orientation, int32_t* out_feature_point, int32_t* out_point_feature,
+                                       int* n_matches, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,4 +197,112 @@ int orc_search_by_projection_frame(const orc_keypoint* kps_un, const uint8_t* de
     return nmatches;
 }
 
+/* ComputeThreeMaxima R21/src/ORBmatcher.cc:1601-1642 on the histogram's bin sizes */
+static void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+enum { kHistoLength = 30 };   /* ORBmatcher::HISTO_LENGTH, R21/src/ORBmatcher.cc:38 */
+
+/* Shared body of SearchByProjection(Frame&, const Frame&, th, bMono) :1328-1470 and
+ * SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) :1472-1599 from the point where the projection
+ * (u, v) is known.  keyframe_mode = 0: levels by direction (:1385-1390), a feature blocks when it holds a point with
+ * observations (:1404-1406), stereo check (:1408-1414), threshold th_high (:1428).  keyframe_mode = 1: levels
+ * [l-1, l+1] (:1531), any occupied feature blocks (:1543-1544), no stereo check, threshold ORBdist (:1557).
+ * out_feature_point[f]: -1 untouched, -2 set to NULL by the rotation check, else the point left in mvpMapPoints[f]. */
+static int projection_body(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right, const uint8_t* occupied,
+                           int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                           const float* scale_factors, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts, float th,
+                           int direction, int keyframe_mode, int check_orientation, int threshold,
+                           int32_t* out_feature_point, int32_t* out_point_feature) {
+    int nmatches = 0;
+    std::vector<int> rotHist[kHistoLength];
+    const float factor = 1.0f / kHistoLength;
+    std::vector<uint8_t> blocked(occupied, occupied + n_f);
+    for (int f = 0; f < n_f; f++) out_feature_point[f] = -1;
+    std::vector<int32_t> cand((size_t)std::max(n_f, 1));
+    for (int i = 0; i < n_pts; i++) {
+        out_point_feature[i] = -1;
+        const orc_proj_point& p = pts[i];
+        if (!p.valid) continue;
+        const int oct = p.octave;
+        const float radius = th * scale_factors[oct];
+        int nc;
+        if (keyframe_mode) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct - 1, oct + 1, cand.data(), n_f);
+        else if (direction == 1) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct, -1, cand.data(), n_f);
+        else if (direction == 2) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, 0, oct, cand.data(), n_f);
+        else nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct - 1, oct + 1, cand.data(), n_f);
+        if (nc == 0) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            if (blocked[i2]) continue;
+            if (!keyframe_mode && u_right[i2] > 0) {
+                const float er = fabsf(p.ur - u_right[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = orc_descriptor_distance(desc_pts + (size_t)i * 32, desc_f + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= threshold) {
+            out_feature_point[bestIdx2] = i;
+            blocked[bestIdx2] = keyframe_mode ? 1 : (p.obs_positive ? 1 : 0);
+            out_point_feature[i] = bestIdx2;
+            nmatches++;
+            if (check_orientation) {
+                float rot = p.angle - kps_un[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)round(rot * factor);
+                if (bin == kHistoLength) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, kHistoLength, ind1, ind2, ind3);
+        for (int i = 0; i < kHistoLength; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    out_feature_point[rotHist[i][j]] = -2;      /* mvpMapPoints[...] = NULL */
+                    nmatches--;
+                }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) :1328-1470.  Per last-frame
+ * feature the caller supplies what :1354-1378 compute (valid = has a point, not an outlier, invzc >= 0, inside the
+ * image bounds; u, v; ur = u - mbf*invzc; octave and angle of LastFrame's key point; obs_positive of its point).
+ * direction: 0 neither, 1 bForward, 2 bBackward (:1348-1349). */
+int orc_search_by_projection_last_frame(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right,
+                                        const uint8_t* occupied, int n_f, const int32_t* cell_ptr, const int32_t* cell_idx,
+                                        const float* bounds, const float* scale_factors, const orc_proj_point* pts,
+                                        const uint8_t* desc_pts, int n_pts, float th, int direction, int check_orientation,
+                                        int th_high, int32_t* out_feature_point, int32_t* out_point_feature) {
+    return projection_body(kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, pts, desc_pts, n_pts,
+                           th, direction, 0, check_orientation, th_high, out_feature_point, out_point_feature);
+}
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) :1472-1599.
+ * valid = the point exists, is not bad, is not in sAlreadyFound, projects inside the bounds and its distance is
+ * inside the scale-invariance range (:1494-1520); octave = PredictScale (:1522); angle = pKF->mvKeysUn[i].angle;
+ * occupied[f] = CurrentFrame.mvpMapPoints[f] != NULL. */
+int orc_search_by_projection_keyframe(const orc_keypoint* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
+                                      const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                                      const float* scale_factors, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts,
+                                      float th, int orb_dist, int check_orientation, int32_t* out_feature_point,
+                                      int32_t* out_point_feature) {
+    return projection_body(kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, pts, desc_pts, n_pts, th,
+                           0, 1, check_orientation, orb_dist, out_feature_point, out_point_feature);
+}
+
 }  // extern "C"

@@ -187,6 +187,29 @@ int orc_search_by_projection_frame(const orc_keypoint* kps_un, const uint8_t* de
                                    const uint8_t* desc_mp, int n_mp, float th, float nnratio, int th_high,
                                    int32_t* out_feature_point, int32_t* out_point_feature);
 
+/* A projected point for the window searches below (what the reference computes before GetFeaturesInArea). */
+typedef struct {
+    float u, v;            /* projection into the current frame */
+    float ur;              /* u - mbf * invzc (:1410) */
+    float angle;           /* angle of the source key point (rotation histogram) */
+    int32_t octave;        /* source key point octave (:1378) or PredictScale (:1522) */
+    int32_t valid;         /* passes every test before the window search */
+    int32_t obs_positive;  /* Observations() > 0 of the point (read by later iterations, :1404-1406) */
+} orc_proj_point;
+
+/* ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (R21/src/ORBmatcher.cc:1328-1470) */
+int orc_search_by_projection_last_frame(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right,
+                                        const uint8_t* occupied, int n_f, const int32_t* cell_ptr, const int32_t* cell_idx,
+                                        const float* bounds, const float* scale_factors, const orc_proj_point* pts,
+                                        const uint8_t* desc_pts, int n_pts, float th, int direction, int check_orientation,
+                                        int th_high, int32_t* out_feature_point, int32_t* out_point_feature);
+/* ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (R21/src/ORBmatcher.cc:1472-1599) */
+int orc_search_by_projection_keyframe(const orc_keypoint* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
+                                      const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                                      const float* scale_factors, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts,
+                                      float th, int orb_dist, int check_orientation, int32_t* out_feature_point,
+                                      int32_t* out_point_feature);
+
 #ifdef __cplusplus
 }
 #endif

@@ -391,3 +391,39 @@ def search_by_projection_frame(kps_un, desc_f, u_right, occupied, ptr, idx, boun
     n = L.orc_search_by_projection_frame(_p(kps_un), _p(df), _p(ur), _p(occ), len(kps_un), _p(ptr), _p(idx), _p(b), _p(sf), _p(mps),
                                          _p(dm), len(mps), th, nnratio, th_high, _p(fp), _p(pf))
     return fp[:len(kps_un)], pf[:len(mps)], n
+
+
+PROJ_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("valid", "<i4"),
+                       ("obs_positive", "<i4")])
+
+
+def search_by_projection_last_frame(kps_un, desc_f, u_right, occupied, ptr, idx, bounds, scale_factors, pts, desc_pts, th, direction,
+                                    check_orientation, th_high=100):
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE); df = np.ascontiguousarray(desc_f, np.uint8)
+    ur = np.ascontiguousarray(u_right, np.float32); occ = np.ascontiguousarray(occupied, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(pts, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
+    fp = np.zeros(max(len(kps_un), 1), np.int32); pf = np.zeros(max(len(pts), 1), np.int32)
+    L = lib()
+    L.orc_search_by_projection_last_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int,
+                                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = L.orc_search_by_projection_last_frame(_p(kps_un), _p(df), _p(ur), _p(occ), len(kps_un), _p(ptr), _p(idx), _p(b), _p(sf), _p(pts),
+                                              _p(dp), len(pts), th, direction, int(check_orientation), th_high, _p(fp), _p(pf))
+    return fp[:len(kps_un)], pf[:len(pts)], n
+
+
+def search_by_projection_keyframe(kps_un, desc_f, occupied, ptr, idx, bounds, scale_factors, pts, desc_pts, th, orb_dist,
+                                  check_orientation):
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE); df = np.ascontiguousarray(desc_f, np.uint8)
+    occ = np.ascontiguousarray(occupied, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(pts, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
+    fp = np.zeros(max(len(kps_un), 1), np.int32); pf = np.zeros(max(len(pts), 1), np.int32)
+    L = lib()
+    L.orc_search_by_projection_keyframe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int,
+                                                    C.c_void_p, C.c_void_p]
+    n = L.orc_search_by_projection_keyframe(_p(kps_un), _p(df), _p(occ), len(kps_un), _p(ptr), _p(idx), _p(b), _p(sf), _p(pts), _p(dp),
+                                            len(pts), th, orb_dist, int(check_orientation), _p(fp), _p(pf))
+    return fp[:len(kps_un)], pf[:len(pts)], n

@@ -207,3 +207,78 @@ def test_gpu_search_by_projection_frame(orb, oracle, synth, golden_dir, nf, nmp,
         assert n == ref_n and np.array_equal(pf, ref_pf) and np.array_equal(fp, ref_fp)
     if nf >= 300:
         assert ref_n > 50
+
+
+def _proj_points(oracle, keys_un, desc_f, npts, rng, rot_deg=12.0):
+    """Projected points of a previous frame: most land near a current feature and carry a noisy copy of its descriptor;
+    their angles differ from the current ones by a common rotation plus outliers (exercises the rotation histogram)."""
+    nf = len(keys_un)
+    p = np.zeros(npts, oracle.PROJ_DTYPE)
+    src = rng.integers(0, nf, npts)
+    p["u"] = keys_un["x"][src] + rng.normal(0, 3.0, npts).astype(np.float32)
+    p["v"] = keys_un["y"][src] + rng.normal(0, 3.0, npts).astype(np.float32)
+    p["ur"] = p["u"] - rng.uniform(0, 30, npts).astype(np.float32)
+    ang = keys_un["angle"][src] + np.float32(rot_deg) + rng.normal(0, 3.0, npts).astype(np.float32)
+    out = rng.random(npts) < 0.15
+    ang[out] = rng.uniform(0, 360, int(out.sum()))
+    p["angle"] = np.mod(ang, 360).astype(np.float32)
+    p["octave"] = np.clip(keys_un["octave"][src] + rng.integers(-1, 2, npts), 0, 7)
+    p["valid"] = rng.random(npts) < 0.9
+    p["obs_positive"] = rng.random(npts) < 0.85
+    dp = desc_f[src].copy()
+    for i in range(npts):
+        for b in rng.integers(0, 256, rng.integers(0, 25)):
+            dp[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return p, dp
+
+
+def test_oracle_last_frame_search_rotation_check(oracle, synth, golden_dir):
+    g = _golden(golden_dir)
+    K, D = g["tum1_K"], g["tum1_D"]
+    keys, desc_f, sf, rng = _scene(oracle, synth, 800, 0, 31, K, D)
+    k = oracle.undistort_keypoints(keys, K, D); b = oracle.image_bounds(640, 480, K, D)
+    ptr, idx = oracle.assign_grid(k, b)
+    pts, dp = _proj_points(oracle, k, desc_f, 700, rng)
+    ur = np.full(len(k), -1, np.float32); occ = np.zeros(len(k), np.uint8)
+    fp0, pf0, n0 = oracle.search_by_projection_last_frame(k, desc_f, ur, occ, ptr, idx, b, sf, pts, dp, 15.0, 0, False)
+    fp1, pf1, n1 = oracle.search_by_projection_last_frame(k, desc_f, ur, occ, ptr, idx, b, sf, pts, dp, 15.0, 0, True)
+    assert np.array_equal(pf0, pf1) and n0 == (pf0 >= 0).sum() > 200
+    removed = (fp1 == -2)
+    assert 0 < removed.sum() < n0 and n1 < n0                     # the angle outliers go, the bulk stays
+    assert np.array_equal(fp0[~removed], fp1[~removed])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nf,npts,crowded,th,direction", [(1200, 1100, False, 15.0, 0), (1200, 1100, False, 7.0, 1), (1500, 2000, False, 30.0, 2),
+                                                         (200, 1500, True, 15.0, 0), (1, 3, False, 7.0, 0)])
+def test_gpu_search_by_projection_last_frame(orb, oracle, synth, golden_dir, nf, npts, crowded, th, direction):
+    g = _golden(golden_dir)
+    K, D = g["tum2_K"], g["tum2_D"]
+    keys, desc_f, sf, rng = _scene(oracle, synth, nf, 0, 300 + nf + direction, K, D, crowded)
+    fr = orb.FrameFeatures(keys, K, D, 640, 480)
+    pts, dp = _proj_points(oracle, fr.keys_un, desc_f, npts, rng)
+    ur = np.where(rng.random(nf) < 0.5, fr.keys_un["x"] - rng.uniform(0, 30, nf), -1).astype(np.float32)
+    occ = (rng.random(nf) < 0.1).astype(np.uint8)
+    for check in (True, False):
+        ref = oracle.search_by_projection_last_frame(fr.keys_un, desc_f, ur, occ, fr.cell_ptr, fr.cell_idx, fr.bounds, sf, pts, dp, th,
+                                                     direction, check)
+        got = orb.search_by_projection_last_frame(fr, desc_f, ur, occ, sf, pts, dp, th, direction=direction, check_orientation=check)
+        assert got[2] == ref[2] and np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+    if nf >= 200:
+        assert ref[2] > 30
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nf,npts,crowded,th,orb_dist", [(1300, 900, False, 10.0, 100), (1300, 1500, False, 3.0, 64), (150, 1200, True, 10.0, 100)])
+def test_gpu_search_by_projection_keyframe(orb, oracle, synth, golden_dir, nf, npts, crowded, th, orb_dist):
+    g = _golden(golden_dir)
+    K, D = g["four_K"], g["four_D"]
+    keys, desc_f, sf, rng = _scene(oracle, synth, nf, 0, 500 + nf + orb_dist, K, D, crowded)
+    fr = orb.FrameFeatures(keys, K, D, 752, 480)
+    pts, dp = _proj_points(oracle, fr.keys_un, desc_f, npts, rng)
+    occ = (rng.random(nf) < 0.2).astype(np.uint8)
+    for check in (True, False):
+        ref = oracle.search_by_projection_keyframe(fr.keys_un, desc_f, occ, fr.cell_ptr, fr.cell_idx, fr.bounds, sf, pts, dp, th, orb_dist, check)
+        got = orb.search_by_projection_keyframe(fr, desc_f, occ, sf, pts, dp, th, orb_dist, check_orientation=check)
+        assert got[2] == ref[2] and np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+    assert ref[2] > 20
