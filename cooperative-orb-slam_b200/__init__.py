@@ -92,6 +92,8 @@ ABI = {
                                                  _VP, _VP, _VP, _I]),
     "orbm_search_by_projection_keyframe": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _I,
                                                _VP, _VP, _VP, _I]),
+    "orbm_search_by_projection_sim3": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _VP, _VP, _VP, _I]),
+    "orbm_window_best_match": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _VP, _VP, _I]),
 }
 
 
@@ -522,6 +524,35 @@ def search_by_projection_keyframe(frame, desc_f, occupied, scale_factors, points
                                                     int(bool(check_orientation)), _p(fp), _p(pf), C.byref(n), frame.device),
            "orbm_search_by_projection_keyframe")
     return fp[:nf], pf[:len(pts)], n.value
+
+
+def search_by_projection_sim3(frame, desc_f, occupied, scale_factors, points, desc_pts, th, th_low=50):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (R21/src/ORBmatcher.cc:290-403)."""
+    df = np.ascontiguousarray(desc_f, np.uint8); occ = np.ascontiguousarray(occupied, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
+    nf = len(frame.keys_un)
+    fp = np.zeros(max(nf, 1), np.int32); pf = np.zeros(max(len(pts), 1), np.int32); n = C.c_int(0)
+    _check(lib().orbm_search_by_projection_sim3(_p(frame.keys_un), _p(df), _p(occ), nf, _p(frame.cell_ptr), _p(frame.cell_idx),
+                                                _p(frame.bounds), _p(sf), len(sf), _p(pts), _p(dp), len(pts), float(th), int(th_low),
+                                                _p(fp), _p(pf), C.byref(n), frame.device), "orbm_search_by_projection_sim3")
+    return fp[:nf], pf[:len(pts)], n.value
+
+
+def window_best_match(frame, desc_f, scale_factors, points, desc_pts, th, u_right=None, inv_level_sigma2=None):
+    """The window search of ORBmatcher::Fuse x2 and SearchBySim3 (R21/src/ORBmatcher.cc:825-1326): per projected point the best
+    feature of levels [l-1, l]; inv_level_sigma2 (+ u_right) enables the chi-square gates of Fuse :905-931.
+    -> (best_idx, best_dist)."""
+    df = np.ascontiguousarray(desc_f, np.uint8); sf = np.ascontiguousarray(scale_factors, np.float32)
+    pts = np.ascontiguousarray(points, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    sg = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+    nf = len(frame.keys_un)
+    bi = np.zeros(max(len(pts), 1), np.int32); bd = np.zeros(max(len(pts), 1), np.int32)
+    _check(lib().orbm_window_best_match(_p(frame.keys_un), _p(df), None if ur is None else _p(ur), nf, _p(frame.cell_ptr),
+                                        _p(frame.cell_idx), _p(frame.bounds), _p(sf), None if sg is None else _p(sg), len(sf), _p(pts),
+                                        _p(dp), len(pts), float(th), _p(bi), _p(bd), frame.device), "orbm_window_best_match")
+    return bi[:len(pts)], bd[:len(pts)]
 
 
 def compute_stereo_matches(ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mbf, mb):

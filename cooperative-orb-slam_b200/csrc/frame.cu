@@ -310,6 +310,44 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
     if (tid == 0) *out_nmatches = s_matches;
 }
 
+// ---------------------------------------------------------------- Fuse x2 / SearchBySim3: independent window search
+// One thread per projected point: the best feature of levels [l-1, l] inside the window, first wins; with
+// inv_level_sigma2 the chi-square gates of ORBmatcher.cc:905-931 (7.8 with a right coordinate, 5.99 without; the
+// float product is compared with the double literal as the reference does).
+__global__ void window_best_kernel(const orb_keypoint_t* __restrict__ kps, const uint32_t* __restrict__ desc_f, const float* __restrict__ u_right,
+                                   const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx, GridParams g,
+                                   const float* __restrict__ scale_factors, const float* __restrict__ inv_level_sigma2,
+                                   const orbm_proj_point_t* __restrict__ pts, const uint32_t* __restrict__ desc_p, int n_p, float th,
+                                   int* __restrict__ best_idx, int* __restrict__ best_dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_p) return;
+    const orbm_proj_point_t p = pts[i];
+    int bestDist = 256, bestIdx = -1;
+    if (p.valid) {
+        const int lvl = p.octave;
+        const float radius = __fmul_rn(th, scale_factors[lvl]);
+        const uint32_t* dp = desc_p + (size_t)i * 8;
+        for_features_in_area(kps, cell_ptr, cell_idx, g, p.u, p.v, radius, -1, -1, [&](int idx) {
+            const int kl = kps[idx].octave;
+            if (kl < lvl - 1 || kl > lvl) return true;
+            if (inv_level_sigma2) {
+                const float ex = __fsub_rn(p.u, kps[idx].x), ey = __fsub_rn(p.v, kps[idx].y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                const float kr = u_right[idx];
+                if (kr >= 0) {
+                    const float er = __fsub_rn(p.ur, kr);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    if ((double)__fmul_rn(e2, inv_level_sigma2[kl]) > 7.8) return true;
+                } else if ((double)__fmul_rn(e2, inv_level_sigma2[kl]) > 5.99) return true;
+            }
+            const int dist = hamming32(dp, desc_f + (size_t)idx * 8);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+            return true;
+        });
+    }
+    best_idx[i] = bestIdx; best_dist[i] = bestDist;
+}
+
 static GridParams make_grid_params(const float* bounds);
 
 // uploads the frame and the windows, runs the search, downloads feature -> point, point -> feature and the count
@@ -539,7 +577,7 @@ int orbm_search_by_projection_frame(const orb_keypoint_t* kps_un, const uint8_t*
                              out_feature_point, out_point_feature, n_matches, device);
 }
 
-static int best_only_search(const char* who, bool keyframe_mode, const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right,
+static int best_only_search(const char* who, bool keyframe_mode, int level_up, const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right,
                             const uint8_t* occupied, int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
                             const float* scale_factors, int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th,
                             int direction, int check_orientation, int threshold, int32_t* out_feature_point, int32_t* out_point_feature,
@@ -556,7 +594,8 @@ static int best_only_search(const char* who, bool keyframe_mode, const orb_keypo
         const int oct = p.octave;
         if (oct < 0 || oct >= n_levels) { set_error("%s: point %d has octave %d of %d", who, i, oct, n_levels); return ORB_ERR_ARG; }
         w.x = p.u; w.y = p.v; w.r = th * scale_factors[oct];      // :1381, :1529
-        if (keyframe_mode || direction == 0) { w.min_level = oct - 1; w.max_level = oct + 1; }      // :1390, :1531
+        if (keyframe_mode) { w.min_level = oct - 1; w.max_level = oct + level_up; }                  // :1531 (+1), :364-367 (+0)
+        else if (direction == 0) { w.min_level = oct - 1; w.max_level = oct + 1; }                   // :1390
         else if (direction == 1) { w.min_level = oct; w.max_level = -1; }                            // :1386
         else { w.min_level = 0; w.max_level = oct; }                                                 // :1388
         w.ur = p.ur;
@@ -578,7 +617,7 @@ int orbm_search_by_projection_last_frame(const orb_keypoint_t* kps_un, const uin
                                          const float* scale_factors, int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts,
                                          int n_pts, float th, int direction, int check_orientation, int th_high,
                                          int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device) {
-    return best_only_search("orbm_search_by_projection_last_frame", false, kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds,
+    return best_only_search("orbm_search_by_projection_last_frame", false, 1, kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds,
                             scale_factors, n_levels, pts, desc_pts, n_pts, th, direction, check_orientation, th_high, out_feature_point,
                             out_point_feature, n_matches, device);
 }
@@ -588,9 +627,54 @@ int orbm_search_by_projection_keyframe(const orb_keypoint_t* kps_un, const uint8
                                        int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int orb_dist,
                                        int check_orientation, int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches,
                                        int device) {
-    return best_only_search("orbm_search_by_projection_keyframe", true, kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds,
+    return best_only_search("orbm_search_by_projection_keyframe", true, 1, kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds,
                             scale_factors, n_levels, pts, desc_pts, n_pts, th, 0, check_orientation, orb_dist, out_feature_point,
                             out_point_feature, n_matches, device);
+}
+
+int orbm_search_by_projection_sim3(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f, const int32_t* cell_ptr,
+                                   const int32_t* cell_idx, const float* bounds, const float* scale_factors, int n_levels,
+                                   const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int th_low,
+                                   int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device) {
+    return best_only_search("orbm_search_by_projection_sim3", true, 0, kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds,
+                            scale_factors, n_levels, pts, desc_pts, n_pts, th, 0, 0, th_low, out_feature_point, out_point_feature, n_matches,
+                            device);
+}
+
+int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right, int n_f, const int32_t* cell_ptr,
+                           const int32_t* cell_idx, const float* bounds, const float* scale_factors, const float* inv_level_sigma2, int n_levels,
+                           const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int32_t* best_idx, int32_t* best_dist,
+                           int device) {
+    if (n_f < 0 || n_pts < 0 || n_levels <= 0 || !bounds || !cell_ptr || !scale_factors || (n_f && (!kps_un || !desc_f || !cell_idx)) ||
+        (n_pts && (!pts || !desc_pts || !best_idx || !best_dist)) || (inv_level_sigma2 && n_f && !u_right)) {
+        set_error("orbm_window_best_match: bad arguments (u_right is required with inv_level_sigma2)");
+        return ORB_ERR_ARG;
+    }
+    for (int i = 0; i < n_pts; i++) {
+        if (pts[i].valid && (pts[i].octave < 0 || pts[i].octave >= n_levels)) { set_error("orbm_window_best_match: point %d predicts level %d of %d", i, pts[i].octave, n_levels); return ORB_ERR_ARG; }
+        best_idx[i] = -1; best_dist[i] = 256;
+    }
+    if (n_f == 0 || n_pts == 0) return ORB_OK;
+    MatchCtx& cx = match_ctx();
+    const size_t kb = (size_t)n_f * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4;
+    const size_t need = kb + (size_t)n_f * (32 + 4 + 4) + pb + (size_t)n_levels * 8 + (size_t)n_pts * (sizeof(orbm_proj_point_t) + 32 + 8) + 20 * 256;
+    if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
+    const orb_keypoint_t* d_k = (const orb_keypoint_t*)cx.upload(kps_un, kb);
+    const uint32_t* d_df = (const uint32_t*)cx.upload(desc_f, (size_t)n_f * 32);
+    const float* d_ur = inv_level_sigma2 ? (const float*)cx.upload(u_right, (size_t)n_f * 4) : nullptr;
+    const int* d_cp = (const int*)cx.upload(cell_ptr, pb);
+    const int* d_ci = (const int*)cx.upload(cell_idx, (size_t)n_f * 4);
+    const float* d_sf = (const float*)cx.upload(scale_factors, (size_t)n_levels * 4);
+    const float* d_is = inv_level_sigma2 ? (const float*)cx.upload(inv_level_sigma2, (size_t)n_levels * 4) : nullptr;
+    const orbm_proj_point_t* d_p = (const orbm_proj_point_t*)cx.upload(pts, (size_t)n_pts * sizeof(orbm_proj_point_t));
+    const uint32_t* d_dp = (const uint32_t*)cx.upload(desc_pts, (size_t)n_pts * 32);
+    int* d_bi = (int*)cx.dalloc((size_t)n_pts * 4); int* d_bd = (int*)cx.dalloc((size_t)n_pts * 4);
+    if (!d_k || !d_df || !d_cp || !d_ci || !d_sf || !d_p || !d_dp || !d_bi || !d_bd || (inv_level_sigma2 && (!d_ur || !d_is))) return ORB_ERR_CUDA;
+    window_best_kernel<<<(n_pts + 127) / 128, 128, 0, cx.stream>>>(d_k, d_df, d_ur, d_cp, d_ci, make_grid_params(bounds), d_sf, d_is, d_p, d_dp, n_pts, th,
+                                                                  d_bi, d_bd);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (!cx.download(best_idx, d_bi, (size_t)n_pts * 4) || !cx.download(best_dist, d_bd, (size_t)n_pts * 4) || !cx.finish()) return ORB_ERR_CUDA;
+    return ORB_OK;
 }
 
 }  // extern "C"

@@ -301,6 +301,30 @@ int orbm_search_by_projection_keyframe(const orb_keypoint_t* kps_un, const uint8
                                        int check_orientation, int32_t* out_feature_point, int32_t* out_point_feature,
                                        int* n_matches, int device);
 
+/* int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints,
+ *                                    vector<MapPoint*>& vpMatched, int th)
+ * R21/src/ORBmatcher.cc:290-403 (LoopClosing::ComputeSim3).  pts[i]: u, v (:331-335), octave = PredictScale (:359),
+ * valid = every test of :315-357 passed.  occupied[f] = vpMatched[f] != NULL on entry; th_low = TH_LOW (50). */
+int orbm_search_by_projection_sim3(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
+                                   const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                                   const float* scale_factors, int n_levels, const orbm_proj_point_t* pts,
+                                   const uint8_t* desc_pts, int n_pts, float th, int th_low,
+                                   int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device);
+
+/* The window search inside
+ *   int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th)   R21/src/ORBmatcher.cc:825-975
+ *       (inv_level_sigma2 = pKF->mvInvLevelSigma2: the chi-square gates of :905-931; u_right = pKF->mvuRight; pts[i].ur = :866),
+ *   int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, vpPoints, float th, vpReplacePoint)        :977-1100  (inv_level_sigma2 = NULL),
+ *   int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12, s12, R12, t12, th) :1102-1326 (each of its two passes).
+ * Per point: the best feature of levels [l-1, l] in the window of half size th * scale_factors[l] (first wins):
+ * best_idx[i] (-1: none) and best_dist[i] (256: none).  Points do not influence each other; the caller applies
+ * the reference's map updates / mutual-consistency test (:945-970, :1075-1095, :1300-1323) in its original order. */
+int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right, int n_f,
+                           const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                           const float* scale_factors, const float* inv_level_sigma2, int n_levels,
+                           const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int32_t* best_idx,
+                           int32_t* best_dist, int device);
+
 #ifdef __cplusplus
 }
 #endif

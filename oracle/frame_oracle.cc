@@ -236,7 +236,8 @@ static int projection_body(const orc_keypoint* kps_un, const uint8_t* desc_f, co
         const int oct = p.octave;
         const float radius = th * scale_factors[oct];
         int nc;
-        if (keyframe_mode) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct - 1, oct + 1, cand.data(), n_f);
+        if (keyframe_mode == 2) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct - 1, oct, cand.data(), n_f);
+        else if (keyframe_mode) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct - 1, oct + 1, cand.data(), n_f);
         else if (direction == 1) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct, -1, cand.data(), n_f);
         else if (direction == 2) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, 0, oct, cand.data(), n_f);
         else nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct - 1, oct + 1, cand.data(), n_f);
@@ -303,6 +304,60 @@ int orc_search_by_projection_keyframe(const orc_keypoint* kps_un, const uint8_t*
                                       int32_t* out_point_feature) {
     return projection_body(kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, pts, desc_pts, n_pts, th,
                            0, 1, check_orientation, orb_dist, out_feature_point, out_point_feature);
+}
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th) :290-403 (loop closing) from the
+ * point where (u, v) and the predicted level are known.  KeyFrame::GetFeaturesInArea (KeyFrame.cc:570-609) has no
+ * level filter; the loop applies [l-1, l] itself (:364-367), which selects the same features in the same order.
+ * occupied[f] = vpMatched[f] != NULL on entry; a match sets it (:381).  Threshold TH_LOW (:378), no rotation check. */
+int orc_search_by_projection_sim3(const orc_keypoint* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
+                                  const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                                  const float* scale_factors, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts,
+                                  float th, int th_low, int32_t* out_feature_point, int32_t* out_point_feature) {
+    return projection_body(kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, pts, desc_pts, n_pts, th,
+                           0, 2, 0, th_low, out_feature_point, out_point_feature);
+}
+
+/* The independent window search shared by Fuse(KeyFrame*, vpMapPoints, th) :825-975 (inv_level_sigma2 != NULL: the
+ * chi-square gates of :905-931), Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) :977-1100 and both passes of
+ * SearchBySim3 :1102-1326 (inv_level_sigma2 == NULL): best feature of levels [l-1, l] in the window, first wins.
+ * No point influences another; the map updates after the search stay with the caller.  best_dist = 256 and
+ * best_idx = -1 when nothing qualifies (the reference starts from 256 or INT_MAX; both fail every threshold). */
+void orc_window_best_match(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right, int n_f,
+                           const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* scale_factors,
+                           const float* inv_level_sigma2, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts, float th,
+                           int32_t* best_idx, int32_t* best_dist) {
+    std::vector<int32_t> cand((size_t)std::max(n_f, 1));
+    for (int i = 0; i < n_pts; i++) {
+        best_idx[i] = -1; best_dist[i] = 256;
+        const orc_proj_point& p = pts[i];
+        if (!p.valid) continue;
+        const int lvl = p.octave;
+        const float radius = th * scale_factors[lvl];
+        const float u = p.u, v = p.v, ur = p.ur;
+        const int nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, u, v, radius, -1, -1, cand.data(), n_f);
+        int bestDist = 256, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = cand[c];
+            const orc_keypoint& kp = kps_un[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            if (inv_level_sigma2) {
+                if (u_right[idx] >= 0) {
+                    const float ex = u - kp.x, ey = v - kp.y, er = ur - u_right[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float ex = u - kp.x, ey = v - kp.y;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = orc_descriptor_distance(desc_pts + (size_t)i * 32, desc_f + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        best_idx[i] = bestIdx; best_dist[i] = bestDist;
+    }
 }
 
 }  // extern "C"

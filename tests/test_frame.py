@@ -282,3 +282,37 @@ def test_gpu_search_by_projection_keyframe(orb, oracle, synth, golden_dir, nf, n
         got = orb.search_by_projection_keyframe(fr, desc_f, occ, sf, pts, dp, th, orb_dist, check_orientation=check)
         assert got[2] == ref[2] and np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
     assert ref[2] > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nf,npts,crowded,th", [(1400, 2500, False, 10.0), (180, 1500, True, 4.0)])
+def test_gpu_search_by_projection_sim3(orb, oracle, synth, golden_dir, nf, npts, crowded, th):
+    g = _golden(golden_dir)
+    K, D = g["barrel_K"], g["barrel_D"]
+    keys, desc_f, sf, rng = _scene(oracle, synth, nf, 0, 700 + nf, K, D, crowded)
+    fr = orb.FrameFeatures(keys, K, D, 640, 480)
+    pts, dp = _proj_points(oracle, fr.keys_un, desc_f, npts, rng)
+    occ = (rng.random(nf) < 0.3).astype(np.uint8)
+    ref = oracle.search_by_projection_sim3(fr.keys_un, desc_f, occ, fr.cell_ptr, fr.cell_idx, fr.bounds, sf, pts, dp, th)
+    got = orb.search_by_projection_sim3(fr, desc_f, occ, sf, pts, dp, th)
+    assert got[2] == ref[2] > 10 and np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gated", [True, False])
+def test_gpu_window_best_match_fuse_and_sim3(orb, oracle, synth, golden_dir, gated):
+    g = _golden(golden_dir)
+    K, D = g["tum1_K"], g["tum1_D"]
+    nf, npts = 1600, 3000
+    keys, desc_f, sf, rng = _scene(oracle, synth, nf, 0, 900 + gated, K, D)
+    fr = orb.FrameFeatures(keys, K, D, 640, 480)
+    pts, dp = _proj_points(oracle, fr.keys_un, desc_f, npts, rng)
+    ur = np.where(rng.random(nf) < 0.5, fr.keys_un["x"] - rng.uniform(0, 30, nf), -1).astype(np.float32)
+    pts["ur"] = np.where(rng.random(npts) < 0.7, pts["u"] - 15, pts["ur"])
+    sig = (1.0 / (sf * sf)).astype(np.float32) if gated else None
+    for th in (3.0, 2.5, 8.0):
+        ref = oracle.window_best_match(fr.keys_un, desc_f, ur if gated else None, fr.cell_ptr, fr.cell_idx, fr.bounds, sf, sig, pts, dp, th)
+        got = orb.window_best_match(fr, desc_f, sf, pts, dp, th, u_right=ur if gated else None, inv_level_sigma2=sig)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+        assert (ref[0] >= 0).sum() > 100
+    assert np.all(ref[0][pts["valid"] == 0] == -1) and np.all(ref[1][pts["valid"] == 0] == 256)
