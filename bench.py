@@ -397,6 +397,36 @@ def run_ours(args):
         loops = {"search_by_bow_kf_f_ms": {"gpu_call": timeit(lambda: mt.SearchByBoW(d1, a1, valid, fv1, d2, a2, fv2)),
                                            "cpu_oracle_1thread": timeit(lambda: oracle_lib.search_by_bow_kf_f(d1, a1, valid, fv1, d2, a2, fv2, 0.7, True))},
                  "features": [len(d1), len(d2)], "note": "host arrays in/out, includes H2D/D2H; problem is tiny (~17 candidates per feature)"}
+        # frame side: undistort + bounds + grid, then SearchByProjection(Frame, local map)
+        frng = np.random.default_rng(5)
+        nf, nmp = 2000, 4000
+        fk = np.zeros(nf, orb.KP_DTYPE)
+        lv = frng.integers(0, 8, nf); sc = 1.2 ** lv
+        fk["x"] = (frng.integers(16, (640 / sc - 16).astype(int)) * sc).astype(np.float32)
+        fk["y"] = (frng.integers(16, (480 / sc - 16).astype(int)) * sc).astype(np.float32)
+        fk["octave"] = lv; fk["angle"] = frng.uniform(0, 360, nf).astype(np.float32)
+        Kc = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
+        Dc = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+        fdesc = synth.descriptors(nf, seed=77)
+        fr = orb.FrameFeatures(fk, Kc, Dc, 640, 480, device=local)
+        mpv = np.zeros(nmp, orb.MPV_DTYPE)
+        srcf = frng.integers(0, nf, nmp)
+        mpv["proj_x"] = fr.keys_un["x"][srcf] + frng.normal(0, 2, nmp).astype(np.float32)
+        mpv["proj_y"] = fr.keys_un["y"][srcf] + frng.normal(0, 2, nmp).astype(np.float32)
+        mpv["proj_xr"] = mpv["proj_x"] - 10; mpv["view_cos"] = 0.999; mpv["level"] = fr.keys_un["octave"][srcf]
+        mpv["in_view"] = 1; mpv["obs_positive"] = 1
+        mdesc = fdesc[srcf].copy(); mdesc[:, 0] ^= frng.integers(0, 256, nmp).astype(np.uint8)
+        sfac = (1.2 ** np.arange(8)).astype(np.float32)
+        ur0 = np.full(nf, -1, np.float32); occ0 = np.zeros(nf, np.uint8)
+        loops["frame_build_ms"] = {
+            "gpu_call": timeit(lambda: orb.FrameFeatures(fk, Kc, Dc, 640, 480, device=local)),
+            "cpu_oracle_1thread": timeit(lambda: (oracle_lib.image_bounds(640, 480, Kc, Dc),
+                                                  oracle_lib.assign_grid(oracle_lib.undistort_keypoints(fk, Kc, Dc), fr.bounds)))}
+        loops["search_by_projection_frame_ms"] = {
+            "gpu_call": timeit(lambda: orb.search_by_projection_frame(fr, fdesc, ur0, occ0, sfac, mpv, mdesc, th=1.0, nnratio=0.8)),
+            "cpu_oracle_1thread": timeit(lambda: oracle_lib.search_by_projection_frame(fr.keys_un, fdesc, ur0, occ0, fr.cell_ptr, fr.cell_idx,
+                                                                                       fr.bounds, sfac, mpv, mdesc, 1.0, 0.8)),
+            "features": nf, "map_points": nmp}
 
     # ---------------- CPU baseline (rank 0, N=1 only; bounded sample) --------------------------------------
     cpu = None

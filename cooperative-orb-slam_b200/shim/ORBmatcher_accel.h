@@ -154,6 +154,73 @@ void ComputeStereoMatches(Frame& F)
                               F.mbf, F.mbf / F.fx, &F.mvuRight[0], &F.mvDepth[0], &n), "orbm_stereo_matches");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Frame side (R21/src/Frame.cc) and the projection searches that consume it.
+// The reference keeps mGrid[64][48] of std::vector<size_t>; the device path keeps the same lists as CSR.
+struct FrameGrid
+{
+    std::vector<int32_t> cell_ptr, cell_idx;
+    float bounds[4];                       // mnMinX, mnMaxX, mnMinY, mnMaxY
+    FrameGrid() : cell_ptr(ORBF_GRID_COLS * ORBF_GRID_ROWS + 1, 0) { bounds[0] = bounds[1] = bounds[2] = bounds[3] = 0.f; }
+};
+
+// void Frame::UndistortKeyPoints()  :409-439  -- body becomes  orbaccel::UndistortKeyPoints(*this);
+template <class Frame>
+void UndistortKeyPoints(Frame& F, int device = 0)
+{
+    static_assert(sizeof(F.mvKeys[0]) == sizeof(orb_keypoint_t), "cv::KeyPoint layout");
+    F.mvKeysUn.resize(F.mvKeys.size());
+    if(F.mvKeys.empty()) return;
+    const float K[4] = {F.fx, F.fy, F.cx, F.cy};
+    check(orbf_undistort_keypoints(reinterpret_cast<const orb_keypoint_t*>(&F.mvKeys[0]), (int)F.mvKeys.size(), K,
+                                   F.mDistCoef.template ptr<float>(0), F.mDistCoef.rows,
+                                   reinterpret_cast<orb_keypoint_t*>(&F.mvKeysUn[0]), device), "orbf_undistort_keypoints");
+}
+
+// void Frame::ComputeImageBounds(imLeft) :441-470 + AssignFeaturesToGrid() :235-250
+template <class Frame>
+FrameGrid AssignFeaturesToGrid(const Frame& F, int cols, int rows, int device = 0)
+{
+    FrameGrid g;
+    const float K[4] = {F.fx, F.fy, F.cx, F.cy};
+    check(orbf_image_bounds(cols, rows, K, F.mDistCoef.template ptr<float>(0), F.mDistCoef.rows, g.bounds, device), "orbf_image_bounds");
+    g.cell_idx.resize(F.mvKeysUn.size() ? F.mvKeysUn.size() : 1);
+    int n = 0;
+    check(orbf_assign_grid(F.mvKeysUn.empty() ? 0 : reinterpret_cast<const orb_keypoint_t*>(&F.mvKeysUn[0]), (int)F.mvKeysUn.size(),
+                           g.bounds, &g.cell_ptr[0], &g.cell_idx[0], &n, device), "orbf_assign_grid");
+    return g;
+}
+
+// int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th)  :45-130
+template <class Frame, class MapPoint>
+int SearchByProjection(Frame& F, const FrameGrid& grid, const std::vector<MapPoint*>& vpMapPoints, float th, float nnratio,
+                       int th_high = 100, int device = 0)
+{
+    const int nMP = (int)vpMapPoints.size(), N = (int)F.mvKeysUn.size();
+    if(nMP == 0 || N == 0) return 0;
+    std::vector<orbm_map_point_view_t> mp(nMP);
+    std::vector<unsigned char> desc((size_t)nMP * 32, 0), occ(N);
+    for(int i = 0; i < nMP; i++)
+    {
+        MapPoint* p = vpMapPoints[i];
+        mp[i].in_view = p->mbTrackInView && !p->isBad();                       // :52-56
+        mp[i].proj_x = p->mTrackProjX; mp[i].proj_y = p->mTrackProjY; mp[i].proj_xr = p->mTrackProjXR;
+        mp[i].view_cos = p->mTrackViewCos; mp[i].level = p->mnTrackScaleLevel;
+        mp[i].obs_positive = p->Observations() > 0;
+        if(mp[i].in_view) std::memcpy(&desc[(size_t)i * 32], p->GetDescriptor().ptr(0), 32);
+    }
+    for(int f = 0; f < N; f++) occ[f] = F.mvpMapPoints[f] && F.mvpMapPoints[f]->Observations() > 0;      // :82-84
+    std::vector<int32_t> fp(N), pf(nMP);
+    int nmatches = 0;
+    check(orbm_search_by_projection_frame(reinterpret_cast<const orb_keypoint_t*>(&F.mvKeysUn[0]), F.mDescriptors.ptr(0), &F.mvuRight[0],
+                                          &occ[0], N, &grid.cell_ptr[0], &grid.cell_idx[0], grid.bounds, &F.mvScaleFactors[0],
+                                          (int)F.mvScaleFactors.size(), &mp[0], &desc[0], nMP, th, nnratio, th_high, &fp[0], &pf[0],
+                                          &nmatches, device), "orbm_search_by_projection_frame");
+    for(int f = 0; f < N; f++)
+        if(fp[f] >= 0) F.mvpMapPoints[f] = vpMapPoints[fp[f]];                 // :121
+    return nmatches;
+}
+
 } // namespace orbaccel
 
 #endif

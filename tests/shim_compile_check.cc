@@ -6,7 +6,12 @@
 #include "ORBextractor.h"
 #include "ORBmatcher_accel.h"
 
-struct MapPoint { bool isBad() { return false; } };
+struct MapPoint {
+    bool isBad() { return false; }
+    bool mbTrackInView; float mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos; int mnTrackScaleLevel;
+    int Observations() { return 1; }
+    cv::Mat GetDescriptor() { return cv::Mat(); }
+};
 typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
 struct KeyFrame {
     int N;
@@ -20,9 +25,11 @@ struct KeyFrame {
 };
 struct Frame {
     int N;
-    float mbf, fx;
-    std::vector<cv::KeyPoint> mvKeys, mvKeysRight;
-    std::vector<float> mvuRight, mvDepth;
+    float mbf, fx, fy, cx, cy;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<float> mvuRight, mvDepth, mvScaleFactors;
+    std::vector<MapPoint*> mvpMapPoints;
+    cv::Mat mDistCoef;
     cv::Mat mDescriptors, mDescriptorsRight;
     FeatureVector mFeatVec;
     ORB_SLAM2::ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
@@ -36,6 +43,9 @@ int shim_instantiate(KeyFrame* a, KeyFrame* b, Frame& f) {
     n += orbaccel::SearchByBoW_KF_KF(a, b, out, 0.75f, true);
     n += orbaccel::SearchForTriangulation(a, b, F12, 0.f, 0.f, pairs, false, false);
     orbaccel::ComputeStereoMatches(f);
+    orbaccel::UndistortKeyPoints(f);
+    orbaccel::FrameGrid grid = orbaccel::AssignFeaturesToGrid(f, 640, 480);
+    n += orbaccel::SearchByProjection(f, grid, out, 1.0f, 0.8f);
     ORB_SLAM2::ORBextractor e(1000, 1.2f, 8, 20, 7);
     std::vector<cv::KeyPoint> k; cv::Mat d, img;
     e(img, cv::Mat(), k, d);
