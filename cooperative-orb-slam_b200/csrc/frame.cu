@@ -140,8 +140,10 @@ __device__ __forceinline__ AreaWindow area_window(const GridParams& g, float x, 
 }
 
 // visits the indices GetFeaturesInArea would return, in its order; f(idx) returns false to stop early
-template <class F>
-__device__ __forceinline__ void for_features_in_area(const orb_keypoint_t* __restrict__ kps, const int* __restrict__ cell_ptr,
+struct KpLite { float x, y; int octave; };      // what the window walk reads of a key point (shared-memory copy)
+
+template <class KP, class F>
+__device__ __forceinline__ void for_features_in_area(const KP* __restrict__ kps, const int* __restrict__ cell_ptr,
                                                      const int* __restrict__ cell_idx, const GridParams& g, float x, float y, float r,
                                                      int min_level, int max_level, F f) {
     const AreaWindow w = area_window(g, x, y, r);
@@ -238,25 +240,48 @@ __device__ __forceinline__ int hamming32(const uint32_t* __restrict__ a, const u
 }
 
 // RATIO: best and second best with the same-level ratio rule (:99-125); otherwise best only (:1419-1424, :1551-1555)
-template <bool RATIO>
-__global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_t* __restrict__ kps, const uint32_t* __restrict__ desc_f,
+// STAGED: key points (x, y, octave), cell_ptr and cell_idx are copied to shared memory first, so the three window
+// walks per round run at shared-memory latency (frames up to kStagedMaxFeatures features; larger ones walk global memory)
+constexpr int kStagedMaxFeatures = 8192;
+
+template <bool RATIO, bool STAGED>
+__global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_t* __restrict__ kps_g, const uint32_t* __restrict__ desc_f,
                                                              const float* __restrict__ u_right, const uint8_t* __restrict__ occupied, int n_f,
-                                                             const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx, GridParams g,
+                                                             const int* __restrict__ cell_ptr_g, const int* __restrict__ cell_idx_g, GridParams g,
                                                              const ProjWindow* __restrict__ wins, const uint32_t* __restrict__ desc_p, int n_p,
                                                              float nnratio, int threshold, int* __restrict__ out_feature_point,
                                                              int* __restrict__ out_point_feature, uint8_t* __restrict__ resolved,
                                                              int* __restrict__ out_nmatches) {
     extern __shared__ int s_dyn[];
     int* s_claim = s_dyn;                                             // [n_f]
-    uint8_t* s_blocked = reinterpret_cast<uint8_t*>(s_dyn + n_f);    // [n_f]
+    int* s_cell_idx = s_claim + n_f;                                  // [n_f]            (STAGED)
+    int* s_cell_ptr = s_cell_idx + (STAGED ? n_f : 0);                // [kGridCells + 1] (STAGED)
+    KpLite* s_kp = reinterpret_cast<KpLite*>(s_cell_ptr + (STAGED ? kGridCells + 1 : 0));      // [n_f] (STAGED)
+    uint8_t* s_blocked = reinterpret_cast<uint8_t*>(s_kp + (STAGED ? n_f : 0));                 // [n_f]
     __shared__ int s_left, s_matches;
     const int tid = threadIdx.x;
-    for (int f = tid; f < n_f; f += 1024) { s_blocked[f] = occupied[f]; out_feature_point[f] = -1; }
+    for (int f = tid; f < n_f; f += 1024) {
+        s_blocked[f] = occupied[f]; out_feature_point[f] = -1;
+        if (STAGED) {
+            s_cell_idx[f] = cell_idx_g[f];
+            KpLite k; k.x = kps_g[f].x; k.y = kps_g[f].y; k.octave = kps_g[f].octave;
+            s_kp[f] = k;
+        }
+    }
+    if (STAGED)
+        for (int c = tid; c <= kGridCells; c += 1024) s_cell_ptr[c] = cell_ptr_g[c];
     for (int i = tid; i < n_p; i += 1024) {
         out_point_feature[i] = -1;
         resolved[i] = (wins[i].flags & kWinValid) ? 0 : 1;
     }
     if (tid == 0) s_matches = 0;
+    const int* cell_ptr = STAGED ? s_cell_ptr : cell_ptr_g;
+    const int* cell_idx = STAGED ? s_cell_idx : cell_idx_g;
+    auto walk = [&](const ProjWindow& w, auto f) {
+        if (STAGED) for_features_in_area(s_kp, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level, f);
+        else for_features_in_area(kps_g, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level, f);
+    };
+    auto octave_of = [&](int idx) { return STAGED ? s_kp[idx].octave : kps_g[idx].octave; };
     while (true) {
         __syncthreads();
         for (int f = tid; f < n_f; f += 1024) s_claim[f] = 0x7fffffff;
@@ -265,20 +290,18 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
         for (int i = tid; i < n_p; i += 1024) {
             if (resolved[i]) continue;
             const ProjWindow w = wins[i];
-            for_features_in_area(kps, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level,
-                                 [&](int idx) { atomicMin(&s_claim[idx], i); return true; });
+            walk(w, [&](int idx) { atomicMin(&s_claim[idx], i); return true; });
         }
         __syncthreads();
         for (int i = tid; i < n_p; i += 1024) {
             if (resolved[i]) continue;
             const ProjWindow w = wins[i];
+            // one walk: search as if the point were safe, give up as soon as a candidate belongs to an earlier one
             bool safe = true;
-            for_features_in_area(kps, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level,
-                                 [&](int idx) { safe = s_claim[idx] >= i; return safe; });
-            if (!safe) { atomicAdd(&s_left, 1); continue; }
             int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
             const uint32_t* dp = desc_p + (size_t)i * 8;
-            for_features_in_area(kps, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level, [&](int idx) {
+            walk(w, [&](int idx) {
+                if (s_claim[idx] < i) { safe = false; return false; }
                 if (s_blocked[idx]) return true;
                 if ((w.flags & kWinStereo) && u_right[idx] > 0) {
                     const float er = fabsf(__fsub_rn(w.ur, u_right[idx]));
@@ -287,14 +310,15 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
                 const int dist = hamming32(dp, desc_f + (size_t)idx * 8);
                 if (dist < bestDist) {
                     bestDist2 = bestDist; bestDist = dist;
-                    bestLevel2 = bestLevel; bestLevel = kps[idx].octave;
+                    bestLevel2 = bestLevel; bestLevel = octave_of(idx);
                     bestIdx = idx;
                 } else if (RATIO && dist < bestDist2) {
-                    bestLevel2 = kps[idx].octave;
+                    bestLevel2 = octave_of(idx);
                     bestDist2 = dist;
                 }
                 return true;
             });
+            if (!safe) { atomicAdd(&s_left, 1); continue; }
             resolved[i] = 1;
             if (bestDist <= threshold) {
                 if (RATIO && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
@@ -373,18 +397,22 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     int* d_fp = (int*)cx.dalloc((size_t)n_f * 4); int* d_pf = (int*)cx.dalloc((size_t)n_p * 4);
     uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_p); int* d_nm = (int*)cx.dalloc(4);
     if (!d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm) return ORB_ERR_CUDA;
+    const bool staged = n_f <= kStagedMaxFeatures;
     static bool configured = false;
     if (!configured) {
-        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 5 + 16));
-        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 5 + 16));
+        const int big = kFrameMaxFeatures * 5 + 16, small = kStagedMaxFeatures * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16;
+        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
         configured = true;
     }
-    const size_t smem = (size_t)n_f * 5 + 16;
+    const size_t smem = staged ? (size_t)n_f * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16 : (size_t)n_f * 5 + 16;
     const GridParams g = make_grid_params(bounds);
-    if (ratio)
-        window_search_kernel<true><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_nm);
-    else
-        window_search_kernel<false><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_nm);
+#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_nm)
+    if (ratio) { if (staged) ORB_LAUNCH_WS(true, true); else ORB_LAUNCH_WS(true, false); }
+    else { if (staged) ORB_LAUNCH_WS(false, true); else ORB_LAUNCH_WS(false, false); }
+#undef ORB_LAUNCH_WS
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(out_feature_point, d_fp, (size_t)n_f * 4) || !cx.download(out_point_feature, d_pf, (size_t)n_p * 4) ||
         !cx.download(n_matches, d_nm, 4) || !cx.finish()) return ORB_ERR_CUDA;

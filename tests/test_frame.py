@@ -191,7 +191,7 @@ def test_gpu_features_in_area(orb, oracle, golden_dir):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("nf,nmp,crowded,th", [(1200, 2500, False, 1.0), (1500, 4000, False, 3.0), (300, 3000, True, 1.0),
-                                              (64, 900, True, 5.0), (1, 5, False, 1.0)])
+                                              (64, 900, True, 5.0), (1, 5, False, 1.0), (9000, 5000, False, 2.0)])
 def test_gpu_search_by_projection_frame(orb, oracle, synth, golden_dir, nf, nmp, crowded, th):
     g = _golden(golden_dir)
     K, D = g["tum1_K"], g["tum1_D"]
