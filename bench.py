@@ -45,6 +45,23 @@ def _peaks():
         return 6650.0, "fallback"
 
 
+def _ncu_traffic(csv_name, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` summary under
+    profiles/ (a static capture of the same kernel and workload; None if the file or the kernel is missing)."""
+    import csv
+    try:
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", csv_name))))
+        head, units = rows[0], rows[1]
+        ir, iw = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel_substr in r[0]:
+                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    except Exception:
+        pass
+    return None
+
+
 def _bf16_peak():
     """Dense bf16 TFLOP/s: MEASURED_PEAKS.json (burst), else the profiling guide's nominal figure."""
     try:
@@ -299,7 +316,10 @@ def run_ours(args):
                   "pyramid": "instruction bound (fixed-point taps, byte gathers from the staged tile), 8 dependent launches",
                   "blur": "issue bound", "cell_nms": "issue bound"}[dkey]
     roof = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src, "note": bound_note,
+            "traffic": _ncu_traffic("r1_ncu_full_final_summary.csv", {"fast_score": "fast_score_kernel", "pyramid": "pyr_resize", "blur": "blur7_kernel<0>",
+                                                                      "cell_nms": "fast_nms_kernel"}[dkey]),
+            "traffic_note": "DRAM bytes of one launch (64 frames) from the ncu capture in profiles/; algorithmic bytes per launch = %d" % (BYTES[dkey] * B),
+            "peak_source": peak_src, "note": bound_note,
             "algorithmic_bytes_per_frame": BYTES[dkey], "kernel_ms_per_launch": kern[dkey]}
     roof["stage_ms_per_batch"] = {k: round(v, 4) for k, v in acc.items()}
     roof["stage_gbs"] = {k: round(BYTES[k] * B / (kern[k] * 1e-3) / 1e9, 1) for k in BYTES if kern.get(k, 0) > 0}
@@ -369,7 +389,8 @@ def run_ours(args):
                     "map_shards": world, "d1_checksum": chk,
                     # one comparison = 256 int8 MACs on the tensor pipe; int8 dense peak = 2 x the measured bf16 peak
                     "roofline": {"bound": "tensor", "achieved": 2 * 256 * gcmp / 1e3, "peak": 2 * _bf16_peak()[0],
-                                 "unit": "TOP/s", "frac": 2 * 256 * gcmp / 1e3 / (2 * _bf16_peak()[0]), "traffic": None,
+                                 "unit": "TOP/s", "frac": 2 * 256 * gcmp / 1e3 / (2 * _bf16_peak()[0]),
+                                 "traffic": _ncu_traffic("r1_ncu_knn2_tcgen05.csv", "knn2_tc_kernel"),
                                  "peak_source": "2 x bf16 burst peak (" + _bf16_peak()[1] + "; int8 runs at twice the bf16 rate); ncu: tensor pipe 71 % active, "
                                                 "shared-memory data pipe 93 % (operand reads + expansion stores) -- profiles/r1_ncu_knn2_tcgen05.csv"},
                     "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8,
