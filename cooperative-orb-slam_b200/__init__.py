@@ -94,6 +94,10 @@ ABI = {
                                                _VP, _VP, _VP, _I]),
     "orbm_search_by_projection_sim3": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _VP, _VP, _VP, _I]),
     "orbm_window_best_match": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _VP, _VP, _I]),
+    "orbv_create": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "orbv_destroy": (_I, [_VP]),
+    "orbv_transform": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
+    "orbv_bow_vectors": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
 }
 
 
@@ -553,6 +557,45 @@ def window_best_match(frame, desc_f, scale_factors, points, desc_pts, th, u_righ
                                         _p(frame.cell_idx), _p(frame.bounds), _p(sf), None if sg is None else _p(sg), len(sf), _p(pts),
                                         _p(dp), len(pts), float(th), _p(bi), _p(bd), frame.device), "orbm_window_best_match")
     return bi[:len(pts)], bd[:len(pts)]
+
+
+class ORBVocabulary:
+    """The device-resident vocabulary tree behind Frame::ComputeBoW (R21/src/Frame.cc:400-407):
+    transform(descriptors, levelsup=4) -> (BowVector as (words, values), FeatureVector as (nodes, ptr, idx))."""
+
+    def __init__(self, child_ptr, child_idx, node_desc, word_id, weight, depth_L, device=0):
+        cp = np.ascontiguousarray(child_ptr, np.int32); ci = np.ascontiguousarray(child_idx, np.int32)
+        nd = np.ascontiguousarray(node_desc, np.uint8); wi = np.ascontiguousarray(word_id, np.int32)
+        wt = np.ascontiguousarray(weight, np.float64)
+        self._h = C.c_void_p()
+        _check(lib().orbv_create(_p(cp), _p(ci), _p(nd), _p(wi), _p(wt), len(cp) - 1, int(depth_L), device, C.byref(self._h)), "orbv_create")
+
+    def close(self):
+        if self._h:
+            lib().orbv_destroy(self._h); self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform_features(self, desc, levelsup=4):
+        """Per-feature (word id, node id, weight)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        w = np.zeros(len(d), np.int32); nd = np.zeros(len(d), np.int32); wt = np.zeros(len(d), np.float64)
+        _check(lib().orbv_transform(self._h, _p(d), len(d), int(levelsup), _p(w), _p(nd), _p(wt)), "orbv_transform")
+        return w, nd, wt
+
+    def transform(self, desc, levelsup=4, normalize=True):
+        w, nd, wt = self.transform_features(desc, levelsup)
+        n = len(w)
+        bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64)
+        fn = np.zeros(max(n, 1), np.int32); fp = np.zeros(n + 1, np.int32); fi = np.zeros(max(n, 1), np.int32)
+        nw = C.c_int(0); nn = C.c_int(0)
+        _check(lib().orbv_bow_vectors(_p(w), _p(nd), _p(wt), n, int(bool(normalize)), _p(bw), _p(bv), C.byref(nw), _p(fn), _p(fp), _p(fi),
+                                      C.byref(nn)), "orbv_bow_vectors")
+        return (bw[:nw.value], bv[:nw.value]), (fn[:nn.value], fp[:nn.value + 1], fi[:fp[nn.value]])
 
 
 def compute_stereo_matches(ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mbf, mb):

@@ -325,6 +325,29 @@ int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, 
                            const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int32_t* best_idx,
                            int32_t* best_dist, int device);
 
+/* ---------------------------------------------------------------- BoW transform --------------- */
+/* void Frame::ComputeBoW() R21/src/Frame.cc:400-407 / KeyFrame::ComputeBoW() R21/src/KeyFrame.cc:60-69:
+ *     mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4);
+ * (DBoW2::TemplatedVocabulary, R21/include/ORBVocabulary.h:31-32; DBoW2 itself is third-party and not vendored).
+ * The vocabulary tree is passed as flat arrays and kept on the device: node i owns the children
+ * child_idx[child_ptr[i] .. child_ptr[i+1]) (none: a leaf = a word), descriptor node_desc[i][32], and for leaves
+ * word_id[i] / weight[i].  Node 0 is the root; depth_L = the vocabulary's L. */
+typedef struct orbv_handle_s* orbv_handle_t;
+int orbv_create(const int32_t* child_ptr, const int32_t* child_idx, const uint8_t* node_desc, const int32_t* word_id,
+                const double* weight, int n_nodes, int depth_L, int device, orbv_handle_t* out);
+int orbv_destroy(orbv_handle_t h);
+/* transform(feature, word, weight, &nid, levelsup) for n descriptors: greedy descent by Hamming distance, the first
+ * child wins ties; out_node = the ancestor at level depth_L - levelsup (the root, 0, if that is <= 0). */
+int orbv_transform(orbv_handle_t h, const uint8_t* desc, int n, int levelsup, int32_t* out_word, int32_t* out_node,
+                   double* out_weight);
+/* The std::map-shaped results of transform(features, v, fv, levelsup) from the per-feature triples (host side, in
+ * the reference's accumulation order): BowVector = (bow_words ascending, bow_values, L1-normalised if asked),
+ * FeatureVector = CSR (fv_nodes ascending, fv_ptr, fv_idx) -- the layout orbm_featvec_t views.
+ * Buffers: bow_words/bow_values/fv_nodes/fv_idx [n], fv_ptr [n+1]. */
+int orbv_bow_vectors(const int32_t* word, const int32_t* node, const double* weight, int n, int normalize_l1,
+                     int32_t* bow_words, double* bow_values, int* n_words, int32_t* fv_nodes, int32_t* fv_ptr,
+                     int32_t* fv_idx, int* n_fv_nodes);
+
 #ifdef __cplusplus
 }
 #endif

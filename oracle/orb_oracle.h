@@ -221,6 +221,13 @@ void orc_window_best_match(const orc_keypoint* kps_un, const uint8_t* desc_f, co
                            const float* inv_level_sigma2, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts, float th,
                            int32_t* best_idx, int32_t* best_dist);
 
+/* ---- BoW transform (oracle/bow_oracle.cc): DBoW2 TemplatedVocabulary::transform, PARITY UNPINNED (DBoW2 is not vendored) ---- */
+void orc_bow_transform(const uint8_t* desc, int n, const int32_t* child_ptr, const int32_t* child_idx, const uint8_t* node_desc,
+                       const int32_t* word_id, const double* weight, int depth_L, int levelsup, int32_t* out_word,
+                       int32_t* out_node, double* out_weight);
+int orc_bow_vectors(const int32_t* word, const int32_t* node, const double* weight, int n, int normalize_l1, int32_t* bow_words,
+                    double* bow_values, int32_t* fv_nodes, int32_t* fv_ptr, int32_t* fv_idx, int* n_nodes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -457,3 +457,30 @@ def window_best_match(kps_un, desc_f, u_right, ptr, idx, bounds, scale_factors, 
     L.orc_window_best_match(_p(kps_un), _p(df), None if ur is None else _p(ur), len(kps_un), _p(ptr), _p(idx), _p(b), _p(sf),
                             None if sg is None else _p(sg), _p(pts), _p(dp), len(pts), th, _p(bi), _p(bd))
     return bi[:len(pts)], bd[:len(pts)]
+
+
+# ----------------------------------------------------------------------------- BoW transform (oracle/bow_oracle.cc)
+def bow_transform(desc, voc, levelsup=4):
+    """voc = dict(child_ptr, child_idx, node_desc, word_id, weight, L) -> per-feature (word, node, weight)."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    w = np.zeros(len(d), np.int32); nd = np.zeros(len(d), np.int32); wt = np.zeros(len(d), np.float64)
+    L = lib()
+    L.orc_bow_transform.restype = None
+    L.orc_bow_transform.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_bow_transform(_p(d), len(d), _p(voc["child_ptr"]), _p(voc["child_idx"]), _p(voc["node_desc"]), _p(voc["word_id"]),
+                        _p(voc["weight"]), voc["L"], levelsup, _p(w), _p(nd), _p(wt))
+    return w, nd, wt
+
+
+def bow_vectors(word, node, weight, normalize=True):
+    n = len(word)
+    word = np.ascontiguousarray(word, np.int32); node = np.ascontiguousarray(node, np.int32); weight = np.ascontiguousarray(weight, np.float64)
+    bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64)
+    fn = np.zeros(max(n, 1), np.int32); fp = np.zeros(n + 1, np.int32); fi = np.zeros(max(n, 1), np.int32)
+    nn = C.c_int(0)
+    L = lib()
+    L.orc_bow_vectors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    nw = L.orc_bow_vectors(_p(word), _p(node), _p(weight), n, int(normalize), _p(bw), _p(bv), _p(fn), _p(fp), _p(fi), C.byref(nn))
+    return (bw[:nw], bv[:nw]), (fn[:nn.value], fp[:nn.value + 1], fi[:fp[nn.value]])
