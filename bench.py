@@ -259,6 +259,41 @@ def run_ours(args):
     value = world * B * args.steps / (dev_ms * 1e-3)
     kp_mean = float(d_cnt[0].float().mean().item())
 
+    # ---------------- cooperative key-frame exchange (N > 1): the agent -> server message of the reference -----
+    # 10 key frames per agent per message (ros_mono.cc:1943-1948), device-resident extractor output, int16 wire
+    # truncation applied on the device, one ncclAllGather per array over NVLink.
+    exchange = None
+    if world > 1:
+        KF = 10
+        L = orb.lib()
+        import ctypes as C
+        kf_k = d_kps[0][:KF].contiguous(); kf_d = d_desc[0][:KF].contiguous(); kf_c = d_cnt[0][:KF].contiguous()
+        all_k = torch.empty((world,) + tuple(kf_k.shape), dtype=kf_k.dtype, device=dev)
+        all_d = torch.empty((world,) + tuple(kf_d.shape), dtype=kf_d.dtype, device=dev)
+        all_c = torch.empty((world,) + tuple(kf_c.shape), dtype=kf_c.dtype, device=dev)
+        cur = torch.cuda.current_stream(dev)
+
+        def exchange_step():
+            rc = L.orbw_quantize_lcm_device(C.c_void_p(kf_k.data_ptr()), C.c_void_p(kf_c.data_ptr()), KF, cap, C.c_void_p(cur.cuda_stream))
+            assert rc == 0
+            dist.all_gather_into_tensor(all_k, kf_k); dist.all_gather_into_tensor(all_d, kf_d); dist.all_gather_into_tensor(all_c, kf_c)
+
+        torch.cuda.synchronize(dev)
+        for _ in range(3):
+            exchange_step()
+        barrier()
+        x0 = torch.cuda.Event(enable_timing=True); x1 = torch.cuda.Event(enable_timing=True)
+        x0.record(cur)
+        for _ in range(20):
+            exchange_step()
+        x1.record(cur)
+        barrier()
+        xms = max_over_ranks(x0.elapsed_time(x1)) / 20
+        msg = kf_k.numel() * 4 + kf_d.numel() + kf_c.numel() * 4
+        exchange = {"keyframes_per_agent": KF, "bytes_per_agent": msg, "ms_per_exchange": xms,
+                    "allgather_gbs": world * msg / (xms * 1e-3) / 1e9,
+                    "note": "reference: one LCM UDP-multicast message of 10 key frames, descriptors as float32 (4x the bytes)"}
+
     # ---------------- e2e: host buffers, H2D + D2H inside the timed region ---------------------------------
     pin_in = [orb.PinnedArray((B, H, W), np.uint8) for _ in range(pool)]
     for p in range(pool):
@@ -469,7 +504,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "keypoints_downloaded": tot_kp},
                 "gpu_launches": int(launches), "clocks": clocks, "matching": matching,
-                "single_frame_latency_ms": latency_ms, "candidate_loops": loops}
+                "single_frame_latency_ms": latency_ms, "candidate_loops": loops, "keyframe_exchange": exchange}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

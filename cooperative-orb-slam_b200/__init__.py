@@ -98,6 +98,8 @@ ABI = {
     "orbv_destroy": (_I, [_VP]),
     "orbv_transform": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "orbv_bow_vectors": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "orbw_quantize_lcm_host": (_I, [_VP, _I]),
+    "orbw_quantize_lcm_device": (_I, [_VP, _VP, _I, _I, _VP]),
 }
 
 
@@ -557,6 +559,14 @@ def window_best_match(frame, desc_f, scale_factors, points, desc_pts, th, u_righ
                                         _p(frame.cell_idx), _p(frame.bounds), _p(sf), None if sg is None else _p(sg), len(sf), _p(pts),
                                         _p(dp), len(pts), float(th), _p(bi), _p(bd), frame.device), "orbm_window_best_match")
     return bi[:len(pts)], bd[:len(pts)]
+
+
+def quantize_lcm(keys):
+    """Key points as the reference's server receives them (int16 truncation of the LCM message,
+    R21/include/lcmKeyFrame/lcmKeyPoint.hpp:19-31)."""
+    k = np.ascontiguousarray(keys, KP_DTYPE).copy()
+    _check(lib().orbw_quantize_lcm_host(_p(k), len(k)), "orbw_quantize_lcm_host")
+    return k
 
 
 class ORBVocabulary:

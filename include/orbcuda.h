@@ -348,6 +348,16 @@ int orbv_bow_vectors(const int32_t* word, const int32_t* node, const double* wei
                      int32_t* bow_words, double* bow_values, int* n_words, int32_t* fv_nodes, int32_t* fv_ptr,
                      int32_t* fv_idx, int* n_fv_nodes);
 
+/* ---------------------------------------------------------------- key-frame message (agent -> server) ---- */
+/* The reference ships key frames as an LCM message whose key points are int16-truncated
+ * (R21/include/lcmKeyFrame/lcmKeyPoint.hpp:19-31, filled R21/Examples/ROS/ORB_SLAM2/src/ros_mono.cc:2071-2077) and whose
+ * descriptors travel one float per byte (lossless).  On one box the message is the device-resident output of
+ * orbx_extract_batch_device exchanged with ncclAllGather; these two calls apply the wire's only lossy step so the
+ * receiver sees what the reference's server sees: x, y, size, response -> (float)(int16_t)v; octave, class_id ->
+ * (int16_t).  Device form: d_kps = [n_frames][cap] key points, d_counts = valid entries per frame (NULL: all cap). */
+int orbw_quantize_lcm_host(orb_keypoint_t* kps, int n);
+int orbw_quantize_lcm_device(void* d_kps, const int32_t* d_counts, int n_frames, int cap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
