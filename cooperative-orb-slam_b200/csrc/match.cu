@@ -952,6 +952,20 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // The per-call scratch comes from the stream-ordered allocator.  With the default release threshold (0) the pool
+    // hands its memory back to the OS at every synchronisation, and the next call pays a map/unmap (0.2 ms typically,
+    // several ms now and then): keep the few MB cached instead.  Once per device.
+    {
+        static bool pool_ready[64] = {false};
+        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_ready[dev] = true;
+        }
+    }
     const int qper = variant >= 3 ? kTcQ : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
     const int tile = variant >= 3 ? kTcN : (variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile));
     const int per_sm = variant >= 3 ? 1 : 2;
