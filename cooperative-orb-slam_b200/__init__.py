@@ -85,6 +85,7 @@ ABI = {
     "orbf_undistort_keypoints": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I]),
     "orbf_image_bounds": (_I, [_I, _I, _VP, _VP, _I, _VP, _I]),
     "orbf_assign_grid": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I]),
+    "orbf_build_frames_device": (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
     "orbf_features_in_area": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I]),
     "orbm_search_by_projection_frame": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _I,
                                             _VP, _VP, _VP, _I]),

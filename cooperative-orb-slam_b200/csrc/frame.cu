@@ -69,6 +69,18 @@ __global__ void undistort_kernel(const orb_keypoint_t* __restrict__ in, int n, U
     out[i] = kp;
 }
 
+// batch form on the extractor's device output: frame f owns kps[f*cap .. f*cap + counts[f])
+__global__ void undistort_batch_kernel(const orb_keypoint_t* __restrict__ in, const int* __restrict__ counts, int cap, UndistortParams p,
+                                       orb_keypoint_t* __restrict__ out) {
+    const int f = blockIdx.y;
+    const int n = min(counts[f], cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        orb_keypoint_t kp = in[(size_t)f * cap + i];
+        if (!p.identity) undistort_point(p, kp.x, kp.y, kp.x, kp.y);
+        out[(size_t)f * cap + i] = kp;
+    }
+}
+
 // ---------------------------------------------------------------- grid: one CTA, stable counting sort by cell
 struct GridParams { float minx, miny, winv, hinv; };
 
@@ -80,9 +92,16 @@ __device__ __forceinline__ int pos_in_grid(const GridParams& g, float x, float y
     return px * kGridRows + py;      // mGrid[ix][iy]
 }
 
-__global__ void __launch_bounds__(1024) grid_kernel(const orb_keypoint_t* __restrict__ kps, int n, GridParams g,
-                                                    int* __restrict__ cell_ptr, int* __restrict__ cell_idx) {
+// one CTA per frame (blockIdx.x): counts == NULL -> a single frame of n key points, else frame f has
+// min(counts[f], cap) key points at kps + f*cap and writes cell_ptr + f*(kGridCells+1), cell_idx + f*cap
+__global__ void __launch_bounds__(1024) grid_kernel(const orb_keypoint_t* __restrict__ kps, int n, const int* __restrict__ counts, int cap,
+                                                    GridParams g, int* __restrict__ cell_ptr, int* __restrict__ cell_idx) {
     extern __shared__ int s_dyn[];
+    if (counts) {
+        const int f = blockIdx.x;
+        n = min(counts[f], cap);
+        kps += (size_t)f * cap; cell_ptr += (size_t)f * (kGridCells + 1); cell_idx += (size_t)f * cap;
+    }
     int* s_count = s_dyn;                                   // [kGridCells + 1]: counts, then exclusive offsets
     short* s_cell = reinterpret_cast<short*>(s_dyn + kGridCells + 1);   // [n]
     __shared__ int s_part[1024];
@@ -522,12 +541,34 @@ int orbf_assign_grid(const orb_keypoint_t* kps_un, int n, const float* bounds, i
         ORB_CUDA_TRY(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16));
         configured = true;
     }
-    grid_kernel<<<1, 1024, smem, cx.stream>>>(d_k, n, make_grid_params(bounds), d_ptr, d_idx);
+    grid_kernel<<<1, 1024, smem, cx.stream>>>(d_k, n, nullptr, 0, make_grid_params(bounds), d_ptr, d_idx);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(cell_ptr, d_ptr, pb)) return ORB_ERR_CUDA;
     if (n && !cx.download(cell_idx, d_idx, (size_t)n * 4)) return ORB_ERR_CUDA;
     if (!cx.finish()) return ORB_ERR_CUDA;
     if (n_assigned) *n_assigned = cell_ptr[kGridCells];
+    return ORB_OK;
+}
+
+int orbf_build_frames_device(const void* d_kps, const int32_t* d_counts, int n_frames, int cap, const float* K, const float* dist, int ndist,
+                             const float* bounds, void* d_kps_un, int32_t* d_cell_ptr, int32_t* d_cell_idx, void* stream) {
+    UndistortParams p;
+    if (!d_kps || !d_counts || n_frames < 0 || cap <= 0 || cap > kFrameMaxFeatures || !bounds || !d_kps_un || !d_cell_ptr || !d_cell_idx ||
+        !make_undistort_params(K, dist, ndist, &p)) {
+        set_error("orbf_build_frames_device: bad arguments (cap <= %d)", kFrameMaxFeatures);
+        return ORB_ERR_ARG;
+    }
+    if (n_frames == 0) return ORB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    static bool configured = false;
+    if (!configured) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16));
+        configured = true;
+    }
+    undistort_batch_kernel<<<dim3((cap + 255) / 256, n_frames), 256, 0, s>>>((const orb_keypoint_t*)d_kps, d_counts, cap, p, (orb_keypoint_t*)d_kps_un);
+    grid_kernel<<<n_frames, 1024, (size_t)(kGridCells + 1) * 4 + (size_t)cap * 2 + 16, s>>>((const orb_keypoint_t*)d_kps_un, 0, d_counts, cap,
+                                                                                         make_grid_params(bounds), d_cell_ptr, d_cell_idx);
+    ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }
 

@@ -239,6 +239,13 @@ int orbf_image_bounds(int cols, int rows, const float* K, const float* dist, int
  * cell_idx[n]; indices ascend inside a cell (push_back order).  *n_assigned = key points inside the grid. */
 int orbf_assign_grid(const orb_keypoint_t* kps_un, int n, const float* bounds, int32_t* cell_ptr, int32_t* cell_idx,
                      int* n_assigned, int device);
+/* UndistortKeyPoints + AssignFeaturesToGrid for a whole batch, on the device-resident output of
+ * orbx_extract_batch_device (d_kps [n_frames][cap], d_counts [n_frames]) without a host round trip, on `stream`:
+ * d_kps_un [n_frames][cap], d_cell_ptr [n_frames][64*48 + 1], d_cell_idx [n_frames][cap].  bounds from
+ * orbf_image_bounds (they depend on the calibration only).  Two launches. */
+int orbf_build_frames_device(const void* d_kps, const int32_t* d_counts, int n_frames, int cap, const float* K,
+                             const float* dist, int ndist, const float* bounds, void* d_kps_un,
+                             int32_t* d_cell_ptr, int32_t* d_cell_idx, void* stream);
 /* vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel)  R21/src/Frame.cc:332-385, for nq windows
  * at once.  Query q owns out_idx[out_ptr[q] .. out_ptr[q+1]) in the reference's order (cells ix-major, then the
  * cell's push_back order).  ORB_ERR_CAPACITY when the total exceeds cap (out_ptr is still complete). */

@@ -316,3 +316,42 @@ def test_gpu_window_best_match_fuse_and_sim3(orb, oracle, synth, golden_dir, gat
         assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
         assert (ref[0] >= 0).sum() > 100
     assert np.all(ref[0][pts["valid"] == 0] == -1) and np.all(ref[1][pts["valid"] == 0] == 256)
+
+
+@pytest.mark.gpu
+def test_gpu_build_frames_on_extractor_device_output(orb, oracle, synth, golden_dir):
+    """extract_batch_device -> orbf_build_frames_device on the same stream: undistorted key points and grids of a whole
+    batch without leaving the device == oracle per frame."""
+    import ctypes as C
+    import torch
+    g = _golden(golden_dir)
+    K, D = g["tum1_K"], g["tum1_D"]
+    B, W, H, cap = 6, 640, 480, 1400
+    frames = np.stack([synth.frame(40 + i, W, H) for i in range(B)])
+    frames[4] = 128                                   # a frame without key points
+    ext = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    dev = torch.device("cuda", 0)
+    d_img = torch.from_numpy(frames).to(dev)
+    d_k = torch.zeros((B, cap, 7), dtype=torch.int32, device=dev); d_d = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_c = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ext.extract_batch_device(d_img.data_ptr(), B, W, H, W, W * H, d_k.data_ptr(), d_d.data_ptr(), cap, d_c.data_ptr())
+    d_un = torch.zeros_like(d_k); d_ptr = torch.zeros((B, 64 * 48 + 1), dtype=torch.int32, device=dev)
+    d_idx = torch.full((B, cap), -7, dtype=torch.int32, device=dev)
+    bounds = oracle.image_bounds(W, H, K, D)
+    rc = orb.lib().orbf_build_frames_device(C.c_void_p(d_k.data_ptr()), C.c_void_p(d_c.data_ptr()), B, cap, K.ctypes.data_as(C.c_void_p),
+                                            D.ctypes.data_as(C.c_void_p), len(D), bounds.ctypes.data_as(C.c_void_p), C.c_void_p(d_un.data_ptr()),
+                                            C.c_void_p(d_ptr.data_ptr()), C.c_void_p(d_idx.data_ptr()), C.c_void_p(ext.stream()))
+    assert rc == 0, orb.lib().orb_last_error()
+    ext.wait()
+    torch.cuda.synchronize()
+    cnt = d_c.cpu().numpy()
+    keys = d_k.cpu().numpy().reshape(B, -1).view(orb.KP_DTYPE).reshape(B, cap)
+    un = d_un.cpu().numpy().reshape(B, -1).view(orb.KP_DTYPE).reshape(B, cap)
+    ptr = d_ptr.cpu().numpy(); idx = d_idx.cpu().numpy()
+    assert cnt[4] == 0 and cnt[0] > 500
+    for f in range(B):
+        n = cnt[f]
+        ref_un = oracle.undistort_keypoints(keys[f, :n], K, D)
+        assert un[f, :n].tobytes() == ref_un.tobytes()
+        rptr, ridx = oracle.assign_grid(ref_un, bounds)
+        assert np.array_equal(ptr[f], rptr) and np.array_equal(idx[f, :rptr[-1]], ridx[:rptr[-1]])
