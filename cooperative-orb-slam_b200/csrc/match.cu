@@ -935,6 +935,247 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_ts_kernel(const uint32_t* 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K7e: K7c on a CTA pair (tcgen05 cta_group::2).  Two CTAs of a cluster (two SMs of a TPC) take 512 queries of one map
+// split: each keeps its own 256 queries (two A tiles) and expands only HALF of every 128-descriptor B tile (64 rows) into
+// its own shared memory; one tcgen05.mma.cta_group::2 (M = 256: 128 rows per CTA, N = 128, K = 32) multiplies both A
+// tiles against the whole B tile, each tensor core taking the other half from the peer.  Per CTA that is half the
+// expansion instructions and stores per comparison and 6 KB instead of 8 KB of operand reads per MMA.
+//   * both CTAs allocate TMEM with .cta_group::2; accumulators as in K7c (2 stages x 2 A tiles x 128 columns per CTA);
+//   * only the leader (cluster rank 0) runs the MMA warp; its full/empty barriers count the worker warps of BOTH CTAs
+//     (the peer arrives through mapa + mbarrier.arrive.release.cluster); tcgen05.commit multicasts `done` to both;
+//   * everything else -- drain, shared pruning bound, merge -- is K7c's, per CTA.
+// Protocol established with tools/probe/cta_pair.cu.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPairHalfN = kTcN / 2;      // B rows expanded per CTA per tile
+
+__device__ __forceinline__ uint32_t cluster_cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
+// arrive on the barrier at the same shared-memory offset in CTA `target` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t target) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(target));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ m, long long nm, long long per_split,
+                 long long index_base, int4* __restrict__ partial, int* __restrict__ shared_d2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 2 x [128 rows][256 B] (64 KB)
+    unsigned char* s_b = s_a + kTcQ * 256;                                               // kTcBStages x [64 rows][256 B]
+    __shared__ __align__(8) unsigned long long s_full[kTcBStages], s_done[2], s_empty[2];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_cta_rank();
+    const int q0 = blockIdx.x * kTcQ;
+
+    if (warp == kTcWorkers) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int sb = 0; sb < kTcBStages; sb++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[sb])), "r"(2 * kTcWorkers));
+#pragma unroll
+        for (int st = 0; st < 2; st++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_done[st])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_empty[st])), "r"(2 * kTcWorkers));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    // ---- my A tiles (weighted +/-): element (r, c) of a tile at (r/8)*2048 + (c/16)*128 + (r%8)*16 + c%16
+    for (int it = tid; it < kTcQ * 8; it += kTcThreads) {
+        const int row = it >> 3, w = it & 7, r = row & 127;
+        const uint32_t bits = q0 + row < nq ? q[(size_t)(q0 + row) * 8 + w] : 0u;
+        uint4 c0, c1;
+        expand32_query(bits, c0, c1);
+        unsigned char* dst = s_a + (row >> 7) * (kTcM * 256) + (r >> 3) * 2048 + (r & 7) * 16 + (2 * w) * 128;
+        *reinterpret_cast<uint4*>(dst) = c0;
+        *reinterpret_cast<uint4*>(dst + 128) = c1;
+    }
+    const long long lo = (long long)blockIdx.y * per_split;
+    const long long hi = min(nm, lo + per_split);
+    const int ntiles = hi > lo ? (int)((hi - lo + kTcN - 1) / kTcN) : 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::);
+    __syncthreads();
+    cluster_sync_all();             // barriers initialised, TMEM allocated and A tiles written in both CTAs
+    asm volatile("tcgen05.fence::after_thread_sync;" ::);
+    const uint32_t tmem = s_tmem;
+    uint32_t full0 = smem_u32(&s_full[0]), done0 = smem_u32(&s_done[0]), empty0 = smem_u32(&s_empty[0]), b0 = smem_u32(s_b);
+    asm volatile("" : "+r"(full0), "+r"(done0), "+r"(empty0), "+r"(b0));
+
+    Top2 best = {256, -1, 256, -1};
+    if (warp == kTcWorkers) {
+        if (rank == 0) {
+            // =========================== MMA warp of the leader ===========================
+            // D = s32, A = signed 8 bit, B = unsigned 8 bit, K-major, N = 128, M = 256 (128 rows in each CTA)
+            const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)((2 * kTcM) >> 4) << 24);
+            const uint64_t a_desc = umma_desc(smem_u32(s_a)), b_desc = umma_desc(b0);
+            uint32_t leader;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
+            for (int i = 0; i < ntiles; i++) {
+                const int st = i & 1, sb = i & (kTcBStages - 1);
+                mbar_wait_cluster_parked(full0 + 8 * sb, (uint32_t)((i / kTcBStages) & 1), 32);    // both halves of B tile i expanded
+                mbar_wait_cluster_parked(empty0 + 8 * st, (uint32_t)(((i >> 1) & 1) ^ 1), 32);     // both CTAs loaded tile i-2 out
+                asm volatile("tcgen05.fence::after_thread_sync;" ::);
+                if (leader) {
+#pragma unroll
+                    for (int t = 0; t < 2; t++)
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++) {
+                            const uint64_t da = a_desc + (uint64_t)((t * (kTcM * 256) + ks * 256) >> 4);
+                            const uint64_t db = b_desc + (uint64_t)((sb * (kPairHalfN * 256) + ks * 256) >> 4);
+                            const uint32_t accumulate = ks ? 1u : 0u;
+                            asm volatile(
+                                "{\n\t"
+                                ".reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+                                "}\n"
+                                :: "r"(tmem + (uint32_t)((2 * st + t) * kTcN)), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u));
+                        }
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 :: "r"(done0 + 8 * st), "h"((unsigned short)3));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =========================== worker warps (both CTAs) ===========================
+        const int row = ((warp >> 2) & 1) * kTcM + (warp & 3) * 32 + lane;
+        const int chalf = warp >> 3;
+        constexpr int kColsPerWarp = kTcN / (kTcWorkers / 8);
+        static_assert(kColsPerWarp == 64, "one packed 32-register load covers the warp's 64 columns");
+        int pa = 0;
+        if (q0 + row < nq) {
+            const uint4 x = *reinterpret_cast<const uint4*>(q + (size_t)(q0 + row) * 8);
+            const uint4 y = *reinterpret_cast<const uint4*>(q + (size_t)(q0 + row) * 8 + 4);
+            pa = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w) + __popc(y.x) + __popc(y.y) + __popc(y.z) + __popc(y.w);
+        }
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) & 1) * kTcN + chalf * kColsPerWarp);
+        // my word of a tile: row 64*rank + r0 of the tile, word w0 (512 threads x 1 word = 64 rows x 8 words)
+        const int r0 = (tid & 7) | ((tid >> 6) << 3), w0 = (tid >> 3) & 7;
+        const int tile_row = (int)rank * kPairHalfN + r0;
+        const uint32_t* src = m + ((size_t)lo + tile_row) * 8 + w0;
+        const uint32_t b_off = (uint32_t)((r0 >> 3) * 2048 + (r0 & 7) * 16 + (2 * w0) * 128);
+        const int ib0 = (int)(index_base + lo) + chalf * kColsPerWarp;
+        const int n_full = (int)((hi - lo) / kTcN);
+        const int last_cnt = (int)(hi - lo) - n_full * kTcN;
+        uint32_t raw_a = 0, raw_b = 0;        // tiles i and i + 1
+        auto fetch = [&](int tile) {          // called with tile = 0, 1, 2, ...
+            const uint32_t v = (tile < n_full || tile_row < last_cnt) ? __ldg(src) : 0u;
+            src += kTcN * 8;
+            return v;
+        };
+        int* const gptr = shared_d2 + q0 + row;
+        int gval = 0x7f7f7f7f;
+        auto drain_load = [&](int tile, uint32_t (&v)[32]) {
+            const int st = tile & 1;
+            mbar_wait(done0 + 8 * st, (uint32_t)((tile >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::);
+            const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;
+            if (cnt > 0) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(trow + (uint32_t)(2 * st * kTcN)));
+            }
+        };
+        auto drain_finish = [&](int tile, uint32_t (&v)[32], int glim) {
+            const int st = tile & 1;
+            const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;
+            const int ib = ib0 + tile * kTcN;
+            if (cnt > 0) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;"
+                    : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                      "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                      "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                    :: "memory");
+            }
+            // my accumulators are in registers: tell the leader this TMEM stage may be overwritten
+            asm volatile("tcgen05.fence::before_thread_sync;" ::);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(empty0 + 8 * st, 0);
+            if (cnt >= kColsPerWarp) tc_drain64<true>(v, pa, ib, kColsPerWarp, glim, gptr, best);
+            else if (cnt > 0) tc_drain64<false>(v, pa, ib, cnt, glim, gptr, best);
+        };
+        if (ntiles > 0) raw_a = fetch(0);
+        if (ntiles > 1) raw_b = fetch(1);
+        for (int i = 0; i < ntiles; i++) {
+            const int sb = i & (kTcBStages - 1);
+            uint32_t v[32];
+            if (i >= kTcLag) drain_load(i - kTcLag, v);
+            // buffer sb was last read by the MMAs of tile i - kTcBStages, whose completion this warp saw (multicast commit)
+            const uint32_t dst = b0 + sb * (kPairHalfN * 256) + b_off;
+            uint4 c0, c1;
+            expand32_map(raw_a, c0, c1);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(dst), "r"(c0.x), "r"(c0.y), "r"(c0.z), "r"(c0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(dst + 128), "r"(c1.x), "r"(c1.y), "r"(c1.z), "r"(c1.w) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(full0 + 8 * sb, 0);
+            raw_a = raw_b;
+            if (i + 2 < ntiles) raw_b = fetch(i + 2);
+            const int glim = pa - gval - 1;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval) : "l"(gptr) : "memory");
+            if (i >= kTcLag) drain_finish(i - kTcLag, v, glim);
+        }
+        for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
+            uint32_t v[32];
+            drain_load(t, v);
+            int gnow;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gnow) : "l"(gptr) : "memory");
+            drain_finish(t, v, pa - gnow - 1);
+        }
+    }
+    // ---- merge the column halves and store (per CTA, as K7c)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::);
+    __syncthreads();
+    int4* s_rec = reinterpret_cast<int4*>(s_a);     // my A tiles are no longer read once every MMA has retired: see the cluster sync
+    cluster_sync_all();                             // both CTAs are past their last drain: all MMAs retired, nobody reads my smem
+    if (warp >= 8 && warp < kTcWorkers) {
+        const int row = ((warp >> 2) & 1) * kTcM + (warp & 3) * 32 + lane;
+        s_rec[row] = make_int4(best.d1, best.i1, best.d2, best.i2);
+    }
+    __syncthreads();
+    if (warp < 8) {
+        const int row = ((warp >> 2) & 1) * kTcM + (warp & 3) * 32 + lane;
+        const int4 o = s_rec[row];
+        top2_merge(best.d1, best.i1, best.d2, best.i2, o.x, o.y, o.z, o.w);
+        if (q0 + row < nq) partial[(size_t)blockIdx.y * nq + q0 + row] = make_int4(best.d1, best.i1, best.d2, best.i2);
+    }
+    if (warp == kTcWorkers) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::);
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+    }
+}
+
 __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -969,7 +1210,8 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     const int qper = variant >= 3 ? kTcQ : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
     const int tile = variant >= 3 ? kTcN : (variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile));
     const int per_sm = variant >= 3 ? 1 : 2;
-    const int qblocks = (nq + qper - 1) / qper;
+    int qblocks = (nq + qper - 1) / qper;
+    if (variant == 5) qblocks = (qblocks + 1) & ~1;      // CTA pairs: an even number of query blocks (a padding block stores nothing)
     // enough map splits to fill the SMs, each at least one tile
     // never more CTAs than fit at once (a partial second wave would double the run time)
     int splits = std::max(1, (per_sm * sms) / qblocks);
@@ -1004,6 +1246,17 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
         knn2_tc_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                       index_base, partial, shared_d2);
+    } else if (variant == 5) {
+        const size_t smem = (size_t)kTcQ * 256 + kTcBStages * (size_t)kPairHalfN * 256 + 1024;
+        static bool configured5 = false;
+        if (!configured5) {
+            if (cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            configured5 = true;
+        }
+        int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
+        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
+        knn2_pair_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
+                                                                        index_base, partial, shared_d2);
     } else if (variant == 4) {
         const size_t smem = kTcBStages * (size_t)kTcN * 256 + 1024;
         static bool configured4 = false;

@@ -22,7 +22,7 @@ int orb_hamming256(const void* a, const void* b) {
 int orbm_knn2_device(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out,
                      int variant, void* stream) {
     if (!d_q || nq < 1 || !d_out || nm < 0 || (nm > 0 && !d_m)) { set_error("orbm_knn2_device: bad arguments"); return ORB_ERR_ARG; }
-    if (variant < 0 || variant > 4) { set_error("orbm_knn2: unknown variant %d (0 = POPC, 1 = mma.sync integer MMA via shared memory, 2 = mma.sync streaming, 3 = tcgen05 integer MMA with TMEM accumulators, 4 = tcgen05 with the query operand in TMEM)", variant); return ORB_ERR_ARG; }
+    if (variant < 0 || variant > 5) { set_error("orbm_knn2: unknown variant %d (0 = POPC, 1 = mma.sync integer MMA via shared memory, 2 = mma.sync streaming, 3 = tcgen05 integer MMA with TMEM accumulators, 4 = tcgen05 with the query operand in TMEM, 5 = tcgen05 on CTA pairs)", variant); return ORB_ERR_ARG; }
     if ((reinterpret_cast<uintptr_t>(d_q) & 15) || (reinterpret_cast<uintptr_t>(d_m) & 15)) {
         set_error("orbm_knn2_device: descriptor arrays must be 16-byte aligned");
         return ORB_ERR_ARG;

@@ -32,7 +32,7 @@ def test_hamming_kat(orb, oracle):
     assert orb.ORBmatcher.DescriptorDistance(z, f) == 256 and orb.ORBmatcher.DescriptorDistance(f, f) == 0
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("nq,nm", [(1, 1), (7, 300), (257, 5000), (2000, 60000), (100, 0)])
 def test_knn2_matches_oracle(orb, oracle, synth, nq, nm, variant):
     m = synth.descriptors(max(nm, 1), seed=5)[:nm]

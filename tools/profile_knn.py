@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 orb = importlib.import_module("cooperative-orb-slam_b200")
 synth = importlib.import_module("cooperative-orb-slam_b200.synth")
-variants = [int(v) for v in sys.argv[1:]] or [0, 1, 2, 3, 4]
+variants = [int(v) for v in sys.argv[1:]] or [0, 1, 2, 3, 4, 5]
 dev = torch.device("cuda", 0)
 m = synth.descriptors(1000000, seed=1234)
 q = synth.descriptors(2000, seed=99)
