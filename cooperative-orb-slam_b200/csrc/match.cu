@@ -948,6 +948,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_ts_kernel(const uint32_t* 
 // Protocol established with tools/probe/cta_pair.cu.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPairHalfN = kTcN / 2;      // B rows expanded per CTA per tile
+constexpr int kPairBStages = 8;           // expanded half tiles in flight per CTA (16 KB each)
 
 __device__ __forceinline__ uint32_t cluster_cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -968,11 +969,16 @@ __device__ __forceinline__ void mbar_wait_cluster_parked(uint32_t bar, uint32_t 
         __nanosleep(ns);
     }
 }
-// arrive on the barrier at the same shared-memory offset in CTA `target` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `target` of the cluster.
+// .relaxed on purpose: .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive (measured: 55 % of
+// all stall samples, 2.3x the run time).  What the consumer needs is already ordered by the instructions in front of
+// the arrive: `fence.proxy.async` has made the expansion stores visible to the tensor cores' proxy (full barrier), and
+// `tcgen05.wait::ld` + `tcgen05.fence::before_thread_sync` have completed the TMEM reads (empty barrier); the arrive
+// itself is issued after them in program order by the same thread.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t target) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(target));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
@@ -980,8 +986,8 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
                  long long index_base, int4* __restrict__ partial, int* __restrict__ shared_d2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 2 x [128 rows][256 B] (64 KB)
-    unsigned char* s_b = s_a + kTcQ * 256;                                               // kTcBStages x [64 rows][256 B]
-    __shared__ __align__(8) unsigned long long s_full[kTcBStages], s_done[2], s_empty[2];
+    unsigned char* s_b = s_a + kTcQ * 256;                                               // kPairBStages x [64 rows][256 B]
+    __shared__ __align__(8) unsigned long long s_full[kPairBStages], s_done[2], s_empty[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_cta_rank();
@@ -993,7 +999,7 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
     }
     if (tid == 0) {
 #pragma unroll
-        for (int sb = 0; sb < kTcBStages; sb++)
+        for (int sb = 0; sb < kPairBStages; sb++)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_full[sb])), "r"(2 * kTcWorkers));
 #pragma unroll
         for (int st = 0; st < 2; st++) {
@@ -1034,9 +1040,11 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             uint32_t leader;
             asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
             for (int i = 0; i < ntiles; i++) {
-                const int st = i & 1, sb = i & (kTcBStages - 1);
-                mbar_wait_cluster_parked(full0 + 8 * sb, (uint32_t)((i / kTcBStages) & 1), 32);    // both halves of B tile i expanded
-                mbar_wait_cluster_parked(empty0 + 8 * st, (uint32_t)(((i >> 1) & 1) ^ 1), 32);     // both CTAs loaded tile i-2 out
+                const int st = i & 1, sb = i & (kPairBStages - 1);
+                // CTA-scope waits on purpose: an acquire.cluster wait adds an L1 invalidate (CCTL.IVALL) per success, and what
+                // the MMAs read afterwards goes through the async proxy (shared memory, TMEM), not through L1
+                mbar_wait(full0 + 8 * sb, (uint32_t)((i / kPairBStages) & 1));      // both halves of B tile i expanded
+                mbar_wait(empty0 + 8 * st, (uint32_t)(((i >> 1) & 1) ^ 1));          // both CTAs loaded tile i-2 out
                 asm volatile("tcgen05.fence::after_thread_sync;" ::);
                 if (leader) {
 #pragma unroll
@@ -1106,10 +1114,11 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
                     : "r"(trow + (uint32_t)(2 * st * kTcN)));
             }
         };
-        auto drain_finish = [&](int tile, uint32_t (&v)[32], int glim) {
+        // the load has landed: hand the TMEM stage back at once (the recycle latency of the two stages, not the worker
+        // instruction count, bounds the pair kernel), the top-2 update follows after the expansion
+        auto drain_release = [&](int tile, uint32_t (&v)[32]) {
             const int st = tile & 1;
             const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;
-            const int ib = ib0 + tile * kTcN;
             if (cnt > 0) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;"
                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
@@ -1118,20 +1127,23 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
                       "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                     :: "memory");
             }
-            // my accumulators are in registers: tell the leader this TMEM stage may be overwritten
             asm volatile("tcgen05.fence::before_thread_sync;" ::);
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(empty0 + 8 * st, 0);
+        };
+        auto drain_update = [&](int tile, uint32_t (&v)[32], int glim) {
+            const int cnt = (tile < n_full ? kTcN : last_cnt) - chalf * kColsPerWarp;
+            const int ib = ib0 + tile * kTcN;
             if (cnt >= kColsPerWarp) tc_drain64<true>(v, pa, ib, kColsPerWarp, glim, gptr, best);
             else if (cnt > 0) tc_drain64<false>(v, pa, ib, cnt, glim, gptr, best);
         };
         if (ntiles > 0) raw_a = fetch(0);
         if (ntiles > 1) raw_b = fetch(1);
         for (int i = 0; i < ntiles; i++) {
-            const int sb = i & (kTcBStages - 1);
+            const int sb = i & (kPairBStages - 1);
             uint32_t v[32];
-            if (i >= kTcLag) drain_load(i - kTcLag, v);
-            // buffer sb was last read by the MMAs of tile i - kTcBStages, whose completion this warp saw (multicast commit)
+            if (i >= kTcLag) { drain_load(i - kTcLag, v); drain_release(i - kTcLag, v); }
+            // buffer sb was last read by the MMAs of tile i - kPairBStages, whose completion this warp saw (multicast commit)
             const uint32_t dst = b0 + sb * (kPairHalfN * 256) + b_off;
             uint4 c0, c1;
             expand32_map(raw_a, c0, c1);
@@ -1144,14 +1156,15 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             if (i + 2 < ntiles) raw_b = fetch(i + 2);
             const int glim = pa - gval - 1;
             asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gval) : "l"(gptr) : "memory");
-            if (i >= kTcLag) drain_finish(i - kTcLag, v, glim);
+            if (i >= kTcLag) drain_update(i - kTcLag, v, glim);
         }
         for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
             uint32_t v[32];
             drain_load(t, v);
+            drain_release(t, v);
             int gnow;
             asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gnow) : "l"(gptr) : "memory");
-            drain_finish(t, v, pa - gnow - 1);
+            drain_update(t, v, pa - gnow - 1);
         }
     }
     // ---- merge the column halves and store (per CTA, as K7c)
@@ -1247,7 +1260,7 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         knn2_tc_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                       index_base, partial, shared_d2);
     } else if (variant == 5) {
-        const size_t smem = (size_t)kTcQ * 256 + kTcBStages * (size_t)kPairHalfN * 256 + 1024;
+        const size_t smem = (size_t)kTcQ * 256 + kPairBStages * (size_t)kPairHalfN * 256 + 1024;
         static bool configured5 = false;
         if (!configured5) {
             if (cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
