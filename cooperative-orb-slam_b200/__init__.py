@@ -370,10 +370,11 @@ class ORBmatcher:
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return lib().orb_hamming256(_p(a), _p(b))
 
-    def knn2(self, queries, map_desc, index_base=0, variant=3):
+    def knn2(self, queries, map_desc, index_base=0, variant=5):
         """Brute-force 2-NN: returns (best_idx, best_dist, second_dist, second_idx).
         variant 0 = LOP3+POPC kernel, 1/2 = mma.sync integer tensor-core AND-popc contraction, 3 = tcgen05 (UMMA + TMEM)
-        contraction (default), 4 = the same with the query operand in TMEM; all variants return identical results."""
+        contraction, 4 = the same with the query operand in TMEM, 5 = the same on CTA pairs (cta_group::2; default); all variants
+        return identical results."""
         q = np.ascontiguousarray(queries, np.uint8); m = np.ascontiguousarray(map_desc, np.uint8)
         nq = q.shape[0]
         bi, bd, sd, si = (np.zeros(nq, np.int32) for _ in range(4))

@@ -146,8 +146,10 @@ int orb_hamming256(const void* a, const void* b);
  *   1  tensor-core AND-popc contraction d = popc(a)+popc(b)-2*popc(a&b) on mma.sync integer MMAs (~1.0 Tcmp/s)
  *   2  same, streaming the map without shared memory (~0.8 Tcmp/s; kept as evidence)
  *   3  the contraction on tcgen05.mma kind::i8 with TMEM accumulators, warp-specialised mbarrier pipeline
- *      (~5.8 Tcmp/s; the default of the Python/C++ host layers)
- *   4  as 3 with the query operand held in TMEM (~5.8 Tcmp/s).  See DESIGN.md section 4 and profiles/. */
+ *      (~6.1 Tcmp/s)
+ *   4  as 3 with the query operand held in TMEM (~6.1 Tcmp/s)
+ *   5  as 3 on CTA pairs (thread-block cluster of 2, tcgen05 cta_group::2: each CTA expands half of every map tile;
+ *      ~6.8 Tcmp/s; the default of the Python/C++ host layers).  See DESIGN.md section 4 and profiles/. */
 int orbm_knn2(const uint8_t* queries, int nq, const uint8_t* map, int64_t nm, int64_t index_base,
               int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int32_t* second_idx,
               int variant, int device);
