@@ -355,3 +355,35 @@ def test_gpu_build_frames_on_extractor_device_output(orb, oracle, synth, golden_
         assert un[f, :n].tobytes() == ref_un.tobytes()
         rptr, ridx = oracle.assign_grid(ref_un, bounds)
         assert np.array_equal(ptr[f], rptr) and np.array_equal(idx[f, :rptr[-1]], ridx[:rptr[-1]])
+
+
+@pytest.mark.gpu
+def test_gpu_frame_api_rejects_bad_arguments(orb, oracle, golden_dir):
+    """Error behaviour of the C ABI: status codes, not crashes."""
+    import ctypes as C
+    g = _golden(golden_dir)
+    L = orb.lib()
+    k = _keys(oracle, 10, 1)
+    out = np.zeros_like(k)
+    K = g["tum1_K"]; D = g["tum1_D"]
+    assert L.orbf_undistort_keypoints(k.ctypes.data_as(C.c_void_p), 10, K.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p), 3,
+                                      out.ctypes.data_as(C.c_void_p), 0) == 1          # ORB_ERR_ARG: 3 distortion coefficients
+    assert L.orbf_undistort_keypoints(None, 10, K.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p), 5, out.ctypes.data_as(C.c_void_p), 0) == 1
+    assert b"orbf_undistort_keypoints" in L.orb_last_error()
+    fr = orb.FrameFeatures(k, K, D, 640, 480)
+    mp = np.zeros(3, orb.MPV_DTYPE); mp["in_view"] = 1; mp["level"] = 9                  # level outside mvScaleFactors
+    with pytest.raises(orb.OrbCudaError):
+        orb.search_by_projection_frame(fr, np.zeros((10, 32), np.uint8), np.full(10, -1, np.float32), np.zeros(10, np.uint8),
+                                       (1.2 ** np.arange(8)).astype(np.float32), mp, np.zeros((3, 32), np.uint8))
+    big = np.zeros(40000, oracle.KP_DTYPE)
+    ptr = np.zeros(64 * 48 + 1, np.int32); idx = np.zeros(40000, np.int32); n = C.c_int(0)
+    assert L.orbf_assign_grid(big.ctypes.data_as(C.c_void_p), 40000, fr.bounds.ctypes.data_as(C.c_void_p), ptr.ctypes.data_as(C.c_void_p),
+                              idx.ctypes.data_as(C.c_void_p), C.byref(n), 0) == 1       # more than 32768 key points
+    # capacity: the total is reported, the caller retries
+    qx = np.full(4, 320, np.float32); qr = np.full(4, 1000, np.float32); lv = np.full(4, -1, np.int32)
+    optr = np.zeros(5, np.int32); oidx = np.zeros(3, np.int32)
+    rc = L.orbf_features_in_area(fr.keys_un.ctypes.data_as(C.c_void_p), 10, fr.cell_ptr.ctypes.data_as(C.c_void_p), fr.cell_idx.ctypes.data_as(C.c_void_p),
+                                 fr.bounds.ctypes.data_as(C.c_void_p), qx.ctypes.data_as(C.c_void_p), qx.ctypes.data_as(C.c_void_p),
+                                 qr.ctypes.data_as(C.c_void_p), lv.ctypes.data_as(C.c_void_p), lv.ctypes.data_as(C.c_void_p), 4,
+                                 optr.ctypes.data_as(C.c_void_p), oidx.ctypes.data_as(C.c_void_p), 3, 0)
+    assert rc == 3 and optr[4] == 4 * fr.n_assigned                                      # ORB_ERR_CAPACITY, out_ptr complete
