@@ -948,6 +948,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn2_ts_kernel(const uint32_t* 
 // Protocol established with tools/probe/cta_pair.cu.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPairHalfN = kTcN / 2;      // B rows expanded per CTA per tile
+#ifndef PAIR_BOUND_EVERY
+#define PAIR_BOUND_EVERY 7
+#endif
+constexpr int kPairBoundEvery = PAIR_BOUND_EVERY;   // refresh the shared bound when (tile & this) == 0
 constexpr int kPairBStages = 8;           // expanded half tiles in flight per CTA (16 KB each)
 
 __device__ __forceinline__ uint32_t cluster_cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -1157,7 +1161,7 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             const int glim = pa - gval - 1;
             // a stale bound is still a bound: one L2 round trip every eighth tile, issued where nothing waits for it soon
             // (a load per tile stalled the loop top -- i.e. the TMEM hand-back -- for 23 % of the samples)
-            if ((i & 7) == 0) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "+r"(gval) : "l"(gptr) : "memory");
+            if ((i & kPairBoundEvery) == 0) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "+r"(gval) : "l"(gptr) : "memory");
             if (i >= kTcLag) drain_update(i - kTcLag, v, glim);
         }
         for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
