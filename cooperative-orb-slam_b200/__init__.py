@@ -94,6 +94,7 @@ ABI = {
     "orbm_search_by_projection_keyframe": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _I,
                                                _VP, _VP, _VP, _I]),
     "orbm_search_by_projection_sim3": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _VP, _VP, _VP, _I]),
+    "orbm_search_for_initialization": (_I, [_VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _F, _I, _I, _VP, _VP, _I]),
     "orbm_window_best_match": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _VP, _VP, _I]),
     "orbv_create": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "orbv_destroy": (_I, [_VP]),
@@ -545,6 +546,20 @@ def search_by_projection_sim3(frame, desc_f, occupied, scale_factors, points, de
                                                 _p(frame.bounds), _p(sf), len(sf), _p(pts), _p(dp), len(pts), float(th), int(th_low),
                                                 _p(fp), _p(pf), C.byref(n), frame.device), "orbm_search_by_projection_sim3")
     return fp[:nf], pf[:len(pts)], n.value
+
+
+def search_for_initialization(keys1_un, desc1, frame2, desc2, prev_matched, window_size=100, nnratio=0.9, check_orientation=True,
+                             th_low=50):
+    """ORBmatcher::SearchForInitialization (R21/src/ORBmatcher.cc:405-520).  frame2: FrameFeatures of F2; prev_matched [n1][2]
+    (vbPrevMatched).  -> (vnMatches12, updated vbPrevMatched, nmatches)."""
+    k1 = np.ascontiguousarray(keys1_un, KP_DTYPE); d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    xy = np.ascontiguousarray(prev_matched, np.float32).reshape(-1, 2).copy()
+    m12 = np.zeros(max(len(k1), 1), np.int32); n = C.c_int(0)
+    _check(lib().orbm_search_for_initialization(_p(k1), _p(d1), len(k1), _p(frame2.keys_un), _p(d2), len(frame2.keys_un), _p(frame2.cell_ptr),
+                                                _p(frame2.cell_idx), _p(frame2.bounds), _p(xy), int(window_size), float(nnratio),
+                                                int(bool(check_orientation)), int(th_low), _p(m12), C.byref(n), frame2.device),
+           "orbm_search_for_initialization")
+    return m12[:len(k1)], xy, n.value
 
 
 def window_best_match(frame, desc_f, scale_factors, points, desc_pts, th, u_right=None, inv_level_sigma2=None):

@@ -391,6 +391,69 @@ __global__ void window_best_kernel(const orb_keypoint_t* __restrict__ kps, const
     best_idx[i] = bestIdx; best_dist[i] = bestDist;
 }
 
+// ---------------------------------------------------------------- SearchForInitialization (ORBmatcher.cc:405-520)
+// Same order problem, different state: a frame-2 feature remembers the distance of its current match
+// (vMatchedDistance) and only yields to a strictly better one; a new match evicts the previous owner (:459-463).
+// Rounds exactly as in window_search_kernel; the per-feature state lives in global memory (matched_dist, owner).
+__global__ void __launch_bounds__(1024) init_search_kernel(const orb_keypoint_t* __restrict__ kps1, const uint32_t* __restrict__ desc1, int n1,
+                                                           const orb_keypoint_t* __restrict__ kps2, const uint32_t* __restrict__ desc2, int n2,
+                                                           const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx, GridParams g,
+                                                           const float* __restrict__ prev_xy, float window, float nnratio, int th_low,
+                                                           int* __restrict__ matched_dist, int* __restrict__ owner, int* __restrict__ matches12,
+                                                           int* __restrict__ ever_matched, uint8_t* __restrict__ resolved,
+                                                           int* __restrict__ out_nmatches) {
+    extern __shared__ int s_dyn[];
+    int* s_claim = s_dyn;      // [n2]
+    __shared__ int s_left, s_matches;
+    const int tid = threadIdx.x;
+    for (int f = tid; f < n2; f += 1024) { matched_dist[f] = 0x7fffffff; owner[f] = -1; }
+    for (int i = tid; i < n1; i += 1024) {
+        matches12[i] = -1; ever_matched[i] = -1;
+        resolved[i] = kps1[i].octave > 0 ? 1 : 0;      // :421-423
+    }
+    if (tid == 0) s_matches = 0;
+    while (true) {
+        __syncthreads();
+        for (int f = tid; f < n2; f += 1024) s_claim[f] = 0x7fffffff;
+        if (tid == 0) s_left = 0;
+        __syncthreads();
+        for (int i = tid; i < n1; i += 1024) {
+            if (resolved[i]) continue;
+            for_features_in_area(kps2, cell_ptr, cell_idx, g, prev_xy[2 * i], prev_xy[2 * i + 1], window, 0, 0,
+                                 [&](int idx) { atomicMin(&s_claim[idx], i); return true; });
+        }
+        __syncthreads();
+        for (int i = tid; i < n1; i += 1024) {
+            if (resolved[i]) continue;
+            bool safe = true;
+            int bestDist = 0x7fffffff, bestDist2 = 0x7fffffff, bestIdx2 = -1;
+            const uint32_t* d1 = desc1 + (size_t)i * 8;
+            for_features_in_area(kps2, cell_ptr, cell_idx, g, prev_xy[2 * i], prev_xy[2 * i + 1], window, 0, 0, [&](int idx) {
+                if (s_claim[idx] < i) { safe = false; return false; }
+                const int dist = hamming32(d1, desc2 + (size_t)idx * 8);
+                if (matched_dist[idx] <= dist) return true;
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = idx; }
+                else if (dist < bestDist2) bestDist2 = dist;
+                return true;
+            });
+            if (!safe) { atomicAdd(&s_left, 1); continue; }
+            resolved[i] = 1;
+            if (bestDist <= th_low && (float)bestDist < __fmul_rn((float)bestDist2, nnratio)) {
+                const int prev = owner[bestIdx2];
+                if (prev >= 0) { matches12[prev] = -1; atomicSub(&s_matches, 1); }
+                matches12[i] = bestIdx2;
+                owner[bestIdx2] = i;
+                matched_dist[bestIdx2] = bestDist;
+                ever_matched[i] = bestIdx2;      // the rotation histogram keeps evicted points too (:469-479)
+                atomicAdd(&s_matches, 1);
+            }
+        }
+        __syncthreads();
+        if (s_left == 0) break;
+    }
+    if (tid == 0) *out_nmatches = s_matches;
+}
+
 static GridParams make_grid_params(const float* bounds);
 
 // uploads the frame and the windows, runs the search, downloads feature -> point, point -> feature and the count
@@ -743,6 +806,75 @@ int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, 
                                                                   d_bi, d_bd);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(best_idx, d_bi, (size_t)n_pts * 4) || !cx.download(best_dist, d_bd, (size_t)n_pts * 4) || !cx.finish()) return ORB_ERR_CUDA;
+    return ORB_OK;
+}
+
+int orbm_search_for_initialization(const orb_keypoint_t* kps1_un, const uint8_t* desc1, int n1, const orb_keypoint_t* kps2_un, const uint8_t* desc2,
+                                   int n2, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, float* prev_xy, int window_size,
+                                   float nnratio, int check_orientation, int th_low, int32_t* out_matches12, int* n_matches, int device) {
+    if (n1 < 0 || n2 < 0 || n2 > kFrameMaxFeatures || !bounds || !cell_ptr || !n_matches || (n1 && (!kps1_un || !desc1 || !prev_xy || !out_matches12)) ||
+        (n2 && (!kps2_un || !desc2 || !cell_idx))) {
+        set_error("orbm_search_for_initialization: bad arguments (at most %d features in frame 2)", kFrameMaxFeatures);
+        return ORB_ERR_ARG;
+    }
+    *n_matches = 0;
+    for (int i = 0; i < n1; i++) out_matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return ORB_OK;
+    MatchCtx& cx = match_ctx();
+    const size_t pb = (size_t)(kGridCells + 1) * 4;
+    const size_t need = (size_t)n1 * (sizeof(orb_keypoint_t) + 32 + 8 + 4 + 4 + 1) + (size_t)n2 * (sizeof(orb_keypoint_t) + 32 + 4 + 4 + 4) + pb + 4 + 24 * 256;
+    if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
+    const orb_keypoint_t* d_k1 = (const orb_keypoint_t*)cx.upload(kps1_un, (size_t)n1 * sizeof(orb_keypoint_t));
+    const uint32_t* d_d1 = (const uint32_t*)cx.upload(desc1, (size_t)n1 * 32);
+    const orb_keypoint_t* d_k2 = (const orb_keypoint_t*)cx.upload(kps2_un, (size_t)n2 * sizeof(orb_keypoint_t));
+    const uint32_t* d_d2 = (const uint32_t*)cx.upload(desc2, (size_t)n2 * 32);
+    const int* d_cp = (const int*)cx.upload(cell_ptr, pb);
+    const int* d_ci = (const int*)cx.upload(cell_idx, (size_t)n2 * 4);
+    const float* d_xy = (const float*)cx.upload(prev_xy, (size_t)n1 * 8);
+    int* d_md = (int*)cx.dalloc((size_t)n2 * 4); int* d_ow = (int*)cx.dalloc((size_t)n2 * 4);
+    int* d_m12 = (int*)cx.dalloc((size_t)n1 * 4); int* d_em = (int*)cx.dalloc((size_t)n1 * 4);
+    uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n1); int* d_nm = (int*)cx.dalloc(4);
+    if (!d_k1 || !d_d1 || !d_k2 || !d_d2 || !d_cp || !d_ci || !d_xy || !d_md || !d_ow || !d_m12 || !d_em || !d_res || !d_nm) return ORB_ERR_CUDA;
+    static bool configured = false;
+    if (!configured) {
+        ORB_CUDA_TRY(cudaFuncSetAttribute(init_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 4 + 16));
+        configured = true;
+    }
+    init_search_kernel<<<1, 1024, (size_t)n2 * 4 + 16, cx.stream>>>(d_k1, d_d1, n1, d_k2, d_d2, n2, d_cp, d_ci, make_grid_params(bounds), d_xy,
+                                                                    (float)window_size, nnratio, th_low, d_md, d_ow, d_m12, d_em, d_res, d_nm);
+    ORB_CUDA_TRY(cudaGetLastError());
+    std::vector<int32_t> ever(n1);
+    if (!cx.download(out_matches12, d_m12, (size_t)n1 * 4) || !cx.download(ever.data(), d_em, (size_t)n1 * 4) || !cx.download(n_matches, d_nm, 4) ||
+        !cx.finish()) return ORB_ERR_CUDA;
+    if (check_orientation) {      // :484-506 -- the histogram holds every point that ever matched, in point order
+        constexpr int kHisto = 30;
+        const float factor = 1.0f / kHisto;
+        int cnt[kHisto] = {0};
+        std::vector<int> bin(n1, -1);
+        for (int i = 0; i < n1; i++) {
+            if (ever[i] < 0) continue;
+            float rot = kps1_un[i].angle - kps2_un[ever[i]].angle;
+            if (rot < 0.0) rot += 360.0f;
+            int b = (int)roundf(rot * factor);
+            if (b == kHisto) b = 0;
+            bin[i] = b; cnt[b]++;
+        }
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < kHisto; i++) {
+            const int c = cnt[i];
+            if (c > max1) { max3 = max2; max2 = max1; max1 = c; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (c > max2) { max3 = max2; max2 = c; ind3 = ind2; ind2 = i; }
+            else if (c > max3) { max3 = c; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < n1; i++) {
+            if (bin[i] < 0 || bin[i] == ind1 || bin[i] == ind2 || bin[i] == ind3) continue;
+            if (out_matches12[i] >= 0) { out_matches12[i] = -1; (*n_matches)--; }
+        }
+    }
+    for (int i = 0; i < n1; i++)      // :513-516
+        if (out_matches12[i] >= 0) { prev_xy[2 * i] = kps2_un[out_matches12[i]].x; prev_xy[2 * i + 1] = kps2_un[out_matches12[i]].y; }
     return ORB_OK;
 }
 

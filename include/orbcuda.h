@@ -334,6 +334,18 @@ int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, 
                            const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int32_t* best_idx,
                            int32_t* best_dist, int device);
 
+/* int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
+ *                                         vector<int>& vnMatches12, int windowSize)
+ * R21/src/ORBmatcher.cc:405-520 (monocular initialisation).  Frame 1: undistorted key points + descriptors; frame 2:
+ * the same plus its grid.  prev_xy [n1][2] = vbPrevMatched, updated in place for the matched features (:513-516);
+ * out_matches12 [n1] = vnMatches12; th_low = TH_LOW (50).  The eviction / vMatchedDistance bookkeeping (:451-466) is
+ * reproduced in the reference's point order. */
+int orbm_search_for_initialization(const orb_keypoint_t* kps1_un, const uint8_t* desc1, int n1,
+                                   const orb_keypoint_t* kps2_un, const uint8_t* desc2, int n2, const int32_t* cell_ptr,
+                                   const int32_t* cell_idx, const float* bounds, float* prev_xy, int window_size,
+                                   float nnratio, int check_orientation, int th_low, int32_t* out_matches12,
+                                   int* n_matches, int device);
+
 /* ---------------------------------------------------------------- BoW transform --------------- */
 /* void Frame::ComputeBoW() R21/src/Frame.cc:400-407 / KeyFrame::ComputeBoW() R21/src/KeyFrame.cc:60-69:
  *     mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4);

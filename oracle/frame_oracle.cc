@@ -16,6 +16,7 @@
  */
 #include "orb_oracle.h"
 
+#include <limits.h>
 #include <math.h>
 #include <algorithm>
 #include <vector>
@@ -358,6 +359,68 @@ void orc_window_best_match(const orc_keypoint* kps_un, const uint8_t* desc_f, co
         }
         best_idx[i] = bestIdx; best_dist[i] = bestDist;
     }
+}
+
+/* ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize) :405-520.
+ * kps1_un / desc1: F1.mvKeysUn / F1.mDescriptors; frame 2 as key points + grid; prev_xy [n1][2] = vbPrevMatched (updated
+ * in place for the matched features, :513-516).  out_matches12 [n1] = vnMatches12.  Returns nmatches. */
+int orc_search_for_initialization(const orc_keypoint* kps1_un, const uint8_t* desc1, int n1, const orc_keypoint* kps2_un,
+                                  const uint8_t* desc2, int n2, const int32_t* cell_ptr, const int32_t* cell_idx,
+                                  const float* bounds, float* prev_xy, int window_size, float nnratio, int check_orientation,
+                                  int th_low, int32_t* out_matches12) {
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) out_matches12[i] = -1;
+    std::vector<int> rotHist[kHistoLength];
+    const float factor = 1.0f / kHistoLength;
+    std::vector<int> vMatchedDistance((size_t)n2, INT_MAX);
+    std::vector<int> vnMatches21((size_t)n2, -1);
+    std::vector<int32_t> cand((size_t)std::max(n2, 1));
+    for (int i1 = 0; i1 < n1; i1++) {
+        const orc_keypoint& kp1 = kps1_un[i1];
+        const int level1 = kp1.octave;
+        if (level1 > 0) continue;
+        const int nc = orc_features_in_area(kps2_un, cell_ptr, cell_idx, bounds, prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)window_size,
+                                            level1, level1, cand.data(), n2);
+        if (nc == 0) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            const int dist = orc_descriptor_distance(desc1 + (size_t)i1 * 32, desc2 + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= th_low) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { out_matches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                out_matches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_orientation) {
+                    float rot = kps1_un[i1].angle - kps2_un[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)round(rot * factor);
+                    if (bin == kHistoLength) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, kHistoLength, ind1, ind2, ind3);
+        for (int i = 0; i < kHistoLength; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                const int idx1 = rotHist[i][j];
+                if (out_matches12[idx1] >= 0) { out_matches12[idx1] = -1; nmatches--; }
+            }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (out_matches12[i1] >= 0) { prev_xy[2 * i1] = kps2_un[out_matches12[i1]].x; prev_xy[2 * i1 + 1] = kps2_un[out_matches12[i1]].y; }
+    return nmatches;
 }
 
 }  // extern "C"

@@ -221,6 +221,12 @@ void orc_window_best_match(const orc_keypoint* kps_un, const uint8_t* desc_f, co
                            const float* inv_level_sigma2, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts, float th,
                            int32_t* best_idx, int32_t* best_dist);
 
+/* ORBmatcher::SearchForInitialization (R21/src/ORBmatcher.cc:405-520) */
+int orc_search_for_initialization(const orc_keypoint* kps1_un, const uint8_t* desc1, int n1, const orc_keypoint* kps2_un,
+                                  const uint8_t* desc2, int n2, const int32_t* cell_ptr, const int32_t* cell_idx,
+                                  const float* bounds, float* prev_xy, int window_size, float nnratio, int check_orientation,
+                                  int th_low, int32_t* out_matches12);
+
 /* ---- BoW transform (oracle/bow_oracle.cc): DBoW2 TemplatedVocabulary::transform, PARITY UNPINNED (DBoW2 is not vendored) ---- */
 void orc_bow_transform(const uint8_t* desc, int n, const int32_t* child_ptr, const int32_t* child_idx, const uint8_t* node_desc,
                        const int32_t* word_id, const double* weight, int depth_L, int levelsup, int32_t* out_word,

@@ -484,3 +484,16 @@ def bow_vectors(word, node, weight, normalize=True):
                                   C.c_void_p, C.c_void_p]
     nw = L.orc_bow_vectors(_p(word), _p(node), _p(weight), n, int(normalize), _p(bw), _p(bv), _p(fn), _p(fp), _p(fi), C.byref(nn))
     return (bw[:nw], bv[:nw]), (fn[:nn.value], fp[:nn.value + 1], fi[:fp[nn.value]])
+
+
+def search_for_initialization(k1, d1, k2, d2, ptr, idx, bounds, prev_xy, window, nnratio, check_orientation, th_low=50):
+    k1 = np.ascontiguousarray(k1, KP_DTYPE); k2 = np.ascontiguousarray(k2, KP_DTYPE)
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    b = np.ascontiguousarray(bounds, np.float32); xy = np.ascontiguousarray(prev_xy, np.float32).reshape(-1, 2).copy()
+    m12 = np.zeros(max(len(k1), 1), np.int32)
+    L = lib()
+    L.orc_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    n = L.orc_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(ptr), _p(idx), _p(b), _p(xy), window, nnratio,
+                                        int(check_orientation), th_low, _p(m12))
+    return m12[:len(k1)], xy, n

@@ -387,3 +387,55 @@ def test_gpu_frame_api_rejects_bad_arguments(orb, oracle, golden_dir):
                                  qr.ctypes.data_as(C.c_void_p), lv.ctypes.data_as(C.c_void_p), lv.ctypes.data_as(C.c_void_p), 4,
                                  optr.ctypes.data_as(C.c_void_p), oidx.ctypes.data_as(C.c_void_p), 3, 0)
     assert rc == 3 and optr[4] == 4 * fr.n_assigned                                      # ORB_ERR_CAPACITY, out_ptr complete
+
+
+def _init_pair(oracle, synth, n, seed, crowded=False):
+    """Two frames for the monocular initialiser: frame 2 = frame 1 moved by a few pixels, descriptors with a little noise."""
+    rng = np.random.default_rng(seed)
+    k1 = _keys(oracle, n, seed)
+    k1["octave"] = np.where(rng.random(n) < 0.6, 0, k1["octave"])        # only level-0 points take part (:421-423)
+    if crowded:
+        k1["x"] = (300 + rng.integers(0, 40, n)).astype(np.float32); k1["y"] = (200 + rng.integers(0, 30, n)).astype(np.float32)
+    d1 = synth.descriptors(n, seed=seed + 1)
+    perm = rng.permutation(n)
+    k2 = k1[perm].copy()
+    k2["x"] += rng.normal(3, 4, n).astype(np.float32); k2["y"] += rng.normal(-2, 4, n).astype(np.float32)
+    k2["angle"] = np.mod(k2["angle"] + 8 + rng.normal(0, 2, n), 360).astype(np.float32)
+    wild = rng.random(n) < 0.1
+    k2["angle"][wild] = rng.uniform(0, 360, int(wild.sum()))
+    d2 = d1[perm].copy()
+    for i in range(n):
+        for b in rng.integers(0, 256, rng.integers(0, 20)):
+            d2[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    if crowded:      # near-duplicate descriptors: many points want the same feature, evictions happen
+        d1[: n // 2] = d1[0]; d2[: n // 2] = d1[0]
+        for i in range(n // 2):
+            d1[i, rng.integers(0, 32)] ^= np.uint8(1 << rng.integers(0, 8)); d2[i, rng.integers(0, 32)] ^= np.uint8(1 << rng.integers(0, 8))
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    return k1, d1, k2, d2, prev
+
+
+def test_oracle_search_for_initialization_properties(oracle, synth):
+    k1, d1, k2, d2, prev = _init_pair(oracle, synth, 1500, 61)
+    b = np.array([0, 640, 0, 480], np.float32)
+    ptr, idx = oracle.assign_grid(k2, b)
+    m12, xy, n = oracle.search_for_initialization(k1, d1, k2, d2, ptr, idx, b, prev, 100, 0.9, True)
+    good = m12 >= 0
+    assert n == good.sum() > 300
+    assert len(set(m12[good])) == good.sum()                                  # a frame-2 feature has one owner
+    assert np.all(k1["octave"][good] == 0) and np.all(k2["octave"][m12[good]] == 0)
+    assert np.array_equal(xy[good], np.stack([k2["x"], k2["y"]], 1)[m12[good]]) and np.array_equal(xy[~good], prev[~good])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,crowded,window,ratio", [(1800, False, 100, 0.9), (2500, False, 30, 0.7), (400, True, 100, 0.9), (1, False, 100, 0.9)])
+def test_gpu_search_for_initialization(orb, oracle, synth, n, crowded, window, ratio):
+    k1, d1, k2, d2, prev = _init_pair(oracle, synth, n, 70 + n, crowded)
+    K = np.array([500, 500, 320, 240], np.float32); D = np.zeros(4, np.float32)
+    f2 = orb.FrameFeatures(k2, K, D, 640, 480)
+    for check in (True, False):
+        rm, rxy, rn = oracle.search_for_initialization(k1, d1, f2.keys_un, d2, f2.cell_ptr, f2.cell_idx, f2.bounds, prev, window, ratio, check)
+        gm, gxy, gn = orb.search_for_initialization(k1, d1, f2, d2, prev, window, ratio, check)
+        assert gn == rn and np.array_equal(gm, rm) and np.array_equal(gxy, rxy)
+    if n >= 400:
+        assert rn > 20
