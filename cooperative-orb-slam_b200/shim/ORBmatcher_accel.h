@@ -221,6 +221,61 @@ int SearchByProjection(Frame& F, const FrameGrid& grid, const std::vector<MapPoi
     return nmatches;
 }
 
+// int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)  :1328-1470
+// The projection statements (:1339-1378) stay as written in the reference; they fill one record per LastFrame feature:
+//     orbm_proj_point_t& p = pts[i];  p.valid = 0;
+//     if(pMP && !LastFrame.mvbOutlier[i]) { ... x3Dc = Rcw*x3Dw+tcw; ... if(invzc<0) continue; u = ...; v = ...;
+//         if(u<mnMinX || ...) continue;
+//         p.u = u; p.v = v; p.ur = u - CurrentFrame.mbf*invzc; p.octave = LastFrame.mvKeys[i].octave;
+//         p.angle = LastFrame.mvKeysUn[i].angle; p.obs_positive = pMP->Observations() > 0; p.valid = 1; }
+// and the window loop + rotation check become this call.  direction: 0 neither, 1 bForward, 2 bBackward (:1348-1349).
+template <class Frame, class MapPoint>
+int SearchByProjectionLastFrame(Frame& CurrentFrame, const FrameGrid& grid, const std::vector<orbm_proj_point_t>& pts,
+                                const std::vector<MapPoint*>& lastMapPoints, float th, int direction, bool checkOri,
+                                int th_high = 100, int device = 0)
+{
+    const int N = (int)CurrentFrame.mvKeysUn.size(), nP = (int)pts.size();
+    if(N == 0 || nP == 0) return 0;
+    std::vector<unsigned char> desc((size_t)nP * 32, 0), occ(N);
+    for(int i = 0; i < nP; i++)
+        if(pts[i].valid) std::memcpy(&desc[(size_t)i * 32], lastMapPoints[i]->GetDescriptor().ptr(0), 32);
+    for(int f = 0; f < N; f++) occ[f] = CurrentFrame.mvpMapPoints[f] && CurrentFrame.mvpMapPoints[f]->Observations() > 0;   // :1404-1406
+    std::vector<int32_t> fp(N), pf(nP);
+    int nmatches = 0;
+    check(orbm_search_by_projection_last_frame(reinterpret_cast<const orb_keypoint_t*>(&CurrentFrame.mvKeysUn[0]),
+                                               CurrentFrame.mDescriptors.ptr(0), &CurrentFrame.mvuRight[0], &occ[0], N, &grid.cell_ptr[0],
+                                               &grid.cell_idx[0], grid.bounds, &CurrentFrame.mvScaleFactors[0],
+                                               (int)CurrentFrame.mvScaleFactors.size(), &pts[0], &desc[0], nP, th, direction, checkOri,
+                                               th_high, &fp[0], &pf[0], &nmatches, device), "orbm_search_by_projection_last_frame");
+    for(int f = 0; f < N; f++)
+    {
+        if(fp[f] >= 0) CurrentFrame.mvpMapPoints[f] = lastMapPoints[fp[f]];              // :1430
+        else if(fp[f] == -2) CurrentFrame.mvpMapPoints[f] = static_cast<MapPoint*>(NULL); // :1459
+    }
+    return nmatches;
+}
+
+// void Frame::ComputeBoW() :400-407 / KeyFrame::ComputeBoW() KeyFrame.cc:60-69.  `voc` = orbv_create() of the loaded
+// ORBVocabulary; BowVector / FeatureVector are the DBoW2 std::map types of the frame.
+template <class Frame>
+void ComputeBoW(Frame& F, orbv_handle_t voc, int levelsup = 4)
+{
+    if(!F.mBowVec.empty()) return;
+    const int N = F.mDescriptors.rows;
+    if(N == 0) return;
+    std::vector<int32_t> word(N), node(N), bw(N), fn(N), fp(N + 1), fi(N);
+    std::vector<double> weight(N), bv(N);
+    int nw = 0, nn = 0;
+    check(orbv_transform(voc, F.mDescriptors.ptr(0), N, levelsup, &word[0], &node[0], &weight[0]), "orbv_transform");
+    check(orbv_bow_vectors(&word[0], &node[0], &weight[0], N, 1, &bw[0], &bv[0], &nw, &fn[0], &fp[0], &fi[0], &nn), "orbv_bow_vectors");
+    for(int k = 0; k < nw; k++) F.mBowVec.insert(F.mBowVec.end(), std::make_pair((unsigned int)bw[k], bv[k]));
+    for(int m = 0; m < nn; m++)
+    {
+        std::vector<unsigned int> feats(fi.begin() + fp[m], fi.begin() + fp[m + 1]);
+        F.mFeatVec.insert(F.mFeatVec.end(), std::make_pair((unsigned int)fn[m], feats));
+    }
+}
+
 } // namespace orbaccel
 
 #endif

@@ -32,6 +32,7 @@ struct Frame {
     cv::Mat mDistCoef;
     cv::Mat mDescriptors, mDescriptorsRight;
     FeatureVector mFeatVec;
+    std::map<unsigned int, double> mBowVec;
     ORB_SLAM2::ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
 };
 
@@ -46,6 +47,9 @@ int shim_instantiate(KeyFrame* a, KeyFrame* b, Frame& f) {
     orbaccel::UndistortKeyPoints(f);
     orbaccel::FrameGrid grid = orbaccel::AssignFeaturesToGrid(f, 640, 480);
     n += orbaccel::SearchByProjection(f, grid, out, 1.0f, 0.8f);
+    std::vector<orbm_proj_point_t> pts(out.size());
+    n += orbaccel::SearchByProjectionLastFrame(f, grid, pts, out, 15.0f, 0, true);
+    orbaccel::ComputeBoW(f, (orbv_handle_t)0);
     ORB_SLAM2::ORBextractor e(1000, 1.2f, 8, 20, 7);
     std::vector<cv::KeyPoint> k; cv::Mat d, img;
     e(img, cv::Mat(), k, d);
