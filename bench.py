@@ -162,10 +162,10 @@ def run_reference(args):
         return
     synth = importlib.import_module("cooperative-orb-slam_b200.synth")
     frames = [synth.frame(s, W, H) for s in range(16)]
-    # each "step" is a bounded sample: ~2 s of all-core extraction
-    per_step = 2.0
+    # each "step" is a bounded sample of all-core extraction, sized so that the whole run stays near one minute
+    per_step = min(2.0, 60.0 / max(args.steps, 1))
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_fps(frames, 0.5)
+        cpu_reference_fps(frames, min(0.5, 5.0 / max(args.warmup, 1)))
     tot_n = 0; tot_t = 0.0; kind = "port"; threads = 1
     for _ in range(args.steps):
         fps, kind, threads, n, dt = cpu_reference_fps(frames, per_step)
@@ -541,8 +541,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--streams", type=int, default=4)
