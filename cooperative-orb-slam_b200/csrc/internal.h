@@ -145,6 +145,15 @@ struct MatchCtx {
 };
 MatchCtx& match_ctx();
 
+// Function attributes (dynamic shared memory opt-in) are per device: true the first time the current device is seen.
+inline bool first_use_on_device(bool (&seen)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (seen[dev]) return false;
+    seen[dev] = true;
+    return true;
+}
+
 void set_error(const char* fmt, ...);
 bool cuda_ok(cudaError_t e, const char* what);
 

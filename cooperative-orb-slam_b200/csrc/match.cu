@@ -1247,19 +1247,17 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     if (cudaMallocAsync((void**)&partial, need, s) != cudaSuccess) return -1;
     if (variant == 1) {
         const size_t smem = (size_t)kMmaTile * 256 + kMmaTile * sizeof(int);
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[64] = {false};
+        if (first_use_on_device(configured)) {
             if (cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            configured = true;
         }
         knn2_mma_kernel<<<dim3(qblocks, splits), kMmaThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);
     } else if (variant == 3) {
         const size_t smem = (size_t)kTcQ * 256 + kTcBStages * (size_t)kTcN * 256 + 1024;
-        static bool configured3 = false;
-        if (!configured3) {
+        static bool configured3[64] = {false};
+        if (first_use_on_device(configured3)) {
             if (cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            configured3 = true;
         }
         int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
         if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
@@ -1267,10 +1265,9 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
                                                                       index_base, partial, shared_d2);
     } else if (variant == 5) {
         const size_t smem = (size_t)kTcQ * 256 + kPairBStages * (size_t)kPairHalfN * 256 + 1024;
-        static bool configured5 = false;
-        if (!configured5) {
+        static bool configured5[64] = {false};
+        if (first_use_on_device(configured5)) {
             if (cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            configured5 = true;
         }
         int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
         if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
@@ -1278,10 +1275,9 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
                                                                         index_base, partial, shared_d2);
     } else if (variant == 4) {
         const size_t smem = kTcBStages * (size_t)kTcN * 256 + 1024;
-        static bool configured4 = false;
-        if (!configured4) {
+        static bool configured4[64] = {false};
+        if (first_use_on_device(configured4)) {
             if (cudaFuncSetAttribute(knn2_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            configured4 = true;
         }
         int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
         if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"

@@ -379,11 +379,14 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(DevPtrs d, FrameLay
 int launch_octree(const DevPtrs& d, const FrameLayout& fl, int n_frames, cudaStream_t s) {
     const size_t smem = octree_smem_bytes(fl.node_cap) > (size_t)kOctThreads * 4 ? octree_smem_bytes(fl.node_cap)
                                                                                  : (size_t)kOctThreads * 4;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    // the opt-in is per device (and grows with the largest node capacity seen on it)
+    static thread_local size_t configured[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
         if (cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -1;
-        configured = smem;
+        configured[dev] = smem;
     }
     octree_kernel<<<dim3(fl.nlevels, n_frames), kOctThreads, smem, s>>>(d, fl);
     return 1;
