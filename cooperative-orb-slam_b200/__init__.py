@@ -100,6 +100,11 @@ ABI = {
     "orbv_destroy": (_I, [_VP]),
     "orbv_transform": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "orbv_bow_vectors": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "orbm_peer_create": (_I, [_I, _I, _I, _I, _VP, _VP]),
+    "orbm_peer_connect": (_I, [_VP, _VP]),
+    "orbm_knn2_exchange_device": (_I, [_VP, _VP, _I, _VP, C.c_int64, C.c_int64, _VP, _I, _VP]),
+    "orbm_peer_error": (_I, [_VP, _VP]),
+    "orbm_peer_destroy": (_I, [_VP]),
     "orbw_quantize_lcm_host": (_I, [_VP, _I]),
     "orbw_quantize_lcm_device": (_I, [_VP, _VP, _I, _I, _VP]),
 }
@@ -576,6 +581,37 @@ def window_best_match(frame, desc_f, scale_factors, points, desc_pts, th, u_righ
                                         _p(frame.cell_idx), _p(frame.bounds), _p(sf), None if sg is None else _p(sg), len(sf), _p(pts),
                                         _p(dp), len(pts), float(th), _p(bi), _p(bd), frame.device), "orbm_window_best_match")
     return bi[:len(pts)], bd[:len(pts)]
+
+
+class PeerExchange:
+    """Symmetric record buffers of all ranks (one process per GPU) for the fused merge + exchange of the sharded map
+    search (csrc/peer.cu).  `all_gather_bytes(b) -> [bytes of rank 0, ..., bytes of rank world-1]` is any host-side
+    exchange (bench.py passes a torch.distributed one); this package itself stays free of torch."""
+
+    def __init__(self, nq_cap, rank, world, device, all_gather_bytes):
+        self._h = C.c_void_p()
+        self.rank, self.world = rank, world
+        hnd = (C.c_ubyte * 64)()
+        _check(lib().orbm_peer_create(int(nq_cap), int(rank), int(world), int(device), C.byref(self._h), hnd), "orbm_peer_create")
+        if world > 1:
+            handles = all_gather_bytes(bytes(hnd))
+            assert len(handles) == world and all(len(h) == 64 for h in handles)
+            blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+            _check(lib().orbm_peer_connect(self._h, blob), "orbm_peer_connect")
+
+    def knn2(self, d_q_ptr, nq, d_m_ptr, nm, index_base, d_out_ptr, variant=5, stream=0):
+        """Raw device pointers (ints).  Every rank must call it; d_out = records of the WHOLE map on every rank."""
+        _check(lib().orbm_knn2_exchange_device(self._h, C.c_void_p(d_q_ptr), int(nq), C.c_void_p(d_m_ptr), int(nm), int(index_base),
+                                               C.c_void_p(d_out_ptr), int(variant), C.c_void_p(stream)), "orbm_knn2_exchange_device")
+
+    def error(self):
+        e = C.c_int(0)
+        _check(lib().orbm_peer_error(self._h, C.byref(e)), "orbm_peer_error")
+        return e.value
+
+    def close(self):
+        if self._h:
+            lib().orbm_peer_destroy(self._h); self._h = C.c_void_p()
 
 
 def quantize_lcm(keys):

@@ -108,8 +108,10 @@ int launch_octree_single(const uint32_t* d_cand, int n, int width, int height, i
 size_t octree_smem_bytes(int node_cap);
 
 // matcher
+struct PeerExchange;   // peer.cu: symmetric record buffers of all ranks, mapped through CUDA IPC
+int launch_merge_exchange(PeerExchange* peer, const void* d_partial, int parts, int nq, int32_t* d_out, cudaStream_t s);
 int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out,
-                int variant, cudaStream_t s);
+                int variant, cudaStream_t s, PeerExchange* peer = nullptr);
 int launch_merge_top2(const int32_t* d_parts, int parts, int nq, int32_t* d_out, cudaStream_t s);
 void host_merge_top2(const int32_t* parts, int nparts, int nq, int32_t* out);
 

@@ -1207,7 +1207,7 @@ __global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, in
 }
 
 int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out, int variant,
-                cudaStream_t s) {
+                cudaStream_t s, PeerExchange* peer) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     int sms = 148;
@@ -1290,7 +1290,12 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         knn2_popc_kernel<<<dim3(qblocks, splits), kKnnThreads, 0, s>>>((const uint4*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);
     }
-    merge_top2_kernel<<<(nq + 255) / 256, 256, 0, s>>>(partial, splits, nq, (int4*)d_out);
+    if (peer) {
+        // multi-GPU: merge my splits, push my records into every rank's buffer over NVLink, wait for theirs, merge: one kernel
+        if (launch_merge_exchange(peer, partial, splits, nq, d_out, s) < 0) { cudaFreeAsync(partial, s); return -1; }
+    } else {
+        merge_top2_kernel<<<(nq + 255) / 256, 256, 0, s>>>(partial, splits, nq, (int4*)d_out);
+    }
     cudaFreeAsync(partial, s);
     return 2;
 }

@@ -1,0 +1,203 @@
+// peer.cu -- the one exchange step of the sharded map search, fused with the merges around it.
+//
+// Each rank searches its shard of the map and ends up with per-split {d1, i1, d2, i2} records for every query.  The
+// NCCL formulation is: merge my splits (kernel) -> ncclAllGather (32 KB per rank) -> merge the ranks' records (kernel).
+// Here it is ONE kernel over peer memory: every rank owns a symmetric buffer (cudaMalloc + CUDA IPC, so it works with one
+// process per GPU); a thread merges the splits of its query and stores the record straight into slot [my rank] of EVERY
+// rank's buffer (16-byte stores over NVLink / NVSwitch), the last block of the grid publishes "rank r, epoch e is
+// complete" with a system-scope release store into every buffer, then every block waits (system-scope acquire loads,
+// bounded) for all ranks' flags in its OWN buffer and merges the world's records of its queries.  The merge is the
+// associative lexicographic (distance, index) reduction, so the result equals the single-GPU search bit for bit.
+//   * no deadlock: the grid is sized to be fully resident (grid-stride loops), a rank's scatter depends on nothing remote,
+//     and the wait is bounded by a timer (it raises an error flag instead of hanging if a peer died);
+//   * two parities of slots/flags: a fast rank's scatter of call k+1 cannot overwrite what a slow rank still reads in
+//     call k, and nobody can be two calls ahead (call k+2 needs everybody's flags of call k+1).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "internal.h"
+#include "orbcuda.h"
+
+namespace orbcuda {
+
+constexpr int kMaxPeers = 16;
+
+struct PeerLayout {
+    // [2 parities][world][nq_cap] int4 records, then [2][kMaxPeers] flags, then an error word
+    int world, nq_cap;
+    __host__ __device__ size_t record_index(int parity, int rank, int q) const { return ((size_t)parity * world + rank) * nq_cap + q; }
+    __host__ __device__ size_t flags_offset() const { return (size_t)2 * world * nq_cap * sizeof(int4); }
+    __host__ __device__ size_t bytes() const { return flags_offset() + 2 * kMaxPeers * sizeof(unsigned) + 64; }
+};
+
+struct PeerPtrs { unsigned char* base[kMaxPeers]; };
+
+struct PeerExchange {
+    int device = 0, rank = 0, world = 0, nq_cap = 0;
+    PeerLayout layout{};
+    unsigned char* local = nullptr;
+    PeerPtrs peers{};
+    bool opened[kMaxPeers] = {false};
+    unsigned epoch = 0;
+    unsigned* d_counter = nullptr;      // blocks that finished the scatter phase
+    int* d_error = nullptr;             // set by the kernel when the bounded wait ran out
+    bool connected = false;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ bool lex_less_rec(int da, int ia, int db, int ib) { return da < db || (da == db && (unsigned)ia < (unsigned)ib); }
+__device__ __forceinline__ void merge_rec(int4& a, const int4 b) {
+    // a and b each hold (best, second) in lexicographic (distance, index) order
+    if (lex_less_rec(b.x, b.y, a.x, a.y)) {
+        if (lex_less_rec(b.z, b.w, a.x, a.y)) { a.z = b.z; a.w = b.w; } else { a.z = a.x; a.w = a.y; }
+        a.x = b.x; a.y = b.y;
+    } else if (lex_less_rec(b.x, b.y, a.z, a.w)) { a.z = b.x; a.w = b.y; }
+}
+
+__global__ void __launch_bounds__(256) merge_exchange_kernel(const int4* __restrict__ parts, int nparts, int nq, int rank, PeerLayout L, PeerPtrs peers,
+                                                             unsigned epoch, unsigned* __restrict__ counter, int* __restrict__ error,
+                                                             unsigned long long timeout_ns, int4* __restrict__ out) {
+    const int parity = (int)(epoch & 1u);
+    // ---- phase 1: merge my splits, store my record into every rank's buffer
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        int4 rec = make_int4(256, -1, 256, -1);
+        for (int p = 0; p < nparts; p++) merge_rec(rec, parts[(size_t)p * nq + q]);
+        const size_t at = L.record_index(parity, rank, q);
+        for (int r = 0; r < L.world; r++) reinterpret_cast<int4*>(peers.base[r])[at] = rec;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        // every block's records are out (fence + counter): publish "rank, epoch" everywhere, reset the counter for the next call
+        if ((int)threadIdx.x < L.world)
+            st_release_sys(reinterpret_cast<unsigned*>(peers.base[threadIdx.x] + L.flags_offset()) + parity * kMaxPeers + rank, epoch);
+        if (threadIdx.x == 0) *counter = 0;
+    }
+    // ---- phase 2: wait for everybody's flag in MY buffer, then merge the world's records of my queries
+    const unsigned* my_flags = reinterpret_cast<const unsigned*>(peers.base[rank] + L.flags_offset()) + parity * kMaxPeers;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < L.world) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(my_flags + threadIdx.x) != epoch) {
+            if (global_timer_ns() - t0 > timeout_ns) { s_ok = 0; atomicExch(error, 1 + (int)threadIdx.x); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    const int4* mine = reinterpret_cast<const int4*>(peers.base[rank]);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        int4 rec = make_int4(256, -1, 256, -1);
+        for (int r = 0; r < L.world; r++) {
+            int4 v;      // written by another GPU: read it past the L1
+            asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "l"(mine + L.record_index(parity, r, q)) : "memory");
+            merge_rec(rec, v);
+        }
+        out[q] = rec;
+    }
+}
+
+int launch_merge_exchange(PeerExchange* pe, const void* d_partial, int parts, int nq, int32_t* d_out, cudaStream_t s) {
+    if (!pe || !pe->connected || nq > pe->nq_cap) { set_error("merge-exchange: peer buffers not connected or nq > capacity"); return -1; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pe->device);
+    const int grid = std::max(1, std::min((nq + 255) / 256, 2 * sms));      // resident for sure: 256 threads, a few registers
+    pe->epoch++;
+    merge_exchange_kernel<<<grid, 256, 0, s>>>((const int4*)d_partial, parts, nq, pe->rank, pe->layout, pe->peers, pe->epoch, pe->d_counter, pe->d_error,
+                                              5ull * 1000 * 1000 * 1000, (int4*)d_out);
+    return 1;
+}
+
+}  // namespace orbcuda
+
+using namespace orbcuda;
+
+extern "C" {
+
+int orbm_peer_create(int nq_cap, int rank, int world, int device, orbm_peer_t* out, void* ipc_handle64) {
+    if (nq_cap < 1 || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !out || !ipc_handle64) { set_error("orbm_peer_create: bad arguments (world <= %d)", kMaxPeers); return ORB_ERR_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the IPC handle travels as 64 opaque bytes");
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    PeerExchange* pe = new PeerExchange;
+    pe->device = device; pe->rank = rank; pe->world = world; pe->nq_cap = nq_cap;
+    pe->layout.world = world; pe->layout.nq_cap = nq_cap;
+    if (!cuda_ok(cudaMalloc((void**)&pe->local, pe->layout.bytes()), "cudaMalloc") || !cuda_ok(cudaMemset(pe->local, 0, pe->layout.bytes()), "cudaMemset") ||
+        !cuda_ok(cudaMalloc((void**)&pe->d_counter, 64), "cudaMalloc") || !cuda_ok(cudaMemset(pe->d_counter, 0, 64), "cudaMemset")) {
+        orbm_peer_destroy(reinterpret_cast<orbm_peer_t>(pe));
+        return ORB_ERR_CUDA;
+    }
+    pe->d_error = reinterpret_cast<int*>(pe->d_counter) + 8;
+    cudaIpcMemHandle_t hnd;
+    if (!cuda_ok(cudaIpcGetMemHandle(&hnd, pe->local), "cudaIpcGetMemHandle")) { orbm_peer_destroy(reinterpret_cast<orbm_peer_t>(pe)); return ORB_ERR_CUDA; }
+    memcpy(ipc_handle64, &hnd, 64);
+    pe->peers.base[rank] = pe->local;
+    if (world == 1) pe->connected = true;
+    *out = reinterpret_cast<orbm_peer_t>(pe);
+    return ORB_OK;
+}
+
+int orbm_peer_connect(orbm_peer_t p, const void* handles) {
+    PeerExchange* pe = reinterpret_cast<PeerExchange*>(p);
+    if (!pe || !handles) { set_error("orbm_peer_connect: bad arguments"); return ORB_ERR_ARG; }
+    ORB_CUDA_TRY(cudaSetDevice(pe->device));
+    for (int r = 0; r < pe->world; r++) {
+        if (r == pe->rank || pe->opened[r]) continue;
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, static_cast<const unsigned char*>(handles) + (size_t)r * 64, 64);
+        void* ptr = nullptr;
+        if (!cuda_ok(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return ORB_ERR_CUDA;
+        pe->peers.base[r] = static_cast<unsigned char*>(ptr);
+        pe->opened[r] = true;
+    }
+    pe->connected = true;
+    return ORB_OK;
+}
+
+int orbm_peer_destroy(orbm_peer_t p) {
+    PeerExchange* pe = reinterpret_cast<PeerExchange*>(p);
+    if (!pe) return ORB_OK;
+    cudaSetDevice(pe->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < pe->world; r++)
+        if (pe->opened[r]) cudaIpcCloseMemHandle(pe->peers.base[r]);
+    if (pe->local) cudaFree(pe->local);
+    if (pe->d_counter) cudaFree(pe->d_counter);
+    cudaGetLastError();
+    delete pe;
+    return ORB_OK;
+}
+
+int orbm_knn2_exchange_device(orbm_peer_t p, const uint8_t* d_q, int nq, const uint8_t* d_m_shard, int64_t nm, int64_t index_base,
+                              int32_t* d_out, int variant, void* stream) {
+    PeerExchange* pe = reinterpret_cast<PeerExchange*>(p);
+    if (!pe || !d_q || nq < 1 || !d_out || nm < 0 || (nm > 0 && !d_m_shard) || variant < 0 || variant > 5) { set_error("orbm_knn2_exchange_device: bad arguments"); return ORB_ERR_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_q) & 15) || (reinterpret_cast<uintptr_t>(d_m_shard) & 15)) { set_error("orbm_knn2_exchange_device: descriptor arrays must be 16-byte aligned"); return ORB_ERR_ARG; }
+    if (launch_knn2(d_q, nq, d_m_shard, nm, index_base, d_out, variant, (cudaStream_t)stream, pe) < 0) {
+        cuda_ok(cudaGetLastError(), "knn2 + exchange launch");
+        return ORB_ERR_CUDA;
+    }
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbm_peer_error(orbm_peer_t p, int* error) {
+    PeerExchange* pe = reinterpret_cast<PeerExchange*>(p);
+    if (!pe || !error) return ORB_ERR_ARG;
+    ORB_CUDA_TRY(cudaSetDevice(pe->device));
+    ORB_CUDA_TRY(cudaMemcpy(error, pe->d_error, 4, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+}  // extern "C"

@@ -379,6 +379,23 @@ int orbv_bow_vectors(const int32_t* word, const int32_t* node, const double* wei
 int orbw_quantize_lcm_host(orb_keypoint_t* kps, int n);
 int orbw_quantize_lcm_device(void* d_kps, const int32_t* d_counts, int n_frames, int cap, void* stream);
 
+/* ---------------------------------------------------------------- sharded map search: fused merge + exchange ---- */
+/* The one exchange step of the cross-agent map search without NCCL: every rank (one process per GPU) owns a
+ * symmetric record buffer, shared through CUDA IPC; orbm_knn2_exchange_device searches the rank's map shard and then ONE
+ * kernel merges the rank's splits, stores its records into every rank's buffer over NVLink, publishes a flag, waits for
+ * the other ranks' flags and merges the world's records: d_out [nq][4] = {d1, i1, d2, i2} of the whole map on every
+ * rank, bit-identical to a single-GPU search.  Setup: orbm_peer_create on every rank (returns a 64-byte IPC handle),
+ * exchange the handles with any host-side mechanism (bench.py: torch.distributed.all_gather), orbm_peer_connect with
+ * the world x 64 bytes.  All ranks must make the same sequence of exchange calls.  The wait is bounded (5 s): on
+ * expiry the call's output is undefined and orbm_peer_error reports 1 + the rank that did not arrive. */
+typedef struct orbm_peer_s* orbm_peer_t;
+int orbm_peer_create(int nq_cap, int rank, int world, int device, orbm_peer_t* out, void* ipc_handle64);
+int orbm_peer_connect(orbm_peer_t p, const void* handles /* [world][64] */);
+int orbm_knn2_exchange_device(orbm_peer_t p, const uint8_t* d_q, int nq, const uint8_t* d_m_shard, int64_t nm,
+                              int64_t index_base, int32_t* d_out, int variant, void* stream);
+int orbm_peer_error(orbm_peer_t p, int* error);
+int orbm_peer_destroy(orbm_peer_t p);
+
 #ifdef __cplusplus
 }
 #endif

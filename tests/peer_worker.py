@@ -1,0 +1,61 @@
+"""Worker of tests/test_peer_exchange.py (run under torchrun, one process per GPU): the fused merge + exchange of the
+sharded map search must give, on every rank, exactly the records of a single-GPU search over the whole map."""
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+orb = importlib.import_module("cooperative-orb-slam_b200")
+synth = importlib.import_module("cooperative-orb-slam_b200.synth")
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+
+    def gather_bytes(b):
+        t = torch.tensor(list(b), dtype=torch.uint8, device=dev)
+        allt = torch.empty((world, len(b)), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allt, t)
+        return [allt[r].cpu().numpy().tobytes() for r in range(world)]
+
+    peer = orb.PeerExchange(5000, rank, world, local, gather_bytes)
+    L = orb.lib()
+    cur = torch.cuda.current_stream(dev)
+    checked = 0
+    for nq, nm, seed in ((2000, 200000, 1), (1, 1000, 2), (333, 77777, 3), (5000, 40000, 4), (64, world - 1, 5)):
+        m = synth.descriptors(max(nm, 1), seed=seed)[:nm]
+        q, m, _ = synth.query_set(m, nq=nq, seed=seed + 10) if nm > nq else (synth.descriptors(nq, seed=seed + 20), m, None)
+        if nm > 10:
+            m[nm // 2] = m[3]; m[nm - 1] = m[3]; q[0] = m[3]      # ties across shards: the first index must win
+        d_q = torch.from_numpy(q).to(dev); d_all = torch.from_numpy(np.ascontiguousarray(m).reshape(-1, 32)).to(dev)
+        lo = nm * rank // world; hi = nm * (rank + 1) // world
+        d_shard = d_all[lo:hi].contiguous() if hi > lo else torch.zeros((1, 32), dtype=torch.uint8, device=dev)
+        full = torch.empty((nq, 4), dtype=torch.int32, device=dev)
+        assert L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), nq, C.c_void_p(d_all.data_ptr()), nm, 0, C.c_void_p(full.data_ptr()), 0,
+                                  C.c_void_p(cur.cuda_stream)) == 0
+        for variant in (0, 3, 5):
+            for rep in range(3):      # repeated calls exercise the two slot parities
+                out = torch.full((nq, 4), -9, dtype=torch.int32, device=dev)
+                peer.knn2(d_q.data_ptr(), nq, d_shard.data_ptr(), hi - lo, lo, out.data_ptr(), variant, cur.cuda_stream)
+                torch.cuda.synchronize()
+                assert peer.error() == 0
+                assert bool((out == full).all().item()), (nq, nm, variant, rep, rank)
+                checked += 1
+    dist.barrier()
+    peer.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("peer exchange ok: %d searches identical to the single-GPU result on %d ranks" % (checked, world))
+
+
+if __name__ == "__main__":
+    main()
