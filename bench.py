@@ -428,7 +428,19 @@ def run_ours(args):
                 allt = torch.empty((world, len(b)), dtype=torch.uint8, device=dev)
                 dist.all_gather_into_tensor(allt, t)
                 return [bytes(allt[r].cpu().numpy().tobytes()) for r in range(world)]
-            peer = orb.PeerExchange(NQ, rank, world, local, gather_bytes)
+            # CUDA IPC can be unavailable in some container setups: the NCCL formulation below is then the only one
+            # measured (every rank must take the same branch, hence the all-reduce of the outcome)
+            ok = 1
+            try:
+                peer = orb.PeerExchange(NQ, rank, world, local, gather_bytes)
+            except Exception as exc:      # noqa: BLE001 -- reported, not hidden
+                peer_error = str(exc); ok = 0
+            okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if int(okt.item()) == 0:
+                if peer is not None:
+                    peer.close()
+                peer = None
             fused_out = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
 
         def match_step_fused(variant):
