@@ -562,6 +562,22 @@ def run_ours(args):
         fps, kind, threads, n, dt = cpu_reference_fps([host_frames[0, i] for i in range(min(B, 16))], args.cpu_seconds)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                "sample": "%d frames of the same workload in %.1f s on %d host threads (one extractor per thread)" % (n, dt, threads)}
+        fps1, _, _, n1, dt1 = cpu_reference_fps([host_frames[0, i] for i in range(min(B, 16))], 2.0, threads=1)
+        cpu["single_thread_value"] = fps1
+        cpu["single_thread_ms_per_frame"] = 1e3 / max(fps1, 1e-9)
+        if matching is not None:
+            # the reference's brute-force loop (DescriptorDistance + best/second rule, ORBmatcher.cc:1647-1663, :216-225),
+            # std::thread-parallel over the queries, on a bounded sample of the same query set and map
+            import oracle_lib
+            nm_s = NM
+            q_s = np.ascontiguousarray(q); m_s = np.ascontiguousarray(m_all[:nm_s])
+            i1 = np.zeros(NQ, np.int32); d1 = np.zeros(NQ, np.int32); d2 = np.zeros(NQ, np.int32)
+            Lc = oracle_lib.lib()
+            t0 = time.perf_counter()
+            Lc.orc_knn2(q_s.ctypes.data, NQ, m_s.ctypes.data, nm_s, 0, i1.ctypes.data, d1.ctypes.data, d2.ctypes.data, threads)
+            dtm = time.perf_counter() - t0
+            matching["cpu_baseline"] = {"value": NQ * nm_s / dtm / 1e9, "unit": "Gcmp/s", "cores": threads, "kind": "port",
+                                        "sample": "2000 queries x %d map descriptors (the whole workload) in %.2f s" % (nm_s, dtm)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
