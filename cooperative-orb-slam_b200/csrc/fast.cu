@@ -93,11 +93,11 @@ __device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
     // best = max( c - min_arcs(max_arc), max_arcs(min_arc) - c )   (per 16-bit lane, signed)
     const uint32_t bestP = __vmaxs2(__vsub2(cP, bminP), __vsub2(amaxP, cP));
     const uint32_t bestQ = __vmaxs2(__vsub2(cQ, bminQ), __vsub2(amaxQ, cQ));
-    const int b0 = (int)(short)(bestP & 0xffffu), b2 = (int)bestP >> 16;
-    const int b1 = (int)(short)(bestQ & 0xffffu), b3 = (int)bestQ >> 16;
-    const uint32_t s0 = b0 > th ? b0 - 1 : 0, s1 = b1 > th ? b1 - 1 : 0;
-    const uint32_t s2 = b2 > th ? b2 - 1 : 0, s3 = b3 > th ? b3 - 1 : 0;
-    return s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+    // score = best - 1 where best > th, else 0 -- still on 16-bit pairs; then interleave (px0, px2) and (px1, px3) into bytes
+    const uint32_t th2 = (uint32_t)th * 0x00010001u;
+    const uint32_t sP = __vsub2(bestP, 0x00010001u) & __vcmpgts2(bestP, th2);
+    const uint32_t sQ = __vsub2(bestQ, 0x00010001u) & __vcmpgts2(bestQ, th2);
+    return __byte_perm(sP, sQ, 0x6240);
 }
 
 __global__ void __launch_bounds__(128) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
