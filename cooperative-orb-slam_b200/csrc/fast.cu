@@ -54,18 +54,18 @@ __device__ __forceinline__ void arc_extrema(const uint32_t (&p)[16], uint32_t& m
         lo3[k] = mn3(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
         hi3[k] = mx3(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
     }
-    uint32_t lo9[16], hi9[16];
+    // Arc k = min3(lo3[k], lo3[k+3], lo3[k+6]).  Arcs k and k+3 share two of their three terms, and
+    // max(min(x, m), min(y, m)) = min(m, max(x, y)), so each pair of arcs costs one max and one min3.  The pairs
+    // (0,3) (6,9) (12,15) (2,5) (8,11) (14,1) (4,7) (10,13) cover the 16 arcs once (3 generates Z16).
+    uint32_t pa[8], pb[8];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        lo9[k] = mn3(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
-        hi9[k] = mx3(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    for (int i = 0; i < 8; i++) {
+        const int k = (6 * i) & 15;
+        pa[i] = mn3(lo3[(k + 3) & 15], lo3[(k + 6) & 15], __vmaxs2(lo3[k], lo3[(k + 9) & 15]));
+        pb[i] = mx3(hi3[(k + 3) & 15], hi3[(k + 6) & 15], __vmins2(hi3[k], hi3[(k + 9) & 15]));
     }
-    uint32_t a = mx3(mx3(lo9[0], lo9[1], lo9[2]), mx3(lo9[3], lo9[4], lo9[5]), mx3(lo9[6], lo9[7], lo9[8]));
-    uint32_t b = mx3(mx3(lo9[9], lo9[10], lo9[11]), mx3(lo9[12], lo9[13], lo9[14]), lo9[15]);
-    max_of_min = __vmaxs2(a, b);
-    a = mn3(mn3(hi9[0], hi9[1], hi9[2]), mn3(hi9[3], hi9[4], hi9[5]), mn3(hi9[6], hi9[7], hi9[8]));
-    b = mn3(mn3(hi9[9], hi9[10], hi9[11]), mn3(hi9[12], hi9[13], hi9[14]), hi9[15]);
-    min_of_max = __vmins2(a, b);
+    max_of_min = mx3(mx3(pa[0], pa[1], pa[2]), mx3(pa[3], pa[4], pa[5]), __vmaxs2(pa[6], pa[7]));
+    min_of_max = mn3(mn3(pb[0], pb[1], pb[2]), mn3(pb[3], pb[4], pb[5]), __vmins2(pb[6], pb[7]));
 }
 
 // scores of the 4 pixels x0..x0+3 of the centre row r[3] (window rows r[0..6] = y-3..y+3), packed u8x4
