@@ -62,6 +62,20 @@ def _ncu_traffic(csv_name, kernel_substr):
     return None
 
 
+def _ncu_metric(csv_name, kernel_substr, metric):
+    """One metric of one kernel from a committed ncu summary under profiles/ (None if missing)."""
+    import csv
+    try:
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", csv_name))))
+        i = rows[0].index(metric)
+        for r in rows[2:]:
+            if kernel_substr in r[0]:
+                return float(r[i])
+    except Exception:
+        pass
+    return None
+
+
 def _bf16_peak():
     """Dense bf16 TFLOP/s: MEASURED_PEAKS.json (burst), else the profiling guide's nominal figure."""
     try:
@@ -382,6 +396,10 @@ def run_ours(args):
                             "algorithmic bytes per launch = %d" % (B, B, BYTES[dkey] * B),
             "peak_source": peak_src, "note": bound_note,
             "algorithmic_bytes_per_frame": BYTES[dkey], "kernel_ms_per_launch": kern[dkey]}
+    # what actually bounds this kernel (from the same committed capture): the half-rate integer ALU pipe
+    kname = {"fast_score": "fast_score_kernel", "pyramid": "pyr_resize", "blur": "blur7_kernel<0>", "cell_nms": "fast_nms_kernel"}[dkey]
+    roof["ncu_alu_pipe_pct"] = _ncu_metric("r1_ncu_full_final_summary.csv", kname, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
+    roof["ncu_issue_active_pct"] = _ncu_metric("r1_ncu_full_final_summary.csv", kname, "smsp__issue_active.avg.pct_of_peak_sustained_active")
     roof["stage_ms_per_batch"] = {k: round(v, 4) for k, v in acc.items()}
     roof["stage_gbs"] = {k: round(BYTES[k] * B / (kern[k] * 1e-3) / 1e9, 1) for k in BYTES if kern.get(k, 0) > 0}
 
