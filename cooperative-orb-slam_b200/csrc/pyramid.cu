@@ -61,18 +61,28 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(DevPtrs d, FrameLayout 
     }
     const int X0 = x0 + 4 * lane;
     const int npx = max(0, min(4, tw - 4 * lane));
-    int o0[4], o1[4], c0[4], c1[4];
+    // horizontal taps of my 4 columns: byte offset of the left source pixel and both weights packed as 16-bit pairs.
+    // The right source pixel is always the next byte: where OpenCV clamps it (pad == ofs at the right edge) the
+    // fraction is zero, so c1 == 0 and whatever byte follows contributes nothing.
+    int o0[4];
+    uint32_t cw[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const ResizeTap t = xt[min(X0 + i, gd.w - 1)];
-        o0[i] = t.ofs - sxa; o1[i] = t.pad - sxa; c0[i] = t.c0; c1[i] = t.c1;
+        o0[i] = t.ofs - sxa;
+        cw[i] = (uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16);
     }
     __syncthreads();
     if (npx == 0) return;
     auto hrow = [&](int r, int (&hh)[4]) {
         const uint8_t* S = s_src + r * spitch;
 #pragma unroll
-        for (int i = 0; i < 4; i++) hh[i] = (S[o0[i]] * c0[i] + S[o1[i]] * c1[i]) >> 4;
+        for (int i = 0; i < 4; i++) {
+            const uint32_t two = (uint32_t)S[o0[i]] | ((uint32_t)S[o0[i] + 1] << 8);
+            int acc;      // S[o0]*c0 + S[o0+1]*c1: 16-bit weights x unsigned bytes
+            asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(cw[i]), "r"(two), "r"(0));
+            hh[i] = acc >> 4;
+        }
     };
     constexpr int kNone = -(1 << 20);
     int lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
@@ -80,7 +90,9 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(DevPtrs d, FrameLayout 
     const int dy_end = min(th, warp * 8 + 8);
     for (int dy = warp * 8; dy < dy_end; dy++) {
         const int Y = y0 + dy;
-        const ResizeTap ty = yt[Y];
+        const uint2 traw = *reinterpret_cast<const uint2*>(yt + Y);      // {ofs, c0, c1, pad} in one load
+        ResizeTap ty;
+        ty.ofs = (int16_t)(traw.x & 0xffffu); ty.c0 = (int16_t)(traw.x >> 16); ty.c1 = (int16_t)(traw.y & 0xffffu); ty.pad = (int16_t)(traw.y >> 16);
         const int r0 = ty.ofs - sy0, r1 = ty.pad - sy0;
         if (r0 != r_lo) {
             if (r0 == r_hi) {
@@ -119,7 +131,7 @@ int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg,
     int launches = 0;
     for (int l = 1; l < fl.nlevels; l++) {   // level 0 is the input image itself
         const LevelGeom& g = hg[l];
-        const size_t smem = (size_t)g.rs_rows * g.rs_cols;
+        const size_t smem = (size_t)g.rs_rows * g.rs_cols + 16;     // + slack: the (zero-weight) byte after the last staged pixel is read
         if (smem > 48 * 1024 || g.rs_cols > 256) return -1;   // scale factors this large are not supported
         const dim3 grid((g.w + kPyrTileW - 1) / kPyrTileW, (g.h + kPyrTileH - 1) / kPyrTileH, n_frames);
         pyr_resize_kernel<<<grid, 256, smem, s>>>(d, fl, l);
