@@ -13,27 +13,49 @@
 //                      to the level's candidate list.  The per-cell iniTh -> minTh fallback happens in
 //                      the quadtree kernel's gather (octree.cu).
 #include "internal.h"
+#include <cstdlib>
 
 namespace orbcuda {
 
+constexpr bool kFastFmaDefault = false;
 constexpr int kFastRows = 14;   // rows per strip (two 7-row register rotations)
 
 __device__ __forceinline__ uint32_t fun16(uint32_t lo, uint32_t hi) { return __funnelshift_r(lo, hi, 16); }
 __device__ __forceinline__ uint32_t mn3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t mx3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 
+// 2-input min/max of non-negative pairs on the FMA pipe (the integer min/max all issue on the half-rate ALU pipe, which
+// bounds this kernel): with a pixel p stored as the fp16 value 1024 + p (bit pattern 0x6400 + p -- ordered and spaced
+// like the integer, so the 16-bit integer min/max/subtract work on it unchanged), max(x, y) = y + relu(x - y) and
+// min(x, y) = y - relu(y - x) are exact in fp16 (|x - y| <= 255).
+__device__ __forceinline__ uint32_t fmax2(uint32_t x, uint32_t y) {
+    uint32_t t, r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(t) : "r"(y), "r"(0xBC00BC00u), "r"(x));
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(y), "r"(t));
+    return r;
+}
+__device__ __forceinline__ uint32_t fmin2(uint32_t x, uint32_t y) {
+    uint32_t t, r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(t) : "r"(x), "r"(0xBC00BC00u), "r"(y));
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(y), "r"(t));
+    return r;
+}
+template <bool HF> __device__ __forceinline__ uint32_t mx2(uint32_t a, uint32_t b) { return HF ? fmax2(a, b) : __vmaxs2(a, b); }
+template <bool HF> __device__ __forceinline__ uint32_t mn2(uint32_t a, uint32_t b) { return HF ? fmin2(a, b) : __vmins2(a, b); }
+
 // One image row around a 4-pixel group at x0 as 16-bit pairs:
 //   a0=(p[x0-4],p[x0-2]) a1=(p[x0-3],p[x0-1]) b0=(p[x0],p[x0+2]) b1=(p[x0+1],p[x0+3])
 //   c0=(p[x0+4],p[x0+6]) c1=(p[x0+5],p[x0+7])
 struct Row6 { uint32_t a0, a1, b0, b1, c0, c1; };
 
-__device__ __forceinline__ Row6 load_row6(const uint8_t* p) {
+template <bool HF> __device__ __forceinline__ Row6 load_row6(const uint8_t* p) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    const uint32_t bias = HF ? 0x64006400u : 0u;      // HF: every 16-bit lane holds the fp16 value 1024 + p
     Row6 r;
-    r.a0 = w0 & 0x00ff00ffu; r.a1 = (w0 >> 8) & 0x00ff00ffu;
-    r.b0 = w1 & 0x00ff00ffu; r.b1 = (w1 >> 8) & 0x00ff00ffu;
-    r.c0 = w2 & 0x00ff00ffu; r.c1 = (w2 >> 8) & 0x00ff00ffu;
+    r.a0 = (w0 & 0x00ff00ffu) | bias; r.a1 = ((w0 >> 8) & 0x00ff00ffu) | bias;
+    r.b0 = (w1 & 0x00ff00ffu) | bias; r.b1 = ((w1 >> 8) & 0x00ff00ffu) | bias;
+    r.c0 = (w2 & 0x00ff00ffu) | bias; r.c1 = ((w2 >> 8) & 0x00ff00ffu) | bias;
     return r;
 }
 // E<t>(row) = (p[x0+t], p[x0+t+2])
@@ -47,7 +69,7 @@ __device__ __forceinline__ uint32_t E3(const Row6& r) { return fun16(r.b1, r.c1)
 __device__ __forceinline__ uint32_t E4(const Row6& r) { return r.c0; }
 
 // max over the 16 circular 9-arcs of min(arc), and min over them of max(arc), on two pixels at once
-__device__ __forceinline__ void arc_extrema(const uint32_t (&p)[16], uint32_t& max_of_min, uint32_t& min_of_max) {
+template <bool HF> __device__ __forceinline__ void arc_extrema(const uint32_t (&p)[16], uint32_t& max_of_min, uint32_t& min_of_max) {
     uint32_t lo3[16], hi3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -61,15 +83,15 @@ __device__ __forceinline__ void arc_extrema(const uint32_t (&p)[16], uint32_t& m
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int k = (6 * i) & 15;
-        pa[i] = mn3(lo3[(k + 3) & 15], lo3[(k + 6) & 15], __vmaxs2(lo3[k], lo3[(k + 9) & 15]));
-        pb[i] = mx3(hi3[(k + 3) & 15], hi3[(k + 6) & 15], __vmins2(hi3[k], hi3[(k + 9) & 15]));
+        pa[i] = mn3(lo3[(k + 3) & 15], lo3[(k + 6) & 15], mx2<HF>(lo3[k], lo3[(k + 9) & 15]));
+        pb[i] = mx3(hi3[(k + 3) & 15], hi3[(k + 6) & 15], mn2<HF>(hi3[k], hi3[(k + 9) & 15]));
     }
-    max_of_min = mx3(mx3(pa[0], pa[1], pa[2]), mx3(pa[3], pa[4], pa[5]), __vmaxs2(pa[6], pa[7]));
-    min_of_max = mn3(mn3(pb[0], pb[1], pb[2]), mn3(pb[3], pb[4], pb[5]), __vmins2(pb[6], pb[7]));
+    max_of_min = mx3(mx3(pa[0], pa[1], pa[2]), mx3(pa[3], pa[4], pa[5]), mx2<HF>(pa[6], pa[7]));
+    min_of_max = mn3(mn3(pb[0], pb[1], pb[2]), mn3(pb[3], pb[4], pb[5]), mn2<HF>(pb[6], pb[7]));
 }
 
 // scores of the 4 pixels x0..x0+3 of the centre row r[3] (window rows r[0..6] = y-3..y+3), packed u8x4
-__device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
+template <bool HF> __device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
     // circle (dx,dy), OpenCV order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
     const uint32_t e2_5 = E2(r[5]), em1_5 = Em1(r[5]), e2_1 = E2(r[1]), em1_1 = Em1(r[1]);
     const uint32_t em1_6 = Em1(r[6]), e2_6 = E2(r[6]), em1_0 = Em1(r[0]), e2_0 = E2(r[0]);
@@ -87,8 +109,8 @@ __device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
     Q[8] = E1(r[0]);  Q[9] = E0(r[0]);  Q[10] = em1_1;     Q[11] = em2_2;
     Q[12] = em2_3;    Q[13] = em2_4;    Q[14] = em1_5;     Q[15] = E0(r[6]);
     uint32_t amaxP, bminP, amaxQ, bminQ;
-    arc_extrema(P, amaxP, bminP);
-    arc_extrema(Q, amaxQ, bminQ);
+    arc_extrema<HF>(P, amaxP, bminP);
+    arc_extrema<HF>(Q, amaxQ, bminQ);
     const uint32_t cP = E0(r[3]), cQ = E1(r[3]);
     // best = max( c - min_arcs(max_arc), max_arcs(min_arc) - c )   (per 16-bit lane, signed)
     const uint32_t bestP = __vmaxs2(__vsub2(cP, bminP), __vsub2(amaxP, cP));
@@ -100,7 +122,7 @@ __device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
     return __byte_perm(sP, sQ, 0x6240);
 }
 
-__global__ void __launch_bounds__(128) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
+template <bool HF> __global__ void __launch_bounds__(128) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
     int level = 0;
     while (level + 1 < fl.nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
     const LevelGeom g = d.geom[level];
@@ -122,12 +144,12 @@ __global__ void __launch_bounds__(128) fast_score_kernel(DevPtrs d, FrameLayout 
 
     Row6 r[7];
 #pragma unroll
-    for (int k = 0; k < 6; k++) r[k] = load_row6(src + (ptrdiff_t)(y0 - 3 + k) * pitch);
+    for (int k = 0; k < 6; k++) r[k] = load_row6<HF>(src + (ptrdiff_t)(y0 - 3 + k) * pitch);
 #pragma unroll
     for (int j = 0; j < kFastRows; j++) {
         const int y = y0 + j;
-        r[6] = load_row6(src + (ptrdiff_t)min(y + 3, g.h - 1) * pitch);
-        const uint32_t s4 = fast_score4(r, th) & colmask;
+        r[6] = load_row6<HF>(src + (ptrdiff_t)min(y + 3, g.h - 1) * pitch);
+        const uint32_t s4 = fast_score4<HF>(r, th) & colmask;
         if (y < g.h - kEdge) *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.spitch) = s4;
 #pragma unroll
         for (int k = 0; k < 6; k++) r[k] = r[k + 1];
@@ -146,7 +168,10 @@ int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* 
         total += (nsx * nsy + threads - 1) / threads;
     }
     for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
-    fast_score_kernel<<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb, min_th);
+    // ORBCUDA_FAST_FMA=0 keeps every min/max on the ALU pipe (A/B switch; results are identical)
+    static const bool hf = [] { const char* e = getenv("ORBCUDA_FAST_FMA"); return e ? atoi(e) != 0 : kFastFmaDefault; }();
+    if (hf) fast_score_kernel<true><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb, min_th);
+    else fast_score_kernel<false><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb, min_th);
     return 1;
 }
 
@@ -162,7 +187,7 @@ int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* 
 // quadtree kernel applies the per-cell iniTh -> minTh fallback from the flags and resolves ties with an
 // explicit (cell, raster) order key, so nothing downstream depends on it.
 // ---------------------------------------------------------------------------------------------
-constexpr int kNmsRows = 16;
+constexpr int kNmsRows = 16;   // < 30 <= h_cell (FAST cells are at least 30 rows high, extractor.cu)
 
 __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict__ score, int64_t plane_frame_bytes,
                                                        uint32_t* __restrict__ cand, int64_t cand_frame_entries,
@@ -174,65 +199,83 @@ __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict
     const LevelGeom g = geom[level];
     const int lane = threadIdx.x & 31;
     const int nsx = (g.w - kEdge - kMinBorder + 3) >> 2;     // same strips as the score kernel: x0 = 16 + 4*sx
-    const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
-    const int sy = id / nsx;
-    const int x0 = kMinBorder + 4 * (id - sy * nsx);
+    const unsigned id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
+    const int sy = (int)(id / (unsigned)nsx);
+    const int x0 = kMinBorder + 4 * ((int)id - sy * nsx);
     const int y0 = kEdge + sy * kNmsRows;
     const bool active = y0 < g.h - kEdge;
     uint32_t* list = cand + (size_t)blockIdx.y * cand_frame_entries + g.cand_off;
     int32_t* counter = level_raw + (size_t)blockIdx.y * kMaxLevels + level;
-    // survivor bitmask of the strip: bit (4*r + b) of km[r / 8] <=> pixel (x0+b, y0+r) survives
-    uint32_t km0 = 0, km1 = 0;
     const uint8_t* src = score + (size_t)blockIdx.y * plane_frame_bytes + g.splane_off + x0;
-    int cy0 = 0, ymod0 = 0;
+    // All 18 rows of the strip are requested before anything is computed: 54 independent 32-bit loads in flight per
+    // thread.  The block barrier pins them there (without it ptxas sinks each row's loads next to their use to save
+    // registers and every row pays the full memory latency: the kernel was latency-bound, ncu long-scoreboard stalls).
+    // Strips past the last row clamp to row H-19 (exists in the plane) and are discarded.
+    const int ylast = g.h - kEdge;   // row H-19 is never a centre row
+    uint32_t W0[kNmsRows + 2], W1[kNmsRows + 2], W2[kNmsRows + 2];
+#pragma unroll
+    for (int r = 0; r < kNmsRows + 2; r++) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)min(y0 - 1 + r, ylast) * g.spitch);
+        W0[r] = __ldg(p - 1); W1[r] = __ldg(p); W2[r] = __ldg(p + 1);
+    }
+    __syncthreads();
+    // survivor bits of the strip, 4 rows per word: pixel (x0+b, y0+4g+q) is bit 8 + 2q + (b&1) + 16*(b>>1) of km[g]
+    uint32_t km[kNmsRows / 4] = {0, 0, 0, 0};
+    // cell column of pixel x0+b = col0 + (b >= wrapb); cell row of strip row r = cy0 + (r > rb)
+    const unsigned ux = (unsigned)(x0 - kEdge + g.w_cell);                 // >= w_cell - 3 > 0
+    const unsigned qx = ux / (unsigned)g.w_cell;
+    const int m0 = (int)(ux - qx * (unsigned)g.w_cell);                     // (x0 - 19) mod w_cell
+    const int col0 = (int)qx - 1, wrapb = g.w_cell - m0;
+    const unsigned uy = (unsigned)(y0 - kEdge);
+    const int cy0 = (int)(uy / (unsigned)g.h_cell);
+    const int ymod0 = (int)uy - cy0 * g.h_cell;
+    // h_cell >= 30 > kNmsRows: a strip crosses at most one cell boundary.  rb = strip row that is the last row of
+    // its cell; the row after it is the first row of the next cell.
+    const int rb = g.h_cell - 1 - ymod0;
+    const int rlast = g.h - kEdge - 1 - y0;            // last row of [19, H-19)
     if (active) {
-        // per-column validity masks (bytes): pixel in range / its left neighbour in the same cell / its right one
-        uint32_t MC = 0, ML = 0, MR = 0;
+        // Scores are handled as 16-bit pairs (the byte-wise SIMD intrinsics are emulated on sm_100a, the 16x2
+        // min/max is one instruction): "even" words hold pixels (x0, x0+2), "odd" words (x0+1, x0+3).
+        // Per-lane masks (0x00ff or 0): left / right neighbour in the same cell; KC: bit 8 of the lane if the pixel is in range.
+        uint32_t MLe = 0, MLo = 0, MRe = 0, MRo = 0, KCe = 0, KCo = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int x = x0 + b;
             if (x >= kEdge && x < g.w - kEdge) {
-                const int m = (x - kEdge) % g.w_cell;
-                MC |= 0xffu << (8 * b);
-                if (m != 0) ML |= 0xffu << (8 * b);
-                if (m != g.w_cell - 1 && x != g.w - kEdge - 1) MR |= 0xffu << (8 * b);
+                const int m = m0 + b - (b >= wrapb ? g.w_cell : 0);
+                const uint32_t lane16 = 0xffu << (16 * (b >> 1));
+                const bool l_ok = m != 0, r_ok = m != g.w_cell - 1 && x != g.w - kEdge - 1;
+                if (b & 1) { KCo |= 0x100u << (16 * (b >> 1)); if (l_ok) MLo |= lane16; if (r_ok) MRo |= lane16; }
+                else       { KCe |= 0x100u << (16 * (b >> 1)); if (l_ok) MLe |= lane16; if (r_ok) MRe |= lane16; }
             }
         }
-        ymod0 = (y0 - kEdge) % g.h_cell;
-        cy0 = (y0 - kEdge) / g.h_cell;
-        int ymod = ymod0;
-        // all rows of the strip are fetched up front (54 independent 32-bit loads in flight per thread)
-        const int ylast = g.h - kEdge;   // row H-19 exists in the plane; it is masked out below
-        uint32_t W0[kNmsRows + 2], W1[kNmsRows + 2], W2[kNmsRows + 2];
+        // per row: centre pairs, max(left, right) and max(left, centre, right) with out-of-cell horizontal neighbours zeroed
+        uint32_t Ce[kNmsRows + 2], Co[kNmsRows + 2], LRe[kNmsRows + 2], LRo[kNmsRows + 2], He[kNmsRows + 2], Ho[kNmsRows + 2];
 #pragma unroll
         for (int r = 0; r < kNmsRows + 2; r++) {
-            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)min(y0 - 1 + r, ylast) * g.spitch);
-            W0[r] = p[-1]; W1[r] = p[0]; W2[r] = p[1];
-        }
-        // h3(row) = bytewise max of (left, centre, right) with out-of-cell horizontal neighbours zeroed
-        uint32_t LR[kNmsRows + 2], H3[kNmsRows + 2];
-#pragma unroll
-        for (int r = 0; r < kNmsRows + 2; r++) {
-            const uint32_t L = __funnelshift_l(W0[r], W1[r], 8) & ML;      // byte b = pixel x0+b-1
-            const uint32_t R = __funnelshift_r(W1[r], W2[r], 8) & MR;      // byte b = pixel x0+b+1
-            LR[r] = __vmaxu4(L, R);
-            H3[r] = __vmaxu4(LR[r], W1[r]);
+            Ce[r] = W1[r] & 0x00ff00ffu;                                     // (p0, p2)
+            Co[r] = __byte_perm(W1[r], 0u, 0x4341);                          // (p1, p3)
+            const uint32_t Le = __byte_perm(W0[r], W1[r], 0x0503) & MLe;     // (p-1, p1); the mask also clears bytes 1 and 3
+            const uint32_t Ro = __byte_perm(W1[r], W2[r], 0x0402) & MRo;     // (p2, p4)
+            const uint32_t Re = Co[r] & MRe, Lo = Ce[r] & MLo;
+            LRe[r] = __vmaxs2(Le, Re); He[r] = __vimax3_s16x2(Le, Re, Ce[r]);
+            LRo[r] = __vmaxs2(Lo, Ro); Ho[r] = __vimax3_s16x2(Lo, Ro, Co[r]);
         }
 #pragma unroll
         for (int r = 0; r < kNmsRows; r++) {
-            const int y = y0 + r;
-            const bool top = ymod == 0, bot = ymod == g.h_cell - 1 || y == g.h - kEdge - 1;
-            const uint32_t up = top ? 0u : H3[r], dn = bot ? 0u : H3[r + 2];   // row 18 / H-19 never used: masked here
-            const uint32_t m = __vmaxu4(__vmaxu4(up, dn), LR[r + 1]);
-            uint32_t keep = __vcmpgtu4(W1[r + 1], m) & MC;      // strict: equal neighbours suppress each other
-            if (y >= g.h - kEdge) keep = 0;
-            const uint32_t bits = ((keep & 0x08040201u) * 0x01010101u) >> 24;   // 0xff bytes -> 4 bits
-            if (r < 8) km0 |= bits << (4 * r); else km1 |= bits << (4 * (r - 8));
-            if (++ymod == g.h_cell) ymod = 0;
+            const bool top = (r == rb + 1) || (r == 0 && ymod0 == 0);
+            const bool bot = (r == rb) || (r == rlast);
+            uint32_t me = LRe[r + 1], mo = LRo[r + 1];
+            if (!top) { me = __vmaxs2(me, He[r]); mo = __vmaxs2(mo, Ho[r]); }          // row 18 is never used: r = 0 there is a cell top
+            if (!bot) { me = __vmaxs2(me, He[r + 2]); mo = __vmaxs2(mo, Ho[r + 2]); }
+            // strict: 256 + m - c keeps bit 8 of the lane set unless c > m (equal neighbours suppress each other)
+            const uint32_t ke = ~(me + 0x01000100u - Ce[r + 1]) & KCe;
+            const uint32_t ko = ~(mo + 0x01000100u - Co[r + 1]) & KCo;
+            if (r <= rlast) km[r >> 2] += (ke + 2u * ko) << (2 * (r & 3));
         }
     }
     // warp-aggregated append: one atomic per warp reserves room for all its survivors
-    const int mine = __popc(km0) + __popc(km1);
+    const int mine = __popc(km[0]) + __popc(km[1]) + __popc(km[2]) + __popc(km[3]);
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -245,24 +288,20 @@ __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict
     if (lane == 31) base = atomicAdd(counter, total);
     int pos = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
     if (mine == 0) return;
-    const int cx0 = (max(x0, kEdge) - kEdge) / g.w_cell;     // cell column of the 4 pixels: cx0 or cx0+1
-    const int xnext = kEdge + (cx0 + 1) * g.w_cell;
-    int32_t* flags = cell_flag + (size_t)blockIdx.y * n_cells + g.cell_base;
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        uint32_t km = half ? km1 : km0;
-        while (km) {
-            const int bit = __ffs(km) - 1;
-            km &= km - 1;
-            const int r = half * 8 + (bit >> 2), b = bit & 3;
-            const int x = x0 + b, y = y0 + r;
-            const uint32_t sc = src[(size_t)y * g.spitch + b];
-            list[pos++] = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | (sc << 24);
-            if ((int)sc >= ini_th) {
-                // cell row of y: rows advance from (cy0, ymod0)
-                const int cy = cy0 + (ymod0 + r) / g.h_cell;
-                flags[cy * g.n_cols + cx0 + (x >= xnext ? 1 : 0)] = 1;
-            }
+    int32_t* flags = cell_flag + (size_t)blockIdx.y * n_cells + g.cell_base + cy0 * g.n_cols + col0;
+    const uint8_t* srow = src + (size_t)y0 * g.spitch;
+    const uint32_t packed0 = (uint32_t)(x0 - kMinBorder) | ((uint32_t)(y0 - kMinBorder) << 12);
+#pragma unroll
+    for (int grp = 0; grp < kNmsRows / 4; grp++) {
+        uint32_t m = km[grp];
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int q = (bit & 15) - 8;
+            const int r = grp * 4 + (q >> 1), b = (q & 1) + 2 * (bit >> 4);
+            const uint32_t sc = srow[r * g.spitch + b];
+            list[pos++] = (packed0 + (uint32_t)b + ((uint32_t)r << 12)) | (sc << 24);
+            if ((int)sc >= ini_th) flags[(r > rb ? g.n_cols : 0) + (b >= wrapb ? 1 : 0)] = 1;
         }
     }
 }
