@@ -123,6 +123,13 @@ template <bool HF> __device__ __forceinline__ uint32_t fast_score4(const Row6 (&
 }
 
 template <bool HF> __global__ void __launch_bounds__(128) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
+    if (blockIdx.x == 0) {
+        // this frame's survivor counters and cell flags, consumed by fast_nms_kernel two launches later on the same
+        // stream (saves two memset nodes per batch)
+        int32_t* cc = d.cell_count + (size_t)blockIdx.y * fl.n_cells;
+        for (int i = threadIdx.x; i < fl.n_cells; i += blockDim.x) cc[i] = 0;
+        if (threadIdx.x < kMaxLevels) d.level_raw[(size_t)blockIdx.y * kMaxLevels + threadIdx.x] = 0;
+    }
     int level = 0;
     while (level + 1 < fl.nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
     const LevelGeom g = d.geom[level];
@@ -318,8 +325,7 @@ int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* 
         total += (nsx * nsy + nthreads - 1) / nthreads;
     }
     for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
-    if (cudaMemsetAsync(d.cell_count, 0, (size_t)n_frames * fl.n_cells * sizeof(int32_t), s) != cudaSuccess) return -1;
-    if (cudaMemsetAsync(d.level_raw, 0, (size_t)n_frames * kMaxLevels * sizeof(int32_t), s) != cudaSuccess) return -1;
+    // d.cell_count and d.level_raw were zeroed by fast_score_kernel (launched before this kernel on the same stream)
     fast_nms_kernel<<<dim3(total, n_frames), nthreads, 0, s>>>(d.score, fl.splane_bytes, d.cand, fl.cand_entries,
                                                                d.cell_count, fl.n_cells, d.level_raw, d.geom, fl.nlevels, lb,
                                                                ini_th);

@@ -322,7 +322,9 @@ size_t octree_smem_bytes(int cap) {
 __global__ void __launch_bounds__(kOctThreads) octree_kernel(DevPtrs d, FrameLayout fl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_total;
-    const int level = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    // grid = (frames, levels): CTAs are dispatched level 0 first for every frame, i.e. longest first (a level-0 CTA runs
+    // about 4x longer than a level-7 one), so the tail of the launch is made of the short ones
+    const int level = blockIdx.y, frame = blockIdx.x, tid = threadIdx.x;
     const LevelGeom g = d.geom[level];
     const int32_t* cc = d.cell_count + (size_t)frame * fl.n_cells + g.cell_base;
     const uint32_t* cand = d.cand + (size_t)frame * fl.cand_entries + g.cand_off;
@@ -388,7 +390,7 @@ int launch_octree(const DevPtrs& d, const FrameLayout& fl, int n_frames, cudaStr
             return -1;
         configured[dev] = smem;
     }
-    octree_kernel<<<dim3(fl.nlevels, n_frames), kOctThreads, smem, s>>>(d, fl);
+    octree_kernel<<<dim3(n_frames, fl.nlevels), kOctThreads, smem, s>>>(d, fl);
     return 1;
 }
 
