@@ -16,9 +16,15 @@
 // "later created == larger pointer" is the one the CPU oracle is pinned to.
 #include "internal.h"
 
+#include <cstdlib>
+
 namespace orbcuda {
 
-constexpr int kOctThreads = 512;
+// CTA size is a template parameter (<= 512: 16 warp slots in the scans).  512 threads give the shortest CTA (single-frame
+// latency); 256 threads make each CTA ~1.3x slower but twice as many fit on an SM, which wins as soon as a launch has
+// more CTAs than the GPU holds (batches): measured +4.4 % frames/s at 4 streams x 128 frames.
+constexpr int kOctThreadsLatency = 512, kOctThreadsBatch = 256;
+constexpr int kOctBatchFrames = 16;     // launches with at least this many frames use the small CTA
 
 struct OctSmem {
     short4* box[2];     // (ulx, uly, brx, bry)
@@ -40,7 +46,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 }
 
 // in-place exclusive scan of a[0..n) by the whole block; returns the total.  `wsum` is 17 ints of smem.
-__device__ int block_excl_scan(int* a, int n, int* wsum) {
+template <int kOctThreads> __device__ int block_excl_scan(int* a, int n, int* wsum) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int running = 0;
     for (int base = 0; base < n; base += kOctThreads) {
@@ -73,7 +79,7 @@ __device__ __forceinline__ int quadrant_of(uint32_t kp, short4 b) {
 // Shared by the batched kernel and the stand-alone entry point.
 // kp[0..n): packed candidates in input order; node[0..n): scratch; out_sel[0..kp_cap): selected
 // candidates in list order; returns the number of nodes (all threads).
-__device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, int height, int N, int n_ini, float h_x,
+template <int kOctThreads> __device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, int height, int N, int n_ini, float h_x,
                           uint32_t* out_sel, int32_t* out_idx, int cap, unsigned char* smem_raw, int order_cols, int w_cell,
                           int h_cell) {
     __shared__ int wsum[17];
@@ -117,7 +123,7 @@ __device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, 
     {
         for (int i = tid; i < n_ini; i += kOctThreads) S.a0[i] = S.cnt[0][i] > 0 ? 1 : 0;
         __syncthreads();
-        const int alive0 = block_excl_scan(S.a0, n_ini, wsum);
+        const int alive0 = block_excl_scan<kOctThreads>(S.a0, n_ini, wsum);
         if (alive0 != n_ini) {
             for (int i = tid; i < n_ini; i += kOctThreads)
                 if (S.cnt[0][i] > 0) { S.box[1][S.a0[i]] = S.box[0][i]; S.cnt[1][S.a0[i]] = S.cnt[0][i]; }
@@ -179,7 +185,7 @@ __device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, 
                 S.a1[j] = nc - 1;
             }
             __syncthreads();
-            block_excl_scan(S.a1, m, wsum);   // exclusive: a1[j] = growth before node j
+            block_excl_scan<kOctThreads>(S.a1, m, wsum);   // exclusive: a1[j] = growth before node j
             // cut = first j with alive + a1[j] + (nc_j-1) >= N ; divide j <= cut   (:731-732)
             if (tid == 0) s_flag[1] = m;   // default: divide all
             __syncthreads();
@@ -199,7 +205,7 @@ __device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, 
         //    a1[i] <- survivor position (for non-divided) ; key[i] <- child base (for divided)
         for (int i = tid; i < alive; i += kOctThreads) S.a1[i] = S.a0[i] ? 0 : 1;
         __syncthreads();
-        const int n_surv = block_excl_scan(S.a1, alive, wsum);
+        const int n_surv = block_excl_scan<kOctThreads>(S.a1, alive, wsum);
         int n_children;
         int* cbase = reinterpret_cast<int*>(S.key);   // reuse (phase-b keys are dead by now)
         if (!phase_b) {
@@ -210,7 +216,7 @@ __device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, 
                 tmp[i] = S.a0[p] ? (S.ccnt[4 * p] > 0) + (S.ccnt[4 * p + 1] > 0) + (S.ccnt[4 * p + 2] > 0) + (S.ccnt[4 * p + 3] > 0) : 0;
             }
             __syncthreads();
-            n_children = block_excl_scan(tmp, alive, wsum);   // tmp[i] = base of node alive-1-i
+            n_children = block_excl_scan<kOctThreads>(tmp, alive, wsum);   // tmp[i] = base of node alive-1-i
         } else {
             int* tmp = cbase;
             const int ndiv = s_flag[1];
@@ -219,7 +225,7 @@ __device__ int octree_run(const uint32_t* kp, uint16_t* node, int n, int width, 
                 tmp[j] = (S.ccnt[4 * p] > 0) + (S.ccnt[4 * p + 1] > 0) + (S.ccnt[4 * p + 2] > 0) + (S.ccnt[4 * p + 3] > 0);
             }
             __syncthreads();
-            n_children = block_excl_scan(tmp, ndiv, wsum);    // tmp[j] = base of node order[j]
+            n_children = block_excl_scan<kOctThreads>(tmp, ndiv, wsum);    // tmp[j] = base of node order[j]
             // scatter to node-indexed form through a0 (flag) -> store base+1 in a0 for divided nodes
             __syncthreads();
             for (int j = tid; j < ndiv; j += kOctThreads) S.a0[S.order[j]] = tmp[j] + 1;
@@ -319,7 +325,7 @@ size_t octree_smem_bytes(int cap) {
                           3 * sizeof(int));
 }
 
-__global__ void __launch_bounds__(kOctThreads) octree_kernel(DevPtrs d, FrameLayout fl) {
+template <int kOctThreads> __global__ void __launch_bounds__(kOctThreads) octree_kernel(DevPtrs d, FrameLayout fl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_total;
     // grid = (frames, levels): CTAs are dispatched level 0 first for every frame, i.e. longest first (a level-0 CTA runs
@@ -371,35 +377,47 @@ __global__ void __launch_bounds__(kOctThreads) octree_kernel(DevPtrs d, FrameLay
     int count = 0;
     if (n > 0) {
         __threadfence_block();
-        count = octree_run(kp, node, n, g.w - 2 * kMinBorder, g.h - 2 * kMinBorder, g.n_feat, g.n_ini, g.h_x,
+        count = octree_run<kOctThreads>(kp, node, n, g.w - 2 * kMinBorder, g.h - 2 * kMinBorder, g.n_feat, g.n_ini, g.h_x,
                            d.sel + (size_t)frame * fl.kp_cap + g.kp_slot, nullptr, fl.node_cap, smem_raw, g.n_cols, g.w_cell,
                            g.h_cell);
     }
     if (tid == 0) d.level_count[(size_t)frame * kMaxLevels + level] = count;
 }
 
-int launch_octree(const DevPtrs& d, const FrameLayout& fl, int n_frames, cudaStream_t s) {
+template <int kOctThreads> static int launch_octree_t(const DevPtrs& d, const FrameLayout& fl, int n_frames, cudaStream_t s) {
     const size_t smem = octree_smem_bytes(fl.node_cap) > (size_t)kOctThreads * 4 ? octree_smem_bytes(fl.node_cap)
                                                                                  : (size_t)kOctThreads * 4;
-    // the opt-in is per device (and grows with the largest node capacity seen on it)
+    // the opt-in is per device and per instantiation (and grows with the largest node capacity seen on it)
     static thread_local size_t configured[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
     if (smem > 48 * 1024 && smem > configured[dev]) {
-        if (cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(octree_kernel<kOctThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -1;
         configured[dev] = smem;
     }
-    octree_kernel<<<dim3(n_frames, fl.nlevels), kOctThreads, smem, s>>>(d, fl);
+    octree_kernel<kOctThreads><<<dim3(n_frames, fl.nlevels), kOctThreads, smem, s>>>(d, fl);
     return 1;
 }
 
-__global__ void __launch_bounds__(kOctThreads) octree_single_kernel(const uint32_t* kp, int n, int width, int height,
+int launch_octree(const DevPtrs& d, const FrameLayout& fl, int n_frames, cudaStream_t s) {
+    // ORBCUDA_OCT_THREADS=128|256|512 forces one CTA size (A/B and soak switch; results are identical)
+    static const int forced = [] { const char* e = getenv("ORBCUDA_OCT_THREADS"); return e ? atoi(e) : 0; }();
+    const int threads = forced ? forced : (n_frames >= kOctBatchFrames ? kOctThreadsBatch : kOctThreadsLatency);
+    switch (threads) {
+        case 128: return launch_octree_t<128>(d, fl, n_frames, s);
+        case 256: return launch_octree_t<256>(d, fl, n_frames, s);
+        case 512: return launch_octree_t<512>(d, fl, n_frames, s);
+        default: return -1;
+    }
+}
+
+template <int kOctThreads> __global__ void __launch_bounds__(kOctThreads) octree_single_kernel(const uint32_t* kp, int n, int width, int height,
                                                                     int n_feat, int n_ini, float h_x, uint16_t* node,
                                                                     uint32_t* sel, int32_t* sel_idx, int32_t* count,
                                                                     int node_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int c = n > 0 ? octree_run(kp, node, n, width, height, n_feat, n_ini, h_x, sel, sel_idx, node_cap, smem_raw, 0, 1, 1) : 0;
+    const int c = n > 0 ? octree_run<kOctThreads>(kp, node, n, width, height, n_feat, n_ini, h_x, sel, sel_idx, node_cap, smem_raw, 0, 1, 1) : 0;
     if (threadIdx.x == 0) *count = c;
 }
 
@@ -409,10 +427,10 @@ int launch_octree_single(const uint32_t* d_cand, int n, int width, int height, i
     (void)kp_cap;
     const size_t smem = octree_smem_bytes(node_cap);
     if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(octree_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(octree_single_kernel<kOctThreadsLatency>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -1;
     }
-    octree_single_kernel<<<1, kOctThreads, smem, s>>>(d_cand, n, width, height, n_feat, n_ini, h_x, d_node, d_sel,
+    octree_single_kernel<kOctThreadsLatency><<<1, kOctThreadsLatency, smem, s>>>(d_cand, n, width, height, n_feat, n_ini, h_x, d_node, d_sel,
                                                       d_sel_idx, d_count, node_cap);
     return 1;
 }

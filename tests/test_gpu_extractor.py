@@ -181,6 +181,21 @@ def test_other_parameters(orb, oracle, synth, case):
     assert np.array_equal(desc, odesc)
 
 
+def test_large_batch_equals_single(orb, oracle, synth):
+    """Batches of >= 16 frames run the quadtree with the small (256-thread) CTA; single frames with the 512-thread one."""
+    rng = np.random.default_rng(5)
+    frames = [synth.frame(200 + s) for s in range(14)] + [synth.frame(300 + s, low_texture=True) for s in range(4)]
+    frames += [rng.integers(0, 256, (480, 640), dtype=np.uint8), np.full((480, 640), 128, np.uint8)]
+    frames = np.stack(frames)
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_width=640, max_height=480, max_batch=len(frames))
+    kps, desc, cnt = ex.extract_batch(frames)
+    oe = oracle.OracleExtractor(1000, trig_mode=1)
+    for i in range(len(frames)):
+        ok, od = oe.extract(frames[i])
+        assert cnt[i] == len(ok), i
+        assert kps[i, :cnt[i]].tobytes() == ok.tobytes() and np.array_equal(desc[i, :cnt[i]], od), i
+
+
 def test_stream_of_frames_kitti_shape(orb, oracle, synth):
     """BASELINE config 2 shape: 1241x376, nFeatures=2000 -- a short stream through one handle, batched."""
     frames = np.stack([synth.frame(100 + s, 1241, 376) for s in range(8)])
