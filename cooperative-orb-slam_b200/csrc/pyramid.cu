@@ -159,9 +159,10 @@ __device__ __forceinline__ uint32_t funnel16(uint32_t lo, uint32_t hi) { return 
 // horizontal 7-tap sums of 4 adjacent pixels x0..x0+3 from the words covering x0-4 .. x0+7;
 // returns (h(x0) | h(x0+2)<<16) in .x and (h(x0+1) | h(x0+3)<<16) in .y
 __device__ __forceinline__ uint2 blur_hsum4(uint32_t w0, uint32_t w1, uint32_t w2) {
-    const uint32_t A0 = w0 & 0x00ff00ffu, A1 = (w0 >> 8) & 0x00ff00ffu;
-    const uint32_t B0 = w1 & 0x00ff00ffu, B1 = (w1 >> 8) & 0x00ff00ffu;
-    const uint32_t C0 = w2 & 0x00ff00ffu, C1 = (w2 >> 8) & 0x00ff00ffu;
+    // bytes (0, 2) by mask, bytes (1, 3) by one PRMT (instead of shift + mask)
+    const uint32_t A0 = w0 & 0x00ff00ffu, A1 = __byte_perm(w0, 0u, 0x4341);
+    const uint32_t B0 = w1 & 0x00ff00ffu, B1 = __byte_perm(w1, 0u, 0x4341);
+    const uint32_t C0 = w2 & 0x00ff00ffu, C1 = __byte_perm(w2, 0u, 0x4341);
     // E[t] = (p(x0+t), p(x0+t+2)) for t=-3..4
     const uint32_t Em3 = A1, Em2 = funnel16(A0, B0), Em1 = funnel16(A1, B1), E0 = B0, E1 = B1,
                    E2 = funnel16(B0, C0), E3 = funnel16(B1, C1), E4 = C0;
@@ -204,24 +205,43 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
             w0[k] = a; w1[k] = b; w2[k] = c;
         }
     }
-    uint2 hs[ROWS + 6];   // hs[k] = horizontal sums of row (y0-3+k)
+    // Vertical pass with dp2a.  hs[k] = horizontal sums of row (y0-3+k), two columns per register; the sums of rows 2j
+    // and 2j+1 of ONE column are paired in a register (pc[c][j], one PRMT each), so the 7 taps of an output pixel are 4
+    // two-way dot products with byte weights -- even output rows r = 2m: pairs m..m+3 . (18,34) (48,56) (48,34) (18,0);
+    // odd rows r = 2m+1: pairs m..m+3 . (0,18) (34,48) (56,48) (34,18).  sum < 2^24, result = byte 2 of (sum + 32768),
+    // picked and packed by PRMT.
+    static_assert(ROWS % 2 == 0, "row pairs");
+    uint32_t pc[4][ROWS / 2 + 3];
 #pragma unroll
-    for (int k = 0; k < ROWS + 6; k++) hs[k] = blur_hsum4(w0[k], w1[k], w2[k]);
+    for (int j = 0; j < ROWS / 2 + 3; j++) {
+        const uint2 h0 = blur_hsum4(w0[2 * j], w1[2 * j], w2[2 * j]);
+        const uint2 h1 = blur_hsum4(w0[2 * j + 1], w1[2 * j + 1], w2[2 * j + 1]);
+        pc[0][j] = __byte_perm(h0.x, h1.x, 0x5410);
+        pc[2][j] = __byte_perm(h0.x, h1.x, 0x7632);
+        pc[1][j] = __byte_perm(h0.y, h1.y, 0x5410);
+        pc[3][j] = __byte_perm(h0.y, h1.y, 0x7632);
+    }
+    const uint32_t we0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // even rows: pairs m, m+1
+    const uint32_t we1 = 48u | (34u << 8) | (18u << 16) | (0u << 24);      //            pairs m+2, m+3
+    const uint32_t wo0 = 0u | (18u << 8) | (34u << 16) | (48u << 24);      // odd rows:  pairs m, m+1
+    const uint32_t wo1 = 56u | (48u << 8) | (34u << 16) | (18u << 24);     //            pairs m+2, m+3
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
+        const int m = r >> 1;
+        const uint32_t wA = (r & 1) ? wo0 : we0, wB = (r & 1) ? wo1 : we1;
         uint32_t o[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            auto H = [&](int k) -> uint32_t {
-                const uint32_t pr = (c & 1) ? hs[r + k].y : hs[r + k].x;
-                return (c & 2) ? (pr >> 16) : (pr & 0xffffu);
-            };
-            const uint32_t sum = 18u * (H(0) + H(6)) + 34u * (H(1) + H(5)) + 48u * (H(2) + H(4)) + 56u * H(3);
-            o[c] = (sum + 32768u) >> 16;
+            uint32_t sum;
+            asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(sum) : "r"(pc[c][m]), "r"(wA), "r"(32768u));
+            asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(sum) : "r"(pc[c][m + 1]), "r"(wA), "r"(sum));
+            asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(sum) : "r"(pc[c][m + 2]), "r"(wB), "r"(sum));
+            asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(sum) : "r"(pc[c][m + 3]), "r"(wB), "r"(sum));
+            o[c] = sum;
         }
         if (y0 + r < h)
             *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + r) * spitch + x0) =
-                o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+                __byte_perm(__byte_perm(o[0], o[1], 0x0062), __byte_perm(o[2], o[3], 0x0062), 0x5410);
     }
 }
 
