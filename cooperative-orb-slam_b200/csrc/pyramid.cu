@@ -154,21 +154,17 @@ constexpr int kBlurRows = 16;
 constexpr int kBlurEdgeRows = 4;   // edge strips gather bytes: keep those threads short
 
 
-__device__ __forceinline__ uint32_t funnel16(uint32_t lo, uint32_t hi) { return __funnelshift_r(lo, hi, 16); }
 
-// horizontal 7-tap sums of 4 adjacent pixels x0..x0+3 from the words covering x0-4 .. x0+7;
-// returns (h(x0) | h(x0+2)<<16) in .x and (h(x0+1) | h(x0+3)<<16) in .y
-__device__ __forceinline__ uint2 blur_hsum4(uint32_t w0, uint32_t w1, uint32_t w2) {
-    // bytes (0, 2) by mask, bytes (1, 3) by one PRMT (instead of shift + mask)
-    const uint32_t A0 = w0 & 0x00ff00ffu, A1 = __byte_perm(w0, 0u, 0x4341);
-    const uint32_t B0 = w1 & 0x00ff00ffu, B1 = __byte_perm(w1, 0u, 0x4341);
-    const uint32_t C0 = w2 & 0x00ff00ffu, C1 = __byte_perm(w2, 0u, 0x4341);
-    // E[t] = (p(x0+t), p(x0+t+2)) for t=-3..4
-    const uint32_t Em3 = A1, Em2 = funnel16(A0, B0), Em1 = funnel16(A1, B1), E0 = B0, E1 = B1,
-                   E2 = funnel16(B0, C0), E3 = funnel16(B1, C1), E4 = C0;
-    uint2 r;
-    r.x = 18u * (Em3 + E3) + 34u * (Em2 + E2) + 48u * (Em1 + E1) + 56u * E0;
-    r.y = 18u * (Em2 + E4) + 34u * (Em1 + E3) + 48u * (E0 + E2) + 56u * E1;
+// horizontal 7-tap sums of 4 adjacent pixels x0..x0+3 from the words covering x0-4 .. x0+7 (w0 = bytes x0-4..x0-1,
+// w1 = x0..x0+3, w2 = x0+4..x0+7): the window of pixel i is the 8 bytes starting i+1 bytes into (w0, w1), i.e. two
+// funnel shifts, and the 7 taps are two dp4a with byte weights (18,34,48,56) (48,34,18,0).  Sums <= 255*256 fit 16 bits.
+__device__ __forceinline__ uint4 blur_hsum4(uint32_t w0, uint32_t w1, uint32_t w2) {
+    const uint32_t k0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), k1 = 48u | (34u << 8) | (18u << 16);
+    uint4 r;
+    r.x = __dp4a(__funnelshift_r(w1, w2, 8), k1, __dp4a(__funnelshift_r(w0, w1, 8), k0, 0u));
+    r.y = __dp4a(__funnelshift_r(w1, w2, 16), k1, __dp4a(__funnelshift_r(w0, w1, 16), k0, 0u));
+    r.z = __dp4a(__funnelshift_r(w1, w2, 24), k1, __dp4a(__funnelshift_r(w0, w1, 24), k0, 0u));
+    r.w = __dp4a(w2, k1, __dp4a(w1, k0, 0u));
     return r;
 }
 
@@ -205,7 +201,7 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
             w0[k] = a; w1[k] = b; w2[k] = c;
         }
     }
-    // Vertical pass with dp2a.  hs[k] = horizontal sums of row (y0-3+k), two columns per register; the sums of rows 2j
+    // Vertical pass with dp2a.  the horizontal sums of rows (y0-3+k) come one pixel per register; the sums of rows 2j
     // and 2j+1 of ONE column are paired in a register (pc[c][j], one PRMT each), so the 7 taps of an output pixel are 4
     // two-way dot products with byte weights -- even output rows r = 2m: pairs m..m+3 . (18,34) (48,56) (48,34) (18,0);
     // odd rows r = 2m+1: pairs m..m+3 . (0,18) (34,48) (56,48) (34,18).  sum < 2^24, result = byte 2 of (sum + 32768),
@@ -214,12 +210,12 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
     uint32_t pc[4][ROWS / 2 + 3];
 #pragma unroll
     for (int j = 0; j < ROWS / 2 + 3; j++) {
-        const uint2 h0 = blur_hsum4(w0[2 * j], w1[2 * j], w2[2 * j]);
-        const uint2 h1 = blur_hsum4(w0[2 * j + 1], w1[2 * j + 1], w2[2 * j + 1]);
+        const uint4 h0 = blur_hsum4(w0[2 * j], w1[2 * j], w2[2 * j]);
+        const uint4 h1 = blur_hsum4(w0[2 * j + 1], w1[2 * j + 1], w2[2 * j + 1]);
         pc[0][j] = __byte_perm(h0.x, h1.x, 0x5410);
-        pc[2][j] = __byte_perm(h0.x, h1.x, 0x7632);
         pc[1][j] = __byte_perm(h0.y, h1.y, 0x5410);
-        pc[3][j] = __byte_perm(h0.y, h1.y, 0x7632);
+        pc[2][j] = __byte_perm(h0.z, h1.z, 0x5410);
+        pc[3][j] = __byte_perm(h0.w, h1.w, 0x5410);
     }
     const uint32_t we0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // even rows: pairs m, m+1
     const uint32_t we1 = 48u | (34u << 8) | (18u << 16) | (0u << 24);      //            pairs m+2, m+3
