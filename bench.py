@@ -384,7 +384,7 @@ def run_ours(args):
     peak, peak_src = _peaks()
     dkey = "pyramid" if dominant.startswith("pyramid") else dominant
     ach = BYTES[dkey] * B / (kern[dkey] * 1e-3) / 1e9
-    bound_note = {"fast_score": "ALU-pipe bound (exact cornerScore of every pixel: ~47 thread-instr/px, ncu alu pipe 84 %), not HBM",
+    bound_note = {"fast_score": "ALU-pipe bound (exact cornerScore of every pixel; part of the min/max moved to the FMA pipe: ncu alu pipe 68 %, fma 21 %, issue 60 %), not HBM",
                   "pyramid": "instruction bound (fixed-point taps, byte gathers from the staged tile), 8 dependent launches",
                   "blur": "issue bound", "cell_nms": "issue bound"}[dkey]
     # the ncu capture under profiles/ is a launch over 64 frames: scale its DRAM bytes to this run's frames per launch
