@@ -480,14 +480,14 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_p); int* d_nm = (int*)cx.dalloc(4);
     if (!d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm) return ORB_ERR_CUDA;
     const bool staged = n_f <= kStagedMaxFeatures;
-    static bool configured[64] = {false};
-    if (first_use_on_device(configured)) {
-        const int big = kFrameMaxFeatures * 5 + 16, small = kStagedMaxFeatures * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16;
-        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-        ORB_CUDA_TRY(cudaFuncSetAttribute(window_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    }
+    static DeviceOnce once_configured;
+    if (!once_configured.run([&] {
+            const int big = kFrameMaxFeatures * 5 + 16, small = kStagedMaxFeatures * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16;
+            return cuda_ok(cudaFuncSetAttribute(window_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big), "cudaFuncSetAttribute") &&
+                   cuda_ok(cudaFuncSetAttribute(window_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big), "cudaFuncSetAttribute") &&
+                   cuda_ok(cudaFuncSetAttribute(window_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small), "cudaFuncSetAttribute") &&
+                   cuda_ok(cudaFuncSetAttribute(window_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small), "cudaFuncSetAttribute");
+        })) return ORB_ERR_CUDA;
     const size_t smem = staged ? (size_t)n_f * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16 : (size_t)n_f * 5 + 16;
     const GridParams g = make_grid_params(bounds);
 #define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_nm)
@@ -598,10 +598,10 @@ int orbf_assign_grid(const orb_keypoint_t* kps_un, int n, const float* bounds, i
     int* d_idx = (int*)cx.dalloc(ib);
     if ((n && !d_k) || !d_ptr || !d_idx) return ORB_ERR_CUDA;
     const size_t smem = (size_t)(kGridCells + 1) * 4 + (size_t)n * 2 + 16;
-    static bool configured[64] = {false};
-    if (first_use_on_device(configured)) {
-        ORB_CUDA_TRY(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16));
-    }
+    static DeviceOnce once_configured;
+    if (!once_configured.run([&] {
+            return cuda_ok(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16), "cudaFuncSetAttribute");
+        })) return ORB_ERR_CUDA;
     grid_kernel<<<1, 1024, smem, cx.stream>>>(d_k, n, nullptr, 0, make_grid_params(bounds), d_ptr, d_idx);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(cell_ptr, d_ptr, pb)) return ORB_ERR_CUDA;
@@ -621,10 +621,10 @@ int orbf_build_frames_device(const void* d_kps, const int32_t* d_counts, int n_f
     }
     if (n_frames == 0) return ORB_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    static bool configured[64] = {false};
-    if (first_use_on_device(configured)) {
-        ORB_CUDA_TRY(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16));
-    }
+    static DeviceOnce once_configured;
+    if (!once_configured.run([&] {
+            return cuda_ok(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16), "cudaFuncSetAttribute");
+        })) return ORB_ERR_CUDA;
     undistort_batch_kernel<<<dim3((cap + 255) / 256, n_frames), 256, 0, s>>>((const orb_keypoint_t*)d_kps, d_counts, cap, p, (orb_keypoint_t*)d_kps_un);
     grid_kernel<<<n_frames, 1024, (size_t)(kGridCells + 1) * 4 + (size_t)cap * 2 + 16, s>>>((const orb_keypoint_t*)d_kps_un, 0, d_counts, cap,
                                                                                          make_grid_params(bounds), d_cell_ptr, d_cell_idx);
@@ -832,10 +832,10 @@ int orbm_search_for_initialization(const orb_keypoint_t* kps1_un, const uint8_t*
     int* d_m12 = (int*)cx.dalloc((size_t)n1 * 4); int* d_em = (int*)cx.dalloc((size_t)n1 * 4);
     uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n1); int* d_nm = (int*)cx.dalloc(4);
     if (!d_k1 || !d_d1 || !d_k2 || !d_d2 || !d_cp || !d_ci || !d_xy || !d_md || !d_ow || !d_m12 || !d_em || !d_res || !d_nm) return ORB_ERR_CUDA;
-    static bool configured[64] = {false};
-    if (first_use_on_device(configured)) {
-        ORB_CUDA_TRY(cudaFuncSetAttribute(init_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 4 + 16));
-    }
+    static DeviceOnce once_configured;
+    if (!once_configured.run([&] {
+            return cuda_ok(cudaFuncSetAttribute(init_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 4 + 16), "cudaFuncSetAttribute");
+        })) return ORB_ERR_CUDA;
     init_search_kernel<<<1, 1024, (size_t)n2 * 4 + 16, cx.stream>>>(d_k1, d_d1, n1, d_k2, d_d2, n2, d_cp, d_ci, make_grid_params(bounds), d_xy,
                                                                     (float)window_size, nnratio, th_low, d_md, d_ow, d_m12, d_em, d_res, d_nm);
     ORB_CUDA_TRY(cudaGetLastError());

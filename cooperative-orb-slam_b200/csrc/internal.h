@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <mutex>
 
 #include "orbcuda.h"
 
@@ -147,14 +148,24 @@ struct MatchCtx {
 };
 MatchCtx& match_ctx();
 
-// Function attributes (dynamic shared memory opt-in) are per device: true the first time the current device is seen.
-inline bool first_use_on_device(bool (&seen)[64]) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-    if (seen[dev]) return false;
-    seen[dev] = true;
-    return true;
-}
+// Function attributes (dynamic shared memory opt-in, memory-pool thresholds) are per device.  The matcher entry points
+// are called concurrently from the reference's Tracking / LocalMapping / LoopClosing threads, so the per-device
+// configuration runs under a lock and a device is marked configured only AFTER its configuration succeeded: a second
+// thread arriving during the first call waits instead of launching with the attribute still unset.
+struct DeviceOnce {
+    std::mutex mu;
+    bool done[64] = {};
+    // runs f() (returns true on success) once per device; returns false if f failed (it is retried on the next call)
+    template <class F> bool run(F&& f) {
+        int dev = 0;
+        const bool indexed = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64;
+        std::lock_guard<std::mutex> lock(mu);
+        if (indexed && done[dev]) return true;
+        if (!f()) return false;
+        if (indexed) done[dev] = true;
+        return true;
+    }
+};
 
 void set_error(const char* fmt, ...);
 bool cuda_ok(cudaError_t e, const char* what);

@@ -1216,15 +1216,15 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     // hands its memory back to the OS at every synchronisation, and the next call pays a map/unmap (0.2 ms typically,
     // several ms now and then): keep the few MB cached instead.  Once per device.
     {
-        static bool pool_ready[64] = {false};
-        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+        static DeviceOnce pool_once;
+        pool_once.run([&] {
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
                 unsigned long long keep = ~0ull;
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
-            pool_ready[dev] = true;
-        }
+            return true;
+        });
     }
     const int qper = variant >= 3 ? kTcQ : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
     const int tile = variant >= 3 ? kTcN : (variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile));
@@ -1247,40 +1247,32 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     if (cudaMallocAsync((void**)&partial, need, s) != cudaSuccess) return -1;
     if (variant == 1) {
         const size_t smem = (size_t)kMmaTile * 256 + kMmaTile * sizeof(int);
-        static bool configured[64] = {false};
-        if (first_use_on_device(configured)) {
-            if (cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        }
+        static DeviceOnce once_configured;
+        if (!once_configured.run([&] { return cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) { cudaFreeAsync(partial, s); return -1; }
         knn2_mma_kernel<<<dim3(qblocks, splits), kMmaThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);
     } else if (variant == 3) {
         const size_t smem = (size_t)kTcQ * 256 + kTcBStages * (size_t)kTcN * 256 + 1024;
-        static bool configured3[64] = {false};
-        if (first_use_on_device(configured3)) {
-            if (cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        }
+        static DeviceOnce once_configured3;
+        if (!once_configured3.run([&] { return cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) { cudaFreeAsync(partial, s); return -1; }
         int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
-        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
+        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) { cudaFreeAsync(partial, s); return -1; }    // "no bound yet"
         knn2_tc_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                       index_base, partial, shared_d2);
     } else if (variant == 5) {
         const size_t smem = (size_t)kTcQ * 256 + kPairBStages * (size_t)kPairHalfN * 256 + 1024;
-        static bool configured5[64] = {false};
-        if (first_use_on_device(configured5)) {
-            if (cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        }
+        static DeviceOnce once_configured5;
+        if (!once_configured5.run([&] { return cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) { cudaFreeAsync(partial, s); return -1; }
         int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
-        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
+        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) { cudaFreeAsync(partial, s); return -1; }    // "no bound yet"
         knn2_pair_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                         index_base, partial, shared_d2);
     } else if (variant == 4) {
         const size_t smem = kTcBStages * (size_t)kTcN * 256 + 1024;
-        static bool configured4[64] = {false};
-        if (first_use_on_device(configured4)) {
-            if (cudaFuncSetAttribute(knn2_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        }
+        static DeviceOnce once_configured4;
+        if (!once_configured4.run([&] { return cudaFuncSetAttribute(knn2_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) { cudaFreeAsync(partial, s); return -1; }
         int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
-        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) return -1;     // "no bound yet"
+        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) { cudaFreeAsync(partial, s); return -1; }    // "no bound yet"
         knn2_ts_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                       index_base, partial, shared_d2);
     } else if (variant == 2) {
