@@ -2,18 +2,23 @@
 """bench.py -- headline benchmark of the ORB front-end hot path (BASELINE.json metric:
 "ORB extract frames/s @640x480/1000kp; Hamming 2-NN Gcmp/s; at 1-8 B200").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs tum,kitti,euroc]
 
-A step = one batch of B synthetic 640x480 frames (TUM1.yaml extractor: 1000 features, 8 levels, 1.2,
-FAST 20/7) through the whole extraction path (pyramid, FAST, quadtree, orientation, blur, rBRIEF).
+Headline (BASELINE config 1, every N): a step = `--batches-per-step` batches of `--batch` synthetic 640x480 frames
+(TUM1.yaml extractor: 1000 features, 8 levels, 1.2, FAST 20/7) through the whole extraction path (pyramid, FAST,
+quadtree, orientation, blur, rBRIEF), dealt round-robin to `--streams` extractor handles (agent streams) per GPU.
   value : frames/s with the frames already resident in HBM (orbx_extract_batch_device), CUDA events on the
           extractor streams, max over ranks.
   e2e   : frames/s through orbx_extract_batch_async/orbx_wait with HOST (pinned) buffers: H2D of every frame
-          and D2H of every key point / descriptor inside the timed region.
-  roofline     : the dominant kernel's algorithmic bytes / CUDA-event duration vs the measured HBM peak.
-  cpu_baseline : the reference's own ORBextractor.cc (oracle/_ref, compiled over oracle/cvshim) on the host cores.
-  matching     : brute-force 2-NN Hamming, 2000 queries x 1M map descriptors (map sharded over the ranks,
-                 per-rank records all-gathered over NCCL and merged), Gcmp/s.
+          and D2H of every key point / descriptor inside the timed region; copy_ceiling_frames_s = the same copies
+          with no kernels in between.
+  roofline     : the dominant pixel kernel's algorithmic bytes / CUDA-event duration vs the measured HBM peak.
+  cpu_baseline : the reference's own ORBextractor.cc (oracle/_ref, compiled over oracle/cvshim) on the host cores, with
+                 cv2's own primitives timed beside the shim's (per_stage, adjusted_value).
+  matching     : brute-force 2-NN Hamming, 2000 queries x 1M map descriptors (BASELINE config 4; map sharded over the
+                 ranks, per-rank records exchanged and merged), Gcmp/s, burst and sustained, checked against the oracle.
+  configs      : (N = 1) BASELINE configs 2 and 3 as their own objects: the KITTI-shape 1241x376 / 2000-feature
+                 1000-frame stream and the EuRoC-shape 752x480 stereo pairs (two extractors + ComputeStereoMatches).
 N > 1: one process per GPU (torchrun), replicas for extraction (weak scaling), sharded map for matching.
 --impl reference: times the reference CPU path (rank 0 only) and prints the same JSON shape.
 """
@@ -31,10 +36,31 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, NFEAT = 640, 480, 1000
 METRIC = "ORB extract frames/s @640x480/1000kp"
-# algorithmic bytes per 640x480 frame
-BYTES = {"pyramid": 2391758, "blur": 1901064, "fast_score": 950532, "cell_nms": 950532}
+# algorithmic bytes per frame of the pixel stages
+CONFIGS = {
+    "tum": {"w": 640, "h": 480, "nfeat": 1000, "stereo": False,
+            "workload": "640x480 gray frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7 (TUM1.yaml)",
+            "bytes": {"pyramid": 2391758, "blur": 1901064, "fast_score": 950532, "cell_nms": 950532}},
+    "kitti": {"w": 1241, "h": 376, "nfeat": 2000, "stereo": False,
+              "workload": "KITTI-shape 1241x376 monocular, nFeatures=2000 (the 2x initialisation extractor, Tracking.cc:125), "
+                          "8 levels, scale 1.2, FAST 20/7, 1000-frame synthetic stream",
+              "bytes": {"pyramid": 3612942, "blur": 2888194, "fast_score": 1444097, "cell_nms": 1444097}},
+    "euroc": {"w": 752, "h": 480, "nfeat": 1200, "stereo": True,
+              "workload": "EuRoC-shape stereo 752x480 pairs, 1200 features per image, two extractors per pair (Frame.cc:80-83) + "
+                          "ComputeStereoMatches (Frame.cc:471-645)",
+              "bytes": {"pyramid": 2794680, "blur": 2234734, "fast_score": 1117367, "cell_nms": 1117367}},
+}
+NCU_SUMMARY = "r2_ncu_full_summary.csv"      # committed `ncu --set full` summary the traffic / pipe figures come from
+NCU_SUMMARY_FALLBACK = "r1_ncu_full_final_summary.csv"
+NCU_FRAMES = 64                               # frames per launch in that capture (tools/profile_step.py)
+
+
+def headline_config():
+    """`config` of the JSON line -- identical in both arms."""
+    return {"workload": CONFIGS["tum"]["workload"],
+            "l2_policy": "GPU arm: inputs + intermediates of one batch (717 MB at 128 frames) exceed the 126 MB L2 and 4 distinct "
+                         "batches are cycled; CPU arm: 16 distinct frames cycled per thread"}
 
 
 def _peaks():
@@ -45,12 +71,37 @@ def _peaks():
         return 6650.0, "fallback"
 
 
-def _ncu_traffic(csv_name, kernel_substr):
+def _bf16_peak(sustained=False):
+    """Dense bf16 TFLOP/s: MEASURED_PEAKS.json (burst or sustained), else the profiling guide's fallback figures."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+            return float(d["bf16_tflops_sustained" if sustained else "bf16_tflops"]), "measured"
+    except Exception:
+        return (1400.0 if sustained else 1590.0), "fallback"
+
+
+def _ncu_rows():
+    import csv
+    for name in (NCU_SUMMARY, NCU_SUMMARY_FALLBACK):
+        try:
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", name))))
+            if len(rows) > 2:
+                return name, rows
+        except Exception:
+            pass
+    return None, None
+
+
+def _ncu_traffic(kernel_substr, csv_name=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` summary under
-    profiles/ (a static capture of the same kernel and workload; None if the file or the kernel is missing)."""
+    profiles/ (a static capture of the same kernel; None if the file or the kernel is missing)."""
     import csv
     try:
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", csv_name))))
+        if csv_name:
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", csv_name))))
+        else:
+            _, rows = _ncu_rows()
         head, units = rows[0], rows[1]
         ir, iw = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -62,11 +113,9 @@ def _ncu_traffic(csv_name, kernel_substr):
     return None
 
 
-def _ncu_metric(csv_name, kernel_substr, metric):
-    """One metric of one kernel from a committed ncu summary under profiles/ (None if missing)."""
-    import csv
+def _ncu_metric(kernel_substr, metric):
     try:
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", csv_name))))
+        _, rows = _ncu_rows()
         i = rows[0].index(metric)
         for r in rows[2:]:
             if kernel_substr in r[0]:
@@ -74,15 +123,6 @@ def _ncu_metric(csv_name, kernel_substr, metric):
     except Exception:
         pass
     return None
-
-
-def _bf16_peak():
-    """Dense bf16 TFLOP/s: MEASURED_PEAKS.json (burst), else the profiling guide's nominal figure."""
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["bf16_tflops"]), "measured"
-    except Exception:
-        return 2250.0, "fallback"
 
 
 class ClockSampler:
@@ -115,20 +155,30 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
             except ValueError:
                 continue
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_mhz_min": min(sm) if sm else None, "power_w_max": max(pw) if pw else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _note(msg):
+    """progress marker on stderr (the JSON line is the only thing on stdout)"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench %6.1fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
 
 
 def _dist_env():
@@ -140,24 +190,41 @@ def _dist_env():
 # ---------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation (oracle/_ref) on all host cores
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_fps(frames, seconds_budget, threads=None):
+def _oracle_lib():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
+    return oracle_lib
+
+
+def cpu_reference_fps(frames, seconds_budget, nfeat=1000, threads=None, stereo=None):
+    """All-core run of the reference extractor (one instance per thread) over `frames` (cycled) for about
+    seconds_budget.  stereo = (right_frames, mbf, mb): each unit is a stereo pair -- left and right extraction plus the
+    oracle's ComputeStereoMatches -- and the rate returned is pairs/s.  Returns (rate, kind, threads, n, seconds)."""
+    oracle_lib = _oracle_lib()
     kind = "reference" if oracle_lib.ref_available() else "port"
     threads = threads or (os.cpu_count() or 1)
-    mk = (lambda: oracle_lib.RefExtractor(NFEAT)) if kind == "reference" else (lambda: oracle_lib.OracleExtractor(NFEAT))
+    mk = (lambda: oracle_lib.RefExtractor(nfeat)) if kind == "reference" else (lambda: oracle_lib.OracleExtractor(nfeat))
     exts = [mk() for _ in range(threads)]
+    exts_r = [mk() for _ in range(threads)] if stereo else None
     done = [0] * threads
     stop_at = [0.0]
+    cap = nfeat + 200
+
+    def unit(t, i):
+        kl, dl = exts[t].extract(frames[i % len(frames)], cap=cap)   # ctypes releases the GIL inside the call
+        if stereo:
+            right, mbf, mb = stereo
+            kr, dr = exts_r[t].extract(right[i % len(right)], cap=cap)
+            oracle_lib.stereo_matches(kl, dl, kr, dr, exts[t], exts_r[t], mbf, mb)
 
     def work(t):
         i = t
         while time.perf_counter() < stop_at[0]:
-            exts[t].extract(frames[i % len(frames)], cap=1100)   # ctypes releases the GIL inside the call
+            unit(t, i)
             done[t] += 1
             i += threads
 
-    exts[0].extract(frames[0], cap=1100)   # warm
+    unit(0, 0)   # warm
     t0 = time.perf_counter()
     stop_at[0] = t0 + seconds_budget
     th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
@@ -170,37 +237,139 @@ def cpu_reference_fps(frames, seconds_budget, threads=None):
     return n / dt, kind, threads, n, dt
 
 
+def cpu_stage_comparison(frames, nfeat, nlevels=8, scale=1.2, reps=3):
+    """the shim primitives under the reference extractor are scalar/portable C++; time cv2 4.13's own
+    resize / copyMakeBorder / GaussianBlur / FAST on the same level shapes beside them (one thread each) and report the
+    faster per stage: adjusted_value is what the reference would reach with stock OpenCV primitives under its own code."""
+    import ctypes as C
+    import cv2
+    oracle_lib = _oracle_lib()
+    if not oracle_lib.ref_available():
+        return None
+    L = oracle_lib.ref_lib(False)
+    if not hasattr(L, "orbref_stage_times"):
+        return None
+    ext = oracle_lib.RefExtractor(nfeat)
+    acc = (C.c_double * 4)()
+    ext.extract(frames[0], cap=nfeat + 200)
+    L.orbref_stage_times(acc, 1)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(reps):
+        for f in frames:
+            ext.extract(f, cap=nfeat + 200); n += 1
+    total_ms = (time.perf_counter() - t0) / n * 1e3
+    L.orbref_stage_times(acc, 1)
+    shim = {"resize": acc[0] / n * 1e3, "copyMakeBorder": acc[1] / n * 1e3, "GaussianBlur": acc[2] / n * 1e3, "FAST": acc[3] / n * 1e3}
+    prev_threads = cv2.getNumThreads()
+    cv2.setNumThreads(1)
+    try:
+        h0, w0 = frames[0].shape
+        sf = [1.0]
+        for _ in range(1, nlevels):
+            sf.append(float(np.float32(sf[-1] * float(np.float32(scale)))))
+        sizes = [(int(np.rint(np.float32(w0) * np.float32(1.0) / np.float32(s))), int(np.rint(np.float32(h0) * np.float32(1.0) / np.float32(s)))) for s in sf]
+        det20 = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True)
+        det7 = cv2.FastFeatureDetector_create(threshold=7, nonmaxSuppression=True)
+
+        def cell_rois(lv):      # the reference's cell grid, R21 ORBextractor.cc:773-807
+            hh, ww = lv.shape
+            minb, maxbx, maxby = 16, ww - 16, hh - 16
+            ncols, nrows = int((maxbx - minb) / 30.0), int((maxby - minb) / 30.0)
+            wc, hc = int(np.ceil((maxbx - minb) / ncols)), int(np.ceil((maxby - minb) / nrows))
+            out = []
+            for i in range(nrows):
+                iy = minb + i * hc
+                if iy >= maxby - 3:
+                    continue
+                my = min(iy + hc + 6, maxby)
+                for j in range(ncols):
+                    ix = minb + j * wc
+                    if ix >= maxbx - 6:
+                        continue
+                    out.append(lv[iy:my, ix:min(ix + wc + 6, maxbx)])
+            return out
+
+        cvt = {"resize": 0.0, "copyMakeBorder": 0.0, "GaussianBlur": 0.0, "FAST": 0.0}
+        m = 0
+        ncalls = 0
+        for _ in range(reps):
+            for f in frames:
+                levels = [f]
+                t = time.perf_counter()
+                for (w, h) in sizes[1:]:
+                    levels.append(cv2.resize(levels[-1], (w, h), interpolation=cv2.INTER_LINEAR))
+                cvt["resize"] += time.perf_counter() - t
+                t = time.perf_counter()
+                for lv in levels:
+                    cv2.copyMakeBorder(lv, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+                cvt["copyMakeBorder"] += time.perf_counter() - t
+                t = time.perf_counter()
+                for lv in levels:
+                    cv2.GaussianBlur(lv, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+                cvt["GaussianBlur"] += time.perf_counter() - t
+                rois = [r for lv in levels for r in cell_rois(lv)]
+                t = time.perf_counter()
+                for r in rois:               # exactly the reference's calls: iniThFAST, then minThFAST on an empty cell
+                    ncalls += 1
+                    if not det20.detect(r):
+                        det7.detect(r); ncalls += 1
+                cvt["FAST"] += time.perf_counter() - t
+                m += 1
+        # the Python binding's per-call cost (argument conversion, result list) is not the reference's: measure it on a
+        # flat cell (no corner, nothing to compute beyond the row setup) and take it out
+        flat = np.full((36, 36), 128, np.uint8)
+        t = time.perf_counter()
+        for _ in range(2000):
+            det20.detect(flat)
+        per_call = (time.perf_counter() - t) / 2000
+        fast_calls_per_frame = ncalls / m
+        cvt["FAST"] = max(cvt["FAST"] - per_call * ncalls, 0.0)
+        cvt = {k: v / m * 1e3 for k, v in cvt.items()}
+    finally:
+        cv2.setNumThreads(prev_threads)
+    faster = {k: min(shim[k], cvt[k]) for k in shim}
+    adjusted_ms = total_ms - sum(shim[k] - faster[k] for k in shim)
+    return {"ms_per_frame_1thread": total_ms, "shim_ms": {k: round(v, 3) for k, v in shim.items()},
+            "cv2_ms": {k: round(v, 3) for k, v in cvt.items()}, "faster_ms": {k: round(v, 3) for k, v in faster.items()},
+            "adjusted_ms_per_frame_1thread": adjusted_ms, "speedup_if_cv2_primitives": total_ms / adjusted_ms,
+            "cv2_fast_calls_per_frame": fast_calls_per_frame, "cv2_python_call_overhead_us": per_call * 1e6,
+            "note": "one thread; cv2 %s primitives timed on the same level shapes; cv2 FAST = the reference's own per-cell calls "
+                    "(threshold 20, then 7 on empty cells) through the Python binding, minus the binding's per-call cost measured on a "
+                    "flat cell; the rest of the extractor (quadtree, orientation, descriptors) is the reference's own code in both "
+                    "columns" % cv2.__version__}
+
+
 def run_reference(args):
     rank, world, local = _dist_env()
     if rank != 0:
         return
     synth = importlib.import_module("cooperative-orb-slam_b200.synth")
-    frames = [synth.frame(s, W, H) for s in range(16)]
+    cfg = CONFIGS["tum"]
+    frames = [synth.frame(s, cfg["w"], cfg["h"]) for s in range(16)]
     # each "step" is a bounded sample of all-core extraction, sized so that the whole run stays near one minute
     per_step = min(2.0, 60.0 / max(args.steps, 1))
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_fps(frames, min(0.5, 5.0 / max(args.warmup, 1)))
+        cpu_reference_fps(frames, min(0.5, 5.0 / max(args.warmup, 1)), cfg["nfeat"])
     tot_n = 0; tot_t = 0.0; kind = "port"; threads = 1
     for _ in range(args.steps):
-        fps, kind, threads, n, dt = cpu_reference_fps(frames, per_step)
+        fps, kind, threads, n, dt = cpu_reference_fps(frames, per_step, cfg["nfeat"])
         tot_n += n; tot_t += dt
     fps = tot_n / tot_t
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "640x480 gray frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7 (TUM1.yaml)",
-                       "sample": "%d frames in %.1f s on %d host threads" % (tot_n, tot_t, threads)},
+            "config": headline_config(),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                             "sample": "%d frames (16 distinct seeds) over %d steps of %.1f s" % (tot_n, args.steps, per_step)},
+                             "sample": "%d frames (16 distinct seeds) over %d steps of %.1f s on %d host threads" % (tot_n, args.steps, per_step, threads)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "timed_region_s": tot_t}
     print(json.dumps(line), flush=True)
 
 
 def _bind_to_gpu_numa_node(torch, local):
-    """Pin this rank's threads (and so its first-touched pinned staging buffers) to the CPUs next to its GPU.  With 8
-    ranks the end-to-end path moves ~35 GB/s of frames per GPU from host memory; without the binding most of it crosses
-    the socket interconnect.  Best effort: returns the node or None."""
+    """Pin this rank's threads (and so its first-touched pinned staging buffers) to the CPUs next to its GPU.  Best
+    effort: returns the node or None (virtualised boxes report no NUMA topology)."""
     try:
         p = torch.cuda.get_device_properties(local)
         bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
@@ -222,6 +391,577 @@ def _bind_to_gpu_numa_node(torch, local):
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
+class Dist:
+    """barrier / max-over-ranks helpers (no-ops at world 1)."""
+
+    def __init__(self, torch, dist, world, dev):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return float(t.item())
+
+
+def _pinned_tensor(orb, torch, shape, np_dtype, keep):
+    """torch view of page-locked memory from the library's own allocator (orb_host_alloc).  torch's caching host
+    allocator records an event on every stream a block was used on when the tensor dies -- on an extractor handle's
+    stream that may already be destroyed."""
+    pa = orb.PinnedArray(shape, np_dtype)
+    keep.append(pa)
+    return torch.from_numpy(pa.array)
+
+
+def copy_ceiling(orb, torch, dev, D, h2d_bytes, d2h_bytes, n_streams, n_batches):
+    """The e2e path's copies alone: n_batches x (H2D of h2d_bytes from pinned memory + D2H of d2h_bytes into pinned
+    memory) dealt over n_streams streams, no kernels.  Returns (batches/s, GB/s H2D, GB/s D2H), max over ranks."""
+    keep = []
+    hin = [_pinned_tensor(orb, torch, (h2d_bytes,), np.uint8, keep) for _ in range(2)]
+    hout = [_pinned_tensor(orb, torch, (d2h_bytes,), np.uint8, keep) for _ in range(n_streams)]
+    din = [torch.empty(h2d_bytes, dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+    dout = [torch.empty(d2h_bytes, dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+
+    def run(n):
+        for i in range(n):
+            s = i % n_streams
+            with torch.cuda.stream(streams[s]):
+                din[s].copy_(hin[i % 2], non_blocking=True)
+                hout[s].copy_(dout[s], non_blocking=True)
+
+    run(2 * n_streams)
+    D.barrier()
+    t0 = time.perf_counter()
+    run(n_batches)
+    torch.cuda.synchronize()
+    dt = D.max(time.perf_counter() - t0)
+    D.barrier()
+    del hin, hout
+    for pa in keep:
+        pa.free()
+    return n_batches / dt, n_batches * h2d_bytes / dt / 1e9, n_batches * d2h_bytes / dt / 1e9
+
+
+def bench_extraction(orb, synth, torch, D, cfg, args, rank, world, local, B, n_batches_timed, n_batches_warm, want_e2e=True,
+                     tight_host_stride=False):
+    """Extraction throughput of one monocular configuration: device-resident (CUDA events on the extractor streams) and
+    end to end from pinned host memory.  n_batches_timed batches of B frames are dealt round-robin to args.streams
+    handles.  Returns a dict (rates are whole-job: x world)."""
+    dev = torch.device("cuda", local)
+    W, H, NFEAT = cfg["w"], cfg["h"], cfg["nfeat"]
+    n_streams = args.streams
+    pool = 4   # distinct batches cycled through (working set per batch >> L2)
+    n_distinct = min(pool * B, 64)
+    host = np.stack([synth.frame(int(s) + 1000 * rank, W, H) for s in range(n_distinct)])
+    reps = (pool * B + n_distinct - 1) // n_distinct
+    host = np.concatenate([host] * reps)[:pool * B].reshape(pool, B, H, W)     # content repeats every 64 frames; distinct memory
+    exts = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local, max_width=W, max_height=H, max_batch=B) for _ in range(n_streams)]
+    cap = exts[0].max_keypoints(W, H)
+    streams = [torch.cuda.ExternalStream(e.stream(), device=dev) for e in exts]
+    pitch = (W + 15) // 16 * 16                                               # the handle's own input layout
+    d_frames = torch.zeros((pool, B, H, pitch), dtype=torch.uint8, device=dev)
+    d_frames[:, :, :, :W] = torch.from_numpy(host).to(dev)
+    d_kps = [torch.empty((B, cap, 7), dtype=torch.int32, device=dev) for _ in range(n_streams)]
+    d_desc = [torch.empty((B, cap, 32), dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+    d_cnt = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(n_streams)]
+
+    def dev_batch(i):
+        s = i % n_streams
+        fr = d_frames[i % pool]
+        exts[s].extract_batch_device(fr.data_ptr(), B, W, H, pitch, pitch * H, d_kps[s].data_ptr(), d_desc[s].data_ptr(), cap,
+                                     d_cnt[s].data_ptr())
+
+    for i in range(max(n_batches_warm, n_streams)):
+        dev_batch(i)
+    D.barrier()
+    l0 = sum(e.launch_count() for e in exts)
+    sampler = ClockSampler(local) if rank == 0 else None
+    start = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_streams)]
+    start.record(streams[0])
+    for s in range(1, n_streams):
+        streams[s].wait_event(start)
+    for i in range(n_batches_timed):
+        dev_batch(i)
+    for s in range(n_streams):
+        ends[s].record(streams[s])
+    D.barrier()
+    dev_ms = max(start.elapsed_time(e) for e in ends)
+    launches = sum(e.launch_count() for e in exts) - l0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = D.max(dev_ms)
+    out = {"value": world * B * n_batches_timed / (dev_ms * 1e-3), "dev_ms": dev_ms, "launches": int(launches), "clocks": clocks,
+           "keypoints_per_frame": float(d_cnt[0].float().mean().item()), "cap": cap, "frames_per_batch": B,
+           "batches_timed": n_batches_timed, "timed_region_s": dev_ms * 1e-3}
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region
+    if want_e2e:
+        hp = W if tight_host_stride else pitch      # tight: the caller's own row stride (cv::Mat of a W-wide image)
+        pin_in = [orb.PinnedArray((B, H, hp), np.uint8) for _ in range(pool)]
+        for p in range(pool):
+            pin_in[p].array[:, :, :W] = host[p]
+        pin_k = [orb.PinnedArray((B, cap), orb.KP_DTYPE) for _ in range(n_streams)]
+        pin_d = [orb.PinnedArray((B, cap, 32), np.uint8) for _ in range(n_streams)]
+        pin_c = [orb.PinnedArray((B,), np.int32) for _ in range(n_streams)]
+
+        def e2e_run(nb):
+            inflight = [False] * n_streams
+            tot = 0
+            for i in range(nb):
+                s = i % n_streams
+                if inflight[s]:
+                    exts[s].wait(); tot += int(pin_c[s].array.sum())
+                exts[s].extract_batch_async(pin_in[i % pool].array[:, :, :W], pin_k[s].array, pin_d[s].array, pin_c[s].array)
+                inflight[s] = True
+            for s in range(n_streams):
+                if inflight[s]:
+                    exts[s].wait(); tot += int(pin_c[s].array.sum())
+            return tot
+
+        e2e_run(max(n_batches_warm, n_streams))
+        D.barrier()
+        t0 = time.perf_counter()
+        tot_kp = e2e_run(n_batches_timed)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        D.barrier()
+        e2e_s = D.max(e2e_s)
+        h2d = B * W * H
+        d2h = B * cap * (28 + 32) + B * 4
+        out["e2e"] = {"value": world * B * n_batches_timed / e2e_s, "unit": "frames/s", "h2d_bytes_per_batch": h2d, "d2h_bytes_per_batch": d2h,
+                      "keypoints_downloaded": tot_kp, "timed_region_s": e2e_s,
+                      "host_row_stride": hp}
+        cps, gh, gd = copy_ceiling(orb, torch, dev, D, h2d, d2h, n_streams, max(n_streams * 8, min(n_batches_timed, 256)))
+        out["e2e"]["copy_ceiling_frames_s"] = world * B * cps
+        out["e2e"]["copy_ceiling_gbs_per_gpu"] = {"h2d": gh, "d2h": gd}
+        for p in pin_in + pin_k + pin_d + pin_c:
+            p.free()
+
+    # ---- per-kernel durations (CUDA events on the extractor stream; outside the timed regions)
+    exts[0].set_profiling(True)
+    acc = {}
+    reps_prof = 5
+    for i in range(reps_prof):
+        dev_batch(i * n_streams)   # always stream 0
+        exts[0].wait()
+        for k, v in exts[0].stage_times().items():
+            acc[k] = acc.get(k, 0.0) + v / reps_prof
+    exts[0].set_profiling(False)
+    out["stage_ms"] = acc
+    out["host_frames"] = host
+    for e in exts:
+        e.close()
+    return out
+
+
+def roofline_of(cfg, res, B):
+    """The `roofline` object of the dominant pixel kernel of one configuration."""
+    BY = cfg["bytes"]
+    acc = res["stage_ms"]
+    kern = {k: acc.get(k, 0.0) for k in ("pyramid", "fast_score", "blur", "cell_nms", "quadtree", "describe")}
+    fused = kern["cell_nms"] <= 0.0      # score + cell NMS run as one kernel: its time is under "fast_score"
+    single = {"fast_score": kern["fast_score"], "blur": kern["blur"], "pyramid": kern["pyramid"]}
+    if not fused:
+        single["cell_nms"] = kern["cell_nms"]
+    dkey = max(single, key=single.get)
+    peak, peak_src = _peaks()
+    ach = BY[dkey] * B / (kern[dkey] * 1e-3) / 1e9
+    kname = {"fast_score": "fast_", "pyramid": "pyr_resize", "blur": "blur7_kernel", "cell_nms": "fast_nms_kernel"}[dkey]
+    src, _ = _ncu_rows()
+    traffic = _ncu_traffic(kname)
+    note = {"fast_score": "exact cornerScore of every pixel at minThFAST (+ cell-local 3x3 NMS when fused): bound by the half-rate integer ALU / FMA pipes, not by HBM",
+            "pyramid": "instruction bound (fixed-point taps), the level chain is serial",
+            "blur": "issue bound", "cell_nms": "issue bound"}[dkey]
+    roof = {"bound": "hbm", "kernel": dkey, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None if traffic is None else traffic * B / float(NCU_FRAMES),
+            "traffic_note": "DRAM bytes per launch of %d frames, from the %d-frame 640x480 ncu capture profiles/%s scaled by frames (and by "
+                            "pixels for other shapes); algorithmic bytes per launch = %d" % (B, NCU_FRAMES, src, BY[dkey] * B),
+            "peak_source": peak_src, "note": note, "algorithmic_bytes_per_frame": BY[dkey], "kernel_ms_per_launch": kern[dkey],
+            "ncu_alu_pipe_pct": _ncu_metric(kname, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            "ncu_fma_pipe_pct": _ncu_metric(kname, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "ncu_issue_active_pct": _ncu_metric(kname, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "stage_ms_per_batch": {k: round(v, 4) for k, v in acc.items()},
+            "stage_sum_ms_per_batch": round(sum(kern.values()), 4),
+            "stage_gbs": {k: round(BY[k] * B / (kern[k] * 1e-3) / 1e9, 1) for k in BY if kern.get(k, 0) > 0}}
+    if roof["traffic"] is not None and cfg is not CONFIGS["tum"]:
+        roof["traffic"] *= BY["fast_score"] / float(CONFIGS["tum"]["bytes"]["fast_score"])
+    return roof
+
+
+def bench_stereo(orb, synth, torch, cfg, args, local, B, min_seconds):
+    """BASELINE config 3: batches of B stereo pairs, left and right images on two extractor handles (two streams, as the
+    reference's two threads, Frame.cc:80-83) + the batched ComputeStereoMatches on the device.  N = 1 only."""
+    dev = torch.device("cuda", local)
+    W, H, NFEAT = cfg["w"], cfg["h"], cfg["nfeat"]
+    n_sets = max(1, args.streams // 2)          # (left, right) handle pairs in flight
+    pool = 2
+    n_distinct = min(pool * B, 32)
+    prs = [synth.stereo_pair(s, W, H) for s in range(n_distinct)]
+    reps = (pool * B + n_distinct - 1) // n_distinct
+    left = np.concatenate([np.stack([p[0] for p in prs])] * reps)[:pool * B].reshape(pool, B, H, W)
+    right = np.concatenate([np.stack([p[1] for p in prs])] * reps)[:pool * B].reshape(pool, B, H, W)
+    mbf, fx = 47.90639384423901, 435.2046959714599          # EuRoC.yaml Camera.bf / Camera.fx
+    mb = mbf / fx
+    el = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local, max_width=W, max_height=H, max_batch=B) for _ in range(n_sets)]
+    er = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local, max_width=W, max_height=H, max_batch=B) for _ in range(n_sets)]
+    cap = el[0].max_keypoints(W, H)
+    pitch = (W + 15) // 16 * 16
+    mk = lambda: (torch.empty((B, cap, 7), dtype=torch.int32, device=dev), torch.empty((B, cap, 32), dtype=torch.uint8, device=dev),
+                  torch.empty((B,), dtype=torch.int32, device=dev))
+    outL = [mk() for _ in range(n_sets)]; outR = [mk() for _ in range(n_sets)]
+    scratch = [torch.empty(orb.stereo_scratch_bytes(B, cap), dtype=torch.uint8, device=dev) for _ in range(n_sets)]
+    ur = [torch.empty((B, cap), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+    dep = [torch.empty((B, cap), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+    nm = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(n_sets)]
+    sL = [torch.cuda.ExternalStream(e.stream(), device=dev) for e in el]
+    sR = [torch.cuda.ExternalStream(e.stream(), device=dev) for e in er]
+    d_left = torch.zeros((pool, B, H, pitch), dtype=torch.uint8, device=dev); d_left[:, :, :, :W] = torch.from_numpy(left).to(dev)
+    d_right = torch.zeros((pool, B, H, pitch), dtype=torch.uint8, device=dev); d_right[:, :, :, :W] = torch.from_numpy(right).to(dev)
+
+    def stereo_call(s):
+        kl, dl, cl = outL[s]; kr, dr, cr = outR[s]
+        # enqueued on the left extractor's stream, which is made to wait for the right one (no host synchronisation)
+        orb.compute_stereo_matches_batch_device(el[s], er[s], kl.data_ptr(), dl.data_ptr(), cl.data_ptr(), kr.data_ptr(), dr.data_ptr(),
+                                                cr.data_ptr(), B, cap, mbf, mb, scratch[s].data_ptr(), ur[s].data_ptr(),
+                                                dep[s].data_ptr(), nm[s].data_ptr(), el[s].stream())
+
+    def dev_batch(i):
+        s = i % n_sets
+        kl, dl, cl = outL[s]; kr, dr, cr = outR[s]
+        # the right extractor must not overwrite its pyramid while the previous stereo search (on the left stream) still reads it
+        sR[s].wait_stream(sL[s])
+        el[s].extract_batch_device(d_left[i % pool].data_ptr(), B, W, H, pitch, pitch * H, kl.data_ptr(), dl.data_ptr(), cap, cl.data_ptr())
+        er[s].extract_batch_device(d_right[i % pool].data_ptr(), B, W, H, pitch, pitch * H, kr.data_ptr(), dr.data_ptr(), cap, cr.data_ptr())
+        stereo_call(s)
+
+    def timed(nb):
+        torch.cuda.synchronize()
+        start = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_sets)]
+        start.record(sL[0])
+        for s in range(1, n_sets):
+            sL[s].wait_event(start)
+        for s in range(n_sets):
+            sR[s].wait_event(start)
+        for i in range(nb):
+            dev_batch(i)
+        for s in range(n_sets):
+            ends[s].record(sL[s])
+        torch.cuda.synchronize()
+        return max(start.elapsed_time(e) for e in ends)
+
+    timed(2 * n_sets)
+    pilot = timed(4 * n_sets) / (4 * n_sets)
+    nb = max(4 * n_sets, int(np.ceil(min_seconds * 1e3 / max(pilot, 1e-3))))
+    sampler = ClockSampler(local)
+    ms = timed(nb)
+    clocks = sampler.stop()
+    matches = float(nm[0].float().mean().item()); kpl = float(outL[0][2].float().mean().item())
+    res = {"value": B * nb / (ms * 1e-3), "unit": "stereo pairs/s", "frames_s": 2 * B * nb / (ms * 1e-3), "pairs_per_batch": B,
+           "batches_timed": nb, "timed_region_s": ms * 1e-3, "clocks": clocks, "keypoints_per_left_image": kpl,
+           "stereo_matches_per_pair": matches, "handle_pairs_in_flight": n_sets}
+
+    # ---- e2e: both images from pinned host memory, mvuRight / mvDepth / key points / descriptors of both sides back
+    pin_l = [orb.PinnedArray((B, H, W), np.uint8) for _ in range(pool)]; pin_r = [orb.PinnedArray((B, H, W), np.uint8) for _ in range(pool)]
+    for p in range(pool):
+        pin_l[p].array[...] = left[p]; pin_r[p].array[...] = right[p]
+    pk = [[orb.PinnedArray((B, cap), orb.KP_DTYPE) for _ in range(2)] for _ in range(n_sets)]
+    pd = [[orb.PinnedArray((B, cap, 32), np.uint8) for _ in range(2)] for _ in range(n_sets)]
+    pc = [[orb.PinnedArray((B,), np.int32) for _ in range(2)] for _ in range(n_sets)]
+    keep = []
+    h_ur = [_pinned_tensor(orb, torch, (B, cap), np.float32, keep) for _ in range(n_sets)]
+    h_dep = [_pinned_tensor(orb, torch, (B, cap), np.float32, keep) for _ in range(n_sets)]
+    h_nm = [_pinned_tensor(orb, torch, (B,), np.int32, keep) for _ in range(n_sets)]
+
+    # The async (host-buffer) extraction API and the device-batch stereo search compose through device buffers, so the
+    # end-to-end stereo path uploads the images itself and downloads every result: H2D of both images, extraction of
+    # both, stereo search, D2H of key points + descriptors of both sides and of mvuRight / mvDepth.
+    hl_dev = [torch.empty((B, H, pitch), dtype=torch.uint8, device=dev) for _ in range(n_sets)]
+    hr_dev = [torch.empty((B, H, pitch), dtype=torch.uint8, device=dev) for _ in range(n_sets)]
+    tl = [torch.from_numpy(p.array) for p in pin_l]; tr = [torch.from_numpy(p.array) for p in pin_r]
+    tk = [[torch.from_numpy(p.array.view(np.int32).reshape(B, cap, 7)) for p in row] for row in pk]
+    td = [[torch.from_numpy(p.array) for p in row] for row in pd]
+    tc = [[torch.from_numpy(p.array) for p in row] for row in pc]
+
+    def e2e_batch(i):
+        s = i % n_sets
+        kl, dl, cl = outL[s]; kr, dr, cr = outR[s]
+        sR[s].wait_stream(sL[s])
+        with torch.cuda.stream(sL[s]):
+            hl_dev[s][:, :, :W].copy_(tl[i % pool], non_blocking=True)
+        with torch.cuda.stream(sR[s]):
+            hr_dev[s][:, :, :W].copy_(tr[i % pool], non_blocking=True)
+        el[s].extract_batch_device(hl_dev[s].data_ptr(), B, W, H, pitch, pitch * H, kl.data_ptr(), dl.data_ptr(), cap, cl.data_ptr())
+        er[s].extract_batch_device(hr_dev[s].data_ptr(), B, W, H, pitch, pitch * H, kr.data_ptr(), dr.data_ptr(), cap, cr.data_ptr())
+        with torch.cuda.stream(sR[s]):
+            tk[s][1].copy_(kr, non_blocking=True); td[s][1].copy_(dr, non_blocking=True); tc[s][1].copy_(cr, non_blocking=True)
+        stereo_call(s)
+        with torch.cuda.stream(sL[s]):
+            tk[s][0].copy_(kl, non_blocking=True); td[s][0].copy_(dl, non_blocking=True); tc[s][0].copy_(cl, non_blocking=True)
+            h_ur[s].copy_(ur[s], non_blocking=True); h_dep[s].copy_(dep[s], non_blocking=True); h_nm[s].copy_(nm[s], non_blocking=True)
+
+    def e2e_loop(nbatches):
+        inflight = [False] * n_sets
+        tot = 0
+        for i in range(nbatches):
+            s = i % n_sets
+            if inflight[s]:
+                sL[s].synchronize(); sR[s].synchronize(); tot += int(h_nm[s].sum().item())
+            e2e_batch(i)
+            inflight[s] = True
+        for s in range(n_sets):
+            if inflight[s]:
+                sL[s].synchronize(); sR[s].synchronize(); tot += int(h_nm[s].sum().item())
+        return tot
+
+    e2e_loop(2 * n_sets)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tot = e2e_loop(nb)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    res["e2e"] = {"value": B * nb / e2e_s, "unit": "stereo pairs/s", "h2d_bytes_per_batch": 2 * B * W * H,
+                  "d2h_bytes_per_batch": 2 * (B * cap * 60 + B * 4) + 2 * B * cap * 4 + B * 4, "stereo_matches_downloaded": tot,
+                  "timed_region_s": e2e_s}
+
+    # stage times of one extractor + the stereo search alone
+    el[0].set_profiling(True)
+    acc = {}
+    for i in range(5):
+        kl, dl, cl = outL[0]
+        el[0].extract_batch_device(d_left[i % pool].data_ptr(), B, W, H, pitch, pitch * H, kl.data_ptr(), dl.data_ptr(), cap, cl.data_ptr())
+        el[0].wait()
+        for k, v in el[0].stage_times().items():
+            acc[k] = acc.get(k, 0.0) + v / 5
+    el[0].set_profiling(False)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(sL[0])
+    for _ in range(10):
+        stereo_call(0)
+    e1.record(sL[0])
+    torch.cuda.synchronize()
+    acc["stereo_search"] = e0.elapsed_time(e1) / 10
+    res["stage_ms"] = acc
+    res["host_left"] = left; res["host_right"] = right; res["mbf"] = mbf; res["mb"] = mb
+    torch.cuda.synchronize()
+    del tl, tr, tk, td, tc, h_ur, h_dep, h_nm
+    for p in pin_l + pin_r + [x for row in pk + pd + pc for x in row] + keep:
+        p.free()
+    for e in el + er:
+        e.close()
+    return res
+
+
+def bench_matching(orb, synth, torch, dist, D, args, rank, world, local):
+    """BASELINE config 4: 2000 queries x 1M map descriptors, map sharded over the ranks."""
+    import ctypes as C
+    dev = torch.device("cuda", local)
+    NQ, NM = 2000, 1000000
+    m_all = synth.descriptors(NM, seed=1234)
+    q, m_all, _ = synth.query_set(m_all, nq=NQ, seed=4321)
+    lo = NM * rank // world; hi = NM * (rank + 1) // world
+    d_m = torch.from_numpy(m_all[lo:hi].copy()).to(dev)
+    d_q = torch.from_numpy(q).to(dev)
+    rec = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
+    L = orb.lib()
+    cur = torch.cuda.current_stream(dev)
+    parts = torch.empty((world, NQ, 4), dtype=torch.int32, device=dev)
+    merged = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
+
+    def match_step(variant):
+        rc = L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), NQ, C.c_void_p(d_m.data_ptr()), hi - lo, lo,
+                                C.c_void_p(rec.data_ptr()), variant, C.c_void_p(cur.cuda_stream))
+        assert rc == 0, L.orb_last_error()
+        if world > 1:
+            dist.all_gather_into_tensor(parts, rec)
+            rc = L.orbm_merge_top2_device(C.c_void_p(parts.data_ptr()), world, NQ, C.c_void_p(merged.data_ptr()),
+                                          C.c_void_p(cur.cuda_stream))
+            assert rc == 0
+            return merged
+        return rec
+
+    # fused merge + exchange over peer memory (csrc/peer.cu) next to the NCCL formulation
+    peer = None
+    if world > 1:
+        def gather_bytes(b):
+            t = torch.tensor(list(b), dtype=torch.uint8, device=dev)
+            allt = torch.empty((world, len(b)), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allt, t)
+            return [bytes(allt[r].cpu().numpy().tobytes()) for r in range(world)]
+        # CUDA IPC can be unavailable in some container setups: the NCCL formulation is then the only one measured
+        # (every rank must take the same branch, hence the all-reduce of the outcome)
+        ok = 1
+        try:
+            peer = orb.PeerExchange(NQ, rank, world, local, gather_bytes)
+        except Exception:      # noqa: BLE001 -- reported through `fused: null`
+            ok = 0
+        if D.min(ok) == 0:
+            if peer is not None:
+                peer.close()
+            peer = None
+        fused_out = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
+
+    def match_step_fused(variant):
+        peer.knn2(d_q.data_ptr(), NQ, d_m.data_ptr(), hi - lo, lo, fused_out.data_ptr(), variant, cur.cuda_stream)
+        return fused_out
+
+    def time_loop(fn, n):
+        D.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for _ in range(n):
+            out = fn()
+        e1.record(cur)
+        D.barrier()
+        return D.max(e0.elapsed_time(e1)) / n, out
+
+    per_variant = {}
+    ref_out = None
+    for variant, name in ((0, "popc"), (1, "imma_smem"), (2, "imma_stream"), (3, "tcgen05"), (4, "tcgen05_a_in_tmem"), (5, "tcgen05_cta_pair")):
+        for _ in range(3):
+            match_step(variant)
+        mms, out = time_loop(lambda: match_step(variant), 10)
+        per_variant[name] = {"ms_per_batch": mms, "gcmp_s": NQ * NM / (mms * 1e-3) / 1e9}
+        if ref_out is None:
+            ref_out = out.clone()
+        else:
+            assert bool((ref_out == out).all().item()), "2-NN variants disagree"
+    if peer is not None:
+        for _ in range(3):
+            match_step_fused(5)
+        fms, fo = time_loop(lambda: match_step_fused(5), 10)
+        assert peer.error() == 0, "peer exchange timed out"
+        assert bool((ref_out == fo).all().item()), "fused merge+exchange differs from the NCCL path"
+        per_variant["tcgen05_cta_pair_fused_exchange"] = {"ms_per_batch": fms, "gcmp_s": NQ * NM / (fms * 1e-3) / 1e9}
+    bestv = max(per_variant, key=lambda k: per_variant[k]["gcmp_s"])
+    best_fn = (lambda: match_step_fused(5)) if bestv.endswith("fused_exchange") else (lambda: match_step(5 if bestv.startswith("tcgen05_cta_pair") else
+                                                                                                       {"popc": 0, "imma_smem": 1, "imma_stream": 2, "tcgen05": 3, "tcgen05_a_in_tmem": 4}[bestv]))
+    # sustained: the best formulation back to back for >= 1.5 s under the clock sampler (the 10-iteration figure is a burst)
+    n_sus = int(max(50, min(20000, 1500.0 / per_variant[bestv]["ms_per_batch"])))
+    sampler = ClockSampler(local) if rank == 0 else None
+    sus_ms, sus_out = time_loop(best_fn, n_sus)
+    sus_clocks = sampler.stop() if sampler else None
+    assert bool((ref_out == sus_out).all().item())
+    gcmp = per_variant[bestv]["gcmp_s"]
+    gcmp_sus = NQ * NM / (sus_ms * 1e-3) / 1e9
+    # ---- parity of the full-size result against the CPU oracle (rank 0; 2e9 comparisons on all host threads)
+    parity = None; cpu = None
+    if rank == 0 and not args.no_cpu:
+        oracle_lib = _oracle_lib()
+        threads = os.cpu_count() or 1
+        i1 = np.zeros(NQ, np.int32); d1 = np.zeros(NQ, np.int32); d2 = np.zeros(NQ, np.int32)
+        t0 = time.perf_counter()
+        oracle_lib.lib().orc_knn2(q.ctypes.data, NQ, m_all.ctypes.data, NM, 0, i1.ctypes.data, d1.ctypes.data, d2.ctypes.data, threads)
+        dtm = time.perf_counter() - t0
+        got = ref_out.cpu().numpy()
+        parity = bool(np.array_equal(got[:, 0], d1) and np.array_equal(got[:, 1], i1) and np.array_equal(got[:, 2], d2))
+        # the reference's brute-force loop (DescriptorDistance + best/second rule, ORBmatcher.cc:1647-1663, :216-225),
+        # std::thread-parallel over the queries, on the whole workload
+        cpu = {"value": NQ * NM / dtm / 1e9, "unit": "Gcmp/s", "cores": threads, "kind": "port",
+               "sample": "2000 queries x %d map descriptors (the whole workload) in %.2f s" % (NM, dtm)}
+    if world > 1:
+        pt = torch.tensor([1 if parity in (None, True) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(pt, op=dist.ReduceOp.MIN)
+        ok = bool(pt.item())
+    else:
+        ok = parity in (None, True)
+    if not ok:
+        raise SystemExit("bench.py: the 2000 x 1M 2-NN records differ from the CPU oracle")
+    tops = 2 * 256 * gcmp / 1e3                      # one comparison = 256 int8 MACs on the tensor pipe
+    tops_sus = 2 * 256 * gcmp_sus / 1e3
+    peak8 = 4500.0 * world                            # nominal dense 8-bit peak per GPU (B200_PROFILING.md) x GPUs
+    pair = bestv.startswith("tcgen05_cta_pair")
+    matching = {"metric": "Hamming 2-NN Gcmp/s (2000 queries x 1M map, 256-bit)", "value": gcmp, "unit": "Gcmp/s",
+                "ms_per_batch": per_variant[bestv]["ms_per_batch"], "kernel": bestv, "variants": per_variant,
+                "sustained": {"value": gcmp_sus, "unit": "Gcmp/s", "ms_per_batch": sus_ms, "iterations": n_sus,
+                              "timed_region_s": sus_ms * n_sus * 1e-3, "clocks": sus_clocks},
+                "map_shards": world, "d1_checksum": int(ref_out[:, 0].sum().item()), "parity_vs_oracle": parity,
+                "roofline": {"bound": "tensor", "achieved": tops, "peak": peak8, "unit": "TOP/s", "frac": tops / peak8,
+                             "achieved_sustained": tops_sus, "frac_sustained": tops_sus / peak8,
+                             "frac_vs_2x_measured_bf16_burst": tops / (2 * _bf16_peak()[0] * world),
+                             "frac_sustained_vs_2x_measured_bf16_sustained": tops_sus / (2 * _bf16_peak(True)[0] * world),
+                             "traffic": _ncu_traffic("knn2_pair_kernel" if pair else "knn2_tc_kernel", "r1_ncu_knn2_tcgen05.csv"),
+                             "peak_source": "fallback: B200_PROFILING.md nominal dense 8-bit tensor peak x %d GPU(s) (MEASURED_PEAKS.json has no "
+                                            "8-bit figure; bf16 %s = %.0f burst / %.0f sustained TFLOP/s per GPU); ncu tensor pipe active 77 %% for "
+                                            "the CTA-pair kernel -- profiles/r1_ncu_knn2_tcgen05.csv"
+                                            % (world, _bf16_peak()[1], _bf16_peak()[0], _bf16_peak(True)[0])},
+                "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8 * world,
+                "popc_kernel_frac_of_popc_peak": per_variant["popc"]["gcmp_s"] / (148 * 16 * 1.965 / 8 * world),
+                "cpu_baseline": cpu}
+    if peer is not None:
+        peer.close()
+    return matching
+
+
+def bench_candidate_loops(orb, synth, local):
+    """Call latency of the latency-sized entry points through the C ABI next to one CPU thread of the oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import matchdata
+    oracle_lib = _oracle_lib()
+    d1, d2, a1, a2, src, dst, rng = matchdata.two_views(1000, 1100, 0)
+    valid = np.ones(len(d1), np.uint8)
+    fv1, fv2 = matchdata.featvec(d1), matchdata.featvec(d2)
+    mt = orb.ORBmatcher(0.7, True, device=local)
+
+    def timeit(fn, n=30):
+        for _ in range(3):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t0) / n * 1e3
+
+    loops = {"search_by_bow_kf_f_ms": {"gpu_call": timeit(lambda: mt.SearchByBoW(d1, a1, valid, fv1, d2, a2, fv2)),
+                                       "cpu_oracle_1thread": timeit(lambda: oracle_lib.search_by_bow_kf_f(d1, a1, valid, fv1, d2, a2, fv2, 0.7, True))},
+             "features": [len(d1), len(d2)], "note": "host arrays in/out, includes H2D/D2H; problem is tiny (~17 candidates per feature)"}
+    frng = np.random.default_rng(5)
+    nf, nmp = 2000, 4000
+    fk = np.zeros(nf, orb.KP_DTYPE)
+    lv = frng.integers(0, 8, nf); sc = 1.2 ** lv
+    fk["x"] = (frng.integers(16, (640 / sc - 16).astype(int)) * sc).astype(np.float32)
+    fk["y"] = (frng.integers(16, (480 / sc - 16).astype(int)) * sc).astype(np.float32)
+    fk["octave"] = lv; fk["angle"] = frng.uniform(0, 360, nf).astype(np.float32)
+    Kc = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
+    Dc = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+    fdesc = synth.descriptors(nf, seed=77)
+    fr = orb.FrameFeatures(fk, Kc, Dc, 640, 480, device=local)
+    mpv = np.zeros(nmp, orb.MPV_DTYPE)
+    srcf = frng.integers(0, nf, nmp)
+    mpv["proj_x"] = fr.keys_un["x"][srcf] + frng.normal(0, 2, nmp).astype(np.float32)
+    mpv["proj_y"] = fr.keys_un["y"][srcf] + frng.normal(0, 2, nmp).astype(np.float32)
+    mpv["proj_xr"] = mpv["proj_x"] - 10; mpv["view_cos"] = 0.999; mpv["level"] = fr.keys_un["octave"][srcf]
+    mpv["in_view"] = 1; mpv["obs_positive"] = 1
+    mdesc = fdesc[srcf].copy(); mdesc[:, 0] ^= frng.integers(0, 256, nmp).astype(np.uint8)
+    sfac = (1.2 ** np.arange(8)).astype(np.float32)
+    ur0 = np.full(nf, -1, np.float32); occ0 = np.zeros(nf, np.uint8)
+    loops["frame_build_ms"] = {
+        "gpu_call": timeit(lambda: orb.FrameFeatures(fk, Kc, Dc, 640, 480, device=local)),
+        "cpu_oracle_1thread": timeit(lambda: (oracle_lib.image_bounds(640, 480, Kc, Dc),
+                                              oracle_lib.assign_grid(oracle_lib.undistort_keypoints(fk, Kc, Dc), fr.bounds)))}
+    loops["search_by_projection_frame_ms"] = {
+        "gpu_call": timeit(lambda: orb.search_by_projection_frame(fr, fdesc, ur0, occ0, sfac, mpv, mdesc, th=1.0, nnratio=0.8)),
+        "cpu_oracle_1thread": timeit(lambda: oracle_lib.search_by_projection_frame(fr.keys_un, fdesc, ur0, occ0, fr.cell_ptr, fr.cell_idx,
+                                                                                   fr.bounds, sfac, mpv, mdesc, 1.0, 0.8)),
+        "features": nf, "map_points": nmp}
+    return loops
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -235,176 +975,25 @@ def run_ours(args):
     orb = importlib.import_module("cooperative-orb-slam_b200")
     synth = importlib.import_module("cooperative-orb-slam_b200.synth")
     dev = torch.device("cuda", local)
+    D = Dist(torch, dist, world, dev)
     B = args.batch
-    n_streams = args.streams
-    pool = 4   # distinct batches cycled through (working set per step >> L2)
-    seeds = np.arange(pool * B) + 1000 * rank
-    host_frames = np.stack([synth.frame(int(s), W, H) for s in seeds[:min(len(seeds), 64)]])
-    # tile the distinct frames over the pool (content repeats every 64 frames; still distinct memory)
-    reps = (pool * B + len(host_frames) - 1) // len(host_frames)
-    host_frames = np.concatenate([host_frames] * reps)[:pool * B].reshape(pool, B, H, W)
+    cfg = CONFIGS["tum"]
+    want = [c for c in args.configs.split(",") if c]
 
-    exts = [orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local, max_width=W, max_height=H, max_batch=B)
-            for _ in range(n_streams)]
-    cap = exts[0].max_keypoints(W, H)
-    streams = [torch.cuda.ExternalStream(e.stream(), device=dev) for e in exts]
+    # ---------------- headline: BASELINE config 1 ----------------------------------------------------------------
+    bps = args.batches_per_step
+    head = bench_extraction(orb, synth, torch, D, cfg, args, rank, world, local, B, args.steps * bps, args.warmup * bps)
+    roof = roofline_of(cfg, head, B)
+    host_frames = head.pop("host_frames")
+    _note("headline: %.0f frames/s device-resident, %.0f end to end" % (head["value"], head["e2e"]["value"]))
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---------------- value: inputs resident in HBM -------------------------------------------------------
-    d_frames = torch.from_numpy(host_frames).to(dev)                      # [pool,B,H,W] uint8
-    d_kps = [torch.empty((B, cap, 7), dtype=torch.int32, device=dev) for _ in range(n_streams)]
-    d_desc = [torch.empty((B, cap, 32), dtype=torch.uint8, device=dev) for _ in range(n_streams)]
-    d_cnt = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(n_streams)]
-
-    def dev_step(i):
-        s = i % n_streams
-        fr = d_frames[i % pool]
-        exts[s].extract_batch_device(fr.data_ptr(), B, W, H, W, W * H, d_kps[s].data_ptr(), d_desc[s].data_ptr(), cap,
-                                     d_cnt[s].data_ptr())
-
-    for i in range(args.warmup):
-        dev_step(i)
-    barrier()
-    l0 = sum(e.launch_count() for e in exts)
-    sampler = ClockSampler(local) if rank == 0 else None
-    start = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_streams)]
-    start.record(streams[0])
-    for s in range(1, n_streams):
-        streams[s].wait_event(start)
-    for i in range(args.steps):
-        dev_step(i)
-    for s in range(n_streams):
-        ends[s].record(streams[s])
-    barrier()
-    dev_ms = max(start.elapsed_time(e) for e in ends)
-    launches = sum(e.launch_count() for e in exts) - l0
-    clocks = sampler.stop() if sampler else None
-    dev_ms = max_over_ranks(dev_ms)
-    value = world * B * args.steps / (dev_ms * 1e-3)
-    kp_mean = float(d_cnt[0].float().mean().item())
-
-    # ---------------- cooperative key-frame exchange (N > 1): the agent -> server message of the reference -----
-    # 10 key frames per agent per message (ros_mono.cc:1943-1948), device-resident extractor output, int16 wire
-    # truncation applied on the device, one ncclAllGather per array over NVLink.
+    # ---------------- cooperative key-frame exchange (N > 1): the agent -> server message of the reference --------
     exchange = None
     if world > 1:
-        KF = 10
-        L = orb.lib()
-        import ctypes as C
-        kf_k = d_kps[0][:KF].contiguous(); kf_d = d_desc[0][:KF].contiguous(); kf_c = d_cnt[0][:KF].contiguous()
-        all_k = torch.empty((world,) + tuple(kf_k.shape), dtype=kf_k.dtype, device=dev)
-        all_d = torch.empty((world,) + tuple(kf_d.shape), dtype=kf_d.dtype, device=dev)
-        all_c = torch.empty((world,) + tuple(kf_c.shape), dtype=kf_c.dtype, device=dev)
-        cur = torch.cuda.current_stream(dev)
-
-        def exchange_step():
-            rc = L.orbw_quantize_lcm_device(C.c_void_p(kf_k.data_ptr()), C.c_void_p(kf_c.data_ptr()), KF, cap, C.c_void_p(cur.cuda_stream))
-            assert rc == 0
-            dist.all_gather_into_tensor(all_k, kf_k); dist.all_gather_into_tensor(all_d, kf_d); dist.all_gather_into_tensor(all_c, kf_c)
-
-        torch.cuda.synchronize(dev)
-        for _ in range(3):
-            exchange_step()
-        barrier()
-        x0 = torch.cuda.Event(enable_timing=True); x1 = torch.cuda.Event(enable_timing=True)
-        x0.record(cur)
-        for _ in range(20):
-            exchange_step()
-        x1.record(cur)
-        barrier()
-        xms = max_over_ranks(x0.elapsed_time(x1)) / 20
-        msg = kf_k.numel() * 4 + kf_d.numel() + kf_c.numel() * 4
-        exchange = {"keyframes_per_agent": KF, "bytes_per_agent": msg, "ms_per_exchange": xms,
-                    "allgather_gbs": world * msg / (xms * 1e-3) / 1e9,
-                    "note": "reference: one LCM UDP-multicast message of 10 key frames, descriptors as float32 (4x the bytes)"}
-
-    # ---------------- e2e: host buffers, H2D + D2H inside the timed region ---------------------------------
-    pin_in = [orb.PinnedArray((B, H, W), np.uint8) for _ in range(pool)]
-    for p in range(pool):
-        pin_in[p].array[...] = host_frames[p]
-    pin_k = [orb.PinnedArray((B, cap), orb.KP_DTYPE) for _ in range(n_streams)]
-    pin_d = [orb.PinnedArray((B, cap, 32), np.uint8) for _ in range(n_streams)]
-    pin_c = [orb.PinnedArray((B,), np.int32) for _ in range(n_streams)]
-
-    def e2e_run(steps):
-        inflight = [False] * n_streams
-        tot = 0
-        for i in range(steps):
-            s = i % n_streams
-            if inflight[s]:
-                exts[s].wait(); tot += int(pin_c[s].array.sum())
-            exts[s].extract_batch_async(pin_in[i % pool].array, pin_k[s].array, pin_d[s].array, pin_c[s].array)
-            inflight[s] = True
-        for s in range(n_streams):
-            if inflight[s]:
-                exts[s].wait(); tot += int(pin_c[s].array.sum())
-        return tot
-
-    e2e_run(max(args.warmup, n_streams))
-    barrier()
-    t0 = time.perf_counter()
-    tot_kp = e2e_run(args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    e2e_s = max_over_ranks(e2e_s)
-    e2e_value = world * B * args.steps / e2e_s
-    h2d = B * W * H
-    d2h = B * cap * (28 + 32) + B * 4
-
-    # ---------------- per-kernel durations (CUDA events on the extractor stream; outside the timed regions) --
-    exts[0].set_profiling(True)
-    acc = {}
-    reps_prof = 5
-    for i in range(reps_prof):
-        dev_step(i * n_streams)   # always stream 0
-        exts[0].wait()
-        for k, v in exts[0].stage_times().items():
-            acc[k] = acc.get(k, 0.0) + v / reps_prof
-    exts[0].set_profiling(False)
-    kern = {k: acc[k] for k in ("pyramid", "fast_score", "blur", "cell_nms", "quadtree", "describe")}
-    # "pyramid" is 8 launches (the level chain is serial); every other stage is one kernel.  The dominant single
-    # kernel among the pixel stages is what the roofline object describes.
-    single = {"fast_score": kern["fast_score"], "blur": kern["blur"], "cell_nms": kern["cell_nms"],
-              "pyramid(8 launches)": kern["pyramid"]}
-    dominant = max(single, key=single.get)
-    peak, peak_src = _peaks()
-    dkey = "pyramid" if dominant.startswith("pyramid") else dominant
-    ach = BYTES[dkey] * B / (kern[dkey] * 1e-3) / 1e9
-    bound_note = {"fast_score": "ALU-pipe bound (exact cornerScore of every pixel; part of the min/max moved to the FMA pipe: ncu alu pipe 68 %, fma 21 %, issue 60 %), not HBM",
-                  "pyramid": "instruction bound (fixed-point taps, byte gathers from the staged tile), 8 dependent launches",
-                  "blur": "issue bound", "cell_nms": "issue bound"}[dkey]
-    # the ncu capture under profiles/ is a launch over 64 frames: scale its DRAM bytes to this run's frames per launch
-    traffic64 = _ncu_traffic("r1_ncu_full_final_summary.csv", {"fast_score": "fast_score_kernel", "pyramid": "pyr_resize", "blur": "blur7_kernel<0>",
-                                                                "cell_nms": "fast_nms_kernel"}[dkey])
-    roof = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None if traffic64 is None else traffic64 * B / 64.0,
-            "traffic_note": "DRAM bytes per launch of %d frames, from the 64-frame ncu capture in profiles/ scaled by %d/64; "
-                            "algorithmic bytes per launch = %d" % (B, B, BYTES[dkey] * B),
-            "peak_source": peak_src, "note": bound_note,
-            "algorithmic_bytes_per_frame": BYTES[dkey], "kernel_ms_per_launch": kern[dkey]}
-    # what actually bounds this kernel (from the same committed capture): the half-rate integer ALU pipe
-    kname = {"fast_score": "fast_score_kernel", "pyramid": "pyr_resize", "blur": "blur7_kernel<0>", "cell_nms": "fast_nms_kernel"}[dkey]
-    roof["ncu_alu_pipe_pct"] = _ncu_metric("r1_ncu_full_final_summary.csv", kname, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
-    roof["ncu_issue_active_pct"] = _ncu_metric("r1_ncu_full_final_summary.csv", kname, "smsp__issue_active.avg.pct_of_peak_sustained_active")
-    roof["stage_ms_per_batch"] = {k: round(v, 4) for k, v in acc.items()}
-    roof["stage_gbs"] = {k: round(BYTES[k] * B / (kern[k] * 1e-3) / 1e9, 1) for k in BYTES if kern.get(k, 0) > 0}
+        exchange = bench_keyframe_exchange(orb, torch, dist, D, world, local, host_frames[0], cfg)
 
     # single-frame latency through the synchronous reference-shaped call (operator())
-    one = orb.ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local)
+    one = orb.ORBextractor(cfg["nfeat"], 1.2, 8, 20, 7, device=local)
     for _ in range(5):
         one(host_frames[0, 0])
     t0 = time.perf_counter()
@@ -413,220 +1002,153 @@ def run_ours(args):
     latency_ms = (time.perf_counter() - t0) / 50 * 1e3
     one.close()
 
-    # ---------------- matching: 2000 x 1M brute-force 2-NN, map sharded over ranks -------------------------
     matching = None
     if not args.no_matching:
-        NQ, NM = 2000, 1000000
-        m_all = synth.descriptors(NM, seed=1234)
-        q, m_all, _ = synth.query_set(m_all, nq=NQ, seed=4321)
-        lo = NM * rank // world; hi = NM * (rank + 1) // world
-        d_m = torch.from_numpy(m_all[lo:hi].copy()).to(dev)
-        d_q = torch.from_numpy(q).to(dev)
-        rec = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
-        L = orb.lib()
-        import ctypes as C
-        cur = torch.cuda.current_stream(dev)
+        matching = bench_matching(orb, synth, torch, dist, D, args, rank, world, local)
+        _note("matching: %.0f Gcmp/s (%s), sustained %.0f, parity_vs_oracle %s" % (matching["value"], matching["kernel"],
+                                                                                   matching["sustained"]["value"], matching["parity_vs_oracle"]))
 
-        def match_step(variant):
-            rc = L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), NQ, C.c_void_p(d_m.data_ptr()), hi - lo, lo,
-                                    C.c_void_p(rec.data_ptr()), variant, C.c_void_p(cur.cuda_stream))
-            assert rc == 0, L.orb_last_error()
-            if world > 1:
-                parts = torch.empty((world, NQ, 4), dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(parts, rec)
-                out = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
-                rc = L.orbm_merge_top2_device(C.c_void_p(parts.data_ptr()), world, NQ, C.c_void_p(out.data_ptr()),
-                                              C.c_void_p(cur.cuda_stream))
-                assert rc == 0
-                return out
-            return rec
-
-        # fused merge + exchange over peer memory (csrc/peer.cu) next to the NCCL formulation
-        peer = None
-        if world > 1:
-            def gather_bytes(b):
-                t = torch.tensor(list(b), dtype=torch.uint8, device=dev)
-                allt = torch.empty((world, len(b)), dtype=torch.uint8, device=dev)
-                dist.all_gather_into_tensor(allt, t)
-                return [bytes(allt[r].cpu().numpy().tobytes()) for r in range(world)]
-            # CUDA IPC can be unavailable in some container setups: the NCCL formulation below is then the only one
-            # measured (every rank must take the same branch, hence the all-reduce of the outcome)
-            ok = 1
-            try:
-                peer = orb.PeerExchange(NQ, rank, world, local, gather_bytes)
-            except Exception as exc:      # noqa: BLE001 -- reported, not hidden
-                peer_error = str(exc); ok = 0
-            okt = torch.tensor([ok], dtype=torch.int32, device=dev)
-            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-            if int(okt.item()) == 0:
-                if peer is not None:
-                    peer.close()
-                peer = None
-            fused_out = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
-
-        def match_step_fused(variant):
-            peer.knn2(d_q.data_ptr(), NQ, d_m.data_ptr(), hi - lo, lo, fused_out.data_ptr(), variant, cur.cuda_stream)
-            return fused_out
-
-        per_variant = {}
-        ref_out = None
-        for variant, name in ((0, "popc"), (1, "imma_smem"), (2, "imma_stream"), (3, "tcgen05"), (4, "tcgen05_a_in_tmem"), (5, "tcgen05_cta_pair")):
-            for _ in range(3):
-                match_step(variant)
-            barrier()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            msteps = 10
-            e0.record(cur)
-            for _ in range(msteps):
-                out = match_step(variant)
-            e1.record(cur)
-            barrier()
-            mms = max_over_ranks(e0.elapsed_time(e1)) / msteps
-            per_variant[name] = {"ms_per_batch": mms, "gcmp_s": NQ * NM / (mms * 1e-3) / 1e9}
-            if ref_out is None:
-                ref_out = out.clone()
-            else:
-                assert bool((ref_out == out).all().item()), "2-NN variants disagree"
-        fused = None
-        if peer is not None:
-            fv = 5
-            for _ in range(3):
-                match_step_fused(fv)
-            barrier()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(cur)
-            for _ in range(10):
-                fo = match_step_fused(fv)
-            e1.record(cur)
-            barrier()
-            fms = max_over_ranks(e0.elapsed_time(e1)) / 10
-            assert peer.error() == 0, "peer exchange timed out"
-            assert bool((ref_out == fo).all().item()), "fused merge+exchange differs from the NCCL path"
-            fused = {"ms_per_batch": fms, "gcmp_s": NQ * NM / (fms * 1e-3) / 1e9, "kernel": "tcgen05_cta_pair + merge_exchange_kernel (peer stores over NVLink, no NCCL)"}
-            per_variant["tcgen05_cta_pair_fused_exchange"] = {"ms_per_batch": fms, "gcmp_s": fused["gcmp_s"]}
-        bestv = max(per_variant, key=lambda k: per_variant[k]["gcmp_s"])
-        gcmp = per_variant[bestv]["gcmp_s"]
-        chk = int(ref_out[:, 0].sum().item())
-        matching = {"metric": "Hamming 2-NN Gcmp/s (2000 queries x 1M map, 256-bit)", "value": gcmp, "unit": "Gcmp/s",
-                    "ms_per_batch": per_variant[bestv]["ms_per_batch"], "kernel": bestv, "variants": per_variant,
-                    "map_shards": world, "d1_checksum": chk,
-                    # one comparison = 256 int8 MACs on the tensor pipe; int8 dense peak = 2 x the measured bf16 peak
-                    # the 8-bit tensor rate is twice the bf16 rate.  MEASURED_PEAKS.json has no 8-bit figure: peak = the profiling
-                    # guide's nominal dense 8-bit number (4.5 POP/s = 8192 MAC/clk/SM at 1.86 GHz, the rate ncu shows for
-                    # UTCIMMA), and the ratio against 2 x the measured (power-capped cuBLAS) bf16 peak is reported beside it
-                    "roofline": {"bound": "tensor", "achieved": 2 * 256 * gcmp / 1e3, "peak": 4500.0,
-                                 "unit": "TOP/s", "frac": 2 * 256 * gcmp / 1e3 / 4500.0,
-                                 "frac_vs_2x_measured_bf16": 2 * 256 * gcmp / 1e3 / (2 * _bf16_peak()[0]),
-                                 "traffic": _ncu_traffic("r1_ncu_knn2_tcgen05.csv", "knn2_pair_kernel" if bestv.startswith("tcgen05_cta_pair") else "knn2_tc_kernel"),
-                                 "peak_source": "fallback: B200_PROFILING.md nominal dense 8-bit tensor peak (no 8-bit number in MEASURED_PEAKS.json; "
-                                                "bf16 " + _bf16_peak()[1] + " = %.0f TFLOP/s); ncu tensor pipe active: 71 %% single CTA (shared-memory "
-                                                "data pipe 93 %%), 77 %% CTA pair -- profiles/r1_ncu_knn2_tcgen05.csv" % _bf16_peak()[0]},
-                    "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8,
-                    "popc_kernel_frac_of_popc_peak": per_variant["popc"]["gcmp_s"] / (148 * 16 * 1.965 / 8)}
-
-    # ---------------- candidate loops (SearchByBoW / SearchForTriangulation / stereo): call latency through the C ABI
     loops = None
     if rank == 0 and world == 1 and not args.no_matching:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import matchdata
-        import oracle_lib
-        d1, d2, a1, a2, src, dst, rng = matchdata.two_views(1000, 1100, 0)
-        valid = np.ones(len(d1), np.uint8)
-        fv1, fv2 = matchdata.featvec(d1), matchdata.featvec(d2)
-        mt = orb.ORBmatcher(0.7, True, device=local)
+        loops = bench_candidate_loops(orb, synth, local)
+        _note("candidate loops done")
 
-        def timeit(fn, n=30):
-            for _ in range(3):
-                fn()
-            t0 = time.perf_counter()
-            for _ in range(n):
-                fn()
-            return (time.perf_counter() - t0) / n * 1e3
-
-        loops = {"search_by_bow_kf_f_ms": {"gpu_call": timeit(lambda: mt.SearchByBoW(d1, a1, valid, fv1, d2, a2, fv2)),
-                                           "cpu_oracle_1thread": timeit(lambda: oracle_lib.search_by_bow_kf_f(d1, a1, valid, fv1, d2, a2, fv2, 0.7, True))},
-                 "features": [len(d1), len(d2)], "note": "host arrays in/out, includes H2D/D2H; problem is tiny (~17 candidates per feature)"}
-        # frame side: undistort + bounds + grid, then SearchByProjection(Frame, local map)
-        frng = np.random.default_rng(5)
-        nf, nmp = 2000, 4000
-        fk = np.zeros(nf, orb.KP_DTYPE)
-        lv = frng.integers(0, 8, nf); sc = 1.2 ** lv
-        fk["x"] = (frng.integers(16, (640 / sc - 16).astype(int)) * sc).astype(np.float32)
-        fk["y"] = (frng.integers(16, (480 / sc - 16).astype(int)) * sc).astype(np.float32)
-        fk["octave"] = lv; fk["angle"] = frng.uniform(0, 360, nf).astype(np.float32)
-        Kc = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
-        Dc = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
-        fdesc = synth.descriptors(nf, seed=77)
-        fr = orb.FrameFeatures(fk, Kc, Dc, 640, 480, device=local)
-        mpv = np.zeros(nmp, orb.MPV_DTYPE)
-        srcf = frng.integers(0, nf, nmp)
-        mpv["proj_x"] = fr.keys_un["x"][srcf] + frng.normal(0, 2, nmp).astype(np.float32)
-        mpv["proj_y"] = fr.keys_un["y"][srcf] + frng.normal(0, 2, nmp).astype(np.float32)
-        mpv["proj_xr"] = mpv["proj_x"] - 10; mpv["view_cos"] = 0.999; mpv["level"] = fr.keys_un["octave"][srcf]
-        mpv["in_view"] = 1; mpv["obs_positive"] = 1
-        mdesc = fdesc[srcf].copy(); mdesc[:, 0] ^= frng.integers(0, 256, nmp).astype(np.uint8)
-        sfac = (1.2 ** np.arange(8)).astype(np.float32)
-        ur0 = np.full(nf, -1, np.float32); occ0 = np.zeros(nf, np.uint8)
-        loops["frame_build_ms"] = {
-            "gpu_call": timeit(lambda: orb.FrameFeatures(fk, Kc, Dc, 640, 480, device=local)),
-            "cpu_oracle_1thread": timeit(lambda: (oracle_lib.image_bounds(640, 480, Kc, Dc),
-                                                  oracle_lib.assign_grid(oracle_lib.undistort_keypoints(fk, Kc, Dc), fr.bounds)))}
-        loops["search_by_projection_frame_ms"] = {
-            "gpu_call": timeit(lambda: orb.search_by_projection_frame(fr, fdesc, ur0, occ0, sfac, mpv, mdesc, th=1.0, nnratio=0.8)),
-            "cpu_oracle_1thread": timeit(lambda: oracle_lib.search_by_projection_frame(fr.keys_un, fdesc, ur0, occ0, fr.cell_ptr, fr.cell_idx,
-                                                                                       fr.bounds, sfac, mpv, mdesc, 1.0, 0.8)),
-            "features": nf, "map_points": nmp}
+    # ---------------- BASELINE configs 2 and 3 (N = 1) ------------------------------------------------------------
+    others = {}
+    if rank == 0 and world == 1:
+        if "kitti" in want:
+            kc = CONFIGS["kitti"]
+            KB = 125                                         # the 1000-frame stream = 8 batches of 125 frames
+            pilot = bench_extraction(orb, synth, torch, D, kc, args, rank, world, local, KB, 8, 8, want_e2e=False)
+            passes = max(1, int(np.ceil(args.config_seconds * 1e3 / max(pilot["dev_ms"], 1e-3))))
+            kr = bench_extraction(orb, synth, torch, D, kc, args, rank, world, local, KB, 8 * passes, 8, tight_host_stride=True)
+            kframes = kr.pop("host_frames")
+            entry = {"workload": kc["workload"], "metric": "ORB extract frames/s @1241x376/2000kp", "value": kr["value"], "unit": "frames/s",
+                     "stream_frames": 1000, "stream_passes_timed": passes, "frames_per_batch": KB, "streams_per_gpu": args.streams,
+                     "timed_region_s": kr["timed_region_s"], "ms_per_1000_frame_stream": kr["dev_ms"] / passes,
+                     "keypoints_per_frame": kr["keypoints_per_frame"], "gpu_launches": kr["launches"], "clocks": kr["clocks"],
+                     "e2e": kr["e2e"], "roofline": roofline_of(kc, kr, KB)}
+            if not args.no_cpu:
+                fps, kind, threads, n, dt = cpu_reference_fps([kframes[0, i] for i in range(16)], args.config_cpu_seconds, kc["nfeat"])
+                entry["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                                         "sample": "%d frames of the same workload in %.1f s on %d host threads" % (n, dt, threads)}
+            others["kitti_1241x376_nf2000"] = entry
+            _note("kitti: %.0f frames/s device-resident, %.0f end to end" % (entry["value"], entry["e2e"]["value"]))
+        if "euroc" in want:
+            ec = CONFIGS["euroc"]
+            sr = bench_stereo(orb, synth, torch, ec, args, local, 64, args.config_seconds)
+            hl, hr = sr.pop("host_left"), sr.pop("host_right")
+            acc = sr.pop("stage_ms")
+            fake = {"stage_ms": acc}
+            entry = {"workload": ec["workload"], "metric": "stereo frames (pairs)/s @2x752x480/1200kp incl. ComputeStereoMatches"}
+            entry.update({k: v for k, v in sr.items() if k not in ("mbf", "mb")})
+            entry["roofline"] = roofline_of(ec, fake, 64)
+            entry["roofline"]["stage_ms_per_batch"] = {k: round(v, 4) for k, v in acc.items()}
+            if not args.no_cpu:
+                pps, kind, threads, n, dt = cpu_reference_fps([hl[0, i] for i in range(16)], args.config_cpu_seconds, ec["nfeat"],
+                                                              stereo=([hr[0, i] for i in range(16)], sr["mbf"], sr["mb"]))
+                entry["cpu_baseline"] = {"value": pps, "unit": "stereo pairs/s", "cores": threads, "kind": kind,
+                                         "sample": "%d pairs in %.1f s on %d host threads: reference extractor x2 per pair (sequential in the "
+                                                   "thread) + the oracle's ComputeStereoMatches restatement" % (n, dt, threads)}
+            others["euroc_stereo_752x480_nf1200"] = entry
+            _note("euroc: %.0f stereo pairs/s device-resident, %.0f end to end" % (entry["value"], entry["e2e"]["value"]))
 
     # ---------------- CPU baseline (rank 0, N=1 only; bounded sample) --------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        fps, kind, threads, n, dt = cpu_reference_fps([host_frames[0, i] for i in range(min(B, 16))], args.cpu_seconds)
+        frames16 = [host_frames[0, i] for i in range(min(B, 16))]
+        fps, kind, threads, n, dt = cpu_reference_fps(frames16, args.cpu_seconds, cfg["nfeat"])
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                "sample": "%d frames of the same workload in %.1f s on %d host threads (one extractor per thread)" % (n, dt, threads)}
-        fps1, _, _, n1, dt1 = cpu_reference_fps([host_frames[0, i] for i in range(min(B, 16))], 2.0, threads=1)
+        fps1, _, _, n1, dt1 = cpu_reference_fps(frames16, 2.0, cfg["nfeat"], threads=1)
         cpu["single_thread_value"] = fps1
         cpu["single_thread_ms_per_frame"] = 1e3 / max(fps1, 1e-9)
-        if matching is not None:
-            # the reference's brute-force loop (DescriptorDistance + best/second rule, ORBmatcher.cc:1647-1663, :216-225),
-            # std::thread-parallel over the queries, on a bounded sample of the same query set and map
-            import oracle_lib
-            nm_s = NM
-            q_s = np.ascontiguousarray(q); m_s = np.ascontiguousarray(m_all[:nm_s])
-            i1 = np.zeros(NQ, np.int32); d1 = np.zeros(NQ, np.int32); d2 = np.zeros(NQ, np.int32)
-            Lc = oracle_lib.lib()
-            t0 = time.perf_counter()
-            Lc.orc_knn2(q_s.ctypes.data, NQ, m_s.ctypes.data, nm_s, 0, i1.ctypes.data, d1.ctypes.data, d2.ctypes.data, threads)
-            dtm = time.perf_counter() - t0
-            matching["cpu_baseline"] = {"value": NQ * nm_s / dtm / 1e9, "unit": "Gcmp/s", "cores": threads, "kind": "port",
-                                        "sample": "2000 queries x %d map descriptors (the whole workload) in %.2f s" % (nm_s, dtm)}
+        try:
+            st = cpu_stage_comparison(frames16[:8], cfg["nfeat"])
+        except Exception as exc:      # noqa: BLE001 -- reported, the baseline itself stands
+            st = {"error": str(exc)}
+        if st and "speedup_if_cv2_primitives" in st:
+            cpu["per_stage"] = st
+            cpu["adjusted_value"] = fps * st["speedup_if_cv2_primitives"]
+        elif st:
+            cpu["per_stage"] = st
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "640x480 gray frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7 (TUM1.yaml)",
-                           "frames_per_step": B, "streams_per_gpu": n_streams, "parallelism": "replicas x%d" % world, "numa_node": numa,
-                           "l2_policy": "inputs+intermediates per step (%.0f MB) exceed the 126 MB L2; %d distinct batches cycled"
-                                        % (B * 5.6, pool),
-                           "keypoints_per_frame": kp_mean},
+        e2e = head["e2e"]
+        line = {"metric": METRIC, "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["dev_ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": headline_config(),
+                "run": {"frames_per_step": B * bps, "frames_per_batch": B, "batches_per_step": bps, "streams_per_gpu": args.streams,
+                        "parallelism": "replicas x%d" % world, "numa_node": numa, "keypoints_per_frame": head["keypoints_per_frame"],
+                        "timed_region_s": head["timed_region_s"]},
                 "roofline": roof, "cpu_baseline": cpu,
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "keypoints_downloaded": tot_kp},
-                "gpu_launches": int(launches), "clocks": clocks, "matching": matching,
-                "single_frame_latency_ms": latency_ms, "candidate_loops": loops, "keyframe_exchange": exchange}
+                "e2e": {"value": e2e["value"], "unit": "frames/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_batch"] * bps,
+                        "d2h_bytes_per_step": e2e["d2h_bytes_per_batch"] * bps, "keypoints_downloaded": e2e["keypoints_downloaded"],
+                        "timed_region_s": e2e["timed_region_s"], "copy_ceiling_frames_s": e2e["copy_ceiling_frames_s"],
+                        "copy_ceiling_gbs_per_gpu": e2e["copy_ceiling_gbs_per_gpu"],
+                        "frac_of_copy_ceiling": e2e["value"] / e2e["copy_ceiling_frames_s"]},
+                "gpu_launches": head["launches"], "clocks": head["clocks"], "matching": matching,
+                "single_frame_latency_ms": latency_ms, "candidate_loops": loops, "keyframe_exchange": exchange,
+                "configs": others or None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def bench_keyframe_exchange(orb, torch, dist, D, world, local, frames, cfg):
+    """10 key frames per agent per message (ros_mono.cc:1943-1948): the extractor's device-resident output, int16 wire
+    truncation on the device, exchanged between all ranks."""
+    import ctypes as C
+    dev = torch.device("cuda", local)
+    KF = 10
+    W, H = cfg["w"], cfg["h"]
+    ext = orb.ORBextractor(cfg["nfeat"], 1.2, 8, 20, 7, device=local, max_width=W, max_height=H, max_batch=KF)
+    cap = ext.max_keypoints(W, H)
+    d_img = torch.from_numpy(np.ascontiguousarray(frames[:KF])).to(dev)
+    kf_k = torch.empty((KF, cap, 7), dtype=torch.int32, device=dev); kf_d = torch.empty((KF, cap, 32), dtype=torch.uint8, device=dev)
+    kf_c = torch.empty((KF,), dtype=torch.int32, device=dev)
+    ext.extract_batch_device(d_img.data_ptr(), KF, W, H, W, W * H, kf_k.data_ptr(), kf_d.data_ptr(), cap, kf_c.data_ptr())
+    ext.wait()
+    L = orb.lib()
+    all_k = torch.empty((world,) + tuple(kf_k.shape), dtype=kf_k.dtype, device=dev)
+    all_d = torch.empty((world,) + tuple(kf_d.shape), dtype=kf_d.dtype, device=dev)
+    all_c = torch.empty((world,) + tuple(kf_c.shape), dtype=kf_c.dtype, device=dev)
+    cur = torch.cuda.current_stream(dev)
+
+    def exchange_step():
+        rc = L.orbw_quantize_lcm_device(C.c_void_p(kf_k.data_ptr()), C.c_void_p(kf_c.data_ptr()), KF, cap, C.c_void_p(cur.cuda_stream))
+        assert rc == 0
+        dist.all_gather_into_tensor(all_k, kf_k); dist.all_gather_into_tensor(all_d, kf_d); dist.all_gather_into_tensor(all_c, kf_c)
+
+    torch.cuda.synchronize(dev)
+    for _ in range(3):
+        exchange_step()
+    D.barrier()
+    x0 = torch.cuda.Event(enable_timing=True); x1 = torch.cuda.Event(enable_timing=True)
+    x0.record(cur)
+    for _ in range(20):
+        exchange_step()
+    x1.record(cur)
+    D.barrier()
+    xms = D.max(x0.elapsed_time(x1)) / 20
+    msg = kf_k.numel() * 4 + kf_d.numel() + kf_c.numel() * 4
+    ext.close()
+    return {"keyframes_per_agent": KF, "bytes_per_agent": msg, "ms_per_exchange": xms, "allgather_gbs": world * msg / (xms * 1e-3) / 1e9,
+            "note": "reference: one LCM UDP-multicast message of 10 key frames, descriptors as float32 (4x the bytes)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=128, help="frames per extraction launch chain")
+    ap.add_argument("--batches-per-step", type=int, default=64, help="a step = this many batches (8192 frames by default: 20 steps run > 1 s)")
     ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--configs", default="tum,kitti,euroc", help="BASELINE configs measured at N = 1 (tum is always the headline)")
+    ap.add_argument("--config-seconds", type=float, default=0.6, help="minimum timed region of the kitti / euroc objects")
+    ap.add_argument("--config-cpu-seconds", type=float, default=5.0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-matching", action="store_true")

@@ -81,6 +81,8 @@ ABI = {
     "orbm_search_for_triangulation": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _F, _F, _VP, _VP, _I, _I, _VP,
                                           _I, _VP, _I]),
     "orbm_stereo_matches": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _VP, _VP, _VP]),
+    "orbm_stereo_matches_batch_device": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _F, _F, _VP, _VP, _VP, _VP, _VP]),
+    "orbm_stereo_scratch_bytes": (_SZ, [_I, _I]),
     "orbm_distinctive_descriptors": (_I, [_VP, _VP, _I, _VP, _I]),
     "orbf_undistort_keypoints": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I]),
     "orbf_image_bounds": (_I, [_I, _I, _VP, _VP, _I, _VP, _I]),
@@ -669,3 +671,18 @@ def compute_stereo_matches(ext_left, ext_right, keys_left, desc_left, keys_right
     _check(lib().orbm_stereo_matches(ext_left._h, ext_right._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr),
                                      float(mbf), float(mb), _p(ur), _p(dep), C.byref(n)), "orbm_stereo_matches")
     return ur, dep, n.value
+
+
+def stereo_scratch_bytes(n_pairs, cap):
+    return int(lib().orbm_stereo_scratch_bytes(int(n_pairs), int(cap)))
+
+
+def compute_stereo_matches_batch_device(ext_left, ext_right, d_kl, d_dl, d_cl, d_kr, d_dr, d_cr, n_pairs, cap, mbf, mb, d_scratch,
+                                        d_u_right, d_depth, d_n_matches, stream=0):
+    """Frame::ComputeStereoMatches for a batch of stereo pairs, device-resident (all d_* are raw device addresses): the
+    outputs of two extract_batch_device/_async calls in, mvuRight / mvDepth [n_pairs][cap] and the match counts out."""
+    _check(lib().orbm_stereo_matches_batch_device(ext_left._h, ext_right._h, C.c_void_p(d_kl), C.c_void_p(d_dl), C.c_void_p(d_cl),
+                                                  C.c_void_p(d_kr), C.c_void_p(d_dr), C.c_void_p(d_cr), int(n_pairs), int(cap),
+                                                  float(mbf), float(mb), C.c_void_p(d_scratch), C.c_void_p(d_u_right),
+                                                  C.c_void_p(d_depth), C.c_void_p(d_n_matches), C.c_void_p(stream)),
+           "orbm_stereo_matches_batch_device")

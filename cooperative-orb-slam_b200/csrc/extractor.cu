@@ -43,6 +43,8 @@ struct orbx_handle_s {
     std::vector<int> nfeat;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[10] = {};
+    cudaEvent_t ev_done = nullptr;   // "last extraction enqueued on `stream`" for consumers on other streams
+    float* d_tables = nullptr;       // [2][kMaxLevels]: mvScaleFactor, mvInvScaleFactor (device copy for the batched stereo search)
     bool profiling = false;
     float stage_ms[9] = {};
     bool timing_pending = false;
@@ -386,7 +388,14 @@ int orbx_create(const orbx_params_t* p, int max_width, int max_height, int max_b
         return ORB_ERR_CUDA;
     }
     if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete h; *out = nullptr; return ORB_ERR_CUDA; }
-    for (auto& e : h->ev) if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) { *out = nullptr; return ORB_ERR_CUDA; }
+    for (auto& e : h->ev) if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) { orbx_destroy(h); *out = nullptr; return ORB_ERR_CUDA; }
+    {
+        float tab[2 * kMaxLevels] = {};
+        for (int i = 0; i < L; i++) { tab[i] = h->sf[i]; tab[kMaxLevels + i] = h->isf[i]; }
+        if (!cuda_ok(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming), "cudaEventCreate") ||
+            !cuda_ok(cudaMalloc((void**)&h->d_tables, sizeof(tab)), "cudaMalloc") ||
+            !cuda_ok(cudaMemcpy(h->d_tables, tab, sizeof(tab), cudaMemcpyHostToDevice), "cudaMemcpy")) { orbx_destroy(h); *out = nullptr; return ORB_ERR_CUDA; }
+    }
     if (max_width > 0 && max_height > 0 && max_batch > 0) {
         int rc = ensure_size(h, max_width, max_height, max_batch);
         if (rc) { orbx_destroy(h); *out = nullptr; return rc; }
@@ -400,11 +409,13 @@ int orbx_destroy(orbx_handle_t h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* dev[] = {h->d_geom, h->d_cells, h->d_xtab, h->d_ytab, h->d_in, h->d_pyr, h->d_blur, h->d_score, h->d_cand,
-                   h->d_scratch, h->d_node, h->d_cell_count, h->d_level_raw, h->d_sel, h->d_level_count, h->d_kps, h->d_desc, h->d_counts};
+                   h->d_scratch, h->d_node, h->d_cell_count, h->d_level_raw, h->d_sel, h->d_level_count, h->d_kps, h->d_desc, h->d_counts,
+                   h->d_tables};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {h->h_in, h->h_kps, h->h_desc, h->h_counts};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return ORB_OK;
@@ -537,7 +548,10 @@ int orbx_extract_batch_async(orbx_handle_t h, const uint8_t* images, int n_frame
                 memcpy(h->h_in + f * dev_frame + (size_t)y * fl.in_pitch, images + f * frame_stride + (size_t)y * row_stride, width);
         ORB_CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, (size_t)n_frames * dev_frame, cudaMemcpyHostToDevice, s));
     }
-    if ((rc = enqueue_kernels(h, h->d_in, dev_frame, n_frames, h->d_kps, h->d_desc, h->d_counts, cap))) return rc;
+    if ((rc = enqueue_kernels(h, h->d_in, dev_frame, n_frames, h->d_kps, h->d_desc, h->d_counts, cap))) {
+        cudaStreamSynchronize(h->stream);   // the upload may still be reading the pinned staging buffer
+        return rc;
+    }
     // ---- download
     const size_t kb = (size_t)n_frames * cap * sizeof(orb_keypoint_t), db = (size_t)n_frames * cap * 32;
     const bool direct = is_pinned(kps) && is_pinned(desc) && is_pinned(counts);
@@ -563,9 +577,10 @@ int orbx_extract_batch_async(orbx_handle_t h, const uint8_t* images, int n_frame
 int orbx_wait(orbx_handle_t h) {
     if (!h) return ORB_ERR_ARG;
     ORB_CUDA_TRY(cudaSetDevice(h->device));
+    const bool was_pending = h->pending;
+    h->pending = false;     // also when the synchronisation fails: the handle must not stay wedged ("previous call not waited for")
     ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (!h->pending) return ORB_OK;
-    h->pending = false;
+    if (!was_pending) return ORB_OK;
     int rc = ORB_OK;
     const int cap = h->p_cap;
     const int32_t* cnt = h->p_direct ? h->p_counts : h->h_counts;
@@ -730,5 +745,23 @@ extern "C" int orbx_internal_view(orbx_handle_t h, const uint8_t** d_pyr, const 
     *d_pyr = h->d_pyr; *d_geom = h->d_geom; *h_geom = h->geom.data(); *fl = h->fl; *device = h->device;
     *sf = h->sf.data(); *isf = h->isf.data();
     *d_level0 = h->last_in; *level0_pitch = h->last_in_pitch;
+    return ORB_OK;
+}
+
+// Internal (not in orbcuda.h): the same for a batch, stream-ordered instead of synchronising -- `consumer` is made to
+// wait for everything enqueued on the handle's stream so far.  d_tables = [mvScaleFactor | mvInvScaleFactor] on the device.
+extern "C" int orbx_internal_view_batch(orbx_handle_t h, const uint8_t** d_pyr, const orbcuda::LevelGeom** d_geom,
+                                        const orbcuda::LevelGeom** h_geom, orbcuda::FrameLayout* fl, int* device,
+                                        const float** d_tables, const uint8_t** d_level0, int* level0_pitch,
+                                        size_t* level0_stride, int* n_frames, void* consumer) {
+    if (!h || h->last_frames < 1) return ORB_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return ORB_ERR_CUDA;
+    if ((cudaStream_t)consumer != h->stream) {
+        if (cudaEventRecord(h->ev_done, h->stream) != cudaSuccess || cudaStreamWaitEvent((cudaStream_t)consumer, h->ev_done, 0) != cudaSuccess)
+            return ORB_ERR_CUDA;
+    }
+    *d_pyr = h->d_pyr; *d_geom = h->d_geom; *h_geom = h->geom.data(); *fl = h->fl; *device = h->device;
+    *d_tables = h->d_tables; *d_level0 = h->last_in; *level0_pitch = h->last_in_pitch; *level0_stride = h->last_in_stride;
+    *n_frames = h->last_frames;
     return ORB_OK;
 }

@@ -151,15 +151,25 @@ __global__ void __launch_bounds__(128) distinctive_kernel(const uint4* __restric
 
 struct StereoOut { float u_right, depth; int sad; int ok; };
 
-// One warp per left key point (Frame::ComputeStereoMatches :504-628).
+// One warp per left key point (Frame::ComputeStereoMatches :504-628).  blockIdx.y = stereo pair of a batch: the
+// key point / descriptor arrays advance by `cap` entries per pair, the pyramids by one frame block, and the per-pair
+// counts come from cntL / cntR (device arrays; nullptr for the single-pair call, which passes nl / nr).
 __global__ void __launch_bounds__(128) stereo_kernel(const orb_keypoint_t* __restrict__ kl, const uint4* __restrict__ dl, int nl,
                                                      const orb_keypoint_t* __restrict__ kr, const uint4* __restrict__ dr, int nr,
+                                                     const int32_t* __restrict__ cntL, const int32_t* __restrict__ cntR, int cap,
                                                      const float* __restrict__ sfs, const float* __restrict__ isfs,
-                                                     const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
+                                                     const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR, size_t pyr_stride,
                                                      const uint8_t* __restrict__ l0L, const uint8_t* __restrict__ l0R, int l0_pitch,
+                                                     size_t l0_strideL, size_t l0_strideR,
                                                      const LevelGeom* __restrict__ geom, int n_rows, float mbf, float max_d,
                                                      StereoOut* __restrict__ out) {
     const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    {
+        const size_t f = blockIdx.y;
+        if (cntL) { nl = min(cntL[f], cap); nr = min(cntR[f], cap); }
+        kl += f * cap; dl += 2 * f * cap; kr += f * cap; dr += 2 * f * cap; out += f * cap;
+        pyrL += f * pyr_stride; pyrR += f * pyr_stride; l0L += f * l0_strideL; l0R += f * l0_strideR;
+    }
     if (iL >= nl) return;
     StereoOut o = {-1.f, -1.f, 0, 0};
     const orb_keypoint_t kpL = kl[iL];
@@ -243,6 +253,51 @@ __global__ void __launch_bounds__(128) stereo_kernel(const orb_keypoint_t* __res
     if (lane == 0) out[iL] = o;
 }
 
+
+// Outlier cut of Frame::ComputeStereoMatches (:630-644) for a batch, one CTA per stereo pair: the median is the
+// element of rank size/2 of the (SAD, index)-sorted list of accepted matches, every match with SAD >= 1.5*1.4*median
+// is dropped (the reference walks the sorted list from the back and stops at the first SAD below the limit).  The rank
+// is found by counting (n <= a few thousand).  Writes mvuRight / mvDepth (-1 where no match) and the kept count.
+__global__ void __launch_bounds__(256) stereo_filter_kernel(const StereoOut* __restrict__ res, const int32_t* __restrict__ cntL, int cap,
+                                                            float* __restrict__ u_right, float* __restrict__ depth,
+                                                            int32_t* __restrict__ n_matches) {
+    const size_t f = blockIdx.x;
+    res += f * cap; u_right += f * cap; depth += f * cap;
+    const int n = min(cntL[f], cap);
+    __shared__ int s_ok, s_median, s_kept;
+    if (threadIdx.x == 0) { s_ok = 0; s_median = -1; s_kept = 0; }
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine += res[i].ok;
+    if (mine) atomicAdd(&s_ok, mine);
+    __syncthreads();
+    const int n_ok = s_ok;
+    if (n_ok > 0) {
+        const int k = n_ok / 2;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (!res[i].ok) continue;
+            const int si = res[i].sad;
+            int rank = 0;
+            for (int j = 0; j < n; j++) {
+                const StereoOut o = res[j];
+                rank += o.ok && (o.sad < si || (o.sad == si && j < i));
+            }
+            if (rank == k) s_median = si;
+        }
+    }
+    __syncthreads();
+    const float th_dist = 1.5f * 1.4f * (float)s_median;
+    int kept = 0;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        float u = -1.f, d = -1.f;
+        if (i < n && res[i].ok && (float)res[i].sad < th_dist) { u = res[i].u_right; d = res[i].depth; kept++; }
+        u_right[i] = u; depth[i] = d;
+    }
+    if (kept) atomicAdd(&s_kept, kept);
+    __syncthreads();
+    if (threadIdx.x == 0) n_matches[f] = s_kept;
+}
+
 // ---- host helpers -----------------------------------------------------------------------------------
 static void shared_nodes(const orbm_featvec_t* a, const orbm_featvec_t* b, std::vector<NodePair>& out) {
     int i = 0, j = 0;   // merge walk of two sorted maps (R21 ORBmatcher.cc:175-263)
@@ -319,6 +374,10 @@ using namespace orbcuda;
 extern "C" int orbx_internal_view(orbx_handle_t h, const uint8_t** d_pyr, const orbcuda::LevelGeom** d_geom,
                                   const orbcuda::LevelGeom** h_geom, orbcuda::FrameLayout* fl, int* device,
                                   const float** sf, const float** isf, const uint8_t** d_level0, int* level0_pitch);
+extern "C" int orbx_internal_view_batch(orbx_handle_t h, const uint8_t** d_pyr, const orbcuda::LevelGeom** d_geom,
+                                        const orbcuda::LevelGeom** h_geom, orbcuda::FrameLayout* fl, int* device,
+                                        const float** d_tables, const uint8_t** d_level0, int* level0_pitch,
+                                        size_t* level0_stride, int* n_frames, void* consumer);
 
 extern "C" {
 
@@ -496,8 +555,8 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
         const float* d_isf = (const float*)cx.upload(isf, (size_t)fll.nlevels * 4);
         StereoOut* d_out = (StereoOut*)cx.dalloc((size_t)n_left * sizeof(StereoOut));
         if (!d_kl || !d_dl || !d_kr || !d_dr || !d_sf || !d_isf || !d_out) return ORB_ERR_CUDA;
-        stereo_kernel<<<(n_left * 32 + 127) / 128, 128, 0, cx.stream>>>(d_kl, d_dl, n_left, d_kr, d_dr, n_right, d_sf, d_isf, pl, pr, l0l, l0r,
-                                                                      l0pl, dgl, hgl[0].h, mbf, max_d, d_out);
+        stereo_kernel<<<(n_left * 32 + 127) / 128, 128, 0, cx.stream>>>(d_kl, d_dl, n_left, d_kr, d_dr, n_right, nullptr, nullptr, 0, d_sf, d_isf,
+                                                                      pl, pr, 0, l0l, l0r, l0pl, 0, 0, dgl, hgl[0].h, mbf, max_d, d_out);
         ORB_CUDA_TRY(cudaGetLastError());
         if (!cx.download(res.data(), d_out, (size_t)n_left * sizeof(StereoOut)) || !cx.finish()) return ORB_ERR_CUDA;
     }
@@ -518,4 +577,38 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
     return ORB_OK;
 }
 
+int orbm_stereo_matches_batch_device(orbx_handle_t hl, orbx_handle_t hr, const void* d_keys_left, const uint8_t* d_desc_left,
+                                     const int32_t* d_counts_left, const void* d_keys_right, const uint8_t* d_desc_right,
+                                     const int32_t* d_counts_right, int n_pairs, int cap, float mbf, float mb, void* d_scratch,
+                                     float* d_u_right, float* d_depth, int32_t* d_n_matches, void* stream) {
+    if (!hl || !hr || n_pairs < 1 || cap < 1 || cap >= (1 << 20) || !d_keys_left || !d_desc_left || !d_counts_left || !d_keys_right ||
+        !d_desc_right || !d_counts_right || !d_scratch || !d_u_right || !d_depth || !d_n_matches) {
+        set_error("orbm_stereo_matches_batch_device: bad arguments");
+        return ORB_ERR_ARG;
+    }
+    const uint8_t *pl, *pr; const LevelGeom *dgl, *dgr, *hgl, *hgr; FrameLayout fll, flr; int devl, devr, nfl, nfr;
+    const float *d_sfl, *d_sfr; const uint8_t *l0l, *l0r; int l0pl, l0pr; size_t l0sl, l0sr;
+    if (orbx_internal_view_batch(hl, &pl, &dgl, &hgl, &fll, &devl, &d_sfl, &l0l, &l0pl, &l0sl, &nfl, stream) ||
+        orbx_internal_view_batch(hr, &pr, &dgr, &hgr, &flr, &devr, &d_sfr, &l0r, &l0pr, &l0sr, &nfr, stream) ||
+        !pl || !pr || !l0l || !l0r || l0pl != l0pr || devl != devr || fll.width != flr.width || fll.height != flr.height ||
+        fll.nlevels != flr.nlevels || nfl < n_pairs || nfr < n_pairs) {
+        set_error("orbm_stereo_matches_batch_device: the two extractors must hold a batch of >= n_pairs same-size images on one device");
+        return ORB_ERR_ARG;
+    }
+    ORB_CUDA_TRY(cudaSetDevice(devl));
+    cudaStream_t s = (cudaStream_t)stream;
+    StereoOut* d_res = (StereoOut*)d_scratch;
+    const float max_d = mbf / mb;   // maxD = mbf/minZ, minZ = mb  (:501-503)
+    stereo_kernel<<<dim3((cap * 32 + 127) / 128, n_pairs), 128, 0, s>>>(
+        (const orb_keypoint_t*)d_keys_left, (const uint4*)d_desc_left, 0, (const orb_keypoint_t*)d_keys_right, (const uint4*)d_desc_right, 0,
+        d_counts_left, d_counts_right, cap, d_sfl, d_sfl + kMaxLevels, pl, pr, (size_t)fll.pyr_bytes, l0l, l0r, l0pl, l0sl, l0sr, dgl, hgl[0].h,
+        mbf, max_d, d_res);
+    stereo_filter_kernel<<<n_pairs, 256, 0, s>>>(d_res, d_counts_left, cap, d_u_right, d_depth, d_n_matches);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+size_t orbm_stereo_scratch_bytes(int n_pairs, int cap) { return (size_t)std::max(n_pairs, 0) * (size_t)std::max(cap, 0) * sizeof(StereoOut); }
+
 }  // extern "C"
+

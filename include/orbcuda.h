@@ -224,6 +224,20 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
                         const uint8_t* desc_right, int n_right, float mbf, float mb, float* u_right,
                         float* depth, int* n_matches);
 
+/* The same for a batch of stereo pairs without leaving the device (two extractors per stereo frame, R21/src/Frame.cc:80-83,
+ * then ComputeStereoMatches :471-645, outlier cut :630-644 included).  hl/hr hold the pyramids of their last
+ * orbx_extract_batch_device/_async call (>= n_pairs frames); d_keys_* / d_desc_* / d_counts_* are the device outputs of
+ * those calls ([n_pairs][cap] layout).  d_scratch: orbm_stereo_scratch_bytes(n_pairs, cap) bytes of device memory.
+ * d_u_right / d_depth: [n_pairs][cap] floats (-1 where a key point has no match), d_n_matches: [n_pairs].  Enqueued on
+ * `stream`, which is made to wait for both extractors' streams; nothing is synchronised. */
+int orbm_stereo_matches_batch_device(orbx_handle_t hl, orbx_handle_t hr, const void* d_keys_left,
+                                     const uint8_t* d_desc_left, const int32_t* d_counts_left,
+                                     const void* d_keys_right, const uint8_t* d_desc_right,
+                                     const int32_t* d_counts_right, int n_pairs, int cap, float mbf, float mb,
+                                     void* d_scratch, float* d_u_right, float* d_depth, int32_t* d_n_matches,
+                                     void* stream);
+size_t orbm_stereo_scratch_bytes(int n_pairs, int cap);
+
 /* ---------------------------------------------------------------- frame (the steps after extraction) ---- */
 #define ORBF_GRID_COLS 64   /* FRAME_GRID_COLS, R21/include/Frame.h:37 */
 #define ORBF_GRID_ROWS 48   /* FRAME_GRID_ROWS, R21/include/Frame.h:36 */

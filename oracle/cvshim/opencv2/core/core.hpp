@@ -19,10 +19,20 @@
 #include <new>
 #include <utility>
 #include <vector>
+#include <chrono>
 
 #include <sys/mman.h>
 
 #include "orb_oracle.h"
+
+// Per-thread time spent inside the shim primitives (seconds): [0] resize, [1] copyMakeBorder, [2] GaussianBlur, [3] FAST.
+// bench.py reads them through orbref_stage_times() to time cv2's own primitives beside the shim's.
+inline double* cvshim_stage_acc() { static thread_local double acc[4] = {0, 0, 0, 0}; return acc; }
+struct CvshimStageTimer {
+    int k; std::chrono::steady_clock::time_point t0;
+    explicit CvshimStageTimer(int kk) : k(kk), t0(std::chrono::steady_clock::now()) {}
+    ~CvshimStageTimer() { cvshim_stage_acc()[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Canonical tie-break for DistributeOctTree's sort of (size, ExtractorNode*) pairs

@@ -5,6 +5,7 @@
 namespace cv {
 // cv::FAST(image, keypoints, threshold, nonmaxSuppression) -- TYPE_9_16 (R21 ORBextractor.cc:809-815)
 inline void FAST(InputArray _img, std::vector<KeyPoint>& keypoints, int threshold, bool nms = true) {
+    CvshimStageTimer timer(3);
     Mat img = _img.getMat();
     keypoints.clear();
     if (img.cols < 7 || img.rows < 7) return;

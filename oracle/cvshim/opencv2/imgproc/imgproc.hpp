@@ -6,6 +6,7 @@ namespace cv {
 // cv::resize, INTER_LINEAR, CV_8UC1 only (R21 ORBextractor.cc:1120)
 inline void resize(InputArray _src, OutputArray _dst, Size dsize, double = 0, double = 0, int interp = INTER_LINEAR) {
     assert(interp == INTER_LINEAR);
+    CvshimStageTimer timer(0);
     (void)interp;
     Mat src = _src.getMat();
     _dst.create(dsize, CV_8UC1);
@@ -16,6 +17,7 @@ inline void resize(InputArray _src, OutputArray _dst, Size dsize, double = 0, do
 // call on a sub-view would read the parent's pixels in OpenCV; the shim always isolates.
 inline void copyMakeBorder(InputArray _src, OutputArray _dst, int top, int bottom, int left, int right, int type) {
     assert((type & ~BORDER_ISOLATED) == BORDER_REFLECT_101);
+    CvshimStageTimer timer(1);
     (void)type;
     Mat src = _src.getMat();
     _dst.create(src.rows + top + bottom, src.cols + left + right, CV_8UC1);
@@ -25,6 +27,7 @@ inline void copyMakeBorder(InputArray _src, OutputArray _dst, int top, int botto
 // cv::GaussianBlur, 7x7 sigma 2 BORDER_REFLECT_101 only (R21 :1086)
 inline void GaussianBlur(InputArray _src, OutputArray _dst, Size ksize, double sx, double sy = 0, int border = BORDER_DEFAULT) {
     assert(ksize.width == 7 && ksize.height == 7 && sx == 2 && sy == 2 && border == BORDER_REFLECT_101);
+    CvshimStageTimer timer(2);
     (void)ksize; (void)sx; (void)sy; (void)border;
     Mat src = _src.getMat();
     _dst.create(src.rows, src.cols, CV_8UC1);

@@ -55,4 +55,10 @@ int orbref_get_pyramid(void* h, int level, int with_border, uint8_t* dst, size_t
     return 0;
 }
 
+// seconds the calling thread has spent in the shim's resize / copyMakeBorder / GaussianBlur / FAST since the last reset
+void orbref_stage_times(double* out4, int reset) {
+    double* acc = cvshim_stage_acc();
+    for (int i = 0; i < 4; i++) { out4[i] = acc[i]; if (reset) acc[i] = 0; }
+}
+
 }  // extern "C"

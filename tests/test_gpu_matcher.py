@@ -137,6 +137,45 @@ def test_stereo_matches(orb, oracle, synth, seed):
     assert n0 == 0 and (ur0 == -1).all()
 
 
+def test_stereo_matches_batch_device(orb, oracle, synth):
+    """Batch form (two extractors per stereo frame, Frame.cc:80-83, then ComputeStereoMatches with its outlier cut, all
+    on the device): every pair must equal the oracle's per-pair result."""
+    import torch
+    B, W, H = 5, 752, 480
+    pairs = [synth.stereo_pair(s, W, H) for s in range(B)]
+    pairs[3] = (pairs[3][0], np.full((H, W), 90, np.uint8))     # a right image without key points: no matches for this pair
+    left = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda(); right = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+    el = orb.ORBextractor(1200, 1.2, 8, 20, 7); er = orb.ORBextractor(1200, 1.2, 8, 20, 7)
+    cap = el.max_keypoints(W, H)
+    mk = lambda: (torch.zeros((B, cap, 7), dtype=torch.int32, device="cuda"), torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda"),
+                  torch.zeros((B,), dtype=torch.int32, device="cuda"))
+    kl, dl, cl = mk(); kr, dr, cr = mk()
+    el.extract_batch_device(left.data_ptr(), B, W, H, W, W * H, kl.data_ptr(), dl.data_ptr(), cap, cl.data_ptr())
+    er.extract_batch_device(right.data_ptr(), B, W, H, W, W * H, kr.data_ptr(), dr.data_ptr(), cap, cr.data_ptr())
+    scratch = torch.empty(orb.stereo_scratch_bytes(B, cap), dtype=torch.uint8, device="cuda")
+    ur = torch.zeros((B, cap), dtype=torch.float32, device="cuda"); dep = torch.zeros_like(ur)
+    nm = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    mbf, fx = 40.0, 458.0
+    st = torch.cuda.Stream()
+    for _ in range(2):      # twice: the call is stream-ordered and must be repeatable
+        orb.compute_stereo_matches_batch_device(el, er, kl.data_ptr(), dl.data_ptr(), cl.data_ptr(), kr.data_ptr(), dr.data_ptr(),
+                                                cr.data_ptr(), B, cap, mbf, mbf / fx, scratch.data_ptr(), ur.data_ptr(), dep.data_ptr(),
+                                                nm.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    ur = ur.cpu().numpy(); dep = dep.cpu().numpy(); nm = nm.cpu().numpy(); cl = cl.cpu().numpy()
+    total = 0
+    for f in range(B):
+        ol = oracle.OracleExtractor(1200, trig_mode=1); orr = oracle.OracleExtractor(1200, trig_mode=1)
+        okl, odl = ol.extract(pairs[f][0]); okr, odr = orr.extract(pairs[f][1])
+        assert cl[f] == len(okl)
+        our, odep, on = oracle.stereo_matches(okl, odl, okr, odr, ol, orr, mbf, mbf / fx)
+        assert nm[f] == on, (f, nm[f], on)
+        assert np.array_equal(ur[f, :len(okl)], our) and np.array_equal(dep[f, :len(okl)], odep)
+        assert (ur[f, len(okl):] == -1).all()
+        total += on
+    assert nm[3] == 0 and total > 400
+
+
 def test_distinctive_descriptors(orb, oracle):
     """MapPoint::ComputeDistinctiveDescriptors batched: least-median descriptor per map point."""
     rng = np.random.default_rng(42)
