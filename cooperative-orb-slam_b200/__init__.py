@@ -95,9 +95,9 @@ ABI = {
                                                  _VP, _VP, _VP, _I]),
     "orbm_search_by_projection_keyframe": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _I,
                                                _VP, _VP, _VP, _I]),
-    "orbm_search_by_projection_sim3": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _VP, _VP, _VP, _I]),
+    "orbm_search_by_projection_sim3": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _I, _VP, _VP, _VP, _VP, _I]),
     "orbm_search_for_initialization": (_I, [_VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _F, _I, _I, _VP, _VP, _I]),
-    "orbm_window_best_match": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _VP, _VP, _I]),
+    "orbm_window_best_match": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _VP, _VP, _VP, _I]),
     "orbv_create": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "orbv_destroy": (_I, [_VP]),
     "orbv_transform": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
@@ -542,8 +542,10 @@ def search_by_projection_keyframe(frame, desc_f, occupied, scale_factors, points
     return fp[:nf], pf[:len(pts)], n.value
 
 
-def search_by_projection_sim3(frame, desc_f, occupied, scale_factors, points, desc_pts, th, th_low=50):
-    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (R21/src/ORBmatcher.cc:290-403)."""
+def search_by_projection_sim3(frame, desc_f, occupied, scale_factors, points, desc_pts, th, th_low=50, grid_origin=None):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (R21/src/ORBmatcher.cc:290-403).  grid_origin =
+    (float(pKF.mnMinX), float(pKF.mnMinY)): the key frame's integer-truncated bounds (None: the frame's float bounds)."""
+    go = None if grid_origin is None else np.ascontiguousarray(grid_origin, np.float32)
     df = np.ascontiguousarray(desc_f, np.uint8); occ = np.ascontiguousarray(occupied, np.uint8)
     sf = np.ascontiguousarray(scale_factors, np.float32)
     pts = np.ascontiguousarray(points, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
@@ -551,7 +553,8 @@ def search_by_projection_sim3(frame, desc_f, occupied, scale_factors, points, de
     fp = np.zeros(max(nf, 1), np.int32); pf = np.zeros(max(len(pts), 1), np.int32); n = C.c_int(0)
     _check(lib().orbm_search_by_projection_sim3(_p(frame.keys_un), _p(df), _p(occ), nf, _p(frame.cell_ptr), _p(frame.cell_idx),
                                                 _p(frame.bounds), _p(sf), len(sf), _p(pts), _p(dp), len(pts), float(th), int(th_low),
-                                                _p(fp), _p(pf), C.byref(n), frame.device), "orbm_search_by_projection_sim3")
+                                                _p(fp), _p(pf), C.byref(n), None if go is None else _p(go), frame.device),
+           "orbm_search_by_projection_sim3")
     return fp[:nf], pf[:len(pts)], n.value
 
 
@@ -569,7 +572,7 @@ def search_for_initialization(keys1_un, desc1, frame2, desc2, prev_matched, wind
     return m12[:len(k1)], xy, n.value
 
 
-def window_best_match(frame, desc_f, scale_factors, points, desc_pts, th, u_right=None, inv_level_sigma2=None):
+def window_best_match(frame, desc_f, scale_factors, points, desc_pts, th, u_right=None, inv_level_sigma2=None, grid_origin=None):
     """The window search of ORBmatcher::Fuse x2 and SearchBySim3 (R21/src/ORBmatcher.cc:825-1326): per projected point the best
     feature of levels [l-1, l]; inv_level_sigma2 (+ u_right) enables the chi-square gates of Fuse :905-931.
     -> (best_idx, best_dist)."""
@@ -577,11 +580,13 @@ def window_best_match(frame, desc_f, scale_factors, points, desc_pts, th, u_righ
     pts = np.ascontiguousarray(points, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
     ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
     sg = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+    go = None if grid_origin is None else np.ascontiguousarray(grid_origin, np.float32)
     nf = len(frame.keys_un)
     bi = np.zeros(max(len(pts), 1), np.int32); bd = np.zeros(max(len(pts), 1), np.int32)
     _check(lib().orbm_window_best_match(_p(frame.keys_un), _p(df), None if ur is None else _p(ur), nf, _p(frame.cell_ptr),
                                         _p(frame.cell_idx), _p(frame.bounds), _p(sf), None if sg is None else _p(sg), len(sf), _p(pts),
-                                        _p(dp), len(pts), float(th), _p(bi), _p(bd), frame.device), "orbm_window_best_match")
+                                        _p(dp), len(pts), float(th), _p(bi), _p(bd), None if go is None else _p(go), frame.device),
+           "orbm_window_best_match")
     return bi[:len(pts)], bd[:len(pts)]
 
 

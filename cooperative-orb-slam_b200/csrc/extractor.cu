@@ -65,6 +65,7 @@ struct orbx_handle_s {
     // per-batch device buffers (grown on demand)
     int batch_cap = 0;
     uint8_t* d_in = nullptr; size_t cap_in = 0;
+    uint8_t* d_raw = nullptr; size_t cap_raw = 0;     // caller-strided upload, repacked into d_in on the device
     uint8_t* d_pyr = nullptr; size_t cap_pyr = 0;
     uint8_t* d_blur = nullptr; size_t cap_blur = 0;
     uint8_t* d_score = nullptr; size_t cap_score = 0;
@@ -410,7 +411,7 @@ int orbx_destroy(orbx_handle_t h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* dev[] = {h->d_geom, h->d_cells, h->d_xtab, h->d_ytab, h->d_in, h->d_pyr, h->d_blur, h->d_score, h->d_cand,
                    h->d_scratch, h->d_node, h->d_cell_count, h->d_level_raw, h->d_sel, h->d_level_count, h->d_kps, h->d_desc, h->d_counts,
-                   h->d_tables};
+                   h->d_tables, h->d_raw};
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {h->h_in, h->h_kps, h->h_desc, h->h_counts};
     for (void* p : host) if (p) cudaFreeHost(p);
@@ -496,10 +497,8 @@ int orbx_extract_batch_device(orbx_handle_t h, const uint8_t* d_images, int n_fr
     if ((row_stride & 3) || (frame_stride & 3) || (reinterpret_cast<uintptr_t>(d_images) & 3)) {
         // unaligned user layout: repack into the handle's own input buffer
         if ((rc = grow_dev(h->d_in, h->cap_in, (size_t)n_frames * h->fl.in_pitch * height))) return rc;
-        for (int f = 0; f < n_frames; f++)
-            ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + (size_t)f * h->fl.in_pitch * height, h->fl.in_pitch,
-                                           d_images + f * frame_stride, row_stride, width, height,
-                                           cudaMemcpyDeviceToDevice, h->stream));
+        h->launches += launch_repack(d_images, row_stride, frame_stride, h->d_in, h->fl.in_pitch, (size_t)h->fl.in_pitch * height, width, height,
+                                     n_frames, h->stream);
         src = h->d_in; fstride = (size_t)h->fl.in_pitch * height; pitch = h->fl.in_pitch;
     }
     const int saved = h->fl.in_pitch;
@@ -538,9 +537,18 @@ int orbx_extract_batch_async(orbx_handle_t h, const uint8_t* images, int n_frame
     if (in_pinned && row_stride == (size_t)fl.in_pitch && frame_stride == dev_frame) {
         ORB_CUDA_TRY(cudaMemcpyAsync(h->d_in, images, (size_t)n_frames * dev_frame, cudaMemcpyHostToDevice, s));
     } else if (in_pinned) {
-        for (int f = 0; f < n_frames; f++)
-            ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + f * dev_frame, fl.in_pitch, images + f * frame_stride, row_stride, width,
-                                           height, cudaMemcpyHostToDevice, s));
+        // caller's own strides (e.g. a tight 1241-byte row): ONE copy of the spanned block, rows re-pitched on the device
+        // (a cudaMemcpy2DAsync per frame from an unaligned pitch ran at a fifth of the link rate)
+        const size_t span = (size_t)(n_frames - 1) * frame_stride + (size_t)(height - 1) * row_stride + width;
+        if (frame_stride >= row_stride * (size_t)(height - 1) + width && span <= 2 * (size_t)n_frames * width * height + 4096) {
+            if ((rc = grow_dev(h->d_raw, h->cap_raw, span))) return rc;
+            ORB_CUDA_TRY(cudaMemcpyAsync(h->d_raw, images, span, cudaMemcpyHostToDevice, s));
+            h->launches += launch_repack(h->d_raw, row_stride, frame_stride, h->d_in, fl.in_pitch, dev_frame, width, height, n_frames, s);
+        } else {
+            for (int f = 0; f < n_frames; f++)
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(h->d_in + f * dev_frame, fl.in_pitch, images + f * frame_stride, row_stride, width,
+                                               height, cudaMemcpyHostToDevice, s));
+        }
     } else {
         if ((rc = grow_host(h->h_in, h->cap_h_in, (size_t)n_frames * dev_frame))) return rc;
         for (int f = 0; f < n_frames; f++)

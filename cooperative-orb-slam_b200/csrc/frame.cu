@@ -454,11 +454,12 @@ __global__ void __launch_bounds__(1024) init_search_kernel(const orb_keypoint_t*
     if (tid == 0) *out_nmatches = s_matches;
 }
 
-static GridParams make_grid_params(const float* bounds);
+static GridParams make_grid_params(const float* bounds, const float* origin = nullptr);
 
 // uploads the frame and the windows, runs the search, downloads feature -> point, point -> feature and the count
 static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right, const uint8_t* occupied,
-                             int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const std::vector<ProjWindow>& wins,
+                             int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* origin,
+                             const std::vector<ProjWindow>& wins,
                              const uint8_t* desc_p, float nnratio, int threshold, int32_t* out_feature_point, int32_t* out_point_feature,
                              int* n_matches, int device) {
     const int n_p = (int)wins.size();
@@ -489,7 +490,7 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
                    cuda_ok(cudaFuncSetAttribute(window_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small), "cudaFuncSetAttribute");
         })) return ORB_ERR_CUDA;
     const size_t smem = staged ? (size_t)n_f * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16 : (size_t)n_f * 5 + 16;
-    const GridParams g = make_grid_params(bounds);
+    const GridParams g = make_grid_params(bounds, origin);
 #define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_nm)
     if (ratio) { if (staged) ORB_LAUNCH_WS(true, true); else ORB_LAUNCH_WS(true, false); }
     else { if (staged) ORB_LAUNCH_WS(false, true); else ORB_LAUNCH_WS(false, false); }
@@ -541,9 +542,11 @@ static bool make_undistort_params(const float* K, const float* dist, int ndist, 
     return true;
 }
 
-static GridParams make_grid_params(const float* bounds) {
+// origin: a KeyFrame looks its grid up from integer-truncated bounds (R21/include/KeyFrame.h: const int mnMinX, mnMinY;
+// KeyFrame.cc:575-589) while the cell size is still the Frame's float one (mfGridElementWidthInv is copied, KeyFrame.cc:33)
+static GridParams make_grid_params(const float* bounds, const float* origin) {
     GridParams g;
-    g.minx = bounds[0]; g.miny = bounds[2];
+    g.minx = origin ? origin[0] : bounds[0]; g.miny = origin ? origin[1] : bounds[2];
     g.winv = (float)kGridCols / (float)(bounds[1] - bounds[0]);      // Frame.cc:216
     g.hinv = (float)kGridRows / (float)(bounds[3] - bounds[2]);      // :217
     return g;
@@ -702,12 +705,12 @@ int orbm_search_by_projection_frame(const orb_keypoint_t* kps_un, const uint8_t*
     for (int f = 0; f < n_f; f++) out_feature_point[f] = -1;
     for (int i = 0; i < n_mp; i++) out_point_feature[i] = -1;
     if (n_f == 0 || n_mp == 0) return ORB_OK;
-    return run_window_search(true, kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds, wins, desc_mp, nnratio, th_high,
+    return run_window_search(true, kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds, nullptr, wins, desc_mp, nnratio, th_high,
                              out_feature_point, out_point_feature, n_matches, device);
 }
 
 static int best_only_search(const char* who, bool keyframe_mode, int level_up, const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right,
-                            const uint8_t* occupied, int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                            const uint8_t* occupied, int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* origin,
                             const float* scale_factors, int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th,
                             int direction, int check_orientation, int threshold, int32_t* out_feature_point, int32_t* out_point_feature,
                             int* n_matches, int device) {
@@ -734,7 +737,7 @@ static int best_only_search(const char* who, bool keyframe_mode, int level_up, c
     for (int f = 0; f < n_f; f++) out_feature_point[f] = -1;
     for (int i = 0; i < n_pts; i++) out_point_feature[i] = -1;
     if (n_f == 0 || n_pts == 0) return ORB_OK;
-    const int rc = run_window_search(false, kps_un, desc_f, keyframe_mode ? nullptr : u_right, occupied, n_f, cell_ptr, cell_idx, bounds, wins,
+    const int rc = run_window_search(false, kps_un, desc_f, keyframe_mode ? nullptr : u_right, occupied, n_f, cell_ptr, cell_idx, bounds, origin, wins,
                                      desc_pts, 0.f, threshold, out_feature_point, out_point_feature, n_matches, device);
     if (rc) return rc;
     if (check_orientation) rotation_check(kps_un, pts, n_pts, out_point_feature, out_feature_point, n_matches);
@@ -746,7 +749,7 @@ int orbm_search_by_projection_last_frame(const orb_keypoint_t* kps_un, const uin
                                          const float* scale_factors, int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts,
                                          int n_pts, float th, int direction, int check_orientation, int th_high,
                                          int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device) {
-    return best_only_search("orbm_search_by_projection_last_frame", false, 1, kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds,
+    return best_only_search("orbm_search_by_projection_last_frame", false, 1, kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds, nullptr,
                             scale_factors, n_levels, pts, desc_pts, n_pts, th, direction, check_orientation, th_high, out_feature_point,
                             out_point_feature, n_matches, device);
 }
@@ -756,7 +759,7 @@ int orbm_search_by_projection_keyframe(const orb_keypoint_t* kps_un, const uint8
                                        int n_levels, const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int orb_dist,
                                        int check_orientation, int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches,
                                        int device) {
-    return best_only_search("orbm_search_by_projection_keyframe", true, 1, kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds,
+    return best_only_search("orbm_search_by_projection_keyframe", true, 1, kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, nullptr,
                             scale_factors, n_levels, pts, desc_pts, n_pts, th, 0, check_orientation, orb_dist, out_feature_point,
                             out_point_feature, n_matches, device);
 }
@@ -764,8 +767,8 @@ int orbm_search_by_projection_keyframe(const orb_keypoint_t* kps_un, const uint8
 int orbm_search_by_projection_sim3(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f, const int32_t* cell_ptr,
                                    const int32_t* cell_idx, const float* bounds, const float* scale_factors, int n_levels,
                                    const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int th_low,
-                                   int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device) {
-    return best_only_search("orbm_search_by_projection_sim3", true, 0, kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds,
+                                   int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, const float* grid_origin, int device) {
+    return best_only_search("orbm_search_by_projection_sim3", true, 0, kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, grid_origin,
                             scale_factors, n_levels, pts, desc_pts, n_pts, th, 0, 0, th_low, out_feature_point, out_point_feature, n_matches,
                             device);
 }
@@ -773,7 +776,7 @@ int orbm_search_by_projection_sim3(const orb_keypoint_t* kps_un, const uint8_t* 
 int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const float* u_right, int n_f, const int32_t* cell_ptr,
                            const int32_t* cell_idx, const float* bounds, const float* scale_factors, const float* inv_level_sigma2, int n_levels,
                            const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int32_t* best_idx, int32_t* best_dist,
-                           int device) {
+                           const float* grid_origin, int device) {
     if (n_f < 0 || n_pts < 0 || n_levels <= 0 || !bounds || !cell_ptr || !scale_factors || (n_f && (!kps_un || !desc_f || !cell_idx)) ||
         (n_pts && (!pts || !desc_pts || !best_idx || !best_dist)) || (inv_level_sigma2 && n_f && !u_right)) {
         set_error("orbm_window_best_match: bad arguments (u_right is required with inv_level_sigma2)");
@@ -799,7 +802,7 @@ int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, 
     const uint32_t* d_dp = (const uint32_t*)cx.upload(desc_pts, (size_t)n_pts * 32);
     int* d_bi = (int*)cx.dalloc((size_t)n_pts * 4); int* d_bd = (int*)cx.dalloc((size_t)n_pts * 4);
     if (!d_k || !d_df || !d_cp || !d_ci || !d_sf || !d_p || !d_dp || !d_bi || !d_bd || (inv_level_sigma2 && (!d_ur || !d_is))) return ORB_ERR_CUDA;
-    window_best_kernel<<<(n_pts + 127) / 128, 128, 0, cx.stream>>>(d_k, d_df, d_ur, d_cp, d_ci, make_grid_params(bounds), d_sf, d_is, d_p, d_dp, n_pts, th,
+    window_best_kernel<<<(n_pts + 127) / 128, 128, 0, cx.stream>>>(d_k, d_df, d_ur, d_cp, d_ci, make_grid_params(bounds, grid_origin), d_sf, d_is, d_p, d_dp, n_pts, th,
                                                                   d_bi, d_bd);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(best_idx, d_bi, (size_t)n_pts * 4) || !cx.download(best_dist, d_bd, (size_t)n_pts * 4) || !cx.finish()) return ORB_ERR_CUDA;

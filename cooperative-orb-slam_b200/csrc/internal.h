@@ -93,6 +93,8 @@ struct DevPtrs {
 };
 
 int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, cudaStream_t s);
+int launch_repack(const uint8_t* src, size_t src_row, size_t src_frame, uint8_t* dst, int dst_pitch, size_t dst_frame, int width,
+                  int height, int n_frames, cudaStream_t s);
 int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, int min_th,
                       cudaStream_t s);
 int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, cudaStream_t s);

@@ -140,6 +140,27 @@ int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg,
     return launches;
 }
 
+// Input repack: rows of an arbitrarily strided / unaligned image block into the aligned layout the kernels read
+// (pitch a multiple of 16).  One aligned 32-bit word per thread, bytes gathered through L1.
+__global__ void __launch_bounds__(128) repack_kernel(const uint8_t* __restrict__ src, size_t src_row, size_t src_frame,
+                                                     uint8_t* __restrict__ dst, int dst_pitch, size_t dst_frame, int width) {
+    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * wx >= width) return;
+    const uint8_t* s = src + blockIdx.z * src_frame + blockIdx.y * src_row + 4 * wx;
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (4 * wx + b < width) v |= (uint32_t)s[b] << (8 * b);
+    *reinterpret_cast<uint32_t*>(dst + blockIdx.z * dst_frame + (size_t)blockIdx.y * dst_pitch + 4 * wx) = v;
+}
+
+int launch_repack(const uint8_t* src, size_t src_row, size_t src_frame, uint8_t* dst, int dst_pitch, size_t dst_frame, int width,
+                  int height, int n_frames, cudaStream_t s) {
+    const dim3 grid(((width + 3) / 4 + 127) / 128, height, n_frames);
+    repack_kernel<<<grid, 128, 0, s>>>(src, src_row, src_frame, dst, dst_pitch, dst_frame, width);
+    return 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2 blur.  cv::GaussianBlur(7x7, sigma 2) on CV_8U uses an 8.8 fixed-point separable kernel
 // [18,34,48,56,48,34,18] with one rounding: (sum + 32768) >> 16.  The source is clone() of the level

@@ -327,12 +327,16 @@ int orbm_search_by_projection_keyframe(const orb_keypoint_t* kps_un, const uint8
 /* int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints,
  *                                    vector<MapPoint*>& vpMatched, int th)
  * R21/src/ORBmatcher.cc:290-403 (LoopClosing::ComputeSim3).  pts[i]: u, v (:331-335), octave = PredictScale (:359),
- * valid = every test of :315-357 passed.  occupied[f] = vpMatched[f] != NULL on entry; th_low = TH_LOW (50). */
+ * valid = every test of :315-357 passed.  occupied[f] = vpMatched[f] != NULL on entry; th_low = TH_LOW (50).
+ * grid_origin: a KeyFrame keeps its image bounds as int (R21/include/KeyFrame.h: const int mnMinX, mnMinY) and
+ * KeyFrame::GetFeaturesInArea (R21/src/KeyFrame.cc:570-609) measures cells from those truncated values while the cell
+ * size stays the Frame's float one; pass {(float)pKF->mnMinX, (float)pKF->mnMinY} (NULL: bounds[0], bounds[2]). */
 int orbm_search_by_projection_sim3(const orb_keypoint_t* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
                                    const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
                                    const float* scale_factors, int n_levels, const orbm_proj_point_t* pts,
                                    const uint8_t* desc_pts, int n_pts, float th, int th_low,
-                                   int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches, int device);
+                                   int32_t* out_feature_point, int32_t* out_point_feature, int* n_matches,
+                                   const float* grid_origin, int device);
 
 /* The window search inside
  *   int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th)   R21/src/ORBmatcher.cc:825-975
@@ -346,7 +350,8 @@ int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, 
                            const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
                            const float* scale_factors, const float* inv_level_sigma2, int n_levels,
                            const orbm_proj_point_t* pts, const uint8_t* desc_pts, int n_pts, float th, int32_t* best_idx,
-                           int32_t* best_dist, int device);
+                           int32_t* best_dist, const float* grid_origin /* as above; all three callers look up a KeyFrame */,
+                           int device);
 
 /* int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
  *                                         vector<int>& vnMatches12, int windowSize)

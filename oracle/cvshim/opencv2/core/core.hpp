@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cassert>
+#include <climits>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -95,9 +96,17 @@ typedef unsigned char uchar;
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32S 4
 #define CV_32F 5
+#define CV_64F 6
+#define CV_32FC1 5
+#define CV_32FC2 13
+#define CV_MAT_DEPTH(t) ((t) & 7)
+#define CV_MAT_CN(t) ((((t) >> 3) & 63) + 1)
+#define CV_MAKETYPE(depth, cn) (CV_MAT_DEPTH(depth) + (((cn) - 1) << 3))
 #define CV_PI 3.1415926535897932384626433832795
 
+enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4 };
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4,
        BORDER_REFLECT101 = 4, BORDER_DEFAULT = 4, BORDER_ISOLATED = 16 };
 enum { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2, INTER_AREA = 3 };
@@ -125,6 +134,13 @@ typedef Point_<int> Point2i;
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
 typedef Point_<double> Point2d;
+template <typename T> struct Point3_ {
+    T x, y, z;
+    Point3_() : x(0), y(0), z(0) {}
+    Point3_(T _x, T _y, T _z) : x(_x), y(_y), z(_z) {}
+};
+typedef Point3_<float> Point3f;
+typedef Point3_<double> Point3d;
 
 struct Size {
     int width, height;
@@ -155,49 +171,62 @@ struct MatStep {
     MatStep& operator=(size_t s) { p = s; return *this; }
 };
 
-struct MatZeros { int rows, cols, type; };
+class Mat;
+// what cv::Mat::zeros / ones / eye return (a cv::MatExpr in OpenCV): assigned into an existing header it fills in place
+struct MatConst {
+    int rows, cols, type, kind;      // kind 0 zeros, 1 ones, 2 eye
+    operator Mat() const;
+};
+typedef MatConst MatZeros;
 
-// CV_8UC1-only reference-counted matrix header with ROI views.
+// Reference-counted matrix header with ROI views.  CV_8UC1 for the image path (the extractor); CV_32F / CV_64F (1 or 2
+// channels) with the handful of arithmetic operators the reference's Frame / KeyFrame / MapPoint / ORBmatcher use.
 class Mat {
 public:
     int rows, cols;
     uchar* data;
     MatStep step;
 
-    Mat() : rows(0), cols(0), data(nullptr), buf_(nullptr) {}
-    Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr), buf_(nullptr) { create(r, c, type); }
-    Mat(Size s, int type) : rows(0), cols(0), data(nullptr), buf_(nullptr) { create(s.height, s.width, type); }
-    Mat(int r, int c, int type, void* ext, size_t st = 0) : rows(r), cols(c), data((uchar*)ext), buf_(nullptr) {
-        (void)type; step = st ? st : (size_t)c;
+    Mat() : rows(0), cols(0), data(nullptr), type_(CV_8UC1), buf_(nullptr) {}
+    Mat(int r, int c, int type) : rows(0), cols(0), data(nullptr), type_(CV_8UC1), buf_(nullptr) { create(r, c, type); }
+    Mat(Size s, int type) : rows(0), cols(0), data(nullptr), type_(CV_8UC1), buf_(nullptr) { create(s.height, s.width, type); }
+    Mat(int r, int c, int type, void* ext, size_t st = 0) : rows(r), cols(c), data((uchar*)ext), type_(type), buf_(nullptr) {
+        step = st ? st : (size_t)c * elemSize();
     }
-    Mat(const Mat& m) : rows(m.rows), cols(m.cols), data(m.data), step(m.step), buf_(m.buf_) { if (buf_) buf_->ref++; }
+    Mat(const Mat& m) : rows(m.rows), cols(m.cols), data(m.data), step(m.step), type_(m.type_), buf_(m.buf_) { if (buf_) buf_->ref++; }
     ~Mat() { release(); }
     Mat& operator=(const Mat& m) {
         if (this != &m) {
             if (m.buf_) m.buf_->ref++;
             release();
-            rows = m.rows; cols = m.cols; data = m.data; step = m.step; buf_ = m.buf_;
+            rows = m.rows; cols = m.cols; data = m.data; step = m.step; type_ = m.type_; buf_ = m.buf_;
         }
         return *this;
     }
-    // cv::Mat::operator=(const MatExpr&) for Mat::zeros: create() is a no-op on a matching header, then fill.
-    Mat& operator=(const MatZeros& z) {
+    // cv::Mat::operator=(const MatExpr&) for Mat::zeros / ones / eye: create() is a no-op on a matching header, then fill.
+    Mat& operator=(const MatConst& z) {
         create(z.rows, z.cols, z.type);
-        for (int r = 0; r < rows; r++) memset(data + (size_t)r * step.p, 0, cols);
+        for (int r = 0; r < rows; r++) memset(data + (size_t)r * step.p, 0, (size_t)cols * elemSize());
+        if (z.kind) {
+            for (int r = 0; r < rows; r++)
+                for (int c = 0; c < cols; c++)
+                    if (z.kind == 1 || r == c) set_scalar(r, c, 1.0);
+        }
         return *this;
     }
-    static MatZeros zeros(int r, int c, int type) { MatZeros z = {r, c, type}; return z; }
+    static MatConst zeros(int r, int c, int type) { MatConst z = {r, c, type, 0}; return z; }
+    static MatConst ones(int r, int c, int type) { MatConst z = {r, c, type, 1}; return z; }
+    static MatConst eye(int r, int c, int type) { MatConst z = {r, c, type, 2}; return z; }
 
     void create(int r, int c, int type) {
-        assert(type == CV_8UC1);
-        (void)type;
-        if (data && rows == r && cols == c) return;
+        if (data && rows == r && cols == c && type_ == type) return;
         release();
-        rows = r; cols = c; step = (size_t)c;
+        type_ = type;
+        rows = r; cols = c; step = (size_t)c * elemSize();
         if ((size_t)r * c > 0) {
             buf_ = new Buf;
             buf_->ref = 1;
-            buf_->mem = (uchar*)malloc((size_t)r * c);
+            buf_->mem = (uchar*)malloc((size_t)r * c * elemSize());
             data = buf_->mem;
         }
     }
@@ -207,26 +236,66 @@ public:
         buf_ = nullptr; data = nullptr; rows = cols = 0; step = 0;
     }
     bool empty() const { return data == nullptr || rows * cols == 0; }
-    int type() const { return CV_8UC1; }
-    int channels() const { return 1; }
-    size_t step1() const { return step.p; }
-    size_t elemSize() const { return 1; }
+    int type() const { return type_; }
+    int depth() const { return CV_MAT_DEPTH(type_); }
+    int channels() const { return CV_MAT_CN(type_); }
+    size_t elemSize1() const { const int d = depth(); return d == CV_8U ? 1 : (d == CV_64F ? 8 : 4); }
+    size_t elemSize() const { return elemSize1() * channels(); }
+    size_t step1() const { return step.p / elemSize1(); }
+    size_t total() const { return (size_t)rows * cols; }
     Size size() const { return Size(cols, rows); }
-    bool isContinuous() const { return step.p == (size_t)cols || rows <= 1; }
+    bool isContinuous() const { return step.p == (size_t)cols * elemSize() || rows <= 1; }
 
     Mat operator()(const Rect& r) const {
         Mat m(*this);
-        m.data = data + (size_t)r.y * step.p + r.x;
+        m.data = data + (size_t)r.y * step.p + (size_t)r.x * elemSize();
         m.rows = r.height; m.cols = r.width;
         return m;
     }
     Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
     Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
     Mat row(int r) const { return rowRange(r, r + 1); }
+    Mat col(int c) const { return colRange(c, c + 1); }
     Mat clone() const {
-        Mat m(rows, cols, CV_8UC1);
-        for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step.p, data + (size_t)r * step.p, cols);
+        Mat m(rows, cols, type_);
+        for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step.p, data + (size_t)r * step.p, (size_t)cols * elemSize());
         return m;
+    }
+    // cv::Mat::copyTo: dst.create() keeps a matching header (so a ROI view of another matrix is written in place)
+    void copyTo(Mat& dst) const {
+        dst.create(rows, cols, type_);
+        for (int r = 0; r < rows; r++) memmove(dst.data + (size_t)r * dst.step.p, data + (size_t)r * step.p, (size_t)cols * elemSize());
+    }
+    void copyTo(const Mat& dst_view) const { Mat d(dst_view); copyTo(d); }      // a temporary ROI: Rwc.copyTo(Twc.rowRange(...))
+    // same memory, other channel count (Frame::UndistortKeyPoints: N x 2 one-channel <-> N x 1 two-channel)
+    Mat reshape(int cn) const {
+        Mat m(*this);
+        const int w = cols * channels();
+        assert(isContinuous() || rows == 1);
+        assert(w % cn == 0);
+        m.type_ = CV_MAKETYPE(depth(), cn);
+        m.cols = w / cn;
+        return m;
+    }
+    void convertTo(Mat& dst, int rtype) const {
+        assert(channels() == 1);
+        Mat out(rows, cols, CV_MAT_DEPTH(rtype));
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++) out.set_scalar(r, c, get_scalar(r, c));
+        dst = out;
+    }
+    Mat t() const {
+        Mat m(cols, rows, type_);
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++) memcpy(m.data + (size_t)c * m.step.p + (size_t)r * elemSize(), data + (size_t)r * step.p + (size_t)c * elemSize(), elemSize());
+        return m;
+    }
+    double dot(const Mat& b) const {
+        assert(total() == b.total());
+        double acc = 0;
+        const int n = (int)total();
+        for (int i = 0; i < n; i++) acc += lin_scalar(i) * b.lin_scalar(i);
+        return acc;
     }
     uchar* ptr(int r = 0) { return data + (ptrdiff_t)r * (ptrdiff_t)step.p; }
     const uchar* ptr(int r = 0) const { return data + (ptrdiff_t)r * (ptrdiff_t)step.p; }
@@ -236,11 +305,113 @@ public:
     template <typename T> const T& at(int r, int c) const {
         return *(const T*)(data + (ptrdiff_t)r * (ptrdiff_t)step.p + (ptrdiff_t)c * sizeof(T));
     }
+    // cv::Mat::at(int i0): element i0 of a row / column vector (or of a continuous matrix)
+    template <typename T> T& at(int i) { return const_cast<T&>(static_cast<const Mat*>(this)->at<T>(i)); }
+    template <typename T> const T& at(int i) const {
+        if (rows == 1 || isContinuous() && cols != 1) return *(const T*)(data + (ptrdiff_t)i * sizeof(T));
+        if (cols == 1) return *(const T*)(data + (ptrdiff_t)i * (ptrdiff_t)step.p);
+        const int r = i / cols;
+        return at<T>(r, i - r * cols);
+    }
+    // element access as double, whatever the depth (one channel)
+    double get_scalar(int r, int c) const {
+        const uchar* p = data + (size_t)r * step.p + (size_t)c * elemSize();
+        switch (depth()) { case CV_8U: return *p; case CV_32F: return *(const float*)p; case CV_64F: return *(const double*)p; default: return *(const int*)p; }
+    }
+    void set_scalar(int r, int c, double v) {
+        uchar* p = data + (size_t)r * step.p + (size_t)c * elemSize();
+        switch (depth()) { case CV_8U: *p = (uchar)v; break; case CV_32F: *(float*)p = (float)v; break; case CV_64F: *(double*)p = v; break; default: *(int*)p = (int)v; }
+    }
+    double lin_scalar(int i) const { const int w = cols * channels(); Mat one = channels() == 1 ? *this : reshape(1); return one.get_scalar(i / w, i % w); }
 
 private:
     struct Buf { int ref; uchar* mem; };
+    int type_;
     Buf* buf_;
 };
+inline MatConst::operator Mat() const { Mat m; m = *this; return m; }
+
+// ---- the arithmetic the reference writes on pose / point matrices (CV_32F).  Products and sums are formed in double
+// and rounded once per element, like cv::gemm's float path (double accumulators).
+inline Mat operator*(const Mat& a, const Mat& b) {
+    assert(a.cols == b.rows && a.type() == b.type());
+    Mat m(a.rows, b.cols, a.type());
+    for (int r = 0; r < a.rows; r++)
+        for (int c = 0; c < b.cols; c++) {
+            double acc = 0;
+            for (int k = 0; k < a.cols; k++) acc += a.get_scalar(r, k) * b.get_scalar(k, c);
+            m.set_scalar(r, c, acc);
+        }
+    return m;
+}
+inline Mat cvshim_binary(const Mat& a, const Mat& b, double sb) {
+    assert(a.rows == b.rows && a.cols == b.cols && a.type() == b.type());
+    Mat m(a.rows, a.cols, a.type());
+    for (int r = 0; r < a.rows; r++)
+        for (int c = 0; c < a.cols; c++) m.set_scalar(r, c, a.get_scalar(r, c) + sb * b.get_scalar(r, c));
+    return m;
+}
+inline Mat cvshim_scaled(const Mat& a, double s) {
+    Mat m(a.rows, a.cols, a.type());
+    for (int r = 0; r < a.rows; r++)
+        for (int c = 0; c < a.cols; c++) m.set_scalar(r, c, a.get_scalar(r, c) * s);
+    return m;
+}
+inline Mat operator+(const Mat& a, const Mat& b) { return cvshim_binary(a, b, 1.0); }
+inline Mat operator-(const Mat& a, const Mat& b) { return cvshim_binary(a, b, -1.0); }
+inline Mat operator-(const Mat& a) { return cvshim_scaled(a, -1.0); }
+inline Mat operator*(const Mat& a, double s) { return cvshim_scaled(a, s); }
+inline Mat operator*(double s, const Mat& a) { return cvshim_scaled(a, s); }
+inline Mat operator/(const Mat& a, double s) { return cvshim_scaled(a, 1.0 / s); }       // MatExpr: alpha = 1/s
+
+inline double norm(const Mat& a, int type = NORM_L2) {
+    double acc = 0;
+    const int n = (int)a.total() * a.channels();
+    for (int i = 0; i < n; i++) { const double v = a.lin_scalar(i); acc += type == NORM_L1 ? std::fabs(v) : v * v; }
+    return type == NORM_L1 ? acc : std::sqrt(acc);
+}
+inline double norm(const Mat& a, const Mat& b, int type = NORM_L2) {
+    assert(a.rows == b.rows && a.cols == b.cols);
+    double acc = 0;
+    for (int r = 0; r < a.rows; r++)
+        for (int c = 0; c < a.cols; c++) { const double v = a.get_scalar(r, c) - b.get_scalar(r, c); acc += type == NORM_L1 ? std::fabs(v) : v * v; }
+    return type == NORM_L1 ? acc : std::sqrt(acc);
+}
+
+// cv::Mat_<T>(r, c) << a, b, c ...   (Frame::UnprojectStereo, KeyFrame::SetPose)
+template <typename T> class Mat_;
+template <typename T> class MatCommaInitializer_ {
+public:
+    MatCommaInitializer_(Mat_<T>* m, T v);
+    MatCommaInitializer_& operator,(T v);
+    operator Mat() const;
+    operator Mat_<T>() const;
+private:
+    Mat_<T>* m_; int i_;
+};
+template <typename T> struct cvshim_depth;
+template <> struct cvshim_depth<float> { enum { value = CV_32F }; };
+template <> struct cvshim_depth<double> { enum { value = CV_64F }; };
+template <> struct cvshim_depth<uchar> { enum { value = CV_8U }; };
+template <> struct cvshim_depth<int> { enum { value = CV_32S }; };
+template <typename T> class Mat_ : public Mat {
+public:
+    Mat_() : Mat() {}
+    Mat_(int r, int c) : Mat(r, c, cvshim_depth<T>::value) {}
+    Mat_(const Mat& m) : Mat(m) {}
+    T& operator()(int r, int c) { return this->template at<T>(r, c); }
+    const T& operator()(int r, int c) const { return this->template at<T>(r, c); }
+};
+template <typename T> MatCommaInitializer_<T>::MatCommaInitializer_(Mat_<T>* m, T v) : m_(m), i_(0) { (*this), v; }
+template <typename T> MatCommaInitializer_<T>& MatCommaInitializer_<T>::operator,(T v) {
+    m_->template at<T>(i_ / m_->cols, i_ % m_->cols) = v; i_++;
+    return *this;
+}
+template <typename T> MatCommaInitializer_<T>::operator Mat() const { return *m_; }
+template <typename T> MatCommaInitializer_<T>::operator Mat_<T>() const { return *m_; }
+template <typename T, typename V> inline MatCommaInitializer_<T> operator<<(const Mat_<T>& m, V v) {
+    return MatCommaInitializer_<T>(const_cast<Mat_<T>*>(&m), (T)v);
+}
 
 class _InputArray {
 public:
@@ -255,6 +426,7 @@ class _OutputArray : public _InputArray {
 public:
     _OutputArray() : o_(nullptr) {}
     _OutputArray(Mat& m) : _InputArray(m), o_(&m) {}
+    _OutputArray(const Mat& m) : _InputArray(m), o_(const_cast<Mat*>(&m)) {}
     void create(int r, int c, int type) const { o_->create(r, c, type); }
     void create(Size s, int type) const { o_->create(s, type); }
     void release() const { if (o_) o_->release(); }

@@ -108,11 +108,19 @@ void orc_assign_grid(const orc_keypoint* kps_un, int n, const float* bounds, int
 }
 
 /* Frame::GetFeaturesInArea :332-385.  Returns the number of indices (writes at most cap). */
+static int features_in_area_o(const orc_keypoint* kps_un, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                              const float* origin, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap);
 int orc_features_in_area(const orc_keypoint* kps_un, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
                          float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
+    return features_in_area_o(kps_un, cell_ptr, cell_idx, bounds, nullptr, x, y, r, min_level, max_level, out, cap);
+}
+/* origin != NULL: KeyFrame::GetFeaturesInArea (R21/src/KeyFrame.cc:570-609) -- the key frame's mnMinX / mnMinY are ints
+ * (KeyFrame.h), truncated from the Frame's float bounds, while mfGridElementWidthInv/HeightInv are the Frame's (KeyFrame.cc:33). */
+static int features_in_area_o(const orc_keypoint* kps_un, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                              const float* origin, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
     const float winv = (float)kGridCols / (float)(bounds[1] - bounds[0]);
     const float hinv = (float)kGridRows / (float)(bounds[3] - bounds[2]);
-    const float minx = bounds[0], miny = bounds[2];
+    const float minx = origin ? origin[0] : bounds[0], miny = origin ? origin[1] : bounds[2];
     int n = 0;
     const int nMinCellX = std::max(0, (int)floor((x - minx - r) * winv));
     if (nMinCellX >= kGridCols) return 0;
@@ -220,7 +228,7 @@ enum { kHistoLength = 30 };   /* ORBmatcher::HISTO_LENGTH, R21/src/ORBmatcher.cc
  * [l-1, l+1] (:1531), any occupied feature blocks (:1543-1544), no stereo check, threshold ORBdist (:1557).
  * out_feature_point[f]: -1 untouched, -2 set to NULL by the rotation check, else the point left in mvpMapPoints[f]. */
 static int projection_body(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right, const uint8_t* occupied,
-                           int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
+                           int n_f, const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* origin,
                            const float* scale_factors, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts, float th,
                            int direction, int keyframe_mode, int check_orientation, int threshold,
                            int32_t* out_feature_point, int32_t* out_point_feature) {
@@ -237,7 +245,7 @@ static int projection_body(const orc_keypoint* kps_un, const uint8_t* desc_f, co
         const int oct = p.octave;
         const float radius = th * scale_factors[oct];
         int nc;
-        if (keyframe_mode == 2) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct - 1, oct, cand.data(), n_f);
+        if (keyframe_mode == 2) nc = features_in_area_o(kps_un, cell_ptr, cell_idx, bounds, origin, p.u, p.v, radius, oct - 1, oct, cand.data(), n_f);
         else if (keyframe_mode) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct - 1, oct + 1, cand.data(), n_f);
         else if (direction == 1) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, oct, -1, cand.data(), n_f);
         else if (direction == 2) nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, p.u, p.v, radius, 0, oct, cand.data(), n_f);
@@ -290,7 +298,7 @@ int orc_search_by_projection_last_frame(const orc_keypoint* kps_un, const uint8_
                                         const float* bounds, const float* scale_factors, const orc_proj_point* pts,
                                         const uint8_t* desc_pts, int n_pts, float th, int direction, int check_orientation,
                                         int th_high, int32_t* out_feature_point, int32_t* out_point_feature) {
-    return projection_body(kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, pts, desc_pts, n_pts,
+    return projection_body(kps_un, desc_f, u_right, occupied, n_f, cell_ptr, cell_idx, bounds, nullptr, scale_factors, pts, desc_pts, n_pts,
                            th, direction, 0, check_orientation, th_high, out_feature_point, out_point_feature);
 }
 
@@ -303,7 +311,7 @@ int orc_search_by_projection_keyframe(const orc_keypoint* kps_un, const uint8_t*
                                       const float* scale_factors, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts,
                                       float th, int orb_dist, int check_orientation, int32_t* out_feature_point,
                                       int32_t* out_point_feature) {
-    return projection_body(kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, pts, desc_pts, n_pts, th,
+    return projection_body(kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, nullptr, scale_factors, pts, desc_pts, n_pts, th,
                            0, 1, check_orientation, orb_dist, out_feature_point, out_point_feature);
 }
 
@@ -314,8 +322,8 @@ int orc_search_by_projection_keyframe(const orc_keypoint* kps_un, const uint8_t*
 int orc_search_by_projection_sim3(const orc_keypoint* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
                                   const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
                                   const float* scale_factors, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts,
-                                  float th, int th_low, int32_t* out_feature_point, int32_t* out_point_feature) {
-    return projection_body(kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, scale_factors, pts, desc_pts, n_pts, th,
+                                  float th, int th_low, int32_t* out_feature_point, int32_t* out_point_feature, const float* grid_origin) {
+    return projection_body(kps_un, desc_f, nullptr, occupied, n_f, cell_ptr, cell_idx, bounds, grid_origin, scale_factors, pts, desc_pts, n_pts, th,
                            0, 2, 0, th_low, out_feature_point, out_point_feature);
 }
 
@@ -327,7 +335,7 @@ int orc_search_by_projection_sim3(const orc_keypoint* kps_un, const uint8_t* des
 void orc_window_best_match(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right, int n_f,
                            const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* scale_factors,
                            const float* inv_level_sigma2, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts, float th,
-                           int32_t* best_idx, int32_t* best_dist) {
+                           int32_t* best_idx, int32_t* best_dist, const float* grid_origin) {
     std::vector<int32_t> cand((size_t)std::max(n_f, 1));
     for (int i = 0; i < n_pts; i++) {
         best_idx[i] = -1; best_dist[i] = 256;
@@ -336,7 +344,7 @@ void orc_window_best_match(const orc_keypoint* kps_un, const uint8_t* desc_f, co
         const int lvl = p.octave;
         const float radius = th * scale_factors[lvl];
         const float u = p.u, v = p.v, ur = p.ur;
-        const int nc = orc_features_in_area(kps_un, cell_ptr, cell_idx, bounds, u, v, radius, -1, -1, cand.data(), n_f);
+        const int nc = features_in_area_o(kps_un, cell_ptr, cell_idx, bounds, grid_origin, u, v, radius, -1, -1, cand.data(), n_f);
         int bestDist = 256, bestIdx = -1;
         for (int c = 0; c < nc; c++) {
             const int idx = cand[c];

@@ -214,12 +214,13 @@ int orc_search_by_projection_keyframe(const orc_keypoint* kps_un, const uint8_t*
 int orc_search_by_projection_sim3(const orc_keypoint* kps_un, const uint8_t* desc_f, const uint8_t* occupied, int n_f,
                                   const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds,
                                   const float* scale_factors, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts,
-                                  float th, int th_low, int32_t* out_feature_point, int32_t* out_point_feature);
+                                  float th, int th_low, int32_t* out_feature_point, int32_t* out_point_feature,
+                                  const float* grid_origin /* NULL or {(float)pKF->mnMinX, (float)pKF->mnMinY}: KeyFrame.cc:575-589 */);
 /* Window search of ORBmatcher::Fuse x2 (:825-975 with the chi-square gates, :977-1100) and SearchBySim3 (:1102-1326) */
 void orc_window_best_match(const orc_keypoint* kps_un, const uint8_t* desc_f, const float* u_right, int n_f,
                            const int32_t* cell_ptr, const int32_t* cell_idx, const float* bounds, const float* scale_factors,
                            const float* inv_level_sigma2, const orc_proj_point* pts, const uint8_t* desc_pts, int n_pts, float th,
-                           int32_t* best_idx, int32_t* best_dist);
+                           int32_t* best_idx, int32_t* best_dist, const float* grid_origin /* as above */);
 
 /* ORBmatcher::SearchForInitialization (R21/src/ORBmatcher.cc:405-520) */
 int orc_search_for_initialization(const orc_keypoint* kps1_un, const uint8_t* desc1, int n1, const orc_keypoint* kps2_un,

@@ -429,7 +429,7 @@ def search_by_projection_keyframe(kps_un, desc_f, occupied, ptr, idx, bounds, sc
     return fp[:len(kps_un)], pf[:len(pts)], n
 
 
-def search_by_projection_sim3(kps_un, desc_f, occupied, ptr, idx, bounds, scale_factors, pts, desc_pts, th, th_low=50):
+def search_by_projection_sim3(kps_un, desc_f, occupied, ptr, idx, bounds, scale_factors, pts, desc_pts, th, th_low=50, grid_origin=None):
     kps_un = np.ascontiguousarray(kps_un, KP_DTYPE); df = np.ascontiguousarray(desc_f, np.uint8)
     occ = np.ascontiguousarray(occupied, np.uint8)
     b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
@@ -437,13 +437,14 @@ def search_by_projection_sim3(kps_un, desc_f, occupied, ptr, idx, bounds, scale_
     fp = np.zeros(max(len(kps_un), 1), np.int32); pf = np.zeros(max(len(pts), 1), np.int32)
     L = lib()
     L.orc_search_by_projection_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    go = None if grid_origin is None else np.ascontiguousarray(grid_origin, np.float32)
     n = L.orc_search_by_projection_sim3(_p(kps_un), _p(df), _p(occ), len(kps_un), _p(ptr), _p(idx), _p(b), _p(sf), _p(pts), _p(dp),
-                                        len(pts), th, th_low, _p(fp), _p(pf))
+                                        len(pts), th, th_low, _p(fp), _p(pf), None if go is None else _p(go))
     return fp[:len(kps_un)], pf[:len(pts)], n
 
 
-def window_best_match(kps_un, desc_f, u_right, ptr, idx, bounds, scale_factors, inv_level_sigma2, pts, desc_pts, th):
+def window_best_match(kps_un, desc_f, u_right, ptr, idx, bounds, scale_factors, inv_level_sigma2, pts, desc_pts, th, grid_origin=None):
     kps_un = np.ascontiguousarray(kps_un, KP_DTYPE); df = np.ascontiguousarray(desc_f, np.uint8)
     b = np.ascontiguousarray(bounds, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
     pts = np.ascontiguousarray(pts, PROJ_DTYPE); dp = np.ascontiguousarray(desc_pts, np.uint8)
@@ -453,9 +454,10 @@ def window_best_match(kps_un, desc_f, u_right, ptr, idx, bounds, scale_factors, 
     L = lib()
     L.orc_window_best_match.restype = None
     L.orc_window_best_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    go = None if grid_origin is None else np.ascontiguousarray(grid_origin, np.float32)
     L.orc_window_best_match(_p(kps_un), _p(df), None if ur is None else _p(ur), len(kps_un), _p(ptr), _p(idx), _p(b), _p(sf),
-                            None if sg is None else _p(sg), _p(pts), _p(dp), len(pts), th, _p(bi), _p(bd))
+                            None if sg is None else _p(sg), _p(pts), _p(dp), len(pts), th, _p(bi), _p(bd), None if go is None else _p(go))
     return bi[:len(pts)], bd[:len(pts)]
 
 

@@ -130,6 +130,41 @@ def test_batch_equals_single(orb, synth):
     assert k2.tobytes() == k1.tobytes() and np.array_equal(d1, d2)
 
 
+def test_strided_pinned_and_unaligned_device_input(orb, synth):
+    """A tight 1241-byte row stride from pinned host memory (one block copy + on-device re-pitch) and an unaligned device
+    batch both equal the plain call."""
+    import torch
+    W, H, B = 1241, 376, 3
+    frames = np.stack([synth.frame(s, W, H) for s in range(B)])
+    single = orb.ORBextractor(2000, 1.2, 8, 20, 7)
+    ref = [single(frames[i]) for i in range(B)]
+    ex = orb.ORBextractor(2000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
+    cap = ex.max_keypoints(W, H)
+    pin = orb.PinnedArray((B, H, W), np.uint8); pin.array[...] = frames
+    pk = orb.PinnedArray((B, cap), orb.KP_DTYPE); pd = orb.PinnedArray((B, cap, 32), np.uint8); pc = orb.PinnedArray((B,), np.int32)
+    ex.extract_batch_async(pin.array, pk.array, pd.array, pc.array); ex.wait()
+    for i in range(B):
+        n = int(pc.array[i])
+        assert n == len(ref[i][0]) and pk.array[i, :n].tobytes() == ref[i][0].tobytes() and np.array_equal(pd.array[i, :n], ref[i][1])
+    # padded pinned rows (stride 1300) with a gap between frames
+    pin2 = orb.PinnedArray((B, H + 5, 1300), np.uint8); pin2.array[:, :H, :W] = frames
+    ex.extract_batch_async(pin2.array[:, :H, :W], pk.array, pd.array, pc.array); ex.wait()
+    for i in range(B):
+        n = int(pc.array[i])
+        assert n == len(ref[i][0]) and pk.array[i, :n].tobytes() == ref[i][0].tobytes() and np.array_equal(pd.array[i, :n], ref[i][1])
+    # device batch with an odd row stride
+    d = torch.from_numpy(frames).cuda()
+    dk = torch.zeros((B, cap, 7), dtype=torch.int32, device="cuda"); dd = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    dc = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(d.data_ptr(), B, W, H, W, W * H, dk.data_ptr(), dd.data_ptr(), cap, dc.data_ptr()); ex.wait()
+    dk = dk.cpu().numpy().view(orb.KP_DTYPE).reshape(B, cap); dd = dd.cpu().numpy(); dc = dc.cpu().numpy()
+    for i in range(B):
+        n = int(dc[i])
+        assert n == len(ref[i][0]) and dk[i, :n].tobytes() == ref[i][0].tobytes() and np.array_equal(dd[i, :n], ref[i][1])
+    for p in (pin, pin2, pk, pd, pc):
+        p.free()
+
+
 def test_degenerate_inputs(orb, oracle):
     ex = orb.ORBextractor(1000, 1.2, 8, 20, 7)
     k, d = ex(np.zeros((0, 0), np.uint8))
