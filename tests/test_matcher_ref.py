@@ -189,3 +189,46 @@ def test_descriptor_distance(flavour):
     for i in range(64):
         ref = wr.mh_descriptor_distance(a[i].ctypes.data, b[i].ctypes.data)
         assert ref == ws.mh_descriptor_distance(a[i].ctypes.data, b[i].ctypes.data) == int(np.unpackbits(a[i] ^ b[i]).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not mr.available("shim_cuda"), reason="oracle/_ref/libmatchshim_cuda.so not built")
+def test_cuda_dropin_frames_from_images(synth):
+    """The reference's Frame constructors (Frame.cc:63-119, :176-233) on top of the product's ORBextractor class (CUDA) against the
+    same constructors on the reference's own extractor: key points, descriptors, undistortion, grid, and the stereo matches --
+    once computed by the reference's ComputeStereoMatches on the drop-in's mvImagePyramid mirror and once by the GPU search."""
+    K = np.array([458.654, 457.296, 367.215, 248.375], np.float32)
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
+    # monocular, TUM shape
+    img = synth.frame(5, 640, 480)
+    got = {}
+    for fl in ("ref", "shim_cuda"):
+        w = mr.World(fl, K, D, 40.0, 35.0, 640, 480, nfeatures=1000)
+        got[fl] = w.frame_get(w.frame_from_image(img))
+        w.close()
+    a, b = got["ref"], got["shim_cuda"]
+    assert len(a["kps"]) == len(b["kps"]) > 900
+    assert a["kps"].tobytes() == b["kps"].tobytes() and a["kps_un"].tobytes() == b["kps_un"].tobytes()
+    assert np.array_equal(a["cell_ptr"], b["cell_ptr"]) and np.array_equal(a["cell_idx"], b["cell_idx"])
+    assert int((a["desc"] != b["desc"]).any(1).sum()) <= max(1, len(a["desc"]) // 1000)
+    # stereo, EuRoC shape
+    left, right = synth.stereo_pair(3, 752, 480)
+    mbf, fx = 47.90639384423901, 458.654
+    res = {}
+    for fl in ("ref", "shim_cuda"):
+        w = mr.World(fl, K, np.zeros(4, np.float32), mbf, 35.0, 752, 480, nfeatures=1200)
+        f = w.frame_from_stereo(left, right, mbf / fx)
+        res[fl] = w.frame_get(f)
+        if fl == "shim_cuda":
+            res["accel"] = w.frame_stereo_accel(f)
+        w.close()
+    a, b = res["ref"], res["shim_cuda"]
+    assert a["kps"].tobytes() == b["kps"].tobytes() and a["kps_right"].tobytes() == b["kps_right"].tobytes()
+    same_desc = np.array_equal(a["desc"], b["desc"]) and np.array_equal(a["desc_right"], b["desc_right"])
+    assert (a["u_right"] >= 0).sum() > 100
+    if same_desc:
+        assert np.array_equal(a["u_right"], b["u_right"]) and np.array_equal(a["depth"], b["depth"])
+        m, ur, dep = res["accel"]
+        assert m == int((a["u_right"] >= 0).sum()) and np.array_equal(ur, a["u_right"]) and np.array_equal(dep, a["depth"])
+    else:      # a descriptor at a rounding boundary (<= 0.1 %): the match lists may differ in those few features
+        assert (a["u_right"] != b["u_right"]).sum() <= 5
