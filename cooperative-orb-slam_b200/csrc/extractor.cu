@@ -230,6 +230,42 @@ int build_geometry(orbx_handle_s* h, int width, int height) {
                 }
                 g.rs_rows = std::max(g.rs_rows, hi - lo + 1);
             }
+            // two-phase kernel (pyramid.cu): tiles span the level width, split so that a tile has at most 160 four-column groups
+            // and its source footprint at most 64 sixteen-byte vectors; as tall as a 40 KB block of horizontal sums allows
+            {
+                const int w4 = (g.w + 3) / 4;
+                int nx = (w4 + 159) / 160;
+                for (;; nx++) {
+                    g.t2_w = (int)align_up((g.w + nx - 1) / nx, 4);
+                    g.t2_nx = (g.w + g.t2_w - 1) / g.t2_w;
+                    g.t2_cols = 0;
+                    for (int x0 = 0; x0 < g.w; x0 += g.t2_w) {
+                        const int x1 = std::min(x0 + g.t2_w, g.w) - 1;
+                        const int lo = xtab[g.xtab_off + x0].ofs & ~15, hi = xtab[g.xtab_off + x1].pad;
+                        g.t2_cols = std::max(g.t2_cols, (int)align_up(hi - lo + 2, 16));     // + the (zero-weight) byte behind the last pixel
+                    }
+                    if (g.t2_cols <= 64 * 16 || g.t2_w <= 4) break;
+                }
+                const int cgx = g.t2_w / 4;
+                const int max_rows = std::max(6, 40960 / (cgx * 16));
+                const double ratio = (double)geom[l - 1].h / g.h;
+                int th = std::max(2, std::min(96, (int)((max_rows - 3) / ratio)));
+                g.t2_ny = (g.h + th - 1) / th;
+                g.t2_h = (g.h + g.t2_ny - 1) / g.t2_ny;
+                g.t2_ny = (g.h + g.t2_h - 1) / g.t2_h;
+                g.t2_rows = 0;
+                for (int y0 = 0; y0 < g.h; y0 += g.t2_h) {
+                    const int y1 = std::min(y0 + g.t2_h, g.h) - 1;
+                    int lo = 1 << 30, hi = 0;
+                    for (int y = y0; y <= y1; y++) {
+                        lo = std::min(lo, (int)ytab[g.ytab_off + y].ofs);
+                        hi = std::max(hi, (int)ytab[g.ytab_off + y].pad);
+                    }
+                    g.t2_rows = std::max(g.t2_rows, hi - lo + 1);
+                }
+                g.t2_smem = g.t2_rows * g.t2_cols + g.t2_rows * cgx * 16 + g.t2_w * 8 + g.t2_h * 16 + 64;
+                if (g.t2_cols > 64 * 16 || cgx > 176) g.t2_smem = -1;       // scale factors this large go to the first kernel
+            }
         }
     }
     if (node_cap > 60000) { set_error("nfeatures per level too large"); return ORB_ERR_ARG; }
@@ -494,8 +530,8 @@ int orbx_extract_batch_device(orbx_handle_t h, const uint8_t* d_images, int n_fr
     const uint8_t* src = d_images;
     size_t fstride = frame_stride;
     int pitch = (int)row_stride;
-    if ((row_stride & 3) || (frame_stride & 3) || (reinterpret_cast<uintptr_t>(d_images) & 3)) {
-        // unaligned user layout: repack into the handle's own input buffer
+    if ((row_stride & 15) || (frame_stride & 15) || (reinterpret_cast<uintptr_t>(d_images) & 15)) {
+        // user layout without 16-byte aligned rows (the resize kernel stages level 0 with 16-byte loads): re-pitch into the handle's own buffer
         if ((rc = grow_dev(h->d_in, h->cap_in, (size_t)n_frames * h->fl.in_pitch * height))) return rc;
         h->launches += launch_repack(d_images, row_stride, frame_stride, h->d_in, h->fl.in_pitch, (size_t)h->fl.in_pitch * height, width, height,
                                      n_frames, h->stream);

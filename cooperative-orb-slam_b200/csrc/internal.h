@@ -39,6 +39,9 @@ struct LevelGeom {
     // resize tables for producing this level from level-1 (offsets into the table buffers)
     int xtab_off, ytab_off;
     int rs_rows, rs_cols;   // source rows / columns (word aligned) one kPyrTileH x kPyrTileW output tile of this level needs
+    // tiling of the two-phase resize kernel (pyr_resize2_kernel): output tiles of t2_w x t2_h, the largest source
+    // footprint of a tile (t2_rows x t2_cols bytes, t2_cols a multiple of 4 incl. 4 bytes of slack) and its shared memory
+    int t2_w, t2_h, t2_nx, t2_ny, t2_rows, t2_cols, t2_smem;
     float scale;            // mvScaleFactor[level]
     float patch_size;       // (float)(int)(31*scale)
 };

@@ -10,6 +10,7 @@
 #include "internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace orbcuda {
 
@@ -127,7 +128,144 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(DevPtrs d, FrameLayout 
     }
 }
 
-int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
+// ---------------------------------------------------------------------------------------------
+// K1, two-phase form (ORBCUDA_PYR=2; NOT the default).  The first kernel above spends ~49 thread-instruction slots per
+// output pixel, most of them on the half-rate integer ALU pipe that bounds the whole extraction step.  This one does the
+// same arithmetic (bit-identical output, same tests) in two passes over shared memory:
+//   phase H: every source row of the tile's footprint is reduced ONCE to its horizontal sums (S[o]*c0 + S[o+1]*c1) >> 4,
+//            two IMADs (FMA pipe) and one shift per tap, stored as int32 (one 16-byte store per four columns);
+//   phase V: every output pixel = (((b0*lo) >> 16) + ((b1*hi) >> 16) + 2) >> 2 with the two products taken as
+//            mul.hi.u32(b << 16, sum) (no shift), four pixels packed by multiply-adds and stored as one word.
+// A thread owns one 4-column group for the whole tile (its eight tap weights and four source offsets stay in registers,
+// every address advances by a constant) and the CTA's threads are laid out [RY][CGX] over (row, column group) with CGX =
+// the tile's number of column groups, whatever that is -- warps simply wrap around rows, so level widths that are no
+// multiple of 128 px cost nothing.  Tiles span the level width (split above ~640 px) and are as tall as 40 KB of sums
+// allow (extractor.cu: t2_*).  The source footprint is staged with 16-byte loads.
+// Measured on the B200 (round 2, ncu + CUDA events, 64-128 frames per launch): the inner loops are as lean as planned
+// (27 instructions per four horizontal sums, ~40 per four output pixels) but a tile is only ~13 rows tall at 40 KB of sums,
+// so the per-CTA set-up and the three barrier-separated phases dominate: 140 us per 64 frames for the seven levels
+// against 128 us for the first kernel; walking six row tiles per CTA (kPyr2Band) removes the set-up but leaves too few
+// CTAs on the small levels (0.26 ms per 128 frames on one stream against 0.196).  Kept as the measured alternative; a
+// version that wins needs rolling row buffers and asynchronous staging inside long-running CTAs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPyr2Threads = 512;
+
+constexpr int kPyr2Band = 6;       // row tiles one CTA walks (amortises the per-CTA set-up: divisions, tap staging, pointer bases)
+
+__global__ void __launch_bounds__(kPyr2Threads) pyr_resize2_kernel(DevPtrs d, FrameLayout fl, int level) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const LevelGeom gs = d.geom[level - 1], gd = d.geom[level];
+    const int tid = threadIdx.x, frame = blockIdx.y;
+    const int tx = blockIdx.x % gd.t2_nx, band = blockIdx.x / gd.t2_nx;
+    const int x0 = tx * gd.t2_w;
+    const int tw = min(gd.t2_w, gd.w - x0);
+    int src_pitch;
+    const uint8_t* src = level_roi(d, fl, gs, level - 1, frame, src_pitch);
+    uint8_t* dst = d.pyr + (size_t)frame * fl.pyr_bytes + gd.plane_off + (size_t)kEdge * gd.pitch + kXPad;
+    const ResizeTap* xt = d.xtab + gd.xtab_off + x0;
+    const int sxa = xt[0].ofs & ~15;                       // 16-byte aligned start of the staged columns
+    const int nvec = (xt[tw - 1].pad - sxa + 16) >> 4;     // 16-byte vectors per staged row
+    const int sp = gd.t2_cols;                             // bytes per staged row (multiple of 16, slack behind the last pixel)
+    const int CGX = gd.t2_w >> 2;                          // column groups of a full tile = thread layout [RY][CGX]
+    const int W4 = (tw + 3) >> 2;                          // column groups of this tile
+    // shared memory: [horizontal sums int4 x t2_rows x CGX][y taps int4 x t2_h][x offsets int x t2_w][x weights u32 x t2_w][source]
+    int4* s_h = reinterpret_cast<int4*>(smem);
+    int4* s_y = s_h + gd.t2_rows * CGX;
+    int* s_xo = reinterpret_cast<int*>(s_y + gd.t2_h);
+    uint32_t* s_xc = reinterpret_cast<uint32_t*>(s_xo + gd.t2_w);
+    unsigned char* s_src = reinterpret_cast<unsigned char*>(s_xc + gd.t2_w);
+    // ---- per CTA: the horizontal taps of my column group, the staging role of this thread
+    for (int i = tid; i < 4 * W4; i += kPyr2Threads) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(xt + min(i, tw - 1));       // {ofs, c0 | c1, pad}
+        s_xo[i] = (int)(raw.x & 0xffffu) - sxa;
+        s_xc[i] = (raw.x >> 16) | (raw.y << 16);                                       // c0 | c1 << 16
+    }
+    const int RV = kPyr2Threads / nvec;                    // nvec <= 64 (host: tiles <= ~1000 source bytes wide)
+    const int vr = tid / nvec, vc = tid - vr * nvec;
+    const int RY = kPyr2Threads / CGX;                     // >= 2 (host: CGX <= 176)
+    const int ry = tid / CGX, cg = tid - ry * CGX;
+    const bool mine = ry < RY && cg < W4;
+    __syncthreads();
+    int4 o = make_int4(0, 0, 0, 0);
+    uint32_t c0x = 0, c1x = 0, c0y = 0, c1y = 0, c0z = 0, c1z = 0, c0w = 0, c1w = 0;
+    if (mine) {
+        o = reinterpret_cast<const int4*>(s_xo)[cg];
+        const uint4 c = reinterpret_cast<const uint4*>(s_xc)[cg];
+        c0x = c.x & 0xffffu; c1x = c.x >> 16; c0y = c.y & 0xffffu; c1y = c.y >> 16;
+        c0z = c.z & 0xffffu; c1z = c.z >> 16; c0w = c.w & 0xffffu; c1w = c.w >> 16;
+    }
+    const int pstep = RY * sp, hstep = RY * CGX;
+    const ptrdiff_t rstep = (ptrdiff_t)RY * gd.pitch;
+    const size_t gstep = (size_t)RV * src_pitch;
+    const int sstep = RV * sp;
+    const int n_last = tw - 4 * cg;                        // >= 4: my four columns are a full word
+
+    const int ty_end = min(gd.t2_ny, (band + 1) * kPyr2Band);
+    for (int ty = band * kPyr2Band; ty < ty_end; ty++) {
+        const int y0 = ty * gd.t2_h;
+        const int th = min(gd.t2_h, gd.h - y0);
+        const ResizeTap* yt = d.ytab + gd.ytab_off + y0;
+        const int sy0 = yt[0].ofs;
+        const int nrows = yt[th - 1].pad - sy0 + 1;
+        // ---- stage the source footprint (thread = one 16-byte column of the footprint, rows strided) and the vertical taps
+        if (vr < RV) {
+            const uint8_t* gp = src + (size_t)(sy0 + vr) * src_pitch + sxa + 16 * vc;
+            unsigned char* sp_ = s_src + vr * sp + 16 * vc;
+            for (int r = vr; r < nrows; r += RV) {
+                *reinterpret_cast<uint4*>(sp_) = *reinterpret_cast<const uint4*>(gp);
+                gp += gstep; sp_ += sstep;
+            }
+        }
+        for (int i = tid; i < th; i += kPyr2Threads) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(yt + i);
+            const int ofs = (int)(raw.x & 0xffffu), c0 = (int)(raw.x >> 16), c1 = (int)(raw.y & 0xffffu), pad = (int)(raw.y >> 16);
+            s_y[i] = make_int4((ofs - sy0) * CGX * 16, (pad - sy0) * CGX * 16, c0 << 16, c1 << 16);   // byte offsets into s_h
+        }
+        __syncthreads();
+        // ---- phase H: my column group, source rows ry, ry + RY, ...
+        if (mine) {
+            const unsigned char* p = s_src + ry * sp;
+            const unsigned char *px = p + o.x, *py = p + o.y, *pz = p + o.z, *pw = p + o.w;
+            int4* ph = s_h + ry * CGX + cg;
+            for (int r = ry; r < nrows; r += RY) {
+                int4 hh;
+                hh.x = (int)(px[0] * c0x + px[1] * c1x) >> 4;
+                hh.y = (int)(py[0] * c0y + py[1] * c1y) >> 4;
+                hh.z = (int)(pz[0] * c0z + pz[1] * c1z) >> 4;
+                hh.w = (int)(pw[0] * c0w + pw[1] * c1w) >> 4;
+                *ph = hh;
+                px += pstep; py += pstep; pz += pstep; pw += pstep; ph += hstep;
+            }
+        }
+        __syncthreads();
+        // ---- phase V: my column group, output rows ry, ry + RY, ...
+        if (mine) {
+            uint8_t* row = dst + (ptrdiff_t)(y0 + ry) * gd.pitch + x0 + 4 * cg;
+            const int4* pt = s_y + ry;
+            const unsigned char* hb = reinterpret_cast<const unsigned char*>(s_h + cg);
+            for (int dy = ry; dy < th; dy += RY) {
+                const int4 t = *pt;
+                const int4 lo = *reinterpret_cast<const int4*>(hb + t.x), hi = *reinterpret_cast<const int4*>(hb + t.y);
+                const uint32_t b0 = (uint32_t)t.z, b1 = (uint32_t)t.w;
+                const uint32_t v0 = (__umulhi(b0, (uint32_t)lo.x) + __umulhi(b1, (uint32_t)hi.x) + 2u) >> 2;
+                const uint32_t v1 = (__umulhi(b0, (uint32_t)lo.y) + __umulhi(b1, (uint32_t)hi.y) + 2u) >> 2;
+                const uint32_t v2 = (__umulhi(b0, (uint32_t)lo.z) + __umulhi(b1, (uint32_t)hi.z) + 2u) >> 2;
+                const uint32_t v3 = (__umulhi(b0, (uint32_t)lo.w) + __umulhi(b1, (uint32_t)hi.w) + 2u) >> 2;
+                if (n_last >= 4) {
+                    *reinterpret_cast<uint32_t*>(row) = v0 + v1 * 256u + v2 * 65536u + v3 * 16777216u;     // every v <= 255
+                } else {
+                    row[0] = (uint8_t)v0;
+                    if (n_last > 1) row[1] = (uint8_t)v1;
+                    if (n_last > 2) row[2] = (uint8_t)v2;
+                }
+                row += rstep; pt += RY;
+            }
+        }
+        __syncthreads();      // the next row tile overwrites the staged source and the taps
+    }
+}
+
+static int launch_pyramid_v1(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
     int launches = 0;
     for (int l = 1; l < fl.nlevels; l++) {   // level 0 is the input image itself
         const LevelGeom& g = hg[l];
@@ -135,6 +273,28 @@ int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg,
         if (smem > 48 * 1024 || g.rs_cols > 256) return -1;   // scale factors this large are not supported
         const dim3 grid((g.w + kPyrTileW - 1) / kPyrTileW, (g.h + kPyrTileH - 1) / kPyrTileH, n_frames);
         pyr_resize_kernel<<<grid, 256, smem, s>>>(d, fl, l);
+        launches++;
+    }
+    return launches;
+}
+
+int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
+    // ORBCUDA_PYR=2 selects the two-phase kernel (A/B switch; results are identical, the first kernel is faster)
+    static const int variant = [] { const char* e = getenv("ORBCUDA_PYR"); return e ? atoi(e) : 1; }();
+    if (variant == 1) return launch_pyramid_v1(d, fl, hg, n_frames, s);
+    int max_smem = 0;
+    for (int l = 1; l < fl.nlevels; l++) {
+        max_smem = std::max(max_smem, hg[l].t2_smem);
+        if (hg[l].t2_smem <= 0) return launch_pyramid_v1(d, fl, hg, n_frames, s);     // a shape the two-phase tiling does not cover
+    }
+    if (max_smem > 160 * 1024) return launch_pyramid_v1(d, fl, hg, n_frames, s);
+    static DeviceOnce once;
+    if (!once.run([&] { return cudaFuncSetAttribute(pyr_resize2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess; }))
+        return -1;
+    int launches = 0;
+    for (int l = 1; l < fl.nlevels; l++) {
+        const LevelGeom& g = hg[l];
+        pyr_resize2_kernel<<<dim3(g.t2_nx * ((g.t2_ny + kPyr2Band - 1) / kPyr2Band), n_frames), kPyr2Threads, g.t2_smem, s>>>(d, fl, l);
         launches++;
     }
     return launches;
