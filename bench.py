@@ -883,6 +883,20 @@ def bench_matching(orb, synth, torch, dist, D, args, rank, world, local):
         ok = parity in (None, True)
     if not ok:
         raise SystemExit("bench.py: the 2000 x 1M 2-NN records differ from the CPU oracle")
+    # what one rank of an 8-GPU job does per search, measured alone (no exchange): the 2000 x 125k shard
+    shard = None
+    if world == 1:
+        ns = NM // 8
+        def shard_step():
+            rc = L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), NQ, C.c_void_p(d_m.data_ptr()), ns, 0, C.c_void_p(rec.data_ptr()), 5,
+                                    C.c_void_p(cur.cuda_stream))
+            assert rc == 0
+            return rec
+        for _ in range(5):
+            shard_step()
+        sms, _ = time_loop(shard_step, 200)
+        shard = {"map_descriptors": ns, "ms_per_search": sms, "ideal_ms_at_8_gpus": per_variant["tcgen05_cta_pair"]["ms_per_batch"] / 8,
+                 "note": "one rank's share of the 8-GPU search (search + split merge, no exchange) on one GPU"}
     tops = 2 * 256 * gcmp / 1e3                      # one comparison = 256 int8 MACs on the tensor pipe
     tops_sus = 2 * 256 * gcmp_sus / 1e3
     peak8 = 4500.0 * world                            # nominal dense 8-bit peak per GPU (B200_PROFILING.md) x GPUs
@@ -891,7 +905,7 @@ def bench_matching(orb, synth, torch, dist, D, args, rank, world, local):
                 "ms_per_batch": per_variant[bestv]["ms_per_batch"], "kernel": bestv, "variants": per_variant,
                 "sustained": {"value": gcmp_sus, "unit": "Gcmp/s", "ms_per_batch": sus_ms, "iterations": n_sus,
                               "timed_region_s": sus_ms * n_sus * 1e-3, "clocks": sus_clocks},
-                "map_shards": world, "d1_checksum": int(ref_out[:, 0].sum().item()), "parity_vs_oracle": parity,
+                "map_shards": world, "d1_checksum": int(ref_out[:, 0].sum().item()), "parity_vs_oracle": parity, "shard_of_8": shard,
                 "roofline": {"bound": "tensor", "achieved": tops, "peak": peak8, "unit": "TOP/s", "frac": tops / peak8,
                              "achieved_sustained": tops_sus, "frac_sustained": tops_sus / peak8,
                              "frac_vs_2x_measured_bf16_burst": tops / (2 * _bf16_peak()[0] * world),

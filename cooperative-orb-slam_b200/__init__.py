@@ -76,6 +76,8 @@ ABI = {
     "orbm_merge_top2_device": (_I, [_VP, _I, _I, _VP, _VP]),
     "orbm_merge_top2_host": (_I, [_VP, _I, _I, _VP]),
     "orbm_ratio_test_host": (_I, [_VP, _I, _F, _I, _I, _VP]),
+    "orbm_knn2_ratio_device": (_I, [_VP, _I, _VP, _I64, _I64, _F, _I, _I, _VP, _VP, _I, _VP]),
+    "orbm_ratio_test_device": (_I, [_VP, _I, _F, _I, _I, _VP, _VP]),
     "orbm_search_by_bow_kf_f": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _F, _I, _VP, _VP, _I]),
     "orbm_search_by_bow_kf_kf": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _F, _I, _VP, _VP, _I]),
     "orbm_search_for_triangulation": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _F, _F, _VP, _VP, _I, _I, _VP,

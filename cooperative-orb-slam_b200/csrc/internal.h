@@ -114,10 +114,33 @@ int launch_octree_single(const uint32_t* d_cand, int n, int width, int height, i
 size_t octree_smem_bytes(int node_cap);
 
 // matcher
-struct PeerExchange;   // peer.cu: symmetric record buffers of all ranks, mapped through CUDA IPC
-int launch_merge_exchange(PeerExchange* peer, const void* d_partial, int parts, int nq, int32_t* d_out, cudaStream_t s);
+constexpr int kMaxPeers = 16;
+// symmetric record buffers of the sharded map search (peer.cu): every rank owns one, mapped into every other rank through CUDA IPC
+struct PeerLayout {
+    // [2 parities][world][nq_cap] int4 records, then [2][kMaxPeers] flags, then an error word
+    int world, nq_cap;
+    __host__ __device__ size_t record_index(int parity, int rank, int q) const { return ((size_t)parity * world + rank) * nq_cap + q; }
+    __host__ __device__ size_t flags_offset() const { return (size_t)2 * world * nq_cap * sizeof(int4); }
+    __host__ __device__ size_t bytes() const { return flags_offset() + 2 * kMaxPeers * sizeof(unsigned) + 64; }
+};
+struct PeerPtrs { unsigned char* base[kMaxPeers]; };
+struct PeerExchange {
+    int device = 0, rank = 0, world = 0, nq_cap = 0;
+    PeerLayout layout{};
+    unsigned char* local = nullptr;
+    PeerPtrs peers{};
+    bool opened[kMaxPeers] = {false};
+    unsigned epoch = 0;
+    unsigned* d_counter = nullptr;      // blocks that finished the scatter phase
+    int* d_error = nullptr;             // set by the kernel when the bounded wait ran out
+    bool connected = false;
+};
+int launch_merge_exchange(PeerExchange* peer, const void* d_partial, int parts, int nq, int32_t* d_out, int* d_bound, int n_bound,
+                          cudaStream_t s);
+struct RatioTest { int32_t* d_match; float ratio; int th; int strict; };   // R21/src/ORBmatcher.cc:228-230 / :598-600 on the merged records
 int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out,
-                int variant, cudaStream_t s, PeerExchange* peer = nullptr);
+                int variant, cudaStream_t s, PeerExchange* peer = nullptr, const RatioTest* rt = nullptr);
+int launch_ratio_test(const int32_t* d_rec, int nq, const RatioTest& rt, cudaStream_t s);
 int launch_merge_top2(const int32_t* d_parts, int parts, int nq, int32_t* d_out, cudaStream_t s);
 void host_merge_top2(const int32_t* parts, int nparts, int nq, int32_t* out);
 

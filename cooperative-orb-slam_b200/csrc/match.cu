@@ -8,6 +8,12 @@
 // be searched independently and merged in any grouping.
 #include "internal.h"
 
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include <algorithm>
 
 namespace orbcuda {
@@ -1161,7 +1167,9 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             const int glim = pa - gval - 1;
             // a stale bound is still a bound: one L2 round trip every eighth tile, issued where nothing waits for it soon
             // (a load per tile stalled the loop top -- i.e. the TMEM hand-back -- for 23 % of the samples)
-            if ((i & kPairBoundEvery) == 0) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "+r"(gval) : "l"(gptr) : "memory");
+            // ... except over the first tiles, where the bound falls fastest: a search over a small map (one rank's shard of a
+            // sharded map is ~50 tiles per CTA) would otherwise run a sixth of its tiles against "no bound yet"
+            if ((i & kPairBoundEvery) == 0 || i < 8) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "+r"(gval) : "l"(gptr) : "memory");
             if (i >= kTcLag) drain_update(i - kTcLag, v, glim);
         }
         for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
@@ -1195,37 +1203,79 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
     }
 }
 
-__global__ void merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out) {
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
-    int d1 = 256, i1 = -1, d2 = 256, i2 = -1;
-    for (int p = 0; p < nparts; p++) {
-        const int4 r = parts[(size_t)p * nq + qi];
-        top2_merge(d1, i1, d2, i2, r.x, r.y, r.z, r.w);
+// Merge of the per-split (or per-rank) records of every query: ONE WARP PER QUERY, lane = split, a shuffle butterfly of
+// the associative lexicographic (distance, index) top-2 merge.  (A thread per query walking the splits one after the other
+// is a chain of ~18 dependent L2 round trips: 14 us for 2000 queries x 18 splits, a third of a 125k-descriptor search.)
+// bound / n_bound: the cross-CTA pruning bounds of the search that produced `parts` (tcgen05 variants); they are put back
+// to "no bound yet" here, behind the search, so that the next search on this stream finds them ready (no memset per call).
+// match != NULL: the reference's acceptance test on the merged record (R21/src/ORBmatcher.cc:228-230 / :598-600):
+// match[q] = i1 if d1 <= th (strict: d1 < th) and (float)d1 < ratio * (float)d2, else -1 -- the 2-NN search and its ratio test
+// leave the device as one result.
+__global__ void __launch_bounds__(256) merge_top2_kernel(const int4* __restrict__ parts, int nparts, int nq, int4* __restrict__ out,
+                                                         int* __restrict__ bound, int n_bound, int* __restrict__ match, float ratio, int th,
+                                                         int strict) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = gtid; i < n_bound; i += gridDim.x * blockDim.x) bound[i] = 0x7f7f7f7f;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int qi = gtid >> 5; qi < nq; qi += nwarps) {
+        int d1 = 256, i1 = -1, d2 = 256, i2 = -1;
+        for (int p = lane; p < nparts; p += 32) {
+            const int4 r = parts[(size_t)p * nq + qi];
+            top2_merge(d1, i1, d2, i2, r.x, r.y, r.z, r.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int e1 = __shfl_xor_sync(0xffffffffu, d1, o), j1 = __shfl_xor_sync(0xffffffffu, i1, o);
+            const int e2 = __shfl_xor_sync(0xffffffffu, d2, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o);
+            top2_merge(d1, i1, d2, i2, e1, j1, e2, j2);
+        }
+        if (lane == 0) {
+            if (out) out[qi] = make_int4(d1, i1, d2, i2);
+            if (match) match[qi] = ((strict ? d1 < th : d1 <= th) && __int2float_rn(d1) < __fmul_rn(ratio, __int2float_rn(d2))) ? i1 : -1;
+        }
     }
-    out[qi] = make_int4(d1, i1, d2, i2);
 }
 
+namespace {
+inline int merge_grid(int nq) { return (std::max(1, std::min((nq + 7) / 8, 1184)) + 1) & ~1; }      // a warp per query, 8 warps per CTA, <= 8 CTAs per SM
+
+constexpr size_t kKnnCounters = 4096;      // query blocks of one search (256 queries each)
+struct KnnScratch { int* bound; int* counters; int4* partial; };
+struct KnnScratchSlot { char* base = nullptr; size_t bound_cap = 0, partial_cap = 0; };
+std::mutex g_scratch_mu;
+std::map<std::pair<int, cudaStream_t>, KnnScratchSlot> g_scratch;
+
+// n_bound ints of pruning bounds + partial_bytes of records for a search on (dev, s).  Growing (rare: first call, larger
+// problem) drains the stream, replaces the buffer and initialises the whole bound region.
+bool knn_scratch(int dev, cudaStream_t s, size_t n_bound, size_t partial_bytes, KnnScratch* out) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    KnnScratchSlot& slot = g_scratch[std::make_pair(dev, s)];
+    if (!slot.base || n_bound > slot.bound_cap || partial_bytes > slot.partial_cap) {
+        const size_t bcap = std::max<size_t>(std::max(n_bound, slot.bound_cap), 4096);
+        const size_t pcap = std::max<size_t>(std::max(partial_bytes, slot.partial_cap) * 3 / 2, (size_t)1 << 20);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return false;
+        if (slot.base) cudaFree(slot.base);
+        slot = KnnScratchSlot();
+        char* p = nullptr;
+        if (cudaMalloc((void**)&p, (bcap + kKnnCounters) * sizeof(int) + pcap) != cudaSuccess) return false;
+        if (cudaMemsetAsync(p, 0x7f, bcap * sizeof(int), s) != cudaSuccess ||
+            cudaMemsetAsync(p + bcap * sizeof(int), 0, kKnnCounters * sizeof(int), s) != cudaSuccess) { cudaFree(p); return false; }
+        slot.base = p; slot.bound_cap = bcap; slot.partial_cap = pcap;
+    }
+    out->bound = reinterpret_cast<int*>(slot.base);
+    out->counters = out->bound + slot.bound_cap;
+    out->partial = reinterpret_cast<int4*>(slot.base + (slot.bound_cap + kKnnCounters) * sizeof(int));
+    return true;
+}
+}  // namespace
+
 int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out, int variant,
-                cudaStream_t s, PeerExchange* peer) {
+                cudaStream_t s, PeerExchange* peer, const RatioTest* rt) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // The per-call scratch comes from the stream-ordered allocator.  With the default release threshold (0) the pool
-    // hands its memory back to the OS at every synchronisation, and the next call pays a map/unmap (0.2 ms typically,
-    // several ms now and then): keep the few MB cached instead.  Once per device.
-    {
-        static DeviceOnce pool_once;
-        pool_once.run([&] {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            return true;
-        });
-    }
     const int qper = variant >= 3 ? kTcQ : (variant >= 1 ? kMmaQPerCta : kKnnThreads);
     const int tile = variant >= 3 ? kTcN : (variant == 1 ? kMmaTile : (variant == 2 ? 8 : kKnnTile));
     const int per_sm = variant >= 3 ? 1 : 2;
@@ -1239,40 +1289,40 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     int64_t per_split = (nm + splits - 1) / splits;
     per_split = (per_split + tile - 1) / tile * tile;
     splits = nm > 0 ? (int)((nm + per_split - 1) / per_split) : 1;
-    // per-call scratch from the stream-ordered allocator: matcher entry points are re-entrant
-    // variant 3 also keeps one int per (padded) query: the smallest second-best distance published by any CTA
-    const size_t bound_bytes = variant >= 3 ? (size_t)qblocks * kTcQ * sizeof(int) : 0;
-    const size_t need = (size_t)splits * nq * sizeof(int4) + bound_bytes;
-    int4* partial = nullptr;
-    if (cudaMallocAsync((void**)&partial, need, s) != cudaSuccess) return -1;
+    // scratch: one grow-only buffer per (device, stream) -- calls on one stream are ordered, so they can share it, and calls
+    // on different streams (the reference's three matcher threads) never do.  Layout: [pruning bounds][per-split records].
+    // The bounds are "no bound yet" (0x7f7f7f7f) whenever no search is in flight: the merge kernel behind every search
+    // restores the entries that search used.  Nothing is allocated, freed or cleared per call.
+    const int n_bound = variant >= 3 ? qblocks * kTcQ : 0;
+    KnnScratch sc;
+    if (!knn_scratch(dev, s, (size_t)n_bound, (size_t)splits * nq * sizeof(int4), &sc)) return -1;
+    int4* partial = sc.partial;
+    int* const bound = sc.bound;
     if (variant == 1) {
         const size_t smem = (size_t)kMmaTile * 256 + kMmaTile * sizeof(int);
         static DeviceOnce once_configured;
-        if (!once_configured.run([&] { return cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) { cudaFreeAsync(partial, s); return -1; }
+        if (!once_configured.run([&] { return cudaFuncSetAttribute(knn2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
         knn2_mma_kernel<<<dim3(qblocks, splits), kMmaThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint4*)d_m, nm, per_split,
                                                                        index_base, partial);
     } else if (variant == 3) {
         const size_t smem = (size_t)kTcQ * 256 + kTcBStages * (size_t)kTcN * 256 + 1024;
         static DeviceOnce once_configured3;
-        if (!once_configured3.run([&] { return cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) { cudaFreeAsync(partial, s); return -1; }
-        int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
-        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) { cudaFreeAsync(partial, s); return -1; }    // "no bound yet"
+        if (!once_configured3.run([&] { return cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+        int* shared_d2 = bound;
         knn2_tc_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                       index_base, partial, shared_d2);
     } else if (variant == 5) {
         const size_t smem = (size_t)kTcQ * 256 + kPairBStages * (size_t)kPairHalfN * 256 + 1024;
         static DeviceOnce once_configured5;
-        if (!once_configured5.run([&] { return cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) { cudaFreeAsync(partial, s); return -1; }
-        int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
-        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) { cudaFreeAsync(partial, s); return -1; }    // "no bound yet"
+        if (!once_configured5.run([&] { return cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+        int* shared_d2 = bound;
         knn2_pair_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                         index_base, partial, shared_d2);
     } else if (variant == 4) {
         const size_t smem = kTcBStages * (size_t)kTcN * 256 + 1024;
         static DeviceOnce once_configured4;
-        if (!once_configured4.run([&] { return cudaFuncSetAttribute(knn2_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) { cudaFreeAsync(partial, s); return -1; }
-        int* shared_d2 = reinterpret_cast<int*>(partial + (size_t)splits * nq);
-        if (cudaMemsetAsync(shared_d2, 0x7f, bound_bytes, s) != cudaSuccess) { cudaFreeAsync(partial, s); return -1; }    // "no bound yet"
+        if (!once_configured4.run([&] { return cudaFuncSetAttribute(knn2_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+        int* shared_d2 = bound;
         knn2_ts_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
                                                                       index_base, partial, shared_d2);
     } else if (variant == 2) {
@@ -1284,16 +1334,22 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     }
     if (peer) {
         // multi-GPU: merge my splits, push my records into every rank's buffer over NVLink, wait for theirs, merge: one kernel
-        if (launch_merge_exchange(peer, partial, splits, nq, d_out, s) < 0) { cudaFreeAsync(partial, s); return -1; }
+        if (launch_merge_exchange(peer, partial, splits, nq, d_out, bound, n_bound, s) < 0) return -1;
     } else {
-        merge_top2_kernel<<<(nq + 255) / 256, 256, 0, s>>>(partial, splits, nq, (int4*)d_out);
+        merge_top2_kernel<<<merge_grid(nq), 256, 0, s>>>(partial, splits, nq, (int4*)d_out, bound, n_bound, rt ? rt->d_match : nullptr,
+                                                           rt ? rt->ratio : 0.f, rt ? rt->th : 0, rt ? rt->strict : 0);
     }
-    cudaFreeAsync(partial, s);
     return 2;
 }
 
 int launch_merge_top2(const int32_t* d_parts, int parts, int nq, int32_t* d_out, cudaStream_t s) {
-    merge_top2_kernel<<<(nq + 255) / 256, 256, 0, s>>>((const int4*)d_parts, parts, nq, (int4*)d_out);
+    merge_top2_kernel<<<merge_grid(nq), 256, 0, s>>>((const int4*)d_parts, parts, nq, (int4*)d_out, nullptr, 0, nullptr, 0.f, 0, 0);
+    return 1;
+}
+
+// the ratio test alone on records already on the device (one "split")
+int launch_ratio_test(const int32_t* d_rec, int nq, const RatioTest& rt, cudaStream_t s) {
+    merge_top2_kernel<<<merge_grid(nq), 256, 0, s>>>((const int4*)d_rec, 1, nq, nullptr, nullptr, 0, rt.d_match, rt.ratio, rt.th, rt.strict);
     return 1;
 }
 

@@ -23,30 +23,6 @@
 
 namespace orbcuda {
 
-constexpr int kMaxPeers = 16;
-
-struct PeerLayout {
-    // [2 parities][world][nq_cap] int4 records, then [2][kMaxPeers] flags, then an error word
-    int world, nq_cap;
-    __host__ __device__ size_t record_index(int parity, int rank, int q) const { return ((size_t)parity * world + rank) * nq_cap + q; }
-    __host__ __device__ size_t flags_offset() const { return (size_t)2 * world * nq_cap * sizeof(int4); }
-    __host__ __device__ size_t bytes() const { return flags_offset() + 2 * kMaxPeers * sizeof(unsigned) + 64; }
-};
-
-struct PeerPtrs { unsigned char* base[kMaxPeers]; };
-
-struct PeerExchange {
-    int device = 0, rank = 0, world = 0, nq_cap = 0;
-    PeerLayout layout{};
-    unsigned char* local = nullptr;
-    PeerPtrs peers{};
-    bool opened[kMaxPeers] = {false};
-    unsigned epoch = 0;
-    unsigned* d_counter = nullptr;      // blocks that finished the scatter phase
-    int* d_error = nullptr;             // set by the kernel when the bounded wait ran out
-    bool connected = false;
-};
-
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -62,14 +38,27 @@ __device__ __forceinline__ void merge_rec(int4& a, const int4 b) {
 
 __global__ void __launch_bounds__(256) merge_exchange_kernel(const int4* __restrict__ parts, int nparts, int nq, int rank, PeerLayout L, PeerPtrs peers,
                                                              unsigned epoch, unsigned* __restrict__ counter, int* __restrict__ error,
-                                                             unsigned long long timeout_ns, int4* __restrict__ out) {
+                                                             unsigned long long timeout_ns, int4* __restrict__ out, int* __restrict__ bound,
+                                                             int n_bound) {
     const int parity = (int)(epoch & 1u);
-    // ---- phase 1: merge my splits, store my record into every rank's buffer
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    // the pruning bounds of the search in front of this kernel go back to "no bound yet" for the next one (match.cu)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bound; i += gridDim.x * blockDim.x) bound[i] = 0x7f7f7f7f;
+    // ---- phase 1: merge my splits (a warp per query, lane = split: one round of loads instead of a chain of them) and store
+    // the record into every rank's buffer (lane r stores to rank r)
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = gwarp; q < nq; q += nwarps) {
         int4 rec = make_int4(256, -1, 256, -1);
-        for (int p = 0; p < nparts; p++) merge_rec(rec, parts[(size_t)p * nq + q]);
+        for (int p = lane; p < nparts; p += 32) merge_rec(rec, parts[(size_t)p * nq + q]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int4 v;
+            v.x = __shfl_xor_sync(0xffffffffu, rec.x, o); v.y = __shfl_xor_sync(0xffffffffu, rec.y, o);
+            v.z = __shfl_xor_sync(0xffffffffu, rec.z, o); v.w = __shfl_xor_sync(0xffffffffu, rec.w, o);
+            merge_rec(rec, v);
+        }
         const size_t at = L.record_index(parity, rank, q);
-        for (int r = 0; r < L.world; r++) reinterpret_cast<int4*>(peers.base[r])[at] = rec;
+        for (int r = lane; r < L.world; r += 32) reinterpret_cast<int4*>(peers.base[r])[at] = rec;
     }
     __threadfence_system();
     __syncthreads();
@@ -91,32 +80,45 @@ __global__ void __launch_bounds__(256) merge_exchange_kernel(const int4* __restr
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(my_flags + threadIdx.x) != epoch) {
             if (global_timer_ns() - t0 > timeout_ns) { s_ok = 0; atomicExch(error, 1 + (int)threadIdx.x); break; }
-            __nanosleep(200);
+            __nanosleep(40);
         }
     }
     __syncthreads();
-    if (!s_ok) return;
+    if (!s_ok) {
+        // a peer did not arrive in time: the call's output is the "no match" record for every query, never stale data
+        for (int q = gwarp; q < nq; q += nwarps) if (lane == 0) out[q] = make_int4(256, -1, 256, -1);
+        return;
+    }
     const int4* mine = reinterpret_cast<const int4*>(peers.base[rank]);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    for (int q = gwarp; q < nq; q += nwarps) {
         int4 rec = make_int4(256, -1, 256, -1);
-        for (int r = 0; r < L.world; r++) {
+        for (int r = lane; r < L.world; r += 32) {
             int4 v;      // written by another GPU: read it past the L1
             asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                          : "l"(mine + L.record_index(parity, r, q)) : "memory");
             merge_rec(rec, v);
         }
-        out[q] = rec;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int4 v;
+            v.x = __shfl_xor_sync(0xffffffffu, rec.x, o); v.y = __shfl_xor_sync(0xffffffffu, rec.y, o);
+            v.z = __shfl_xor_sync(0xffffffffu, rec.z, o); v.w = __shfl_xor_sync(0xffffffffu, rec.w, o);
+            merge_rec(rec, v);
+        }
+        if (lane == 0) out[q] = rec;
     }
 }
 
-int launch_merge_exchange(PeerExchange* pe, const void* d_partial, int parts, int nq, int32_t* d_out, cudaStream_t s) {
+int launch_merge_exchange(PeerExchange* pe, const void* d_partial, int parts, int nq, int32_t* d_out, int* d_bound, int n_bound,
+                          cudaStream_t s) {
     if (!pe || !pe->connected || nq > pe->nq_cap) { set_error("merge-exchange: peer buffers not connected or nq > capacity"); return -1; }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pe->device);
-    const int grid = std::max(1, std::min((nq + 255) / 256, 2 * sms));      // resident for sure: 256 threads, a few registers
+    const int grid = std::max(1, std::min((nq + 7) / 8, 4 * sms));          // a warp per query; resident for sure: 256 threads, a few registers
+    merge_exchange_kernel<<<grid, 256, 0, s>>>((const int4*)d_partial, parts, nq, pe->rank, pe->layout, pe->peers, pe->epoch + 1, pe->d_counter,
+                                              pe->d_error, 5ull * 1000 * 1000 * 1000, (int4*)d_out, d_bound, n_bound);
+    if (cudaPeekAtLastError() != cudaSuccess) return -1;      // the epoch advances only with a launch that went out: ranks stay in step
     pe->epoch++;
-    merge_exchange_kernel<<<grid, 256, 0, s>>>((const int4*)d_partial, parts, nq, pe->rank, pe->layout, pe->peers, pe->epoch, pe->d_counter, pe->d_error,
-                                              5ull * 1000 * 1000 * 1000, (int4*)d_out);
     return 1;
 }
 
@@ -184,6 +186,7 @@ int orbm_knn2_exchange_device(orbm_peer_t p, const uint8_t* d_q, int nq, const u
     PeerExchange* pe = reinterpret_cast<PeerExchange*>(p);
     if (!pe || !d_q || nq < 1 || !d_out || nm < 0 || (nm > 0 && !d_m_shard) || variant < 0 || variant > 5) { set_error("orbm_knn2_exchange_device: bad arguments"); return ORB_ERR_ARG; }
     if ((reinterpret_cast<uintptr_t>(d_q) & 15) || (reinterpret_cast<uintptr_t>(d_m_shard) & 15)) { set_error("orbm_knn2_exchange_device: descriptor arrays must be 16-byte aligned"); return ORB_ERR_ARG; }
+    ORB_CUDA_TRY(cudaSetDevice(pe->device));
     if (launch_knn2(d_q, nq, d_m_shard, nm, index_base, d_out, variant, (cudaStream_t)stream, pe) < 0) {
         cuda_ok(cudaGetLastError(), "knn2 + exchange launch");
         return ORB_ERR_CUDA;
@@ -197,6 +200,7 @@ int orbm_peer_error(orbm_peer_t p, int* error) {
     if (!pe || !error) return ORB_ERR_ARG;
     ORB_CUDA_TRY(cudaSetDevice(pe->device));
     ORB_CUDA_TRY(cudaMemcpy(error, pe->d_error, 4, cudaMemcpyDeviceToHost));
+    if (*error) ORB_CUDA_TRY(cudaMemset(pe->d_error, 0, 4));      // reported once: the next exchange starts clean
     return ORB_OK;
 }
 

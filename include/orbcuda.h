@@ -165,6 +165,12 @@ int orbm_merge_top2_host(const int32_t* parts_rec, int parts, int nq, int32_t* o
 /* Acceptance test of R21 ORBmatcher.cc:228-230 on merged records: match iff d1 <= th (or < th when
  * strict) and (float)d1 < ratio*(float)d2.  out_match[i] = i1 or -1. */
 int orbm_ratio_test_host(const int32_t* rec, int nq, float ratio, int th, int strict, int32_t* out_match);
+/* The same acceptance test on the device.  orbm_knn2_ratio_device = orbm_knn2_device + the test in one call chain (the
+ * test is folded into the kernel that merges the map splits): d_match[q] = accepted nearest neighbour or -1; d_rec may be
+ * NULL.  orbm_ratio_test_device applies it to records already on the device (e.g. a sharded search's merged records). */
+int orbm_knn2_ratio_device(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, float ratio,
+                           int th, int strict, int32_t* d_rec, int32_t* d_match, int variant, void* stream);
+int orbm_ratio_test_device(const int32_t* d_rec, int nq, float ratio, int th, int strict, int32_t* d_match, void* stream);
 
 /* void MapPoint::ComputeDistinctiveDescriptors()  R21/src/MapPoint.cc:242-307, batched over map points.
  * Point p owns the descriptors of its (non-bad) observations desc[ptr[p] .. ptr[p+1]) (N x 32 bytes, host);

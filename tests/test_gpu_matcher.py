@@ -137,6 +137,41 @@ def test_stereo_matches(orb, oracle, synth, seed):
     assert n0 == 0 and (ur0 == -1).all()
 
 
+def test_knn2_with_device_ratio_test(orb, oracle, synth):
+    """2-NN + the reference's acceptance test (ORBmatcher.cc:228-230 / :598-600) on the device in one call chain, and the test
+    alone on device-resident records: both equal the host formula on the oracle's records."""
+    import ctypes as C
+    import torch
+    m = synth.descriptors(30000, seed=21)
+    q, m, _ = synth.query_set(m, nq=700, seed=22)
+    L = oracle.lib()
+    i1, d1, d2 = (np.zeros(len(q), np.int32) for _ in range(3))
+    L.orc_knn2(q.ctypes.data, len(q), m.ctypes.data, len(m), 0, i1.ctypes.data, d1.ctypes.data, d2.ctypes.data, 4)
+    dq = torch.from_numpy(q).cuda(); dm = torch.from_numpy(m).cuda()
+    rec = torch.zeros((len(q), 4), dtype=torch.int32, device="cuda"); match = torch.zeros(len(q), dtype=torch.int32, device="cuda")
+    lib = orb.lib()
+    for ratio, th, strict in ((0.6, 50, 0), (0.75, 50, 1), (0.9, 100, 0)):
+        want = np.where(((d1 < th) if strict else (d1 <= th)) & (d1.astype(np.float32) < np.float32(ratio) * d2.astype(np.float32)), i1, -1)
+        for variant in (0, 5):
+            rc = lib.orbm_knn2_ratio_device(C.c_void_p(dq.data_ptr()), len(q), C.c_void_p(dm.data_ptr()), len(m), 0, ratio, th, strict,
+                                            C.c_void_p(rec.data_ptr()), C.c_void_p(match.data_ptr()), variant, None)
+            assert rc == 0, lib.orb_last_error()
+            torch.cuda.synchronize()
+            assert np.array_equal(match.cpu().numpy(), want) and np.array_equal(rec.cpu().numpy()[:, 0], d1)
+        match.zero_()
+        assert lib.orbm_ratio_test_device(C.c_void_p(rec.data_ptr()), len(q), ratio, th, strict, C.c_void_p(match.data_ptr()), None) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(match.cpu().numpy(), want)
+    assert (want >= 0).sum() > 100
+    # the host-array entry point runs on the calling thread's workspace: repeated calls, growing sizes
+    for n in (100, 5000, 400000):
+        mm = synth.descriptors(n, seed=n)
+        bi, bd, sd, si = orb.ORBmatcher().knn2(q[:64], mm)
+        j1, e1, e2 = (np.zeros(64, np.int32) for _ in range(3))
+        L.orc_knn2(q.ctypes.data, 64, mm.ctypes.data, n, 0, j1.ctypes.data, e1.ctypes.data, e2.ctypes.data, 4)
+        assert np.array_equal(bi, j1) and np.array_equal(bd, e1) and np.array_equal(sd, e2)
+
+
 def test_stereo_matches_batch_device(orb, oracle, synth):
     """Batch form (two extractors per stereo frame, Frame.cc:80-83, then ComputeStereoMatches with its outlier cut, all
     on the device): every pair must equal the oracle's per-pair result."""
