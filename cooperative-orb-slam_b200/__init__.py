@@ -62,6 +62,7 @@ ABI = {
     "orbx_extract_batch_device": (_I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _VP, _VP, _I, _VP]),
     "orbx_level_size": (_I, [_VP, _I, _VP, _VP]),
     "orbx_download_level": (_I, [_VP, _I, _I, _I, _VP, _SZ]),
+    "orbx_download_pyramid": (_I, [_VP, _I, _I, _VP, _VP]),
     "orbx_download_blurred": (_I, [_VP, _I, _I, _VP, _SZ]),
     "orbx_download_candidates": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I, _VP]),
     "orbx_download_scores": (_I, [_VP, _I, _I, _VP, _SZ]),

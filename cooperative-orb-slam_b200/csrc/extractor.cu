@@ -85,6 +85,20 @@ struct orbx_handle_s {
     uint8_t* h_desc = nullptr; size_t cap_h_desc = 0;
     int32_t* h_counts = nullptr; size_t cap_h_counts = 0;
 
+    // CUDA graph of the kernel chain for small (latency-bound) calls: captured on the second call with the same signature,
+    // replayed afterwards -- one graph launch instead of 13 kernel launches (ORBCUDA_GRAPH=0 disables it)
+    struct GraphKey {
+        int n_frames, width, height, cap, in_pitch; const void *in, *kps, *desc, *counts; size_t in_stride;
+        bool operator==(const GraphKey& o) const {
+            return n_frames == o.n_frames && width == o.width && height == o.height && cap == o.cap && in_pitch == o.in_pitch && in == o.in &&
+                   kps == o.kps && desc == o.desc && counts == o.counts && in_stride == o.in_stride;
+        }
+    };
+    cudaGraphExec_t graph_exec = nullptr;
+    GraphKey graph_key = {}, graph_seen = {};
+    int graph_kernels = 0;
+    int64_t graph_replays = 0;
+
     // pending async call
     bool pending = false;
     int p_frames = 0, p_cap = 0;
@@ -305,6 +319,8 @@ int ensure_size(orbx_handle_s* h, int width, int height, int n_frames) {
         if ((rc = build_geometry(h, width, height))) return rc;
         if ((rc = upload_geometry(h))) return rc;
         h->cur_w = width; h->cur_h = height;
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        h->graph_seen = orbx_handle_s::GraphKey{};
     }
     const FrameLayout& fl = h->fl;
     const size_t B = (size_t)n_frames;
@@ -359,6 +375,54 @@ int enqueue_kernels(orbx_handle_s* h, const uint8_t* d_in, size_t in_frame_strid
     h->launches += n;
     if (prof) cudaEventRecord(h->ev[7], s);
     ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+constexpr int kGraphMaxFrames = 4;
+
+// enqueue_kernels, through a CUDA graph when the call is small and repeats an earlier call's signature
+int enqueue_kernels_maybe_graph(orbx_handle_s* h, const uint8_t* d_in, size_t in_frame_stride, int n_frames, int width, int height,
+                                orb_keypoint_t* d_kps, uint8_t* d_desc, int32_t* d_counts, int cap) {
+    static const bool enabled = [] { const char* e = getenv("ORBCUDA_GRAPH"); return e ? atoi(e) != 0 : true; }();
+    if (!enabled || h->profiling || n_frames > kGraphMaxFrames) return enqueue_kernels(h, d_in, in_frame_stride, n_frames, d_kps, d_desc, d_counts, cap);
+    const orbx_handle_s::GraphKey key = {n_frames, width, height, cap, h->fl.in_pitch, d_in, d_kps, d_desc, d_counts, in_frame_stride};
+    if (h->graph_exec && key == h->graph_key) {
+        ORB_CUDA_TRY(cudaGraphLaunch(h->graph_exec, h->stream));
+        h->launches += h->graph_kernels;
+        h->graph_replays++;
+        h->last_in = d_in; h->last_in_stride = in_frame_stride; h->last_in_pitch = h->fl.in_pitch;
+        return ORB_OK;
+    }
+    if (!(key == h->graph_seen)) {       // first call with this signature: plain launches (also warms lazily loaded kernels)
+        h->graph_seen = key;
+        return enqueue_kernels(h, d_in, in_frame_stride, n_frames, d_kps, d_desc, d_counts, cap);
+    }
+    // second call: capture the chain, instantiate, replay
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    const int64_t before = h->launches;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return enqueue_kernels(h, d_in, in_frame_stride, n_frames, d_kps, d_desc, d_counts, cap);
+    }
+    const int rc = enqueue_kernels(h, d_in, in_frame_stride, n_frames, d_kps, d_desc, d_counts, cap);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (rc != ORB_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->graph_seen = orbx_handle_s::GraphKey{};
+        h->launches = before;
+        return rc != ORB_OK ? rc : enqueue_kernels(h, d_in, in_frame_stride, n_frames, d_kps, d_desc, d_counts, cap);
+    }
+    h->graph_kernels = (int)(h->launches - before);
+    h->launches = before;
+    const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); h->graph_exec = nullptr; return enqueue_kernels(h, d_in, in_frame_stride, n_frames, d_kps, d_desc, d_counts, cap); }
+    h->graph_key = key;
+    ORB_CUDA_TRY(cudaGraphLaunch(h->graph_exec, h->stream));
+    h->launches += h->graph_kernels;
+    h->graph_replays++;
     return ORB_OK;
 }
 
@@ -453,6 +517,7 @@ int orbx_destroy(orbx_handle_t h) {
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return ORB_OK;
@@ -592,7 +657,7 @@ int orbx_extract_batch_async(orbx_handle_t h, const uint8_t* images, int n_frame
                 memcpy(h->h_in + f * dev_frame + (size_t)y * fl.in_pitch, images + f * frame_stride + (size_t)y * row_stride, width);
         ORB_CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, (size_t)n_frames * dev_frame, cudaMemcpyHostToDevice, s));
     }
-    if ((rc = enqueue_kernels(h, h->d_in, dev_frame, n_frames, h->d_kps, h->d_desc, h->d_counts, cap))) {
+    if ((rc = enqueue_kernels_maybe_graph(h, h->d_in, dev_frame, n_frames, width, height, h->d_kps, h->d_desc, h->d_counts, cap))) {
         cudaStreamSynchronize(h->stream);   // the upload may still be reading the pinned staging buffer
         return rc;
     }
@@ -686,6 +751,45 @@ int orbx_download_level(orbx_handle_t h, int frame, int level, int with_border, 
         for (int k = 1; k <= b; k++) {
             memcpy(roi + (ptrdiff_t)(-k) * (ptrdiff_t)dst_stride - b, roi + (size_t)refl(-k, g.h) * dst_stride - b, g.w + 2 * b);
             memcpy(roi + (size_t)(g.h - 1 + k) * dst_stride - b, roi + (size_t)refl(g.h - 1 + k, g.h) * dst_stride - b, g.w + 2 * b);
+        }
+    }
+    return ORB_OK;
+}
+
+// All levels of one frame in one go (the mvImagePyramid mirror of the C++ class): the copies are queued back to back on the
+// handle's stream -- truly asynchronous when the destination planes are page-locked (orb_host_alloc) -- and waited for once;
+// the REFLECT_101 borders are rebuilt on the host as in orbx_download_level.
+int orbx_download_pyramid(orbx_handle_t h, int frame, int with_border, uint8_t* const* dst, const size_t* dst_stride) {
+    if (!h || !dst || !dst_stride || frame < 0 || frame >= h->last_frames) return ORB_ERR_ARG;
+    ORB_CUDA_TRY(cudaSetDevice(h->device));
+    const int b = with_border ? kEdge : 0;
+    const int L = (int)h->geom.size();
+    for (int level = 0; level < L; level++) {
+        const LevelGeom& g = h->geom[level];
+        if (!dst[level]) return ORB_ERR_ARG;
+        uint8_t* roi = dst[level] + (size_t)b * dst_stride[level] + b;
+        if (level == 0)
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(roi, dst_stride[level], h->last_in + (size_t)frame * h->last_in_stride, h->last_in_pitch, g.w, g.h,
+                                           cudaMemcpyDeviceToHost, h->stream));
+        else
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(roi, dst_stride[level], h->d_pyr + (size_t)frame * h->fl.pyr_bytes + g.plane_off + (size_t)kEdge * g.pitch + kXPad,
+                                           g.pitch, g.w, g.h, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ORB_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (b) {
+        auto refl = [](int p, int len) { if (p < 0) p = -p; if (p >= len) p = 2 * len - 2 - p; return p; };
+        for (int level = 0; level < L; level++) {
+            const LevelGeom& g = h->geom[level];
+            const size_t st = dst_stride[level];
+            uint8_t* roi = dst[level] + (size_t)b * st + b;
+            for (int y = 0; y < g.h; y++) {
+                uint8_t* row = roi + (size_t)y * st;
+                for (int k = 1; k <= b; k++) { row[-k] = row[refl(-k, g.w)]; row[g.w - 1 + k] = row[refl(g.w - 1 + k, g.w)]; }
+            }
+            for (int k = 1; k <= b; k++) {
+                memcpy(roi + (ptrdiff_t)(-k) * (ptrdiff_t)st - b, roi + (size_t)refl(-k, g.h) * st - b, g.w + 2 * b);
+                memcpy(roi + (size_t)(g.h - 1 + k) * st - b, roi + (size_t)refl(g.h - 1 + k, g.h) * st - b, g.w + 2 * b);
+            }
         }
     }
     return ORB_OK;

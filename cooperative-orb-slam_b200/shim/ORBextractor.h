@@ -37,7 +37,9 @@ public:
 
     // Host mirror of the device pyramid: every element is the ROI (+19,+19) of a padded plane, exactly
     // like the reference (R21/src/ORBextractor.cc:1113-1116), so Frame::ComputeStereoMatches may read
-    // it (R21/src/Frame.cc:478,568,585).  Filled after each call unless SetPyramidMirror(false).
+    // it (R21/src/Frame.cc:478,568,585).  Filled after each call (eight queued downloads into page-locked planes, one
+    // synchronisation) unless SetPyramidMirror(false) or ORBCUDA_PYRAMID_MIRROR=0: monocular tracking never reads it and
+    // the drop-in's stereo search (orbaccel::ComputeStereoMatches) uses the device pyramids.
     std::vector<cv::Mat> mvImagePyramid;
 
     // ---- additions (not in the reference) ----
@@ -49,7 +51,10 @@ protected:
     orbx_handle_s* mpHandle;
     bool mbMirrorPyramid;
     static int msDevice;
-    std::vector<cv::Mat> mvPadded;
+    std::vector<cv::Mat> mvPadded;       // headers over the page-locked planes below
+    std::vector<void*> mvPinned;
+    void* mpStage = 0;                   // page-locked key point / descriptor staging of the current image size
+    int mnCapWidth, mnCapHeight, mnCap;
 
     int nfeatures;
     double scaleFactor;

@@ -108,6 +108,10 @@ int orbx_level_size(orbx_handle_t h, int level, int* width, int* height);
 /* mvImagePyramid[level] (R21/include/ORBextractor.h:85; ROI of the padded plane :1113-1116).
  * with_border != 0 copies the (w+38) x (h+38) padded plane, else the w x h ROI. */
 int orbx_download_level(orbx_handle_t h, int frame, int level, int with_border, uint8_t* dst, size_t dst_stride);
+/* The same for every level of one frame at once (the whole mvImagePyramid mirror): dst[l] / dst_stride[l] = plane and row stride
+ * of level l, (w_l + 38) x (h_l + 38) with the border.  One stream synchronisation instead of one per level; the copies are
+ * asynchronous when the planes are page-locked (orb_host_alloc). */
+int orbx_download_pyramid(orbx_handle_t h, int frame, int with_border, uint8_t* const* dst, const size_t* dst_stride);
 /* The 7x7 sigma=2 blurred level used for descriptors (R21 :1085-1086). */
 int orbx_download_blurred(orbx_handle_t h, int frame, int level, uint8_t* dst, size_t dst_stride);
 /* vToDistributeKeys of a level (R21 :789-826): candidates in cell-major, raster-in-cell order;

@@ -21,6 +21,7 @@
 #include <string>
 #include <cmath>
 #include <algorithm>
+#include <chrono>
 
 #include <opencv2/opencv.hpp>
 
@@ -411,6 +412,29 @@ int mh_search_by_sim3(void* h, int k1, int k2, int32_t* matches12, float s12, co
 int mh_descriptor_distance(const uint8_t* a, const uint8_t* b) {
     cv::Mat ma(1, 32, CV_8U, (void*)a), mb(1, 32, CV_8U, (void*)b);
     return ORBmatcher::DescriptorDistance(ma, mb);
+}
+
+// per-frame latency of ORBextractor::operator() as Tracking calls it (Tracking.cc:258-260 -> Frame.cc:252-258), wall clock, in
+// milliseconds: mirror = 0 / 1 switches the mvImagePyramid host mirror of the drop-in (ignored by the reference build)
+double mh_extract_latency_ms(void* h, const uint8_t* img, size_t stride, int iters, int mirror, int* n_keys) {
+    World* w = (World*)h;
+    cv::Mat im(w->rows, w->cols, CV_8UC1, (void*)img, stride);
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat desc;
+#ifdef MH_CUDA_DROPIN
+    w->ext_l->SetPyramidMirror(mirror != 0);
+#else
+    (void)mirror;
+#endif
+    for (int i = 0; i < 3; i++) (*w->ext_l)(im, cv::Mat(), keys, desc);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < iters; i++) (*w->ext_l)(im, cv::Mat(), keys, desc);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+    if (n_keys) *n_keys = (int)keys.size();
+#ifdef MH_CUDA_DROPIN
+    w->ext_l->SetPyramidMirror(true);
+#endif
+    return ms;
 }
 
 #ifdef MH_CUDA_DROPIN

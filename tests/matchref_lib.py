@@ -248,6 +248,14 @@ class World:
         self.L.mh_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
         return self.L.mh_descriptor_distance(_p(a), _p(b))
 
+    def extract_latency_ms(self, img, iters=100, mirror=True):
+        img = np.ascontiguousarray(img, np.uint8)
+        n = C.c_int(0)
+        self.L.mh_extract_latency_ms.restype = C.c_double
+        self.L.mh_extract_latency_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+        ms = self.L.mh_extract_latency_ms(self.h, _p(img), img.strides[0], int(iters), int(mirror), C.byref(n))
+        return ms, n.value
+
     def frame_stereo_accel(self, f):
         n = self.frame_n(f)
         ur = np.zeros(n, np.float32); dep = np.zeros(n, np.float32)

@@ -232,3 +232,25 @@ def test_cuda_dropin_frames_from_images(synth):
         assert m == int((a["u_right"] >= 0).sum()) and np.array_equal(ur, a["u_right"]) and np.array_equal(dep, a["depth"])
     else:      # a descriptor at a rounding boundary (<= 0.1 %): the match lists may differ in those few features
         assert (a["u_right"] != b["u_right"]).sum() <= 5
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not mr.available("shim_cuda"), reason="oracle/_ref/libmatchshim_cuda.so not built")
+def test_cuda_dropin_single_frame_calls(synth):
+    """operator() called frame after frame through the C++ class (the reference's real calling pattern): the replayed CUDA graph
+    and the one-synchronisation pyramid mirror give the same key points as the first (plain) call, and the latency is reported."""
+    K = np.array([517.3, 516.5, 318.6, 255.3], np.float32)
+    w = mr.World("shim_cuda", K, np.zeros(4, np.float32), 40.0, 35.0, 640, 480, nfeatures=1000)
+    imgs = [synth.frame(s, 640, 480) for s in range(3)]
+    first = [w.frame_get(w.frame_from_image(im))["kps"].tobytes() for im in imgs]
+    again = [w.frame_get(w.frame_from_image(im))["kps"].tobytes() for im in imgs]      # these run through the captured graph
+    assert first == again
+    wr = mr.World("ref", K, np.zeros(4, np.float32), 40.0, 35.0, 640, 480, nfeatures=1000)
+    assert [wr.frame_get(wr.frame_from_image(im))["kps"].tobytes() for im in imgs] == first
+    ms_on, n = w.extract_latency_ms(imgs[0], 200, True)
+    ms_off, _ = w.extract_latency_ms(imgs[0], 200, False)
+    ms_ref, _ = wr.extract_latency_ms(imgs[0], 5, True)
+    print("\nshim operator() per frame: %.3f ms with the mvImagePyramid mirror, %.3f ms without; reference CPU %.1f ms (%d key points)"
+          % (ms_on, ms_off, ms_ref, n))
+    assert n > 900 and ms_off <= ms_on
+    w.close(); wr.close()
