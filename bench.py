@@ -1005,6 +1005,7 @@ def run_ours(args):
     exchange = None
     if world > 1:
         exchange = bench_keyframe_exchange(orb, torch, dist, D, world, local, host_frames[0], cfg)
+        _note("key-frame exchange: %.3f ms (NCCL arrays), fused message path %s" % (exchange["ms_per_exchange"], exchange.get("fused_message_exchange")))
 
     # single-frame latency through the synchronous reference-shaped call (operator())
     one = orb.ORBextractor(cfg["nfeat"], 1.2, 8, 20, 7, device=local)
@@ -1146,9 +1147,55 @@ def bench_keyframe_exchange(orb, torch, dist, D, world, local, frames, cfg):
     D.barrier()
     xms = D.max(x0.elapsed_time(x1)) / 20
     msg = kf_k.numel() * 4 + kf_d.numel() + kf_c.numel() * 4
+    out = {"keyframes_per_agent": KF, "bytes_per_agent": msg, "ms_per_exchange": xms, "allgather_gbs": world * msg / (xms * 1e-3) / 1e9,
+           "path": "orbw_quantize_lcm_device + 3 x ncclAllGather of the cap-padded arrays",
+           "note": "reference: one LCM UDP-multicast message of 10 key frames, descriptors as float32 (4x the bytes)"}
+    # the library's own message path: pack (compacted to the key point counts, int16 truncation applied) -> ONE fused exchange kernel
+    # over peer memory (stores into every rank's slot over NVLink, flag, wait, copy-out) -> unpack of every agent's message
+    def gather_bytes(b):
+        t = torch.tensor(list(b), dtype=torch.uint8, device=dev)
+        allt = torch.empty((world, len(b)), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allt, t)
+        return [bytes(allt[r].cpu().numpy().tobytes()) for r in range(world)]
+    nbytes = orb.message_bytes(KF, cap, 0)
+    ok = 1
+    peer = None
+    try:
+        peer = orb.PeerExchange(nbytes // 16, int(os.environ.get("RANK", "0")), world, local, gather_bytes)
+    except Exception:      # noqa: BLE001 -- CUDA IPC unavailable: reported as fused = null
+        ok = 0
+    if D.min(ok) == 1:
+        d_msg = torch.zeros(nbytes, dtype=torch.uint8, device=dev); d_all = torch.zeros((world, nbytes), dtype=torch.uint8, device=dev)
+        o_k = torch.empty_like(all_k); o_d = torch.empty_like(all_d); o_c = torch.empty_like(all_c)
+
+        def fused_step():
+            orb.pack_keyframes_device(kf_k.data_ptr(), kf_d.data_ptr(), kf_c.data_ptr(), KF, cap, d_msg.data_ptr(), stream=cur.cuda_stream)
+            peer.exchange_messages(d_msg.data_ptr(), nbytes, d_all.data_ptr(), nbytes, cur.cuda_stream)
+            for r in range(world):
+                orb.unpack_keyframes_device(d_all[r].data_ptr(), KF, cap, 0, o_k[r].data_ptr(), o_d[r].data_ptr(), o_c[r].data_ptr(), stream=cur.cuda_stream)
+
+        for _ in range(3):
+            fused_step()
+        D.barrier()
+        x0.record(cur)
+        for _ in range(20):
+            fused_step()
+        x1.record(cur)
+        D.barrier()
+        fms = D.max(x0.elapsed_time(x1)) / 20
+        assert peer.error() == 0
+        same = bool((o_c == all_c).all().item())
+        n0 = int(all_c[0, 0].item())
+        same = same and bool((o_d[0, 0, :n0] == all_d[0, 0, :n0]).all().item()) and bool((o_k[0, 0, :n0] == all_k[0, 0, :n0]).all().item())
+        out["fused_message_exchange"] = {"ms_per_exchange": fms, "message_bytes": nbytes, "equals_nccl_path": same,
+                                         "path": "orbw_pack_keyframes_device + orbw_exchange_messages_device (one kernel, peer stores over NVLink) + "
+                                                 "orbw_unpack_keyframes_device x world"}
+    else:
+        out["fused_message_exchange"] = None
+    if peer is not None:
+        peer.close()
     ext.close()
-    return {"keyframes_per_agent": KF, "bytes_per_agent": msg, "ms_per_exchange": xms, "allgather_gbs": world * msg / (xms * 1e-3) / 1e9,
-            "note": "reference: one LCM UDP-multicast message of 10 key frames, descriptors as float32 (4x the bytes)"}
+    return out
 
 
 def main():

@@ -112,6 +112,10 @@ ABI = {
     "orbm_peer_destroy": (_I, [_VP]),
     "orbw_quantize_lcm_host": (_I, [_VP, _I]),
     "orbw_quantize_lcm_device": (_I, [_VP, _VP, _I, _I, _VP]),
+    "orbw_message_bytes": (_SZ, [_I, _I, _I]),
+    "orbw_pack_keyframes_device": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP]),
+    "orbw_unpack_keyframes_device": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "orbw_exchange_messages_device": (_I, [_VP, _VP, _SZ, _VP, _SZ, _VP]),
 }
 
 
@@ -614,6 +618,12 @@ class PeerExchange:
         _check(lib().orbm_knn2_exchange_device(self._h, C.c_void_p(d_q_ptr), int(nq), C.c_void_p(d_m_ptr), int(nm), int(index_base),
                                                C.c_void_p(d_out_ptr), int(variant), C.c_void_p(stream)), "orbm_knn2_exchange_device")
 
+    def exchange_messages(self, d_msg_ptr, nbytes, d_all_ptr, slot_bytes, stream=0):
+        """All-gather of one key-frame message per rank over the peer buffers (orbw_exchange_messages_device):
+        d_all = [world][slot_bytes]."""
+        _check(lib().orbw_exchange_messages_device(self._h, C.c_void_p(d_msg_ptr), int(nbytes), C.c_void_p(d_all_ptr), int(slot_bytes),
+                                                   C.c_void_p(stream)), "orbw_exchange_messages_device")
+
     def error(self):
         e = C.c_int(0)
         _check(lib().orbm_peer_error(self._h, C.byref(e)), "orbm_peer_error")
@@ -622,6 +632,25 @@ class PeerExchange:
     def close(self):
         if self._h:
             lib().orbm_peer_destroy(self._h); self._h = C.c_void_p()
+
+
+def message_bytes(n_frames, cap, flags=0):
+    return int(lib().orbw_message_bytes(int(n_frames), int(cap), int(flags)))
+
+
+def pack_keyframes_device(d_kps, d_desc, d_counts, n_frames, cap, d_msg, d_kps_un=0, d_u_right=0, d_depth=0, d_mappoints=0, stream=0):
+    """The agent -> server key-frame message (csrc/wire.cu) from device-resident extractor output; raw device addresses.
+    Returns the message's flags (1 stereo | 2 map points | 4 kps_un)."""
+    vp = lambda a: C.c_void_p(a) if a else None
+    _check(lib().orbw_pack_keyframes_device(vp(d_kps), vp(d_kps_un), vp(d_desc), vp(d_counts), vp(d_u_right), vp(d_depth), vp(d_mappoints),
+                                            int(n_frames), int(cap), vp(d_msg), vp(stream)), "orbw_pack_keyframes_device")
+    return (1 if d_u_right else 0) | (2 if d_mappoints else 0) | (4 if d_kps_un else 0)
+
+
+def unpack_keyframes_device(d_msg, n_frames, cap, flags, d_kps, d_desc, d_counts, d_kps_un=0, d_u_right=0, d_depth=0, d_mappoints=0, stream=0):
+    vp = lambda a: C.c_void_p(a) if a else None
+    _check(lib().orbw_unpack_keyframes_device(vp(d_msg), int(n_frames), int(cap), int(flags), vp(d_kps), vp(d_kps_un), vp(d_desc), vp(d_counts),
+                                              vp(d_u_right), vp(d_depth), vp(d_mappoints), vp(stream)), "orbw_unpack_keyframes_device")
 
 
 def quantize_lcm(keys):

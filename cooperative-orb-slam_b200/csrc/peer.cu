@@ -109,6 +109,51 @@ __global__ void __launch_bounds__(256) merge_exchange_kernel(const int4* __restr
     }
 }
 
+// The same protocol for an opaque message (the key-frame message of wire.cu): every rank stores its `units` 16-byte units into
+// slot [rank] of every rank's buffer, the last block publishes the flag, every block waits for all flags and copies the
+// world's slots out of its own buffer into dst ([world][dst_units]).
+__global__ void __launch_bounds__(256) blob_exchange_kernel(const int4* __restrict__ src, int units, int rank, PeerLayout L, PeerPtrs peers, unsigned epoch,
+                                                            unsigned* __restrict__ counter, int* __restrict__ error, unsigned long long timeout_ns,
+                                                            int4* __restrict__ dst, size_t dst_units) {
+    const int parity = (int)(epoch & 1u);
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    for (int r = 0; r < L.world; r++) {
+        int4* slot = reinterpret_cast<int4*>(peers.base[r]) + L.record_index(parity, rank, 0);
+        for (int i = gtid; i < units; i += gsize) slot[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        if ((int)threadIdx.x < L.world)
+            st_release_sys(reinterpret_cast<unsigned*>(peers.base[threadIdx.x] + L.flags_offset()) + parity * kMaxPeers + rank, epoch);
+        if (threadIdx.x == 0) *counter = 0;
+    }
+    const unsigned* my_flags = reinterpret_cast<const unsigned*>(peers.base[rank] + L.flags_offset()) + parity * kMaxPeers;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < L.world) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(my_flags + threadIdx.x) != epoch) {
+            if (global_timer_ns() - t0 > timeout_ns) { s_ok = 0; atomicExch(error, 1 + (int)threadIdx.x); break; }
+            __nanosleep(40);
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    for (int r = 0; r < L.world; r++) {
+        const int4* slot = reinterpret_cast<const int4*>(peers.base[rank]) + L.record_index(parity, r, 0);
+        for (int i = gtid; i < units; i += gsize) {
+            int4 v;      // written by another GPU: read it past the L1
+            asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(slot + i) : "memory");
+            dst[(size_t)r * dst_units + i] = v;
+        }
+    }
+}
+
 int launch_merge_exchange(PeerExchange* pe, const void* d_partial, int parts, int nq, int32_t* d_out, int* d_bound, int n_bound,
                           cudaStream_t s) {
     if (!pe || !pe->connected || nq > pe->nq_cap) { set_error("merge-exchange: peer buffers not connected or nq > capacity"); return -1; }
@@ -192,6 +237,28 @@ int orbm_knn2_exchange_device(orbm_peer_t p, const uint8_t* d_q, int nq, const u
         return ORB_ERR_CUDA;
     }
     ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+// All-gather of one opaque message per rank over the peer buffers (orbm_peer_create with nq_cap >= bytes / 16): d_all receives
+// [world][slot_bytes].  Same calling rules as orbm_knn2_exchange_device (every rank makes the same sequence of calls on this
+// peer object; use a separate object for messages and for searches).
+int orbw_exchange_messages_device(orbm_peer_t p, const void* d_msg, size_t bytes, void* d_all, size_t slot_bytes, void* stream) {
+    PeerExchange* pe = reinterpret_cast<PeerExchange*>(p);
+    if (!pe || !pe->connected || !d_msg || !d_all || (bytes & 15) || (slot_bytes & 15) || bytes > slot_bytes || bytes / 16 > (size_t)pe->nq_cap ||
+        (reinterpret_cast<uintptr_t>(d_msg) & 15) || (reinterpret_cast<uintptr_t>(d_all) & 15)) {
+        set_error("orbw_exchange_messages_device: bad arguments (16-byte aligned buffers, bytes <= slot_bytes, bytes / 16 <= the peer's capacity)");
+        return ORB_ERR_ARG;
+    }
+    ORB_CUDA_TRY(cudaSetDevice(pe->device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pe->device);
+    const int units = (int)(bytes / 16);
+    const int grid = std::max(1, std::min((units + 255) / 256, 2 * sms));
+    blob_exchange_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const int4*)d_msg, units, pe->rank, pe->layout, pe->peers, pe->epoch + 1, pe->d_counter, pe->d_error,
+                                                                 5ull * 1000 * 1000 * 1000, (int4*)d_all, slot_bytes / 16);
+    ORB_CUDA_TRY(cudaGetLastError());
+    pe->epoch++;
     return ORB_OK;
 }
 

@@ -408,6 +408,22 @@ int orbv_bow_vectors(const int32_t* word, const int32_t* node, const double* wei
 int orbw_quantize_lcm_host(orb_keypoint_t* kps, int n);
 int orbw_quantize_lcm_device(void* d_kps, const int32_t* d_counts, int n_frames, int cap, void* stream);
 
+/* The key-frame message as one contiguous device buffer for a batch of key frames (what lcmKeyFrameInfo carries for the
+ * server's KeyFrame rebuild, R21/include/lcmKeyFrame/lcmKeyFrameInfo.hpp:24-145, filled ros_mono.cc:1929-2399, decoded
+ * ORB_SLAM2/Examples/ROS/ORB_SLAM2/src/ros_mono.cc:230-544): per frame the key point count, mvKeys (and optionally mvKeysUn)
+ * with the wire's int16 truncation applied, the 32-byte descriptors, optionally mvuRight / mvDepth and per feature the
+ * map-point record {x, y, z, has} of lcmKeyFrameMapPoints (16 bytes).  Entries are compacted to the counts; the section
+ * offsets depend on (n_frames, cap, flags) only.  flags = 1 (u_right + depth) | 2 (map points) | 4 (kps_un), derived from
+ * the non-NULL inputs by pack and passed to unpack.  orbw_message_bytes = size of the buffer (a multiple of 16). */
+size_t orbw_message_bytes(int n_frames, int cap, int flags);
+int orbw_pack_keyframes_device(const void* d_kps, const void* d_kps_un, const uint8_t* d_desc, const int32_t* d_counts,
+                               const float* d_u_right, const float* d_depth, const float* d_mappoints, int n_frames,
+                               int cap, void* d_msg, void* stream);
+/* d_counts[f] = -1 if the message does not match (n_frames, cap, flags). */
+int orbw_unpack_keyframes_device(const void* d_msg, int n_frames, int cap, int flags, void* d_kps, void* d_kps_un,
+                                 uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth,
+                                 float* d_mappoints, void* stream);
+
 /* ---------------------------------------------------------------- sharded map search: fused merge + exchange ---- */
 /* The one exchange step of the cross-agent map search without NCCL: every rank (one process per GPU) owns a
  * symmetric record buffer, shared through CUDA IPC; orbm_knn2_exchange_device searches the rank's map shard and then ONE
@@ -422,6 +438,11 @@ int orbm_peer_create(int nq_cap, int rank, int world, int device, orbm_peer_t* o
 int orbm_peer_connect(orbm_peer_t p, const void* handles /* [world][64] */);
 int orbm_knn2_exchange_device(orbm_peer_t p, const uint8_t* d_q, int nq, const uint8_t* d_m_shard, int64_t nm,
                               int64_t index_base, int32_t* d_out, int variant, void* stream);
+/* All-gather of one message per rank (agent -> every server) over the same peer buffers, ONE kernel: stores into every
+ * rank's slot over NVLink, flag, bounded wait, copy-out.  d_all = [world][slot_bytes]; the peer object must have been
+ * created with nq_cap >= bytes / 16 and should not be shared with searches. */
+int orbw_exchange_messages_device(orbm_peer_t p, const void* d_msg, size_t bytes, void* d_all, size_t slot_bytes,
+                                  void* stream);
 int orbm_peer_error(orbm_peer_t p, int* error);
 int orbm_peer_destroy(orbm_peer_t p);
 

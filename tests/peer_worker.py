@@ -52,9 +52,56 @@ def main():
                 checked += 1
     dist.barrier()
     peer.close()
+    # ---- the key-frame message: every rank packs its own key frames, one fused exchange, every rank unpacks everybody's
+    B, cap = 10, 1027
+    flags = 1 | 2 | 4
+    nbytes = orb.message_bytes(B, cap, flags)
+    mpeer = orb.PeerExchange(nbytes // 16, rank, world, local, gather_bytes)
+
+    def case(r):
+        rng = np.random.default_rng(100 + r)
+        k = np.zeros((B, cap), orb.KP_DTYPE)
+        for f in ("x", "y", "size", "response"):
+            k[f] = rng.uniform(0, 1500, (B, cap)).astype(np.float32)
+        k["angle"] = rng.uniform(0, 360, (B, cap)).astype(np.float32); k["octave"] = rng.integers(0, 8, (B, cap)); k["class_id"] = -1
+        ku = k.copy(); ku["x"] += np.float32(0.37)
+        desc = rng.integers(0, 256, (B, cap, 32), dtype=np.uint8)
+        cnt = rng.integers(0, cap + 1, B).astype(np.int32)
+        ur = rng.uniform(-1, 700, (B, cap)).astype(np.float32); dep = rng.uniform(-1, 40, (B, cap)).astype(np.float32)
+        mp = rng.normal(0, 5, (B, cap, 4)).astype(np.float32)
+        return k, ku, desc, cnt, ur, dep, mp
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
+    k, ku, desc, cnt, ur, dep, mp = case(rank)
+    d = [t(a) for a in (k, ku, desc, cnt, ur, dep, mp)]
+    msg = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    allmsg = torch.zeros((world, nbytes), dtype=torch.uint8, device=dev)
+    for rep in range(3):
+        orb.pack_keyframes_device(d[0].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), B, cap, msg.data_ptr(), d[1].data_ptr(), d[4].data_ptr(),
+                                  d[5].data_ptr(), d[6].data_ptr(), stream=cur.cuda_stream)
+        mpeer.exchange_messages(msg.data_ptr(), nbytes, allmsg.data_ptr(), nbytes, cur.cuda_stream)
+        torch.cuda.synchronize()
+        assert mpeer.error() == 0
+        for r in range(world):
+            ek, eku, edesc, ecnt, eur, edep, emp = case(r)
+            o = [torch.zeros_like(x) for x in d]
+            orb.unpack_keyframes_device(allmsg[r].data_ptr(), B, cap, flags, o[0].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), o[1].data_ptr(),
+                                        o[4].data_ptr(), o[5].data_ptr(), o[6].data_ptr(), stream=cur.cuda_stream)
+            torch.cuda.synchronize()
+            gc = o[3].cpu().numpy().view(np.int32)
+            assert np.array_equal(gc, ecnt), (rank, r)
+            gk = o[0].cpu().numpy().view(orb.KP_DTYPE).reshape(B, cap); gd = o[2].cpu().numpy().reshape(B, cap, 32)
+            gmp = o[6].cpu().numpy().view(np.float32).reshape(B, cap, 4)
+            for b in range(B):
+                n = ecnt[b]
+                assert gk[b, :n].tobytes() == orb.quantize_lcm(ek[b, :n]).tobytes() and np.array_equal(gd[b, :n], edesc[b, :n])
+                assert np.array_equal(gmp[b, :n], emp[b, :n])
+    dist.barrier()
+    mpeer.close()
     dist.destroy_process_group()
     if rank == 0:
-        print("peer exchange ok: %d searches identical to the single-GPU result on %d ranks" % (checked, world))
+        print("peer exchange ok: %d searches identical to the single-GPU result on %d ranks; key-frame messages of %d bytes exchanged and unpacked"
+              % (checked, world, nbytes))
 
 
 if __name__ == "__main__":
