@@ -1171,8 +1171,8 @@ def bench_keyframe_exchange(orb, torch, dist, D, world, local, frames, cfg):
         def fused_step():
             orb.pack_keyframes_device(kf_k.data_ptr(), kf_d.data_ptr(), kf_c.data_ptr(), KF, cap, d_msg.data_ptr(), stream=cur.cuda_stream)
             peer.exchange_messages(d_msg.data_ptr(), nbytes, d_all.data_ptr(), nbytes, cur.cuda_stream)
-            for r in range(world):
-                orb.unpack_keyframes_device(d_all[r].data_ptr(), KF, cap, 0, o_k[r].data_ptr(), o_d[r].data_ptr(), o_c[r].data_ptr(), stream=cur.cuda_stream)
+            orb.unpack_keyframes_device(d_all.data_ptr(), KF, cap, 0, o_k.data_ptr(), o_d.data_ptr(), o_c.data_ptr(), stream=cur.cuda_stream,
+                                        n_msgs=world, msg_stride=nbytes)
 
         for _ in range(3):
             fused_step()
@@ -1189,7 +1189,7 @@ def bench_keyframe_exchange(orb, torch, dist, D, world, local, frames, cfg):
         same = same and bool((o_d[0, 0, :n0] == all_d[0, 0, :n0]).all().item()) and bool((o_k[0, 0, :n0] == all_k[0, 0, :n0]).all().item())
         out["fused_message_exchange"] = {"ms_per_exchange": fms, "message_bytes": nbytes, "equals_nccl_path": same,
                                          "path": "orbw_pack_keyframes_device + orbw_exchange_messages_device (one kernel, peer stores over NVLink) + "
-                                                 "orbw_unpack_keyframes_device x world"}
+                                                 "orbw_unpack_keyframes_device (all agents, one launch)"}
     else:
         out["fused_message_exchange"] = None
     if peer is not None:

@@ -114,7 +114,7 @@ ABI = {
     "orbw_quantize_lcm_device": (_I, [_VP, _VP, _I, _I, _VP]),
     "orbw_message_bytes": (_SZ, [_I, _I, _I]),
     "orbw_pack_keyframes_device": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP]),
-    "orbw_unpack_keyframes_device": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "orbw_unpack_keyframes_device": (_I, [_VP, _I, _SZ, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "orbw_exchange_messages_device": (_I, [_VP, _VP, _SZ, _VP, _SZ, _VP]),
 }
 
@@ -647,9 +647,12 @@ def pack_keyframes_device(d_kps, d_desc, d_counts, n_frames, cap, d_msg, d_kps_u
     return (1 if d_u_right else 0) | (2 if d_mappoints else 0) | (4 if d_kps_un else 0)
 
 
-def unpack_keyframes_device(d_msg, n_frames, cap, flags, d_kps, d_desc, d_counts, d_kps_un=0, d_u_right=0, d_depth=0, d_mappoints=0, stream=0):
+def unpack_keyframes_device(d_msg, n_frames, cap, flags, d_kps, d_desc, d_counts, d_kps_un=0, d_u_right=0, d_depth=0, d_mappoints=0, stream=0,
+                            n_msgs=1, msg_stride=0):
+    """n_msgs messages msg_stride bytes apart (the [world][slot_bytes] result of PeerExchange.exchange_messages) in one launch; the
+    outputs are then [n_msgs][n_frames][cap]."""
     vp = lambda a: C.c_void_p(a) if a else None
-    _check(lib().orbw_unpack_keyframes_device(vp(d_msg), int(n_frames), int(cap), int(flags), vp(d_kps), vp(d_kps_un), vp(d_desc), vp(d_counts),
+    _check(lib().orbw_unpack_keyframes_device(vp(d_msg), int(n_msgs), int(msg_stride), int(n_frames), int(cap), int(flags), vp(d_kps), vp(d_kps_un), vp(d_desc), vp(d_counts),
                                               vp(d_u_right), vp(d_depth), vp(d_mappoints), vp(stream)), "orbw_unpack_keyframes_device")
 
 

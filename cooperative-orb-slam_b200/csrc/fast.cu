@@ -48,9 +48,12 @@ template <bool HF> __device__ __forceinline__ uint32_t mn2(uint32_t a, uint32_t 
 //   c0=(p[x0+4],p[x0+6]) c1=(p[x0+5],p[x0+7])
 struct Row6 { uint32_t a0, a1, b0, b1, c0, c1; };
 
+template <bool HF> __device__ __forceinline__ Row6 unpack_row6(uint32_t w0, uint32_t w1, uint32_t w2);
 template <bool HF> __device__ __forceinline__ Row6 load_row6(const uint8_t* p) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return unpack_row6<HF>(w[0], w[1], w[2]);
+}
+template <bool HF> __device__ __forceinline__ Row6 unpack_row6(uint32_t w0, uint32_t w1, uint32_t w2) {
     // one PRMT per pair: bytes (0, 2) resp. (1, 3) of the word into the low bytes of the two 16-bit lanes, the high bytes
     // from B (HF: 0x64, every lane then holds the fp16 value 1024 + p)
     const uint32_t B = HF ? 0x64646464u : 0u;
@@ -124,7 +127,7 @@ template <bool HF> __device__ __forceinline__ uint32_t fast_score4(const Row6 (&
     return __byte_perm(sP, sQ, 0x6240);
 }
 
-template <bool HF> __global__ void __launch_bounds__(128, 6) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
+template <bool HF> __global__ void __launch_bounds__(128, 5) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
     if (blockIdx.x == 0) {
         // this frame's survivor counters and cell flags, consumed by fast_nms_kernel two launches later on the same
         // stream (saves two memset nodes per batch)
@@ -151,17 +154,36 @@ template <bool HF> __global__ void __launch_bounds__(128, 6) fast_score_kernel(D
     for (int b = 0; b < 4; b++)
         if (x0 + b >= kEdge && x0 + b < g.w - kEdge) colmask |= 0xffu << (8 * b);
 
+    // The 7-row window lives in registers and turns by one row per output row.  The row loop is rolled in blocks of seven
+    // fully unrolled rows: after seven rows the window is back in the registers it started in (no copies), and the body is
+    // half the code of a 14-row unroll -- the straight-line version streamed 56 KB of instructions once per warp and a
+    // fifth of its stall samples were instruction-cache misses.  The three words of the NEXT row are requested a whole row
+    // of arithmetic ahead of their use (the load of a row used to sit right in front of its first use: long-scoreboard
+    // stalls were the top reason).
     Row6 r[7];
 #pragma unroll
     for (int k = 0; k < 6; k++) r[k] = load_row6<HF>(src + (ptrdiff_t)(y0 - 3 + k) * pitch);
+    uint32_t n0, n1, n2;
+    {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)min(y0 + 3, g.h - 1) * pitch);
+        n0 = w[0]; n1 = w[1]; n2 = w[2];
+    }
+    static_assert(kFastRows % 7 == 0, "blocks of seven rows");
+#pragma unroll 1
+    for (int blk = 0; blk < kFastRows / 7; blk++) {
 #pragma unroll
-    for (int j = 0; j < kFastRows; j++) {
-        const int y = y0 + j;
-        r[6] = load_row6<HF>(src + (ptrdiff_t)min(y + 3, g.h - 1) * pitch);
-        const uint32_t s4 = fast_score4<HF>(r, th) & colmask;
-        if (y < g.h - kEdge) *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.spitch) = s4;
+        for (int j = 0; j < 7; j++) {
+            const int y = y0 + blk * 7 + j;
+            r[6] = unpack_row6<HF>(n0, n1, n2);
+            {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)min(y + 4, g.h - 1) * pitch);
+                n0 = w[0]; n1 = w[1]; n2 = w[2];
+            }
+            const uint32_t s4 = fast_score4<HF>(r, th) & colmask;
+            if (y < g.h - kEdge) *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.spitch) = s4;
 #pragma unroll
-        for (int k = 0; k < 6; k++) r[k] = r[k + 1];
+            for (int k = 0; k < 6; k++) r[k] = r[k + 1];
+        }
     }
 }
 

@@ -332,7 +332,6 @@ int launch_repack(const uint8_t* src, size_t src_row, size_t src_frame, uint8_t*
 // (row sums <= 255*256 fit 16 bits).  Vertical pass in 32 bit with the symmetric-tap factoring.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlurRows = 16;
-constexpr int kBlurEdgeRows = 4;   // edge strips gather bytes: keep those threads short
 
 
 
@@ -368,17 +367,25 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
             const uint32_t* p = reinterpret_cast<const uint32_t*>(row + x0 - 4);
             w0[k] = p[0]; w1[k] = p[1]; w2[k] = p[2];
         } else {
-            uint32_t a = 0, b = 0, c = 0;
+            // Edge strips: a word of the window that lies inside the row is loaded whole, only the others are put together
+            // byte by byte with reflected column indices (12 byte loads per row made these few strips 40 % of the blur time).
+            // Left edge (x0 == 0): the window's first word is pixels (4, 3, 2, 1) -- one PRMT of the two words that follow.
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(row + x0);
+            uint32_t a, b, c;
+            if (x0 + 3 < w) b = p[0];
+            else {
+                b = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                int xa = x0 - 4 + i, xb = x0 + i, xc = x0 + 4 + i;
-                xa = xa < 0 ? -xa : xa;
-                xb = xb >= w ? max(2 * w - 2 - xb, 0) : xb;
-                xc = xc >= w ? max(2 * w - 2 - xc, 0) : xc;
-                a |= (uint32_t)row[xa] << (8 * i);
-                b |= (uint32_t)row[xb] << (8 * i);
-                c |= (uint32_t)row[xc] << (8 * i);
+                for (int i = 0; i < 4; i++) { int xb = x0 + i; xb = xb >= w ? max(2 * w - 2 - xb, 0) : xb; b |= (uint32_t)row[xb] << (8 * i); }
             }
+            if (x0 + 7 < w) c = p[1];
+            else {
+                c = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { int xc = x0 + 4 + i; xc = xc >= w ? max(2 * w - 2 - xc, 0) : xc; c |= (uint32_t)row[xc] << (8 * i); }
+            }
+            if (x0 >= 4) a = p[-1];
+            else a = __byte_perm(b, c, 0x1234);          // x0 == 0 (levels are far wider than 8 px: b and c are plain words here)
             w0[k] = a; w1[k] = b; w2[k] = c;
         }
     }
@@ -422,46 +429,45 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
     }
 }
 
-// EDGE = false: the interior strips (4 <= x0 <= w-8) of every level; EDGE = true: the 2-3 edge strips per strip row.
-template <bool EDGE>
-__global__ void __launch_bounds__(128) blur7_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb) {
+// One launch: the interior strips (4 <= x0 <= w-8) of every level first, then the 2-3 edge strips per strip row of every
+// level (blocks >= lb_edge.start[0] -- whole blocks take one path or the other).
+__global__ void __launch_bounds__(128) blur7_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, LevelBlocks lb_edge) {
+    const bool edge = (int)blockIdx.x >= lb_edge.start[0];
+    const LevelBlocks& B = edge ? lb_edge : lb;
     int level = 0;
-    while (level + 1 < fl.nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
+    while (level + 1 < fl.nlevels && (int)blockIdx.x >= B.start[level + 1]) level++;
     const LevelGeom g = d.geom[level];
     // strips of a level are flattened so every block is full whatever the level width
     const int nsx = (g.w + 3) >> 2;
     const int ni = max((g.w - 8) >> 2, 0);            // interior strips per row: x0 = 4, 8, ..., 4*ni
-    const int per_row = EDGE ? nsx - ni : ni;
-    constexpr int ROWS = EDGE ? kBlurEdgeRows : kBlurRows;
-    const int nsy = (g.h + ROWS - 1) / ROWS;
-    const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
+    const int per_row = edge ? nsx - ni : ni;
+    const int nsy = (g.h + kBlurRows - 1) / kBlurRows;
+    const int id = (blockIdx.x - B.start[level]) * blockDim.x + threadIdx.x;
     if (id >= per_row * nsy) return;
     int pitch;
     const uint8_t* src = level_roi(d, fl, g, level, blockIdx.y, pitch);
     uint8_t* dst = d.blur + (size_t)blockIdx.y * fl.splane_bytes + g.splane_off;
     const int sy = id / per_row, k = id - sy * per_row;
-    const int x0 = EDGE ? (k == 0 ? 0 : 4 * (ni + k)) : 4 + 4 * k;
-    blur_strip<EDGE, ROWS>(src, pitch, dst, g.spitch, g.w, g.h, x0, sy * ROWS);
+    if (edge) blur_strip<true, kBlurRows>(src, pitch, dst, g.spitch, g.w, g.h, k == 0 ? 0 : 4 * (ni + k), sy * kBlurRows);
+    else blur_strip<false, kBlurRows>(src, pitch, dst, g.spitch, g.w, g.h, 4 + 4 * k, sy * kBlurRows);
 }
 
 int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
     const int threads = 128;
+    LevelBlocks lb[2];
+    int total = 0;
     for (int edge = 0; edge < 2; edge++) {
-        LevelBlocks lb;
-        int total = 0;
         for (int l = 0; l < fl.nlevels; l++) {
-            lb.start[l] = total;
+            lb[edge].start[l] = total;
             const int nsx = (hg[l].w + 3) / 4, ni = std::max((hg[l].w - 8) / 4, 0);
-            const int rows = edge ? kBlurEdgeRows : kBlurRows;
-            const int strips = (edge ? nsx - ni : ni) * ((hg[l].h + rows - 1) / rows);
+            const int strips = (edge ? nsx - ni : ni) * ((hg[l].h + kBlurRows - 1) / kBlurRows);
             total += (strips + threads - 1) / threads;
         }
-        for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
-        if (total == 0) continue;
-        if (edge) blur7_kernel<true><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb);
-        else blur7_kernel<false><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb);
+        for (int l = fl.nlevels; l <= kMaxLevels; l++) lb[edge].start[l] = total;
     }
-    return 2;
+    if (total == 0) return 0;
+    blur7_kernel<<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb[0], lb[1]);
+    return 1;
 }
 
 }  // namespace orbcuda

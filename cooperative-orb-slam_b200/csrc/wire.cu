@@ -108,11 +108,19 @@ __global__ void __launch_bounds__(256) wire_pack_kernel(const orb_keypoint_t* __
     for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) o_d[i] = desc[2 * base + i];
 }
 
-__global__ void __launch_bounds__(256) wire_unpack_kernel(const unsigned char* __restrict__ msg, int n_frames, int cap, int flags,
+// blockIdx.y = message (one per sending agent, msg_stride bytes apart); the outputs are [n_msgs][n_frames][cap]
+__global__ void __launch_bounds__(256) wire_unpack_kernel(const unsigned char* __restrict__ msg, size_t msg_stride, int n_frames, int cap, int flags,
                                                           orb_keypoint_t* __restrict__ kps, orb_keypoint_t* __restrict__ kps_un, uint4* __restrict__ desc,
                                                           int* __restrict__ counts, float* __restrict__ u_right, float* __restrict__ depth,
                                                           float4* __restrict__ mappoints) {
     const int f = blockIdx.x;
+    {
+        const size_t m = blockIdx.y, fo = m * n_frames * (size_t)cap;
+        msg += m * msg_stride; kps += fo; desc += 2 * fo; counts += m * n_frames;
+        if (kps_un) kps_un += fo;
+        if (u_right) { u_right += fo; depth += fo; }
+        if (mappoints) mappoints += fo;
+    }
     const int* hdr = reinterpret_cast<const int*>(msg);
     if (hdr[0] != kWireMagic || hdr[1] != n_frames || hdr[4] != cap || hdr[3] != flags) { if (threadIdx.x == 0) counts[f] = -1; return; }
     const WireSections w = wire_sections(n_frames, (size_t)n_frames * cap, flags);
@@ -153,11 +161,11 @@ int orbw_pack_keyframes_device(const void* d_kps, const void* d_kps_un, const ui
     return ORB_OK;
 }
 
-int orbw_unpack_keyframes_device(const void* d_msg, int n_frames, int cap, int flags, void* d_kps, void* d_kps_un, uint8_t* d_desc, int32_t* d_counts,
-                                 float* d_u_right, float* d_depth, float* d_mappoints, void* stream) {
-    if (!d_msg || n_frames < 1 || cap < 1 || !d_kps || !d_desc || !d_counts || (reinterpret_cast<uintptr_t>(d_msg) & 15) ||
+int orbw_unpack_keyframes_device(const void* d_msg, int n_msgs, size_t msg_stride, int n_frames, int cap, int flags, void* d_kps, void* d_kps_un,
+                                 uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth, float* d_mappoints, void* stream) {
+    if (!d_msg || n_msgs < 1 || (msg_stride & 15) || n_frames < 1 || cap < 1 || !d_kps || !d_desc || !d_counts || (reinterpret_cast<uintptr_t>(d_msg) & 15) ||
         (reinterpret_cast<uintptr_t>(d_desc) & 15) || (d_u_right && !d_depth)) { set_error("orbw_unpack_keyframes_device: bad arguments"); return ORB_ERR_ARG; }
-    wire_unpack_kernel<<<n_frames, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)d_msg, n_frames, cap, flags, (orb_keypoint_t*)d_kps, (orb_keypoint_t*)d_kps_un,
+    wire_unpack_kernel<<<dim3(n_frames, n_msgs), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)d_msg, msg_stride, n_frames, cap, flags, (orb_keypoint_t*)d_kps, (orb_keypoint_t*)d_kps_un,
                                                                   (uint4*)d_desc, d_counts, d_u_right, d_depth, (float4*)d_mappoints);
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;

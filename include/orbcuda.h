@@ -419,10 +419,12 @@ size_t orbw_message_bytes(int n_frames, int cap, int flags);
 int orbw_pack_keyframes_device(const void* d_kps, const void* d_kps_un, const uint8_t* d_desc, const int32_t* d_counts,
                                const float* d_u_right, const float* d_depth, const float* d_mappoints, int n_frames,
                                int cap, void* d_msg, void* stream);
-/* d_counts[f] = -1 if the message does not match (n_frames, cap, flags). */
-int orbw_unpack_keyframes_device(const void* d_msg, int n_frames, int cap, int flags, void* d_kps, void* d_kps_un,
-                                 uint8_t* d_desc, int32_t* d_counts, float* d_u_right, float* d_depth,
-                                 float* d_mappoints, void* stream);
+/* n_msgs messages (one per sending agent, msg_stride bytes apart: the [world][slot_bytes] result of the exchange below) in ONE
+ * launch; outputs are [n_msgs][n_frames][cap] (counts [n_msgs][n_frames]).  d_counts[m][f] = -1 if message m does not match
+ * (n_frames, cap, flags). */
+int orbw_unpack_keyframes_device(const void* d_msg, int n_msgs, size_t msg_stride, int n_frames, int cap, int flags,
+                                 void* d_kps, void* d_kps_un, uint8_t* d_desc, int32_t* d_counts, float* d_u_right,
+                                 float* d_depth, float* d_mappoints, void* stream);
 
 /* ---------------------------------------------------------------- sharded map search: fused merge + exchange ---- */
 /* The one exchange step of the cross-agent map search without NCCL: every rank (one process per GPU) owns a
