@@ -9,16 +9,12 @@
 // (__float2int_rn).  cos/sin are evaluated in double and rounded once to float (the reference calls
 // libm cosf/sinf, which is not correctly rounded and differs between glibc builds).
 #include "internal.h"
+#include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 
 namespace orbcuda {
-
-__constant__ int8_t c_pattern[1024] = {
-#include "orb_pattern.inc"
-};
-// u_max of the 31x31 circular patch (R21 :452-469)
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 // cv::fastAtan2 scalar path (OpenCV core/mathfuncs_core atan_f32)
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -44,65 +40,116 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-// round-half-even of |v| < 2^22 without the conversion pipe: adding 1.5*2^23 leaves rint(v) in the low mantissa bits
-__device__ __forceinline__ int round_rn(float v) {
-    return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4b400000;
-}
-
 constexpr int kDescWarps = 4;
 constexpr int kPatchR = 18;                     // the pattern's largest radius is 18.38 (point (-13,-13)): |cvRound(rotated coordinate)| <= 18
-constexpr int kPatchRows = 2 * kPatchR + 1;     // 37 rows of the blurred level around a key point
-constexpr int kPatchStride = 64;                // bytes per staged row: four 16-byte chunks (the 128-bit stores of a quarter warp cover two whole rows: no bank conflicts)
+constexpr int kBlurBoxW = 80, kBlurBoxH = 2 * kPatchR + 1;    // TMA box of the blurred level: 37 rows x 80 bytes from the 16-byte aligned column at or left of x - 18
+constexpr int kImgBoxW = 48, kImgBoxH = 31;                   // TMA box of the un-blurred level: 31 rows x 48 bytes from the aligned column at or left of x - 15
+constexpr int kStageBytes = 3072;               // one staging buffer (>= 80 * 37 = 2960, a multiple of 128)
 
 __device__ __forceinline__ int dp4a_us(uint32_t px, uint32_t w, int acc) {   // 4 unsigned pixels x 4 signed weights
     int r;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(px), "r"(w), "r"(acc));
     return r;
 }
+__device__ __forceinline__ uint32_t dsc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dsc_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+// one elected lane: arm the barrier with the box size and start the bulk tensor copy (TMA) of one box into shared memory;
+// columns / rows of the box outside the tensor are zero-filled by the copy engine (they are never used)
+__device__ __forceinline__ void dsc_tma_box(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int frame, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(frame) : "memory");
+}
 
-// per key point of a warp's group: what the two cooperative phases need, broadcast through shared memory
-struct __align__(16) KpWork {
-    const uint8_t* img;     // un-blurred level, pixel (x - 15, y)                       } first 16 bytes: moments
-    int pitch, cx;          // cx = x - (16-byte aligned start column of the staged rows)  }
-    const uint8_t* blr;     // blurred level, row y - 18, the aligned start column      } second 16 bytes: descriptor
-    float a, b;             // cos, sin of the orientation                                 }
+// ---- compile-time tables (copied to shared memory by every CTA with coalesced loads) ----
+constexpr int kUmaxHost[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+constexpr int8_t kPatternHost[1024] = {
+#include "orb_pattern.inc"
 };
+constexpr uint32_t half_bits_of_small_int(int v) {     // fp16 bit pattern of an integer |v| < 2048
+    if (v == 0) return 0;
+    const uint32_t sign = v < 0 ? 0x8000u : 0u;
+    uint32_t a = (uint32_t)(v < 0 ? -v : v);
+    int e = 0;
+    while ((a >> (e + 1)) != 0) e++;
+    return sign | ((uint32_t)(e + 15) << 10) | ((a << (10 - e)) & 0x3ffu);
+}
+// test pattern as fp16 pairs {(x0, y0), (x1, y1)} per pair, in pair order (the coordinates are small integers: exact)
+struct PatTable { uint2 v[256]; };
+constexpr PatTable make_pat_table() {
+    PatTable t{};
+    for (int i = 0; i < 256; i++) {
+        t.v[i].x = half_bits_of_small_int(kPatternHost[4 * i]) | (half_bits_of_small_int(kPatternHost[4 * i + 1]) << 16);
+        t.v[i].y = half_bits_of_small_int(kPatternHost[4 * i + 2]) | (half_bits_of_small_int(kPatternHost[4 * i + 3]) << 16);
+    }
+    return t;
+}
+// moment weights: entry [al][v + 15][word] = {u, v} for the four pixels of an aligned word of patch row v when the row's first
+// pixel (u = -15) sits at byte `al` of word 0; zero outside the disc |u| <= umax[|v|] (R21 :462-469, :77-104)
+constexpr int kMwEntries = 4 * 31 * 9;
+struct MwTable { uint2 v[kMwEntries]; };
+constexpr MwTable make_mw_table() {
+    MwTable t{};
+    for (int al = 0; al < 4; al++)
+        for (int row = 0; row < 31; row++)
+            for (int w = 0; w < 9; w++) {
+                const int v = row - 15, av = v < 0 ? -v : v;
+                uint32_t wu = 0, wv = 0;
+                for (int bb = 0; bb < 4; bb++) {
+                    const int u = 4 * w + bb - al - 15;
+                    if ((u < 0 ? -u : u) <= kUmaxHost[av]) { wu |= (uint32_t)(u & 0xff) << (8 * bb); wv |= (uint32_t)(v & 0xff) << (8 * bb); }
+                }
+                t.v[(al * 31 + row) * 9 + w].x = wu;
+                t.v[(al * 31 + row) * 9 + w].y = wv;
+            }
+    return t;
+}
+__device__ const PatTable g_pat = make_pat_table();
+__device__ const MwTable g_mw = make_mw_table();
+
+struct TmapSet { CUtensorMap img[kMaxLevels]; CUtensorMap blr[kMaxLevels]; };   // [B][rows][pitch] uint8 tensors of every level
 
 // A warp owns a group of G consecutive output key points of one frame and walks three phases:
-//  1. moments (IC_Angle), cooperatively per key point: lane = patch row v, the row's 31 pixels arrive as nine aligned
-//     32-bit words and are reduced with dp4a against per-(alignment, |v|) weight words from shared memory (u inside the disc
-//     -> m10, 1 inside the disc -> row sum -> m01 = v * row sum).  Lane k keeps the moments of key point k.
+//  1. moments (IC_Angle), cooperatively per key point: the 31 x 48-byte neighbourhood of the un-blurred level arrives in
+//     shared memory as ONE bulk tensor copy (TMA, requested one key point ahead, completion on an mbarrier); lane = (row mod 3,
+//     word) reads one aligned word of 11 rows and reduces it with two dp4a against per-(alignment, row, word) weight words
+//     (u inside the disc -> m10, v inside the disc -> m01).  Lane k keeps the moments of key point k.
 //  2. orientation, one key point per LANE: fastAtan2 and the double-precision sincos run once per 32 key points instead of
-//     once per key point on all 32 lanes (a quarter of the old kernel's instructions were this redundant trigonometry).
-//  3. descriptor, cooperatively per key point: the 37 x 37 blurred neighbourhood is staged in shared memory with 16-byte
-//     row chunks (<= 5 coalesced loads per lane, requested one key point ahead), lane i builds byte i from 16 shared-memory
-//     byte gathers.  The old kernel gathered straight from global memory: 16 warp-wide loads of 32 scattered bytes per key
-//     point, ~25 L1 wavefronts each -- that, not arithmetic, was its limit.
+//     once per key point on all 32 lanes (a quarter of the first kernel's instructions were this redundant trigonometry).
+//  3. descriptor, cooperatively per key point: the 37 x 80-byte blurred neighbourhood arrives by TMA the same way; 8 rounds of
+//     32 test pairs, lane L evaluates pair 32 j + L from two shared-memory byte gathers, the warp ballot of round j is
+//     descriptor word j.  The first kernel gathered straight from global memory: 16 warp-wide loads of 32 scattered bytes
+//     per key point, ~25 L1 wavefronts each -- that, not arithmetic, was its limit.
 template <int G>
-__global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(DevPtrs d, FrameLayout fl,
-                                                                  orb_keypoint_t* __restrict__ out_kps,
-                                                                  uint8_t* __restrict__ out_desc,
-                                                                  int32_t* __restrict__ out_counts, int cap) {
-    // pattern as floats, one float4 (x0,y0,x1,y1) per test pair, laid out [pair % 8][pair / 8] so that the 32 lanes
-    // (lane = descriptor byte = pair / 8) read consecutive float4s: no bank conflicts
-    __shared__ float4 s_pat[256];
-    __shared__ uint2 s_mw[4][16 * 9 + 1];                             // moment weights {u, 1} per (row alignment, |v| * 9 + word); the last entry is zero
-    __shared__ KpWork s_kp[kDescWarps][G];
-    __shared__ __align__(16) uint8_t s_patch[kDescWarps][kPatchRows * kPatchStride];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
-        s_pat[(i & 7) * 32 + (i >> 3)] = make_float4((float)c_pattern[4 * i], (float)c_pattern[4 * i + 1],
-                                                     (float)c_pattern[4 * i + 2], (float)c_pattern[4 * i + 3]);
-    for (int e = threadIdx.x; e < 4 * (16 * 9 + 1); e += blockDim.x) {
-        const int al = e / (16 * 9 + 1), t = e % (16 * 9 + 1), av = t / 9, i = t % 9;
-        uint32_t wu = 0, w1 = 0;
-        for (int bb = 0; bb < 4 && t < 16 * 9; bb++) {
-            const int u = 4 * i + bb - al - 15;
-            if ((u < 0 ? -u : u) <= c_umax[av]) { wu |= (uint32_t)(u & 0xff) << (8 * bb); w1 |= 1u << (8 * bb); }
-        }
-        s_mw[al][t] = make_uint2(wu, w1);
+__global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(const __grid_constant__ TmapSet tm, DevPtrs d, FrameLayout fl,
+                                                                     orb_keypoint_t* __restrict__ out_kps,
+                                                                     uint8_t* __restrict__ out_desc,
+                                                                     int32_t* __restrict__ out_counts, int cap) {
+    __shared__ uint2 s_pat[256];
+    __shared__ uint2 s_mw[kMwEntries];
+    __shared__ int4 s_kp[kDescWarps][G];                               // x | y << 16, level, cos, sin
+    __shared__ __align__(128) uint8_t s_stage[kDescWarps][2][kStageBytes];
+    __shared__ __align__(8) uint64_t s_bar[kDescWarps][2];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pat[i] = g_pat.v[i];
+    for (int i = threadIdx.x; i < kMwEntries; i += blockDim.x) s_mw[i] = g_mw.v[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(dsc_smem_u32(&s_bar[warp][0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(dsc_smem_u32(&s_bar[warp][1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int frame = blockIdx.y;
     // per-level slot starts / counts of this frame, one level per lane
     const int32_t* lc = d.level_count + (size_t)frame * kMaxLevels;
@@ -119,18 +166,10 @@ __global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(DevPtrs d,
     const int excl = incl - my_cnt;
     const int n_out = min(total, cap);
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
-    KpWork* const kw = s_kp[warp];
-    // moment items of this lane: row offset v, byte offset of the word inside the row, byte offset of its weight pair
-    int item_v[9], item_b[9], item_t[9];
-#pragma unroll
-    for (int it = 0; it < 9; it++) {
-        const int idx = it * 32 + lane, row = idx / 9, word = idx - row * 9;
-        const bool ok = row < 31;
-        const int v = ok ? row - 15 : 0;
-        item_v[it] = v; item_b[it] = ok ? 4 * word : 0;
-        item_t[it] = 8 * (ok ? (v < 0 ? -v : v) * 9 + word : 16 * 9);
-    }
-    uint8_t* const patch = s_patch[warp];
+    int4* const kw = s_kp[warp];
+    const uint32_t stage0 = dsc_smem_u32(s_stage[warp][0]);
+    const uint32_t bar0 = dsc_smem_u32(&s_bar[warp][0]);
+    uint32_t par = 0;                                            // phase parity of the two barriers (bit b = barrier b)
 
     for (int first = (blockIdx.x * kDescWarps + warp) * G; first < n_out; first += gridDim.x * kDescWarps * G) {
         const int n = min(G, n_out - first);                      // key points of this group (warp-uniform)
@@ -144,58 +183,53 @@ __global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(DevPtrs d,
         int x = 0, y = 0;
         const bool mine = lane < n;
         if (mine) {
-            const LevelGeom* gp = d.geom + level;
             pk = d.sel[(size_t)frame * fl.kp_cap + slot];
             x = (int)(pk & 0xfff) + kMinBorder; y = (int)((pk >> 12) & 0xfff) + kMinBorder;
-            int pitch;
-            const uint8_t* roi = level_roi(d, fl, *gp, level, frame, pitch);
-            const int spitch = gp->spitch;
-            const int xs = (x - kPatchR) & ~15;
-            KpWork w;
-            w.img = roi + (size_t)y * pitch + (x - 15);       // key points sit >= 19 px inside the level, the patch radius is 15
-            w.pitch = pitch;
-            w.cx = (x - xs) | (spitch << 8);                  // spitch <= 4096 + 15
-            w.blr = d.blur + (size_t)frame * fl.splane_bytes + gp->splane_off + (size_t)(y - kPatchR) * spitch + xs;
-            w.a = 0.f; w.b = 0.f;
-            kw[lane] = w;
+            kw[lane] = make_int4(x | (y << 16), level, 0, 0);
         }
         __syncwarp();
 
-        // ---- phase 1: IC_Angle on the un-blurred level, one key point at a time.  The 31 rows x 9 aligned words of the disc's
-        // bounding box are dealt to the lanes in row-major order (item = it * 32 + lane: a warp-wide load covers 3.5 consecutive
-        // rows, ~5 cache lines; with lane = row every load touched 31 lines and the kernel sat on the L1 data pipe).
+        // ---- phase 1: IC_Angle on the un-blurred level, one key point at a time (key points sit >= 19 px inside the level, the
+        // patch radius is 15).  Levels >= 1 live in padded planes: pixel (x, y) is element (kXPad + x, kEdge + y) of the tensor.
         int M01 = 0, M10 = 0;
         {
-            uint32_t w[9], wn[9];
-            auto request = [&](int k, uint32_t (&dst)[9], int& al) {
-                const int4 q = *reinterpret_cast<const int4*>(&kw[k]);            // img (2 words), pitch, cx
-                const uint8_t* p = reinterpret_cast<const uint8_t*>(((uint64_t)(uint32_t)q.y << 32) | (uint32_t)q.x);
-                al = (int)(reinterpret_cast<uintptr_t>(p) & 3);                   // same for every row: pitches are multiples of 4
-                p -= al;
-#pragma unroll
-                for (int it = 0; it < 9; it++) dst[it] = __ldg(reinterpret_cast<const uint32_t*>(p + (ptrdiff_t)(item_v[it] * q.z + item_b[it])));
+            const int lr = lane / 9, lw = lane - 9 * lr;          // lanes 27..31 repeat rows of other lanes: zeroed below
+            const uint32_t lane_px = stage0 + lr * kImgBoxW + 4 * lw;
+            const unsigned char* const lane_tab = reinterpret_cast<const unsigned char*>(s_mw) + (lr * 9 + lw) * 8;
+            auto request = [&](int k) {
+                const int4 q = kw[k];
+                const int kx = q.x & 0xffff, ky = q.x >> 16, lv = q.y;
+                dsc_tma_box(stage0 + (k & 1) * kStageBytes, &tm.img[lv], bar0 + 8 * (k & 1), ((kx - 15) & ~15) + (lv ? kXPad : 0),
+                            ky - 15 + (lv ? kEdge : 0), frame, kImgBoxW * kImgBoxH);
             };
-            int al, aln = 0;
-            request(0, w, al);
+            if (lane == 0) request(0);
             for (int k = 0; k < n; k++) {
-                if (k + 1 < n) request(k + 1, wn, aln);
-                const unsigned char* tab = reinterpret_cast<const unsigned char*>(s_mw[al]);
+                const int cur = k & 1;
+                if (lane == 0 && k + 1 < n) request(k + 1);       // its buffer was last read in iteration k - 1 (warp barrier below)
+                const int al16 = ((kw[k].x & 0xffff) - 15) & 15;
+                const uint32_t px = lane_px + cur * kStageBytes + (al16 & ~3);
+                const unsigned char* tab = lane_tab + (al16 & 3) * (31 * 9 * 8);
+                dsc_mbar_wait(bar0 + 8 * cur, (par >> cur) & 1);
+                par ^= 1u << cur;
                 int m01 = 0, m10 = 0;
 #pragma unroll
-                for (int it = 0; it < 9; it++) {
-                    const uint2 t = *reinterpret_cast<const uint2*>(tab + item_t[it]);
-                    m10 = dp4a_us(w[it], t.x, m10);
-                    m01 += item_v[it] * dp4a_us(w[it], t.y, 0);
+                for (int it = 0; it < 11; it++) {
+                    if (it < 10 || lr == 0) {                     // row 3 it + lr < 31
+                        uint32_t w;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(px + it * 3 * kImgBoxW));
+                        const uint2 t = *reinterpret_cast<const uint2*>(tab + it * 3 * 9 * 8);
+                        m10 = dp4a_us(w, t.x, m10);
+                        m01 = dp4a_us(w, t.y, m01);
+                    }
                 }
+                if (lane >= 27) { m01 = 0; m10 = 0; }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     m01 += __shfl_xor_sync(0xffffffffu, m01, o);
                     m10 += __shfl_xor_sync(0xffffffffu, m10, o);
                 }
                 if (lane == k) { M01 = m01; M10 = m10; }
-#pragma unroll
-                for (int it = 0; it < 9; it++) w[it] = wn[it];
-                al = aln;
+                __syncwarp();
             }
         }
 
@@ -205,7 +239,7 @@ __global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(DevPtrs d,
             const float rad = __fmul_rn(angle, factorPI);
             double sd, cd;
             sincos((double)rad, &sd, &cd);
-            kw[lane].a = (float)cd; kw[lane].b = (float)sd;
+            kw[lane].z = __float_as_int((float)cd); kw[lane].w = __float_as_int((float)sd);
             const LevelGeom* gp = d.geom + level;
             orb_keypoint_t k;
             const float fx = (float)x, fy = (float)y, sc = gp->scale;
@@ -220,67 +254,120 @@ __global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(DevPtrs d,
         }
         __syncwarp();
 
-        // ---- phase 3: steered rBRIEF on the blurred level: lane i produces descriptor byte i of one key point at a time
+        // ---- phase 3: steered rBRIEF on the blurred level, one key point at a time: 8 rounds of 32 test pairs
         {
-            // staged rows: lane handles (row, chunk) = (idx >> 2, idx & 3), idx = it * 32 + lane; a chunk is needed while it
-            // starts at or left of column x + 18 (every needed chunk lies inside the row: x + 18 < w <= spitch)
-            uint4 st[5];
+            // this lane's test pairs in registers for the 32 key points of the group: round j, lane L evaluates pair 32 j + L
+            uint2 pat[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) pat[j] = s_pat[32 * j + lane];
             auto request = [&](int k) {
-                const int4 q0 = *reinterpret_cast<const int4*>(&kw[k]);
-                const int4 q1 = *(reinterpret_cast<const int4*>(&kw[k]) + 1);
-                const uint8_t* base = reinterpret_cast<const uint8_t*>(((uint64_t)(uint32_t)q1.y << 32) | (uint32_t)q1.x);
-                const int cx = q0.w & 0xff, spitch = q0.w >> 8;
-                const int nchunk = ((cx + kPatchR) >> 4) + 1;
-#pragma unroll
-                for (int it = 0; it < 5; it++) {
-                    const int idx = it * 32 + lane, r = idx >> 2, c = idx & 3;
-                    st[it] = make_uint4(0, 0, 0, 0);
-                    if (r < kPatchRows && c < nchunk) st[it] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * spitch + c * 16));
-                }
+                const int4 q = kw[k];
+                const int kx = q.x & 0xffff, ky = q.x >> 16;
+                dsc_tma_box(stage0 + (k & 1) * kStageBytes, &tm.blr[q.y], bar0 + 8 * (k & 1), (kx - kPatchR) & ~15, ky - kPatchR, frame,
+                            kBlurBoxW * kBlurBoxH);
             };
-            request(0);
+            if (lane == 0) request(0);
             for (int k = 0; k < n; k++) {
-                __syncwarp();                                   // the previous key point's gathers are done
-#pragma unroll
-                for (int it = 0; it < 5; it++) {
-                    const int idx = it * 32 + lane, r = idx >> 2, c = idx & 3;
-                    if (r < kPatchRows) *reinterpret_cast<uint4*>(patch + r * kPatchStride + c * 16) = st[it];
-                }
-                const int4 q0 = *reinterpret_cast<const int4*>(&kw[k]);
-                const int4 q1 = *(reinterpret_cast<const int4*>(&kw[k]) + 1);
-                __syncwarp();
-                if (k + 1 < n) request(k + 1);
-                const float a = __int_as_float(q1.z), b = __int_as_float(q1.w);
-                const uint8_t* ctr = patch + kPatchR * kPatchStride + (q0.w & 0xff);
-                int val = 0;
+                const int cur = k & 1;
+                if (lane == 0 && k + 1 < n) request(k + 1);
+                const int4 q = kw[k];
+                const float a = __int_as_float(q.z), b = __int_as_float(q.w);
+                // byte (r, c) of the patch is at stage + (18 + r) * 80 + cx + c; the rounding constant 0x4b400000 that round_rn
+                // would subtract from each coordinate is folded into the base (32-bit shared addresses wrap)
+                const uint32_t ctr = stage0 + cur * kStageBytes + kPatchR * kBlurBoxW + (uint32_t)(((q.x & 0xffff) - kPatchR) & 15) + kPatchR
+                                     - 0x4b400000u * (uint32_t)(kBlurBoxW + 1);
+                dsc_mbar_wait(bar0 + 8 * cur, (par >> cur) & 1);
+                par ^= 1u << cur;
+                uint32_t word = 0;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const float4 p = s_pat[j * 32 + lane];   // x0, y0, x1, y1
-                    const int r0 = round_rn(__fadd_rn(__fmul_rn(p.x, b), __fmul_rn(p.y, a)));
-                    const int c0 = round_rn(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, b)));
-                    const int r1 = round_rn(__fadd_rn(__fmul_rn(p.z, b), __fmul_rn(p.w, a)));
-                    const int c1 = round_rn(__fsub_rn(__fmul_rn(p.z, a), __fmul_rn(p.w, b)));
-                    const int t0 = ctr[r0 * kPatchStride + c0];
-                    const int t1 = ctr[r1 * kPatchStride + c1];
-                    val |= (t0 < t1) << j;
+                    const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&pat[j].x));   // (x0, y0)
+                    const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&pat[j].y));   // (x1, y1)
+                    // cvRound(x*b + y*a), cvRound(x*a - y*b): adding 1.5 * 2^23 leaves rint() in the low mantissa bits
+                    const uint32_t r0 = (uint32_t)__float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(p0.x, b), __fmul_rn(p0.y, a)), 12582912.f));
+                    const uint32_t c0 = (uint32_t)__float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(p0.x, a), __fmul_rn(p0.y, b)), 12582912.f));
+                    const uint32_t r1 = (uint32_t)__float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(p1.x, b), __fmul_rn(p1.y, a)), 12582912.f));
+                    const uint32_t c1 = (uint32_t)__float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(p1.x, a), __fmul_rn(p1.y, b)), 12582912.f));
+                    uint32_t t0, t1;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(ctr + r0 * kBlurBoxW + c0));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(ctr + r1 * kBlurBoxW + c1));
+                    const uint32_t bits = __ballot_sync(0xffffffffu, t0 < t1);
+                    if (lane == j) word = bits;
                 }
-                out_desc[((size_t)frame * cap + first + k) * 32 + lane] = (uint8_t)val;
+                if (lane < 8) reinterpret_cast<uint32_t*>(out_desc + ((size_t)frame * cap + first + k) * 32)[lane] = word;
+                __syncwarp();                                     // every lane is done with this buffer before it is refilled
             }
         }
-        __syncwarp();                                           // kw / patch are reused by the next group
     }
 }
 
-int launch_describe(const DevPtrs& d, const FrameLayout& fl, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
-                    int32_t* d_counts, int cap, cudaStream_t s) {
+// ---- host side: tensor maps -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+struct DescribeMaps {
+    TmapSet set;
+    // what the maps were built for
+    const void* in = nullptr; const void* pyr = nullptr; const void* blur = nullptr;
+    size_t in_stride = 0; int in_pitch = 0, width = 0, height = 0, nlevels = 0, frames = 0;
+    int64_t pyr_bytes = 0, splane_bytes = 0;
+    bool valid = false;
+};
+DescribeMaps* describe_maps_create() { return new DescribeMaps(); }
+void describe_maps_destroy(DescribeMaps* m) { delete m; }
+
+static bool encode_u8_3d(CUtensorMap* map, const void* base, uint64_t pitch, uint64_t rows, uint64_t frames, uint64_t frame_stride, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from this driver"); return false; }
+    const cuuint64_t dims[3] = {pitch, rows, frames};
+    const cuuint64_t strides[2] = {pitch, frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): base %p pitch %llu rows %llu frames %llu stride %llu", (int)r, base,
+                                       (unsigned long long)pitch, (unsigned long long)rows, (unsigned long long)frames, (unsigned long long)frame_stride); return false; }
+    return true;
+}
+
+int launch_describe(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
+                    int32_t* d_counts, int cap, DescribeMaps* m, cudaStream_t s) {
+    // the tensor maps only change with the buffers / the input pointer: rebuilt on demand (16 host-side encodes)
+    if (!m->valid || m->in != d.in || m->pyr != d.pyr || m->blur != d.blur || m->in_stride != d.in_frame_stride || m->in_pitch != fl.in_pitch ||
+        m->width != fl.width || m->height != fl.height || m->nlevels != fl.nlevels || m->frames < n_frames || m->pyr_bytes != fl.pyr_bytes ||
+        m->splane_bytes != fl.splane_bytes) {
+        m->valid = false;
+        for (int l = 0; l < fl.nlevels; l++) {
+            const bool ok_img = l == 0 ? encode_u8_3d(&m->set.img[0], d.in, (uint64_t)fl.in_pitch, (uint64_t)fl.height, (uint64_t)n_frames, d.in_frame_stride, kImgBoxW, kImgBoxH)
+                                       : encode_u8_3d(&m->set.img[l], d.pyr + hg[l].plane_off, (uint64_t)hg[l].pitch, (uint64_t)hg[l].plane_rows, (uint64_t)n_frames,
+                                                      (uint64_t)fl.pyr_bytes, kImgBoxW, kImgBoxH);
+            if (!ok_img) return -1;
+            if (!encode_u8_3d(&m->set.blr[l], d.blur + hg[l].splane_off, (uint64_t)hg[l].spitch, (uint64_t)hg[l].h, (uint64_t)n_frames, (uint64_t)fl.splane_bytes,
+                              kBlurBoxW, kBlurBoxH)) return -1;
+        }
+        for (int l = fl.nlevels; l < kMaxLevels; l++) { m->set.img[l] = m->set.img[0]; m->set.blr[l] = m->set.blr[0]; }
+        m->in = d.in; m->pyr = d.pyr; m->blur = d.blur; m->in_stride = d.in_frame_stride; m->in_pitch = fl.in_pitch; m->width = fl.width;
+        m->height = fl.height; m->nlevels = fl.nlevels; m->frames = n_frames; m->pyr_bytes = fl.pyr_bytes; m->splane_bytes = fl.splane_bytes;
+        m->valid = true;
+    }
     // Batches: groups of 32 key points per warp (the per-lane trigonometry is fully used); few frames: groups of 8, four
     // times as many warps, so a single frame's ~1000 key points still spread over the GPU (latency).
     if (n_frames >= 8) {
         const int groups = (fl.kp_cap + 31) / 32;
-        describe_kernel<32><<<dim3(std::max(1, (groups + kDescWarps - 1) / kDescWarps), n_frames), 32 * kDescWarps, 0, s>>>(d, fl, d_kps, d_desc, d_counts, cap);
+        describe_kernel<32><<<dim3(std::max(1, (groups + kDescWarps - 1) / kDescWarps), n_frames), 32 * kDescWarps, 0, s>>>(m->set, d, fl, d_kps, d_desc, d_counts, cap);
     } else {
         const int groups = (fl.kp_cap + 7) / 8;
-        describe_kernel<8><<<dim3(std::max(1, (groups + kDescWarps - 1) / kDescWarps), n_frames), 32 * kDescWarps, 0, s>>>(d, fl, d_kps, d_desc, d_counts, cap);
+        describe_kernel<8><<<dim3(std::max(1, (groups + kDescWarps - 1) / kDescWarps), n_frames), 32 * kDescWarps, 0, s>>>(m->set, d, fl, d_kps, d_desc, d_counts, cap);
     }
     return 1;
 }

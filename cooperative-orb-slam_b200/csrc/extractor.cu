@@ -98,6 +98,8 @@ struct orbx_handle_s {
     GraphKey graph_key = {}, graph_seen = {};
     int graph_kernels = 0;
     int64_t graph_replays = 0;
+    DescribeMaps* dmaps = nullptr;      // TMA descriptors of the describe kernel (describe.cu)
+    ~orbx_handle_s() { if (dmaps) describe_maps_destroy(dmaps); }
 
     // pending async call
     bool pending = false;
@@ -371,7 +373,7 @@ int enqueue_kernels(orbx_handle_s* h, const uint8_t* d_in, size_t in_frame_strid
     if ((n = launch_octree(d, h->fl, n_frames, s)) < 0) { set_error("quadtree kernel configuration failed"); return ORB_ERR_CUDA; }
     h->launches += n;
     if (prof) cudaEventRecord(h->ev[6], s);
-    if ((n = launch_describe(d, h->fl, n_frames, d_kps, d_desc, d_counts, cap, s)) < 0) return ORB_ERR_CUDA;
+    if ((n = launch_describe(d, h->fl, h->geom.data(), n_frames, d_kps, d_desc, d_counts, cap, h->dmaps, s)) < 0) return ORB_ERR_CUDA;
     h->launches += n;
     if (prof) cudaEventRecord(h->ev[7], s);
     ORB_CUDA_TRY(cudaGetLastError());
@@ -460,6 +462,7 @@ int orbx_create(const orbx_params_t* p, int max_width, int max_height, int max_b
         return ORB_ERR_ARG;
     }
     orbx_handle_s* h = new orbx_handle_s;
+    h->dmaps = describe_maps_create();
     h->prm = *p;
     h->device = device;
     // R21 ORBextractor.cc:415-446 -- same float/double mix

@@ -104,8 +104,12 @@ int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom,
 int launch_fast_cells(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, int ini_th,
                       cudaStream_t s);
 int launch_octree(const DevPtrs& d, const FrameLayout& fl, int n_frames, cudaStream_t s);
-int launch_describe(const DevPtrs& d, const FrameLayout& fl, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
-                    int32_t* d_counts, int cap, cudaStream_t s);
+// tensor maps (TMA descriptors) of the describe kernel's two staged neighbourhoods, cached per extractor handle
+struct DescribeMaps;
+DescribeMaps* describe_maps_create();
+void describe_maps_destroy(DescribeMaps* m);
+int launch_describe(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hgeom, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
+                    int32_t* d_counts, int cap, DescribeMaps* maps, cudaStream_t s);
 
 // stand-alone quadtree on packed candidates already in device memory
 int launch_octree_single(const uint32_t* d_cand, int n, int width, int height, int n_feat, int n_ini, float h_x,
