@@ -13,6 +13,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace orbcuda {
 
@@ -40,7 +41,6 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-constexpr int kDescWarps = 4;
 constexpr int kPatchR = 18;                     // the pattern's largest radius is 18.38 (point (-13,-13)): |cvRound(rotated coordinate)| <= 18
 constexpr int kBlurBoxW = 80, kBlurBoxH = 2 * kPatchR + 1;    // TMA box of the blurred level: 37 rows x 80 bytes from the 16-byte aligned column at or left of x - 18
 constexpr int kImgBoxW = 48, kImgBoxH = 31;                   // TMA box of the un-blurred level: 31 rows x 48 bytes from the aligned column at or left of x - 15
@@ -131,26 +131,39 @@ struct TmapSet { CUtensorMap img[kMaxLevels]; CUtensorMap blr[kMaxLevels]; };   
 //     32 test pairs, lane L evaluates pair 32 j + L from two shared-memory byte gathers, the warp ballot of round j is
 //     descriptor word j.  The first kernel gathered straight from global memory: 16 warp-wide loads of 32 scattered bytes
 //     per key point, ~25 L1 wavefronts each -- that, not arithmetic, was its limit.
-template <int G>
-__global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(const __grid_constant__ TmapSet tm, DevPtrs d, FrameLayout fl,
-                                                                     orb_keypoint_t* __restrict__ out_kps,
-                                                                     uint8_t* __restrict__ out_desc,
-                                                                     int32_t* __restrict__ out_counts, int cap) {
-    __shared__ uint2 s_pat[256];
-    __shared__ uint2 s_mw[kMwEntries];
-    __shared__ int4 s_kp[kDescWarps][G];                               // x | y << 16, level, cos, sin
-    __shared__ __align__(128) uint8_t s_stage[kDescWarps][2][kStageBytes];
-    __shared__ __align__(8) uint64_t s_bar[kDescWarps][2];
+template <int G, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) describe_kernel(const __grid_constant__ TmapSet tm, DevPtrs d, FrameLayout fl,
+                                                                    orb_keypoint_t* __restrict__ out_kps,
+                                                                    uint8_t* __restrict__ out_desc,
+                                                                    int32_t* __restrict__ out_counts, int cap, int n_frames, int groups_per_frame) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    // layout: [WARPS][2][kStageBytes] staging | s_mw | s_pat | [WARPS][G] key point records | [WARPS][2] barriers
+    uint8_t* const s_stage = s_dyn;
+    uint2* const s_mw = reinterpret_cast<uint2*>(s_dyn + WARPS * 2 * kStageBytes);
+    uint2* const s_pat = s_mw + kMwEntries;
+    int4* const s_kp = reinterpret_cast<int4*>(s_pat + 256);                 // x | y << 16, level, cos, sin
+    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(s_kp + WARPS * G);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pat[i] = g_pat.v[i];
     for (int i = threadIdx.x; i < kMwEntries; i += blockDim.x) s_mw[i] = g_mw.v[i];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(dsc_smem_u32(&s_bar[warp][0])), "r"(1));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(dsc_smem_u32(&s_bar[warp][1])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(dsc_smem_u32(&s_bar[2 * warp])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(dsc_smem_u32(&s_bar[2 * warp + 1])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
     __syncthreads();
-    const int frame = blockIdx.y;
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    int4* const kw = s_kp + warp * G;
+    const uint32_t stage0 = dsc_smem_u32(s_stage + (size_t)warp * 2 * kStageBytes);
+    const uint32_t bar0 = dsc_smem_u32(&s_bar[2 * warp]);
+    uint32_t par = 0;                                            // phase parity of the two barriers (bit b = barrier b)
+
+    // Persistent warps: work item = (frame, group of G output key points); every warp of the grid strides over the items, so the
+    // load is even whatever the batch size (one launch wave; with one CTA per (frame, 4 groups) the last wave ran a tenth full).
+    const int n_items = n_frames * groups_per_frame;
+    for (int item = blockIdx.x * WARPS + warp; item < n_items; item += gridDim.x * WARPS) {
+    const int frame = item / groups_per_frame;
+    const int first = (item - frame * groups_per_frame) * G;
     // per-level slot starts / counts of this frame, one level per lane
     const int32_t* lc = d.level_count + (size_t)frame * kMaxLevels;
     const int my_cnt = lane < fl.nlevels ? lc[lane] : 0;
@@ -162,16 +175,11 @@ __global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(const __gr
         if (lane >= o) incl += t;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (blockIdx.x == 0 && threadIdx.x == 0) out_counts[frame] = total;
+    if (first == 0 && lane == 0) out_counts[frame] = total;
     const int excl = incl - my_cnt;
     const int n_out = min(total, cap);
-    const float factorPI = (float)(3.14159265358979323846 / 180.f);
-    int4* const kw = s_kp[warp];
-    const uint32_t stage0 = dsc_smem_u32(s_stage[warp][0]);
-    const uint32_t bar0 = dsc_smem_u32(&s_bar[warp][0]);
-    uint32_t par = 0;                                            // phase parity of the two barriers (bit b = barrier b)
-
-    for (int first = (blockIdx.x * kDescWarps + warp) * G; first < n_out; first += gridDim.x * kDescWarps * G) {
+    if (first >= n_out) continue;
+    {
         const int n = min(G, n_out - first);                      // key points of this group (warp-uniform)
         // ---- lane L < n: its own key point
         const int oidx = first + lane;
@@ -299,6 +307,7 @@ __global__ void __launch_bounds__(32 * kDescWarps, 7) describe_kernel(const __gr
             }
         }
     }
+    }
 }
 
 // ---- host side: tensor maps -------------------------------------------------------------------------------------
@@ -340,6 +349,44 @@ static bool encode_u8_3d(CUtensorMap* map, const void* base, uint64_t pitch, uin
     return true;
 }
 
+constexpr int kDescWarps = 8;
+template <int G, int WARPS> constexpr size_t describe_smem_bytes() {
+    return (size_t)WARPS * 2 * kStageBytes + (size_t)(kMwEntries + 256) * sizeof(uint2) + (size_t)WARPS * G * sizeof(int4) + (size_t)WARPS * 2 * sizeof(uint64_t);
+}
+struct DescribeGrid { int blocks_per_sm = 0, sms = 0; };
+template <int G, int WARPS, int MINB>
+static int launch_describe_g(const TmapSet& set, const DevPtrs& d, const FrameLayout& fl, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
+                             int32_t* d_counts, int cap, cudaStream_t s) {
+    constexpr size_t smem = describe_smem_bytes<G, WARPS>();
+    static DeviceOnce once;
+    static DescribeGrid grid[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (!once.run([&] {
+            if (cudaFuncSetAttribute(describe_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+            int bps = 0, sms = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, describe_kernel<G, WARPS, MINB>, 32 * WARPS, smem) != cudaSuccess || bps < 1) return false;
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+            grid[dev].blocks_per_sm = bps; grid[dev].sms = sms;
+            return true;
+        })) { set_error("describe kernel configuration failed"); return -1; }
+    const int gpf = (fl.kp_cap + G - 1) / G;
+    const int items = n_frames * gpf;
+    const int blocks = std::max(1, std::min((items + WARPS - 1) / WARPS, grid[dev].blocks_per_sm * grid[dev].sms));
+    describe_kernel<G, WARPS, MINB><<<blocks, 32 * WARPS, smem, s>>>(set, d, fl, d_kps, d_desc, d_counts, cap, n_frames, gpf);
+    return 1;
+}
+static int launch_describe_variant(const TmapSet& set, const DevPtrs& d, const FrameLayout& fl, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
+                                   int32_t* d_counts, int cap, cudaStream_t s) {
+    // Groups of G key points per work item: the per-lane trigonometry of a group costs the same for any G, small groups
+    // balance better and spread a single frame over the whole GPU.  ORBCUDA_DESC_G = 8 | 16 | 32 forces one (A/B switch).
+    static const int forced = [] { const char* e = getenv("ORBCUDA_DESC_G"); return e ? atoi(e) : 0; }();
+    const int g = forced ? forced : 8;   // measured on 128-frame batches: 0.099 ms (G = 8), 0.106 (16), 0.132 (32)
+    if (g >= 32) return launch_describe_g<32, kDescWarps, 3>(set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
+    if (g >= 16) return launch_describe_g<16, kDescWarps, 3>(set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
+    return launch_describe_g<8, kDescWarps, 3>(set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
+}
+
 int launch_describe(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
                     int32_t* d_counts, int cap, DescribeMaps* m, cudaStream_t s) {
     // the tensor maps only change with the buffers / the input pointer: rebuilt on demand (16 host-side encodes)
@@ -360,16 +407,7 @@ int launch_describe(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg
         m->height = fl.height; m->nlevels = fl.nlevels; m->frames = n_frames; m->pyr_bytes = fl.pyr_bytes; m->splane_bytes = fl.splane_bytes;
         m->valid = true;
     }
-    // Batches: groups of 32 key points per warp (the per-lane trigonometry is fully used); few frames: groups of 8, four
-    // times as many warps, so a single frame's ~1000 key points still spread over the GPU (latency).
-    if (n_frames >= 8) {
-        const int groups = (fl.kp_cap + 31) / 32;
-        describe_kernel<32><<<dim3(std::max(1, (groups + kDescWarps - 1) / kDescWarps), n_frames), 32 * kDescWarps, 0, s>>>(m->set, d, fl, d_kps, d_desc, d_counts, cap);
-    } else {
-        const int groups = (fl.kp_cap + 7) / 8;
-        describe_kernel<8><<<dim3(std::max(1, (groups + kDescWarps - 1) / kDescWarps), n_frames), 32 * kDescWarps, 0, s>>>(m->set, d, fl, d_kps, d_desc, d_counts, cap);
-    }
-    return 1;
+    return launch_describe_variant(m->set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
 }
 
 }  // namespace orbcuda
