@@ -17,7 +17,7 @@
 
 namespace orbcuda {
 
-constexpr bool kFastFmaDefault = true;    // +0.4 % frames/s with both variants capped at 80 registers (6 CTAs per SM)
+constexpr int kFastFmaDefault = 8;      // two-input min/max per side on the FMA pipe (of 24)
 constexpr int kFastRows = 14;   // rows per strip (two 7-row register rotations)
 
 __device__ __forceinline__ uint32_t fun16(uint32_t lo, uint32_t hi) { return __funnelshift_r(lo, hi, 16); }
@@ -73,30 +73,41 @@ __device__ __forceinline__ uint32_t E2(const Row6& r) { return fun16(r.b0, r.c0)
 __device__ __forceinline__ uint32_t E3(const Row6& r) { return fun16(r.b1, r.c1); }
 __device__ __forceinline__ uint32_t E4(const Row6& r) { return r.c0; }
 
-// max over the 16 circular 9-arcs of min(arc), and min over them of max(arc), on two pixels at once
-template <bool HF> __device__ __forceinline__ void arc_extrema(const uint32_t (&p)[16], uint32_t& max_of_min, uint32_t& min_of_max) {
-    uint32_t lo3[16], hi3[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        lo3[k] = mn3(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
-        hi3[k] = mx3(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
-    }
-    // Arc k = min3(lo3[k], lo3[k+3], lo3[k+6]).  Arcs k and k+3 share two of their three terms, and
-    // max(min(x, m), min(y, m)) = min(m, max(x, y)), so each pair of arcs costs one max and one min3.  The pairs
-    // (0,3) (6,9) (12,15) (2,5) (8,11) (14,1) (4,7) (10,13) cover the 16 arcs once (3 generates Z16).
-    uint32_t pa[8], pb[8];
+// max over the 16 circular 9-arcs of min(arc), and min over them of max(arc), on two pixels at once.
+// Arcs k and k+1 (k even) share the eight pixels k+1..k+8: max(min(p[k], X), min(X, p[k+9])) = min(X, max(p[k], p[k+9])) with
+// X = min(p[k+1..k+8]) = min of two 4-runs that start at odd positions.  Per side that is 8 pair minima (odd starts), 8 4-run
+// minima, 8 outer maxima, 8 three-input minima and a 4-instruction tree: 36 operations as with the 3-runs formulation this
+// replaces, but 25 of them are TWO-input -- and those can be issued on either half-rate pipe (ALU: one VIMNMX; FMA: fma.relu +
+// add on the fp16 view).  The kernel is bound by the ALU pipe, so the split (FA of the 24 flexible operations per side go to the
+// FMA pipe) is what balances the two.
+template <bool HF, bool FMA_PIPE> __device__ __forceinline__ uint32_t mx2p(uint32_t a, uint32_t b) { return (HF && FMA_PIPE) ? fmax2(a, b) : __vmaxs2(a, b); }
+template <bool HF, bool FMA_PIPE> __device__ __forceinline__ uint32_t mn2p(uint32_t a, uint32_t b) { return (HF && FMA_PIPE) ? fmin2(a, b) : __vmins2(a, b); }
+template <bool HF, int FA> __device__ __forceinline__ void arc_extrema(const uint32_t (&p)[16], uint32_t& max_of_min, uint32_t& min_of_max) {
+    // flexible operation number f (0..23 per side: pair minima 0..7, outer maxima 8..15, 4-run minima 16..23) runs on the FMA pipe if f < FA
+    uint32_t lo2[8], hi2[8], lo4[8], hi4[8], ox[8], on[8], ra[8], rb[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const int k = (6 * i) & 15;
-        pa[i] = mn3(lo3[(k + 3) & 15], lo3[(k + 6) & 15], mx2<HF>(lo3[k], lo3[(k + 9) & 15]));
-        pb[i] = mx3(hi3[(k + 3) & 15], hi3[(k + 6) & 15], mn2<HF>(hi3[k], hi3[(k + 9) & 15]));
+        lo2[i] = (i < FA) ? mn2p<HF, true>(p[2 * i + 1], p[(2 * i + 2) & 15]) : mn2p<HF, false>(p[2 * i + 1], p[(2 * i + 2) & 15]);
+        hi2[i] = (i < FA) ? mx2p<HF, true>(p[2 * i + 1], p[(2 * i + 2) & 15]) : mx2p<HF, false>(p[2 * i + 1], p[(2 * i + 2) & 15]);
+        ox[i] = (8 + i < FA) ? mx2p<HF, true>(p[2 * i], p[(2 * i + 9) & 15]) : mx2p<HF, false>(p[2 * i], p[(2 * i + 9) & 15]);
+        on[i] = (8 + i < FA) ? mn2p<HF, true>(p[2 * i], p[(2 * i + 9) & 15]) : mn2p<HF, false>(p[2 * i], p[(2 * i + 9) & 15]);
     }
-    max_of_min = mx3(mx3(pa[0], pa[1], pa[2]), mx3(pa[3], pa[4], pa[5]), mx2<HF>(pa[6], pa[7]));
-    min_of_max = mn3(mn3(pb[0], pb[1], pb[2]), mn3(pb[3], pb[4], pb[5]), mn2<HF>(pb[6], pb[7]));
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        lo4[i] = (16 + i < FA) ? mn2p<HF, true>(lo2[i], lo2[(i + 1) & 7]) : mn2p<HF, false>(lo2[i], lo2[(i + 1) & 7]);
+        hi4[i] = (16 + i < FA) ? mx2p<HF, true>(hi2[i], hi2[(i + 1) & 7]) : mx2p<HF, false>(hi2[i], hi2[(i + 1) & 7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        ra[i] = mn3(lo4[i], lo4[(i + 2) & 7], ox[i]);      // max(arc 2i, arc 2i+1) of the minima
+        rb[i] = mx3(hi4[i], hi4[(i + 2) & 7], on[i]);      // min(arc 2i, arc 2i+1) of the maxima
+    }
+    max_of_min = mx3(mx3(ra[0], ra[1], ra[2]), mx3(ra[3], ra[4], ra[5]), __vmaxs2(ra[6], ra[7]));
+    min_of_max = mn3(mn3(rb[0], rb[1], rb[2]), mn3(rb[3], rb[4], rb[5]), __vmins2(rb[6], rb[7]));
 }
 
 // scores of the 4 pixels x0..x0+3 of the centre row r[3] (window rows r[0..6] = y-3..y+3), packed u8x4
-template <bool HF> __device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
+template <bool HF, int FA> __device__ __forceinline__ uint32_t fast_score4(const Row6 (&r)[7], int th) {
     // circle (dx,dy), OpenCV order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
     const uint32_t e2_5 = E2(r[5]), em1_5 = Em1(r[5]), e2_1 = E2(r[1]), em1_1 = Em1(r[1]);
     const uint32_t em1_6 = Em1(r[6]), e2_6 = E2(r[6]), em1_0 = Em1(r[0]), e2_0 = E2(r[0]);
@@ -114,8 +125,8 @@ template <bool HF> __device__ __forceinline__ uint32_t fast_score4(const Row6 (&
     Q[8] = E1(r[0]);  Q[9] = E0(r[0]);  Q[10] = em1_1;     Q[11] = em2_2;
     Q[12] = em2_3;    Q[13] = em2_4;    Q[14] = em1_5;     Q[15] = E0(r[6]);
     uint32_t amaxP, bminP, amaxQ, bminQ;
-    arc_extrema<HF>(P, amaxP, bminP);
-    arc_extrema<HF>(Q, amaxQ, bminQ);
+    arc_extrema<HF, FA>(P, amaxP, bminP);
+    arc_extrema<HF, FA>(Q, amaxQ, bminQ);
     const uint32_t cP = E0(r[3]), cQ = E1(r[3]);
     // best = max( c - min_arcs(max_arc), max_arcs(min_arc) - c )   (per 16-bit lane, signed)
     const uint32_t bestP = __vmaxs2(__vsub2(cP, bminP), __vsub2(amaxP, cP));
@@ -127,7 +138,7 @@ template <bool HF> __device__ __forceinline__ uint32_t fast_score4(const Row6 (&
     return __byte_perm(sP, sQ, 0x6240);
 }
 
-template <bool HF> __global__ void __launch_bounds__(128, 5) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
+template <bool HF, int FA> __global__ void __launch_bounds__(128, 5) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
     if (blockIdx.x == 0) {
         // this frame's survivor counters and cell flags, consumed by fast_nms_kernel two launches later on the same
         // stream (saves two memset nodes per batch)
@@ -179,7 +190,7 @@ template <bool HF> __global__ void __launch_bounds__(128, 5) fast_score_kernel(D
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)min(y + 4, g.h - 1) * pitch);
                 n0 = w[0]; n1 = w[1]; n2 = w[2];
             }
-            const uint32_t s4 = fast_score4<HF>(r, th) & colmask;
+            const uint32_t s4 = fast_score4<HF, FA>(r, th) & colmask;
             if (y < g.h - kEdge) *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.spitch) = s4;
 #pragma unroll
             for (int k = 0; k < 6; k++) r[k] = r[k + 1];
@@ -199,10 +210,18 @@ int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* 
         total += (nsx * nsy + threads - 1) / threads;
     }
     for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
-    // ORBCUDA_FAST_FMA=0 keeps every min/max on the ALU pipe (A/B switch; results are identical)
-    static const bool hf = [] { const char* e = getenv("ORBCUDA_FAST_FMA"); return e ? atoi(e) != 0 : kFastFmaDefault; }();
-    if (hf) fast_score_kernel<true><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb, min_th);
-    else fast_score_kernel<false><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb, min_th);
+    // ORBCUDA_FAST_FMA = number of the 24 two-input operations per side issued on the FMA pipe (0 keeps every min/max on the ALU
+    // pipe; A/B switch, results are identical)
+    static const int fa = [] { const char* e = getenv("ORBCUDA_FAST_FMA"); return e ? atoi(e) : kFastFmaDefault; }();
+    const dim3 grid(total, n_frames);
+    switch (fa) {
+        case 0: fast_score_kernel<false, 0><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 12: fast_score_kernel<true, 12><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 20: fast_score_kernel<true, 20><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 24: fast_score_kernel<true, 24><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 16: fast_score_kernel<true, 16><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        default: fast_score_kernel<true, 8><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+    }
     return 1;
 }
 
