@@ -146,8 +146,7 @@ template <bool HF, int FA> __global__ void __launch_bounds__(128, 5) fast_score_
         for (int i = threadIdx.x; i < fl.n_cells; i += blockDim.x) cc[i] = 0;
         if (threadIdx.x < kMaxLevels) d.level_raw[(size_t)blockIdx.y * kMaxLevels + threadIdx.x] = 0;
     }
-    int level = 0;
-    while (level + 1 < fl.nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
+    const int level = level_of_block(lb, (int)blockIdx.x);
     const LevelGeom g = d.geom[level];
     // strips: x0 = 16 + 4*sx covers [16, W-19); y0 = 19 + kFastRows*sy covers [19, H-19)
     const int nsx = (g.w - kEdge - kMinBorder + 3) >> 2;
@@ -244,8 +243,7 @@ __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict
                                                        int32_t* __restrict__ cell_flag, int n_cells,
                                                        int32_t* __restrict__ level_raw, const LevelGeom* __restrict__ geom,
                                                        int nlevels, LevelBlocks lb, int ini_th) {
-    int level = 0;
-    while (level + 1 < nlevels && (int)blockIdx.x >= lb.start[level + 1]) level++;
+    const int level = level_of_block(lb, (int)blockIdx.x);
     const LevelGeom g = geom[level];
     const int lane = threadIdx.x & 31;
     const int nsx = (g.w - kEdge - kMinBorder + 3) >> 2;     // same strips as the score kernel: x0 = 16 + 4*sx
@@ -341,18 +339,19 @@ __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict
     int32_t* flags = cell_flag + (size_t)blockIdx.y * n_cells + g.cell_base + cy0 * g.n_cols + col0;
     const uint8_t* srow = src + (size_t)y0 * g.spitch;
     const uint32_t packed0 = (uint32_t)(x0 - kMinBorder) | ((uint32_t)(y0 - kMinBorder) << 12);
-#pragma unroll
-    for (int grp = 0; grp < kNmsRows / 4; grp++) {
-        uint32_t m = km[grp];
-        while (m) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            const int q = (bit & 15) - 8;
-            const int r = grp * 4 + (q >> 1), b = (q & 1) + 2 * (bit >> 4);
-            const uint32_t sc = srow[r * g.spitch + b];
-            list[pos++] = (packed0 + (uint32_t)b + ((uint32_t)r << 12)) | (sc << 24);
-            if ((int)sc >= ini_th) flags[(r > rb ? g.n_cols : 0) + (b >= wrapb ? 1 : 0)] = 1;
-        }
+    // one loop over the strip's 64 survivor bits (16 per group of four rows, packed: bit t of a group = pixel b = (t & 1) +
+    // 2 * (t >> 3), row (t & 7) >> 1): a warp runs as many iterations as its busiest lane has survivors -- four loops, one per
+    // group, ran the sum of the four per-group maxima, about twice as many
+    auto pack16 = [](uint32_t m) { return ((m >> 8) & 0xffu) | ((m >> 16) & 0xff00u); };
+    unsigned long long m = (unsigned long long)(pack16(km[0]) | (pack16(km[1]) << 16)) |
+                           ((unsigned long long)(pack16(km[2]) | (pack16(km[3]) << 16)) << 32);
+    while (m) {
+        const int T = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int r = (T >> 4) * 4 + ((T & 7) >> 1), b = (T & 1) + 2 * ((T >> 3) & 1);
+        const uint32_t sc = srow[r * g.spitch + b];
+        list[pos++] = (packed0 + (uint32_t)b + ((uint32_t)r << 12)) | (sc << 24);
+        if ((int)sc >= ini_th) flags[(r > rb ? g.n_cols : 0) + (b >= wrapb ? 1 : 0)] = 1;
     }
 }
 

@@ -149,6 +149,14 @@ int launch_merge_top2(const int32_t* d_parts, int parts, int nq, int32_t* d_out,
 void host_merge_top2(const int32_t* parts, int nparts, int nq, int32_t* out);
 
 #ifdef __CUDACC__
+// level of a block of a flattened (level, block) grid: start[l] of the unused levels equals the grid size, so a straight count
+// of the starts at or below the block index is the level (7 uniform compares instead of a data-dependent loop per thread)
+__device__ __forceinline__ int level_of_block(const LevelBlocks& lb, int bx) {
+    int level = 0;
+#pragma unroll
+    for (int l = 1; l < kMaxLevels; l++) level += bx >= lb.start[l] ? 1 : 0;
+    return level;
+}
 // Pointer to pixel (0,0) of a pyramid level and its row pitch.  Level 0 is the input image itself; levels >= 1
 // live in the padded planes of the pyramid block (only the interior is ever written or read on the device:
 // every consumer either stays inside the level or applies REFLECT_101 itself).

@@ -434,8 +434,7 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
 __global__ void __launch_bounds__(128) blur7_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, LevelBlocks lb_edge) {
     const bool edge = (int)blockIdx.x >= lb_edge.start[0];
     const LevelBlocks& B = edge ? lb_edge : lb;
-    int level = 0;
-    while (level + 1 < fl.nlevels && (int)blockIdx.x >= B.start[level + 1]) level++;
+    const int level = edge ? level_of_block(lb_edge, (int)blockIdx.x) : level_of_block(lb, (int)blockIdx.x);
     const LevelGeom g = d.geom[level];
     // strips of a level are flattened so every block is full whatever the level width
     const int nsx = (g.w + 3) >> 2;
