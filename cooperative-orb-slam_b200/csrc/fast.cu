@@ -146,11 +146,12 @@ template <bool HF, int FA> __global__ void __launch_bounds__(128, 5) fast_score_
         for (int i = threadIdx.x; i < fl.n_cells; i += blockDim.x) cc[i] = 0;
         if (threadIdx.x < kMaxLevels) d.level_raw[(size_t)blockIdx.y * kMaxLevels + threadIdx.x] = 0;
     }
-    const int level = level_of_block(lb, (int)blockIdx.x);
+    int first_block;
+    const int level = level_of_block(lb, (int)blockIdx.x, first_block);
     const LevelGeom g = d.geom[level];
     // strips: x0 = 16 + 4*sx covers [16, W-19); y0 = 19 + kFastRows*sy covers [19, H-19)
     const int nsx = (g.w - kEdge - kMinBorder + 3) >> 2;
-    const int id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
+    const int id = (blockIdx.x - first_block) * blockDim.x + threadIdx.x;
     const int sy = id / nsx;
     const int x0 = kMinBorder + 4 * (id - sy * nsx);
     const int y0 = kEdge + sy * kFastRows;
@@ -243,11 +244,12 @@ __global__ void __launch_bounds__(128) fast_nms_kernel(const uint8_t* __restrict
                                                        int32_t* __restrict__ cell_flag, int n_cells,
                                                        int32_t* __restrict__ level_raw, const LevelGeom* __restrict__ geom,
                                                        int nlevels, LevelBlocks lb, int ini_th) {
-    const int level = level_of_block(lb, (int)blockIdx.x);
+    int first_block;
+    const int level = level_of_block(lb, (int)blockIdx.x, first_block);
     const LevelGeom g = geom[level];
     const int lane = threadIdx.x & 31;
     const int nsx = (g.w - kEdge - kMinBorder + 3) >> 2;     // same strips as the score kernel: x0 = 16 + 4*sx
-    const unsigned id = (blockIdx.x - lb.start[level]) * blockDim.x + threadIdx.x;
+    const unsigned id = (blockIdx.x - first_block) * blockDim.x + threadIdx.x;
     const int sy = (int)(id / (unsigned)nsx);
     const int x0 = kMinBorder + 4 * ((int)id - sy * nsx);
     const int y0 = kEdge + sy * kNmsRows;

@@ -151,10 +151,12 @@ void host_merge_top2(const int32_t* parts, int nparts, int nq, int32_t* out);
 #ifdef __CUDACC__
 // level of a block of a flattened (level, block) grid: start[l] of the unused levels equals the grid size, so a straight count
 // of the starts at or below the block index is the level (7 uniform compares instead of a data-dependent loop per thread)
-__device__ __forceinline__ int level_of_block(const LevelBlocks& lb, int bx) {
+__device__ __forceinline__ int level_of_block(const LevelBlocks& lb, int bx, int& first_block) {
     int level = 0;
+    first_block = lb.start[0];
 #pragma unroll
-    for (int l = 1; l < kMaxLevels; l++) level += bx >= lb.start[l] ? 1 : 0;
+    for (int l = 1; l < kMaxLevels; l++)
+        if (bx >= lb.start[l]) { level++; first_block = lb.start[l]; }      // constant indices only: the struct stays in the parameter bank
     return level;
 }
 // Pointer to pixel (0,0) of a pyramid level and its row pitch.  Level 0 is the input image itself; levels >= 1
