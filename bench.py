@@ -71,6 +71,24 @@ def _peaks():
         return 6650.0, "fallback"
 
 
+def _i8_peak():
+    """(burst, sustained, source) TOP/s of tcgen05.mma kind::i8 on one GPU: tools/probe/i8_peak (a bare MMA issue loop, no operand
+    traffic) run on this box, else its committed result, else the nominal figure of B200_PROFILING.md."""
+    exe = os.path.join(ROOT, "tools", "probe", "i8_peak")
+    if os.access(exe, os.X_OK):
+        try:
+            out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout.strip().splitlines()[-1]
+            j = json.loads(out)
+            return max(float(j["burst_tops"]), float(j["sustained_tops"])), float(j["sustained_tops"]), "measured live: tools/probe/i8_peak (bare tcgen05.mma kind::i8 issue loop)"
+        except Exception:
+            pass
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r2_i8_peak.json")))
+        return max(float(j["burst_tops"]), float(j["sustained_tops"])), float(j["sustained_tops"]), "measured on this pool earlier: profiles/r2_i8_peak.json (tools/probe/i8_peak)"
+    except Exception:
+        return 4500.0, 4500.0, "fallback: B200_PROFILING.md nominal dense 8-bit tensor peak"
+
+
 def _bf16_peak(sustained=False):
     """Dense bf16 TFLOP/s: MEASURED_PEAKS.json (burst or sustained), else the profiling guide's fallback figures."""
     try:
@@ -899,7 +917,11 @@ def bench_matching(orb, synth, torch, dist, D, args, rank, world, local):
                  "note": "one rank's share of the 8-GPU search (search + split merge, no exchange) on one GPU"}
     tops = 2 * 256 * gcmp / 1e3                      # one comparison = 256 int8 MACs on the tensor pipe
     tops_sus = 2 * 256 * gcmp_sus / 1e3
-    peak8 = 4500.0 * world                            # nominal dense 8-bit peak per GPU (B200_PROFILING.md) x GPUs
+    # 8-bit tensor peak: measured live with the bare tcgen05.mma kind::i8 issue probe when its binary is here (built by
+    # __graft_entry__.build()), else the figure the same probe gave on this pool (profiles/r2_i8_peak.json), else nominal
+    i8_burst, i8_sus, i8_src = _i8_peak()
+    peak8 = i8_burst * world
+    peak8_sus = i8_sus * world
     pair = bestv.startswith("tcgen05_cta_pair")
     matching = {"metric": "Hamming 2-NN Gcmp/s (2000 queries x 1M map, 256-bit)", "value": gcmp, "unit": "Gcmp/s",
                 "ms_per_batch": per_variant[bestv]["ms_per_batch"], "kernel": bestv, "variants": per_variant,
@@ -907,14 +929,14 @@ def bench_matching(orb, synth, torch, dist, D, args, rank, world, local):
                               "timed_region_s": sus_ms * n_sus * 1e-3, "clocks": sus_clocks},
                 "map_shards": world, "d1_checksum": int(ref_out[:, 0].sum().item()), "parity_vs_oracle": parity, "shard_of_8": shard,
                 "roofline": {"bound": "tensor", "achieved": tops, "peak": peak8, "unit": "TOP/s", "frac": tops / peak8,
-                             "achieved_sustained": tops_sus, "frac_sustained": tops_sus / peak8,
+                             "achieved_sustained": tops_sus, "peak_sustained": peak8_sus, "frac_sustained": tops_sus / peak8_sus,
+                             "frac_vs_nominal_4500": tops / (4500.0 * world),
                              "frac_vs_2x_measured_bf16_burst": tops / (2 * _bf16_peak()[0] * world),
                              "frac_sustained_vs_2x_measured_bf16_sustained": tops_sus / (2 * _bf16_peak(True)[0] * world),
                              "traffic": _ncu_traffic("knn2_pair_kernel" if pair else "knn2_tc_kernel", "r1_ncu_knn2_tcgen05.csv"),
-                             "peak_source": "fallback: B200_PROFILING.md nominal dense 8-bit tensor peak x %d GPU(s) (MEASURED_PEAKS.json has no "
-                                            "8-bit figure; bf16 %s = %.0f burst / %.0f sustained TFLOP/s per GPU); ncu tensor pipe active 77 %% for "
-                                            "the CTA-pair kernel -- profiles/r1_ncu_knn2_tcgen05.csv"
-                                            % (world, _bf16_peak()[1], _bf16_peak()[0], _bf16_peak(True)[0])},
+                             "peak_source": "%s x %d GPU(s) (MEASURED_PEAKS.json has no 8-bit figure; bf16 %s = %.0f burst / %.0f sustained "
+                                            "TFLOP/s per GPU); ncu tensor pipe active 77 %% for the CTA-pair kernel -- profiles/r1_ncu_knn2_tcgen05.csv"
+                                            % (i8_src, world, _bf16_peak()[1], _bf16_peak()[0], _bf16_peak(True)[0])},
                 "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8 * world,
                 "popc_kernel_frac_of_popc_peak": per_variant["popc"]["gcmp_s"] / (148 * 16 * 1.965 / 8 * world),
                 "cpu_baseline": cpu}
