@@ -113,10 +113,13 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(DevPtrs d, FrameLayout 
             }
             r_hi = r1;
         }
-        const int b0 = ty.c0, b1 = ty.c1;
+        // ((b0*lo) >> 16) + ((b1*hi) >> 16) + 2 as two multiply-high-adds on weights pre-shifted by 16 (the products are < 2^42,
+        // each term is floored on its own exactly as in OpenCV): 2 instructions on the FMA pipe instead of 2 multiplies + 2 shifts
+        // + 2 adds, and the result is < 1024 so no mask is needed after the final shift
+        const int b0 = (int)ty.c0 << 16, b1 = (int)ty.c1 << 16;
         uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = (uint32_t)((((b0 * lo[i]) >> 16) + ((b1 * hi[i]) >> 16) + 2) >> 2) & 0xffu;
+        for (int i = 0; i < 4; i++) v[i] = (uint32_t)(__mulhi(b1, hi[i]) + __mulhi(b0, lo[i]) + 2) >> 2;
         uint8_t* row = dst + (ptrdiff_t)Y * gd.pitch;
         if (npx == 4) {
             *reinterpret_cast<uint32_t*>(row + X0) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
