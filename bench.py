@@ -131,6 +131,16 @@ def _ncu_traffic(kernel_substr, csv_name=None):
     return None
 
 
+def _knn_tensor_pct():
+    """sm__pipe_tensor_cycles_active of the CTA-pair 2-NN kernel in the committed round-2 capture."""
+    import csv
+    try:
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r2_ncu_knn2_pair.csv"))))
+        return float(rows[2][rows[0].index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")])
+    except Exception:
+        return None
+
+
 def _ncu_metric(kernel_substr, metric):
     try:
         _, rows = _ncu_rows()
@@ -933,9 +943,10 @@ def bench_matching(orb, synth, torch, dist, D, args, rank, world, local):
                              "frac_vs_nominal_4500": tops / (4500.0 * world),
                              "frac_vs_2x_measured_bf16_burst": tops / (2 * _bf16_peak()[0] * world),
                              "frac_sustained_vs_2x_measured_bf16_sustained": tops_sus / (2 * _bf16_peak(True)[0] * world),
-                             "traffic": _ncu_traffic("knn2_pair_kernel" if pair else "knn2_tc_kernel", "r1_ncu_knn2_tcgen05.csv"),
+                             "traffic": _ncu_traffic("knn2_pair_kernel", "r2_ncu_knn2_pair.csv") if pair else _ncu_traffic("knn2_tc_kernel", "r1_ncu_knn2_tcgen05.csv"),
+                             "ncu_tensor_pipe_active_pct": _knn_tensor_pct() if pair else None,
                              "peak_source": "%s x %d GPU(s) (MEASURED_PEAKS.json has no 8-bit figure; bf16 %s = %.0f burst / %.0f sustained "
-                                            "TFLOP/s per GPU); ncu tensor pipe active 77 %% for the CTA-pair kernel -- profiles/r1_ncu_knn2_tcgen05.csv"
+                                            "TFLOP/s per GPU); ncu tensor pipe active: profiles/r2_ncu_knn2_pair.csv"
                                             % (i8_src, world, _bf16_peak()[1], _bf16_peak()[0], _bf16_peak(True)[0])},
                 "popc_pipe_peak_gcmp_s": 148 * 16 * 1.965 / 8 * world,
                 "popc_kernel_frac_of_popc_peak": per_variant["popc"]["gcmp_s"] / (148 * 16 * 1.965 / 8 * world),

@@ -101,3 +101,32 @@ def test_product_never_touches_the_oracle():
     assert not bad, bad
     out = subprocess.check_output(["ldd", os.path.join(ROOT, "cooperative-orb-slam_b200", "liborbcuda.so")], text=True)
     assert "oracle" not in out and "orbref" not in out
+
+
+def _pattern_inc_values():
+    text = open(os.path.join(ROOT, "cooperative-orb-slam_b200", "csrc", "orb_pattern.inc")).read()
+    text = re.sub(r"//.*", "", text)
+    return [int(v) for v in re.findall(r"-?\d+", text)]
+
+
+def test_pattern_table_is_the_published_one():
+    """The oracle and the product share csrc/orb_pattern.inc, so a wrong table would pass oracle-vs-CUDA.  Pin it: 1024 values,
+    the sha256 recorded when it was extracted from the reference (tools/gen_pattern.py), values inside the 31 x 31 patch."""
+    import hashlib
+    import struct
+    vals = _pattern_inc_values()
+    assert len(vals) == 1024
+    assert hashlib.sha256(struct.pack("<1024i", *vals)).hexdigest().startswith("7e645581387b8278")
+    assert min(vals) >= -15 and max(vals) <= 15
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ORB_SLAM2.1/src/ORBextractor.cc"), reason="reference tree not on this box")
+def test_pattern_table_equals_the_reference_source():
+    """csrc/orb_pattern.inc == bit_pattern_31_ of R21/src/ORBextractor.cc:150-408, value for value."""
+    text = open("/root/reference/ORB_SLAM2.1/src/ORBextractor.cc", errors="replace").read()
+    start = text.index("bit_pattern_31_[256*4]")
+    body = text[text.index("{", start) + 1: text.index("};", start)]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    body = re.sub(r"//.*", "", body)
+    ref = [int(v) for v in re.findall(r"-?\d+", body)]
+    assert ref == _pattern_inc_values()
