@@ -246,6 +246,29 @@ int build_geometry(orbx_handle_s* h, int width, int height) {
                 }
                 g.rs_rows = std::max(g.rs_rows, hi - lo + 1);
             }
+            // pair-staged kernel (pyramid.cu, the default): tiles as tall as the level allows (<= 128 rows, a multiple of 8, the
+            // level height split evenly) within 96 KB of staged source pairs
+            {
+                int ny = (g.h + 127) / 128;
+                int th = std::min(128, (int)align_up((g.h + ny - 1) / ny, 8));
+                g.t3_row_bytes = 2 * (g.rs_cols + 4);
+                for (;; th -= 8) {
+                    g.t3_rows = 0;
+                    for (int y0 = 0; y0 < g.h; y0 += th) {
+                        const int y1 = std::min(y0 + th, g.h) - 1;
+                        int lo = 1 << 30, hi = 0;
+                        for (int y = y0; y <= y1; y++) {
+                            lo = std::min(lo, (int)ytab[g.ytab_off + y].ofs);
+                            hi = std::max(hi, (int)ytab[g.ytab_off + y].pad);
+                        }
+                        g.t3_rows = std::max(g.t3_rows, hi - lo + 1);
+                    }
+                    g.t3_smem = g.t3_rows * g.t3_row_bytes;
+                    if (g.t3_smem <= 96 * 1024 || th <= 8) break;
+                }
+                g.t3_h = th;
+                if (g.t3_smem > 96 * 1024 || g.rs_cols > 256) g.t3_smem = -1;     // scale factors this large go to the first kernel
+            }
             // two-phase kernel (pyramid.cu): tiles span the level width, split so that a tile has at most 160 four-column groups
             // and its source footprint at most 64 sixteen-byte vectors; as tall as a 40 KB block of horizontal sums allows
             {

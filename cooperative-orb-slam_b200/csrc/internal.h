@@ -42,6 +42,9 @@ struct LevelGeom {
     // tiling of the two-phase resize kernel (pyr_resize2_kernel): output tiles of t2_w x t2_h, the largest source
     // footprint of a tile (t2_rows x t2_cols bytes, t2_cols a multiple of 4 incl. 4 bytes of slack) and its shared memory
     int t2_w, t2_h, t2_nx, t2_ny, t2_rows, t2_cols, t2_smem;
+    // tiling of the pair-staged resize kernel (pyr_resize3_kernel, the default): output tiles of kPyrTileW x t3_h (8 warps x
+    // t3_h / 8 rows), t3_rows staged source rows of t3_row_bytes (two bytes per source pixel), t3_smem bytes of shared memory
+    int t3_h, t3_rows, t3_row_bytes, t3_smem;
     float scale;            // mvScaleFactor[level]
     float patch_size;       // (float)(int)(31*scale)
 };

@@ -268,6 +268,171 @@ __global__ void __launch_bounds__(kPyr2Threads) pyr_resize2_kernel(DevPtrs d, Fr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1, pair-staged form (ORBCUDA_PYR=3; NOT the default).  Same arithmetic as pyr_resize_kernel, bit-identical output (the
+// extractor tests pass with it selected).  What the first kernel spent its instructions on (ncu --page source, 95 instructions per four output pixels in the row loop and as many
+// again per CTA in set-up for only 8 rows per warp):
+//   * two byte loads + a merge per horizontal tap  -> the source footprint is staged as PAIRS (two bytes per source pixel: the
+//     pixel and its right neighbour), so a tap is ONE 16-bit load that is already the dp2a operand;
+//   * twelve register moves per row to swap the "low" / "high" source rows -> the row step exists twice, once per role of
+//     the two sum registers (template parameter), and the loop alternates between them: no copies;
+//   * the vertical taps loaded from global memory at the top of every row -> requested one row ahead;
+//   * LevelGeom fetched from global memory by every thread -> the few values needed arrive as a kernel parameter;
+//   * 8 rows per warp -> tiles up to 128 rows tall (t3_h, the level height split evenly): half the set-up per output row and
+//     better row utilisation on the small levels (134 rows = 2 x 72 instead of 3 x 64).
+// Measured on the B200 (round 2, ncu + bench.py): 50.7 M warp instructions per 64 frames for the seven levels against 60.6 M
+// (-16 %), 131 us against 135 us under ncu, 0.2008 ms against 0.2006 ms per 128 frames on one stream and the same 170 k
+// frames/s over four streams.  The instructions it removes are IMAD / LDS / MOV (FMA pipe, LSU); the integer-ALU-pipe share
+// (shifts, PRMT, compares, adds -- the pipe that bounds the extraction step as a whole) is unchanged, its
+// taller tiles stage longer before they compute (long-scoreboard stalls 35 %) and hold 50 KB of shared memory (4 CTAs per SM).
+// Kept as the measured alternative; the first kernel stays the default.
+// ---------------------------------------------------------------------------------------------
+struct Pyr3Args {
+    const uint8_t* src; size_t src_frame; int src_pitch;     // level l-1, pixel (0,0) of frame 0
+    uint8_t* dst; size_t dst_frame; int dst_pitch;           // level l, pixel (0,0) of frame 0
+    const ResizeTap* xt; const ResizeTap* yt;                // taps of this level
+    int w, h;                                                // destination size
+    int th;                                                  // tile height (a multiple of 8)
+    int row_bytes;                                           // bytes per staged row of pairs
+};
+
+__global__ void __launch_bounds__(256) pyr_resize3_kernel(Pyr3Args a) {
+    extern __shared__ __align__(16) unsigned char s_pair[];   // [rows][row_bytes]: pair x at byte 2 x
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * kPyrTileW, y0 = blockIdx.y * a.th;
+    const int tw = min(kPyrTileW, a.w - x0), th = min(a.th, a.h - y0);
+    const uint8_t* src = a.src + (size_t)blockIdx.z * a.src_frame;
+    uint8_t* dst = a.dst + (size_t)blockIdx.z * a.dst_frame;
+    const ResizeTap* __restrict__ xt = a.xt;
+    const ResizeTap* __restrict__ yt = a.yt;
+    // source footprint of the tile
+    const int sxa = xt[x0].ofs & ~3;
+    const int sxe = xt[x0 + tw - 1].pad;
+    const int sy0 = yt[y0].ofs;
+    const int nrows = yt[y0 + th - 1].pad - sy0 + 1;
+    const int nwords = (sxe - sxa + 4) >> 2;       // <= 64 (checked on the host)
+    {
+        // a warp stages 32 consecutive words of one source row per pass (rows tid >> 6, +4, ...); the byte that follows a word
+        // comes from the next lane's word (shuffle), for lane 31 from one more load
+        const int wcol = tid & 63;
+        const bool mine = wcol < nwords;
+        const bool next_in_row = mine && sxa + 4 * wcol + 4 < a.src_pitch;      // the word after the row's last one is never needed (zero weight)
+        const uint8_t* gp = src + (size_t)(sy0 + (tid >> 6)) * a.src_pitch + sxa + 4 * wcol;
+        unsigned char* sp = s_pair + (tid >> 6) * a.row_bytes + 8 * wcol;
+        const size_t gstep = (size_t)4 * a.src_pitch;
+        const int sstep = 4 * a.row_bytes;
+        for (int r = tid >> 6; r < nrows; r += 4, gp += gstep, sp += sstep) {
+            const uint32_t w = mine ? *reinterpret_cast<const uint32_t*>(gp) : 0u;
+            uint32_t wn = __shfl_down_sync(0xffffffffu, w, 1);
+            if (lane == 31) wn = next_in_row ? *reinterpret_cast<const uint32_t*>(gp + 4) : 0u;
+            // pairs (p0,p1) (p1,p2) | (p2,p3) (p3,p4)
+            if (mine) *reinterpret_cast<uint2*>(sp) = make_uint2(__byte_perm(w, wn, 0x2110), __byte_perm(w, wn, 0x4332));
+        }
+    }
+    const int X0 = x0 + 4 * lane;
+    const int npx = max(0, min(4, tw - 4 * lane));
+    // horizontal taps of my 4 columns: shared-memory address of the pair and both weights packed as 16-bit pairs.  Where OpenCV
+    // clamps the right tap (pad == ofs at the right edge) the fraction is zero, so c1 == 0 and the pair's second byte
+    // contributes nothing.
+    uint32_t pa[4], cw[4];
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_pair);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint2 traw = *reinterpret_cast<const uint2*>(xt + min(X0 + i, a.w - 1));      // {ofs, c0 | c1, pad}
+        pa[i] = s_base + 2u * (uint32_t)((int)(int16_t)(traw.x & 0xffffu) - sxa);
+        cw[i] = (traw.x >> 16) | (traw.y << 16);
+    }
+    __syncthreads();
+    if (npx == 0) return;
+    const int rw = a.th >> 3;
+    int dy = warp * rw;
+    const int dy_end = min(th, dy + rw);
+    if (dy >= dy_end) return;
+
+    int HA[4] = {0, 0, 0, 0}, HB[4] = {0, 0, 0, 0};
+    constexpr int kNone = -(1 << 20);
+    int r_lo = kNone, r_hi = kNone;
+    uint8_t* out = dst + (size_t)(y0 + dy) * a.dst_pitch + X0;
+    uint2 tnext = *reinterpret_cast<const uint2*>(yt + y0 + dy);
+    auto hrow = [&](int r, int (&hh)[4]) {
+        const uint32_t ro = (uint32_t)(r * a.row_bytes);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t two;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(two) : "r"(pa[i] + ro));
+            int acc;      // S[o]*c0 + S[o+1]*c1: 16-bit weights x unsigned bytes
+            asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(cw[i]), "r"(two), "r"(0));
+            hh[i] = acc >> 4;
+        }
+    };
+    // ((b0*lo) >> 16) + ((b1*hi) >> 16) + 2 as multiply-high-adds on weights pre-shifted by 16 (each term floored on its own exactly
+    // as in OpenCV); the result is < 1024, so no mask is needed after the final shift
+    auto emit = [&](const int (&L)[4], const int (&H)[4], int b0, int b1) {
+        uint32_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = (uint32_t)(__mulhi(b1, H[i]) + __mulhi(b0, L[i]) + 2) >> 2;
+        if (npx == 4) {
+            *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                if (i < npx) out[i] = (uint8_t)v[i];
+        }
+        out += a.dst_pitch;
+        dy++;
+    };
+    // one output row with the low source row's sums in `lo` and the high row's in `hi`; returns true if the roles swapped.  Every
+    // path names its registers statically (no run-time choice between the two arrays: that costs a dozen moves per row).
+    auto row_step = [&](int (&lo)[4], int (&hi)[4]) -> bool {
+        const uint2 traw = tnext;
+        if (dy + 1 < dy_end) tnext = *reinterpret_cast<const uint2*>(yt + y0 + dy + 1);
+        const int r0 = (int)(int16_t)(traw.x & 0xffffu) - sy0, r1 = (int)(int16_t)(traw.y >> 16) - sy0;
+        const int b0 = (int)(traw.x & 0xffff0000u), b1 = (int)(traw.y << 16);      // weights << 16
+        if (r0 == r_hi && r1 != r0) {
+            // the usual step: the old high row becomes the low row, the new high row goes where the old low row was
+            hrow(r1, lo);
+            r_lo = r0; r_hi = r1;
+            emit(hi, lo, b0, b1);
+            return true;
+        }
+        if (r0 != r_lo) { hrow(r0, lo); r_hi = kNone; }
+        if (r1 == r0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) hi[i] = lo[i];
+        } else if (r1 != r_hi) hrow(r1, hi);
+        r_lo = r0; r_hi = r1;
+        emit(lo, hi, b0, b1);
+        return false;
+    };
+    // state 0: low row in HA, high row in HB; state 1: the other way round
+    bool state1 = false;
+    while (dy < dy_end) {
+        if (!state1) { if (row_step(HA, HB)) state1 = true; }
+        else { if (row_step(HB, HA)) state1 = false; }
+    }
+}
+
+static int launch_pyramid_v3(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
+    static DeviceOnce once;
+    if (!once.run([&] { return cudaFuncSetAttribute(pyr_resize3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) == cudaSuccess; }))
+        return -1;
+    int launches = 0;
+    for (int l = 1; l < fl.nlevels; l++) {   // level 0 is the input image itself
+        const LevelGeom& g = hg[l];
+        const LevelGeom& gs = hg[l - 1];
+        Pyr3Args a;
+        if (l == 1) { a.src = d.in; a.src_frame = d.in_frame_stride; a.src_pitch = fl.in_pitch; }
+        else { a.src = d.pyr + gs.plane_off + (size_t)kEdge * gs.pitch + kXPad; a.src_frame = (size_t)fl.pyr_bytes; a.src_pitch = gs.pitch; }
+        a.dst = d.pyr + g.plane_off + (size_t)kEdge * g.pitch + kXPad; a.dst_frame = (size_t)fl.pyr_bytes; a.dst_pitch = g.pitch;
+        a.xt = d.xtab + g.xtab_off; a.yt = d.ytab + g.ytab_off;
+        a.w = g.w; a.h = g.h; a.th = g.t3_h; a.row_bytes = g.t3_row_bytes;
+        const dim3 grid((g.w + kPyrTileW - 1) / kPyrTileW, (g.h + g.t3_h - 1) / g.t3_h, n_frames);
+        pyr_resize3_kernel<<<grid, 256, (size_t)g.t3_smem + 16, s>>>(a);
+        launches++;
+    }
+    return launches;
+}
+
 static int launch_pyramid_v1(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
     int launches = 0;
     for (int l = 1; l < fl.nlevels; l++) {   // level 0 is the input image itself
@@ -282,8 +447,15 @@ static int launch_pyramid_v1(const DevPtrs& d, const FrameLayout& fl, const Leve
 }
 
 int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
-    // ORBCUDA_PYR=2 selects the two-phase kernel (A/B switch; results are identical, the first kernel is faster)
+    // ORBCUDA_PYR: 1 (default) the first kernel, 2 the two-phase kernel, 3 the pair-staged kernel (A/B switch; results are identical,
+    // the first kernel is as fast as the third and faster than the second)
     static const int variant = [] { const char* e = getenv("ORBCUDA_PYR"); return e ? atoi(e) : 1; }();
+    if (variant == 3) {
+        bool ok = true;
+        for (int l = 1; l < fl.nlevels; l++) ok = ok && hg[l].t3_smem > 0;
+        if (ok) return launch_pyramid_v3(d, fl, hg, n_frames, s);
+        return launch_pyramid_v1(d, fl, hg, n_frames, s);        // a scale factor the pair tiling does not cover
+    }
     if (variant == 1) return launch_pyramid_v1(d, fl, hg, n_frames, s);
     int max_smem = 0;
     for (int l = 1; l < fl.nlevels; l++) {
