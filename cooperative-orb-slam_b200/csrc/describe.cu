@@ -1,4 +1,5 @@
-// describe.cu -- K5: IC_Angle orientation + steered rBRIEF descriptor, fused, one warp per key point
+// describe.cu -- K5: IC_Angle orientation + steered rBRIEF descriptor, fused; persistent warps, a warp owns a group of key
+// points, both pixel neighbourhoods of a key point arrive in shared memory by TMA bulk tensor copies
 // (replaces computeOrientation/IC_Angle R21/src/ORBextractor.cc:472-479,:77-104 and
 // computeDescriptors/computeOrbDescriptor :1034-1041,:108-147, plus the level -> image coordinate
 // scaling and level-major concatenation of operator() :1072-1104).
@@ -6,7 +7,7 @@
 // Float parity: fastAtan2 is OpenCV's degree-7 polynomial evaluated in strict fp32 with separate
 // multiplies and adds (__fmul_rn/__fadd_rn: no FMA contraction); the pattern rotation is
 // x*b + y*a / x*a - y*b again without FMA and rounded with cvRound == round-half-even
-// (__float2int_rn).  cos/sin are evaluated in double and rounded once to float (the reference calls
+// (magic-number add).  cos/sin are evaluated in double and rounded once to float (the reference calls
 // libm cosf/sinf, which is not correctly rounded and differs between glibc builds).
 #include "internal.h"
 #include <cuda.h>

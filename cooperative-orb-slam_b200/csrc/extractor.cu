@@ -86,7 +86,7 @@ struct orbx_handle_s {
     int32_t* h_counts = nullptr; size_t cap_h_counts = 0;
 
     // CUDA graph of the kernel chain for small (latency-bound) calls: captured on the second call with the same signature,
-    // replayed afterwards -- one graph launch instead of 13 kernel launches (ORBCUDA_GRAPH=0 disables it)
+    // replayed afterwards -- one graph launch instead of 12 kernel launches (ORBCUDA_GRAPH=0 disables it)
     struct GraphKey {
         int n_frames, width, height, cap, in_pitch; const void *in, *kps, *desc, *counts; size_t in_stride;
         bool operator==(const GraphKey& o) const {

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Small fixed launch sequence for ncu: 3 batches of 64 frames (13 launches each: 8 pyramid, fast score,
+"""Small fixed launch sequence for ncu: 3 batches of 64 frames (12 launches each: 7 pyramid, fast score,
 blur, cell nms, quadtree, describe) followed by one 2000 x 1M 2-NN search (2 launches)."""
 import ctypes as C
 import importlib, os, sys
