@@ -380,12 +380,14 @@ static int launch_describe_g(const TmapSet& set, const DevPtrs& d, const FrameLa
 static int launch_describe_variant(const TmapSet& set, const DevPtrs& d, const FrameLayout& fl, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,
                                    int32_t* d_counts, int cap, cudaStream_t s) {
     // Groups of G key points per work item: the per-lane trigonometry of a group costs the same for any G, small groups
-    // balance better and spread a single frame over the whole GPU.  ORBCUDA_DESC_G = 8 | 16 | 32 forces one (A/B switch).
+    // balance better and spread a single frame over the whole GPU (measured on 128-frame batches: 0.099 ms with G = 8, 0.106
+    // with 16, 0.132 with 32; single frame: 17 us with G = 8, 23 with 16, 38 with 32).  ORBCUDA_DESC_G = 4 | 8 | 16 | 32 forces one.
     static const int forced = [] { const char* e = getenv("ORBCUDA_DESC_G"); return e ? atoi(e) : 0; }();
-    const int g = forced ? forced : 8;   // measured on 128-frame batches: 0.099 ms (G = 8), 0.106 (16), 0.132 (32)
+    const int g = forced ? forced : (n_frames < 4 ? 4 : 8);
     if (g >= 32) return launch_describe_g<32, kDescWarps, 3>(set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
     if (g >= 16) return launch_describe_g<16, kDescWarps, 3>(set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
-    return launch_describe_g<8, kDescWarps, 3>(set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
+    if (g >= 8) return launch_describe_g<8, kDescWarps, 3>(set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
+    return launch_describe_g<4, kDescWarps, 3>(set, d, fl, n_frames, d_kps, d_desc, d_counts, cap, s);
 }
 
 int launch_describe(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, orb_keypoint_t* d_kps, uint8_t* d_desc,

@@ -138,7 +138,7 @@ template <bool HF, int FA> __device__ __forceinline__ uint32_t fast_score4(const
     return __byte_perm(sP, sQ, 0x6240);
 }
 
-template <bool HF, int FA> __global__ void __launch_bounds__(128, 5) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
+template <bool HF, int FA, int ROWS> __global__ void __launch_bounds__(128, 5) fast_score_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, int th) {
     if (blockIdx.x == 0) {
         // this frame's survivor counters and cell flags, consumed by fast_nms_kernel two launches later on the same
         // stream (saves two memset nodes per batch)
@@ -154,7 +154,7 @@ template <bool HF, int FA> __global__ void __launch_bounds__(128, 5) fast_score_
     const int id = (blockIdx.x - first_block) * blockDim.x + threadIdx.x;
     const int sy = id / nsx;
     const int x0 = kMinBorder + 4 * (id - sy * nsx);
-    const int y0 = kEdge + sy * kFastRows;
+    const int y0 = kEdge + sy * ROWS;
     if (y0 >= g.h - kEdge) return;
     int pitch;
     const uint8_t* src = level_roi(d, fl, g, level, blockIdx.y, pitch) + (x0 - 4);   // x0 >= 16: never leaves the row
@@ -179,9 +179,9 @@ template <bool HF, int FA> __global__ void __launch_bounds__(128, 5) fast_score_
         const uint32_t* w = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)min(y0 + 3, g.h - 1) * pitch);
         n0 = w[0]; n1 = w[1]; n2 = w[2];
     }
-    static_assert(kFastRows % 7 == 0, "blocks of seven rows");
+    static_assert(ROWS % 7 == 0, "blocks of seven rows");
 #pragma unroll 1
-    for (int blk = 0; blk < kFastRows / 7; blk++) {
+    for (int blk = 0; blk < ROWS / 7; blk++) {
 #pragma unroll
         for (int j = 0; j < 7; j++) {
             const int y = y0 + blk * 7 + j;
@@ -200,13 +200,16 @@ template <bool HF, int FA> __global__ void __launch_bounds__(128, 5) fast_score_
 
 int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, int min_th,
                       cudaStream_t s) {
+    // rows per strip: 14 for batches, 7 for a few frames (twice as many threads of half the length: a single frame is a latency
+    // problem, 114 CTAs of 14-row strips do not even fill the SMs)
+    const int rows = n_frames >= 4 ? kFastRows : 7;
     LevelBlocks lb;
     int total = 0;
     const int threads = 128;
     for (int l = 0; l < fl.nlevels; l++) {
         lb.start[l] = total;
         const int nsx = (hg[l].w - kEdge - kMinBorder + 3) / 4;
-        const int nsy = (hg[l].h - 2 * kEdge + kFastRows - 1) / kFastRows;
+        const int nsy = (hg[l].h - 2 * kEdge + rows - 1) / rows;
         total += (nsx * nsy + threads - 1) / threads;
     }
     for (int l = fl.nlevels; l <= kMaxLevels; l++) lb.start[l] = total;
@@ -214,13 +217,14 @@ int launch_fast_score(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* 
     // pipe; A/B switch, results are identical)
     static const int fa = [] { const char* e = getenv("ORBCUDA_FAST_FMA"); return e ? atoi(e) : kFastFmaDefault; }();
     const dim3 grid(total, n_frames);
+    if (rows == 7) { fast_score_kernel<true, 8, 7><<<grid, threads, 0, s>>>(d, fl, lb, min_th); return 1; }
     switch (fa) {
-        case 0: fast_score_kernel<false, 0><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
-        case 12: fast_score_kernel<true, 12><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
-        case 20: fast_score_kernel<true, 20><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
-        case 24: fast_score_kernel<true, 24><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
-        case 16: fast_score_kernel<true, 16><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
-        default: fast_score_kernel<true, 8><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 0: fast_score_kernel<false, 0, kFastRows><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 12: fast_score_kernel<true, 12, kFastRows><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 16: fast_score_kernel<true, 16, kFastRows><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 20: fast_score_kernel<true, 20, kFastRows><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        case 24: fast_score_kernel<true, 24, kFastRows><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
+        default: fast_score_kernel<true, 8, kFastRows><<<grid, threads, 0, s>>>(d, fl, lb, min_th); break;
     }
     return 1;
 }

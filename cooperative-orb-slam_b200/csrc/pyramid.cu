@@ -412,7 +412,8 @@ __global__ void __launch_bounds__(256) pyr_resize3_kernel(Pyr3Args a) {
     }
 }
 
-static int launch_pyramid_v3(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
+// th_small > 0: tiles of that many rows instead of the level's t3_h (a few frames: many short CTAs instead of few long ones)
+static int launch_pyramid_v3(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s, int th_small = 0) {
     static DeviceOnce once;
     if (!once.run([&] { return cudaFuncSetAttribute(pyr_resize3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) == cudaSuccess; }))
         return -1;
@@ -425,9 +426,17 @@ static int launch_pyramid_v3(const DevPtrs& d, const FrameLayout& fl, const Leve
         else { a.src = d.pyr + gs.plane_off + (size_t)kEdge * gs.pitch + kXPad; a.src_frame = (size_t)fl.pyr_bytes; a.src_pitch = gs.pitch; }
         a.dst = d.pyr + g.plane_off + (size_t)kEdge * g.pitch + kXPad; a.dst_frame = (size_t)fl.pyr_bytes; a.dst_pitch = g.pitch;
         a.xt = d.xtab + g.xtab_off; a.yt = d.ytab + g.ytab_off;
-        a.w = g.w; a.h = g.h; a.th = g.t3_h; a.row_bytes = g.t3_row_bytes;
-        const dim3 grid((g.w + kPyrTileW - 1) / kPyrTileW, (g.h + g.t3_h - 1) / g.t3_h, n_frames);
-        pyr_resize3_kernel<<<grid, 256, (size_t)g.t3_smem + 16, s>>>(a);
+        a.w = g.w; a.h = g.h; a.row_bytes = g.t3_row_bytes;
+        size_t smem = (size_t)g.t3_smem + 16;
+        a.th = g.t3_h;
+        if (th_small > 0 && th_small < g.t3_h) {
+            // rows a tile of th_small output rows can touch: its taps advance by src/dst rows per output row (+ the two ends)
+            a.th = th_small;
+            const int rows = (int)((double)th_small * gs.h / g.h) + 4;
+            smem = (size_t)std::min(rows, g.t3_rows) * g.t3_row_bytes + 16;
+        }
+        const dim3 grid((g.w + kPyrTileW - 1) / kPyrTileW, (g.h + a.th - 1) / a.th, n_frames);
+        pyr_resize3_kernel<<<grid, 256, smem, s>>>(a);
         launches++;
     }
     return launches;
@@ -447,15 +456,15 @@ static int launch_pyramid_v1(const DevPtrs& d, const FrameLayout& fl, const Leve
 }
 
 int launch_pyramid(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
-    // ORBCUDA_PYR: 1 (default) the first kernel, 2 the two-phase kernel, 3 the pair-staged kernel (A/B switch; results are identical,
-    // the first kernel is as fast as the third and faster than the second)
-    static const int variant = [] { const char* e = getenv("ORBCUDA_PYR"); return e ? atoi(e) : 1; }();
-    if (variant == 3) {
-        bool ok = true;
-        for (int l = 1; l < fl.nlevels; l++) ok = ok && hg[l].t3_smem > 0;
-        if (ok) return launch_pyramid_v3(d, fl, hg, n_frames, s);
-        return launch_pyramid_v1(d, fl, hg, n_frames, s);        // a scale factor the pair tiling does not cover
-    }
+    // ORBCUDA_PYR: 0 (default) = the first kernel for batches and the pair-staged kernel with 16-row tiles for a few frames (a single
+    // frame is a latency problem: seven dependent launches of ~9 us each with 64-row tiles, 8 rows per warp one after the other);
+    // 1 the first kernel, 2 the two-phase kernel, 3 the pair-staged kernel with tall tiles (A/B switches; results are identical)
+    static const int variant = [] { const char* e = getenv("ORBCUDA_PYR"); return e ? atoi(e) : 0; }();
+    bool v3_ok = true;
+    for (int l = 1; l < fl.nlevels; l++) v3_ok = v3_ok && hg[l].t3_smem > 0;
+    static const int th_small = [] { const char* e = getenv("ORBCUDA_PYR_TH"); return e ? atoi(e) : 16; }();
+    if (variant == 0) return (n_frames < 4 && v3_ok) ? launch_pyramid_v3(d, fl, hg, n_frames, s, th_small) : launch_pyramid_v1(d, fl, hg, n_frames, s);
+    if (variant == 3) return v3_ok ? launch_pyramid_v3(d, fl, hg, n_frames, s) : launch_pyramid_v1(d, fl, hg, n_frames, s);
     if (variant == 1) return launch_pyramid_v1(d, fl, hg, n_frames, s);
     int max_smem = 0;
     for (int l = 1; l < fl.nlevels; l++) {
@@ -617,6 +626,7 @@ __device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ src, int 
 
 // One launch: the interior strips (4 <= x0 <= w-8) of every level first, then the 2-3 edge strips per strip row of every
 // level (blocks >= lb_edge.start[0] -- whole blocks take one path or the other).
+template <int ROWS>
 __global__ void __launch_bounds__(128) blur7_kernel(DevPtrs d, FrameLayout fl, LevelBlocks lb, LevelBlocks lb_edge) {
     const bool edge = (int)blockIdx.x >= lb_edge.start[0];
     int first_block;
@@ -626,18 +636,24 @@ __global__ void __launch_bounds__(128) blur7_kernel(DevPtrs d, FrameLayout fl, L
     const int nsx = (g.w + 3) >> 2;
     const int ni = max((g.w - 8) >> 2, 0);            // interior strips per row: x0 = 4, 8, ..., 4*ni
     const int per_row = edge ? nsx - ni : ni;
-    const int nsy = (g.h + kBlurRows - 1) / kBlurRows;
+    const int nsy = (g.h + ROWS - 1) / ROWS;
     const int id = (blockIdx.x - first_block) * blockDim.x + threadIdx.x;
     if (id >= per_row * nsy) return;
     int pitch;
     const uint8_t* src = level_roi(d, fl, g, level, blockIdx.y, pitch);
     uint8_t* dst = d.blur + (size_t)blockIdx.y * fl.splane_bytes + g.splane_off;
     const int sy = id / per_row, k = id - sy * per_row;
-    if (edge) blur_strip<true, kBlurRows>(src, pitch, dst, g.spitch, g.w, g.h, k == 0 ? 0 : 4 * (ni + k), sy * kBlurRows);
-    else blur_strip<false, kBlurRows>(src, pitch, dst, g.spitch, g.w, g.h, 4 + 4 * k, sy * kBlurRows);
+    if (edge) blur_strip<true, ROWS>(src, pitch, dst, g.spitch, g.w, g.h, k == 0 ? 0 : 4 * (ni + k), sy * ROWS);
+    else blur_strip<false, ROWS>(src, pitch, dst, g.spitch, g.w, g.h, 4 + 4 * k, sy * ROWS);
 }
 
 int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, int n_frames, cudaStream_t s) {
+    // Rows per strip: 16 for batches (fewest redundant window rows: 22 loaded for 16 written); 4 for a few frames -- a single frame
+    // has only ~15 k strips of 16 rows (one CTA per SM, each thread a serial chain of 16 rows: 18.7 us); four rows per strip are
+    // four times as many threads of a quarter of the length (ORBCUDA_BLUR_ROWS forces one)
+    static const int forced = [] { const char* e = getenv("ORBCUDA_BLUR_ROWS"); return e ? atoi(e) : 0; }();
+    int rows = forced ? forced : (n_frames >= 4 ? kBlurRows : 4);
+    if (rows != 4 && rows != 8) rows = kBlurRows;
     const int threads = 128;
     LevelBlocks lb[2];
     int total = 0;
@@ -645,13 +661,15 @@ int launch_blur(const DevPtrs& d, const FrameLayout& fl, const LevelGeom* hg, in
         for (int l = 0; l < fl.nlevels; l++) {
             lb[edge].start[l] = total;
             const int nsx = (hg[l].w + 3) / 4, ni = std::max((hg[l].w - 8) / 4, 0);
-            const int strips = (edge ? nsx - ni : ni) * ((hg[l].h + kBlurRows - 1) / kBlurRows);
+            const int strips = (edge ? nsx - ni : ni) * ((hg[l].h + rows - 1) / rows);
             total += (strips + threads - 1) / threads;
         }
         for (int l = fl.nlevels; l <= kMaxLevels; l++) lb[edge].start[l] = total;
     }
     if (total == 0) return 0;
-    blur7_kernel<<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb[0], lb[1]);
+    if (rows == 4) blur7_kernel<4><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb[0], lb[1]);
+    else if (rows == 8) blur7_kernel<8><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb[0], lb[1]);
+    else blur7_kernel<kBlurRows><<<dim3(total, n_frames), threads, 0, s>>>(d, fl, lb[0], lb[1]);
     return 1;
 }
 

@@ -56,7 +56,7 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     rng = np.random.default_rng(seed)
     t_end = time.time() + budget
-    n_ext = n_kp = n_knn = n_rej = 0
+    n_ext = n_kp = n_knn = n_rej = n_batch = 0
     pool = ThreadPoolExecutor(8)
     while time.time() < t_end:
         cases = [one_extraction(rng) for _ in range(8)]
@@ -91,6 +91,17 @@ def main():
             else:
                 assert k.tobytes() == rk.tobytes() and np.array_equal(d, rd), ("extraction differs", c[0], len(k), len(rk))
             n_ext += 1; n_kp += len(rk)
+            if n_ext % 2 == 0:
+                # the same image as a batch of five frames: batches of >= 4 frames run the throughput variants of the kernels
+                # (14-row FAST strips, 16-row blur strips, 64-row resize tiles), single frames the latency variants
+                ex = orb.ORBextractor(nfeat, sf, nl, ini, mn, max_width=w, max_height=h, max_batch=5)
+                bk, bd, bc = ex.extract_batch(np.stack([img] * 5))
+                for f in range(5):
+                    assert bc[f] == len(rk), ("batch count differs", c[0], f)
+                    if len(rk):
+                        assert bk[f, :bc[f]].tobytes() == rk.tobytes() and np.array_equal(bd[f, :bc[f]], rd), ("batch extraction differs", c[0], f)
+                ex.close()
+                n_batch += 1
         # matcher
         nq = int(rng.integers(1, 3000)); nm = int(rng.integers(0, 150000))
         m = synth.descriptors(max(nm, 1), seed=int(rng.integers(0, 1 << 30)))[:nm]
@@ -107,7 +118,8 @@ def main():
         oracle_lib.lib().orc_knn2(q.ctypes.data, nq, np.ascontiguousarray(m).ctypes.data, nm, 0, i1.ctypes.data, d1.ctypes.data, d2.ctypes.data, 8)
         assert np.array_equal(ref0[0], i1) and np.array_equal(ref0[1], d1) and np.array_equal(ref0[2], d2), ("2-NN differs from the oracle", nq, nm)
         n_knn += 1
-    print("soak ok: %d extractions (%d key points, %d rejected by both), %d 2-NN problems x 6 variants, seed %d" % (n_ext, n_kp, n_rej, n_knn, seed))
+    print("soak ok: %d extractions (%d key points, %d rejected by both; %d of them again as batches of 5), %d 2-NN problems x 6 variants, seed %d"
+          % (n_ext, n_kp, n_rej, n_batch, n_knn, seed))
 
 
 if __name__ == "__main__":
