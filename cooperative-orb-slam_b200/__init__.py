@@ -273,8 +273,17 @@ class ORBextractor:
         return kps, desc, cnt
 
     def extract_batch_async(self, images, kps, desc, cnt):
+        """Queue one batch; `kps` [b][cap] KP_DTYPE, `desc` [b][cap][32] uint8 and `cnt` [b] int32 are written by wait().  The
+        arrays must be C-contiguous (rows of `images` may be strided); references are kept until wait()."""
         b, h, w = images.shape
         cap = kps.shape[1]
+        if images.dtype != np.uint8 or images.strides[2] != 1:
+            raise ValueError("images must be uint8 with contiguous rows")
+        if not (kps.flags.c_contiguous and desc.flags.c_contiguous and cnt.flags.c_contiguous):
+            raise ValueError("output arrays must be C-contiguous")
+        if kps.dtype.itemsize != 28 or desc.dtype != np.uint8 or cnt.dtype != np.int32 or kps.shape[0] != b or desc.shape != (b, cap, 32) or cnt.shape != (b,):
+            raise ValueError("output arrays: kps [b][cap] of 28-byte records, desc [b][cap][32] uint8, cnt [b] int32")
+        self._pending_refs = (images, kps, desc, cnt)
         _check(self._L.orbx_extract_batch_async(self._h, C.c_void_p(images.ctypes.data), b, w, h, images.strides[1],
                                                 images.strides[0], _p(kps), _p(desc), cap, _p(cnt)),
                "orbx_extract_batch_async")
@@ -289,7 +298,10 @@ class ORBextractor:
         self._last = (b, w, h)
 
     def wait(self):
-        _check(self._L.orbx_wait(self._h), "orbx_wait")
+        try:
+            _check(self._L.orbx_wait(self._h), "orbx_wait")
+        finally:
+            self._pending_refs = None
 
     # ---- mvImagePyramid and the other stage views
     def level_size(self, level):
