@@ -128,8 +128,13 @@ struct PeerLayout {
     int world, nq_cap;
     __host__ __device__ size_t record_index(int parity, int rank, int q) const { return ((size_t)parity * world + rank) * nq_cap + q; }
     __host__ __device__ size_t flags_offset() const { return (size_t)2 * world * nq_cap * sizeof(int4); }
-    __host__ __device__ size_t bytes() const { return flags_offset() + 2 * kMaxPeers * sizeof(unsigned) + 64; }
+    // pruning bounds of the sharded search, one int per query (rounded up to whole query blocks): every rank's tcgen05 kernel
+    // publishes its second-best distances into EVERY rank's array, so a shard does not have to warm its bound up alone
+    __host__ __device__ size_t bound_offset() const { return (flags_offset() + 2 * kMaxPeers * sizeof(unsigned) + 64 + 255) & ~(size_t)255; }
+    __host__ __device__ int bound_ints() const { return (nq_cap + 511) / 512 * 512; }
+    __host__ __device__ size_t bytes() const { return bound_offset() + (size_t)bound_ints() * sizeof(int); }
 };
+struct BoundPeers { int* remote[kMaxPeers - 1]; int n; };      // the other ranks' bound arrays (n = 0: not shared)
 struct PeerPtrs { unsigned char* base[kMaxPeers]; };
 struct PeerExchange {
     int device = 0, rank = 0, world = 0, nq_cap = 0;
@@ -143,7 +148,7 @@ struct PeerExchange {
     bool connected = false;
 };
 int launch_merge_exchange(PeerExchange* peer, const void* d_partial, int parts, int nq, int32_t* d_out, int* d_bound, int n_bound,
-                          cudaStream_t s);
+                          cudaStream_t s, bool bound_is_shared = false);
 struct RatioTest { int32_t* d_match; float ratio; int th; int strict; };   // R21/src/ORBmatcher.cc:228-230 / :598-600 on the merged records
 int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int64_t index_base, int32_t* d_out,
                 int variant, cudaStream_t s, PeerExchange* peer = nullptr, const RatioTest* rt = nullptr);

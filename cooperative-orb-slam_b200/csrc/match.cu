@@ -993,7 +993,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t targe
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ m, long long nm, long long per_split,
-                 long long index_base, int4* __restrict__ partial, int* __restrict__ shared_d2) {
+                 long long index_base, int4* __restrict__ partial, int* __restrict__ shared_d2, BoundPeers bp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* s_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 2 x [128 rows][256 B] (64 KB)
     unsigned char* s_b = s_a + kTcQ * 256;                                               // kPairBStages x [64 rows][256 B]
@@ -1147,6 +1147,25 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             if (cnt >= kColsPerWarp) tc_drain64<true>(v, pa, ib, kColsPerWarp, glim, gptr, best);
             else if (cnt > 0) tc_drain64<false>(v, pa, ib, cnt, glim, gptr, best);
         };
+        // Sharded map: the other ranks prune with this rank's bounds too.  Publishing every improvement of every thread to
+        // every peer was measured SLOWER than not sharing (millions of 4-byte NVLink transactions per search).  Instead ONE
+        // thread per query of the rank (split 0, first column half) forwards the rank's bound -- the minimum over all its CTAs,
+        // read from the local array -- to the peers' arrays at tiles 1, 2, 4, 8, ... and only when it fell: ~10^5 fire-and-forget
+        // minima per search.  It is a bound on the merged result whichever shard produced it.
+        const bool forwarder = bp.n > 0 && blockIdx.y == 0 && chalf == 0 && q0 + row < nq;
+        int last_fwd = 0x7f7f7f7f;
+        auto forward_bound = [&](int i, int g) {
+            if (forwarder && (i & (i - 1)) == 0 && g < last_fwd) {
+                last_fwd = g;
+                // the element index goes through an opaque move so that the 15 remote addresses are formed here, in this rare
+                // path, instead of being hoisted into 30 registers that stay live across the whole tile loop
+                int qidx;
+                asm volatile("mov.s32 %0, %1;" : "=r"(qidx) : "r"(q0 + row));
+#pragma unroll
+                for (int p = 0; p < kMaxPeers - 1; p++)
+                    if (p < bp.n) asm volatile("red.relaxed.sys.global.min.s32 [%0], %1;" :: "l"(bp.remote[p] + qidx), "r"(g) : "memory");
+            }
+        };
         if (ntiles > 0) raw_a = fetch(0);
         if (ntiles > 1) raw_b = fetch(1);
         for (int i = 0; i < ntiles; i++) {
@@ -1171,6 +1190,7 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             // sharded map is ~50 tiles per CTA) would otherwise run a sixth of its tiles against "no bound yet"
             if ((i & kPairBoundEvery) == 0 || i < 8) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "+r"(gval) : "l"(gptr) : "memory");
             if (i >= kTcLag) drain_update(i - kTcLag, v, glim);
+            forward_bound(i, gval);
         }
         for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
             uint32_t v[32];
@@ -1298,6 +1318,7 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     if (!knn_scratch(dev, s, (size_t)n_bound, (size_t)splits * nq * sizeof(int4), &sc)) return -1;
     int4* partial = sc.partial;
     int* const bound = sc.bound;
+    int* shared_bound = nullptr;       // set when the bounds of this search live in the peer buffer
     if (variant == 1) {
         const size_t smem = (size_t)kMmaTile * 256 + kMmaTile * sizeof(int);
         static DeviceOnce once_configured;
@@ -1315,9 +1336,19 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
         const size_t smem = (size_t)kTcQ * 256 + kPairBStages * (size_t)kPairHalfN * 256 + 1024;
         static DeviceOnce once_configured5;
         if (!once_configured5.run([&] { return cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+        // sharded search over peer buffers: the bounds live in the peer buffer and every rank's kernel publishes into all of them
+        // (ORBCUDA_SHARE_BOUND=0: each rank keeps its bounds to itself -- A/B switch, results are identical)
+        static const bool share = [] { const char* e = getenv("ORBCUDA_SHARE_BOUND"); return e ? atoi(e) != 0 : true; }();
+        BoundPeers bp{};
         int* shared_d2 = bound;
+        if (peer && peer->connected && peer->world > 1 && share && n_bound <= peer->layout.bound_ints()) {
+            shared_d2 = reinterpret_cast<int*>(peer->local + peer->layout.bound_offset());
+            for (int r = 0; r < peer->world; r++)
+                if (r != peer->rank) bp.remote[bp.n++] = reinterpret_cast<int*>(peer->peers.base[r] + peer->layout.bound_offset());
+            shared_bound = shared_d2;
+        }
         knn2_pair_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
-                                                                        index_base, partial, shared_d2);
+                                                                        index_base, partial, shared_d2, bp);
     } else if (variant == 4) {
         const size_t smem = kTcBStages * (size_t)kTcN * 256 + 1024;
         static DeviceOnce once_configured4;
@@ -1334,7 +1365,7 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     }
     if (peer) {
         // multi-GPU: merge my splits, push my records into every rank's buffer over NVLink, wait for theirs, merge: one kernel
-        if (launch_merge_exchange(peer, partial, splits, nq, d_out, bound, n_bound, s) < 0) return -1;
+        if (launch_merge_exchange(peer, partial, splits, nq, d_out, shared_bound ? shared_bound : bound, n_bound, s, shared_bound != nullptr) < 0) return -1;
     } else {
         merge_top2_kernel<<<merge_grid(nq), 256, 0, s>>>(partial, splits, nq, (int4*)d_out, bound, n_bound, rt ? rt->d_match : nullptr,
                                                            rt ? rt->ratio : 0.f, rt ? rt->th : 0, rt ? rt->strict : 0);

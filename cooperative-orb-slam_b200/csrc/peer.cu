@@ -39,10 +39,13 @@ __device__ __forceinline__ void merge_rec(int4& a, const int4 b) {
 __global__ void __launch_bounds__(256) merge_exchange_kernel(const int4* __restrict__ parts, int nparts, int nq, int rank, PeerLayout L, PeerPtrs peers,
                                                              unsigned epoch, unsigned* __restrict__ counter, int* __restrict__ error,
                                                              unsigned long long timeout_ns, int4* __restrict__ out, int* __restrict__ bound,
-                                                             int n_bound) {
+                                                             int n_bound, int bound_is_shared) {
     const int parity = (int)(epoch & 1u);
-    // the pruning bounds of the search in front of this kernel go back to "no bound yet" for the next one (match.cu)
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bound; i += gridDim.x * blockDim.x) bound[i] = 0x7f7f7f7f;
+    // the pruning bounds of the search in front of this kernel go back to "no bound yet" for the next one (match.cu).  Bounds that
+    // the other ranks write into (shared bounds) are reset only behind the wait below: every rank's search of this call is over
+    // then, and nobody starts the next one before this kernel ends, so no late value of this call can leak into the next.
+    if (!bound_is_shared)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bound; i += gridDim.x * blockDim.x) bound[i] = 0x7f7f7f7f;
     // ---- phase 1: merge my splits (a warp per query, lane = split: one round of loads instead of a chain of them) and store
     // the record into every rank's buffer (lane r stores to rank r)
     const int lane = threadIdx.x & 31;
@@ -84,6 +87,8 @@ __global__ void __launch_bounds__(256) merge_exchange_kernel(const int4* __restr
         }
     }
     __syncthreads();
+    if (bound_is_shared)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bound; i += gridDim.x * blockDim.x) bound[i] = 0x7f7f7f7f;
     if (!s_ok) {
         // a peer did not arrive in time: the call's output is the "no match" record for every query, never stale data
         for (int q = gwarp; q < nq; q += nwarps) if (lane == 0) out[q] = make_int4(256, -1, 256, -1);
@@ -155,13 +160,13 @@ __global__ void __launch_bounds__(256) blob_exchange_kernel(const int4* __restri
 }
 
 int launch_merge_exchange(PeerExchange* pe, const void* d_partial, int parts, int nq, int32_t* d_out, int* d_bound, int n_bound,
-                          cudaStream_t s) {
+                          cudaStream_t s, bool bound_is_shared) {
     if (!pe || !pe->connected || nq > pe->nq_cap) { set_error("merge-exchange: peer buffers not connected or nq > capacity"); return -1; }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pe->device);
     const int grid = std::max(1, std::min((nq + 7) / 8, 4 * sms));          // a warp per query; resident for sure: 256 threads, a few registers
     merge_exchange_kernel<<<grid, 256, 0, s>>>((const int4*)d_partial, parts, nq, pe->rank, pe->layout, pe->peers, pe->epoch + 1, pe->d_counter,
-                                              pe->d_error, 5ull * 1000 * 1000 * 1000, (int4*)d_out, d_bound, n_bound);
+                                              pe->d_error, 5ull * 1000 * 1000 * 1000, (int4*)d_out, d_bound, n_bound, bound_is_shared ? 1 : 0);
     if (cudaPeekAtLastError() != cudaSuccess) return -1;      // the epoch advances only with a launch that went out: ranks stay in step
     pe->epoch++;
     return 1;
@@ -181,6 +186,7 @@ int orbm_peer_create(int nq_cap, int rank, int world, int device, orbm_peer_t* o
     pe->device = device; pe->rank = rank; pe->world = world; pe->nq_cap = nq_cap;
     pe->layout.world = world; pe->layout.nq_cap = nq_cap;
     if (!cuda_ok(cudaMalloc((void**)&pe->local, pe->layout.bytes()), "cudaMalloc") || !cuda_ok(cudaMemset(pe->local, 0, pe->layout.bytes()), "cudaMemset") ||
+        !cuda_ok(cudaMemset(pe->local + pe->layout.bound_offset(), 0x7f, (size_t)pe->layout.bound_ints() * sizeof(int)), "cudaMemset") ||      // "no bound yet"
         !cuda_ok(cudaMalloc((void**)&pe->d_counter, 64), "cudaMalloc") || !cuda_ok(cudaMemset(pe->d_counter, 0, 64), "cudaMemset")) {
         orbm_peer_destroy(reinterpret_cast<orbm_peer_t>(pe));
         return ORB_ERR_CUDA;

@@ -50,6 +50,33 @@ def main():
                 assert peer.error() == 0
                 assert bool((out == full).all().item()), (nq, nm, variant, rep, rank)
                 checked += 1
+    # ---- back-to-back searches with alternating query sets and UNEVEN shards (ranks finish at different times): the pruning bounds
+    # that the ranks publish into each other's buffers (csrc/match.cu forward_bound) must never survive into the next search --
+    # set A are near copies of map descriptors (bounds fall to a few bits), set B random ones (a leaked A bound would prune away
+    # B's true neighbours)
+    nm, nq = 150000, 2000
+    m = synth.descriptors(nm, seed=77)
+    qa, m, _ = synth.query_set(m, nq=nq, seed=78)
+    qb = synth.descriptors(nq, seed=79)
+    d_all = torch.from_numpy(np.ascontiguousarray(m).reshape(-1, 32)).to(dev)
+    tri = world * (world + 1) // 2
+    lo = nm * (rank * (rank + 1) // 2) // tri; hi = nm * ((rank + 1) * (rank + 2) // 2) // tri
+    d_shard = d_all[lo:hi].contiguous()
+    d_qs = [torch.from_numpy(x).to(dev) for x in (qa, qb)]
+    fulls = [torch.empty((nq, 4), dtype=torch.int32, device=dev) for _ in range(2)]
+    for d_q, full in zip(d_qs, fulls):
+        assert L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), nq, C.c_void_p(d_all.data_ptr()), nm, 0, C.c_void_p(full.data_ptr()), 0,
+                                  C.c_void_p(cur.cuda_stream)) == 0
+    outs = [torch.full((nq, 4), -9, dtype=torch.int32, device=dev) for _ in range(2)]
+    bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    for it in range(300):
+        k = it & 1
+        peer.knn2(d_qs[k].data_ptr(), nq, d_shard.data_ptr(), hi - lo, lo, outs[k].data_ptr(), 5, cur.cuda_stream)
+        bad += (outs[k] != fulls[k]).sum()          # queued on the same stream: no host synchronisation between the searches
+    torch.cuda.synchronize()
+    assert peer.error() == 0
+    assert int(bad.item()) == 0, ("back-to-back alternating searches", rank, int(bad.item()))
+    checked += 300
     dist.barrier()
     peer.close()
     # ---- the key-frame message: every rank packs its own key frames, one fused exchange, every rank unpacks everybody's
