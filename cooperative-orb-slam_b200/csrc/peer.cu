@@ -114,6 +114,79 @@ __global__ void __launch_bounds__(256) merge_exchange_kernel(const int4* __restr
     }
 }
 
+// The same exchange as a SMALL grid (a thread per query, 128 threads per block: 16 blocks for 2000 queries).  A grid this small
+// always finds room next to the tensor-core kernel of ANOTHER search (144 of the 148 SMs, one CTA each, most of the registers):
+// with two or three searches in flight on their own streams and peer buffers, the cross-GPU wait of one search hides behind the
+// kernel of the next.  (The warp-per-query grid above is 250 blocks; next to a running search kernel only a few of them are
+// resident, they spin on the flags, and the blocks that still have to send their records wait for an SM: the exchange then ends
+// only when the other search's kernel does.)  The loads of a thread are issued in batches of six before the first merge.
+__global__ void __launch_bounds__(128) merge_exchange_small_kernel(const int4* __restrict__ parts, int nparts, int nq, int rank, PeerLayout L,
+                                                                   PeerPtrs peers, unsigned epoch, unsigned* __restrict__ counter,
+                                                                   int* __restrict__ error, unsigned long long timeout_ns, int4* __restrict__ out,
+                                                                   int* __restrict__ bound, int n_bound, int bound_is_shared) {
+    const int parity = (int)(epoch & 1u);
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    if (!bound_is_shared)
+        for (int i = gtid; i < n_bound; i += gsize) bound[i] = 0x7f7f7f7f;
+    for (int q = gtid; q < nq; q += gsize) {
+        int4 rec = make_int4(256, -1, 256, -1);
+        for (int p0 = 0; p0 < nparts; p0 += 6) {
+            int4 v[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) v[j] = p0 + j < nparts ? parts[(size_t)(p0 + j) * nq + q] : make_int4(256, -1, 256, -1);
+#pragma unroll
+            for (int j = 0; j < 6; j++) merge_rec(rec, v[j]);
+        }
+        const size_t at = L.record_index(parity, rank, q);
+        for (int r = 0; r < L.world; r++) reinterpret_cast<int4*>(peers.base[r])[at] = rec;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        if ((int)threadIdx.x < L.world)
+            st_release_sys(reinterpret_cast<unsigned*>(peers.base[threadIdx.x] + L.flags_offset()) + parity * kMaxPeers + rank, epoch);
+        if (threadIdx.x == 0) *counter = 0;
+    }
+    const unsigned* my_flags = reinterpret_cast<const unsigned*>(peers.base[rank] + L.flags_offset()) + parity * kMaxPeers;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < L.world) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(my_flags + threadIdx.x) != epoch) {
+            if (global_timer_ns() - t0 > timeout_ns) { s_ok = 0; atomicExch(error, 1 + (int)threadIdx.x); break; }
+            __nanosleep(40);
+        }
+    }
+    __syncthreads();
+    if (bound_is_shared)
+        for (int i = gtid; i < n_bound; i += gsize) bound[i] = 0x7f7f7f7f;
+    if (!s_ok) {
+        for (int q = gtid; q < nq; q += gsize) out[q] = make_int4(256, -1, 256, -1);
+        return;
+    }
+    const int4* mine = reinterpret_cast<const int4*>(peers.base[rank]);
+    for (int q = gtid; q < nq; q += gsize) {
+        int4 rec = make_int4(256, -1, 256, -1);
+        for (int r0 = 0; r0 < L.world; r0 += 8) {
+            int4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                v[j] = make_int4(256, -1, 256, -1);
+                if (r0 + j < L.world)      // written by another GPU: read it past the L1
+                    asm volatile("ld.relaxed.sys.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
+                                 : "l"(mine + L.record_index(parity, r0 + j, q)) : "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) merge_rec(rec, v[j]);
+        }
+        out[q] = rec;
+    }
+}
+
 // The same protocol for an opaque message (the key-frame message of wire.cu): every rank stores its `units` 16-byte units into
 // slot [rank] of every rank's buffer, the last block publishes the flag, every block waits for all flags and copies the
 // world's slots out of its own buffer into dst ([world][dst_units]).
@@ -164,9 +237,18 @@ int launch_merge_exchange(PeerExchange* pe, const void* d_partial, int parts, in
     if (!pe || !pe->connected || nq > pe->nq_cap) { set_error("merge-exchange: peer buffers not connected or nq > capacity"); return -1; }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pe->device);
-    const int grid = std::max(1, std::min((nq + 7) / 8, 4 * sms));          // a warp per query; resident for sure: 256 threads, a few registers
-    merge_exchange_kernel<<<grid, 256, 0, s>>>((const int4*)d_partial, parts, nq, pe->rank, pe->layout, pe->peers, pe->epoch + 1, pe->d_counter,
-                                              pe->d_error, 5ull * 1000 * 1000 * 1000, (int4*)d_out, d_bound, n_bound, bound_is_shared ? 1 : 0);
+    // ORBCUDA_MEX=0: the warp-per-query grid (up to 4 blocks per SM), 1 (default): the small thread-per-query grid (see its header)
+    static const int small = [] { const char* e = getenv("ORBCUDA_MEX"); return e ? atoi(e) : 1; }();
+    if (small) {
+        const int grid = std::max(1, std::min((nq + 127) / 128, sms / 4));
+        merge_exchange_small_kernel<<<grid, 128, 0, s>>>((const int4*)d_partial, parts, nq, pe->rank, pe->layout, pe->peers, pe->epoch + 1,
+                                                        pe->d_counter, pe->d_error, 5ull * 1000 * 1000 * 1000, (int4*)d_out, d_bound, n_bound,
+                                                        bound_is_shared ? 1 : 0);
+    } else {
+        const int grid = std::max(1, std::min((nq + 7) / 8, 4 * sms));      // a warp per query; resident for sure: 256 threads, a few registers
+        merge_exchange_kernel<<<grid, 256, 0, s>>>((const int4*)d_partial, parts, nq, pe->rank, pe->layout, pe->peers, pe->epoch + 1, pe->d_counter,
+                                                  pe->d_error, 5ull * 1000 * 1000 * 1000, (int4*)d_out, d_bound, n_bound, bound_is_shared ? 1 : 0);
+    }
     if (cudaPeekAtLastError() != cudaSuccess) return -1;      // the epoch advances only with a launch that went out: ranks stay in step
     pe->epoch++;
     return 1;

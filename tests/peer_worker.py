@@ -77,7 +77,24 @@ def main():
     assert peer.error() == 0
     assert int(bad.item()) == 0, ("back-to-back alternating searches", rank, int(bad.item()))
     checked += 300
+    # ---- two searches in flight: two streams, each with its own peer buffers -- the exchange of one search runs next to the
+    # search kernel of the other (the small merge-exchange grid must make progress there) and the results stay those of one search
+    peer2 = orb.PeerExchange(5000, rank, world, local, gather_bytes)
+    side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    for st in side:
+        st.wait_stream(cur)
+    bads = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
+    for it in range(200):
+        k = it & 1
+        (peer, peer2)[k].knn2(d_qs[k].data_ptr(), nq, d_shard.data_ptr(), hi - lo, lo, outs[k].data_ptr(), 5, side[k].cuda_stream)
+        with torch.cuda.stream(side[k]):
+            bads[k] += (outs[k] != fulls[k]).sum()
+    torch.cuda.synchronize()
+    assert peer.error() == 0 and peer2.error() == 0
+    assert int(bads[0].item()) == 0 and int(bads[1].item()) == 0, ("two searches in flight", rank)
+    checked += 200
     dist.barrier()
+    peer2.close()
     peer.close()
     # ---- the key-frame message: every rank packs its own key frames, one fused exchange, every rank unpacks everybody's
     B, cap = 10, 1027
