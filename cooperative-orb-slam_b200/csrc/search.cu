@@ -151,10 +151,19 @@ __global__ void __launch_bounds__(128) distinctive_kernel(const uint4* __restric
 
 struct StereoOut { float u_right, depth; int sad; int ok; };
 
-// One warp per left key point (Frame::ComputeStereoMatches :504-628).  blockIdx.y = stereo pair of a batch: the
-// key point / descriptor arrays advance by `cap` entries per pair, the pyramids by one frame block, and the per-pair
-// counts come from cntL / cntR (device arrays; nullptr for the single-pair call, which passes nl / nr).
-__global__ void __launch_bounds__(128) stereo_kernel(const orb_keypoint_t* __restrict__ kl, const uint4* __restrict__ dl, int nl,
+// Frame::ComputeStereoMatches :504-628.  A CTA of 8 warps takes 32 left key points of one stereo pair (blockIdx.y = pair of a
+// batch: the key point / descriptor arrays advance by `cap` entries per pair, the pyramids by one frame block, the per-pair
+// counts come from cntL / cntR -- device arrays; nullptr for the single-pair call, which passes nl / nr).
+//   * the right key points are reduced ONCE per CTA to what the candidate test needs -- x, the row band [minr, maxr] of
+//     vRowIndices (:481-498) clamped to rows >= 0, the octave: 11 bytes each in shared memory, sorted by row bin -- instead of
+//     every warp re-reading all 28-byte key points and redoing ceilf/floorf for each of its left key points (2.6 GB of L1/L2
+//     reads per 64 pairs);
+//   * a warp scans the bins around its row 32 entries at a time for each of its 4 left key points, collects the candidates
+//     with a ballot, then computes their Hamming distances a candidate per lane (all descriptor loads in flight);
+//   * the 11 x 11 left window and the 11 x 21 right strip of the SAD search (:548-598) are staged in shared memory once (12
+//     byte loads per lane instead of 83), the 11 x 11 (shift, window row) sums are spread over the lanes.
+constexpr int kStWarps = 8, kStPerWarp = 4, kStLeftPerCta = kStWarps * kStPerWarp, kStChunk = 2048, kStCand = 64, kStBins = 128;
+__global__ void __launch_bounds__(kStWarps * 32) stereo_kernel(const orb_keypoint_t* __restrict__ kl, const uint4* __restrict__ dl, int nl,
                                                      const orb_keypoint_t* __restrict__ kr, const uint4* __restrict__ dr, int nr,
                                                      const int32_t* __restrict__ cntL, const int32_t* __restrict__ cntR, int cap,
                                                      const float* __restrict__ sfs, const float* __restrict__ isfs,
@@ -163,137 +172,275 @@ __global__ void __launch_bounds__(128) stereo_kernel(const orb_keypoint_t* __res
                                                      size_t l0_strideL, size_t l0_strideR,
                                                      const LevelGeom* __restrict__ geom, int n_rows, float mbf, float max_d,
                                                      StereoOut* __restrict__ out) {
-    const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    __shared__ float s_x[kStChunk];
+    __shared__ unsigned s_rows[kStChunk];                 // minr | (maxr + 1) << 16, both clamped to [0, 65535]
+    __shared__ uint8_t s_oct[kStChunk];
+    __shared__ unsigned short s_idx[kStChunk];           // position in the chunk of the key point staged in slot i
+    __shared__ int s_hist[kStBins], s_start[kStBins], s_w;
+    __shared__ int s_cand[kStWarps][kStCand];
+    __shared__ int s_part[kStWarps][128];
+    __shared__ uint8_t s_winL[kStWarps][128], s_winR[kStWarps][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {
         const size_t f = blockIdx.y;
         if (cntL) { nl = min(cntL[f], cap); nr = min(cntR[f], cap); }
         kl += f * cap; dl += 2 * f * cap; kr += f * cap; dr += 2 * f * cap; out += f * cap;
         pyrL += f * pyr_stride; pyrR += f * pyr_stride; l0L += f * l0_strideL; l0R += f * l0_strideR;
     }
-    if (iL >= nl) return;
-    StereoOut o = {-1.f, -1.f, 0, 0};
-    const orb_keypoint_t kpL = kl[iL];
-    const int levelL = kpL.octave;
-    const float vL = kpL.y, uL = kpL.x;
-    const int row = (int)vL;
-    const float minU = __fsub_rn(uL, max_d), maxU = uL;
-    bool alive = row >= 0 && row < n_rows && !(maxU < 0);
-    unsigned best = 0xffffffffu;
-    if (alive) {
-        const uint4 a0 = dl[2 * (size_t)iL], a1 = dl[2 * (size_t)iL + 1];
-        for (int iR = lane; iR < nr; iR += 32) {
-            const orb_keypoint_t kpR = kr[iR];
-            // membership of iR in vRowIndices[row] (:481-498)
-            const float r = __fmul_rn(2.0f, sfs[kpR.octave]);
-            const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
-            if (row < minr || row > maxr) continue;
-            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
-            if (!(kpR.x >= minU && kpR.x <= maxU)) continue;
-            const int d = hamming256(a0, a1, dr + 2 * (size_t)iR);
-            if (d < TH_HIGH) best = min(best, ((unsigned)d << 20) | (unsigned)iR);   // first strict minimum
-        }
-        best = warp_min(best);
-        alive = best != 0xffffffffu && (int)(best >> 20) < (TH_HIGH + TH_LOW) / 2;
-    }
-    if (alive) {
-        const int bestIdxR = (int)(best & 0xfffff);
-        const float uR0 = kr[bestIdxR].x;
-        const float scaleFactor = isfs[levelL];
-        const int cu = (int)roundf(__fmul_rn(kpL.x, scaleFactor));
-        const int cv = (int)roundf(__fmul_rn(kpL.y, scaleFactor));
-        const int cr0 = (int)roundf(__fmul_rn(uR0, scaleFactor));
-        const LevelGeom g = geom[levelL];
-        const int w = 5, L = 5;
-        if (!(cr0 < 0 || cr0 + L + w + 1 >= g.w)) {   // iniu < 0 || endu >= cols  (:579-582)
-            // level 0 is the input image itself, levels >= 1 live in the padded pyramid planes
-            const int pitch = levelL ? g.pitch : l0_pitch;
-            const uint8_t* PL = levelL ? pyrL + g.plane_off + (size_t)kEdge * g.pitch + kXPad : l0L;
-            const uint8_t* PR = levelL ? pyrR + g.plane_off + (size_t)kEdge * g.pitch + kXPad : l0R;
-            const int cL = PL[(ptrdiff_t)cv * pitch + cu];
-            int sads[11];
+    const int base = blockIdx.x * kStLeftPerCta;
+    if (base >= nl) return;
+    // ---- my four left key points
+    int iLs[kStPerWarp], rowv[kStPerWarp], lev[kStPerWarp];
+    float minUs[kStPerWarp], maxUs[kStPerWarp];
+    bool alive[kStPerWarp];
+    unsigned best[kStPerWarp];
 #pragma unroll
-            for (int s = 0; s < 11; s++) {
-                const int incR = s - L;
-                const int cR = PR[(ptrdiff_t)cv * pitch + cr0 + incR];
-                int acc = 0;
-                for (int t = lane; t < 121; t += 32) {
-                    const int dy = t / 11 - w, dx = t % 11 - w;
-                    const int a = (int)PL[(ptrdiff_t)(cv + dy) * pitch + cu + dx] - cL;
-                    const int b = (int)PR[(ptrdiff_t)(cv + dy) * pitch + cr0 + incR + dx] - cR;
-                    acc += abs(a - b);
+    for (int j = 0; j < kStPerWarp; j++) {
+        const int iL = base + j * kStWarps + warp;
+        iLs[j] = iL; best[j] = 0xffffffffu; alive[j] = false; rowv[j] = 0; lev[j] = 0; minUs[j] = 0.f; maxUs[j] = 0.f;
+        if (iL < nl) {
+            const orb_keypoint_t kpL = kl[iL];
+            rowv[j] = (int)kpL.y; lev[j] = kpL.octave;
+            minUs[j] = __fsub_rn(kpL.x, max_d); maxUs[j] = kpL.x;
+            alive[j] = rowv[j] >= 0 && rowv[j] < n_rows && !(maxUs[j] < 0);
+        }
+    }
+    // ---- candidate search over the right key points, kStChunk at a time.  Staging sorts them by the first row of their band
+    // (a counting sort over bins of `h` rows): iR is a candidate of `row` only if minr lies in (row - W, row], W = the widest
+    // band staged, so a left key point scans the few bins that cover those rows -- ~7 % of the right key points -- and applies
+    // the exact test there.  The order inside a bin is arbitrary: the winner is the least (distance, iR) key whatever the order.
+    const int h = max(8, (n_rows + kStBins - 1) / kStBins);
+    auto reduce_kp = [&](const orb_keypoint_t& kpR, unsigned& rw) {
+        // membership of iR in vRowIndices[row] (:481-498): minr <= row <= maxr; row >= 0, so the clamps change nothing
+        const float r = __fmul_rn(2.0f, sfs[kpR.octave]);
+        const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
+        const int lo = min(max(minr, 0), 65535), hi = min(max(maxr + 1, 0), 65535);
+        rw = (unsigned)lo | ((unsigned)hi << 16);
+        return min(lo, n_rows - 1) / h;
+    };
+    for (int c0 = 0; c0 < nr; c0 += kStChunk) {
+        const int nc = min(kStChunk, nr - c0);
+        if (c0) __syncthreads();
+        for (int i = threadIdx.x; i < kStBins; i += blockDim.x) s_hist[i] = 0;
+        if (threadIdx.x == 0) s_w = 0;
+        __syncthreads();
+        int wmax = 0;
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+            unsigned rw;
+            const int bin = reduce_kp(kr[c0 + i], rw);
+            atomicAdd(&s_hist[bin], 1);
+            wmax = max(wmax, (int)(rw >> 16) - (int)(rw & 0xffffu));
+        }
+        wmax = __reduce_max_sync(0xffffffffu, wmax);
+        if (lane == 0 && wmax > 0) atomicMax(&s_w, wmax);
+        __syncthreads();
+        if (warp == 0) {                                 // exclusive prefix of the bin counts -> first slot of every bin
+            constexpr int kPer = kStBins / 32;
+            int c[kPer], sum = 0;
+#pragma unroll
+            for (int k = 0; k < kPer; k++) { c[k] = s_hist[lane * kPer + k]; sum += c[k]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int at = incl - sum;
+#pragma unroll
+            for (int k = 0; k < kPer; k++) { s_start[lane * kPer + k] = at; s_hist[lane * kPer + k] = at; at += c[k]; }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+            const orb_keypoint_t kpR = kr[c0 + i];
+            unsigned rw;
+            const int bin = reduce_kp(kpR, rw);
+            const int at = atomicAdd(&s_hist[bin], 1);   // afterwards s_hist[b] = end of bin b
+            s_x[at] = kpR.x; s_rows[at] = rw; s_oct[at] = (uint8_t)min(max(kpR.octave, 0), 255); s_idx[at] = (unsigned short)i;
+        }
+        __syncthreads();
+        const int W = max(s_w, 1);
+#pragma unroll
+        for (int j = 0; j < kStPerWarp; j++) {
+            if (!alive[j]) continue;                     // warp-uniform
+            const int row = rowv[j], lo_oct = lev[j] - 1, hi_oct = lev[j] + 1;
+            const float minU = minUs[j], maxU = maxUs[j];
+            const uint4 a0 = dl[2 * (size_t)iLs[j]], a1 = dl[2 * (size_t)iLs[j] + 1];
+            unsigned b = best[j];
+            int count = 0;
+            const int i_begin = s_start[max(row - W + 1, 0) / h], i_end = s_hist[row / h];
+            for (int i0 = i_begin; i0 < i_end; i0 += 32) {
+                const int i = i0 + lane;
+                bool cand = false;
+                if (i < i_end) {
+                    const unsigned rw = s_rows[i];
+                    const int oc = s_oct[i];
+                    const float x = s_x[i];
+                    cand = row >= (int)(rw & 0xffffu) && row < (int)(rw >> 16) && oc >= lo_oct && oc <= hi_oct && x >= minU && x <= maxU;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (m) {
+                    const int pos = count + __popc(m & ((1u << lane) - 1u));
+                    if (cand) {
+                        const int iR = c0 + s_idx[i];
+                        if (pos < kStCand) s_cand[warp][pos] = iR;
+                        else {                            // more candidates than the list holds (crowded rows): compare here
+                            const int d = hamming256(a0, a1, dr + 2 * (size_t)iR);
+                            if (d < TH_HIGH) b = min(b, ((unsigned)d << 20) | (unsigned)iR);
+                        }
+                    }
+                    count += __popc(m);
+                }
+            }
+            __syncwarp();
+            for (int c = lane; c < min(count, kStCand); c += 32) {
+                const int iR = s_cand[warp][c];
+                const int d = hamming256(a0, a1, dr + 2 * (size_t)iR);
+                if (d < TH_HIGH) b = min(b, ((unsigned)d << 20) | (unsigned)iR);   // first strict minimum: least (distance, iR)
+            }
+            __syncwarp();
+            best[j] = b;
+        }
+    }
+    // ---- sub-pixel refinement by SAD of each surviving key point (:548-628)
+#pragma unroll
+    for (int j = 0; j < kStPerWarp; j++) {
+        if (iLs[j] >= nl) continue;
+        StereoOut o = {-1.f, -1.f, 0, 0};
+        const unsigned bw = warp_min(best[j]);
+        if (alive[j] && bw != 0xffffffffu && (int)(bw >> 20) < (TH_HIGH + TH_LOW) / 2) {
+            const orb_keypoint_t kpL = kl[iLs[j]];
+            const int levelL = kpL.octave;
+            const float uL = kpL.x;
+            const int bestIdxR = (int)(bw & 0xfffff);
+            const float uR0 = kr[bestIdxR].x;
+            const float scaleFactor = isfs[levelL];
+            const int cu = (int)roundf(__fmul_rn(kpL.x, scaleFactor));
+            const int cv = (int)roundf(__fmul_rn(kpL.y, scaleFactor));
+            const int cr0 = (int)roundf(__fmul_rn(uR0, scaleFactor));
+            const LevelGeom g = geom[levelL];
+            const int w = 5, L = 5;
+            if (!(cr0 < 0 || cr0 + L + w + 1 >= g.w)) {   // iniu < 0 || endu >= cols  (:579-582)
+                // level 0 is the input image itself, levels >= 1 live in the padded pyramid planes
+                const int pitch = levelL ? g.pitch : l0_pitch;
+                const uint8_t* PL = levelL ? pyrL + g.plane_off + (size_t)kEdge * g.pitch + kXPad : l0L;
+                const uint8_t* PR = levelL ? pyrR + g.plane_off + (size_t)kEdge * g.pitch + kXPad : l0R;
+                PL += (ptrdiff_t)(cv - w) * pitch + (cu - w);
+                PR += (ptrdiff_t)(cv - w) * pitch + (cr0 - L - w);
+                uint8_t* wl = s_winL[warp];
+                uint8_t* wr = s_winR[warp];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int t = lane + 32 * k;
+                    if (t < 121) { const int dy = t / 11, dx = t - 11 * dy; wl[t] = PL[(ptrdiff_t)dy * pitch + dx]; }
                 }
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                sads[s] = acc;
-            }
-            int bestSad = 0x7fffffff, bestinc = 0;
+                for (int k = 0; k < 8; k++) {
+                    const int t = lane + 32 * k;
+                    if (t < 231) { const int dy = t / 21, dx = t - 21 * dy; wr[t] = PR[(ptrdiff_t)dy * pitch + dx]; }
+                }
+                __syncwarp();
+                const int cL = wl[5 * 11 + 5];
 #pragma unroll
-            for (int s = 0; s < 11; s++)
-                if (sads[s] < bestSad) { bestSad = sads[s]; bestinc = s - L; }
-            if (bestinc != -L && bestinc != L) {
-                float d1 = 0, d2 = 0, d3 = 0;
+                for (int k = 0; k < 4; k++) {
+                    const int t = lane + 32 * k;          // t = shift * 11 + window row
+                    if (t < 121) {
+                        const int sft = t / 11, dy = t - 11 * sft;
+                        const int c = cL - (int)wr[5 * 21 + sft + 5];
+                        const uint8_t* a = wl + dy * 11;
+                        const uint8_t* bb = wr + dy * 21 + sft;
+                        int acc = 0;
 #pragma unroll
-                for (int s = 1; s < 10; s++)
-                    if (s - L == bestinc) { d1 = (float)sads[s - 1]; d2 = (float)sads[s]; d3 = (float)sads[s + 1]; }
-                const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
-                if (!(deltaR < -1 || deltaR > 1)) {
-                    float bestuR = __fmul_rn(sfs[levelL], __fadd_rn(__fadd_rn((float)cr0, (float)bestinc), deltaR));
-                    float disparity = __fsub_rn(uL, bestuR);
-                    if (disparity >= 0 && disparity < max_d) {
-                        if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
-                        o.depth = __fdiv_rn(mbf, disparity);
-                        o.u_right = bestuR;
-                        o.sad = bestSad;
-                        o.ok = 1;
+                        for (int i = 0; i < 11; i++) acc += abs((int)a[i] - (int)bb[i] - c);
+                        s_part[warp][t] = acc;
                     }
                 }
+                __syncwarp();
+                int sad = 0;
+                if (lane < 11) {
+#pragma unroll
+                    for (int i = 0; i < 11; i++) sad += s_part[warp][lane * 11 + i];
+                }
+                const unsigned key = lane < 11 ? ((unsigned)sad << 4) | (unsigned)lane : 0xffffffffu;
+                const unsigned bk = warp_min(key);        // least SAD, first shift on ties (:590-594)
+                const int bestSad = (int)(bk >> 4), bs = (int)(bk & 15u), bestinc = bs - L;
+                const float d1 = (float)__shfl_sync(0xffffffffu, sad, max(bs - 1, 0));
+                const float d3 = (float)__shfl_sync(0xffffffffu, sad, min(bs + 1, 10));
+                const float d2 = (float)bestSad;
+                if (bestinc != -L && bestinc != L) {
+                    const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+                    if (!(deltaR < -1 || deltaR > 1)) {
+                        float bestuR = __fmul_rn(sfs[levelL], __fadd_rn(__fadd_rn((float)cr0, (float)bestinc), deltaR));
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= 0 && disparity < max_d) {
+                            if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                            o.depth = __fdiv_rn(mbf, disparity);
+                            o.u_right = bestuR;
+                            o.sad = bestSad;
+                            o.ok = 1;
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
+        if (lane == 0) out[iLs[j]] = o;
     }
-    if (lane == 0) out[iL] = o;
 }
 
 
 // Outlier cut of Frame::ComputeStereoMatches (:630-644) for a batch, one CTA per stereo pair: the median is the
 // element of rank size/2 of the (SAD, index)-sorted list of accepted matches, every match with SAD >= 1.5*1.4*median
-// is dropped (the reference walks the sorted list from the back and stops at the first SAD below the limit).  The rank
-// is found by counting (n <= a few thousand).  Writes mvuRight / mvDepth (-1 where no match) and the kept count.
+// is dropped (the reference walks the sorted list from the back and stops at the first SAD below the limit).  Only the
+// SAD VALUE of that rank matters: it is the largest v with count(SAD < v) <= rank, found bit by bit (a SAD is at most
+// 121 * 510 < 2^16) -- 16 counting rounds over the pair's results instead of a rank count per element (n^2 loads).
+// Writes mvuRight / mvDepth (-1 where no match) and the kept count.
 __global__ void __launch_bounds__(256) stereo_filter_kernel(const StereoOut* __restrict__ res, const int32_t* __restrict__ cntL, int cap,
                                                             float* __restrict__ u_right, float* __restrict__ depth,
                                                             int32_t* __restrict__ n_matches) {
+    constexpr int kKeep = 4096;
     const size_t f = blockIdx.x;
     res += f * cap; u_right += f * cap; depth += f * cap;
     const int n = min(cntL[f], cap);
-    __shared__ int s_ok, s_median, s_kept;
-    if (threadIdx.x == 0) { s_ok = 0; s_median = -1; s_kept = 0; }
+    __shared__ int s_sad[kKeep];                         // SAD of the accepted matches, 0x7fffffff otherwise
+    __shared__ int s_cnt[18], s_kept;
+    if (threadIdx.x < 18) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_kept = 0;
     __syncthreads();
+    auto sad_of = [&](int i) { return i < kKeep ? s_sad[i] : (res[i].ok ? res[i].sad : 0x7fffffff); };
     int mine = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mine += res[i].ok;
-    if (mine) atomicAdd(&s_ok, mine);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const StereoOut o = res[i];
+        if (i < kKeep) s_sad[i] = o.ok ? o.sad : 0x7fffffff;
+        mine += o.ok;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt[16], mine);
     __syncthreads();
-    const int n_ok = s_ok;
+    const int n_ok = s_cnt[16];
+    int median = -1;
     if (n_ok > 0) {
         const int k = n_ok / 2;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            if (!res[i].ok) continue;
-            const int si = res[i].sad;
-            int rank = 0;
-            for (int j = 0; j < n; j++) {
-                const StereoOut o = res[j];
-                rank += o.ok && (o.sad < si || (o.sad == si && j < i));
-            }
-            if (rank == k) s_median = si;
+        int v = 0;
+        for (int bit = 15; bit >= 0; bit--) {
+            const int t = v | (1 << bit);
+            int below = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) below += sad_of(i) < t;
+            below = __reduce_add_sync(0xffffffffu, below);
+            if ((threadIdx.x & 31) == 0 && below) atomicAdd(&s_cnt[bit], below);
+            __syncthreads();
+            if (s_cnt[bit] <= k) v = t;
         }
+        median = v;
     }
-    __syncthreads();
-    const float th_dist = 1.5f * 1.4f * (float)s_median;
+    const float th_dist = 1.5f * 1.4f * (float)median;
     int kept = 0;
     for (int i = threadIdx.x; i < cap; i += blockDim.x) {
         float u = -1.f, d = -1.f;
-        if (i < n && res[i].ok && (float)res[i].sad < th_dist) { u = res[i].u_right; d = res[i].depth; kept++; }
+        if (i < n) {
+            const StereoOut o = res[i];
+            if (o.ok && (float)o.sad < th_dist) { u = o.u_right; d = o.depth; kept++; }
+        }
         u_right[i] = u; depth[i] = d;
     }
-    if (kept) atomicAdd(&s_kept, kept);
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&s_kept, kept);
     __syncthreads();
     if (threadIdx.x == 0) n_matches[f] = s_kept;
 }
@@ -540,7 +687,7 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
         set_error("orbm_stereo_matches: the two extractors must have processed same-size images on one device");
         return ORB_ERR_ARG;
     }
-    if (n_right >= (1 << 20)) return ORB_ERR_ARG;
+    if (n_right >= (1 << 20) || hgl[0].h > 65535) return ORB_ERR_ARG;     // index / row-band packing of stereo_kernel
     std::vector<StereoOut> res(n_left);
     {
         const float max_d = mbf / mb;   // maxD = mbf/minZ, minZ = mb  (:501-503)
@@ -555,7 +702,7 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
         const float* d_isf = (const float*)cx.upload(isf, (size_t)fll.nlevels * 4);
         StereoOut* d_out = (StereoOut*)cx.dalloc((size_t)n_left * sizeof(StereoOut));
         if (!d_kl || !d_dl || !d_kr || !d_dr || !d_sf || !d_isf || !d_out) return ORB_ERR_CUDA;
-        stereo_kernel<<<(n_left * 32 + 127) / 128, 128, 0, cx.stream>>>(d_kl, d_dl, n_left, d_kr, d_dr, n_right, nullptr, nullptr, 0, d_sf, d_isf,
+        stereo_kernel<<<(n_left + kStLeftPerCta - 1) / kStLeftPerCta, kStWarps * 32, 0, cx.stream>>>(d_kl, d_dl, n_left, d_kr, d_dr, n_right, nullptr, nullptr, 0, d_sf, d_isf,
                                                                       pl, pr, 0, l0l, l0r, l0pl, 0, 0, dgl, hgl[0].h, mbf, max_d, d_out);
         ORB_CUDA_TRY(cudaGetLastError());
         if (!cx.download(res.data(), d_out, (size_t)n_left * sizeof(StereoOut)) || !cx.finish()) return ORB_ERR_CUDA;
@@ -591,7 +738,7 @@ int orbm_stereo_matches_batch_device(orbx_handle_t hl, orbx_handle_t hr, const v
     if (orbx_internal_view_batch(hl, &pl, &dgl, &hgl, &fll, &devl, &d_sfl, &l0l, &l0pl, &l0sl, &nfl, stream) ||
         orbx_internal_view_batch(hr, &pr, &dgr, &hgr, &flr, &devr, &d_sfr, &l0r, &l0pr, &l0sr, &nfr, stream) ||
         !pl || !pr || !l0l || !l0r || l0pl != l0pr || devl != devr || fll.width != flr.width || fll.height != flr.height ||
-        fll.nlevels != flr.nlevels || nfl < n_pairs || nfr < n_pairs) {
+        fll.nlevels != flr.nlevels || nfl < n_pairs || nfr < n_pairs || hgl[0].h > 65535) {
         set_error("orbm_stereo_matches_batch_device: the two extractors must hold a batch of >= n_pairs same-size images on one device");
         return ORB_ERR_ARG;
     }
@@ -599,7 +746,7 @@ int orbm_stereo_matches_batch_device(orbx_handle_t hl, orbx_handle_t hr, const v
     cudaStream_t s = (cudaStream_t)stream;
     StereoOut* d_res = (StereoOut*)d_scratch;
     const float max_d = mbf / mb;   // maxD = mbf/minZ, minZ = mb  (:501-503)
-    stereo_kernel<<<dim3((cap * 32 + 127) / 128, n_pairs), 128, 0, s>>>(
+    stereo_kernel<<<dim3((cap + kStLeftPerCta - 1) / kStLeftPerCta, n_pairs), kStWarps * 32, 0, s>>>(
         (const orb_keypoint_t*)d_keys_left, (const uint4*)d_desc_left, 0, (const orb_keypoint_t*)d_keys_right, (const uint4*)d_desc_right, 0,
         d_counts_left, d_counts_right, cap, d_sfl, d_sfl + kMaxLevels, pl, pr, (size_t)fll.pyr_bytes, l0l, l0r, l0pl, l0sl, l0sr, dgl, hgl[0].h,
         mbf, max_d, d_res);
