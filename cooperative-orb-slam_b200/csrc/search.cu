@@ -163,7 +163,7 @@ struct StereoOut { float u_right, depth; int sad; int ok; };
 //   * the 11 x 11 left window and the 11 x 21 right strip of the SAD search (:548-598) are staged in shared memory once (12
 //     byte loads per lane instead of 83), the 11 x 11 (shift, window row) sums are spread over the lanes.
 constexpr int kStWarps = 8, kStPerWarp = 4, kStLeftPerCta = kStWarps * kStPerWarp, kStChunk = 2048, kStCand = 64, kStBins = 128;
-__global__ void __launch_bounds__(kStWarps * 32) stereo_kernel(const orb_keypoint_t* __restrict__ kl, const uint4* __restrict__ dl, int nl,
+__global__ void __launch_bounds__(kStWarps * 32, 4) stereo_kernel(const orb_keypoint_t* __restrict__ kl, const uint4* __restrict__ dl, int nl,
                                                      const orb_keypoint_t* __restrict__ kr, const uint4* __restrict__ dr, int nr,
                                                      const int32_t* __restrict__ cntL, const int32_t* __restrict__ cntR, int cap,
                                                      const float* __restrict__ sfs, const float* __restrict__ isfs,
@@ -325,15 +325,13 @@ __global__ void __launch_bounds__(kStWarps * 32) stereo_kernel(const orb_keypoin
                 PR += (ptrdiff_t)(cv - w) * pitch + (cr0 - L - w);
                 uint8_t* wl = s_winL[warp];
                 uint8_t* wr = s_winR[warp];
+                {   // lanes 0..20 copy a column of the right strip each, lanes 21..31 a column of the left window
+                    const bool right = lane < 21;
+                    const uint8_t* src = right ? PR + lane : PL + (lane - 21);
+                    uint8_t* dst = right ? wr + lane : wl + (lane - 21);
+                    const int dstride = right ? 21 : 11;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int t = lane + 32 * k;
-                    if (t < 121) { const int dy = t / 11, dx = t - 11 * dy; wl[t] = PL[(ptrdiff_t)dy * pitch + dx]; }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int t = lane + 32 * k;
-                    if (t < 231) { const int dy = t / 21, dx = t - 21 * dy; wr[t] = PR[(ptrdiff_t)dy * pitch + dx]; }
+                    for (int dy = 0; dy < 11; dy++) dst[dy * dstride] = src[(ptrdiff_t)dy * pitch];
                 }
                 __syncwarp();
                 const int cL = wl[5 * 11 + 5];
