@@ -162,8 +162,8 @@ struct StereoOut { float u_right, depth; int sad; int ok; };
 //     with a ballot, then computes their Hamming distances a candidate per lane (all descriptor loads in flight);
 //   * the 11 x 11 left window and the 11 x 21 right strip of the SAD search (:548-598) are staged in shared memory once (12
 //     byte loads per lane instead of 83), the 11 x 11 (shift, window row) sums are spread over the lanes.
-constexpr int kStWarps = 8, kStPerWarp = 4, kStLeftPerCta = kStWarps * kStPerWarp, kStChunk = 2048, kStCand = 64, kStBins = 128;
-__global__ void __launch_bounds__(kStWarps * 32, 4) stereo_kernel(const orb_keypoint_t* __restrict__ kl, const uint4* __restrict__ dl, int nl,
+constexpr int kStWarps = 16, kStPerWarp = 4, kStLeftPerCta = kStWarps * kStPerWarp, kStChunk = 2048, kStCand = 64, kStBins = 128;
+__global__ void __launch_bounds__(kStWarps * 32, 2) stereo_kernel(const orb_keypoint_t* __restrict__ kl, const uint4* __restrict__ dl, int nl,
                                                      const orb_keypoint_t* __restrict__ kr, const uint4* __restrict__ dr, int nr,
                                                      const int32_t* __restrict__ cntL, const int32_t* __restrict__ cntR, int cap,
                                                      const float* __restrict__ sfs, const float* __restrict__ isfs,
