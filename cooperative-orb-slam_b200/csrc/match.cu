@@ -991,6 +991,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t targe
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
 }
 
+template <bool kShareBound>      // true: the sharded search of several ranks that forward their pruning bounds to each other (bp)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ m, long long nm, long long per_split,
                  long long index_base, int4* __restrict__ partial, int* __restrict__ shared_d2, BoundPeers bp) {
@@ -1152,10 +1153,10 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
         // thread per query of the rank (split 0, first column half) forwards the rank's bound -- the minimum over all its CTAs,
         // read from the local array -- to the peers' arrays at tiles 1, 2, 4, 8, ... and only when it fell: ~10^5 fire-and-forget
         // minima per search.  It is a bound on the merged result whichever shard produced it.
-        const bool forwarder = bp.n > 0 && blockIdx.y == 0 && chalf == 0 && q0 + row < nq;
+        const bool forwarder = kShareBound && bp.n > 0 && blockIdx.y == 0 && chalf == 0 && q0 + row < nq;
         int last_fwd = 0x7f7f7f7f;
         auto forward_bound = [&](int i, int g) {
-            if (forwarder && (i & (i - 1)) == 0 && g < last_fwd) {
+            if (kShareBound && forwarder && (i & (i - 1)) == 0 && g < last_fwd) {
                 last_fwd = g;
                 // the element index goes through an opaque move so that the 15 remote addresses are formed here, in this rare
                 // path, instead of being hoisted into 30 registers that stay live across the whole tile loop
@@ -1335,7 +1336,10 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
     } else if (variant == 5) {
         const size_t smem = (size_t)kTcQ * 256 + kPairBStages * (size_t)kPairHalfN * 256 + 1024;
         static DeviceOnce once_configured5;
-        if (!once_configured5.run([&] { return cudaFuncSetAttribute(knn2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) return -1;
+        if (!once_configured5.run([&] {
+                return cudaFuncSetAttribute(knn2_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                       cudaFuncSetAttribute(knn2_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+            })) return -1;
         // sharded search over peer buffers: the bounds live in the peer buffer and every rank's kernel publishes into all of them
         // (ORBCUDA_SHARE_BOUND=0: each rank keeps its bounds to itself -- A/B switch, results are identical)
         static const bool share = [] { const char* e = getenv("ORBCUDA_SHARE_BOUND"); return e ? atoi(e) != 0 : true; }();
@@ -1347,8 +1351,12 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
                 if (r != peer->rank) bp.remote[bp.n++] = reinterpret_cast<int*>(peer->peers.base[r] + peer->layout.bound_offset());
             shared_bound = shared_d2;
         }
-        knn2_pair_kernel<<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
-                                                                        index_base, partial, shared_d2, bp);
+        if (bp.n > 0)
+            knn2_pair_kernel<true><<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
+                                                                                  index_base, partial, shared_d2, bp);
+        else
+            knn2_pair_kernel<false><<<dim3(qblocks, splits), kTcThreads, smem, s>>>((const uint32_t*)d_q, nq, (const uint32_t*)d_m, nm, per_split,
+                                                                                   index_base, partial, shared_d2, bp);
     } else if (variant == 4) {
         const size_t smem = kTcBStages * (size_t)kTcN * 256 + 1024;
         static DeviceOnce once_configured4;
