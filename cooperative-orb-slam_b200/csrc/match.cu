@@ -1000,10 +1000,12 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
     unsigned char* s_b = s_a + kTcQ * 256;                                               // kPairBStages x [64 rows][256 B]
     __shared__ __align__(8) unsigned long long s_full[kPairBStages], s_done[2], s_empty[2];
     __shared__ uint32_t s_tmem;
+    __shared__ int s_workers_done;          // kShareBound: worker warps of this CTA that have left their tile loop
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_cta_rank();
     const int q0 = blockIdx.x * kTcQ;
 
+    if (tid == 0) s_workers_done = 0;
     if (warp == kTcWorkers) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
@@ -1078,6 +1080,48 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
                 }
                 __syncwarp();
             }
+        } else if (kShareBound && bp.n > 0 && blockIdx.y == 0) {
+            // =========================== bound forwarder (the otherwise idle 17th warp of the second CTA) ===========================
+            // Sharded map: the other ranks prune with this rank's bounds too.  Publishing every improvement of every worker
+            // thread to every peer was measured SLOWER than not sharing (millions of 4-byte NVLink transactions per search), and
+            // a forwarding test inside the worker loop cost 3 % of the kernel.  This warp has nothing else to do: at ~1, 3, 7, 15,
+            // ... us into the search (the bounds fall fastest at the start) it reads the
+            // rank's bounds of the pair's 512 queries (the minimum over all the rank's CTAs, in the local array) and sends those
+            // that fell to every peer as fire-and-forget system-scope minima.  A bound of one shard is a bound on the merged result.
+            const int qb = (blockIdx.x & ~1) * kTcQ;
+            int last[2 * kTcQ / 32];
+#pragma unroll
+            for (int k = 0; k < 2 * kTcQ / 32; k++) last[k] = 0x7f7f7f7f;
+            // (the workers' "done" count is polled every ~0.1 us: __nanosleep(1000) was measured to hold the CTA -- and with it
+            // the kernel -- for ~6 us after the last worker had left)
+            unsigned long long t_next = 0, t_step = 1000;
+            {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                t_next = now + t_step;
+            }
+            while (true) {
+                __nanosleep(100);
+                if (*reinterpret_cast<volatile int*>(&s_workers_done) == kTcWorkers) break;
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now < t_next) continue;
+                t_step *= 2; t_next = now + t_step;      // forwarding passes ~1, 3, 7, 15, 31, ... us into the search
+#pragma unroll
+                for (int k = 0; k < 2 * kTcQ / 32; k++) {
+                    const int qi = qb + k * 32 + lane;
+                    if (qi < nq) {
+                        int g;
+                        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(g) : "l"(shared_d2 + qi) : "memory");
+                        if (g < last[k]) {
+                            last[k] = g;
+                            for (int p = 0; p < bp.n; p++)
+                                asm volatile("red.relaxed.sys.global.min.s32 [%0], %1;" :: "l"(bp.remote[p] + qi), "r"(g) : "memory");
+                        }
+                    }
+                }
+            }
+            __syncwarp();
         }
     } else {
         // =========================== worker warps (both CTAs) ===========================
@@ -1148,25 +1192,6 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             if (cnt >= kColsPerWarp) tc_drain64<true>(v, pa, ib, kColsPerWarp, glim, gptr, best);
             else if (cnt > 0) tc_drain64<false>(v, pa, ib, cnt, glim, gptr, best);
         };
-        // Sharded map: the other ranks prune with this rank's bounds too.  Publishing every improvement of every thread to
-        // every peer was measured SLOWER than not sharing (millions of 4-byte NVLink transactions per search).  Instead ONE
-        // thread per query of the rank (split 0, first column half) forwards the rank's bound -- the minimum over all its CTAs,
-        // read from the local array -- to the peers' arrays at tiles 1, 2, 4, 8, ... and only when it fell: ~10^5 fire-and-forget
-        // minima per search.  It is a bound on the merged result whichever shard produced it.
-        const bool forwarder = kShareBound && bp.n > 0 && blockIdx.y == 0 && chalf == 0 && q0 + row < nq;
-        int last_fwd = 0x7f7f7f7f;
-        auto forward_bound = [&](int i, int g) {
-            if (kShareBound && forwarder && (i & (i - 1)) == 0 && g < last_fwd) {
-                last_fwd = g;
-                // the element index goes through an opaque move so that the 15 remote addresses are formed here, in this rare
-                // path, instead of being hoisted into 30 registers that stay live across the whole tile loop
-                int qidx;
-                asm volatile("mov.s32 %0, %1;" : "=r"(qidx) : "r"(q0 + row));
-#pragma unroll
-                for (int p = 0; p < kMaxPeers - 1; p++)
-                    if (p < bp.n) asm volatile("red.relaxed.sys.global.min.s32 [%0], %1;" :: "l"(bp.remote[p] + qidx), "r"(g) : "memory");
-            }
-        };
         if (ntiles > 0) raw_a = fetch(0);
         if (ntiles > 1) raw_b = fetch(1);
         for (int i = 0; i < ntiles; i++) {
@@ -1191,7 +1216,6 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             // sharded map is ~50 tiles per CTA) would otherwise run a sixth of its tiles against "no bound yet"
             if ((i & kPairBoundEvery) == 0 || i < 8) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "+r"(gval) : "l"(gptr) : "memory");
             if (i >= kTcLag) drain_update(i - kTcLag, v, glim);
-            forward_bound(i, gval);
         }
         for (int t = max(0, ntiles - kTcLag); t < ntiles; t++) {
             uint32_t v[32];
@@ -1200,6 +1224,10 @@ knn2_pair_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restr
             int gnow;
             asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gnow) : "l"(gptr) : "memory");
             drain_update(t, v, pa - gnow - 1);
+        }
+        if (kShareBound) {
+            __syncwarp();
+            if (lane == 0) atomicAdd(&s_workers_done, 1);
         }
     }
     // ---- merge the column halves and store (per CTA, as K7c)
@@ -1342,7 +1370,11 @@ int launch_knn2(const uint8_t* d_q, int nq, const uint8_t* d_m, int64_t nm, int6
             })) return -1;
         // sharded search over peer buffers: the bounds live in the peer buffer and every rank's kernel publishes into all of them
         // (ORBCUDA_SHARE_BOUND=0: each rank keeps its bounds to itself -- A/B switch, results are identical)
-        static const bool share = [] { const char* e = getenv("ORBCUDA_SHARE_BOUND"); return e ? atoi(e) != 0 : true; }();
+        // OFF unless ORBCUDA_SHARE_BOUND=1: measured on 2 / 4 / 8 B200s (profiles/r2_shard_search_*.txt) a search with shared
+        // bounds takes ~5 us LONGER than one without (0.1107 vs 0.1059 ms at 4 GPUs, 0.0800 vs 0.0742 at 8), with one or two
+        // searches in flight; only the first form of it -- the forwarding test inside the worker loop, which cost the single-GPU
+        // kernel 3 % -- was ahead at 8 GPUs (0.0729 vs 0.0755).  Kept as a measured alternative; results are identical.
+        static const bool share = [] { const char* e = getenv("ORBCUDA_SHARE_BOUND"); return e ? atoi(e) > 0 : false; }();
         BoundPeers bp{};
         int* shared_d2 = bound;
         if (peer && peer->connected && peer->world > 1 && share && n_bound <= peer->layout.bound_ints()) {

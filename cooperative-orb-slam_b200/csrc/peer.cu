@@ -87,8 +87,12 @@ __global__ void __launch_bounds__(256) merge_exchange_kernel(const int4* __restr
         }
     }
     __syncthreads();
-    if (bound_is_shared)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bound; i += gridDim.x * blockDim.x) bound[i] = 0x7f7f7f7f;
+    // the bound array in MY peer buffer: other ranks may have published into it during this search whether or not my own
+    // search read it (the ranks decide per shard size) -- it goes back to "no bound yet" here in every case
+    {
+        int* pb = reinterpret_cast<int*>(peers.base[rank] + L.bound_offset());
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.bound_ints(); i += gridDim.x * blockDim.x) pb[i] = 0x7f7f7f7f;
+    }
     if (!s_ok) {
         // a peer did not arrive in time: the call's output is the "no match" record for every query, never stale data
         for (int q = gwarp; q < nq; q += nwarps) if (lane == 0) out[q] = make_int4(256, -1, 256, -1);
@@ -162,8 +166,10 @@ __global__ void __launch_bounds__(128) merge_exchange_small_kernel(const int4* _
         }
     }
     __syncthreads();
-    if (bound_is_shared)
-        for (int i = gtid; i < n_bound; i += gsize) bound[i] = 0x7f7f7f7f;
+    {   // the bound array in MY peer buffer (see merge_exchange_kernel)
+        int* pb = reinterpret_cast<int*>(peers.base[rank] + L.bound_offset());
+        for (int i = gtid; i < L.bound_ints(); i += gsize) pb[i] = 0x7f7f7f7f;
+    }
     if (!s_ok) {
         for (int q = gtid; q < nq; q += gsize) out[q] = make_int4(256, -1, 256, -1);
         return;

@@ -50,28 +50,35 @@ def main():
                 assert peer.error() == 0
                 assert bool((out == full).all().item()), (nq, nm, variant, rep, rank)
                 checked += 1
-    # ---- back-to-back searches with alternating query sets and UNEVEN shards (ranks finish at different times): the pruning bounds
-    # that the ranks publish into each other's buffers (csrc/match.cu forward_bound) must never survive into the next search --
-    # set A are near copies of map descriptors (bounds fall to a few bits), set B random ones (a leaked A bound would prune away
-    # B's true neighbours)
-    nm, nq = 150000, 2000
-    m = synth.descriptors(nm, seed=77)
+    # ---- back-to-back searches alternating between two query sets and two ways of cutting the map (ranks finish at different
+    # times): the pruning bounds that the ranks publish into each other's buffers (csrc/match.cu, the forwarder warp of the CTA
+    # pair kernel) must never survive into the next search -- set A are near copies of map descriptors (bounds fall to a few
+    # bits), set B random ones (a leaked A bound would prune away B's true neighbours).
+    # Search A: queries near map descriptors over the whole 400k map, rank 0 holding only 1/8 of it (its shard is small enough to
+    # publish bounds, the other ranks' shards are not: mixed decisions).  Search B: random queries over the first 150k descriptors,
+    # cut evenly (every rank publishes and prunes with the shared bounds).
+    nmA, nmB, nq = 400000, 150000, 2000
+    m = synth.descriptors(nmA, seed=77)
     qa, m, _ = synth.query_set(m, nq=nq, seed=78)
     qb = synth.descriptors(nq, seed=79)
     d_all = torch.from_numpy(np.ascontiguousarray(m).reshape(-1, 32)).to(dev)
-    tri = world * (world + 1) // 2
-    lo = nm * (rank * (rank + 1) // 2) // tri; hi = nm * ((rank + 1) * (rank + 2) // 2) // tri
-    d_shard = d_all[lo:hi].contiguous()
+    cutsA = [0] + [nmA // 8 + (nmA - nmA // 8) * r // (world - 1) for r in range(world)]
+    cutsB = [nmB * r // world for r in range(world + 1)]
+    spans = [(cutsA[rank], cutsA[rank + 1]), (cutsB[rank], cutsB[rank + 1])]
     d_qs = [torch.from_numpy(x).to(dev) for x in (qa, qb)]
     fulls = [torch.empty((nq, 4), dtype=torch.int32, device=dev) for _ in range(2)]
-    for d_q, full in zip(d_qs, fulls):
-        assert L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), nq, C.c_void_p(d_all.data_ptr()), nm, 0, C.c_void_p(full.data_ptr()), 0,
+    for d_q, full, n_map in zip(d_qs, fulls, (nmA, nmB)):
+        assert L.orbm_knn2_device(C.c_void_p(d_q.data_ptr()), nq, C.c_void_p(d_all.data_ptr()), n_map, 0, C.c_void_p(full.data_ptr()), 0,
                                   C.c_void_p(cur.cuda_stream)) == 0
+
+    def shard_ptr(k):
+        return d_all[spans[k][0]:].data_ptr(), spans[k][1] - spans[k][0], spans[k][0]
+
     outs = [torch.full((nq, 4), -9, dtype=torch.int32, device=dev) for _ in range(2)]
     bad = torch.zeros(1, dtype=torch.int64, device=dev)
     for it in range(300):
         k = it & 1
-        peer.knn2(d_qs[k].data_ptr(), nq, d_shard.data_ptr(), hi - lo, lo, outs[k].data_ptr(), 5, cur.cuda_stream)
+        peer.knn2(d_qs[k].data_ptr(), nq, *shard_ptr(k), outs[k].data_ptr(), 5, cur.cuda_stream)
         bad += (outs[k] != fulls[k]).sum()          # queued on the same stream: no host synchronisation between the searches
     torch.cuda.synchronize()
     assert peer.error() == 0
@@ -86,7 +93,7 @@ def main():
     bads = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2)]
     for it in range(200):
         k = it & 1
-        (peer, peer2)[k].knn2(d_qs[k].data_ptr(), nq, d_shard.data_ptr(), hi - lo, lo, outs[k].data_ptr(), 5, side[k].cuda_stream)
+        (peer, peer2)[k].knn2(d_qs[k].data_ptr(), nq, *shard_ptr(k), outs[k].data_ptr(), 5, side[k].cuda_stream)
         with torch.cuda.stream(side[k]):
             bads[k] += (outs[k] != fulls[k]).sum()
     torch.cuda.synchronize()
