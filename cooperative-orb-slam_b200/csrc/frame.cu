@@ -237,12 +237,18 @@ __global__ void area_fill_kernel(const orb_keypoint_t* __restrict__ kps, const i
 
 // ---------------------------------------------------------------- SearchByProjection: window searches
 // The reference walks the projected points in order; a feature taken by an earlier point is skipped by the later ones
-// (ORBmatcher.cc:82-84, :1404-1406, :1543-1544), so the result depends on the order.  One CTA reproduces it in rounds:
-// every unresolved point claims its candidate features (GetFeaturesInArea) with atomicMin(point index); a point whose
-// candidates are claimed by nobody earlier cannot be influenced by an unresolved point any more and is resolved exactly
-// as the sequential loop would resolve it.  Points resolved in one round have pairwise disjoint candidate sets, so
-// their writes do not race.  The lowest unresolved point is always resolvable: the loop ends after at most n rounds
-// (a handful in practice).
+// (ORBmatcher.cc:82-84, :1404-1406, :1543-1544), so the result depends on the order.  One CTA reproduces it in rounds.
+// In a round every unresolved point i walks its window ONCE over the features that are free at the start of the round and
+//   * finds its outcome as if it were its turn: best B and second best S (the two candidates the reference's best / second
+//     slots would end up holding) and whether the match is accepted;
+//   * claims, with atomicMin(point index), every candidate it could still TAKE later: free, within `threshold`.
+// The outcome of i depends on the identity of B and S only (removing any other candidate from the walk changes neither slot),
+// and an earlier unresolved point j can take a feature only if it claimed it.  So i is final as soon as neither B nor S
+// carries a claim of an earlier point; the decisions are applied after a barrier (no walk reads a feature state that a
+// decision of the same round has already changed).  Two points finalised in one round never take the same feature (the
+// later one would have seen the earlier one's claim on its B), the lowest unresolved point is always final, and crowded
+// scenes need as many rounds as points compete for ONE feature -- the earlier rule (a point waits while ANY of its
+// candidates is claimed by ANY earlier window) needed ~30 rounds and two walks per round on 4000 points over 2000 features.
 struct ProjWindow {
     float x, y, r;              // window centre and half size (already multiplied by the scale factor)
     int min_level, max_level;   // GetFeaturesInArea level filter
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
                                                              const ProjWindow* __restrict__ wins, const uint32_t* __restrict__ desc_p, int n_p,
                                                              float nnratio, int threshold, int* __restrict__ out_feature_point,
                                                              int* __restrict__ out_point_feature, uint8_t* __restrict__ resolved,
-                                                             int* __restrict__ out_nmatches) {
+                                                             int2* __restrict__ tentative, int* __restrict__ out_nmatches) {
     extern __shared__ int s_dyn[];
     int* s_claim = s_dyn;                                             // [n_f]
     int* s_cell_idx = s_claim + n_f;                                  // [n_f]            (STAGED)
@@ -309,40 +315,38 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
         for (int i = tid; i < n_p; i += 1024) {
             if (resolved[i]) continue;
             const ProjWindow w = wins[i];
-            walk(w, [&](int idx) { atomicMin(&s_claim[idx], i); return true; });
-        }
-        __syncthreads();
-        for (int i = tid; i < n_p; i += 1024) {
-            if (resolved[i]) continue;
-            const ProjWindow w = wins[i];
-            // one walk: search as if the point were safe, give up as soon as a candidate belongs to an earlier one
-            bool safe = true;
-            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1, secondIdx = -1;
             const uint32_t* dp = desc_p + (size_t)i * 8;
             walk(w, [&](int idx) {
-                if (s_claim[idx] < i) { safe = false; return false; }
                 if (s_blocked[idx]) return true;
                 if ((w.flags & kWinStereo) && u_right[idx] > 0) {
                     const float er = fabsf(__fsub_rn(w.ur, u_right[idx]));
                     if (er > w.r) return true;
                 }
                 const int dist = hamming32(dp, desc_f + (size_t)idx * 8);
+                if (dist <= threshold) atomicMin(&s_claim[idx], i);       // a feature this point could take, now or later
                 if (dist < bestDist) {
-                    bestDist2 = bestDist; bestDist = dist;
-                    bestLevel2 = bestLevel; bestLevel = octave_of(idx);
-                    bestIdx = idx;
+                    bestDist2 = bestDist; bestLevel2 = bestLevel; secondIdx = bestIdx;
+                    bestDist = dist; bestLevel = octave_of(idx); bestIdx = idx;
                 } else if (RATIO && dist < bestDist2) {
-                    bestLevel2 = octave_of(idx);
-                    bestDist2 = dist;
+                    bestLevel2 = octave_of(idx); bestDist2 = dist; secondIdx = idx;
                 }
                 return true;
             });
-            if (!safe) { atomicAdd(&s_left, 1); continue; }
+            if (bestDist > threshold) { resolved[i] = 1; continue; }       // nothing within reach, whatever the earlier points take
+            const bool accept = !(RATIO && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2));
+            tentative[i] = make_int2(bestIdx | (accept ? (1 << 30) : 0), RATIO ? secondIdx : -1);
+        }
+        __syncthreads();
+        for (int i = tid; i < n_p; i += 1024) {
+            if (resolved[i]) continue;
+            const int2 t = tentative[i];
+            const int bestIdx = t.x & ~(1 << 30);
+            if (s_claim[bestIdx] < i || (t.y >= 0 && s_claim[t.y] < i)) { atomicAdd(&s_left, 1); continue; }
             resolved[i] = 1;
-            if (bestDist <= threshold) {
-                if (RATIO && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
+            if (t.x & (1 << 30)) {
                 out_feature_point[bestIdx] = i;
-                s_blocked[bestIdx] = (w.flags & kWinBlocks) ? 1 : 0;
+                s_blocked[bestIdx] = (wins[i].flags & kWinBlocks) ? 1 : 0;
                 out_point_feature[i] = bestIdx;
                 atomicAdd(&s_matches, 1);
             }
@@ -465,7 +469,7 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     const int n_p = (int)wins.size();
     MatchCtx& cx = match_ctx();
     const size_t kb = (size_t)n_f * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4;
-    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4) + pb + (size_t)n_p * (sizeof(ProjWindow) + 32 + 4 + 1) + 4 + 20 * 256;
+    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4) + pb + (size_t)n_p * (sizeof(ProjWindow) + 32 + 4 + 1 + 8) + 4 + 20 * 256;
     if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
     std::vector<float> no_stereo;
     if (!u_right) { no_stereo.assign(n_f, -1.0f); u_right = no_stereo.data(); }
@@ -479,7 +483,8 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     const uint32_t* d_dp = (const uint32_t*)cx.upload(desc_p, (size_t)n_p * 32);
     int* d_fp = (int*)cx.dalloc((size_t)n_f * 4); int* d_pf = (int*)cx.dalloc((size_t)n_p * 4);
     uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_p); int* d_nm = (int*)cx.dalloc(4);
-    if (!d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm) return ORB_ERR_CUDA;
+    int2* d_tent = (int2*)cx.dalloc((size_t)n_p * sizeof(int2));
+    if (!d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm || !d_tent) return ORB_ERR_CUDA;
     const bool staged = n_f <= kStagedMaxFeatures;
     static DeviceOnce once_configured;
     if (!once_configured.run([&] {
@@ -491,7 +496,7 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
         })) return ORB_ERR_CUDA;
     const size_t smem = staged ? (size_t)n_f * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16 : (size_t)n_f * 5 + 16;
     const GridParams g = make_grid_params(bounds, origin);
-#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_nm)
+#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_tent, d_nm)
     if (ratio) { if (staged) ORB_LAUNCH_WS(true, true); else ORB_LAUNCH_WS(true, false); }
     else { if (staged) ORB_LAUNCH_WS(false, true); else ORB_LAUNCH_WS(false, false); }
 #undef ORB_LAUNCH_WS
