@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "internal.h"
@@ -238,14 +239,15 @@ __global__ void area_fill_kernel(const orb_keypoint_t* __restrict__ kps, const i
 // ---------------------------------------------------------------- SearchByProjection: window searches
 // The reference walks the projected points in order; a feature taken by an earlier point is skipped by the later ones
 // (ORBmatcher.cc:82-84, :1404-1406, :1543-1544), so the result depends on the order.  One CTA reproduces it in rounds.
-// In a round every unresolved point i walks its window ONCE over the features that are free at the start of the round and
+// In a round every unresolved point i walks its window ONCE over the features that no EARLIER point has taken so far and
 //   * finds its outcome as if it were its turn: best B and second best S (the two candidates the reference's best / second
 //     slots would end up holding) and whether the match is accepted;
 //   * claims, with atomicMin(point index), every candidate it could still TAKE later: free, within `threshold`.
 // The outcome of i depends on the identity of B and S only (removing any other candidate from the walk changes neither slot),
 // and an earlier unresolved point j can take a feature only if it claimed it.  So i is final as soon as neither B nor S
 // carries a claim of an earlier point; the decisions are applied after a barrier (no walk reads a feature state that a
-// decision of the same round has already changed).  Two points finalised in one round never take the same feature (the
+// decision of the same round has already changed).  A feature remembers WHICH point took it: a later point that became final
+// in an earlier round hides the feature from the points after it only, never from an unresolved earlier one.  Two points finalised in one round never take the same feature (the
 // later one would have seen the earlier one's claim on its B), the lowest unresolved point is always final, and crowded
 // scenes need as many rounds as points compete for ONE feature -- the earlier rule (a point waits while ANY of its
 // candidates is claimed by ANY earlier window) needed ~30 rounds and two walks per round on 4000 points over 2000 features.
@@ -269,6 +271,56 @@ __device__ __forceinline__ int hamming32(const uint32_t* __restrict__ a, const u
 // walks per round run at shared-memory latency (frames up to kStagedMaxFeatures features; larger ones walk global memory)
 constexpr int kStagedMaxFeatures = 8192;
 
+// One point's walk of a round: its outcome over the features that are free in `blocked`, its claims into `claim`.
+template <bool RATIO, class KP, class BLOCKED>
+__device__ __forceinline__ void window_point_round(int i, const ProjWindow& w, const KP* __restrict__ kps, const int* __restrict__ cell_ptr,
+                                                   const int* __restrict__ cell_idx, const GridParams& g, BLOCKED blocked_for_me,
+                                                   const float* __restrict__ u_right, const uint32_t* __restrict__ desc_f,
+                                                   const uint32_t* __restrict__ desc_p, int threshold, float nnratio, int* claim,
+                                                   uint8_t* __restrict__ resolved, int2* __restrict__ tentative) {
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1, secondIdx = -1;
+    const uint32_t* dp = desc_p + (size_t)i * 8;
+    for_features_in_area(kps, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level, [&](int idx) {
+        if (blocked_for_me(idx)) return true;
+        if ((w.flags & kWinStereo) && u_right[idx] > 0) {
+            const float er = fabsf(__fsub_rn(w.ur, u_right[idx]));
+            if (er > w.r) return true;
+        }
+        const int dist = hamming32(dp, desc_f + (size_t)idx * 8);
+        if (dist <= threshold) atomicMin(&claim[idx], i);       // a feature this point could take, now or later
+        if (dist < bestDist) {
+            bestDist2 = bestDist; bestLevel2 = bestLevel; secondIdx = bestIdx;
+            bestDist = dist; bestLevel = kps[idx].octave; bestIdx = idx;
+        } else if (RATIO && dist < bestDist2) {
+            bestLevel2 = kps[idx].octave; bestDist2 = dist; secondIdx = idx;
+        }
+        return true;
+    });
+    if (bestDist > threshold) { resolved[i] = 1; return; }       // nothing within reach, whatever the earlier points take
+    const bool accept = !(RATIO && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2));
+    tentative[i] = make_int2(bestIdx | (accept ? (1 << 30) : 0), RATIO ? secondIdx : -1);
+}
+
+// The first round -- every point is unresolved, nothing is taken yet -- on the whole GPU, a thread per point: claims into a global
+// array (preset to "no claim"), outcomes into `tentative`.  The single CTA below then starts with the decisions of round 1.
+template <bool RATIO>
+__global__ void __launch_bounds__(128) window_first_round_kernel(const orb_keypoint_t* __restrict__ kps_g, const uint32_t* __restrict__ desc_f,
+                                                                 const float* __restrict__ u_right, const uint8_t* __restrict__ occupied,
+                                                                 const int* __restrict__ cell_ptr_g, const int* __restrict__ cell_idx_g, GridParams g,
+                                                                 const ProjWindow* __restrict__ wins, const uint32_t* __restrict__ desc_p, int n_p,
+                                                                 float nnratio, int threshold, int* __restrict__ claim_g,
+                                                                 int* __restrict__ out_point_feature, uint8_t* __restrict__ resolved,
+                                                                 int2* __restrict__ tentative) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_p) return;
+    const ProjWindow w = wins[i];
+    out_point_feature[i] = -1;
+    if (!(w.flags & kWinValid)) { resolved[i] = 1; return; }
+    resolved[i] = 0;
+    window_point_round<RATIO>(i, w, kps_g, cell_ptr_g, cell_idx_g, g, [&](int idx) { return occupied[idx] != 0; }, u_right, desc_f, desc_p, threshold,
+                              nnratio, claim_g, resolved, tentative);
+}
+
 template <bool RATIO, bool STAGED>
 __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_t* __restrict__ kps_g, const uint32_t* __restrict__ desc_f,
                                                              const float* __restrict__ u_right, const uint8_t* __restrict__ occupied, int n_f,
@@ -276,17 +328,21 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
                                                              const ProjWindow* __restrict__ wins, const uint32_t* __restrict__ desc_p, int n_p,
                                                              float nnratio, int threshold, int* __restrict__ out_feature_point,
                                                              int* __restrict__ out_point_feature, uint8_t* __restrict__ resolved,
-                                                             int2* __restrict__ tentative, int* __restrict__ out_nmatches) {
+                                                             int2* __restrict__ tentative, const int* __restrict__ first_round_claims,
+                                                             int* __restrict__ taker_g, int* __restrict__ out_nmatches) {
     extern __shared__ int s_dyn[];
     int* s_claim = s_dyn;                                             // [n_f]
     int* s_cell_idx = s_claim + n_f;                                  // [n_f]            (STAGED)
     int* s_cell_ptr = s_cell_idx + (STAGED ? n_f : 0);                // [kGridCells + 1] (STAGED)
     KpLite* s_kp = reinterpret_cast<KpLite*>(s_cell_ptr + (STAGED ? kGridCells + 1 : 0));      // [n_f] (STAGED)
-    uint8_t* s_blocked = reinterpret_cast<uint8_t*>(s_kp + (STAGED ? n_f : 0));                 // [n_f]
+    int* s_taker = STAGED ? reinterpret_cast<int*>(s_kp + n_f) : taker_g;                      // [n_f] see below (global memory for large frames)
     __shared__ int s_left, s_matches;
     const int tid = threadIdx.x;
     for (int f = tid; f < n_f; f += 1024) {
-        s_blocked[f] = occupied[f]; out_feature_point[f] = -1;
+        // the point that took the feature and blocks it: -1 = occupied from the start (blocked for every point), "none" otherwise.
+        // Point i skips a feature only if its taker is EARLIER than i: a later point that was final in an earlier round must not
+        // change what i sees at its turn.
+        s_taker[f] = occupied[f] ? -1 : 0x7fffffff; out_feature_point[f] = -1;
         if (STAGED) {
             s_cell_idx[f] = cell_idx_g[f];
             KpLite k; k.x = kps_g[f].x; k.y = kps_g[f].y; k.octave = kps_g[f].octave;
@@ -295,47 +351,30 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
     }
     if (STAGED)
         for (int c = tid; c <= kGridCells; c += 1024) s_cell_ptr[c] = cell_ptr_g[c];
-    for (int i = tid; i < n_p; i += 1024) {
-        out_point_feature[i] = -1;
-        resolved[i] = (wins[i].flags & kWinValid) ? 0 : 1;
-    }
+    if (!first_round_claims)
+        for (int i = tid; i < n_p; i += 1024) {
+            out_point_feature[i] = -1;
+            resolved[i] = (wins[i].flags & kWinValid) ? 0 : 1;
+        }
     if (tid == 0) s_matches = 0;
     const int* cell_ptr = STAGED ? s_cell_ptr : cell_ptr_g;
     const int* cell_idx = STAGED ? s_cell_idx : cell_idx_g;
-    auto walk = [&](const ProjWindow& w, auto f) {
-        if (STAGED) for_features_in_area(s_kp, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level, f);
-        else for_features_in_area(kps_g, cell_ptr, cell_idx, g, w.x, w.y, w.r, w.min_level, w.max_level, f);
-    };
-    auto octave_of = [&](int idx) { return STAGED ? s_kp[idx].octave : kps_g[idx].octave; };
-    while (true) {
+    for (int round = 0;; round++) {
         __syncthreads();
-        for (int f = tid; f < n_f; f += 1024) s_claim[f] = 0x7fffffff;
-        if (tid == 0) s_left = 0;
-        __syncthreads();
-        for (int i = tid; i < n_p; i += 1024) {
-            if (resolved[i]) continue;
-            const ProjWindow w = wins[i];
-            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1, secondIdx = -1;
-            const uint32_t* dp = desc_p + (size_t)i * 8;
-            walk(w, [&](int idx) {
-                if (s_blocked[idx]) return true;
-                if ((w.flags & kWinStereo) && u_right[idx] > 0) {
-                    const float er = fabsf(__fsub_rn(w.ur, u_right[idx]));
-                    if (er > w.r) return true;
-                }
-                const int dist = hamming32(dp, desc_f + (size_t)idx * 8);
-                if (dist <= threshold) atomicMin(&s_claim[idx], i);       // a feature this point could take, now or later
-                if (dist < bestDist) {
-                    bestDist2 = bestDist; bestLevel2 = bestLevel; secondIdx = bestIdx;
-                    bestDist = dist; bestLevel = octave_of(idx); bestIdx = idx;
-                } else if (RATIO && dist < bestDist2) {
-                    bestLevel2 = octave_of(idx); bestDist2 = dist; secondIdx = idx;
-                }
-                return true;
-            });
-            if (bestDist > threshold) { resolved[i] = 1; continue; }       // nothing within reach, whatever the earlier points take
-            const bool accept = !(RATIO && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2));
-            tentative[i] = make_int2(bestIdx | (accept ? (1 << 30) : 0), RATIO ? secondIdx : -1);
+        if (round == 0 && first_round_claims) {
+            // round 1 was walked by window_first_round_kernel
+            for (int f = tid; f < n_f; f += 1024) s_claim[f] = first_round_claims[f];
+            if (tid == 0) s_left = 0;
+        } else {
+            for (int f = tid; f < n_f; f += 1024) s_claim[f] = 0x7fffffff;
+            if (tid == 0) s_left = 0;
+            __syncthreads();
+            for (int i = tid; i < n_p; i += 1024) {
+                if (resolved[i]) continue;
+                auto blocked_for_me = [&](int idx) { return s_taker[idx] < i; };
+                if (STAGED) window_point_round<RATIO>(i, wins[i], s_kp, cell_ptr, cell_idx, g, blocked_for_me, u_right, desc_f, desc_p, threshold, nnratio, s_claim, resolved, tentative);
+                else window_point_round<RATIO>(i, wins[i], kps_g, cell_ptr, cell_idx, g, blocked_for_me, u_right, desc_f, desc_p, threshold, nnratio, s_claim, resolved, tentative);
+            }
         }
         __syncthreads();
         for (int i = tid; i < n_p; i += 1024) {
@@ -346,7 +385,7 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
             resolved[i] = 1;
             if (t.x & (1 << 30)) {
                 out_feature_point[bestIdx] = i;
-                s_blocked[bestIdx] = (wins[i].flags & kWinBlocks) ? 1 : 0;
+                if (wins[i].flags & kWinBlocks) s_taker[bestIdx] = i;
                 out_point_feature[i] = bestIdx;
                 atomicAdd(&s_matches, 1);
             }
@@ -469,7 +508,7 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     const int n_p = (int)wins.size();
     MatchCtx& cx = match_ctx();
     const size_t kb = (size_t)n_f * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4;
-    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4) + pb + (size_t)n_p * (sizeof(ProjWindow) + 32 + 4 + 1 + 8) + 4 + 20 * 256;
+    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4 + 4 + 4) + pb + (size_t)n_p * (sizeof(ProjWindow) + 32 + 4 + 1 + 8) + 4 + 20 * 256;
     if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
     std::vector<float> no_stereo;
     if (!u_right) { no_stereo.assign(n_f, -1.0f); u_right = no_stereo.data(); }
@@ -484,19 +523,30 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     int* d_fp = (int*)cx.dalloc((size_t)n_f * 4); int* d_pf = (int*)cx.dalloc((size_t)n_p * 4);
     uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_p); int* d_nm = (int*)cx.dalloc(4);
     int2* d_tent = (int2*)cx.dalloc((size_t)n_p * sizeof(int2));
-    if (!d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm || !d_tent) return ORB_ERR_CUDA;
+    int* d_claim = (int*)cx.dalloc((size_t)n_f * 4);
+    int* d_taker = (int*)cx.dalloc((size_t)n_f * 4);
+    if (!d_taker || !d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm || !d_tent || !d_claim) return ORB_ERR_CUDA;
     const bool staged = n_f <= kStagedMaxFeatures;
     static DeviceOnce once_configured;
     if (!once_configured.run([&] {
-            const int big = kFrameMaxFeatures * 5 + 16, small = kStagedMaxFeatures * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16;
+            const int big = kFrameMaxFeatures * 4 + 16, small = kStagedMaxFeatures * (4 + 4 + 12 + 4) + (kGridCells + 1) * 4 + 16;
             return cuda_ok(cudaFuncSetAttribute(window_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big), "cudaFuncSetAttribute") &&
                    cuda_ok(cudaFuncSetAttribute(window_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big), "cudaFuncSetAttribute") &&
                    cuda_ok(cudaFuncSetAttribute(window_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small), "cudaFuncSetAttribute") &&
                    cuda_ok(cudaFuncSetAttribute(window_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small), "cudaFuncSetAttribute");
         })) return ORB_ERR_CUDA;
-    const size_t smem = staged ? (size_t)n_f * (4 + 4 + 12 + 1) + (kGridCells + 1) * 4 + 16 : (size_t)n_f * 5 + 16;
+    const size_t smem = staged ? (size_t)n_f * (4 + 4 + 12 + 4) + (kGridCells + 1) * 4 + 16 : (size_t)n_f * 4 + 16;
     const GridParams g = make_grid_params(bounds, origin);
-#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_tent, d_nm)
+    // round 1 on the whole GPU when there are enough points to fill more than one SM (ORBCUDA_WS_FIRST=0: everything in the one CTA)
+    static const bool first_on_grid = [] { const char* e = getenv("ORBCUDA_WS_FIRST"); return e ? atoi(e) != 0 : true; }();
+    const int* d_first = nullptr;
+    if (first_on_grid && n_p >= 1024 && n_f > 0) {
+        ORB_CUDA_TRY(cudaMemsetAsync(d_claim, 0x7f, (size_t)n_f * 4, cx.stream));      // 0x7f7f7f7f: above every point index
+        if (ratio) window_first_round_kernel<true><<<(n_p + 127) / 128, 128, 0, cx.stream>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
+        else window_first_round_kernel<false><<<(n_p + 127) / 128, 128, 0, cx.stream>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
+        d_first = d_claim;
+    }
+#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_tent, d_first, d_taker, d_nm)
     if (ratio) { if (staged) ORB_LAUNCH_WS(true, true); else ORB_LAUNCH_WS(true, false); }
     else { if (staged) ORB_LAUNCH_WS(false, true); else ORB_LAUNCH_WS(false, false); }
 #undef ORB_LAUNCH_WS

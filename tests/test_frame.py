@@ -209,6 +209,27 @@ def test_gpu_search_by_projection_frame(orb, oracle, synth, golden_dir, nf, nmp,
         assert ref_n > 50
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,nf,nmp,ci", [(907405640, 641, 4287, 0), (907405640, 641, 4287, 1), (5, 400, 4500, 0), (6, 900, 3000, 1)])
+def test_gpu_search_by_projection_frame_wide_windows(orb, oracle, synth, golden_dir, seed, nf, nmp, ci):
+    """th = 15 in a crowded scene: every window holds a large part of the frame, points wait for each other over ~15 rounds, and a
+    point that becomes final early (a LATER one in the reference's order) takes a feature that is the second best of an earlier,
+    still unresolved point -- the earlier point must go on seeing it (found by tools/soak_frame.py, seed 7)."""
+    g = _golden(golden_dir)
+    K, D = (g["tum1_K"], g["tum1_D"]) if ci == 0 else (np.array([500, 500, 320, 240], np.float32), np.zeros(4, np.float32))
+    keys, desc_f, sf, rng = _scene(oracle, synth, nf, 0, seed, K, D, True)
+    fr = orb.FrameFeatures(keys, K, D, 640, 480)
+    ur = np.where(rng.random(nf) < 0.5, fr.keys_un["x"] - rng.uniform(0, 30, nf), -1).astype(np.float32)
+    occ = (rng.random(nf) < 0.1).astype(np.uint8)
+    mp, dm = _map_points(oracle, fr.keys_un, desc_f, nmp, rng)
+    for th, nnratio in ((15.0, 0.6), (15.0, 0.9), (7.0, 0.6)):
+        ref_fp, ref_pf, ref_n = oracle.search_by_projection_frame(fr.keys_un, desc_f, ur, occ, fr.cell_ptr, fr.cell_idx, fr.bounds, sf,
+                                                                  mp, dm, th, nnratio)
+        fp, pf, n = orb.search_by_projection_frame(fr, desc_f, ur, occ, sf, mp, dm, th=th, nnratio=nnratio)
+        assert n == ref_n and np.array_equal(pf, ref_pf) and np.array_equal(fp, ref_fp), (th, nnratio)
+    assert ref_n > 50
+
+
 def _proj_points(oracle, keys_un, desc_f, npts, rng, rot_deg=12.0):
     """Projected points of a previous frame: most land near a current feature and carry a noisy copy of its descriptor;
     their angles differ from the current ones by a common rotation plus outliers (exercises the rotation histogram)."""
