@@ -131,13 +131,22 @@ __global__ void __launch_bounds__(1024) grid_kernel(const orb_keypoint_t* __rest
     if (tid == 1023) s_count[kGridCells] = s_part[1023];
     __syncthreads();
     for (int k = tid; k <= kGridCells; k += 1024) cell_ptr[k] = s_count[k];
-    // stable placement: rank inside the cell = number of earlier key points of the same cell (push_back order)
-    for (int i = tid; i < n; i += 1024) {
-        const int ci = s_cell[i];
-        if (ci < 0) continue;
-        int rank = 0;
-        for (int j = 0; j < i; j++) rank += (s_cell[j] == ci);
-        cell_idx[s_count[ci] + rank] = i;
+    __syncthreads();
+    // stable placement (push_back order inside a cell): ONE warp walks the key points 32 at a time in index order; inside a
+    // group of 32 the rank among the same-cell lanes comes from __match_any_sync, across groups from the cell's cursor in
+    // s_count, which the first lane of every cell group advances.  (A rank count over all earlier key points per key point is
+    // n^2 / 2 shared-memory reads with a critical path of n: 58 us for 2000 key points, 8 us this way.)
+    if (tid < 32) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + tid;
+            const int ci = i < n ? (int)s_cell[i] : -2;
+            const unsigned same = __match_any_sync(0xffffffffu, ci);
+            const int rank = __popc(same & ((1u << tid) - 1u));
+            if (ci >= 0) cell_idx[s_count[ci] + rank] = i;
+            __syncwarp();
+            if (ci >= 0 && rank == 0) s_count[ci] += __popc(same);
+            __syncwarp();
+        }
     }
 }
 
