@@ -2,7 +2,7 @@
 """Sharded 2000 x 1M map search alone (no extraction): the fused peer-memory exchange (orbm_knn2_exchange_device) timed on every
 rank's stream, max over ranks, and its records compared with the unsharded search of rank 0's own full copy of the map.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/shard_search_bench.py
-ORBCUDA_SHARE_BOUND=0 switches the cross-rank pruning bounds off (A/B).  SEARCHES_IN_FLIGHT=k (default 1) keeps k independent
+ORBCUDA_SHARE_BOUND=1 switches the cross-rank pruning bounds on (A/B; off by default).  SEARCHES_IN_FLIGHT=k (default 1) keeps k independent
 searches in flight on k streams, each with its own peer buffers: the exchange of one search (a cross-GPU wait) overlaps the tensor
 core kernel of the next -- the throughput a server sees that matches the key frames of several agents."""
 import ctypes as C
@@ -94,7 +94,7 @@ for rep in range(3):
 assert all(torch.equal(o, ref) for o in outs) and all(p.error() == 0 for p in peers)
 if rank == 0:
     print("world %d share_bound=%s searches_in_flight=%d: %.4f ms per search (runs: %s), records == single search" %
-          (world, os.environ.get("ORBCUDA_SHARE_BOUND", "1"), K, min(res), ", ".join("%.4f" % r for r in res)))
+          (world, os.environ.get("ORBCUDA_SHARE_BOUND", "0 (default)"), K, min(res), ", ".join("%.4f" % r for r in res)))
 for p in peers:
     p.close()
 dist.destroy_process_group()
