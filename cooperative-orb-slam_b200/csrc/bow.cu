@@ -117,7 +117,7 @@ int orbv_transform(orbv_handle_t h, const uint8_t* desc, int n, int levelsup, in
     const uint32_t* d_desc = (const uint32_t*)cx.upload(desc, (size_t)n * 32);
     int* d_w = (int*)cx.dalloc((size_t)n * 4); int* d_n = (int*)cx.dalloc((size_t)n * 4); double* d_wt = (double*)cx.dalloc((size_t)n * 8);
     if (!d_desc || !d_w || !d_n || !d_wt) return ORB_ERR_CUDA;
-    bow_descend_kernel<<<(n + 3) / 4, 128, 0, cx.stream>>>(d_desc, n, v->d_child_ptr, v->d_child_idx, v->d_desc, v->d_word, v->d_weight,
+    bow_descend_kernel<<<(n + 3) / 4, 128, 0, cx.s()>>>(d_desc, n, v->d_child_ptr, v->d_child_idx, v->d_desc, v->d_word, v->d_weight,
                                                           v->depth - levelsup, d_w, d_n, d_wt);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(out_word, d_w, (size_t)n * 4) || !cx.download(out_node, d_n, (size_t)n * 4) || !cx.download(out_weight, d_wt, (size_t)n * 8) ||

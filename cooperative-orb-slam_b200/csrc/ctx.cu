@@ -58,7 +58,16 @@ bool MatchCtx::begin(int dev, size_t dev_bytes, size_t host_bytes) {
         hcap = want;
     }
     doff = hoff = 0; npend = 0;
+    up_bytes = dl_bytes = 0; copy_failed = false;
     return true;
+}
+
+cudaStream_t MatchCtx::s() {
+    if (up_bytes) {
+        if (!cuda_ok(cudaMemcpyAsync(up_d, up_h, up_bytes, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync")) copy_failed = true;
+        up_bytes = 0;
+    }
+    return stream;
 }
 
 void* MatchCtx::dalloc(size_t bytes) {
@@ -78,23 +87,36 @@ void* MatchCtx::upload(const void* src, size_t bytes) {
     void* hstage = hbase + hoff;
     hoff += hb;
     memcpy(hstage, src, bytes);
-    if (!cuda_ok(cudaMemcpyAsync(d, hstage, bytes, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync")) return nullptr;
-    return d;
+    if (up_bytes && (char*)d == up_d + up256(up_bytes) && (char*)hstage == up_h + up256(up_bytes)) {
+        up_bytes = up256(up_bytes) + bytes;      // the padding in between is arena space of nobody
+    } else {
+        s();
+        up_d = (char*)d; up_h = (char*)hstage; up_bytes = bytes;
+    }
+    return copy_failed ? nullptr : d;
 }
 
 bool MatchCtx::download(void* dst, const void* dsrc, size_t bytes) {
     if (bytes == 0) return true;
     const size_t hb = up256(bytes);
     if (hoff + hb > hcap || npend >= 8) { set_error("matcher workspace overflow (download)"); return false; }
-    void* hstage = hbase + hoff;
+    char* hstage = hbase + hoff;
     hoff += hb;
-    if (!cuda_ok(cudaMemcpyAsync(hstage, dsrc, bytes, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync")) return false;
+    if (dl_bytes && (const char*)dsrc == dl_d + up256(dl_bytes) && hstage == dl_h + up256(dl_bytes)) {
+        dl_bytes = up256(dl_bytes) + bytes;
+    } else {
+        if (dl_bytes && !cuda_ok(cudaMemcpyAsync(dl_h, dl_d, dl_bytes, cudaMemcpyDeviceToHost, s()), "cudaMemcpyAsync")) return false;
+        dl_d = (const char*)dsrc; dl_h = hstage; dl_bytes = bytes;
+    }
     pend[npend++] = Pending{dst, hstage, bytes};
     return true;
 }
 
 bool MatchCtx::finish() {
-    if (!cuda_ok(cudaStreamSynchronize(stream), "matcher kernel")) return false;
+    cudaStream_t st = s();
+    if (dl_bytes && !cuda_ok(cudaMemcpyAsync(dl_h, dl_d, dl_bytes, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync")) copy_failed = true;
+    dl_bytes = 0;
+    if (!cuda_ok(cudaStreamSynchronize(stream), "matcher kernel") || copy_failed) return false;
     for (int i = 0; i < npend; i++) memcpy(pend[i].dst, pend[i].staged, pend[i].bytes);
     npend = 0;
     return true;

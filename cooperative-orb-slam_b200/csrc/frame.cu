@@ -530,7 +530,8 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     const ProjWindow* d_w = (const ProjWindow*)cx.upload(wins.data(), (size_t)n_p * sizeof(ProjWindow));
     const uint32_t* d_dp = (const uint32_t*)cx.upload(desc_p, (size_t)n_p * 32);
     int* d_fp = (int*)cx.dalloc((size_t)n_f * 4); int* d_pf = (int*)cx.dalloc((size_t)n_p * 4);
-    uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_p); int* d_nm = (int*)cx.dalloc(4);
+    int* d_nm = (int*)cx.dalloc(4);                 // right behind d_fp and d_pf: the three downloads leave as one copy
+    uint8_t* d_res = (uint8_t*)cx.dalloc((size_t)n_p);
     int2* d_tent = (int2*)cx.dalloc((size_t)n_p * sizeof(int2));
     int* d_claim = (int*)cx.dalloc((size_t)n_f * 4);
     int* d_taker = (int*)cx.dalloc((size_t)n_f * 4);
@@ -550,12 +551,12 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     static const bool first_on_grid = [] { const char* e = getenv("ORBCUDA_WS_FIRST"); return e ? atoi(e) != 0 : true; }();
     const int* d_first = nullptr;
     if (first_on_grid && n_p >= 1024 && n_f > 0) {
-        ORB_CUDA_TRY(cudaMemsetAsync(d_claim, 0x7f, (size_t)n_f * 4, cx.stream));      // 0x7f7f7f7f: above every point index
-        if (ratio) window_first_round_kernel<true><<<(n_p + 127) / 128, 128, 0, cx.stream>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
-        else window_first_round_kernel<false><<<(n_p + 127) / 128, 128, 0, cx.stream>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
+        ORB_CUDA_TRY(cudaMemsetAsync(d_claim, 0x7f, (size_t)n_f * 4, cx.s()));      // 0x7f7f7f7f: above every point index
+        if (ratio) window_first_round_kernel<true><<<(n_p + 127) / 128, 128, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
+        else window_first_round_kernel<false><<<(n_p + 127) / 128, 128, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
         d_first = d_claim;
     }
-#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.stream>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_tent, d_first, d_taker, d_nm)
+#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.s()>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_tent, d_first, d_taker, d_nm)
     if (ratio) { if (staged) ORB_LAUNCH_WS(true, true); else ORB_LAUNCH_WS(true, false); }
     else { if (staged) ORB_LAUNCH_WS(false, true); else ORB_LAUNCH_WS(false, false); }
 #undef ORB_LAUNCH_WS
@@ -632,7 +633,7 @@ int orbf_undistort_keypoints(const orb_keypoint_t* kps, int n, const float* K, c
     const orb_keypoint_t* d_in = (const orb_keypoint_t*)cx.upload(kps, bytes);
     orb_keypoint_t* d_out = (orb_keypoint_t*)cx.dalloc(bytes);
     if (!d_in || !d_out) return ORB_ERR_CUDA;
-    undistort_kernel<<<(n + 255) / 256, 256, 0, cx.stream>>>(d_in, n, p, d_out);
+    undistort_kernel<<<(n + 255) / 256, 256, 0, cx.s()>>>(d_in, n, p, d_out);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(out, d_out, bytes) || !cx.finish()) return ORB_ERR_CUDA;
     return ORB_OK;
@@ -669,7 +670,7 @@ int orbf_assign_grid(const orb_keypoint_t* kps_un, int n, const float* bounds, i
     if (!once_configured.run([&] {
             return cuda_ok(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16), "cudaFuncSetAttribute");
         })) return ORB_ERR_CUDA;
-    grid_kernel<<<1, 1024, smem, cx.stream>>>(d_k, n, nullptr, 0, make_grid_params(bounds), d_ptr, d_idx);
+    grid_kernel<<<1, 1024, smem, cx.s()>>>(d_k, n, nullptr, 0, make_grid_params(bounds), d_ptr, d_idx);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(cell_ptr, d_ptr, pb)) return ORB_ERR_CUDA;
     if (n && !cx.download(cell_idx, d_idx, (size_t)n * 4)) return ORB_ERR_CUDA;
@@ -719,9 +720,9 @@ int orbf_features_in_area(const orb_keypoint_t* kps_un, int n, const int32_t* ce
     int* d_cnt = (int*)cx.dalloc(qb); int* d_ptr = (int*)cx.dalloc(qb + 4); int* d_out = (int*)cx.dalloc(ob);
     if ((n && (!d_k || !d_ci)) || !d_cp || !d_qx || !d_qy || !d_qr || !d_mn || !d_mx || !d_cnt || !d_ptr || !d_out) return ORB_ERR_CUDA;
     const GridParams g = make_grid_params(bounds);
-    area_count_kernel<<<(nq + 127) / 128, 128, 0, cx.stream>>>(d_k, d_cp, d_ci, g, d_qx, d_qy, d_qr, d_mn, d_mx, nq, d_cnt);
-    scan_kernel<<<1, 1024, 0, cx.stream>>>(d_cnt, nq, d_ptr);
-    area_fill_kernel<<<(nq + 127) / 128, 128, 0, cx.stream>>>(d_k, d_cp, d_ci, g, d_qx, d_qy, d_qr, d_mn, d_mx, nq, d_ptr, d_out, cap);
+    area_count_kernel<<<(nq + 127) / 128, 128, 0, cx.s()>>>(d_k, d_cp, d_ci, g, d_qx, d_qy, d_qr, d_mn, d_mx, nq, d_cnt);
+    scan_kernel<<<1, 1024, 0, cx.s()>>>(d_cnt, nq, d_ptr);
+    area_fill_kernel<<<(nq + 127) / 128, 128, 0, cx.s()>>>(d_k, d_cp, d_ci, g, d_qx, d_qy, d_qr, d_mn, d_mx, nq, d_ptr, d_out, cap);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(out_ptr, d_ptr, qb + 4)) return ORB_ERR_CUDA;
     if (cap && !cx.download(out_idx, d_out, ob)) return ORB_ERR_CUDA;
@@ -866,7 +867,7 @@ int orbm_window_best_match(const orb_keypoint_t* kps_un, const uint8_t* desc_f, 
     const uint32_t* d_dp = (const uint32_t*)cx.upload(desc_pts, (size_t)n_pts * 32);
     int* d_bi = (int*)cx.dalloc((size_t)n_pts * 4); int* d_bd = (int*)cx.dalloc((size_t)n_pts * 4);
     if (!d_k || !d_df || !d_cp || !d_ci || !d_sf || !d_p || !d_dp || !d_bi || !d_bd || (inv_level_sigma2 && (!d_ur || !d_is))) return ORB_ERR_CUDA;
-    window_best_kernel<<<(n_pts + 127) / 128, 128, 0, cx.stream>>>(d_k, d_df, d_ur, d_cp, d_ci, make_grid_params(bounds, grid_origin), d_sf, d_is, d_p, d_dp, n_pts, th,
+    window_best_kernel<<<(n_pts + 127) / 128, 128, 0, cx.s()>>>(d_k, d_df, d_ur, d_cp, d_ci, make_grid_params(bounds, grid_origin), d_sf, d_is, d_p, d_dp, n_pts, th,
                                                                   d_bi, d_bd);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(best_idx, d_bi, (size_t)n_pts * 4) || !cx.download(best_dist, d_bd, (size_t)n_pts * 4) || !cx.finish()) return ORB_ERR_CUDA;
@@ -903,7 +904,7 @@ int orbm_search_for_initialization(const orb_keypoint_t* kps1_un, const uint8_t*
     if (!once_configured.run([&] {
             return cuda_ok(cudaFuncSetAttribute(init_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameMaxFeatures * 4 + 16), "cudaFuncSetAttribute");
         })) return ORB_ERR_CUDA;
-    init_search_kernel<<<1, 1024, (size_t)n2 * 4 + 16, cx.stream>>>(d_k1, d_d1, n1, d_k2, d_d2, n2, d_cp, d_ci, make_grid_params(bounds), d_xy,
+    init_search_kernel<<<1, 1024, (size_t)n2 * 4 + 16, cx.s()>>>(d_k1, d_d1, n1, d_k2, d_d2, n2, d_cp, d_ci, make_grid_params(bounds), d_xy,
                                                                     (float)window_size, nnratio, th_low, d_md, d_ow, d_m12, d_em, d_res, d_nm);
     ORB_CUDA_TRY(cudaGetLastError());
     std::vector<int32_t> ever(n1);

@@ -189,10 +189,18 @@ struct MatchCtx {
     char* hbase = nullptr; size_t hcap = 0, hoff = 0;
     struct Pending { void* dst; const void* staged; size_t bytes; };
     Pending pend[8]; int npend = 0;
+    // Uploads that follow each other are contiguous in the device arena AND in the staging arena (both advance by the same
+    // padded size), so they leave as ONE copy when the first kernel is launched; downloads of neighbouring device blocks
+    // likewise come back as one copy in finish().  (A call like the window search made 8 + 3 copies of a few KB each: ~5 us
+    // apiece on the stream.)  Kernels and copies of the entry points therefore take their stream from s().
+    char* up_d = nullptr; char* up_h = nullptr; size_t up_bytes = 0;
+    const char* dl_d = nullptr; char* dl_h = nullptr; size_t dl_bytes = 0;
+    bool copy_failed = false;
     bool begin(int dev, size_t dev_bytes, size_t host_bytes);   // select device, size the arenas, reset them
     void* dalloc(size_t bytes);                                   // device bump allocation (256-B aligned)
-    void* upload(const void* src, size_t bytes);                  // staged async H2D, returns the device copy
-    bool download(void* dst, const void* dsrc, size_t bytes);     // async D2H into staging; copied out by finish()
+    void* upload(const void* src, size_t bytes);                  // staged H2D (sent by s() / finish()), returns the device copy
+    bool download(void* dst, const void* dsrc, size_t bytes);     // D2H into staging (sent by finish()); copied out by finish()
+    cudaStream_t s();                                             // the stream, after the pending uploads have been queued on it
     bool finish();                                                // stream sync + deliver the downloads
     ~MatchCtx();
 };

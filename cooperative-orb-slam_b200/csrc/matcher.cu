@@ -106,14 +106,14 @@ int orbm_knn2(const uint8_t* queries, int nq, const uint8_t* map, int64_t nm, in
     uint8_t* d_m = nullptr;
     if (big_map) {
         d_m = (uint8_t*)cx.dalloc(mb);
-        if (d_m && !cuda_ok(cudaMemcpyAsync(d_m, map, (size_t)nm * 32, cudaMemcpyHostToDevice, cx.stream), "cudaMemcpyAsync")) return ORB_ERR_CUDA;
+        if (d_m && !cuda_ok(cudaMemcpyAsync(d_m, map, (size_t)nm * 32, cudaMemcpyHostToDevice, cx.s()), "cudaMemcpyAsync")) return ORB_ERR_CUDA;
     } else {
         d_m = (uint8_t*)cx.upload(map, nm > 0 ? (size_t)nm * 32 : 0);
     }
     int32_t* d_out = (int32_t*)cx.dalloc(rb);
     if (!d_q || !d_m || !d_out) return ORB_ERR_CUDA;
-    int rc = orbm_knn2_device(d_q, nq, d_m, nm, index_base, d_out, variant, cx.stream);
-    if (rc) { cudaStreamSynchronize(cx.stream); return rc; }
+    int rc = orbm_knn2_device(d_q, nq, d_m, nm, index_base, d_out, variant, cx.s());
+    if (rc) { cudaStreamSynchronize(cx.s()); return rc; }
     std::vector<int32_t> rec((size_t)nq * 4);
     if (!cx.download(rec.data(), d_out, rb) || !cx.finish()) return ORB_ERR_CUDA;
     for (int i = 0; i < nq; i++) {

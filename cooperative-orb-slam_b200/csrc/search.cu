@@ -501,10 +501,10 @@ static int run_bow(int mode, const uint8_t* dA, const uint8_t* vA, int nA, const
     int* d_mB = (int*)cx.dalloc((size_t)nB * 4);
     int* d_mA = (int*)cx.dalloc((size_t)nA * 4);
     if (!d_dA || !d_vA || !d_iA || !d_dB || !d_vB || !d_iB || !d_pairs || !d_mB || !d_mA) return ORB_ERR_CUDA;
-    ORB_CUDA_TRY(cudaMemsetAsync(d_mB, 0xff, (size_t)nB * 4, cx.stream));
-    ORB_CUDA_TRY(cudaMemsetAsync(d_mA, 0xff, (size_t)nA * 4, cx.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_mB, 0xff, (size_t)nB * 4, cx.s()));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_mA, 0xff, (size_t)nA * 4, cx.s()));
     const int np = (int)pairs.size();
-    bow_kernel<<<(np * 32 + 127) / 128, 128, 0, cx.stream>>>(d_dA, d_vA, d_iA, d_dB, d_vB, d_iB, d_pairs, np, ratio, mode, d_mB, d_mA);
+    bow_kernel<<<(np * 32 + 127) / 128, 128, 0, cx.s()>>>(d_dA, d_vA, d_iA, d_dB, d_vB, d_iB, d_pairs, np, ratio, mode, d_mB, d_mA);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(matchB.data(), d_mB, (size_t)nB * 4) || !cx.download(matchA.data(), d_mA, (size_t)nA * 4) || !cx.finish())
         return ORB_ERR_CUDA;
@@ -615,9 +615,9 @@ int orbm_search_for_triangulation(const uint8_t* desc1, const orbm_tri_feature_t
         const float* d_s2 = (const float*)cx.upload(level_sigma2_2, (size_t)(max_oct + 1) * 4);
         int* d_m = (int*)cx.dalloc((size_t)n1 * 4);
         if (!d_d1 || !d_f1 || !d_d2 || !d_f2 || !d_i2 || !d_it || !d_F || !d_sf || !d_s2 || !d_m) return ORB_ERR_CUDA;
-        ORB_CUDA_TRY(cudaMemsetAsync(d_m, 0xff, (size_t)n1 * 4, cx.stream));
+        ORB_CUDA_TRY(cudaMemsetAsync(d_m, 0xff, (size_t)n1 * 4, cx.s()));
         const int ni = (int)items.size();
-        triangulation_kernel<<<(ni * 32 + 127) / 128, 128, 0, cx.stream>>>(d_d1, d_f1, d_d2, d_f2, d_i2, d_it, ni, d_F, ex, ey, d_sf, d_s2,
+        triangulation_kernel<<<(ni * 32 + 127) / 128, 128, 0, cx.s()>>>(d_d1, d_f1, d_d2, d_f2, d_i2, d_it, ni, d_F, ex, ey, d_sf, d_s2,
                                                                          only_stereo, d_m);
         ORB_CUDA_TRY(cudaGetLastError());
         if (!cx.download(m12.data(), d_m, (size_t)n1 * 4) || !cx.finish()) return ORB_ERR_CUDA;
@@ -662,7 +662,7 @@ int orbm_distinctive_descriptors(const uint8_t* desc, const int32_t* ptr, int n_
     unsigned short* d_scr = (unsigned short*)cx.dalloc((size_t)soff[n_points] * 2);
     int* d_best = (int*)cx.dalloc((size_t)n_points * 4);
     if (!d_desc || !d_ptr || !d_soff || !d_scr || !d_best) return ORB_ERR_CUDA;
-    distinctive_kernel<<<(n_points * 32 + 127) / 128, 128, 0, cx.stream>>>(d_desc, d_ptr, d_soff, n_points, d_scr, d_best);
+    distinctive_kernel<<<(n_points * 32 + 127) / 128, 128, 0, cx.s()>>>(d_desc, d_ptr, d_soff, n_points, d_scr, d_best);
     ORB_CUDA_TRY(cudaGetLastError());
     if (!cx.download(best, d_best, (size_t)n_points * 4) || !cx.finish()) return ORB_ERR_CUDA;
     return ORB_OK;
@@ -700,7 +700,7 @@ int orbm_stereo_matches(orbx_handle_t hl, orbx_handle_t hr, const orb_keypoint_t
         const float* d_isf = (const float*)cx.upload(isf, (size_t)fll.nlevels * 4);
         StereoOut* d_out = (StereoOut*)cx.dalloc((size_t)n_left * sizeof(StereoOut));
         if (!d_kl || !d_dl || !d_kr || !d_dr || !d_sf || !d_isf || !d_out) return ORB_ERR_CUDA;
-        stereo_kernel<<<(n_left + kStLeftPerCta - 1) / kStLeftPerCta, kStWarps * 32, 0, cx.stream>>>(d_kl, d_dl, n_left, d_kr, d_dr, n_right, nullptr, nullptr, 0, d_sf, d_isf,
+        stereo_kernel<<<(n_left + kStLeftPerCta - 1) / kStLeftPerCta, kStWarps * 32, 0, cx.s()>>>(d_kl, d_dl, n_left, d_kr, d_dr, n_right, nullptr, nullptr, 0, d_sf, d_isf,
                                                                       pl, pr, 0, l0l, l0r, l0pl, 0, 0, dgl, hgl[0].h, mbf, max_d, d_out);
         ORB_CUDA_TRY(cudaGetLastError());
         if (!cx.download(res.data(), d_out, (size_t)n_left * sizeof(StereoOut)) || !cx.finish()) return ORB_ERR_CUDA;
