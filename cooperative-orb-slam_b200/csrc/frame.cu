@@ -310,24 +310,83 @@ __device__ __forceinline__ void window_point_round(int i, const ProjWindow& w, c
     tentative[i] = make_int2(bestIdx | (accept ? (1 << 30) : 0), RATIO ? secondIdx : -1);
 }
 
-// The first round -- every point is unresolved, nothing is taken yet -- on the whole GPU, a thread per point: claims into a global
+// The first round -- every point is unresolved, nothing is taken yet -- on the whole GPU, a WARP per point: claims into a global
 // array (preset to "no claim"), outcomes into `tentative`.  The single CTA below then starts with the decisions of round 1.
+// The lanes take one grid cell of the window each (a thread walking its window alone is a chain of dependent loads -- cell
+// range, feature index, key point, descriptor -- per candidate: 42 us for the bench scene).  That is possible because the
+// reference's best / second slots end up holding the two smallest (distance, walk position) keys of the walk -- the first
+// strict minimum, and the earliest minimum among the rest -- so the candidates may be visited in any order.
+struct Cand2 { unsigned k1, k2; int p1, p2; };      // two smallest keys (distance << 20 | position) and their (index | octave << 16)
+__device__ __forceinline__ void cand2_insert(Cand2& c, unsigned k, int p) {
+    if (k < c.k1) { c.k2 = c.k1; c.p2 = c.p1; c.k1 = k; c.p1 = p; }
+    else if (k < c.k2) { c.k2 = k; c.p2 = p; }
+}
 template <bool RATIO>
-__global__ void __launch_bounds__(128) window_first_round_kernel(const orb_keypoint_t* __restrict__ kps_g, const uint32_t* __restrict__ desc_f,
+__global__ void __launch_bounds__(256) window_first_round_kernel(const orb_keypoint_t* __restrict__ kps, const uint32_t* __restrict__ desc_f,
                                                                  const float* __restrict__ u_right, const uint8_t* __restrict__ occupied,
-                                                                 const int* __restrict__ cell_ptr_g, const int* __restrict__ cell_idx_g, GridParams g,
+                                                                 const int* __restrict__ cell_ptr, const int* __restrict__ cell_idx, GridParams g,
                                                                  const ProjWindow* __restrict__ wins, const uint32_t* __restrict__ desc_p, int n_p,
                                                                  float nnratio, int threshold, int* __restrict__ claim_g,
                                                                  int* __restrict__ out_point_feature, uint8_t* __restrict__ resolved,
                                                                  int2* __restrict__ tentative) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_p) return;
     const ProjWindow w = wins[i];
-    out_point_feature[i] = -1;
-    if (!(w.flags & kWinValid)) { resolved[i] = 1; return; }
+    if (lane == 0) out_point_feature[i] = -1;
+    if (!(w.flags & kWinValid)) { if (lane == 0) resolved[i] = 1; return; }
+    Cand2 best = {0xffffffffu, 0xffffffffu, -1, -1};
+    const AreaWindow aw = area_window(g, w.x, w.y, w.r);
+    if (!aw.empty) {
+        const bool check_levels = (w.min_level > 0) || (w.max_level >= 0);
+        const uint32_t* dp = desc_p + (size_t)i * 8;
+        const int ny = aw.y1 - aw.y0 + 1, ncells = (aw.x1 - aw.x0 + 1) * ny;
+        int base = 0;                                   // walk position of the first entry of this group of 32 cells
+        for (int c0 = 0; c0 < ncells; c0 += 32) {
+            const int cl = c0 + lane;
+            int beg = 0, cnt = 0;
+            if (cl < ncells) {
+                const int c = (aw.x0 + cl / ny) * kGridRows + aw.y0 + cl % ny;      // the walk's order: ix outer, iy inner
+                beg = cell_ptr[c]; cnt = cell_ptr[c + 1] - beg;
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int pos0 = base + incl - cnt;
+            base += __shfl_sync(0xffffffffu, incl, 31);
+            for (int j = 0; j < cnt; j++) {
+                const int idx = cell_idx[beg + j];
+                const int octave = kps[idx].octave;
+                if (check_levels) {
+                    if (octave < w.min_level) continue;
+                    if (w.max_level >= 0 && octave > w.max_level) continue;
+                }
+                const float distx = __fsub_rn(kps[idx].x, w.x), disty = __fsub_rn(kps[idx].y, w.y);
+                if (!(fabsf(distx) < w.r && fabsf(disty) < w.r)) continue;
+                if (occupied[idx]) continue;
+                if ((w.flags & kWinStereo) && u_right[idx] > 0) {
+                    const float er = fabsf(__fsub_rn(w.ur, u_right[idx]));
+                    if (er > w.r) continue;
+                }
+                const int dist = hamming32(dp, desc_f + (size_t)idx * 8);
+                if (dist <= threshold) atomicMin(&claim_g[idx], i);
+                cand2_insert(best, ((unsigned)dist << 20) | (unsigned)(pos0 + j), idx | (octave << 16));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned k1 = __shfl_xor_sync(0xffffffffu, best.k1, o), k2 = __shfl_xor_sync(0xffffffffu, best.k2, o);
+        const int p1 = __shfl_xor_sync(0xffffffffu, best.p1, o), p2 = __shfl_xor_sync(0xffffffffu, best.p2, o);
+        cand2_insert(best, k1, p1);
+        cand2_insert(best, k2, p2);
+    }
+    if (lane) return;
+    const int bestDist = best.p1 >= 0 ? (int)(best.k1 >> 20) : 256, bestDist2 = best.p2 >= 0 ? (int)(best.k2 >> 20) : 256;
+    if (bestDist > threshold) { resolved[i] = 1; return; }
     resolved[i] = 0;
-    window_point_round<RATIO>(i, w, kps_g, cell_ptr_g, cell_idx_g, g, [&](int idx) { return occupied[idx] != 0; }, u_right, desc_f, desc_p, threshold,
-                              nnratio, claim_g, resolved, tentative);
+    const int bestLevel = best.p1 >> 16, bestLevel2 = best.p2 >= 0 ? best.p2 >> 16 : -1;
+    const bool accept = !(RATIO && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2));
+    tentative[i] = make_int2((best.p1 & 0xffff) | (accept ? (1 << 30) : 0), RATIO && best.p2 >= 0 ? (best.p2 & 0xffff) : -1);
 }
 
 template <bool RATIO, bool STAGED>
@@ -552,8 +611,8 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     const int* d_first = nullptr;
     if (first_on_grid && n_p >= 1024 && n_f > 0) {
         ORB_CUDA_TRY(cudaMemsetAsync(d_claim, 0x7f, (size_t)n_f * 4, cx.s()));      // 0x7f7f7f7f: above every point index
-        if (ratio) window_first_round_kernel<true><<<(n_p + 127) / 128, 128, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
-        else window_first_round_kernel<false><<<(n_p + 127) / 128, 128, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
+        if (ratio) window_first_round_kernel<true><<<(n_p + 7) / 8, 256, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
+        else window_first_round_kernel<false><<<(n_p + 7) / 8, 256, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
         d_first = d_claim;
     }
 #define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.s()>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_tent, d_first, d_taker, d_nm)
