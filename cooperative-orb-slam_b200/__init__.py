@@ -90,6 +90,7 @@ ABI = {
     "orbf_undistort_keypoints": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I]),
     "orbf_image_bounds": (_I, [_I, _I, _VP, _VP, _I, _VP, _I]),
     "orbf_assign_grid": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I]),
+    "orbf_build_frame": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I]),
     "orbf_build_frames_device": (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
     "orbf_features_in_area": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I]),
     "orbm_search_by_projection_frame": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _F, _F, _I,
@@ -475,21 +476,29 @@ class FrameFeatures:
     """The Frame-side steps right after extraction (R21/src/Frame.cc): UndistortKeyPoints (:409-439),
     ComputeImageBounds (:441-470), AssignFeaturesToGrid (:235-250), GetFeaturesInArea (:332-385)."""
 
+    _bounds_cache = {}
+
     def __init__(self, keys, K, dist, cols, rows, device=0):
         self.device = device
         self.K = np.ascontiguousarray(K, np.float32); self.dist = np.ascontiguousarray(dist, np.float32).ravel()
         assert self.K.shape == (4,), "K = (fx, fy, cx, cy)"
         L = lib()
         k = np.ascontiguousarray(keys, KP_DTYPE)
-        self.bounds = np.zeros(4, np.float32)
-        _check(L.orbf_image_bounds(cols, rows, _p(self.K), _p(self.dist), len(self.dist), _p(self.bounds), device), "orbf_image_bounds")
+        # the image bounds belong to the camera, not to the frame: computed once per (K, dist, size) like the reference's
+        # mbInitialComputations block (R21/src/Frame.cc:96-110)
+        key = (self.K.tobytes(), self.dist.tobytes(), int(cols), int(rows), int(device))
+        b = FrameFeatures._bounds_cache.get(key)
+        if b is None:
+            b = np.zeros(4, np.float32)
+            _check(L.orbf_image_bounds(cols, rows, _p(self.K), _p(self.dist), len(self.dist), _p(b), device), "orbf_image_bounds")
+            FrameFeatures._bounds_cache[key] = b
+        self.bounds = b.copy()
         self.keys_un = np.zeros(len(k), KP_DTYPE)
-        _check(L.orbf_undistort_keypoints(_p(k), len(k), _p(self.K), _p(self.dist), len(self.dist), _p(self.keys_un), device),
-               "orbf_undistort_keypoints")
         self.cell_ptr = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32); self.cell_idx = np.zeros(max(len(k), 1), np.int32)
         n = C.c_int(0)
-        _check(L.orbf_assign_grid(_p(self.keys_un), len(k), _p(self.bounds), _p(self.cell_ptr), _p(self.cell_idx), C.byref(n), device),
-               "orbf_assign_grid")
+        # UndistortKeyPoints + AssignFeaturesToGrid in one pass over the device
+        _check(L.orbf_build_frame(_p(k), len(k), _p(self.K), _p(self.dist), len(self.dist), _p(self.bounds), _p(self.keys_un), _p(self.cell_ptr),
+                                  _p(self.cell_idx), C.byref(n), device), "orbf_build_frame")
         self.n_assigned = n.value
 
     def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):

@@ -738,6 +738,37 @@ int orbf_assign_grid(const orb_keypoint_t* kps_un, int n, const float* bounds, i
     return ORB_OK;
 }
 
+int orbf_build_frame(const orb_keypoint_t* kps, int n, const float* K, const float* dist, int ndist, const float* bounds,
+                     orb_keypoint_t* out_kps_un, int32_t* cell_ptr, int32_t* cell_idx, int* n_assigned, int device) {
+    UndistortParams p;
+    if (n < 0 || n > kFrameMaxFeatures || !bounds || !cell_ptr || (n && (!kps || !out_kps_un || !cell_idx)) || !make_undistort_params(K, dist, ndist, &p)) {
+        set_error("orbf_build_frame: bad arguments (at most %d key points; K = fx,fy,cx,cy; 4..12 distortion coefficients)", kFrameMaxFeatures);
+        return ORB_ERR_ARG;
+    }
+    MatchCtx& cx = match_ctx();
+    const size_t kb = (size_t)std::max(n, 1) * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4, ib = (size_t)std::max(n, 1) * 4;
+    if (!cx.begin(device, 2 * kb + pb + ib + 2048, 2 * kb + pb + ib + 2048)) return ORB_ERR_CUDA;
+    const orb_keypoint_t* d_in = (const orb_keypoint_t*)cx.upload(kps, (size_t)n * sizeof(orb_keypoint_t));
+    orb_keypoint_t* d_un = (orb_keypoint_t*)cx.dalloc(kb);      // the three results lie side by side: one download
+    int* d_ptr = (int*)cx.dalloc(pb);
+    int* d_idx = (int*)cx.dalloc(ib);
+    if ((n && !d_in) || !d_un || !d_ptr || !d_idx) return ORB_ERR_CUDA;
+    const size_t smem = (size_t)(kGridCells + 1) * 4 + (size_t)n * 2 + 16;
+    static DeviceOnce once_configured;
+    if (!once_configured.run([&] {
+            return cuda_ok(cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCells + 1) * 4 + kFrameMaxFeatures * 2 + 16), "cudaFuncSetAttribute");
+        })) return ORB_ERR_CUDA;
+    if (n) undistort_kernel<<<(n + 255) / 256, 256, 0, cx.s()>>>(d_in, n, p, d_un);
+    grid_kernel<<<1, 1024, smem, cx.s()>>>(d_un, n, nullptr, 0, make_grid_params(bounds), d_ptr, d_idx);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (n && !cx.download(out_kps_un, d_un, (size_t)n * sizeof(orb_keypoint_t))) return ORB_ERR_CUDA;
+    if (!cx.download(cell_ptr, d_ptr, pb)) return ORB_ERR_CUDA;
+    if (n && !cx.download(cell_idx, d_idx, (size_t)n * 4)) return ORB_ERR_CUDA;
+    if (!cx.finish()) return ORB_ERR_CUDA;
+    if (n_assigned) *n_assigned = cell_ptr[kGridCells];
+    return ORB_OK;
+}
+
 int orbf_build_frames_device(const void* d_kps, const int32_t* d_counts, int n_frames, int cap, const float* K, const float* dist, int ndist,
                              const float* bounds, void* d_kps_un, int32_t* d_cell_ptr, int32_t* d_cell_idx, void* stream) {
     UndistortParams p;

@@ -265,6 +265,12 @@ int orbf_image_bounds(int cols, int rows, const float* K, const float* dist, int
  * cell_idx[n]; indices ascend inside a cell (push_back order).  *n_assigned = key points inside the grid. */
 int orbf_assign_grid(const orb_keypoint_t* kps_un, int n, const float* bounds, int32_t* cell_ptr, int32_t* cell_idx,
                      int* n_assigned, int device);
+/* Frame::UndistortKeyPoints (:409-439) followed by Frame::AssignFeaturesToGrid (:235-250), the two steps the Frame constructor
+ * (R21/src/Frame.cc:58-116, :119-174, :177-232) runs back to back on the extractor's key points, as ONE pass over the device:
+ * one upload of the key points, two kernels, one download of out_kps_un[n], cell_ptr[64*48 + 1] and cell_idx[n].  bounds = the
+ * result of orbf_image_bounds for this camera (the reference computes it once: mbInitialComputations). */
+int orbf_build_frame(const orb_keypoint_t* kps, int n, const float* K, const float* dist, int ndist, const float* bounds,
+                     orb_keypoint_t* out_kps_un, int32_t* cell_ptr, int32_t* cell_idx, int* n_assigned, int device);
 /* UndistortKeyPoints + AssignFeaturesToGrid for a whole batch, on the device-resident output of
  * orbx_extract_batch_device (d_kps [n_frames][cap], d_counts [n_frames]) without a host round trip, on `stream`:
  * d_kps_un [n_frames][cap], d_cell_ptr [n_frames][64*48 + 1], d_cell_idx [n_frames][cap].  bounds from
