@@ -17,6 +17,8 @@ quadtree, orientation, blur, rBRIEF), dealt round-robin to `--streams` extractor
                  cv2's own primitives timed beside the shim's (per_stage, adjusted_value).
   matching     : brute-force 2-NN Hamming, 2000 queries x 1M map descriptors (BASELINE config 4; map sharded over the
                  ranks, per-rank records exchanged and merged), Gcmp/s, burst and sustained, checked against the oracle.
+                 `value` is the best formulation: two independent searches in flight on two streams (own result and peer
+                 buffers); `one_search_at_a_time` is the latency of a single search, `variants` holds every kernel.
   configs      : (N = 1) BASELINE configs 2 and 3 as their own objects: the KITTI-shape 1241x376 / 2000-feature
                  1000-frame stream and the EuRoC-shape 752x480 stereo pairs (two extractors + ComputeStereoMatches).
 N > 1: one process per GPU (torchrun), replicas for extraction (weak scaling), sharded map for matching.
