@@ -191,6 +191,27 @@ FrameGrid AssignFeaturesToGrid(const Frame& F, int cols, int rows, int device = 
     return g;
 }
 
+// UndistortKeyPoints() :409-439 and AssignFeaturesToGrid() :235-250 of the Frame constructors in ONE pass over the device
+// (orbf_build_frame: one upload of mvKeys, two kernels, one download).  `bounds` is the camera's image bounds -- the reference
+// computes them once (mbInitialComputations, :96-110): keep the FrameGrid::bounds of the first frame (AssignFeaturesToGrid above)
+// and pass them to every later frame.
+template <class Frame>
+FrameGrid BuildFrame(Frame& F, const float bounds[4], int device = 0)
+{
+    static_assert(sizeof(F.mvKeys[0]) == sizeof(orb_keypoint_t), "cv::KeyPoint layout");
+    FrameGrid g;
+    for(int i = 0; i < 4; i++) g.bounds[i] = bounds[i];
+    F.mvKeysUn.resize(F.mvKeys.size());
+    g.cell_idx.resize(F.mvKeys.size() ? F.mvKeys.size() : 1);
+    const float K[4] = {F.fx, F.fy, F.cx, F.cy};
+    int n = 0;
+    check(orbf_build_frame(F.mvKeys.empty() ? 0 : reinterpret_cast<const orb_keypoint_t*>(&F.mvKeys[0]), (int)F.mvKeys.size(), K,
+                           F.mDistCoef.template ptr<float>(0), F.mDistCoef.rows, g.bounds,
+                           F.mvKeysUn.empty() ? 0 : reinterpret_cast<orb_keypoint_t*>(&F.mvKeysUn[0]), &g.cell_ptr[0], &g.cell_idx[0], &n, device),
+          "orbf_build_frame");
+    return g;
+}
+
 // int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th)  :45-130
 template <class Frame, class MapPoint>
 int SearchByProjection(Frame& F, const FrameGrid& grid, const std::vector<MapPoint*>& vpMapPoints, float th, float nnratio,

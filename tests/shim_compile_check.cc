@@ -47,6 +47,8 @@ int shim_instantiate(KeyFrame* a, KeyFrame* b, Frame& f) {
     orbaccel::UndistortKeyPoints(f);
     orbaccel::FrameGrid grid = orbaccel::AssignFeaturesToGrid(f, 640, 480);
     n += orbaccel::SearchByProjection(f, grid, out, 1.0f, 0.8f);
+    orbaccel::FrameGrid grid2 = orbaccel::BuildFrame(f, grid.bounds);
+    n += (int)grid2.cell_idx.size();
     std::vector<orbm_proj_point_t> pts(out.size());
     n += orbaccel::SearchByProjectionLastFrame(f, grid, pts, out, 15.0f, 0, true);
     orbaccel::ComputeBoW(f, (orbv_handle_t)0);
