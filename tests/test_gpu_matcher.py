@@ -137,6 +137,23 @@ def test_stereo_matches(orb, oracle, synth, seed):
     assert n0 == 0 and (ur0 == -1).all()
 
 
+@pytest.mark.parametrize("w,h,nfeat,max_disp_px", [(752, 480, 7000, 400.0), (800, 1300, 5000, 30.0)])
+def test_stereo_matches_many_keypoints(orb, oracle, synth, w, h, nfeat, max_disp_px):
+    """More right key points than one staging chunk of the stereo kernel holds (2048), row bands that hold more candidates than its
+    per-warp list (64: a wide disparity range keeps them all), and an image taller than 1024 rows (row bins of more than 8 rows)."""
+    left, right = synth.stereo_pair(3, w, h)
+    el = orb.ORBextractor(nfeat, 1.2, 8, 20, 7); er = orb.ORBextractor(nfeat, 1.2, 8, 20, 7)
+    kl, dl = el(left); kr, dr = er(right)
+    ol = oracle.OracleExtractor(nfeat, trig_mode=1); orr = oracle.OracleExtractor(nfeat, trig_mode=1)
+    okl, odl = ol.extract(left); okr, odr = orr.extract(right)
+    assert kl.tobytes() == okl.tobytes() and kr.tobytes() == okr.tobytes() and len(kr) > 2048
+    mbf = 40.0; mb = mbf / max_disp_px      # maxD = mbf / mb = max_disp_px
+    ur, dep, n = orb.compute_stereo_matches(el, er, kl, dl, kr, dr, mbf, mb)
+    our, odep, on = oracle.stereo_matches(okl, odl, okr, odr, ol, orr, mbf, mb)
+    assert n == on and n > 100, (n, on)
+    assert np.array_equal(ur, our) and np.array_equal(dep, odep)
+
+
 def test_knn2_with_device_ratio_test(orb, oracle, synth):
     """2-NN + the reference's acceptance test (ORBmatcher.cc:228-230 / :598-600) on the device in one call chain, and the test
     alone on device-resident records: both equal the host formula on the oracle's records."""
