@@ -316,6 +316,7 @@ __device__ __forceinline__ void window_point_round(int i, const ProjWindow& w, c
 // range, feature index, key point, descriptor -- per candidate: 42 us for the bench scene).  That is possible because the
 // reference's best / second slots end up holding the two smallest (distance, walk position) keys of the walk -- the first
 // strict minimum, and the earliest minimum among the rest -- so the candidates may be visited in any order.
+constexpr int kWinCache = 16;      // candidates per point kept for the later rounds (8 bytes each)
 struct Cand2 { unsigned k1, k2; int p1, p2; };      // two smallest keys (distance << 20 | position) and their (index | octave << 16)
 __device__ __forceinline__ void cand2_insert(Cand2& c, unsigned k, int p) {
     if (k < c.k1) { c.k2 = c.k1; c.p2 = c.p1; c.k1 = k; c.p1 = p; }
@@ -328,12 +329,15 @@ __global__ void __launch_bounds__(256) window_first_round_kernel(const orb_keypo
                                                                  const ProjWindow* __restrict__ wins, const uint32_t* __restrict__ desc_p, int n_p,
                                                                  float nnratio, int threshold, int* __restrict__ claim_g,
                                                                  int* __restrict__ out_point_feature, uint8_t* __restrict__ resolved,
-                                                                 int2* __restrict__ tentative) {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+                                                                 int2* __restrict__ tentative, int2* __restrict__ cache, int* __restrict__ cache_n) {
+    __shared__ int s_n[8];
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (i >= n_p) return;
+    if (lane == 0) s_n[wib] = 0;
+    __syncwarp();
     const ProjWindow w = wins[i];
     if (lane == 0) out_point_feature[i] = -1;
-    if (!(w.flags & kWinValid)) { if (lane == 0) resolved[i] = 1; return; }
+    if (!(w.flags & kWinValid)) { if (lane == 0) { resolved[i] = 1; cache_n[i] = 0; } return; }
     Cand2 best = {0xffffffffu, 0xffffffffu, -1, -1};
     const AreaWindow aw = area_window(g, w.x, w.y, w.r);
     if (!aw.empty) {
@@ -369,7 +373,13 @@ __global__ void __launch_bounds__(256) window_first_round_kernel(const orb_keypo
                 }
                 const int dist = hamming32(dp, desc_f + (size_t)idx * 8);
                 if (dist <= threshold) atomicMin(&claim_g[idx], i);
-                cand2_insert(best, ((unsigned)dist << 20) | (unsigned)(pos0 + j), idx | (octave << 16));
+                const unsigned key = ((unsigned)dist << 20) | (unsigned)(pos0 + j);
+                const int payload = idx | (octave << 16);
+                cand2_insert(best, key, payload);
+                // the later rounds (window_search_kernel) re-evaluate this point from the cached candidates: the static tests
+                // (window, level, occupied, stereo) and the distance are done; only "who has taken it since" changes
+                const int slot = atomicAdd(&s_n[wib], 1);
+                if (slot < kWinCache) cache[(size_t)i * kWinCache + slot] = make_int2((int)key, payload);
             }
         }
     }
@@ -380,7 +390,9 @@ __global__ void __launch_bounds__(256) window_first_round_kernel(const orb_keypo
         cand2_insert(best, k1, p1);
         cand2_insert(best, k2, p2);
     }
+    __syncwarp();
     if (lane) return;
+    cache_n[i] = s_n[wib];          // more than kWinCache: the later rounds walk the window again
     const int bestDist = best.p1 >= 0 ? (int)(best.k1 >> 20) : 256, bestDist2 = best.p2 >= 0 ? (int)(best.k2 >> 20) : 256;
     if (bestDist > threshold) { resolved[i] = 1; return; }
     resolved[i] = 0;
@@ -397,6 +409,7 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
                                                              float nnratio, int threshold, int* __restrict__ out_feature_point,
                                                              int* __restrict__ out_point_feature, uint8_t* __restrict__ resolved,
                                                              int2* __restrict__ tentative, const int* __restrict__ first_round_claims,
+                                                             const int2* __restrict__ cache, const int* __restrict__ cache_n,
                                                              int* __restrict__ taker_g, int* __restrict__ out_nmatches) {
     extern __shared__ int s_dyn[];
     int* s_claim = s_dyn;                                             // [n_f]
@@ -439,6 +452,25 @@ __global__ void __launch_bounds__(1024) window_search_kernel(const orb_keypoint_
             __syncthreads();
             for (int i = tid; i < n_p; i += 1024) {
                 if (resolved[i]) continue;
+                const int nc = first_round_claims ? cache_n[i] : kWinCache + 1;
+                if (nc <= kWinCache) {
+                    // from the candidates the first round cached: no window walk, no descriptor loads
+                    Cand2 best = {0xffffffffu, 0xffffffffu, -1, -1};
+                    const int2* c = cache + (size_t)i * kWinCache;
+                    for (int k = 0; k < nc; k++) {
+                        const int2 e = c[k];
+                        const int idx = e.y & 0xffff;
+                        if (s_taker[idx] < i) continue;
+                        if ((int)((unsigned)e.x >> 20) <= threshold) atomicMin(&s_claim[idx], i);
+                        cand2_insert(best, (unsigned)e.x, e.y);
+                    }
+                    const int bestDist = best.p1 >= 0 ? (int)(best.k1 >> 20) : 256, bestDist2 = best.p2 >= 0 ? (int)(best.k2 >> 20) : 256;
+                    if (bestDist > threshold) { resolved[i] = 1; continue; }
+                    const int bestLevel = best.p1 >> 16, bestLevel2 = best.p2 >= 0 ? best.p2 >> 16 : -1;
+                    const bool accept = !(RATIO && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2));
+                    tentative[i] = make_int2((best.p1 & 0xffff) | (accept ? (1 << 30) : 0), RATIO && best.p2 >= 0 ? (best.p2 & 0xffff) : -1);
+                    continue;
+                }
                 auto blocked_for_me = [&](int idx) { return s_taker[idx] < i; };
                 if (STAGED) window_point_round<RATIO>(i, wins[i], s_kp, cell_ptr, cell_idx, g, blocked_for_me, u_right, desc_f, desc_p, threshold, nnratio, s_claim, resolved, tentative);
                 else window_point_round<RATIO>(i, wins[i], kps_g, cell_ptr, cell_idx, g, blocked_for_me, u_right, desc_f, desc_p, threshold, nnratio, s_claim, resolved, tentative);
@@ -576,7 +608,7 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     const int n_p = (int)wins.size();
     MatchCtx& cx = match_ctx();
     const size_t kb = (size_t)n_f * sizeof(orb_keypoint_t), pb = (size_t)(kGridCells + 1) * 4;
-    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4 + 4 + 4) + pb + (size_t)n_p * (sizeof(ProjWindow) + 32 + 4 + 1 + 8) + 4 + 20 * 256;
+    const size_t need = kb + (size_t)n_f * (32 + 4 + 1 + 4 + 4 + 4 + 4) + pb + (size_t)n_p * (sizeof(ProjWindow) + 32 + 4 + 1 + 8 + kWinCache * 8 + 4) + 4 + 32 * 256;
     if (!cx.begin(device, need, need)) return ORB_ERR_CUDA;
     std::vector<float> no_stereo;
     if (!u_right) { no_stereo.assign(n_f, -1.0f); u_right = no_stereo.data(); }
@@ -594,7 +626,9 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     int2* d_tent = (int2*)cx.dalloc((size_t)n_p * sizeof(int2));
     int* d_claim = (int*)cx.dalloc((size_t)n_f * 4);
     int* d_taker = (int*)cx.dalloc((size_t)n_f * 4);
-    if (!d_taker || !d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm || !d_tent || !d_claim) return ORB_ERR_CUDA;
+    int2* d_cache = (int2*)cx.dalloc((size_t)n_p * kWinCache * sizeof(int2));
+    int* d_cache_n = (int*)cx.dalloc((size_t)n_p * 4);
+    if (!d_cache || !d_cache_n || !d_taker || !d_k || !d_df || !d_ur || !d_occ || !d_cp || !d_ci || !d_w || !d_dp || !d_fp || !d_pf || !d_res || !d_nm || !d_tent || !d_claim) return ORB_ERR_CUDA;
     const bool staged = n_f <= kStagedMaxFeatures;
     static DeviceOnce once_configured;
     if (!once_configured.run([&] {
@@ -611,11 +645,11 @@ static int run_window_search(bool ratio, const orb_keypoint_t* kps_un, const uin
     const int* d_first = nullptr;
     if (first_on_grid && n_p >= 1024 && n_f > 0) {
         ORB_CUDA_TRY(cudaMemsetAsync(d_claim, 0x7f, (size_t)n_f * 4, cx.s()));      // 0x7f7f7f7f: above every point index
-        if (ratio) window_first_round_kernel<true><<<(n_p + 7) / 8, 256, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
-        else window_first_round_kernel<false><<<(n_p + 7) / 8, 256, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent);
+        if (ratio) window_first_round_kernel<true><<<(n_p + 7) / 8, 256, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent, d_cache, d_cache_n);
+        else window_first_round_kernel<false><<<(n_p + 7) / 8, 256, 0, cx.s()>>>(d_k, d_df, d_ur, d_occ, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_claim, d_pf, d_res, d_tent, d_cache, d_cache_n);
         d_first = d_claim;
     }
-#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.s()>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_tent, d_first, d_taker, d_nm)
+#define ORB_LAUNCH_WS(R, S) window_search_kernel<R, S><<<1, 1024, smem, cx.s()>>>(d_k, d_df, d_ur, d_occ, n_f, d_cp, d_ci, g, d_w, d_dp, n_p, nnratio, threshold, d_fp, d_pf, d_res, d_tent, d_first, d_cache, d_cache_n, d_taker, d_nm)
     if (ratio) { if (staged) ORB_LAUNCH_WS(true, true); else ORB_LAUNCH_WS(true, false); }
     else { if (staged) ORB_LAUNCH_WS(false, true); else ORB_LAUNCH_WS(false, false); }
 #undef ORB_LAUNCH_WS
