@@ -87,6 +87,13 @@ def _run(flavour, sc, obs):
         for i in range(0, len(kps2), 9):
             w.frame_set_mappoint(c, i, mps[i % len(mps)])
         R["local", th] = w.search_by_projection_local(c, mps + only1, th, 0.8)
+    # the same search with windows that span a large part of the frame and a strict ratio: hundreds of points compete for each
+    # feature, the outcome of a point hangs on which features the points before it took (the order-exact rounds of the CUDA path)
+    for th, ratio in ((15.0, 0.6), (15.0, 0.9)):
+        c = fresh(2)
+        for i in range(0, len(kps2), 9):
+            w.frame_set_mappoint(c, i, mps[i % len(mps)])
+        R["local_wide", th, ratio] = w.search_by_projection_local(c, (mps + only1) * 2, th, ratio)
     # TrackWithMotionModel: last = frame 1 carrying its key frame's points (some flagged outliers)
     last = fresh(1)
     kf1_mps = w.keyframe_mappoints(k1)
